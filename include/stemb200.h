@@ -1,0 +1,156 @@
+/*
+ * stemb200 — C ABI of the B200-native STEM P-frame hot path (libstemb200.so).
+ *
+ * The reference (mmSir/SpatioTemporalEntropyModel, a CompressAI 1.1.1 fork) has no FFI layer on this path:
+ * its boundary is the Python nn.Module API, whose arithmetic is ATen library calls. Each entry point below
+ * therefore cites the reference *call site* (file:line under /root/reference) whose arithmetic it replaces.
+ * The Python package `spatiotemporalentropymodel_b200` binds these with ctypes and mirrors the module API.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; device pointers unless the name says `host`;
+ *   - every function returns 0 on success or a negative STEMB200_E_* code (never throws, never allocates
+ *     device memory; outputs and workspaces are caller-allocated);
+ *   - `stream` is a cudaStream_t passed as void*; functions are stateless and thread-safe per stream;
+ *   - activations between kernels are NHWC ("pixels x channels"), element type given by STEMB200_DT_*;
+ *     tensors crossing the reference API are NCHW fp32 and are converted by the nchw/nhwc entry points.
+ */
+#ifndef STEMB200_H_
+#define STEMB200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define STEMB200_OK 0
+#define STEMB200_E_INVALID -1   /* bad argument / unsupported geometry */
+#define STEMB200_E_CUDA -2      /* a CUDA runtime / driver call failed (see stemb200_last_error) */
+#define STEMB200_E_NODEVICE -3  /* no sm_100 device */
+
+#define STEMB200_DT_F16 0 /* IEEE half operands, fp32 accumulate (tcgen05 kind::f16) */
+#define STEMB200_DT_F32 1 /* fp32 storage (epilogue outputs that feed quantisation) */
+
+/* epilogue selectors for stemb200_conv2d_fwd */
+#define STEMB200_EPI_LINEAR 0 /* out = acc + bias, then LeakyReLU(slope) (slope = 1 -> identity) */
+#define STEMB200_EPI_GDN 1    /* out = aux * rsqrt(bias + sq_scale_inv * acc)   (GDN,  gdn.py:52-67) */
+#define STEMB200_EPI_IGDN 2   /* out = aux * sqrt (bias + sq_scale_inv * acc)   (IGDN, gdn.py:60-61) */
+
+const char* stemb200_version(void);
+const char* stemb200_last_error(void);
+/* number of kernels this library has launched since process start (bench.py: gpu_launches) */
+uint64_t stemb200_launch_count(void);
+
+/* ---------------------------------------------------------------------------------------------------
+ * Dense contractions: nn.Conv2d / nn.ConvTranspose2d / MaskedConv2d / GDN's gamma conv as implicit GEMM
+ * on tcgen05 (TMEM accumulators, TMA-fed). Replaces F.conv2d / F.conv_transpose2d at
+ *   compressai/models/utils.py:112-130 (conv/deconv factories, k5 s2),
+ *   compressai/models/spatiotemporalpriors.py:523-554 (TPM, HE, HD, context_prediction, EPM),
+ *   compressai/layers/layers.py:44-47 (MaskedConv2d), compressai/layers/gdn.py:58 (gamma 1x1 conv).
+ * ------------------------------------------------------------------------------------------------- */
+typedef struct stemb200_conv_desc {
+  int32_t batch;        /* N */
+  int32_t h_in, w_in;   /* input spatial size (all sources share it) */
+  int32_t n_src;        /* 1..3 inputs concatenated along channels (torch.cat(..., 1) folded into K) */
+  int32_t c_in[3];      /* channels per source, each a multiple of 64 */
+  int32_t c_out;        /* output channels (multiple of 16) */
+  int32_t kh, kw;       /* kernel size (1, 3 or 5; square padding k/2) */
+  int32_t stride;       /* 1 or 2 */
+  int32_t transposed;   /* 1: ConvTranspose2d(k, stride 2, padding k/2, output_padding 1) */
+  uint32_t tap_mask;    /* bit (r*kw+s) set = tap used; 0 = all taps (mask 'A' 5x5 = 0x00000FFF) */
+  int32_t epilogue;     /* STEMB200_EPI_* */
+  float lrelu_slope;    /* EPI_LINEAR: negative slope, 1.0f = no activation */
+  int32_t out_dtype;    /* STEMB200_DT_F16 or STEMB200_DT_F32 (NHWC) */
+  int32_t write_sq;     /* 1: also write out_sq = (sq_scale * out)^2 as fp16 (input of the GDN contraction) */
+  float sq_scale;       /* prescale before squaring (keeps x^2 inside fp16 range); epilogue GDN multiplies
+                           acc by 1/sq_scale^2 */
+  int32_t tile_h, tile_w; /* output patch per 128-row MMA tile, tile_h*tile_w <= 128; 0 = choose */
+  int32_t direct_store; /* 1: epilogue stores straight from registers (debug / c_out < 32) */
+} stemb200_conv_desc;
+
+/* K extent of the packed weight matrix [c_out][K] for this geometry */
+int64_t stemb200_conv2d_packed_k(const stemb200_conv_desc* d);
+/* Repack a PyTorch weight (Conv2d: [c_out][c_in][kh][kw]; ConvTranspose2d: [c_in][c_out][kh][kw]), fp32 on
+ * device, into the K-major fp16 matrix the kernel's TMA descriptor expects. Masked taps are dropped. */
+int stemb200_conv2d_pack_weight(const stemb200_conv_desc* d, const float* weight_f32, void* packed_f16,
+                                void* stream);
+/* in[s]: NHWC fp16 [batch][h_in][w_in][c_in[s]]; out: NHWC [batch][h_out][w_out][c_out];
+ * bias: fp32 [c_out] (EPI_GDN/IGDN: beta); aux: NHWC fp16 like out (EPI_GDN/IGDN multiplicand) or NULL;
+ * out_sq: NHWC fp16 like out or NULL. */
+int stemb200_conv2d_fwd(const stemb200_conv_desc* d, const void* const* in, const void* packed_weight,
+                        const float* bias, const void* aux, void* out, void* out_sq, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * Layout / staging kernels at the API boundary
+ * ------------------------------------------------------------------------------------------------- */
+/* NCHW fp32 -> NHWC fp16 (optionally rounding to nearest-even integer first: y_hat = round(y),
+ * entropy_models.py:141) */
+int stemb200_nchw_f32_to_nhwc_f16(const float* in, void* out, int32_t n, int32_t c, int32_t h, int32_t w,
+                                  int32_t round_first, void* stream);
+int stemb200_nhwc_f16_to_nchw_f32(const void* in, float* out, int32_t n, int32_t c, int32_t h, int32_t w,
+                                  void* stream);
+int stemb200_nhwc_f32_to_nchw_f32(const float* in, float* out, int32_t n, int32_t c, int32_t h, int32_t w,
+                                  void* stream);
+/* First analysis conv (3 -> N, k5 s2 p2, priors.py:422) operand staging: im2col of the NCHW fp32 frame into
+ * [n*h_out*w_out][128] fp16 rows (75 real taps*channels, zero padded), with the frame embedded at
+ * (pad_top, pad_left) inside a zero canvas of h_pad x w_pad (evalSTEM.py:96-109 pads to a multiple of 64). */
+int stemb200_im2col_k5s2_c3(const float* x_nchw, void* out_rows, int32_t n, int32_t h, int32_t w,
+                            int32_t h_pad, int32_t w_pad, int32_t pad_top, int32_t pad_left, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * Entropy-model elementwise kernels
+ * ------------------------------------------------------------------------------------------------- */
+/* P-frame latent staging (spatiotemporalpriors.py:570, :852-856): y NHWC fp32 ->
+ *   y_f16  = fp16(y)                      (HE input, first half of the cat)
+ *   yq_f16 = fp16(round(y - sub)) where sub = residual ? cond : 0   (context_prediction input)
+ * cond may be NULL when residual == 0. */
+int stemb200_latent_stage(const float* y_nhwc, const void* cond_f16, void* y_f16, void* yq_f16,
+                          int64_t numel, int32_t residual, void* stream);
+
+/* GaussianConditional forward + build_indexes + symbols + bit count in one pass
+ * (entropy_models.py:588-604, :122-150, :570-586; bound_ops.py:50-53; evalSTEM.py:133-136).
+ *   inputs : y, params NHWC fp32; params = EPM output [pixels][2*C], scales = ch [0,C), means = ch [C,2C)
+ *            (chunk(2,1), spatiotemporalpriors.py:577). y has C channels.
+ *   outputs (any may be NULL): y_hat, lik NCHW fp32; idx, sym NCHW int32;
+ *            bits[frame] (double) += sum(-log2(lik)) over the frame.
+ *   scale_table: fp32 [n_scales] on device (may be NULL when idx == NULL).
+ * y_hat = round(y - mu) + mu; lik evaluated at |y_hat - mu| with sigma = max(sigma, scale_bound);
+ * lik floored at lik_bound; idx = (n_scales-1) - #{k < n_scales-1 : sigma <= table[k]}. */
+int stemb200_gaussian_conditional_fwd(const float* y_nhwc, const float* params_nhwc, int32_t n, int32_t c,
+                                      int32_t h, int32_t w, const float* scale_table, int32_t n_scales,
+                                      float scale_bound, float lik_bound, float* y_hat_nchw,
+                                      float* lik_nchw, int32_t* idx_nchw, int32_t* sym_nchw, double* bits,
+                                      void* stream);
+/* Same arithmetic on flat arrays (no layout change); the isolated parity test of a9 runs through this. */
+int stemb200_gaussian_conditional_flat(const float* y, const float* scales, const float* means,
+                                       int64_t numel, const float* scale_table, int32_t n_scales,
+                                       float scale_bound, float lik_bound, float* y_hat, float* lik,
+                                       int32_t* idx, int32_t* sym, double* bits, void* stream);
+
+/* EntropyBottleneck forward, eval mode (entropy_models.py:424-452, :388-422): z NHWC fp32 [n][h][w][c];
+ * params: fp32 [c][59] = softplus(M0)(3) b0(3) tanh(f0)(3) | softplus(M1)(9) b1(3) tanh(f1)(3) | M2.. | M3.. |
+ * softplus(M4)(3) b4(1) | median(1)  (folded once per load_state_dict).
+ * Outputs: z_hat NHWC fp16 (HD input), z_hat / lik NCHW fp32 (API), bits[frame] += sum(-log2 lik). */
+int stemb200_entropy_bottleneck_fwd(const float* z_nhwc, const float* params, int32_t n, int32_t c,
+                                    int32_t h, int32_t w, float lik_bound, void* z_hat_nhwc_f16,
+                                    float* z_hat_nchw, float* lik_nchw, double* bits, void* stream);
+
+/* Last synthesis step (priors.py:397-402 clamp; evalSTEM.py:29-31,127-129 crop + MSE):
+ * in: NHWC fp32 [n][h2][w2][16], channel (p*2+q)*3+ch holds x_hat[ch][2*i+p][2*j+q] (merged-phase deconv);
+ * out: x_hat NCHW fp32 [n][3][2*h2][2*w2] clamped to [0,1]; when x_ref != NULL (unpadded NCHW fp32
+ * [n][3][h_ref][w_ref], embedded at pad_top/pad_left) sq_err[frame] (double) += sum (x_ref - x_hat)^2. */
+int stemb200_synthesis_tail(const float* in_nhwc16, float* x_hat_nchw, int32_t n, int32_t h2, int32_t w2,
+                            const float* x_ref, int32_t h_ref, int32_t w_ref, int32_t pad_top,
+                            int32_t pad_left, double* sq_err, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * Host-side helper that the reference implements in C++ (compressai/cpp_exts/ops/ops.cpp:24-81)
+ * ------------------------------------------------------------------------------------------------- */
+/* cdf_out must hold pmf_len + 1 entries. */
+int stemb200_pmf_to_quantized_cdf_host(const float* pmf, int32_t pmf_len, int32_t precision,
+                                       int32_t* cdf_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* STEMB200_H_ */

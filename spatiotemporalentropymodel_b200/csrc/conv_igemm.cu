@@ -1,0 +1,777 @@
+// Implicit-GEMM convolution / transposed convolution on tcgen05 (sm_100a).
+//
+//   D[pixel, c_out] = sum_{tap, c_in} A[pixel + tap offset, c_in] * W[c_out, tap, c_in]
+//
+// * A tiles (128 output pixels x 64 input channels, fp16) are fetched by TMA straight from the NHWC activation
+//   tensor: a 4-D box {64 ch, tile_w, tile_h, 1} at (c0, w0+dw, h0+dh, n). Out-of-bounds box elements are
+//   zero-filled by the TMA unit, which implements the convolution's zero padding for free.
+// * stride-2 convolutions read four "phase" views (even/odd rows x even/odd columns) of the input, each a
+//   strided tensor map, so every tap is again a unit-stride box.
+// * transposed convolutions (k, s2, p=k/2, op=1) are four independent sub-problems, one per output phase
+//   (p, q): a stride-1 conv with the taps kh == p+pad (mod 2), written through a strided output tensor map.
+// * torch.cat(..., 1) inputs are K-segments: the K loop walks (tap, source, 64-channel chunk) triples listed
+//   in a table carried in the kernel parameters.
+// * accumulators live in TMEM (double buffered, 2 x BLOCK_N columns), MMAs are issued by one thread,
+//   the epilogue (4 warps) overlaps the next tile's main loop; persistent CTAs, one per SM.
+//
+// Reference call sites this replaces: compressai/models/utils.py:112-130, spatiotemporalpriors.py:523-554,
+// layers/layers.py:44-47, layers/gdn.py:52-67 (F.conv2d(x**2, gamma, beta) + rsqrt/sqrt + multiply).
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <vector>
+
+#include "../../include/stemb200.h"
+#include "internal.h"
+#include "ptx.cuh"
+
+namespace stem {
+
+constexpr int kMaxKSteps = 256;
+constexpr int kKChunk = 64;         // fp16 elements per 128-byte swizzle row
+constexpr int kAStageBytes = 128 * 128;
+constexpr int kOutStageBytes = 128 * 128;
+constexpr int kNumThreads = 256;
+constexpr int kSmemLimit = 232448;  // 227 KB
+
+struct ConvKernelParams {
+  alignas(64) CUtensorMap a_map[4];
+  alignas(64) CUtensorMap b_map;
+  alignas(64) CUtensorMap out_map[4];
+  alignas(64) CUtensorMap sq_map[4];
+  uint32_t ksteps[kMaxKSteps];  // [1:0] map | [5:2] dh+8 | [9:6] dw+8 | [31:10] channel offset
+  int sub_kbeg[4], sub_kend[4];
+  int sub_p[4], sub_q[4];
+  int n_sub;
+  int batch, h_out, w_out;  // output grid of one sub-problem
+  int tile_h, tile_w, tiles_h, tiles_w;
+  int n_tiles_n, total_tiles;
+  int c_out;
+  int epilogue;
+  float slope, sq_scale, sq_inv;
+  int out_f32, write_sq, direct;
+  int os, full_h, full_w;  // output phase stride and full output size (direct store / aux addressing)
+  const float* bias;
+  const __half* aux;
+  void* out;
+};
+
+template <int BLOCK_N>
+struct ConvCfg {
+  static constexpr int kBStageBytes = BLOCK_N * 128;
+  static constexpr int kStageBytes = kAStageBytes + kBStageBytes;
+  static constexpr bool kSqAllowed = BLOCK_N <= 192;
+  static constexpr int kNumOutBufs = kSqAllowed ? 4 : 2;
+  static constexpr int kBarrierBytes = 256;
+  static constexpr int kFree = kSmemLimit - 1024 - kNumOutBufs * kOutStageBytes - kBarrierBytes;
+  static constexpr int kStagesRaw = kFree / kStageBytes;
+  static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
+  static constexpr int kSmemBytes =
+      1024 + kStages * kStageBytes + kNumOutBufs * kOutStageBytes + kBarrierBytes;
+  static constexpr int kTmemCols = (2 * BLOCK_N <= 32)    ? 32
+                                   : (2 * BLOCK_N <= 64)  ? 64
+                                   : (2 * BLOCK_N <= 128) ? 128
+                                   : (2 * BLOCK_N <= 256) ? 256
+                                                          : 512;
+  static_assert(kStages >= 3, "pipeline too shallow");
+  static_assert(2 * BLOCK_N <= 512, "TMEM overflow");
+};
+
+struct TileCoord {
+  int sub, n_img, h0, w0, n0;
+};
+
+__device__ __forceinline__ TileCoord decode_tile(const ConvKernelParams& p, int tile, int block_n) {
+  TileCoord t;
+  int nt = tile % p.n_tiles_n;
+  int m = tile / p.n_tiles_n;
+  int twi = m % p.tiles_w;
+  m /= p.tiles_w;
+  int thi = m % p.tiles_h;
+  m /= p.tiles_h;
+  t.n_img = m % p.batch;
+  t.sub = m / p.batch;
+  t.h0 = thi * p.tile_h;
+  t.w0 = twi * p.tile_w;
+  t.n0 = nt * block_n;
+  return t;
+}
+
+__device__ __forceinline__ uint32_t pack_half2(float a, float b) {
+  __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+template <int BLOCK_N>
+__global__ void __launch_bounds__(kNumThreads, 1)
+conv_igemm_kernel(const __grid_constant__ ConvKernelParams p) {
+  using Cfg = ConvCfg<BLOCK_N>;
+  constexpr int kStages = Cfg::kStages;
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t stage_base = smem_base;
+  const uint32_t out_base = smem_base + kStages * Cfg::kStageBytes;
+  const uint32_t bar_base = out_base + Cfg::kNumOutBufs * kOutStageBytes;
+  // barriers: full[kStages], empty[kStages], tmem_full[2], tmem_empty[2], then the TMEM base address slot
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (kStages + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * kStages + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * kStages + 2 + a); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * kStages + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    for (int i = 0; i < 4; ++i) tma_prefetch_desc(&p.a_map[i]);
+    tma_prefetch_desc(&p.b_map);
+    if (!p.direct) {
+      for (int i = 0; i < p.n_sub; ++i) tma_prefetch_desc(&p.out_map[i]);
+      if (p.write_sq)
+        for (int i = 0; i < p.n_sub; ++i) tma_prefetch_desc(&p.sq_map[i]);
+    }
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull_bar(a), 1);
+      mbar_init(tempty_bar(a), 4);  // one arrival per epilogue warp
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, Cfg::kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  const uint32_t a_tx_bytes = static_cast<uint32_t>(p.tile_h * p.tile_w) * 128u;
+
+  if (warp == 0 && lane == 0) {
+    // ===================== TMA producer =====================
+    int s = 0;
+    uint32_t ph = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      const TileCoord t = decode_tile(p, tile, BLOCK_N);
+      const int kbeg = p.sub_kbeg[t.sub], kend = p.sub_kend[t.sub];
+      for (int k = kbeg; k < kend; ++k) {
+        mbar_wait(empty_bar(s), ph ^ 1u);
+        const uint32_t e = p.ksteps[k];
+        const int map = e & 3;
+        const int dh = static_cast<int>((e >> 2) & 15u) - 8;
+        const int dw = static_cast<int>((e >> 6) & 15u) - 8;
+        const int c0 = static_cast<int>(e >> 10);
+        const uint32_t a_dst = stage_base + s * Cfg::kStageBytes;
+        const uint32_t b_dst = a_dst + kAStageBytes;
+        mbar_arrive_expect_tx(full_bar(s), a_tx_bytes + Cfg::kBStageBytes);
+        tma_load_4d(a_dst, &p.a_map[map], full_bar(s), c0, t.w0 + dw, t.h0 + dh, t.n_img);
+        tma_load_2d(b_dst, &p.b_map, full_bar(s), k * kKChunk, t.n0);
+        if (++s == kStages) {
+          s = 0;
+          ph ^= 1u;
+        }
+      }
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ===================== MMA issuer =====================
+    constexpr uint32_t idesc = umma_idesc(/*F16*/ 0u, 128u, BLOCK_N);
+    int s = 0;
+    uint32_t ph = 0;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+      const TileCoord t = decode_tile(p, tile, BLOCK_N);
+      const int kbeg = p.sub_kbeg[t.sub], kend = p.sub_kend[t.sub];
+      const int acc = it & 1;
+      const uint32_t accph = (it >> 1) & 1;
+      mbar_wait(tempty_bar(acc), accph ^ 1u);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+      for (int k = kbeg; k < kend; ++k) {
+        mbar_wait(full_bar(s), ph);
+        tc_fence_after();
+        const uint32_t a_addr = stage_base + s * Cfg::kStageBytes;
+        const uint64_t adesc = umma_desc_sw128(a_addr);
+        const uint64_t bdesc = umma_desc_sw128(a_addr + kAStageBytes);
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+          // +32 bytes (one K=16 slice) inside the 128-byte swizzle row => +2 in the >>4 address field
+          mma_f16_ss(d_tmem, adesc + 2u * kk, bdesc + 2u * kk, idesc, (k > kbeg || kk > 0) ? 1u : 0u);
+        }
+        mma_commit(empty_bar(s));
+        if (++s == kStages) {
+          s = 0;
+          ph ^= 1u;
+        }
+      }
+      mma_commit(tfull_bar(acc));
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue (TMEM -> registers -> smem -> TMA store) =====================
+    const int ew = warp - 4;            // == warp % 4: TMEM lane group
+    const int etid = threadIdx.x - 128;  // 0..127 == accumulator row
+    const int row = etid;
+    const int npix = p.tile_h * p.tile_w;
+    uint32_t chunk_ctr = 0;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+      const TileCoord t = decode_tile(p, tile, BLOCK_N);
+      const int acc = it & 1;
+      const uint32_t accph = (it >> 1) & 1;
+      const int th = row / p.tile_w, tw = row - th * p.tile_w;
+      const int oh = t.h0 + th, ow = t.w0 + tw;
+      const bool inb = (row < npix) && (oh < p.h_out) && (ow < p.w_out);
+      // flat pixel index in the full-resolution output (direct store / aux)
+      const long long pix =
+          (static_cast<long long>(t.n_img) * p.full_h + (oh * p.os + p.sub_p[t.sub])) * p.full_w +
+          (ow * p.os + p.sub_q[t.sub]);
+
+      mbar_wait(tfull_bar(acc), accph);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + acc * BLOCK_N + (static_cast<uint32_t>(ew * 32) << 16);
+
+      constexpr int kCols = (BLOCK_N >= 32) ? 32 : 16;
+#pragma unroll 1
+      for (int c = 0; c < BLOCK_N; c += kCols) {
+        float v[kCols];
+        {
+          uint32_t r[kCols];
+          if constexpr (kCols == 32) {
+            tmem_ld_32x32(t_row + c, r);
+          } else {
+            tmem_ld_32x16(t_row + c, r);
+          }
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < kCols; ++i) v[i] = __uint_as_float(r[i]);
+        }
+        const int ch0 = t.n0 + c;
+        if (p.epilogue == STEMB200_EPI_LINEAR) {
+#pragma unroll
+          for (int i = 0; i < kCols; ++i) {
+            float x = v[i] + __ldg(p.bias + ch0 + i);
+            v[i] = x > 0.f ? x : x * p.slope;
+          }
+        } else {
+          // GDN / IGDN: aux * (r)sqrt(beta + acc / sq_scale^2)
+          uint4 a4[kCols / 8];
+          if (inb) {
+            const uint4* ap = reinterpret_cast<const uint4*>(p.aux + pix * p.c_out + ch0);
+#pragma unroll
+            for (int j = 0; j < kCols / 8; ++j) a4[j] = __ldg(ap + j);
+          } else {
+#pragma unroll
+            for (int j = 0; j < kCols / 8; ++j) a4[j] = make_uint4(0, 0, 0, 0);
+          }
+          const __half* ah = reinterpret_cast<const __half*>(a4);
+#pragma unroll
+          for (int i = 0; i < kCols; ++i) {
+            float nrm = fmaf(v[i], p.sq_inv, __ldg(p.bias + ch0 + i));
+            float f = (p.epilogue == STEMB200_EPI_GDN) ? rsqrtf(nrm) : sqrtf(nrm);
+            v[i] = __half2float(ah[i]) * f;
+          }
+        }
+
+        if (p.direct) {
+          if (inb) {
+            if (p.out_f32) {
+              float4* op = reinterpret_cast<float4*>(static_cast<float*>(p.out) + pix * p.c_out + ch0);
+#pragma unroll
+              for (int j = 0; j < kCols / 4; ++j)
+                op[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            } else {
+              uint4* op = reinterpret_cast<uint4*>(static_cast<__half*>(p.out) + pix * p.c_out + ch0);
+#pragma unroll
+              for (int j = 0; j < kCols / 8; ++j)
+                op[j] = make_uint4(pack_half2(v[8 * j], v[8 * j + 1]), pack_half2(v[8 * j + 2], v[8 * j + 3]),
+                                   pack_half2(v[8 * j + 4], v[8 * j + 5]),
+                                   pack_half2(v[8 * j + 6], v[8 * j + 7]));
+            }
+          }
+        } else if constexpr (kCols == 32) {
+          // ---- staged TMA store. fp32: one 128-byte row = 32 columns; fp16: 64 columns (two loads). ----
+          const bool second_half = (!p.out_f32) && ((c & 32) != 0);
+          const uint32_t buf = chunk_ctr & 1u;
+          const uint32_t obuf = out_base + buf * kOutStageBytes;
+          const uint32_t sbuf = out_base + (2u + buf) * kOutStageBytes;
+          if (!second_half) {
+            // the buffer was last used two chunks ago: its TMA store must have finished reading smem
+            if (etid == 0) tma_store_wait_read<1>();
+            named_bar_sync(1, 128);
+          }
+          const uint32_t rsw = static_cast<uint32_t>(row & 7);
+          const uint32_t rbase = obuf + static_cast<uint32_t>(row) * 128u;
+          if (p.out_f32) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const uint32_t addr = rbase + ((static_cast<uint32_t>(j) ^ rsw) << 4);
+              asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v[4 * j]),
+                           "f"(v[4 * j + 1]), "f"(v[4 * j + 2]), "f"(v[4 * j + 3])
+                           : "memory");
+            }
+          } else {
+            const uint32_t jo = second_half ? 4u : 0u;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const uint32_t addr = rbase + (((static_cast<uint32_t>(j) + jo) ^ rsw) << 4);
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr),
+                           "r"(pack_half2(v[8 * j], v[8 * j + 1])),
+                           "r"(pack_half2(v[8 * j + 2], v[8 * j + 3])),
+                           "r"(pack_half2(v[8 * j + 4], v[8 * j + 5])),
+                           "r"(pack_half2(v[8 * j + 6], v[8 * j + 7]))
+                           : "memory");
+            }
+            if (Cfg::kSqAllowed && p.write_sq) {
+              const uint32_t sbase = sbuf + static_cast<uint32_t>(row) * 128u;
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                float q[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                  // square the value the next layer will actually read (the fp16-rounded one)
+                  float xr = __half2float(__float2half_rn(v[8 * j + i])) * p.sq_scale;
+                  q[i] = xr * xr;
+                }
+                const uint32_t addr = sbase + (((static_cast<uint32_t>(j) + jo) ^ rsw) << 4);
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr),
+                             "r"(pack_half2(q[0], q[1])), "r"(pack_half2(q[2], q[3])),
+                             "r"(pack_half2(q[4], q[5])), "r"(pack_half2(q[6], q[7]))
+                             : "memory");
+              }
+            }
+          }
+          const bool chunk_done = p.out_f32 || second_half || (c + 32 >= BLOCK_N);
+          if (chunk_done) {
+            fence_proxy_async_smem();
+            named_bar_sync(1, 128);
+            if (etid == 0) {
+              const int cstart = p.out_f32 ? ch0 : (ch0 & ~63);
+              tma_store_4d(&p.out_map[t.sub], obuf, cstart, t.w0, t.h0, t.n_img);
+              if (Cfg::kSqAllowed && p.write_sq) tma_store_4d(&p.sq_map[t.sub], sbuf, cstart, t.w0, t.h0, t.n_img);
+              tma_store_commit();
+            }
+            ++chunk_ctr;
+          }
+        }
+      }
+      // all TMEM reads of this accumulator are complete -> hand it back to the MMA warp
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(acc));
+    }
+    if (etid == 0) tma_store_wait_all<0>();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, Cfg::kTmemCols);
+}
+
+// =====================================================================================================
+// weight repack: PyTorch OIHW (or IOHW for ConvTranspose2d) fp32 -> [c_out][K] fp16, K ordered like the
+// kernel's k-step table
+// =====================================================================================================
+struct PackParams {
+  uint32_t info[kMaxKSteps];  // [2:0] r | [5:3] s | [31:6] global input-channel base
+  int n_steps;
+  int c_out, c_in_total, kh, kw, transposed;
+};
+
+__global__ void pack_weight_kernel(const __grid_constant__ PackParams pp, const float* __restrict__ w,
+                                   __half* __restrict__ out) {
+  const long long K = static_cast<long long>(pp.n_steps) * kKChunk;
+  const long long total = K * pp.c_out;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int o = static_cast<int>(i / K);
+    const int k = static_cast<int>(i - static_cast<long long>(o) * K);
+    const uint32_t e = pp.info[k / kKChunk];
+    const int r = e & 7, s = (e >> 3) & 7;
+    const int ci = static_cast<int>(e >> 6) + (k % kKChunk);
+    float v = 0.f;
+    if (ci < pp.c_in_total) {
+      const long long idx = pp.transposed
+                                ? ((static_cast<long long>(ci) * pp.c_out + o) * pp.kh + r) * pp.kw + s
+                                : ((static_cast<long long>(o) * pp.c_in_total + ci) * pp.kh + r) * pp.kw + s;
+      v = w[idx];
+    }
+    out[i] = __float2half_rn(v);
+  }
+}
+
+// =====================================================================================================
+// host side: geometry -> k-step table, tensor maps, launch
+// =====================================================================================================
+namespace {
+
+struct Plan {
+  int n_maps = 0;
+  int map_src[4] = {0, 0, 0, 0};
+  int map_ph[4] = {0, 0, 0, 0}, map_pw[4] = {0, 0, 0, 0};
+  int in_stride_mul = 1;  // 2 for phase views of a stride-2 conv
+  std::vector<uint32_t> ksteps;
+  std::vector<uint32_t> pack_info;
+  int n_sub = 1;
+  int sub_kbeg[4] = {0, 0, 0, 0}, sub_kend[4] = {0, 0, 0, 0};
+  int sub_p[4] = {0, 0, 0, 0}, sub_q[4] = {0, 0, 0, 0};
+  int h_out = 0, w_out = 0, os = 1, full_h = 0, full_w = 0;
+  int c_in_total = 0;
+  int block_n = 0;
+};
+
+int pick_block_n(int c_out, bool write_sq) {
+  if (c_out % 256 == 0 && !write_sq) return 256;
+  if (c_out % 192 == 0) return 192;
+  if (c_out % 128 == 0) return 128;
+  if (c_out % 64 == 0) return 64;
+  if (c_out == 16) return 16;
+  return 0;
+}
+
+int build_plan(const stemb200_conv_desc& d, Plan& pl) {
+  if (d.batch < 1 || d.h_in < 1 || d.w_in < 1) return set_error("conv: bad shape");
+  if (d.n_src < 1 || d.n_src > 3) return set_error("conv: n_src must be 1..3");
+  if (d.kh != d.kw || (d.kh != 1 && d.kh != 3 && d.kh != 5)) return set_error("conv: kernel must be 1,3,5");
+  if (d.stride != 1 && d.stride != 2) return set_error("conv: stride must be 1 or 2");
+  if (d.transposed && d.stride != 2) return set_error("conv: transposed needs stride 2");
+  if ((d.stride == 2) && d.n_src != 1) return set_error("conv: strided conv takes one source");
+  int src_base[3] = {0, 0, 0};
+  pl.c_in_total = 0;
+  for (int s = 0; s < d.n_src; ++s) {
+    if (d.c_in[s] < kKChunk || d.c_in[s] % kKChunk) return set_error("conv: c_in must be a multiple of 64");
+    src_base[s] = pl.c_in_total;
+    pl.c_in_total += d.c_in[s];
+  }
+  pl.block_n = pick_block_n(d.c_out, d.write_sq != 0);
+  if (!pl.block_n) return set_error("conv: unsupported c_out");
+  if (d.write_sq && d.out_dtype != STEMB200_DT_F16) return set_error("conv: write_sq needs fp16 output");
+  if (d.write_sq && d.direct_store) return set_error("conv: write_sq needs the TMA store path");
+  if (pl.block_n < 32 && !d.direct_store) return set_error("conv: c_out < 32 needs direct_store");
+  if (!d.direct_store && d.out_dtype == STEMB200_DT_F16 && (d.c_out % 64)) return set_error("conv: c_out%64");
+
+  const int k = d.kh, pad = k / 2;
+  const uint32_t mask = d.tap_mask ? d.tap_mask : ((1u << (k * k)) - 1u);
+  auto tap_on = [&](int r, int s) { return (mask >> (r * k + s)) & 1u; };
+  auto push = [&](int map, int dh, int dw, int c0, int r, int s, int cbase) {
+    pl.ksteps.push_back(static_cast<uint32_t>(map) | (static_cast<uint32_t>(dh + 8) << 2) |
+                        (static_cast<uint32_t>(dw + 8) << 6) | (static_cast<uint32_t>(c0) << 10));
+    pl.pack_info.push_back(static_cast<uint32_t>(r) | (static_cast<uint32_t>(s) << 3) |
+                           (static_cast<uint32_t>(cbase) << 6));
+  };
+
+  if (!d.transposed && d.stride == 1) {
+    pl.n_maps = d.n_src;
+    for (int s = 0; s < d.n_src; ++s) pl.map_src[s] = s;
+    pl.h_out = d.h_in;
+    pl.w_out = d.w_in;
+    for (int r = 0; r < k; ++r)
+      for (int s = 0; s < k; ++s) {
+        if (!tap_on(r, s)) continue;
+        for (int src = 0; src < d.n_src; ++src)
+          for (int c0 = 0; c0 < d.c_in[src]; c0 += kKChunk) push(src, r - pad, s - pad, c0, r, s, src_base[src] + c0);
+      }
+    pl.n_sub = 1;
+    pl.sub_kbeg[0] = 0;
+    pl.sub_kend[0] = static_cast<int>(pl.ksteps.size());
+    pl.os = 1;
+    pl.full_h = pl.h_out;
+    pl.full_w = pl.w_out;
+  } else if (!d.transposed) {  // stride 2
+    pl.n_maps = 4;
+    pl.in_stride_mul = 2;
+    for (int m = 0; m < 4; ++m) {
+      pl.map_ph[m] = m >> 1;
+      pl.map_pw[m] = m & 1;
+    }
+    pl.h_out = (d.h_in + 2 * pad - k) / 2 + 1;
+    pl.w_out = (d.w_in + 2 * pad - k) / 2 + 1;
+    for (int r = 0; r < k; ++r)
+      for (int s = 0; s < k; ++s) {
+        if (!tap_on(r, s)) continue;
+        const int a = r - pad, b = s - pad;
+        const int ph = a & 1, pw = b & 1;
+        const int dh = (a - ph) / 2, dw = (b - pw) / 2;
+        for (int c0 = 0; c0 < d.c_in[0]; c0 += kKChunk) push(ph * 2 + pw, dh, dw, c0, r, s, c0);
+      }
+    pl.n_sub = 1;
+    pl.sub_kbeg[0] = 0;
+    pl.sub_kend[0] = static_cast<int>(pl.ksteps.size());
+    pl.os = 1;
+    pl.full_h = pl.h_out;
+    pl.full_w = pl.w_out;
+  } else {  // transposed, stride 2, padding k/2, output_padding 1: out = 2*in
+    pl.n_maps = 1;
+    pl.h_out = d.h_in;
+    pl.w_out = d.w_in;
+    pl.os = 2;
+    pl.full_h = 2 * d.h_in;
+    pl.full_w = 2 * d.w_in;
+    pl.n_sub = 4;
+    for (int sp = 0; sp < 4; ++sp) {
+      const int p = sp >> 1, q = sp & 1;
+      pl.sub_p[sp] = p;
+      pl.sub_q[sp] = q;
+      pl.sub_kbeg[sp] = static_cast<int>(pl.ksteps.size());
+      // oh = 2*ih - pad + r  with oh = 2*h + p  =>  ih = h + (p + pad - r)/2, needs (p + pad - r) even
+      for (int r = 0; r < k; ++r) {
+        if ((p + pad - r) & 1) continue;
+        for (int s = 0; s < k; ++s) {
+          if ((q + pad - s) & 1) continue;
+          if (!tap_on(r, s)) continue;
+          const int dh = (p + pad - r) / 2, dw = (q + pad - s) / 2;
+          for (int c0 = 0; c0 < d.c_in[0]; c0 += kKChunk) push(0, dh, dw, c0, r, s, c0);
+        }
+      }
+      pl.sub_kend[sp] = static_cast<int>(pl.ksteps.size());
+    }
+  }
+  if (pl.ksteps.empty() || pl.ksteps.size() > kMaxKSteps) return set_error("conv: K-step table overflow");
+  return 0;
+}
+
+void pick_tile(int h, int w, int& th, int& tw) {
+  double best = -1.0;
+  int bth = 1, btw = std::min(w, 128);
+  for (int a = 1; a <= 128; ++a) {
+    for (int b = 1; b <= 128 / a; ++b) {
+      if (b > 256) continue;
+      const long long tiles = static_cast<long long>((h + a - 1) / a) * ((w + b - 1) / b);
+      const double eff = static_cast<double>(h) * w / (static_cast<double>(tiles) * 128.0);
+      // tie-break towards square patches (smaller halo => better L2 reuse across taps)
+      const double score = eff - 1e-4 * (static_cast<double>(a + b) / (a * b));
+      if (score > best) {
+        best = score;
+        bth = a;
+        btw = b;
+      }
+    }
+  }
+  th = bth;
+  tw = btw;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(f);
+  });
+  return fn;
+}
+
+// NHWC view {C, W, H, N} with optional phase sub-sampling (mul) and origin (ph, pw)
+int encode_nhwc(CUtensorMap* m, const void* base, int elem_bytes, int n, int h, int w, int c, int mul, int ph,
+                int pw, int box_c, int box_w, int box_h) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return set_error("cuTensorMapEncodeTiled unavailable");
+  const int hv = (h - ph + mul - 1) / mul, wv = (w - pw + mul - 1) / mul;
+  if (hv < 1 || wv < 1) return set_error("conv: empty phase view");
+  cuuint64_t dims[4] = {static_cast<cuuint64_t>(c), static_cast<cuuint64_t>(wv), static_cast<cuuint64_t>(hv),
+                        static_cast<cuuint64_t>(n)};
+  cuuint64_t strides[3] = {static_cast<cuuint64_t>(c) * elem_bytes * mul,
+                           static_cast<cuuint64_t>(w) * c * elem_bytes * mul,
+                           static_cast<cuuint64_t>(h) * w * c * elem_bytes};
+  cuuint32_t box[4] = {static_cast<cuuint32_t>(box_c), static_cast<cuuint32_t>(box_w),
+                       static_cast<cuuint32_t>(box_h), 1u};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  const char* origin = static_cast<const char*>(base) +
+                       (static_cast<size_t>(ph) * w + pw) * static_cast<size_t>(c) * elem_bytes;
+  CUresult r = enc(m, elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4,
+                   const_cast<char*>(origin), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    char buf[160];
+    snprintf(buf, sizeof(buf), "cuTensorMapEncodeTiled(nhwc) failed: %d (c=%d w=%d h=%d n=%d box=%d,%d,%d)",
+             static_cast<int>(r), c, wv, hv, n, box_c, box_w, box_h);
+    return set_error(buf);
+  }
+  return 0;
+}
+
+int encode_weight(CUtensorMap* m, const void* base, long long K, int c_out, int block_n) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return set_error("cuTensorMapEncodeTiled unavailable");
+  cuuint64_t dims[2] = {static_cast<cuuint64_t>(K), static_cast<cuuint64_t>(c_out)};
+  cuuint64_t strides[1] = {static_cast<cuuint64_t>(K) * 2};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(kKChunk), static_cast<cuuint32_t>(block_n)};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    char buf[128];
+    snprintf(buf, sizeof(buf), "cuTensorMapEncodeTiled(weight) failed: %d", static_cast<int>(r));
+    return set_error(buf);
+  }
+  return 0;
+}
+
+template <int BLOCK_N>
+int launch_conv(const ConvKernelParams& kp, int grid, cudaStream_t stream) {
+  using Cfg = ConvCfg<BLOCK_N>;
+  static bool configured = false;  // benign race: attribute set is idempotent
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(conv_igemm_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         Cfg::kSmemBytes);
+    if (e != cudaSuccess) return set_cuda_error("cudaFuncSetAttribute(conv)", e);
+    configured = true;
+  }
+  conv_igemm_kernel<BLOCK_N><<<grid, kNumThreads, Cfg::kSmemBytes, stream>>>(kp);
+  count_launch();
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_cuda_error("conv_igemm launch", e);
+  return 0;
+}
+
+}  // namespace
+}  // namespace stem
+
+using namespace stem;
+
+extern "C" int64_t stemb200_conv2d_packed_k(const stemb200_conv_desc* d) {
+  if (!d) return STEMB200_E_INVALID;
+  Plan pl;
+  if (int rc = build_plan(*d, pl)) return rc;
+  return static_cast<int64_t>(pl.ksteps.size()) * kKChunk;
+}
+
+extern "C" int stemb200_conv2d_pack_weight(const stemb200_conv_desc* d, const float* weight_f32,
+                                           void* packed_f16, void* stream) {
+  if (!d || !weight_f32 || !packed_f16) return set_error("pack_weight: null argument");
+  Plan pl;
+  if (int rc = build_plan(*d, pl)) return rc;
+  PackParams pp;
+  memset(&pp, 0, sizeof(pp));
+  pp.n_steps = static_cast<int>(pl.pack_info.size());
+  for (int i = 0; i < pp.n_steps; ++i) pp.info[i] = pl.pack_info[i];
+  pp.c_out = d->c_out;
+  pp.c_in_total = pl.c_in_total;
+  pp.kh = d->kh;
+  pp.kw = d->kw;
+  pp.transposed = d->transposed;
+  const long long total = static_cast<long long>(pp.n_steps) * kKChunk * d->c_out;
+  const int blocks = static_cast<int>(std::min<long long>((total + 255) / 256, 148 * 16));
+  pack_weight_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      pp, weight_f32, static_cast<__half*>(packed_f16));
+  count_launch();
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_cuda_error("pack_weight launch", e);
+  return 0;
+}
+
+extern "C" int stemb200_conv2d_fwd(const stemb200_conv_desc* d, const void* const* in,
+                                   const void* packed_weight, const float* bias, const void* aux, void* out,
+                                   void* out_sq, void* stream) {
+  if (!d || !in || !packed_weight || !bias || !out) return set_error("conv2d_fwd: null argument");
+  Plan pl;
+  if (int rc = build_plan(*d, pl)) return rc;
+  if (d->epilogue != STEMB200_EPI_LINEAR && !aux) return set_error("conv2d_fwd: GDN epilogue needs aux");
+  if (d->write_sq && !out_sq) return set_error("conv2d_fwd: write_sq needs out_sq");
+  for (int s = 0; s < d->n_src; ++s)
+    if (!in[s]) return set_error("conv2d_fwd: null input");
+
+  ConvKernelParams kp;
+  memset(&kp, 0, sizeof(kp));
+  int th = d->tile_h, tw = d->tile_w;
+  if (th <= 0 || tw <= 0) pick_tile(pl.h_out, pl.w_out, th, tw);
+  if (th * tw > 128 || tw > 256 || th > 256) return set_error("conv2d_fwd: tile_h*tile_w must be <= 128");
+
+  // A maps
+  for (int m = 0; m < 4; ++m) {
+    const int mm = m < pl.n_maps ? m : 0;
+    const int src = pl.map_src[mm];
+    if (int rc = encode_nhwc(&kp.a_map[m], in[src], 2, d->batch, d->h_in, d->w_in, d->c_in[src],
+                             pl.in_stride_mul, pl.map_ph[mm], pl.map_pw[mm], kKChunk, tw, th))
+      return rc;
+  }
+  const long long K = static_cast<long long>(pl.ksteps.size()) * kKChunk;
+  if (int rc = encode_weight(&kp.b_map, packed_weight, K, d->c_out, pl.block_n)) return rc;
+  const int out_bytes = d->out_dtype == STEMB200_DT_F32 ? 4 : 2;
+  const int out_box_c = d->out_dtype == STEMB200_DT_F32 ? 32 : 64;
+  if (!d->direct_store) {
+    for (int sp = 0; sp < 4; ++sp) {
+      const int ss = sp < pl.n_sub ? sp : 0;
+      if (int rc = encode_nhwc(&kp.out_map[sp], out, out_bytes, d->batch, pl.full_h, pl.full_w, d->c_out, pl.os,
+                               pl.sub_p[ss], pl.sub_q[ss], out_box_c, tw, th))
+        return rc;
+    }
+    for (int sp = 0; sp < 4; ++sp) {
+      const int ss = sp < pl.n_sub ? sp : 0;
+      if (d->write_sq) {
+        if (int rc = encode_nhwc(&kp.sq_map[sp], out_sq, 2, d->batch, pl.full_h, pl.full_w, d->c_out, pl.os,
+                                 pl.sub_p[ss], pl.sub_q[ss], 64, tw, th))
+          return rc;
+      } else {
+        kp.sq_map[sp] = kp.out_map[sp];
+      }
+    }
+  }
+  for (size_t i = 0; i < pl.ksteps.size(); ++i) kp.ksteps[i] = pl.ksteps[i];
+  for (int i = 0; i < 4; ++i) {
+    kp.sub_kbeg[i] = pl.sub_kbeg[i];
+    kp.sub_kend[i] = pl.sub_kend[i];
+    kp.sub_p[i] = pl.sub_p[i];
+    kp.sub_q[i] = pl.sub_q[i];
+  }
+  kp.n_sub = pl.n_sub;
+  kp.batch = d->batch;
+  kp.h_out = pl.h_out;
+  kp.w_out = pl.w_out;
+  kp.tile_h = th;
+  kp.tile_w = tw;
+  kp.tiles_h = (pl.h_out + th - 1) / th;
+  kp.tiles_w = (pl.w_out + tw - 1) / tw;
+  kp.n_tiles_n = d->c_out / pl.block_n;
+  const long long total =
+      static_cast<long long>(pl.n_sub) * d->batch * kp.tiles_h * kp.tiles_w * kp.n_tiles_n;
+  if (total > 0x7fffffffLL) return set_error("conv2d_fwd: too many tiles");
+  kp.total_tiles = static_cast<int>(total);
+  kp.c_out = d->c_out;
+  kp.epilogue = d->epilogue;
+  kp.slope = d->lrelu_slope;
+  kp.sq_scale = d->sq_scale;
+  kp.sq_inv = d->sq_scale != 0.f ? 1.0f / (d->sq_scale * d->sq_scale) : 1.0f;
+  kp.out_f32 = d->out_dtype == STEMB200_DT_F32;
+  kp.write_sq = d->write_sq;
+  kp.direct = d->direct_store;
+  kp.os = pl.os;
+  kp.full_h = pl.full_h;
+  kp.full_w = pl.full_w;
+  kp.bias = bias;
+  kp.aux = static_cast<const __half*>(aux);
+  kp.out = out;
+
+  const int grid = std::min(kp.total_tiles, num_sms());
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  switch (pl.block_n) {
+    case 16: return launch_conv<16>(kp, grid, st);
+    case 64: return launch_conv<64>(kp, grid, st);
+    case 128: return launch_conv<128>(kp, grid, st);
+    case 192: return launch_conv<192>(kp, grid, st);
+    case 256: return launch_conv<256>(kp, grid, st);
+    default: return set_error("conv2d_fwd: no kernel for this c_out");
+  }
+}

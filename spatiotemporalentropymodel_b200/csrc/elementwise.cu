@@ -1,0 +1,521 @@
+// HBM-bound kernels of the STEM P-frame path: API-boundary layout changes, first-layer im2col staging,
+// GaussianConditional (quantise + erfc likelihood + scale-table index + symbols + bit count),
+// EntropyBottleneck forward, synthesis tail (pixel-unshuffle + clamp + squared error).
+// Compiled with -fmad=false so that the fp32 operation order of the reference (entropy_models.py) is kept.
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdint>
+
+#include "../../include/stemb200.h"
+#include "internal.h"
+
+namespace stem {
+
+// ---------------------------------------------------------------------------------------------------
+// reductions
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// block-wide fp32 partials -> one fp64 atomicAdd per block
+__device__ __forceinline__ void block_accumulate(float v, double* dst, float* red /*>= 32 floats smem*/) {
+  v = warp_sum(v);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) red[warp] = v;
+  __syncthreads();
+  if (warp == 0) {
+    const int nw = (blockDim.x + 31) >> 5;
+    float s = lane < nw ? red[lane] : 0.f;
+    s = warp_sum(s);
+    if (lane == 0) atomicAdd(dst, static_cast<double>(s));
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// layout kernels (32x32 smem transposes)
+// ---------------------------------------------------------------------------------------------------
+// in: [n][c][hw] fp32 -> out: [n][hw][c] fp16
+__global__ void nchw_to_nhwc_f16_kernel(const float* __restrict__ in, __half* __restrict__ out, int c, int hw,
+                                        int round_first) {
+  __shared__ float tile[32][33];
+  const int n = blockIdx.z;
+  const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const float* src = in + static_cast<long long>(n) * c * hw;
+  __half* dst = out + static_cast<long long>(n) * c * hw;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int cc = c0 + i, pp = p0 + threadIdx.x;
+    float v = 0.f;
+    if (cc < c && pp < hw) v = src[static_cast<long long>(cc) * hw + pp];
+    tile[i][threadIdx.x] = round_first ? rintf(v) : v;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int pp = p0 + i, cc = c0 + threadIdx.x;
+    if (cc < c && pp < hw) dst[static_cast<long long>(pp) * c + cc] = __float2half_rn(tile[threadIdx.x][i]);
+  }
+}
+
+// in: [n][hw][c] (fp16 or fp32) -> out: [n][c][hw] fp32
+template <typename TIn>
+__global__ void nhwc_to_nchw_f32_kernel(const TIn* __restrict__ in, float* __restrict__ out, int c, int hw) {
+  __shared__ float tile[32][33];
+  const int n = blockIdx.z;
+  const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const TIn* src = in + static_cast<long long>(n) * c * hw;
+  float* dst = out + static_cast<long long>(n) * c * hw;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int pp = p0 + i, cc = c0 + threadIdx.x;
+    float v = 0.f;
+    if (cc < c && pp < hw) v = static_cast<float>(src[static_cast<long long>(pp) * c + cc]);
+    tile[i][threadIdx.x] = v;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int cc = c0 + i, pp = p0 + threadIdx.x;
+    if (cc < c && pp < hw) dst[static_cast<long long>(cc) * hw + pp] = tile[threadIdx.x][i];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// first analysis layer operand staging: one warp per output pixel, 128 fp16 per row
+// k = (r*5 + s)*3 + ch for k < 75, zero above
+// ---------------------------------------------------------------------------------------------------
+__global__ void im2col_k5s2_c3_kernel(const float* __restrict__ x, __half* __restrict__ rows, int n, int h,
+                                      int w, int h_out, int w_out, int pad_top, int pad_left) {
+  const int lane = threadIdx.x & 31;
+  const long long warp_global = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5;
+  const long long n_warps = (gridDim.x * static_cast<long long>(blockDim.x)) >> 5;
+  const long long total = static_cast<long long>(n) * h_out * w_out;
+  for (long long pix = warp_global; pix < total; pix += n_warps) {
+    const int ow = static_cast<int>(pix % w_out);
+    const long long t = pix / w_out;
+    const int oh = static_cast<int>(t % h_out);
+    const int img = static_cast<int>(t / h_out);
+    const float* xi = x + static_cast<long long>(img) * 3 * h * w;
+    __half v[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int k = lane * 4 + j;
+      float f = 0.f;
+      if (k < 75) {
+        const int tap = k / 3, ch = k - tap * 3;
+        const int r = tap / 5, s = tap - r * 5;
+        const int ih = 2 * oh + r - 2 - pad_top, iw = 2 * ow + s - 2 - pad_left;
+        if (ih >= 0 && ih < h && iw >= 0 && iw < w) f = __ldg(xi + (static_cast<long long>(ch) * h + ih) * w + iw);
+      }
+      v[j] = __float2half_rn(f);
+    }
+    uint2 pk;
+    pk.x = static_cast<uint32_t>(__half_as_ushort(v[0])) | (static_cast<uint32_t>(__half_as_ushort(v[1])) << 16);
+    pk.y = static_cast<uint32_t>(__half_as_ushort(v[2])) | (static_cast<uint32_t>(__half_as_ushort(v[3])) << 16);
+    reinterpret_cast<uint2*>(rows + pix * 128)[lane] = pk;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// latent staging
+// ---------------------------------------------------------------------------------------------------
+__global__ void latent_stage_kernel(const float* __restrict__ y, const __half* __restrict__ cond,
+                                    __half* __restrict__ y16, __half* __restrict__ yq16, long long numel,
+                                    int residual) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < numel;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const float v = y[i];
+    if (y16) y16[i] = __float2half_rn(v);
+    if (yq16) {
+      const float sub = residual ? __half2float(cond[i]) : 0.f;
+      yq16[i] = __float2half_rn(rintf(v - sub));
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// GaussianConditional arithmetic (entropy_models.py:122-150, 521-526, 570-604; bound_ops.py:50-53)
+// ---------------------------------------------------------------------------------------------------
+struct GcOut {
+  float y_hat, lik;
+  int idx, sym;
+};
+
+__device__ __forceinline__ float lower_bound(float x, float b) {
+  // torch.max(x, bound): NaN propagates
+  return (x != x) ? x : fmaxf(x, b);
+}
+
+__device__ __forceinline__ GcOut gc_eval(float y, float sigma, float mu, const float* __restrict__ table,
+                                         int n_scales, float scale_bound, float lik_bound, bool want_idx) {
+  GcOut o;
+  const float t = rintf(y - mu);  // torch.round: half to even
+  o.sym = static_cast<int>(t);
+  o.y_hat = t + mu;
+  const float v = fabsf(o.y_hat - mu);
+  const float s = lower_bound(sigma, scale_bound);
+  const float c = -0.70710678118654752440f;  // float(-(2 ** -0.5))
+  const float upper = 0.5f * erfcf(c * ((0.5f - v) / s));
+  const float lower = 0.5f * erfcf(c * ((-0.5f - v) / s));
+  o.lik = lower_bound(upper - lower, lik_bound);
+  o.idx = 0;
+  if (want_idx) {
+    // idx = (n-1) - #{k < n-1 : s <= table[k]} == first k in [0, n-1) with s <= table[k] (table ascending),
+    // n-1 when there is none (also for NaN, where every comparison is false)
+    int lo = 0, hi = n_scales - 1;
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      if (s <= table[mid]) hi = mid;
+      else lo = mid + 1;
+    }
+    o.idx = lo;
+  }
+  return o;
+}
+
+__global__ void gc_flat_kernel(const float* __restrict__ y, const float* __restrict__ scales,
+                               const float* __restrict__ means, long long numel,
+                               const float* __restrict__ table_g, int n_scales, float scale_bound,
+                               float lik_bound, float* __restrict__ y_hat, float* __restrict__ lik,
+                               int* __restrict__ idx, int* __restrict__ sym, double* bits) {
+  __shared__ float table[256];
+  __shared__ float red[32];
+  const bool want_idx = idx != nullptr;
+  if (want_idx)
+    for (int i = threadIdx.x; i < n_scales; i += blockDim.x) table[i] = table_g[i];
+  __syncthreads();
+  float acc = 0.f;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < numel;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const GcOut o = gc_eval(y[i], scales[i], means ? means[i] : 0.f, table, n_scales, scale_bound, lik_bound,
+                            want_idx);
+    if (y_hat) y_hat[i] = o.y_hat;
+    if (lik) lik[i] = o.lik;
+    if (idx) idx[i] = o.idx;
+    if (sym) sym[i] = o.sym;
+    acc -= log2f(o.lik);
+  }
+  if (bits) block_accumulate(acc, bits, red);
+}
+
+// NHWC inputs -> NCHW outputs. Block = 32 pixels x 64 channels; reads are 256-byte channel runs,
+// writes are 128-byte pixel runs.
+constexpr int kGcPix = 32, kGcCh = 64;
+__global__ void __launch_bounds__(256)
+gc_nhwc_kernel(const float* __restrict__ y, const float* __restrict__ params, int c, int hw,
+               const float* __restrict__ table_g, int n_scales, float scale_bound, float lik_bound,
+               float* __restrict__ y_hat, float* __restrict__ lik, int* __restrict__ idx, int* __restrict__ sym,
+               double* bits) {
+  __shared__ float s_yhat[kGcCh][kGcPix + 1];
+  __shared__ float s_lik[kGcCh][kGcPix + 1];
+  __shared__ int s_idx[kGcCh][kGcPix + 1];
+  __shared__ int s_sym[kGcCh][kGcPix + 1];
+  __shared__ float table[256];
+  __shared__ float red[32];
+  const int n = blockIdx.z;
+  const int p0 = blockIdx.x * kGcPix, c0 = blockIdx.y * kGcCh;
+  const bool want_idx = idx != nullptr;
+  if (want_idx)
+    for (int i = threadIdx.x; i < n_scales; i += blockDim.x) table[i] = table_g[i];
+  __syncthreads();
+  const float* yb = y + static_cast<long long>(n) * hw * c;
+  const float* pb = params + static_cast<long long>(n) * hw * 2 * c;
+  float acc = 0.f;
+  {
+    const int ch = threadIdx.x & (kGcCh - 1);
+    const int cc = c0 + ch;
+    for (int pi = threadIdx.x / kGcCh; pi < kGcPix; pi += 256 / kGcCh) {
+      const int pp = p0 + pi;
+      if (pp < hw && cc < c) {
+        const float yv = yb[static_cast<long long>(pp) * c + cc];
+        const float sg = pb[static_cast<long long>(pp) * 2 * c + cc];
+        const float mu = pb[static_cast<long long>(pp) * 2 * c + c + cc];
+        const GcOut o = gc_eval(yv, sg, mu, table, n_scales, scale_bound, lik_bound, want_idx);
+        s_yhat[ch][pi] = o.y_hat;
+        s_lik[ch][pi] = o.lik;
+        s_idx[ch][pi] = o.idx;
+        s_sym[ch][pi] = o.sym;
+        acc -= log2f(o.lik);
+      }
+    }
+  }
+  __syncthreads();
+  {
+    const int pi = threadIdx.x & (kGcPix - 1);
+    const int pp = p0 + pi;
+    for (int ch = threadIdx.x / kGcPix; ch < kGcCh; ch += 256 / kGcPix) {
+      const int cc = c0 + ch;
+      if (pp < hw && cc < c) {
+        const long long o = (static_cast<long long>(n) * c + cc) * hw + pp;
+        if (y_hat) y_hat[o] = s_yhat[ch][pi];
+        if (lik) lik[o] = s_lik[ch][pi];
+        if (idx) idx[o] = s_idx[ch][pi];
+        if (sym) sym[o] = s_sym[ch][pi];
+      }
+    }
+  }
+  if (bits) block_accumulate(acc, bits + n, red);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// EntropyBottleneck forward (eval): one thread per channel, 16 pixels per block
+// ---------------------------------------------------------------------------------------------------
+constexpr int kEbParams = 59;
+constexpr int kEbPix = 16;
+
+__device__ __forceinline__ float eb_logits(float x, const float* __restrict__ q) {
+  float l[3], m[3];
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    float t = q[j] * x + q[3 + j];
+    l[j] = t + q[6 + j] * tanhf(t);
+  }
+  const float* r = q + 9;
+#pragma unroll
+  for (int layer = 0; layer < 3; ++layer) {
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      float t = r[3 * i] * l[0] + r[3 * i + 1] * l[1] + r[3 * i + 2] * l[2] + r[9 + i];
+      m[i] = t + r[12 + i] * tanhf(t);
+    }
+#pragma unroll
+    for (int i = 0; i < 3; ++i) l[i] = m[i];
+    r += 15;
+  }
+  return r[0] * l[0] + r[1] * l[1] + r[2] * l[2] + r[3];
+}
+
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+__global__ void eb_fwd_kernel(const float* __restrict__ z, const float* __restrict__ params, int c, int hw,
+                              float lik_bound, __half* __restrict__ zhat16, float* __restrict__ zhat_nchw,
+                              float* __restrict__ lik_nchw, double* bits) {
+  extern __shared__ float sm[];  // [2][c][kEbPix+1] + red[32]
+  float* s_z = sm;
+  float* s_l = sm + c * (kEbPix + 1);
+  float* red = sm + 2 * c * (kEbPix + 1);
+  const int n = blockIdx.y;
+  const int p0 = blockIdx.x * kEbPix;
+  const int ch = threadIdx.x;
+  float acc = 0.f;
+  if (ch < c) {
+    float q[kEbParams];
+#pragma unroll
+    for (int i = 0; i < kEbParams; ++i) q[i] = params[ch * kEbParams + i];
+    const float med = q[58];
+    for (int pi = 0; pi < kEbPix; ++pi) {
+      const int pp = p0 + pi;
+      if (pp >= hw) break;
+      const long long off = (static_cast<long long>(n) * hw + pp) * c + ch;
+      const float zq = rintf(z[off] - med) + med;
+      const float lo = eb_logits(zq - 0.5f, q);
+      const float up = eb_logits(zq + 0.5f, q);
+      const float sum = lo + up;
+      const float sgn = sum > 0.f ? -1.f : (sum < 0.f ? 1.f : 0.f);
+      float lk = fabsf(sigmoidf_(sgn * up) - sigmoidf_(sgn * lo));
+      lk = lower_bound(lk, lik_bound);
+      if (zhat16) zhat16[off] = __float2half_rn(zq);
+      s_z[ch * (kEbPix + 1) + pi] = zq;
+      s_l[ch * (kEbPix + 1) + pi] = lk;
+      acc -= log2f(lk);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < c * kEbPix; i += blockDim.x) {
+    const int cc = i / kEbPix, pi = i % kEbPix;
+    const int pp = p0 + pi;
+    if (pp < hw) {
+      const long long o = (static_cast<long long>(n) * c + cc) * hw + pp;
+      if (zhat_nchw) zhat_nchw[o] = s_z[cc * (kEbPix + 1) + pi];
+      if (lik_nchw) lik_nchw[o] = s_l[cc * (kEbPix + 1) + pi];
+    }
+  }
+  if (bits) block_accumulate(acc, bits + n, red);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// synthesis tail: merged-phase [n][h2][w2][16] -> NCHW [n][3][2*h2][2*w2], clamp, squared error
+// ---------------------------------------------------------------------------------------------------
+__global__ void synthesis_tail_kernel(const float* __restrict__ in, float* __restrict__ xhat, int h2, int w2,
+                                      const float* __restrict__ xref, int h_ref, int w_ref, int pad_top,
+                                      int pad_left, double* sq_err) {
+  __shared__ float red[32];
+  const int n = blockIdx.y;
+  const long long per = static_cast<long long>(h2) * w2;
+  const int H = 2 * h2, W = 2 * w2;
+  float acc = 0.f;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < per;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int ii = static_cast<int>(i / w2), jj = static_cast<int>(i - static_cast<long long>(ii) * w2);
+    const float4* src = reinterpret_cast<const float4*>(in + (static_cast<long long>(n) * per + i) * 16);
+    float v[16];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float4 f = __ldg(src + k);
+      v[4 * k] = f.x;
+      v[4 * k + 1] = f.y;
+      v[4 * k + 2] = f.z;
+      v[4 * k + 3] = f.w;
+    }
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) {
+#pragma unroll
+      for (int p = 0; p < 2; ++p) {
+        const int Y = 2 * ii + p;
+        float a = fminf(fmaxf(v[(p * 2 + 0) * 3 + ch], 0.f), 1.f);
+        float b = fminf(fmaxf(v[(p * 2 + 1) * 3 + ch], 0.f), 1.f);
+        const long long o = ((static_cast<long long>(n) * 3 + ch) * H + Y) * W + 2 * jj;
+        *reinterpret_cast<float2*>(xhat + o) = make_float2(a, b);
+        if (xref) {
+          const int yr = Y - pad_top;
+          if (yr >= 0 && yr < h_ref) {
+            const float* rrow = xref + ((static_cast<long long>(n) * 3 + ch) * h_ref + yr) * w_ref;
+            const int x0 = 2 * jj - pad_left;
+            if (x0 >= 0 && x0 < w_ref) {
+              const float d = rrow[x0] - a;
+              acc += d * d;
+            }
+            if (x0 + 1 >= 0 && x0 + 1 < w_ref) {
+              const float d = rrow[x0 + 1] - b;
+              acc += d * d;
+            }
+          }
+        }
+      }
+    }
+  }
+  if (sq_err) block_accumulate(acc, sq_err + n, red);
+}
+
+}  // namespace stem
+
+using namespace stem;
+
+#define CHECK_LAUNCH(name)                                         \
+  do {                                                             \
+    count_launch();                                                \
+    cudaError_t e__ = cudaGetLastError();                          \
+    if (e__ != cudaSuccess) return set_cuda_error(name, e__);      \
+  } while (0)
+
+extern "C" int stemb200_nchw_f32_to_nhwc_f16(const float* in, void* out, int32_t n, int32_t c, int32_t h,
+                                             int32_t w, int32_t round_first, void* stream) {
+  if (!in || !out || n < 1 || c < 1 || h < 1 || w < 1) return set_error("nchw_to_nhwc: bad argument");
+  const int hw = h * w;
+  dim3 grid((hw + 31) / 32, (c + 31) / 32, n), block(32, 8);
+  nchw_to_nhwc_f16_kernel<<<grid, block, 0, static_cast<cudaStream_t>(stream)>>>(
+      in, static_cast<__half*>(out), c, hw, round_first);
+  CHECK_LAUNCH("nchw_to_nhwc_f16");
+  return 0;
+}
+
+extern "C" int stemb200_nhwc_f16_to_nchw_f32(const void* in, float* out, int32_t n, int32_t c, int32_t h,
+                                             int32_t w, void* stream) {
+  if (!in || !out || n < 1 || c < 1 || h < 1 || w < 1) return set_error("nhwc_to_nchw: bad argument");
+  const int hw = h * w;
+  dim3 grid((hw + 31) / 32, (c + 31) / 32, n), block(32, 8);
+  nhwc_to_nchw_f32_kernel<__half><<<grid, block, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __half*>(in), out, c, hw);
+  CHECK_LAUNCH("nhwc_f16_to_nchw_f32");
+  return 0;
+}
+
+extern "C" int stemb200_nhwc_f32_to_nchw_f32(const float* in, float* out, int32_t n, int32_t c, int32_t h,
+                                             int32_t w, void* stream) {
+  if (!in || !out || n < 1 || c < 1 || h < 1 || w < 1) return set_error("nhwc_to_nchw: bad argument");
+  const int hw = h * w;
+  dim3 grid((hw + 31) / 32, (c + 31) / 32, n), block(32, 8);
+  nhwc_to_nchw_f32_kernel<float><<<grid, block, 0, static_cast<cudaStream_t>(stream)>>>(in, out, c, hw);
+  CHECK_LAUNCH("nhwc_f32_to_nchw_f32");
+  return 0;
+}
+
+extern "C" int stemb200_im2col_k5s2_c3(const float* x_nchw, void* out_rows, int32_t n, int32_t h, int32_t w,
+                                       int32_t h_pad, int32_t w_pad, int32_t pad_top, int32_t pad_left,
+                                       void* stream) {
+  if (!x_nchw || !out_rows || n < 1 || h < 1 || w < 1 || h_pad < h || w_pad < w || pad_top < 0 || pad_left < 0)
+    return set_error("im2col: bad argument");
+  const int h_out = (h_pad - 1) / 2 + 1, w_out = (w_pad - 1) / 2 + 1;
+  const long long total = static_cast<long long>(n) * h_out * w_out;
+  const int blocks = static_cast<int>(std::min<long long>((total + 7) / 8, 148LL * 64));
+  im2col_k5s2_c3_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      x_nchw, static_cast<__half*>(out_rows), n, h, w, h_out, w_out, pad_top, pad_left);
+  CHECK_LAUNCH("im2col_k5s2_c3");
+  return 0;
+}
+
+extern "C" int stemb200_latent_stage(const float* y_nhwc, const void* cond_f16, void* y_f16, void* yq_f16,
+                                     int64_t numel, int32_t residual, void* stream) {
+  if (!y_nhwc || numel < 1 || (residual && !cond_f16)) return set_error("latent_stage: bad argument");
+  const int blocks = static_cast<int>(std::min<long long>((numel + 255) / 256, 148LL * 16));
+  latent_stage_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      y_nhwc, static_cast<const __half*>(cond_f16), static_cast<__half*>(y_f16), static_cast<__half*>(yq_f16),
+      numel, residual);
+  CHECK_LAUNCH("latent_stage");
+  return 0;
+}
+
+extern "C" int stemb200_gaussian_conditional_flat(const float* y, const float* scales, const float* means,
+                                                  int64_t numel, const float* scale_table, int32_t n_scales,
+                                                  float scale_bound, float lik_bound, float* y_hat, float* lik,
+                                                  int32_t* idx, int32_t* sym, double* bits, void* stream) {
+  if (!y || !scales || numel < 1) return set_error("gaussian_conditional_flat: bad argument");
+  if (idx && (!scale_table || n_scales < 1 || n_scales > 256))
+    return set_error("gaussian_conditional_flat: idx needs a scale table of 1..256 entries");
+  const int blocks = static_cast<int>(std::min<long long>((numel + 255) / 256, 148LL * 16));
+  gc_flat_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      y, scales, means, numel, scale_table, n_scales, scale_bound, lik_bound, y_hat, lik, idx, sym, bits);
+  CHECK_LAUNCH("gaussian_conditional_flat");
+  return 0;
+}
+
+extern "C" int stemb200_gaussian_conditional_fwd(const float* y_nhwc, const float* params_nhwc, int32_t n,
+                                                 int32_t c, int32_t h, int32_t w, const float* scale_table,
+                                                 int32_t n_scales, float scale_bound, float lik_bound,
+                                                 float* y_hat_nchw, float* lik_nchw, int32_t* idx_nchw,
+                                                 int32_t* sym_nchw, double* bits, void* stream) {
+  if (!y_nhwc || !params_nhwc || n < 1 || c < 1 || h < 1 || w < 1)
+    return set_error("gaussian_conditional_fwd: bad argument");
+  if (idx_nchw && (!scale_table || n_scales < 1 || n_scales > 256))
+    return set_error("gaussian_conditional_fwd: idx needs a scale table of 1..256 entries");
+  const int hw = h * w;
+  dim3 grid((hw + kGcPix - 1) / kGcPix, (c + kGcCh - 1) / kGcCh, n);
+  gc_nhwc_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      y_nhwc, params_nhwc, c, hw, scale_table, n_scales, scale_bound, lik_bound, y_hat_nchw, lik_nchw, idx_nchw,
+      sym_nchw, bits);
+  CHECK_LAUNCH("gaussian_conditional_fwd");
+  return 0;
+}
+
+extern "C" int stemb200_entropy_bottleneck_fwd(const float* z_nhwc, const float* params, int32_t n, int32_t c,
+                                               int32_t h, int32_t w, float lik_bound, void* z_hat_nhwc_f16,
+                                               float* z_hat_nchw, float* lik_nchw, double* bits, void* stream) {
+  if (!z_nhwc || !params || n < 1 || c < 1 || c > 1024 || h < 1 || w < 1)
+    return set_error("entropy_bottleneck_fwd: bad argument");
+  const int hw = h * w;
+  const int threads = ((c + 31) / 32) * 32;
+  const size_t smem = (2 * static_cast<size_t>(c) * (kEbPix + 1) + 32) * sizeof(float);
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(eb_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         static_cast<int>(smem));
+    if (e != cudaSuccess) return set_cuda_error("cudaFuncSetAttribute(eb)", e);
+  }
+  dim3 grid((hw + kEbPix - 1) / kEbPix, n);
+  eb_fwd_kernel<<<grid, threads, smem, static_cast<cudaStream_t>(stream)>>>(
+      z_nhwc, params, c, hw, lik_bound, static_cast<__half*>(z_hat_nhwc_f16), z_hat_nchw, lik_nchw, bits);
+  CHECK_LAUNCH("entropy_bottleneck_fwd");
+  return 0;
+}
+
+extern "C" int stemb200_synthesis_tail(const float* in_nhwc16, float* x_hat_nchw, int32_t n, int32_t h2,
+                                       int32_t w2, const float* x_ref, int32_t h_ref, int32_t w_ref,
+                                       int32_t pad_top, int32_t pad_left, double* sq_err, void* stream) {
+  if (!in_nhwc16 || !x_hat_nchw || n < 1 || h2 < 1 || w2 < 1) return set_error("synthesis_tail: bad argument");
+  const long long per = static_cast<long long>(h2) * w2;
+  dim3 grid(static_cast<unsigned>(std::min<long long>((per + 255) / 256, 148LL * 8)), n);
+  synthesis_tail_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      in_nhwc16, x_hat_nchw, h2, w2, x_ref, h_ref, w_ref, pad_top, pad_left, sq_err);
+  CHECK_LAUNCH("synthesis_tail");
+  return 0;
+}
