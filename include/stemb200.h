@@ -83,10 +83,10 @@ int stemb200_conv2d_fwd(const stemb200_conv_desc* d, const void* const* in, cons
 /* ---------------------------------------------------------------------------------------------------
  * Layout / staging kernels at the API boundary
  * ------------------------------------------------------------------------------------------------- */
-/* NCHW fp32 -> NHWC fp16 (optionally rounding to nearest-even integer first: y_hat = round(y),
- * entropy_models.py:141) */
-int stemb200_nchw_f32_to_nhwc_f16(const float* in, void* out, int32_t n, int32_t c, int32_t h, int32_t w,
-                                  int32_t round_first, void* stream);
+/* NCHW fp32 -> NHWC fp16 of (in - sub) (sub may be NULL), optionally rounded to nearest-even integer first:
+ * y_hat = round(y) / round(y_cur - y_conditioned) (entropy_models.py:141, spatiotemporalpriors.py:852-856) */
+int stemb200_nchw_f32_to_nhwc_f16(const float* in, const float* sub, void* out, int32_t n, int32_t c, int32_t h,
+                                  int32_t w, int32_t round_first, void* stream);
 int stemb200_nhwc_f16_to_nchw_f32(const void* in, float* out, int32_t n, int32_t c, int32_t h, int32_t w,
                                   void* stream);
 int stemb200_nhwc_f32_to_nchw_f32(const float* in, float* out, int32_t n, int32_t c, int32_t h, int32_t w,
@@ -100,27 +100,31 @@ int stemb200_im2col_k5s2_c3(const float* x_nchw, void* out_rows, int32_t n, int3
 /* ---------------------------------------------------------------------------------------------------
  * Entropy-model elementwise kernels
  * ------------------------------------------------------------------------------------------------- */
-/* P-frame latent staging (spatiotemporalpriors.py:570, :852-856): y NHWC fp32 ->
- *   y_f16  = fp16(y)                      (HE input, first half of the cat)
- *   yq_f16 = fp16(round(y - sub)) where sub = residual ? cond : 0   (context_prediction input)
- * cond may be NULL when residual == 0. */
-int stemb200_latent_stage(const float* y_nhwc, const void* cond_f16, void* y_f16, void* yq_f16,
-                          int64_t numel, int32_t residual, void* stream);
+/* P-frame latent staging (spatiotemporalpriors.py:570, :852-868): y NHWC fp32 ->
+ *   y_f16    = fp16(y)                     (HE input, first half of the cat)
+ *   yq_f16   = fp16(round(y - sub))        (context_prediction input), sub = cond (fp16 NHWC) or 0 when NULL
+ *   yhat_f16 = fp16(round(y - sub) + sub)  (y_hat: next frame's y_conditioned, g_s input)
+ * any output may be NULL. */
+int stemb200_latent_stage(const float* y_nhwc, const void* cond_f16, void* y_f16, void* yq_f16, void* yhat_f16,
+                          int64_t numel, void* stream);
 
 /* GaussianConditional forward + build_indexes + symbols + bit count in one pass
  * (entropy_models.py:588-604, :122-150, :570-586; bound_ops.py:50-53; evalSTEM.py:133-136).
- *   inputs : y, params NHWC fp32; params = EPM output [pixels][2*C], scales = ch [0,C), means = ch [C,2C)
- *            (chunk(2,1), spatiotemporalpriors.py:577). y has C channels.
+ *   inputs : y fp32 with C channels, NHWC or (y_is_nchw) NCHW; cond fp16 NHWC or NULL: when given the coded
+ *            quantity is y - cond (_Res, spatiotemporalpriors.py:852); params NHWC fp32 = EPM output
+ *            [pixels][2*C], scales = ch [0,C), means = ch [C,2C) (chunk(2,1), spatiotemporalpriors.py:577).
+ *   yhat_mode 0: y_hat = round(y - mu) + mu (GaussianConditional output, WithoutSPM variants :188);
+ *             1: y_hat = round(y - cond) + cond (SPM variants return the mean-free rounding, :570,:856-868).
  *   outputs (any may be NULL): y_hat, lik NCHW fp32; idx, sym NCHW int32;
  *            bits[frame] (double) += sum(-log2(lik)) over the frame.
  *   scale_table: fp32 [n_scales] on device (may be NULL when idx == NULL).
  * y_hat = round(y - mu) + mu; lik evaluated at |y_hat - mu| with sigma = max(sigma, scale_bound);
  * lik floored at lik_bound; idx = (n_scales-1) - #{k < n_scales-1 : sigma <= table[k]}. */
-int stemb200_gaussian_conditional_fwd(const float* y_nhwc, const float* params_nhwc, int32_t n, int32_t c,
-                                      int32_t h, int32_t w, const float* scale_table, int32_t n_scales,
-                                      float scale_bound, float lik_bound, float* y_hat_nchw,
-                                      float* lik_nchw, int32_t* idx_nchw, int32_t* sym_nchw, double* bits,
-                                      void* stream);
+int stemb200_gaussian_conditional_fwd(const float* y, int32_t y_is_nchw, const void* cond_f16,
+                                      const float* params_nhwc, int32_t n, int32_t c, int32_t h, int32_t w,
+                                      const float* scale_table, int32_t n_scales, float scale_bound,
+                                      float lik_bound, int32_t yhat_mode, float* y_hat_nchw, float* lik_nchw,
+                                      int32_t* idx_nchw, int32_t* sym_nchw, double* bits, void* stream);
 /* Same arithmetic on flat arrays (no layout change); the isolated parity test of a9 runs through this. */
 int stemb200_gaussian_conditional_flat(const float* y, const float* scales, const float* means,
                                        int64_t numel, const float* scale_table, int32_t n_scales,

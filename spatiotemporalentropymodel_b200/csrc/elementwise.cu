@@ -40,8 +40,8 @@ __device__ __forceinline__ void block_accumulate(float v, double* dst, float* re
 // layout kernels (32x32 smem transposes)
 // ---------------------------------------------------------------------------------------------------
 // in: [n][c][hw] fp32 -> out: [n][hw][c] fp16
-__global__ void nchw_to_nhwc_f16_kernel(const float* __restrict__ in, __half* __restrict__ out, int c, int hw,
-                                        int round_first) {
+__global__ void nchw_to_nhwc_f16_kernel(const float* __restrict__ in, const float* __restrict__ sub,
+                                        __half* __restrict__ out, int c, int hw, int round_first) {
   __shared__ float tile[32][33];
   const int n = blockIdx.z;
   const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
@@ -50,7 +50,11 @@ __global__ void nchw_to_nhwc_f16_kernel(const float* __restrict__ in, __half* __
   for (int i = threadIdx.y; i < 32; i += blockDim.y) {
     const int cc = c0 + i, pp = p0 + threadIdx.x;
     float v = 0.f;
-    if (cc < c && pp < hw) v = src[static_cast<long long>(cc) * hw + pp];
+    if (cc < c && pp < hw) {
+      const long long o = static_cast<long long>(cc) * hw + pp;
+      v = src[o];
+      if (sub) v -= sub[static_cast<long long>(n) * c * hw + o];
+    }
     tile[i][threadIdx.x] = round_first ? rintf(v) : v;
   }
   __syncthreads();
@@ -121,16 +125,16 @@ __global__ void im2col_k5s2_c3_kernel(const float* __restrict__ x, __half* __res
 // latent staging
 // ---------------------------------------------------------------------------------------------------
 __global__ void latent_stage_kernel(const float* __restrict__ y, const __half* __restrict__ cond,
-                                    __half* __restrict__ y16, __half* __restrict__ yq16, long long numel,
-                                    int residual) {
+                                    __half* __restrict__ y16, __half* __restrict__ yq16,
+                                    __half* __restrict__ yhat16, long long numel) {
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < numel;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
     const float v = y[i];
     if (y16) y16[i] = __float2half_rn(v);
-    if (yq16) {
-      const float sub = residual ? __half2float(cond[i]) : 0.f;
-      yq16[i] = __float2half_rn(rintf(v - sub));
-    }
+    const float sub = cond ? __half2float(cond[i]) : 0.f;
+    const float q = rintf(v - sub);
+    if (yq16) yq16[i] = __float2half_rn(q);
+    if (yhat16) yhat16[i] = __float2half_rn(q + sub);
   }
 }
 
@@ -153,7 +157,7 @@ __device__ __forceinline__ GcOut gc_eval(float y, float sigma, float mu, const f
   const float t = rintf(y - mu);  // torch.round: half to even
   o.sym = static_cast<int>(t);
   o.y_hat = t + mu;
-  const float v = fabsf(o.y_hat - mu);
+  const float v = fabsf(o.y_hat - mu);  // likelihood is evaluated at the de-quantised value
   const float s = lower_bound(sigma, scale_bound);
   const float c = -0.70710678118654752440f;  // float(-(2 ** -0.5))
   const float upper = 0.5f * erfcf(c * ((0.5f - v) / s));
@@ -203,7 +207,8 @@ __global__ void gc_flat_kernel(const float* __restrict__ y, const float* __restr
 // writes are 128-byte pixel runs.
 constexpr int kGcPix = 32, kGcCh = 64;
 __global__ void __launch_bounds__(256)
-gc_nhwc_kernel(const float* __restrict__ y, const float* __restrict__ params, int c, int hw,
+gc_nhwc_kernel(const float* __restrict__ y, int y_is_nchw, const __half* __restrict__ cond,
+               const float* __restrict__ params, int c, int hw, int yhat_mode,
                const float* __restrict__ table_g, int n_scales, float scale_bound, float lik_bound,
                float* __restrict__ y_hat, float* __restrict__ lik, int* __restrict__ idx, int* __restrict__ sym,
                double* bits) {
@@ -220,18 +225,33 @@ gc_nhwc_kernel(const float* __restrict__ y, const float* __restrict__ params, in
     for (int i = threadIdx.x; i < n_scales; i += blockDim.x) table[i] = table_g[i];
   __syncthreads();
   const float* yb = y + static_cast<long long>(n) * hw * c;
+  const __half* cb = cond ? cond + static_cast<long long>(n) * hw * c : nullptr;
   const float* pb = params + static_cast<long long>(n) * hw * 2 * c;
   float acc = 0.f;
+  if (y_is_nchw) {
+    // stage the NCHW tile through smem so the channel-major phase below reads it conflict-free
+    const int pi = threadIdx.x & (kGcPix - 1);
+    const int pp = p0 + pi;
+    for (int ch = threadIdx.x / kGcPix; ch < kGcCh; ch += 256 / kGcPix) {
+      const int cc = c0 + ch;
+      s_yhat[ch][pi] = (pp < hw && cc < c) ? yb[static_cast<long long>(cc) * hw + pp] : 0.f;
+    }
+    __syncthreads();
+  }
   {
     const int ch = threadIdx.x & (kGcCh - 1);
     const int cc = c0 + ch;
     for (int pi = threadIdx.x / kGcCh; pi < kGcPix; pi += 256 / kGcCh) {
       const int pp = p0 + pi;
       if (pp < hw && cc < c) {
-        const float yv = yb[static_cast<long long>(pp) * c + cc];
+        float yv = y_is_nchw ? s_yhat[ch][pi] : yb[static_cast<long long>(pp) * c + cc];
+        const float cv = cb ? __half2float(cb[static_cast<long long>(pp) * c + cc]) : 0.f;
+        yv -= cv;  // _Res: the coded quantity is y_cur - y_conditioned (spatiotemporalpriors.py:852)
         const float sg = pb[static_cast<long long>(pp) * 2 * c + cc];
         const float mu = pb[static_cast<long long>(pp) * 2 * c + c + cc];
-        const GcOut o = gc_eval(yv, sg, mu, table, n_scales, scale_bound, lik_bound, want_idx);
+        GcOut o = gc_eval(yv, sg, mu, table, n_scales, scale_bound, lik_bound, want_idx);
+        // SPM variants return y_hat = round(y [- cond]) [+ cond] (:570, :856-868), not the GC output
+        if (yhat_mode == 1) o.y_hat = rintf(yv) + cv;
         s_yhat[ch][pi] = o.y_hat;
         s_lik[ch][pi] = o.lik;
         s_idx[ch][pi] = o.idx;
@@ -399,13 +419,13 @@ using namespace stem;
     if (e__ != cudaSuccess) return set_cuda_error(name, e__);      \
   } while (0)
 
-extern "C" int stemb200_nchw_f32_to_nhwc_f16(const float* in, void* out, int32_t n, int32_t c, int32_t h,
-                                             int32_t w, int32_t round_first, void* stream) {
+extern "C" int stemb200_nchw_f32_to_nhwc_f16(const float* in, const float* sub, void* out, int32_t n, int32_t c,
+                                             int32_t h, int32_t w, int32_t round_first, void* stream) {
   if (!in || !out || n < 1 || c < 1 || h < 1 || w < 1) return set_error("nchw_to_nhwc: bad argument");
   const int hw = h * w;
   dim3 grid((hw + 31) / 32, (c + 31) / 32, n), block(32, 8);
   nchw_to_nhwc_f16_kernel<<<grid, block, 0, static_cast<cudaStream_t>(stream)>>>(
-      in, static_cast<__half*>(out), c, hw, round_first);
+      in, sub, static_cast<__half*>(out), c, hw, round_first);
   CHECK_LAUNCH("nchw_to_nhwc_f16");
   return 0;
 }
@@ -446,12 +466,12 @@ extern "C" int stemb200_im2col_k5s2_c3(const float* x_nchw, void* out_rows, int3
 }
 
 extern "C" int stemb200_latent_stage(const float* y_nhwc, const void* cond_f16, void* y_f16, void* yq_f16,
-                                     int64_t numel, int32_t residual, void* stream) {
-  if (!y_nhwc || numel < 1 || (residual && !cond_f16)) return set_error("latent_stage: bad argument");
+                                     void* yhat_f16, int64_t numel, void* stream) {
+  if (!y_nhwc || numel < 1) return set_error("latent_stage: bad argument");
   const int blocks = static_cast<int>(std::min<long long>((numel + 255) / 256, 148LL * 16));
   latent_stage_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
       y_nhwc, static_cast<const __half*>(cond_f16), static_cast<__half*>(y_f16), static_cast<__half*>(yq_f16),
-      numel, residual);
+      static_cast<__half*>(yhat_f16), numel);
   CHECK_LAUNCH("latent_stage");
   return 0;
 }
@@ -470,9 +490,10 @@ extern "C" int stemb200_gaussian_conditional_flat(const float* y, const float* s
   return 0;
 }
 
-extern "C" int stemb200_gaussian_conditional_fwd(const float* y_nhwc, const float* params_nhwc, int32_t n,
-                                                 int32_t c, int32_t h, int32_t w, const float* scale_table,
-                                                 int32_t n_scales, float scale_bound, float lik_bound,
+extern "C" int stemb200_gaussian_conditional_fwd(const float* y_nhwc, int32_t y_is_nchw, const void* cond_f16,
+                                                 const float* params_nhwc, int32_t n, int32_t c, int32_t h,
+                                                 int32_t w, const float* scale_table, int32_t n_scales,
+                                                 float scale_bound, float lik_bound, int32_t yhat_mode,
                                                  float* y_hat_nchw, float* lik_nchw, int32_t* idx_nchw,
                                                  int32_t* sym_nchw, double* bits, void* stream) {
   if (!y_nhwc || !params_nhwc || n < 1 || c < 1 || h < 1 || w < 1)
@@ -482,8 +503,8 @@ extern "C" int stemb200_gaussian_conditional_fwd(const float* y_nhwc, const floa
   const int hw = h * w;
   dim3 grid((hw + kGcPix - 1) / kGcPix, (c + kGcCh - 1) / kGcCh, n);
   gc_nhwc_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      y_nhwc, params_nhwc, c, hw, scale_table, n_scales, scale_bound, lik_bound, y_hat_nchw, lik_nchw, idx_nchw,
-      sym_nchw, bits);
+      y_nhwc, y_is_nchw, static_cast<const __half*>(cond_f16), params_nhwc, c, hw, yhat_mode, scale_table,
+      n_scales, scale_bound, lik_bound, y_hat_nchw, lik_nchw, idx_nchw, sym_nchw, bits);
   CHECK_LAUNCH("gaussian_conditional_fwd");
   return 0;
 }

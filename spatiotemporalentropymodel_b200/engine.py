@@ -1,0 +1,501 @@
+"""Host-side execution engine: weight repacking, workspace, and the kernel chains of the P-frame path.
+
+All arithmetic happens in libstemb200.so (hand-written sm_100a kernels); PyTorch is used for device memory,
+streams and parameter storage only.  Nothing here falls back to torch ops for compute: a non-CUDA tensor or a
+missing library raises.
+
+Kernel chains (reference lines in parentheses):
+  analysis   g_a  (priors.py:421-429)      im2col -> [GEMM+x^2] -> GDN -> [conv s2+x^2] -> GDN -> ... -> conv s2 (fp32 y)
+  STEM            (spatiotemporalpriors.py:561-585 and variants) HE -> EB -> HD, TPM, ctx, EPM -> GC
+  synthesis  g_s  (priors.py:431-439,397-402)  [deconv+x^2] -> IGDN -> ... -> merged-phase deconv -> tail (clamp, MSE)
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+import torch.nn.functional as F
+
+from . import _lib
+from ._lib import DT_F16, DT_F32, EPI_GDN, EPI_IGDN, EPI_LINEAR, ConvDesc
+
+Tensor = torch.Tensor
+MASK_A_5x5 = 0x00000FFF  # taps (r, s) with r < 2, or r == 2 and s < 2 (layers/layers.py:39-42)
+SQ_SCALE = 0.125         # x^2 is carried as (x/8)^2 in fp16 (|x| < 2047 stays finite)
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: Optional[Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _require_cuda(*ts: Tensor) -> None:
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("spatiotemporalentropymodel_b200 runs on CUDA (sm_100a) tensors only; "
+                               "there is no CPU fallback")
+
+
+class Workspace:
+    """Named, shape-keyed device buffers that persist across calls (so CUDA graphs can capture the chain)."""
+
+    def __init__(self, device: torch.device):
+        self.device = device
+        self._bufs: Dict[str, Tensor] = {}
+
+    def get(self, name: str, shape: Sequence[int], dtype: torch.dtype) -> Tensor:
+        t = self._bufs.get(name)
+        shape = tuple(int(s) for s in shape)
+        if t is None or tuple(t.shape) != shape or t.dtype != dtype:
+            t = torch.empty(shape, dtype=dtype, device=self.device)
+            self._bufs[name] = t
+        return t
+
+    def nbytes(self) -> int:
+        return sum(t.numel() * t.element_size() for t in self._bufs.values())
+
+
+class ConvOp:
+    """One packed convolution: geometry + repacked fp16 weight matrix + fp32 bias on the device."""
+
+    def __init__(self, weight: Tensor, bias: Tensor, *, c_in: Sequence[int], c_out: int, k: int, stride: int = 1,
+                 transposed: bool = False, tap_mask: int = 0, epilogue: int = EPI_LINEAR, slope: float = 1.0,
+                 out_dtype: int = DT_F16, write_sq: bool = False, direct_store: bool = False):
+        _require_cuda(weight, bias)
+        self.lib = _lib.load()
+        self.c_in = list(c_in)
+        self.c_out = c_out
+        self.k, self.stride, self.transposed = k, stride, transposed
+        self.out_dtype, self.write_sq = out_dtype, write_sq
+        d = ConvDesc()
+        d.batch, d.h_in, d.w_in = 1, 16, 16
+        d.n_src = len(c_in)
+        for i, c in enumerate(c_in):
+            d.c_in[i] = c
+        d.c_out = c_out
+        d.kh = d.kw = k
+        d.stride = stride
+        d.transposed = int(transposed)
+        d.tap_mask = tap_mask
+        d.epilogue = epilogue
+        d.lrelu_slope = slope
+        d.out_dtype = out_dtype
+        d.write_sq = int(write_sq)
+        d.sq_scale = SQ_SCALE
+        d.tile_h = d.tile_w = 0
+        d.direct_store = int(direct_store)
+        self.desc = d
+        K = self.lib.stemb200_conv2d_packed_k(C.byref(d))
+        if K <= 0:
+            _lib.check(int(K), "conv2d_packed_k")
+        w32 = weight.detach().to(torch.float32).contiguous()
+        self.packed = torch.empty((c_out, K), dtype=torch.float16, device=weight.device)
+        _lib.check(self.lib.stemb200_conv2d_pack_weight(C.byref(d), w32.data_ptr(), self.packed.data_ptr(),
+                                                        _stream()), "conv2d_pack_weight")
+        self.bias = bias.detach().to(torch.float32).contiguous()
+        self.flops_per_pixel = 2 * K * c_out  # per output pixel of one sub-problem (upper bound for deconv)
+
+    def out_hw(self, h: int, w: int) -> Tuple[int, int]:
+        if self.transposed:
+            return 2 * h, 2 * w
+        if self.stride == 2:
+            p = self.k // 2
+            return (h + 2 * p - self.k) // 2 + 1, (w + 2 * p - self.k) // 2 + 1
+        return h, w
+
+    def __call__(self, inputs: Sequence[Tensor], batch: int, h: int, w: int, out: Tensor,
+                 aux: Optional[Tensor] = None, out_sq: Optional[Tensor] = None) -> Tensor:
+        d = self.desc
+        d.batch, d.h_in, d.w_in = batch, h, w
+        arr = (C.c_void_p * len(inputs))(*[t.data_ptr() for t in inputs])
+        _lib.check(self.lib.stemb200_conv2d_fwd(C.byref(d), arr, self.packed.data_ptr(), self.bias.data_ptr(),
+                                                _ptr(aux), out.data_ptr(), _ptr(out_sq), _stream()),
+                   "conv2d_fwd")
+        return out
+
+
+# ------------------------------------------------------------------------------------------------------
+# thin wrappers of the elementwise entry points
+# ------------------------------------------------------------------------------------------------------
+def nchw_to_nhwc_f16(x: Tensor, out: Tensor, sub: Optional[Tensor] = None, round_first: bool = False) -> Tensor:
+    n, c, h, w = x.shape
+    _lib.check(_lib.load().stemb200_nchw_f32_to_nhwc_f16(x.data_ptr(), _ptr(sub), out.data_ptr(), n, c, h, w,
+                                                         int(round_first), _stream()), "nchw_to_nhwc_f16")
+    return out
+
+
+def nhwc_f16_to_nchw(x: Tensor, out: Tensor) -> Tensor:
+    n, h, w, c = x.shape
+    _lib.check(_lib.load().stemb200_nhwc_f16_to_nchw_f32(x.data_ptr(), out.data_ptr(), n, c, h, w, _stream()),
+               "nhwc_f16_to_nchw_f32")
+    return out
+
+
+def nhwc_f32_to_nchw(x: Tensor, out: Tensor) -> Tensor:
+    n, h, w, c = x.shape
+    _lib.check(_lib.load().stemb200_nhwc_f32_to_nchw_f32(x.data_ptr(), out.data_ptr(), n, c, h, w, _stream()),
+               "nhwc_f32_to_nchw_f32")
+    return out
+
+
+def gaussian_conditional_flat(y: Tensor, scales: Tensor, means: Optional[Tensor], table: Optional[Tensor],
+                              scale_bound: float, lik_bound: float, want_yhat=True, want_lik=True,
+                              want_idx=False, want_sym=False, want_bits=False):
+    """Flat-array GaussianConditional (entropy_models.py:588-604) on CUDA fp32 tensors of equal shape."""
+    _require_cuda(y, scales, means)
+    y = y.contiguous()
+    scales = scales.contiguous()
+    means = means.contiguous() if means is not None else None
+    dev = y.device
+    y_hat = torch.empty_like(y) if want_yhat else None
+    lik = torch.empty_like(y) if want_lik else None
+    idx = torch.empty(y.shape, dtype=torch.int32, device=dev) if want_idx else None
+    sym = torch.empty(y.shape, dtype=torch.int32, device=dev) if want_sym else None
+    bits = torch.zeros(1, dtype=torch.float64, device=dev) if want_bits else None
+    n_scales = 0 if table is None else table.numel()
+    _lib.check(_lib.load().stemb200_gaussian_conditional_flat(
+        y.data_ptr(), scales.data_ptr(), _ptr(means), y.numel(), _ptr(table), n_scales, scale_bound, lik_bound,
+        _ptr(y_hat), _ptr(lik), _ptr(idx), _ptr(sym), _ptr(bits), _stream()), "gaussian_conditional_flat")
+    return y_hat, lik, idx, sym, bits
+
+
+# ------------------------------------------------------------------------------------------------------
+# g_a / g_s of the I-frame model (mbt2018), the transforms a P-frame goes through
+# ------------------------------------------------------------------------------------------------------
+def _gdn_fold(beta_p: Tensor, gamma_p: Tensor) -> Tuple[Tensor, Tensor]:
+    """NonNegativeParametrizer forward folded once at load (ops/parametrizers.py:42-45, gdn.py:55-57)."""
+    ped = 2.0 ** -36
+    beta = torch.clamp_min(beta_p.float(), (1e-6 + ped) ** 0.5) ** 2 - ped
+    gamma = torch.clamp_min(gamma_p.float(), ped ** 0.5) ** 2 - ped
+    return beta, gamma
+
+
+class TransformsEngine:
+    """Packed g_a / g_s (N = M = 192 for mbt2018 q4; any multiple of 64 works)."""
+
+    def __init__(self, sd: Dict[str, Tensor], device: torch.device):
+        dev = device
+        g = lambda k: sd[k].detach().to(dev, torch.float32)
+        self.device = dev
+        self.ws = Workspace(dev)
+        N = sd["g_a.0.weight"].shape[0]
+        M = sd["g_a.6.weight"].shape[0]
+        self.N, self.M = N, M
+        # --- analysis
+        w0 = g("g_a.0.weight")  # (N, 3, 5, 5) -> (N, 128): k = (r*5+s)*3 + ch, zero padded
+        w0 = F.pad(w0.permute(0, 2, 3, 1).reshape(N, 75), (0, 128 - 75)).reshape(N, 128, 1, 1).contiguous()
+        self.ga_conv = [ConvOp(w0, g("g_a.0.bias"), c_in=[128], c_out=N, k=1, write_sq=True)]
+        for i in (2, 4):
+            self.ga_conv.append(ConvOp(g(f"g_a.{i}.weight"), g(f"g_a.{i}.bias"), c_in=[N], c_out=N, k=5, stride=2,
+                                       write_sq=True))
+        self.ga_conv.append(ConvOp(g("g_a.6.weight"), g("g_a.6.bias"), c_in=[N], c_out=M, k=5, stride=2,
+                                   out_dtype=DT_F32))
+        self.ga_gdn = []
+        for i in (1, 3, 5):
+            beta, gamma = _gdn_fold(g(f"g_a.{i}.beta"), g(f"g_a.{i}.gamma"))
+            self.ga_gdn.append(ConvOp(gamma.reshape(N, N, 1, 1), beta, c_in=[N], c_out=N, k=1, epilogue=EPI_GDN))
+        # --- synthesis
+        self.gs_conv = []
+        for i, cin in ((0, M), (2, N), (4, N)):
+            self.gs_conv.append(ConvOp(g(f"g_s.{i}.weight"), g(f"g_s.{i}.bias"), c_in=[cin], c_out=N, k=5, stride=2,
+                                       transposed=True, write_sq=True))
+        self.gs_gdn = []
+        for i in (1, 3, 5):
+            beta, gamma = _gdn_fold(g(f"g_s.{i}.beta"), g(f"g_s.{i}.gamma"))
+            self.gs_gdn.append(ConvOp(gamma.reshape(N, N, 1, 1), beta, c_in=[N], c_out=N, k=1, epilogue=EPI_IGDN))
+        # last deconv (N -> 3): the four output phases merged into one 3x3 conv with 12 (+4 pad) outputs:
+        #   x_hat[c][2i+p][2j+q] = sum_{u,v} in[i+u-1][j+v-1] . W[:, c, p+4-2u, q+4-2v]
+        wt = g("g_s.6.weight")  # (N, 3, 5, 5) ConvTranspose layout (in, out, kh, kw)
+        wm = torch.zeros((16, N, 3, 3), device=dev)
+        bm = torch.zeros(16, device=dev)
+        b6 = g("g_s.6.bias")
+        for p in range(2):
+            for q in range(2):
+                for u in range(3):
+                    r = p + 4 - 2 * u
+                    if r > 4:
+                        continue
+                    for v in range(3):
+                        s = q + 4 - 2 * v
+                        if s > 4:
+                            continue
+                        wm[(p * 2 + q) * 3:(p * 2 + q) * 3 + 3, :, u, v] = wt[:, :, r, s].t()
+                bm[(p * 2 + q) * 3:(p * 2 + q) * 3 + 3] = b6
+        self.gs_last = ConvOp(wm, bm, c_in=[N], c_out=16, k=3, out_dtype=DT_F32, direct_store=True)
+
+    # -------------------------------------------------------------------------------------------------
+    def analysis(self, x: Tensor, pad: Tuple[int, int, int, int] = (0, 0, 0, 0)) -> Tuple[Tensor, int, int]:
+        """x: (B, 3, H, W) fp32 NCHW; pad = (left, right, top, bottom) zero canvas (evalSTEM.py:96-109).
+        Returns y as NHWC fp32 (B, h, w, M) plus (h, w)."""
+        _require_cuda(x)
+        x = x.contiguous()
+        B, _, H, W = x.shape
+        left, right, top, bottom = pad
+        Hp, Wp = H + top + bottom, W + left + right
+        lib, ws, N = _lib.load(), self.ws, self.N
+        h, w = (Hp - 1) // 2 + 1, (Wp - 1) // 2 + 1
+        rows = ws.get("ga_rows", (B, h, w, 128), torch.float16)
+        _lib.check(lib.stemb200_im2col_k5s2_c3(x.data_ptr(), rows.data_ptr(), B, H, W, Hp, Wp, top, left,
+                                               _stream()), "im2col_k5s2_c3")
+        cur = rows
+        for li in range(3):
+            conv = self.ga_conv[li]
+            ho, wo = conv.out_hw(h, w) if li else (h, w)
+            xb = ws.get(f"ga_x{li}", (B, ho, wo, N), torch.float16)
+            sq = ws.get(f"ga_sq{li}", (B, ho, wo, N), torch.float16)
+            conv([cur], B, h, w, xb, out_sq=sq)
+            gb = ws.get(f"ga_g{li}", (B, ho, wo, N), torch.float16)
+            self.ga_gdn[li]([sq], B, ho, wo, gb, aux=xb)
+            cur, h, w = gb, ho, wo
+        conv = self.ga_conv[3]
+        ho, wo = conv.out_hw(h, w)
+        y = ws.get("ga_y", (B, ho, wo, self.M), torch.float32)
+        conv([cur], B, h, w, y)
+        return y, ho, wo
+
+    def synthesis(self, y_hat16: Tensor, x_ref: Optional[Tensor] = None,
+                  pad: Tuple[int, int, int, int] = (0, 0, 0, 0), sq_err: Optional[Tensor] = None,
+                  out: Optional[Tensor] = None) -> Tensor:
+        """y_hat16: (B, h, w, M) fp16 NHWC -> x_hat (B, 3, 16h, 16w) fp32 NCHW clamped to [0, 1]; when x_ref
+        (unpadded frames) is given, sq_err[b] += sum((x_ref - crop(x_hat))^2)."""
+        B, h, w, _ = y_hat16.shape
+        lib, ws, N = _lib.load(), self.ws, self.N
+        cur = y_hat16
+        for li in range(3):
+            ho, wo = 2 * h, 2 * w
+            xb = ws.get(f"gs_x{li}", (B, ho, wo, N), torch.float16)
+            sq = ws.get(f"gs_sq{li}", (B, ho, wo, N), torch.float16)
+            self.gs_conv[li]([cur], B, h, w, xb, out_sq=sq)
+            gb = ws.get(f"gs_g{li}", (B, ho, wo, N), torch.float16)
+            self.gs_gdn[li]([sq], B, ho, wo, gb, aux=xb)
+            cur, h, w = gb, ho, wo
+        merged = ws.get("gs_merged", (B, h, w, 16), torch.float32)
+        self.gs_last([cur], B, h, w, merged)
+        if out is None:
+            out = ws.get("gs_xhat", (B, 3, 2 * h, 2 * w), torch.float32)
+        left, right, top, bottom = pad
+        href = wref = 0
+        if x_ref is not None:
+            href, wref = x_ref.shape[2], x_ref.shape[3]
+        _lib.check(lib.stemb200_synthesis_tail(merged.data_ptr(), out.data_ptr(), B, h, w, _ptr(x_ref), href, wref,
+                                               top, left, _ptr(sq_err), _stream()), "synthesis_tail")
+        return out
+
+
+# ------------------------------------------------------------------------------------------------------
+# STEM entropy model
+# ------------------------------------------------------------------------------------------------------
+class StemEngine:
+    """Packed TPM / HE / HD / context_prediction / EPM + EntropyBottleneck parameters of one STEM variant."""
+
+    def __init__(self, sd: Dict[str, Tensor], device: torch.device, has_tpm: bool, has_spm: bool, residual: bool,
+                 eb_packed: Tensor, scale_table: Optional[Tensor], scale_bound: float = 0.11,
+                 lik_bound: float = 1e-9):
+        dev = device
+        g = lambda k: sd[k].detach().to(dev, torch.float32)
+        self.device = dev
+        self.ws = Workspace(dev)
+        self.has_tpm, self.has_spm, self.residual = has_tpm, has_spm, residual
+        self.scale_bound, self.lik_bound = float(scale_bound), float(lik_bound)
+        C2 = sd["HD.4.weight"].shape[0]
+        self.C = C2 // 2
+        Cc = self.C
+        self.zc = sd["HE.4.weight"].shape[0]
+        lre = 0.01  # nn.LeakyReLU() default
+        if has_tpm:
+            self.tpm = [
+                ConvOp(g("TPM.0.weight"), g("TPM.0.bias"), c_in=[Cc], c_out=256, k=5, slope=lre),
+                ConvOp(g("TPM.2.weight"), g("TPM.2.bias"), c_in=[256], c_out=320, k=5, slope=lre),
+                ConvOp(g("TPM.4.weight"), g("TPM.4.bias"), c_in=[320], c_out=C2, k=5),
+            ]
+        self.he = [
+            ConvOp(g("HE.0.weight"), g("HE.0.bias"), c_in=[Cc, Cc], c_out=256, k=3, slope=lre),
+            ConvOp(g("HE.2.weight"), g("HE.2.bias"), c_in=[256], c_out=256, k=5, stride=2, slope=lre),
+            ConvOp(g("HE.4.weight"), g("HE.4.bias"), c_in=[256], c_out=self.zc, k=5, stride=2, out_dtype=DT_F32),
+        ]
+        self.hd = [
+            ConvOp(g("HD.0.weight"), g("HD.0.bias"), c_in=[self.zc], c_out=256, k=5, stride=2, transposed=True,
+                   slope=lre),
+            ConvOp(g("HD.2.weight"), g("HD.2.bias"), c_in=[256], c_out=256, k=5, stride=2, transposed=True,
+                   slope=lre),
+            ConvOp(g("HD.4.weight"), g("HD.4.bias"), c_in=[256], c_out=C2, k=3),
+        ]
+        if has_spm:
+            # MaskedConv2d: weight * mask, only the 12 causal taps are packed (layers.py:38-47)
+            self.ctx = ConvOp(g("context_prediction.weight"), g("context_prediction.bias"), c_in=[Cc], c_out=C2, k=5,
+                              tap_mask=MASK_A_5x5)
+        n_in = [C2] * (1 + int(has_tpm) + int(has_spm))  # cat order: tp | hp | ctx (:576), hp | ctx (:301), tp | hp (:185)
+        self.epm = [
+            ConvOp(g("EPM.0.weight"), g("EPM.0.bias"), c_in=n_in, c_out=768, k=1, slope=lre),
+            ConvOp(g("EPM.2.weight"), g("EPM.2.bias"), c_in=[768], c_out=576, k=1, slope=lre),
+            ConvOp(g("EPM.4.weight"), g("EPM.4.bias"), c_in=[576], c_out=C2, k=1, out_dtype=DT_F32),
+        ]
+        self.eb_params = eb_packed.detach().to(dev, torch.float32).contiguous()
+        self.scale_table = None if scale_table is None or scale_table.numel() == 0 else \
+            scale_table.detach().to(dev, torch.float32).contiguous()
+
+    # -------------------------------------------------------------------------------------------------
+    def gaussian_params(self, y16: Tensor, cond16: Tensor, yq16: Optional[Tensor], B: int, h: int, w: int,
+                        z_hat_nchw: Optional[Tensor] = None, z_lik_nchw: Optional[Tensor] = None,
+                        bits_z: Optional[Tensor] = None) -> Tensor:
+        """HE -> EntropyBottleneck -> HD, TPM, context, EPM. Returns params NHWC fp32 (B, h, w, 2C)."""
+        lib, ws = _lib.load(), self.ws
+        f16, f32 = torch.float16, torch.float32
+        if h % 4 or w % 4:
+            raise ValueError("latent height/width must be multiples of 4 (two stride-2 stages in HE/HD)")
+        h2, w2, h4, w4 = h // 2, w // 2, h // 4, w // 4
+        # hyper encoder on cat[y_cur, y_cond]
+        t1 = self.he[0]([y16, cond16], B, h, w, ws.get("he1", (B, h, w, 256), f16))
+        t2 = self.he[1]([t1], B, h, w, ws.get("he2", (B, h2, w2, 256), f16))
+        z = self.he[2]([t2], B, h2, w2, ws.get("z", (B, h4, w4, self.zc), f32))
+        zhat16 = ws.get("zhat16", (B, h4, w4, self.zc), f16)
+        _lib.check(lib.stemb200_entropy_bottleneck_fwd(z.data_ptr(), self.eb_params.data_ptr(), B, self.zc, h4, w4,
+                                                       self.lik_bound, zhat16.data_ptr(), _ptr(z_hat_nchw),
+                                                       _ptr(z_lik_nchw), _ptr(bits_z), _stream()),
+                   "entropy_bottleneck_fwd")
+        d1 = self.hd[0]([zhat16], B, h4, w4, ws.get("hd1", (B, h2, w2, 256), f16))
+        d2 = self.hd[1]([d1], B, h2, w2, ws.get("hd2", (B, h, w, 256), f16))
+        hp = self.hd[2]([d2], B, h, w, ws.get("hp", (B, h, w, 2 * self.C), f16))
+        srcs: List[Tensor] = []
+        if self.has_tpm:
+            p1 = self.tpm[0]([cond16], B, h, w, ws.get("tp1", (B, h, w, 256), f16))
+            p2 = self.tpm[1]([p1], B, h, w, ws.get("tp2", (B, h, w, 320), f16))
+            srcs.append(self.tpm[2]([p2], B, h, w, ws.get("tp", (B, h, w, 2 * self.C), f16)))
+        srcs.append(hp)
+        if self.has_spm:
+            srcs.append(self.ctx([yq16], B, h, w, ws.get("ctx", (B, h, w, 2 * self.C), f16)))
+        e1 = self.epm[0](srcs, B, h, w, ws.get("e1", (B, h, w, 768), f16))
+        e2 = self.epm[1]([e1], B, h, w, ws.get("e2", (B, h, w, 576), f16))
+        return self.epm[2]([e2], B, h, w, ws.get("gparams", (B, h, w, 2 * self.C), f32))
+
+    def gaussian_conditional(self, y: Tensor, y_is_nchw: bool, cond16: Optional[Tensor], params: Tensor, B: int,
+                             h: int, w: int, y_hat: Optional[Tensor], lik: Optional[Tensor],
+                             idx: Optional[Tensor] = None, sym: Optional[Tensor] = None,
+                             bits: Optional[Tensor] = None) -> None:
+        if idx is not None and self.scale_table is None:
+            raise ValueError("build_indexes needs the scale table: call update() first")
+        n_scales = 0 if self.scale_table is None else self.scale_table.numel()
+        _lib.check(_lib.load().stemb200_gaussian_conditional_fwd(
+            y.data_ptr(), int(y_is_nchw), _ptr(cond16 if self.residual else None), params.data_ptr(), B, self.C, h, w,
+            _ptr(self.scale_table), n_scales, self.scale_bound, self.lik_bound, 1 if self.has_spm else 0,
+            _ptr(y_hat), _ptr(lik), _ptr(idx), _ptr(sym), _ptr(bits), _stream()), "gaussian_conditional_fwd")
+
+    # -------------------------------------------------------------------------------------------------
+    def forward_nchw(self, y_cur: Tensor, y_cond: Tensor, want_indexes: bool = False):
+        """Drop-in forward: NCHW fp32 in, NCHW fp32 out (spatiotemporalpriors.py:561-585 & variants)."""
+        _require_cuda(y_cur, y_cond)
+        y_cur = y_cur.contiguous().float()
+        y_cond = y_cond.contiguous().float()
+        B, Cc, h, w = y_cur.shape
+        if Cc != self.C or tuple(y_cond.shape) != tuple(y_cur.shape):
+            raise ValueError(f"expected two (B, {self.C}, h, w) latents, got {tuple(y_cur.shape)} / "
+                             f"{tuple(y_cond.shape)}")
+        ws, dev = self.ws, self.device
+        f16 = torch.float16
+        y16 = nchw_to_nhwc_f16(y_cur, ws.get("y16", (B, h, w, Cc), f16))
+        cond16 = nchw_to_nhwc_f16(y_cond, ws.get("cond16", (B, h, w, Cc), f16))
+        yq16 = None
+        if self.has_spm:
+            yq16 = nchw_to_nhwc_f16(y_cur, ws.get("yq16", (B, h, w, Cc), f16),
+                                    sub=y_cond if self.residual else None, round_first=True)
+        zc, h4, w4 = self.zc, h // 4, w // 4
+        z_hat = torch.empty((B, zc, h4, w4), dtype=torch.float32, device=dev)
+        z_lik = torch.empty((B, zc, h4, w4), dtype=torch.float32, device=dev)
+        bits = torch.zeros((2, B), dtype=torch.float64, device=dev)
+        params = self.gaussian_params(y16, cond16, yq16, B, h, w, z_hat, z_lik, bits[1])
+        y_hat = torch.empty_like(y_cur)
+        y_lik = torch.empty_like(y_cur)
+        idx = sym = None
+        if want_indexes:
+            idx = torch.empty(y_cur.shape, dtype=torch.int32, device=dev)
+            sym = torch.empty(y_cur.shape, dtype=torch.int32, device=dev)
+        self.gaussian_conditional(y_cur, True, cond16, params, B, h, w, y_hat, y_lik, idx, sym, bits[0])
+        return {"y_hat": y_hat, "likelihoods": {"y": y_lik, "z": z_lik}, "z_hat": z_hat, "bits": bits,
+                "indexes": idx, "symbols": sym, "params_nhwc": params}
+
+
+def pad64(h: int, w: int) -> Tuple[int, int, int, int]:
+    """(left, right, top, bottom) of evalSTEM.py:96-109."""
+    p = 64
+    nh, nw = (h + p - 1) // p * p, (w + p - 1) // p * p
+    left = (nw - w) // 2
+    top = (nh - h) // 2
+    return left, nw - w - left, top, nh - h - top
+
+
+class PFramePipeline:
+    """The evalSTEM P-frame loop body (stem/evalSTEM.py:93-154 without the entropy coder) for a whole GOP:
+    pad -> g_a -> STEM forward (+likelihoods) -> g_s -> crop/clamp -> bit and squared-error sums.
+
+    For SpatioTemporalPriorModel / _Res the frames of a GOP are processed as one batch (y_hat[t] depends on
+    frame t-1 only through an elementwise scan); the WithoutSPM* variants are serial in t.
+    """
+
+    def __init__(self, transforms: TransformsEngine, stem: StemEngine):
+        self.tr, self.stem = transforms, stem
+        self.ws = Workspace(stem.device)
+
+    def forward_gop(self, frames: Tensor, y_cond0: Tensor, want_outputs: bool = True):
+        """frames: (T, 3, H, W) fp32 NCHW CUDA (unpadded); y_cond0: (1, C, h, w) fp32 NCHW (previous decoded
+        latent). Returns dict with per-frame bits_y, bits_z, sq_err (fp64 device tensors) and, optionally,
+        x_hat / y_hat / likelihood tensors."""
+        _require_cuda(frames, y_cond0)
+        st, tr, ws = self.stem, self.tr, self.ws
+        lib = _lib.load()
+        T, _, H, W = frames.shape
+        pad = pad64(H, W)
+        y32, h, w = tr.analysis(frames, pad)  # (T, h, w, C) fp32 NHWC
+        Cc, dev = st.C, st.device
+        f16, f32 = torch.float16, torch.float32
+        yhat_all = ws.get("yhat_all", (T + 1, h, w, Cc), f16)
+        nchw_to_nhwc_f16(y_cond0.contiguous().float(), yhat_all[0:1])
+        y16 = ws.get("y16", (T, h, w, Cc), f16)
+        yq16 = ws.get("yq16", (T, h, w, Cc), f16) if st.has_spm else None
+        stats = torch.zeros((3, T), dtype=torch.float64, device=dev)  # bits_y, bits_z, sq_err
+        zc, h4, w4 = st.zc, h // 4, w // 4
+        outs = {}
+        if want_outputs:
+            outs["y_hat"] = torch.empty((T, Cc, h, w), dtype=f32, device=dev)
+            outs["lik_y"] = torch.empty((T, Cc, h, w), dtype=f32, device=dev)
+            outs["lik_z"] = torch.empty((T, zc, h4, w4), dtype=f32, device=dev)
+        per = h * w * Cc
+        if st.has_spm:
+            # y_hat scan (elementwise, serial in t only for _Res), then everything else batched over the GOP
+            if st.residual:
+                for t in range(T):
+                    _lib.check(lib.stemb200_latent_stage(y32[t].data_ptr(), yhat_all[t].data_ptr(), y16[t].data_ptr(),
+                                                         yq16[t].data_ptr(), yhat_all[t + 1].data_ptr(), per,
+                                                         _stream()), "latent_stage")
+            else:
+                _lib.check(lib.stemb200_latent_stage(y32.data_ptr(), None, y16.data_ptr(), yq16.data_ptr(),
+                                                     yhat_all[1:].data_ptr(), per * T, _stream()), "latent_stage")
+            cond16 = yhat_all[0:T]
+            params = st.gaussian_params(y16, cond16, yq16, T, h, w, None, outs.get("lik_z"), stats[1])
+            st.gaussian_conditional(y32, False, cond16, params, T, h, w, outs.get("y_hat"), outs.get("lik_y"),
+                                    bits=stats[0])
+        else:
+            # y_hat[t] = round(y - mu) + mu depends on the whole network applied to y_hat[t-1]: serial
+            _lib.check(lib.stemb200_latent_stage(y32.data_ptr(), None, y16.data_ptr(), None, None, per * T,
+                                                 _stream()), "latent_stage")
+            yh = outs.get("y_hat")
+            if yh is None:
+                yh = ws.get("yhat_nchw", (T, Cc, h, w), f32)
+            for t in range(T):
+                lz = outs["lik_z"][t:t + 1] if want_outputs else None
+                params = st.gaussian_params(y16[t:t + 1], yhat_all[t:t + 1], None, 1, h, w, None, lz,
+                                            stats[1, t:t + 1])
+                ly = outs["lik_y"][t:t + 1] if want_outputs else None
+                st.gaussian_conditional(y32[t:t + 1], False, None, params, 1, h, w, yh[t:t + 1], ly,
+                                        bits=stats[0, t:t + 1])
+                nchw_to_nhwc_f16(yh[t:t + 1], yhat_all[t + 1:t + 2])
+        x_hat = tr.synthesis(yhat_all[1:], x_ref=frames.contiguous(), pad=pad, sq_err=stats[2],
+                             out=None)
+        outs["x_hat_padded"] = x_hat
+        outs["pad"] = pad
+        outs["stats"] = stats
+        outs["num_pixels"] = H * W
+        return outs

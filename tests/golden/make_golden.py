@@ -1,0 +1,147 @@
+"""Generate tests/golden/*.npz by running the REFERENCE classes (mmSir/SpatioTemporalEntropyModel) themselves.
+
+Run in the build container only (needs /root/reference, which does not exist on the GPU box):
+
+    python tests/golden/make_golden.py
+
+It copies the reference tree to a scratch directory (the reference is read-only and its setup.py rewrites
+version.py), builds the two pybind11 extensions there, adds the missing `compressai/models/gain.py`
+(SURVEY.md §8c shim 2), imports the reference model classes, loads the seeded synthetic checkpoints of
+`spatiotemporalentropymodel_b200.synthetic` into them with their own `load_state_dict` (strict, so the key /
+shape contract is verified), and records their CPU outputs.  The fixtures pin both the oracle
+(tests/test_oracle.py) and the CUDA path (tests/test_gpu_parity.py).
+"""
+import os
+import shutil
+import subprocess
+import sys
+
+import numpy as np
+import torch
+
+REPO = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+OUT = os.path.join(REPO, "tests", "golden")
+SCRATCH = os.environ.get("STEM_REF_SCRATCH", "/tmp/stemref")
+sys.path.insert(0, REPO)
+
+
+def prepare_reference():
+    if not os.path.exists(os.path.join(SCRATCH, "compressai", "models", "gain.py")):
+        if os.path.exists(SCRATCH):
+            shutil.rmtree(SCRATCH)
+        shutil.copytree("/root/reference", SCRATCH)
+        for f in os.listdir(os.path.join(SCRATCH, "compressai")):
+            if f.endswith(".pyd"):
+                os.remove(os.path.join(SCRATCH, "compressai", f))
+        subprocess.check_call([sys.executable, "setup.py", "build_ext", "--inplace"], cwd=SCRATCH,
+                              stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        open(os.path.join(SCRATCH, "compressai", "models", "gain.py"), "w").close()
+    sys.path.insert(0, SCRATCH)
+
+
+def main():
+    prepare_reference()
+    import compressai  # noqa: F401  (the reference)
+    from compressai.entropy_models import EntropyBottleneck, GaussianConditional
+    from compressai.models import spatiotemporalpriors as ref_stem
+    from compressai.zoo import models as ref_models
+    from compressai._CXX import pmf_to_quantized_cdf as ref_pmf_to_cdf
+
+    from spatiotemporalentropymodel_b200 import synthetic as S
+
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
+    torch.manual_seed(0)
+
+    # ---------------------------------------------------------------- I-frame transforms + STEM variants
+    sd_i = S.make_iframe_state_dict(seed=0)
+    iframe = ref_models["mbt2018"](quality=4)
+    iframe.load_state_dict(sd_i)
+    iframe.update(force=True)
+    iframe.eval()
+    with torch.no_grad():
+        for variant in S.STEM_VARIANTS:
+            size = 256 if variant == "SpatioTemporalPriorModel" else 128
+            frames = S.make_frames(2, size, size, seed=1234)
+            y0, _ = iframe.getY(frames[0:1])
+            y_cond = torch.round(y0)  # stand-in for the I-frame codec's decoded latent
+            y_cur, _ = iframe.getY(frames[1:2])
+            sd_s = S.make_stem_state_dict(variant, seed=0)
+            stem = getattr(ref_stem, variant)()
+            stem.load_state_dict(sd_s)
+            stem.update(force=True)
+            stem.eval()
+            out = stem(y_cur, y_cond)
+            rec = {
+                "y_cur": y_cur.numpy(), "y_cond": y_cond.numpy(), "y_hat": out["y_hat"].numpy(),
+                "lik_y": out["likelihoods"]["y"].numpy(), "lik_z": out["likelihoods"]["z"].numpy(),
+            }
+            if variant == "SpatioTemporalPriorModel":
+                x_hat = iframe.getX(out["y_hat"])
+                rec["x_hat"] = x_hat.numpy()
+                rec["gc_quantized_cdf"] = stem.gaussian_conditional._quantized_cdf.numpy()
+                rec["gc_offset"] = stem.gaussian_conditional._offset.numpy()
+                rec["gc_cdf_length"] = stem.gaussian_conditional._cdf_length.numpy()
+                rec["eb_quantized_cdf"] = stem.entropy_bottleneck._quantized_cdf.numpy()
+                rec["eb_offset"] = stem.entropy_bottleneck._offset.numpy()
+                rec["eb_cdf_length"] = stem.entropy_bottleneck._cdf_length.numpy()
+            np.savez_compressed(os.path.join(OUT, f"stem_{variant}.npz"), **rec)
+            bits = float((-torch.log2(out["likelihoods"]["y"])).sum() + (-torch.log2(out["likelihoods"]["z"])).sum())
+            print(f"{variant}: size {size}, bpp {bits / (size * size):.4f}")
+
+    # ---------------------------------------------------------------- isolated GaussianConditional (a9)
+    table = ref_stem.get_scale_table()
+    gc = GaussianConditional(None)
+    gc.update_scale_table(table, force=True)
+    gc.eval()
+    g = torch.Generator().manual_seed(99)
+    n = 8192
+    y = 4.0 * torch.randn(n, generator=g)
+    y[:512] = torch.round(y[:512]) + 0.5                       # exact .5 ties (half-to-even)
+    mu = (torch.rand(n, generator=g) * 4 - 2)
+    mu[:256] = 0.0
+    sigma = torch.exp(torch.rand(n, generator=g) * (np.log(400.0) - np.log(0.02)) + np.log(0.02))
+    edges = torch.cat([table, torch.nextafter(table, torch.tensor(float("inf"))),
+                       torch.nextafter(table, torch.tensor(0.0))])
+    sigma[1024:1024 + edges.numel()] = edges                   # every table entry and its neighbours
+    sigma[2000:2008] = torch.tensor([0.0, -1.0, 0.11, 0.10999999, 1e-8, 256.0, 300.0, 1e4])
+    # survey KAT
+    y[3000:3008] = torch.tensor([1.7, -2.5, 0.5, 1.5, 0.04, 10.2, -0.49, 3.0])
+    mu[3000:3008] = torch.tensor([0.3, 0, 0, 0, 0, -0.7, 0.02, 2.5])
+    sigma[3000:3008] = torch.tensor([0.5, 0.05, 0.11, 1.0, 0.12, 4.0, 300, 0.1244])
+    with torch.no_grad():
+        y_hat, lik = gc(y, sigma, means=mu)
+        idx = gc.build_indexes(sigma)
+        sym = gc.quantize(y, "symbols", mu)
+    np.savez_compressed(os.path.join(OUT, "gaussian_conditional_kat.npz"), y=y.numpy(), mu=mu.numpy(),
+                        sigma=sigma.numpy(), y_hat=y_hat.numpy(), lik=lik.numpy(), idx=idx.numpy(),
+                        sym=sym.numpy(), scale_table=table.numpy())
+
+    # ---------------------------------------------------------------- EntropyBottleneck forward (a4)
+    sd_s = S.make_stem_state_dict("SpatioTemporalPriorModel", seed=0)
+    eb = EntropyBottleneck(256)
+    eb.load_state_dict({k[len("entropy_bottleneck."):]: v for k, v in sd_s.items()
+                        if k.startswith("entropy_bottleneck.") and "_offset" not in k and "_quantized_cdf" not in k
+                        and "_cdf_length" not in k}, strict=False)
+    eb.eval()
+    z = 5.0 * torch.randn((2, 256, 5, 7), generator=g)
+    with torch.no_grad():
+        z_hat, z_lik = eb(z)
+    np.savez_compressed(os.path.join(OUT, "entropy_bottleneck_kat.npz"), z=z.numpy(), z_hat=z_hat.numpy(),
+                        lik=z_lik.numpy())
+
+    # ---------------------------------------------------------------- pmf_to_quantized_cdf (ops.cpp)
+    pmfs = [[0.1, 0.2, 0.3, 0.4], [1e-9, 0.5, 0.5, 1e-9], [0.25] * 4, [1e-12] * 6 + [1.0], [0.3, 1e-7, 0.7 - 1e-7]]
+    gp = torch.Generator().manual_seed(7)
+    for _ in range(6):
+        p = torch.rand(int(torch.randint(3, 40, (1,), generator=gp)), generator=gp) ** 6
+        pmfs.append((p / p.sum()).tolist())
+    rec = {}
+    for i, p in enumerate(pmfs):
+        rec[f"pmf{i}"] = np.asarray(p, dtype=np.float32)
+        rec[f"cdf{i}"] = np.asarray(ref_pmf_to_cdf([float(np.float32(v)) for v in p], 16), dtype=np.int32)
+    np.savez_compressed(os.path.join(OUT, "pmf_to_quantized_cdf_kat.npz"), **rec)
+    print("golden fixtures written to", OUT)
+
+
+if __name__ == "__main__":
+    main()

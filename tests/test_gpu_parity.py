@@ -1,0 +1,250 @@
+"""GPU parity tests (-m gpu): the CUDA path, called through the C ABI, against the oracle and the
+reference-generated golden fixtures.
+
+Tolerances (BASELINE.json north_star): symbols / CDF indexes bit-exact given identical scales; likelihoods
+within 1e-4 relative given identical inputs; end-to-end bpp within 0.5 %, PSNR within 0.01 dB.  The dense
+layers compute with fp16 operands / fp32 accumulation, so per-layer outputs are compared with a relative-RMS
+bound (2e-3) rather than element-wise equality.
+"""
+import math
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import stem_oracle as O
+from spatiotemporalentropymodel_b200 import synthetic as S
+
+pytestmark = pytest.mark.gpu
+
+LIK_RTOL = 1e-4
+
+
+def t(a):
+    return torch.from_numpy(np.asarray(a))
+
+
+def rel_rms(a, b):
+    a, b = a.double(), b.double()
+    return float(torch.sqrt(((a - b) ** 2).mean() / (b ** 2).mean().clamp_min(1e-30)))
+
+
+def lik_close(got, ref, rtol=LIK_RTOL):
+    """relative comparison after the 1e-9 floor ("floor-aware")"""
+    err = (got.double() - ref.double()).abs() / ref.double().abs()
+    return float(err.max())
+
+
+@pytest.fixture(scope="module")
+def dev():
+    assert torch.cuda.is_available(), "these tests need a CUDA device"
+    from spatiotemporalentropymodel_b200 import _lib
+    _lib.load()  # fails loudly if libstemb200.so is missing
+    return torch.device("cuda:0")
+
+
+# ------------------------------------------------------------------------------------------- a9 isolated
+def test_gaussian_conditional_kat_bit_exact(dev, golden):
+    from spatiotemporalentropymodel_b200.engine import gaussian_conditional_flat
+    g = golden("gaussian_conditional_kat.npz")
+    y, mu, sigma = t(g["y"]).to(dev), t(g["mu"]).to(dev), t(g["sigma"]).to(dev)
+    table = t(g["scale_table"]).to(dev)
+    y_hat, lik, idx, sym, bits = gaussian_conditional_flat(y, sigma, mu, table, 0.11, 1e-9, want_idx=True,
+                                                          want_sym=True, want_bits=True)
+    assert torch.equal(idx.cpu(), t(g["idx"])), "scale-table indexes must be bit-exact"
+    assert torch.equal(sym.cpu(), t(g["sym"])), "symbols must be bit-exact"
+    assert torch.equal(y_hat.cpu(), t(g["y_hat"])), "dequantised values must be bit-exact"
+    assert lik_close(lik.cpu(), t(g["lik"])) <= LIK_RTOL
+    ref_bits = float((-torch.log2(t(g["lik"]).double())).sum())
+    assert abs(float(bits.item()) - ref_bits) / ref_bits < 1e-5
+
+
+def test_gaussian_conditional_module_api(dev, golden):
+    from spatiotemporalentropymodel_b200.entropy_models import GaussianConditional
+    from spatiotemporalentropymodel_b200.models import get_scale_table
+    g = golden("gaussian_conditional_kat.npz")
+    gc = GaussianConditional(None).eval()
+    gc.update_scale_table(get_scale_table(), force=True)
+    gc = gc.to(dev)
+    y, mu, sigma = t(g["y"]).to(dev), t(g["mu"]).to(dev), t(g["sigma"]).to(dev)
+    y_hat, lik = gc(y.view(2, 4, 32, 32), sigma.view(2, 4, 32, 32), means=mu.view(2, 4, 32, 32))
+    assert y_hat.shape == (2, 4, 32, 32)
+    assert torch.equal(y_hat.flatten().cpu(), t(g["y_hat"]))
+    assert torch.equal(gc.build_indexes(sigma).cpu(), t(g["idx"]))
+    # means=None path: round(x) exactly (compressai_tests/test_entropy_models.py:249-259)
+    out, _ = gc(y, sigma)
+    assert torch.equal(out.cpu(), torch.round(t(g["y"])))
+
+
+def test_gaussian_conditional_large_properties(dev):
+    """Full 1080p latent size: idempotence of the quantiser, index monotonicity, floor, checksum vs oracle."""
+    from spatiotemporalentropymodel_b200.engine import gaussian_conditional_flat
+    n = 192 * 68 * 120
+    g = torch.Generator().manual_seed(3)
+    y = 4 * torch.randn(n, generator=g)
+    mu = torch.rand(n, generator=g) * 4 - 2
+    sigma = torch.exp(torch.rand(n, generator=g) * 9 - 4)
+    table = O.get_scale_table()
+    yh, lik, idx, sym, bits = gaussian_conditional_flat(y.to(dev), sigma.to(dev), mu.to(dev), table.to(dev), 0.11,
+                                                        1e-9, want_idx=True, want_sym=True, want_bits=True)
+    yh2, _, _, sym2, _ = gaussian_conditional_flat(yh, sigma.to(dev), mu.to(dev), None, 0.11, 1e-9, want_sym=True)
+    assert torch.equal(yh2, yh) and torch.equal(sym2, sym)          # quantising a quantised value is a no-op
+    order = torch.argsort(sigma)
+    assert bool((idx.cpu()[order][1:] >= idx.cpu()[order][:-1]).all())  # indexes are monotone in sigma
+    assert float(lik.min()) >= 9.99e-10 and float(lik.max()) <= 1.0
+    ref_yh, ref_lik = O.gaussian_conditional_forward(y, sigma, mu)
+    assert torch.equal(yh.cpu(), ref_yh)
+    assert torch.equal(idx.cpu(), O.build_indexes(sigma, table))
+    assert int(sym.cpu().long().sum()) == int(O.quantize_symbols(y, mu).long().sum())
+    assert lik_close(lik.cpu(), ref_lik) <= LIK_RTOL
+    ref_bits = float((-torch.log2(ref_lik.double())).sum())
+    assert abs(float(bits.item()) - ref_bits) / ref_bits < 1e-5
+
+
+# ------------------------------------------------------------------------------------------- a4
+def test_entropy_bottleneck_kat(dev, golden):
+    from spatiotemporalentropymodel_b200.entropy_models import EntropyBottleneck
+    g = golden("entropy_bottleneck_kat.npz")
+    sd = S.make_stem_state_dict("SpatioTemporalPriorModel", seed=0)
+    eb = EntropyBottleneck(256)
+    eb.load_state_dict({k[len("entropy_bottleneck."):]: v for k, v in sd.items()
+                        if k.startswith("entropy_bottleneck.") and v.numel()}, strict=False)
+    eb = eb.to(dev).eval()
+    z_hat, lik = eb(t(g["z"]).to(dev))
+    assert torch.equal(z_hat.cpu(), t(g["z_hat"]))
+    assert lik_close(lik.cpu(), t(g["lik"])) <= LIK_RTOL
+
+
+# ------------------------------------------------------------------------------------------- conv layers
+CONV_CASES = [
+    # name, cin list, cout, k, stride, transposed, masked, h, w
+    ("tpm0_5x5", [192], 256, 5, 1, False, False, 16, 24),
+    ("he0_3x3_cat", [192, 192], 256, 3, 1, False, False, 16, 24),
+    ("he2_5x5_s2", [256], 256, 5, 2, False, False, 16, 24),
+    ("hd0_deconv", [256], 256, 5, 2, True, False, 7, 9),
+    ("ctx_masked", [192], 384, 5, 1, False, True, 16, 24),
+    ("epm0_1x1_cat3", [384, 384, 384], 768, 1, 1, False, False, 16, 24),
+    ("tpm2_320", [256], 320, 5, 1, False, False, 12, 20),
+]
+
+
+@pytest.mark.parametrize("case", CONV_CASES, ids=[c[0] for c in CONV_CASES])
+def test_conv_layers_vs_torch(dev, case):
+    """Each geometry of the path through stemb200_conv2d_fwd against F.conv2d / F.conv_transpose2d (fp32, CPU)
+    on fp16-representable operands: then the only difference is fp32 accumulation order."""
+    from spatiotemporalentropymodel_b200.engine import ConvOp, MASK_A_5x5, nchw_to_nhwc_f16, nhwc_f32_to_nchw
+    from spatiotemporalentropymodel_b200._lib import DT_F32
+    name, cins, cout, k, stride, transposed, masked, h, w = case
+    g = torch.Generator().manual_seed(11)
+    B, cin = 2, sum(cins)
+    x = (torch.randn((B, cin, h, w), generator=g)).half().float()
+    wshape = (cin, cout, k, k) if transposed else (cout, cin, k, k)
+    wt = (torch.randn(wshape, generator=g) / math.sqrt(cin * k * k)).half().float()
+    bias = torch.randn(cout, generator=g)
+    if masked:
+        ref = F.conv2d(x, O.masked_weight({"context_prediction.weight": wt}), bias, padding=2)
+    elif transposed:
+        ref = F.conv_transpose2d(x, wt, bias, stride=2, padding=k // 2, output_padding=1)
+    else:
+        ref = F.conv2d(x, wt, bias, stride=stride, padding=k // 2)
+    ref = F.leaky_relu(ref, 0.01)
+    op = ConvOp(wt.to(dev), bias.to(dev), c_in=cins, c_out=cout, k=k, stride=stride, transposed=transposed,
+                tap_mask=MASK_A_5x5 if masked else 0, slope=0.01, out_dtype=DT_F32)
+    srcs, c0 = [], 0
+    for c in cins:
+        xs = x[:, c0:c0 + c].contiguous().to(dev)
+        srcs.append(nchw_to_nhwc_f16(xs, torch.empty((B, h, w, c), dtype=torch.float16, device=dev)))
+        c0 += c
+    ho, wo = op.out_hw(h, w)
+    out = op(srcs, B, h, w, torch.full((B, ho, wo, cout), float("nan"), device=dev))
+    got = nhwc_f32_to_nchw(out, torch.empty((B, cout, ho, wo), device=dev)).cpu()
+    assert got.shape == ref.shape
+    assert torch.isfinite(got).all()
+    assert float((got - ref).abs().max()) < 2e-4 * max(1.0, float(ref.abs().max()))
+
+
+# ------------------------------------------------------------------------------------------- STEM forward
+@pytest.mark.parametrize("variant", S.STEM_VARIANTS)
+def test_stem_forward_vs_reference_golden(dev, golden, variant):
+    from spatiotemporalentropymodel_b200 import models as M
+    g = golden(f"stem_{variant}.npz")
+    model = getattr(M, variant)()
+    model.load_state_dict(S.make_stem_state_dict(variant, seed=0))
+    model.update(force=True)
+    model = model.to(dev).eval()
+    y_cur, y_cond = t(g["y_cur"]).to(dev), t(g["y_cond"]).to(dev)
+    out = model(y_cur, y_cond)
+    assert set(out.keys()) == {"y_hat", "likelihoods"} and set(out["likelihoods"].keys()) == {"y", "z"}
+    ref_lz, ref_ly = t(g["lik_z"]), t(g["lik_y"])
+    assert out["likelihoods"]["z"].shape == ref_lz.shape and out["likelihoods"]["y"].shape == ref_ly.shape
+    has_spm = "WithoutSPM" not in variant
+    if has_spm:
+        assert torch.equal(out["y_hat"].cpu(), t(g["y_hat"]))  # round(y [- cond]) [+ cond] is exact
+    bits = lambda l: float((-torch.log2(l.double())).sum())
+    got_bits = bits(out["likelihoods"]["y"].cpu()) + bits(out["likelihoods"]["z"].cpu())
+    ref_bits = bits(ref_ly) + bits(ref_lz)
+    assert abs(got_bits - ref_bits) / ref_bits < 5e-3, (got_bits, ref_bits)   # bpp within 0.5 %
+    # z: a flipped rounding of z changes z_hat by 1; report the mismatch rate, require it to stay rare
+    z_bits_err = abs(bits(out["likelihoods"]["z"].cpu()) - bits(ref_lz)) / bits(ref_lz)
+    assert z_bits_err < 5e-3
+
+    # given identical scales/means the entropy kernel itself is exact: feed the engine's own parameters
+    # to the oracle's GaussianConditional
+    full = model.forward_with_indexes(y_cur, y_cond)
+    params = full["params_nhwc"].permute(0, 3, 1, 2).contiguous().cpu()
+    scales, means = params.chunk(2, 1)
+    target = (t(g["y_cur"]) - t(g["y_cond"])) if variant.endswith("_Res") else t(g["y_cur"])
+    ref_yhat, ref_lik = O.gaussian_conditional_forward(target, scales, means)
+    assert lik_close(full["likelihoods"]["y"].cpu(), ref_lik) <= LIK_RTOL
+    assert torch.equal(full["indexes"].cpu(), O.build_indexes(scales))
+    assert torch.equal(full["symbols"].cpu(), O.quantize_symbols(target, means))
+    if not has_spm:
+        assert torch.equal(full["y_hat"].cpu(), ref_yhat)
+
+
+def test_transforms_vs_oracle(dev, golden):
+    from spatiotemporalentropymodel_b200 import models as M
+    g = golden("stem_SpatioTemporalPriorModel.npz")
+    net = M.models["mbt2018"](quality=4)
+    net.load_state_dict(S.make_iframe_state_dict(seed=0))
+    net = net.to(dev).eval()
+    frames = S.make_frames(2, 256, 256, seed=1234)
+    y, yq = net.getY(frames[1:2].to(dev))
+    assert rel_rms(y.cpu(), t(g["y_cur"])) < 2e-3
+    assert float((yq.cpu() != torch.round(t(g["y_cur"]))).float().mean()) < 0.02  # rounding flips stay rare
+    x_hat = net.getX(t(g["y_hat"]).to(dev))
+    ref = t(g["x_hat"])
+    assert x_hat.shape == ref.shape and float(x_hat.min()) >= 0 and float(x_hat.max()) <= 1
+    assert rel_rms(x_hat.cpu(), ref) < 2e-3
+
+
+@pytest.mark.parametrize("variant", ["SpatioTemporalPriorModel", "SpatioTemporalPriorModel_Res",
+                                     "SpatioTemporalPriorModelWithoutSPM"])
+def test_pframe_pipeline_bpp_psnr(dev, variant):
+    """End to end (pad -> g_a -> STEM -> g_s -> crop): bpp within 0.5 %, PSNR within 0.01 dB of the oracle,
+    on a GOP of 3 P-frames of a non-multiple-of-64 size (exercises the evalSTEM padding)."""
+    from spatiotemporalentropymodel_b200 import models as M
+    sd_i, sd_s = S.make_iframe_state_dict(seed=0), S.make_stem_state_dict(variant, seed=0)
+    net = M.models["mbt2018"](quality=4)
+    net.load_state_dict(sd_i)
+    stem = getattr(M, variant)()
+    stem.load_state_dict(sd_s)
+    net, stem = net.to(dev).eval(), stem.to(dev).eval()
+    H, W, T = 120, 200, 3
+    frames = S.make_frames(T, H, W, seed=77)
+    y_cond0 = S.make_latent(1, 192, 8, 16, seed=5)
+    pipe = M.make_pipeline(net, stem)
+    out = pipe.forward_gop(frames.to(dev), y_cond0.to(dev))
+    stats = out["stats"].cpu()
+    bpp = (stats[0] + stats[1]) / (H * W)
+    psnr = -10 * torch.log10(stats[2] / (3 * H * W))
+    ref = O.gop_forward(frames, y_cond0, sd_i, sd_s, variant)
+    for i in range(T):
+        rb, rp = float(ref[i]["bpp"]), float(ref[i]["psnr"])
+        assert abs(float(bpp[i]) - rb) / rb < 5e-3, (i, float(bpp[i]), rb)
+        assert abs(float(psnr[i]) - rp) < 0.01, (i, float(psnr[i]), rp)
+    l, r, tp, b = out["pad"]
+    x_hat = out["x_hat_padded"][:, :, tp:tp + H, l:l + W].cpu()
+    assert rel_rms(x_hat, torch.cat([o["x_hat"] for o in ref])) < 5e-2
+    assert out["y_hat"].shape == (T, 192, 8, 16)
