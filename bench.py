@@ -1,0 +1,403 @@
+#!/usr/bin/env python
+"""Benchmark of the STEM P-frame hot path (BASELINE.json metric: 1080p P-frames/s, STEM fwd + likelihoods).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload ...]
+
+One "step" = one GOP's worth of P-frames (default 11 = GOP 12 minus the I-frame, BASELINE.json configs[2]) through
+pad -> g_a -> STEM forward + likelihoods -> g_s -> clamp/crop -> bit and squared-error sums.  Prints ONE JSON
+line (rank 0).  `value` has the frames resident in HBM; `e2e` feeds pinned HOST frames through the same public
+call (H2D inside the timed region, per-frame bpp/PSNR sums read back).  Under torchrun every rank processes its
+own GOPs (weak scaling) and the 3 x T statistics are all-reduced over NCCL each step.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, REPO)
+
+WORKLOADS = {
+    # name: (variant, frames per step, H, W, BASELINE.json config it corresponds to)
+    "gop12_full_1080p": ("SpatioTemporalPriorModel", 11, 1080, 1920,
+                         "configs[2]: SpatioTemporalPriorModel full P-frame fwd+likelihoods, 1920x1080 GOP of 12"),
+    "gop12_res_1080p": ("SpatioTemporalPriorModel_Res", 11, 1080, 1920, "configs[3] per-GPU shape (HEVC-B-like)"),
+    "nospm_1frame_1080p": ("SpatioTemporalPriorModelWithoutSPM", 1, 1080, 1920,
+                           "configs[1]: SpatioTemporalPriorModelWithoutSPM P-frame forward, 1 frame"),
+    "smoke_256": ("SpatioTemporalPriorModel", 2, 256, 256, "configs[0]-shaped quick run"),
+}
+
+METRIC = "1080p P-frames/sec (STEM fwd+likelihoods)"
+UNIT = "frames/s"
+
+
+def algorithmic_gflop_per_frame(variant: str, H: int, W: int) -> float:
+    """2*Cin*Cout*taps*Hout*Wout per conv (deconv: Hin*Win), masked conv = 12 taps, on the
+    frame padded to a multiple of 64."""
+    Hp, Wp = (H + 63) // 64 * 64, (W + 63) // 64 * 64
+    N = 192
+    f = 0.0
+    h, w = Hp, Wp
+    chans = [3, N, N, N, N]
+    for i in range(4):  # g_a convs (+GDN 1x1)
+        h, w = h // 2, w // 2
+        f += 2 * chans[i] * N * 25 * h * w
+        if i < 3:
+            f += 2 * N * N * h * w
+    ga = f
+    gs = ga  # mirror
+    from spatiotemporalentropymodel_b200.synthetic import variant_flags
+    has_tpm, has_spm, _ = variant_flags(variant)
+    px = h * w
+    st = 0.0
+    st += 2 * 384 * 256 * 9 * px + 2 * 256 * 256 * 25 * (px / 4) + 2 * 256 * 256 * 25 * (px / 16)   # HE
+    st += 2 * 256 * 256 * 25 * (px / 16) + 2 * 256 * 256 * 25 * (px / 4) + 2 * 256 * 384 * 9 * px   # HD
+    if has_tpm:
+        st += 2 * 25 * px * (192 * 256 + 256 * 320 + 320 * 384)
+    if has_spm:
+        st += 2 * 192 * 384 * 12 * px
+    k0 = 384 * (1 + int(has_tpm) + int(has_spm))
+    st += 2 * px * (k0 * 768 + 768 * 576 + 576 * 384)
+    return (ga + st + gs) / 1e9
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            if len(r) < 6:
+                continue
+            try:
+                sm.append(float(r[0]))
+                mx = float(r[1])
+            except ValueError:
+                continue
+            for n, v in zip(names, r[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def load_peaks():
+    p = os.path.join(REPO, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": d.get("hbm_gbs"), "tf_burst": d.get("bf16_tflops"),
+                "tf_sustained": d.get("bf16_tflops_sustained"), "source": "MEASURED_PEAKS.json"}
+    return {"hbm_gbs": 6650.0, "tf_burst": 1590.0, "tf_sustained": 1400.0, "source": "B200_PROFILING.md fallback"}
+
+
+def cpu_reference_fps(variant, H, W, n_frames, threads=None):
+    """The reference's CPU path (oracle port = same torch CPU ops as the reference classes) on n_frames frames."""
+    from oracle import stem_oracle as O
+    from spatiotemporalentropymodel_b200 import synthetic as S
+    threads = threads or os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    sd_i, sd_s = S.make_iframe_state_dict(0), S.make_stem_state_dict(variant, 0)
+    frames = S.make_frames(n_frames, H, W, seed=1234)
+    hp, wp = (H + 63) // 64 * 64 // 16, (W + 63) // 64 * 64 // 16
+    y_cond = S.make_latent(1, 192, hp, wp, seed=5)
+    t0 = time.perf_counter()
+    with torch.no_grad():
+        O.gop_forward(frames, y_cond, sd_i, sd_s, variant)
+    dt = time.perf_counter() - t0
+    return n_frames / dt, dt, torch.get_num_threads()
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path, all host threads, bounded sample."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    variant, T, H, W, desc = WORKLOADS[args.workload]
+    from oracle import stem_oracle as O
+    from spatiotemporalentropymodel_b200 import synthetic as S
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    sd_i, sd_s = S.make_iframe_state_dict(0), S.make_stem_state_dict(variant, 0)
+    frames = S.make_frames(2, H, W, seed=1234)
+    hp, wp = (H + 63) // 64 * 64 // 16, (W + 63) // 64 * 64 // 16
+    y_cond = S.make_latent(1, 192, hp, wp, seed=5)
+    times = []
+    with torch.no_grad():
+        for i in range(args.warmup + args.steps):
+            t0 = time.perf_counter()
+            O.pframe_forward(frames[i % 2:i % 2 + 1], y_cond, sd_i, sd_s, variant)  # one step = ONE frame
+            if i >= args.warmup:
+                times.append(time.perf_counter() - t0)
+    total = sum(times)
+    fps = len(times) / total
+    line = {
+        "impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": args.workload, "desc": desc, "variant": variant, "height": H, "width": W,
+                   "frames_per_step": 1, "note": "CPU: each step is ONE 1080p P-frame (bounded sample of the GOP)"},
+        "cpu_baseline": {"value": fps, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+                         "sample": f"{len(times)} single P-frames, torch CPU fp32 oracle port of the reference path"},
+        "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="gop12_full_1080p", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-graph", action="store_true", help="do not capture the step in a CUDA graph")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-frames", type=int, default=2)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    import torch.distributed as dist
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    from spatiotemporalentropymodel_b200 import _lib, models as M, synthetic as S
+    from spatiotemporalentropymodel_b200.dist import reduce_stats
+
+    variant, T, H, W, desc = WORKLOADS[args.workload]
+    sd_i, sd_s = S.make_iframe_state_dict(0), S.make_stem_state_dict(variant, 0)
+    net = M.models["mbt2018"](quality=4)
+    net.load_state_dict(sd_i)
+    stem = getattr(M, variant)()
+    stem.load_state_dict(sd_s)
+    stem.update(force=True)
+    net, stem = net.to(dev).eval(), stem.to(dev).eval()
+    pipe = M.make_pipeline(net, stem)
+
+    # every rank gets its own GOP (different seed): weak scaling over independent GOPs
+    frames_host = S.make_frames(T, H, W, seed=1234 + rank).pin_memory()
+    hp, wp = (H + 63) // 64 * 64 // 16, (W + 63) // 64 * 64 // 16
+    y_cond0 = S.make_latent(1, 192, hp, wp, seed=5 + rank).to(dev)
+    frames_dev = frames_host.to(dev)
+
+    def step_resident():
+        out = pipe.forward_gop(frames_dev, y_cond0, want_outputs=True)
+        return out["stats"]
+
+    # ---------------------------------------------------------------- device-resident timing ("value")
+    for _ in range(args.warmup):
+        stats = step_resident()
+        if world > 1:
+            reduce_stats(stats)
+    torch.cuda.synchronize()
+    graph = None
+    if not args.no_graph:
+        try:
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                g_stats = step_resident()
+            graph.replay()
+            torch.cuda.synchronize()
+        except Exception as e:  # graph capture is an optimisation, not a requirement
+            if rank == 0:
+                print(f"[bench] CUDA graph capture failed ({type(e).__name__}: {e}); timing eager launches",
+                      file=sys.stderr)
+            graph = None
+            torch.cuda.synchronize()
+
+    def run_step():
+        if graph is not None:
+            graph.replay()
+            return g_stats
+        return step_resident()
+
+    for _ in range(2):
+        run_step()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local_rank)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    if rank == 0:
+        sampler.start()
+    n0 = _lib.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(args.steps):
+        stats = run_step()
+        if world > 1:
+            reduce_stats(stats)
+    ev1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    ms_total = ev0.elapsed_time(ev1)
+    clocks = sampler.stop() if rank == 0 else None
+    launches_timed = _lib.launch_count() - n0
+    if graph is not None:
+        # a replayed graph re-issues the kernels captured once: count them from an eager step
+        n1 = _lib.launch_count()
+        step_resident()
+        torch.cuda.synchronize()
+        launches_timed = (_lib.launch_count() - n1) * args.steps
+    tmax = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    ms_total = float(tmax.item())
+    ms_per_step = ms_total / args.steps
+    value = world * T * args.steps / (ms_total / 1e3)
+
+    # ---------------------------------------------------------------- end-to-end: pinned host frames in, stats out
+    copy_stream = torch.cuda.Stream(device=dev)
+    bufs = [torch.empty_like(frames_dev), torch.empty_like(frames_dev)]
+    host_stats = torch.empty((3, T), dtype=torch.float64).pin_memory()
+
+    def e2e_loop(n):
+        """double-buffered: the H2D copy of step i+1 overlaps the kernels of step i"""
+        ready = [torch.cuda.Event(), torch.cuda.Event()]
+        done = [torch.cuda.Event(), torch.cuda.Event()]
+        with torch.cuda.stream(copy_stream):
+            bufs[0].copy_(frames_host, non_blocking=True)
+            ready[0].record(copy_stream)
+        for i in range(n):
+            b = i & 1
+            if i + 1 < n:
+                with torch.cuda.stream(copy_stream):
+                    copy_stream.wait_event(done[b ^ 1]) if i >= 1 else None
+                    bufs[b ^ 1].copy_(frames_host, non_blocking=True)
+                    ready[b ^ 1].record(copy_stream)
+            torch.cuda.current_stream().wait_event(ready[b])
+            out = pipe.forward_gop(bufs[b], y_cond0, want_outputs=True)
+            st = out["stats"]
+            if world > 1:
+                reduce_stats(st)
+            host_stats.copy_(st, non_blocking=True)
+            done[b].record()
+        torch.cuda.synchronize()
+
+    e2e_loop(3)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    e2e_loop(args.steps)
+    e1.record()
+    torch.cuda.synchronize()
+    e2e_ms = max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3)
+    te = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = world * T * args.steps / (float(te.item()) / 1e3)
+
+    # ---------------------------------------------------------------- roofline of the dominant kernel
+    peaks = load_peaks()
+    roofline = None
+    if rank == 0:
+        from spatiotemporalentropymodel_b200 import engine as E
+        recs = []
+        orig = E.ConvOp.__call__
+
+        def timed_call(self, inputs, batch, h, w, out, aux=None, out_sq=None):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            r = orig(self, inputs, batch, h, w, out, aux, out_sq)
+            b.record()
+            recs.append((a, b))
+            return r
+
+        E.ConvOp.__call__ = timed_call
+        try:
+            for _ in range(2):
+                recs.clear()
+                step_resident()
+                torch.cuda.synchronize()
+        finally:
+            E.ConvOp.__call__ = orig
+        conv_ms = sum(a.elapsed_time(b) for a, b in recs)
+        gflop_step = algorithmic_gflop_per_frame(variant, H, W) * T
+        achieved = gflop_step / conv_ms  # GFLOP/ms == TFLOP/s
+        peak = peaks["tf_sustained"]
+        roofline = {"bound": "tensor", "kernel": "stem::conv_igemm_kernel<BLOCK_N> (all dense contractions of the step)",
+                    "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                    "peak_kind": f"bf16 dense sustained, {peaks['source']}", "traffic": None,
+                    "launches_per_step": len(recs), "kernel_ms_per_step": conv_ms,
+                    "algorithmic_gflop_per_step": gflop_step,
+                    "kernel_share_of_step": conv_ms / ms_per_step}
+
+    # ---------------------------------------------------------------- CPU baseline (rank 0, N == 1 only)
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        fps, dt, cores = cpu_reference_fps(variant, H, W, args.cpu_frames)
+        cpu = {"value": fps, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": f"{args.cpu_frames} P-frames of the same workload ({dt:.1f} s), torch CPU fp32 oracle port"}
+
+    if rank == 0:
+        h2d = frames_host.numel() * 4
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f16 operands / f32 accumulate (tcgen05 kind::f16); entropy kernels f32",
+            "data": "synthetic",
+            "config": {"workload": args.workload, "desc": desc, "variant": variant, "height": H, "width": W,
+                       "frames_per_step": T, "per_gpu_frames_per_step": T, "cuda_graph": graph is not None,
+                       "l2": "per-step working set (several GB of activations) exceeds the 126 MB L2; no flush needed",
+                       "checkpoint": "seeded synthetic (spatiotemporalentropymodel_b200.synthetic)"},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": host_stats.numel() * 8},
+            "gpu_launches": launches_timed,
+            "roofline": roofline,
+            "cpu_baseline": cpu,
+            "algorithmic_gflop_per_frame": algorithmic_gflop_per_frame(variant, H, W),
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

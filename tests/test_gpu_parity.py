@@ -30,10 +30,19 @@ def rel_rms(a, b):
     return float(torch.sqrt(((a - b) ** 2).mean() / (b ** 2).mean().clamp_min(1e-30)))
 
 
-def lik_close(got, ref, rtol=LIK_RTOL):
-    """relative comparison after the 1e-9 floor ("floor-aware")"""
-    err = (got.double() - ref.double()).abs() / ref.double().abs()
-    return float(err.max())
+def lik_close(got, ref, sigma=None):
+    """Max relative error after the 1e-9 floor ("floor-aware"), over the elements whose scale lies
+    inside the reference's scale table (sigma <= 256).  Beyond the table the reference's own fp32 formula
+    (difference of two erfc values near 1/2, entropy_models.py:583-585) is only accurate to ~5e-4 relative
+    (1 ulp of 0.5 against a likelihood ~ 1/(sigma*sqrt(2*pi))), and torch's CPU erfc is not even the same routine
+    for the vectorised body and the scalar tail of one tensor, so there the bound is absolute: 4 ulp(0.5)."""
+    got, ref = got.double().flatten(), ref.double().flatten()
+    err = (got - ref).abs()
+    if sigma is None:
+        return float((err / ref.abs()).max())
+    inside = sigma.flatten().double() <= 256.0
+    assert float(err[~inside].max() if (~inside).any() else 0.0) <= 2.4e-7
+    return float((err[inside] / ref[inside].abs()).max())
 
 
 @pytest.fixture(scope="module")
@@ -55,7 +64,7 @@ def test_gaussian_conditional_kat_bit_exact(dev, golden):
     assert torch.equal(idx.cpu(), t(g["idx"])), "scale-table indexes must be bit-exact"
     assert torch.equal(sym.cpu(), t(g["sym"])), "symbols must be bit-exact"
     assert torch.equal(y_hat.cpu(), t(g["y_hat"])), "dequantised values must be bit-exact"
-    assert lik_close(lik.cpu(), t(g["lik"])) <= LIK_RTOL
+    assert lik_close(lik.cpu(), t(g["lik"]), t(g["sigma"])) <= LIK_RTOL
     ref_bits = float((-torch.log2(t(g["lik"]).double())).sum())
     assert abs(float(bits.item()) - ref_bits) / ref_bits < 1e-5
 
@@ -97,7 +106,7 @@ def test_gaussian_conditional_large_properties(dev):
     assert torch.equal(yh.cpu(), ref_yh)
     assert torch.equal(idx.cpu(), O.build_indexes(sigma, table))
     assert int(sym.cpu().long().sum()) == int(O.quantize_symbols(y, mu).long().sum())
-    assert lik_close(lik.cpu(), ref_lik) <= LIK_RTOL
+    assert lik_close(lik.cpu(), ref_lik, sigma) <= LIK_RTOL
     ref_bits = float((-torch.log2(ref_lik.double())).sum())
     assert abs(float(bits.item()) - ref_bits) / ref_bits < 1e-5
 
@@ -196,7 +205,7 @@ def test_stem_forward_vs_reference_golden(dev, golden, variant):
     scales, means = params.chunk(2, 1)
     target = (t(g["y_cur"]) - t(g["y_cond"])) if variant.endswith("_Res") else t(g["y_cur"])
     ref_yhat, ref_lik = O.gaussian_conditional_forward(target, scales, means)
-    assert lik_close(full["likelihoods"]["y"].cpu(), ref_lik) <= LIK_RTOL
+    assert lik_close(full["likelihoods"]["y"].cpu(), ref_lik, scales) <= LIK_RTOL
     assert torch.equal(full["indexes"].cpu(), O.build_indexes(scales))
     assert torch.equal(full["symbols"].cpu(), O.quantize_symbols(target, means))
     if not has_spm:
