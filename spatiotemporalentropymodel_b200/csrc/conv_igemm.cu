@@ -68,7 +68,7 @@ struct ConvCfg {
   static constexpr int kStageBytes = kAStageBytes + kBStageBytes;
   static constexpr bool kSqAllowed = BLOCK_N <= 192;
   static constexpr int kNumOutBufs = kSqAllowed ? 4 : 2;
-  static constexpr int kBarrierBytes = 256;
+  static constexpr int kBarrierBytes = 256 + BLOCK_N * 4;  // mbarriers + TMEM slot, then the tile's bias slice
   static constexpr int kFree = kSmemLimit - 1024 - kNumOutBufs * kOutStageBytes - kBarrierBytes;
   static constexpr int kStagesRaw = kFree / kStageBytes;
   static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
@@ -125,6 +125,7 @@ conv_igemm_kernel(const __grid_constant__ ConvKernelParams p) {
   auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * kStages + a); };
   auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * kStages + 2 + a); };
   const uint32_t tmem_slot = bar_base + 8u * (2 * kStages + 4);
+  const uint32_t bias_smem = bar_base + 256u;  // BLOCK_N floats: bias (or GDN beta) of the current N tile
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -239,6 +240,29 @@ conv_igemm_kernel(const __grid_constant__ ConvKernelParams p) {
           (static_cast<long long>(t.n_img) * p.full_h + (oh * p.os + p.sub_p[t.sub])) * p.full_w +
           (ow * p.os + p.sub_q[t.sub]);
 
+      // stage this tile's bias slice in smem (global loads per column were the epilogue's critical path:
+      // ~200 cycles of exposed latency each, see profiles/r01_ncu_gdn_epilogue.txt)
+      named_bar_sync(1, 128);  // every thread is done with the previous tile's slice
+      for (int i = etid; i < BLOCK_N; i += 128) {
+        const float b = __ldg(p.bias + t.n0 + i);
+        asm volatile("st.shared.f32 [%0], %1;" ::"r"(bias_smem + 4u * i), "f"(b) : "memory");
+      }
+      named_bar_sync(1, 128);
+      // GDN: prefetch the first aux chunk while waiting for the accumulator
+      constexpr int kColsPre = (BLOCK_N >= 32) ? 32 : 16;
+      uint4 aux_nxt[kColsPre / 8];
+      const bool is_gdn = p.epilogue != STEMB200_EPI_LINEAR;
+      if (is_gdn) {
+        if (inb) {
+          const uint4* ap = reinterpret_cast<const uint4*>(p.aux + pix * p.c_out + t.n0);
+#pragma unroll
+          for (int j = 0; j < kColsPre / 8; ++j) aux_nxt[j] = __ldg(ap + j);
+        } else {
+#pragma unroll
+          for (int j = 0; j < kColsPre / 8; ++j) aux_nxt[j] = make_uint4(0, 0, 0, 0);
+        }
+      }
+
       mbar_wait(tfull_bar(acc), accph);
       tc_fence_after();
       const uint32_t t_row = tmem_base + acc * BLOCK_N + (static_cast<uint32_t>(ew * 32) << 16);
@@ -259,29 +283,36 @@ conv_igemm_kernel(const __grid_constant__ ConvKernelParams p) {
           for (int i = 0; i < kCols; ++i) v[i] = __uint_as_float(r[i]);
         }
         const int ch0 = t.n0 + c;
-        if (p.epilogue == STEMB200_EPI_LINEAR) {
+        float bs[kCols];
+#pragma unroll
+        for (int j = 0; j < kCols / 4; ++j) {
+          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                       : "=f"(bs[4 * j]), "=f"(bs[4 * j + 1]), "=f"(bs[4 * j + 2]), "=f"(bs[4 * j + 3])
+                       : "r"(bias_smem + 4u * (c + 4 * j)));
+        }
+        if (!is_gdn) {
 #pragma unroll
           for (int i = 0; i < kCols; ++i) {
-            float x = v[i] + __ldg(p.bias + ch0 + i);
+            float x = v[i] + bs[i];
             v[i] = x > 0.f ? x : x * p.slope;
           }
         } else {
-          // GDN / IGDN: aux * (r)sqrt(beta + acc / sq_scale^2)
+          // GDN / IGDN: aux * (r)sqrt(beta + acc / sq_scale^2); the next chunk's aux is prefetched
           uint4 a4[kCols / 8];
-          if (inb) {
-            const uint4* ap = reinterpret_cast<const uint4*>(p.aux + pix * p.c_out + ch0);
 #pragma unroll
-            for (int j = 0; j < kCols / 8; ++j) a4[j] = __ldg(ap + j);
-          } else {
+          for (int j = 0; j < kCols / 8; ++j) a4[j] = aux_nxt[j];
+          if (c + kCols < BLOCK_N && inb) {
+            const uint4* ap = reinterpret_cast<const uint4*>(p.aux + pix * p.c_out + ch0 + kCols);
 #pragma unroll
-            for (int j = 0; j < kCols / 8; ++j) a4[j] = make_uint4(0, 0, 0, 0);
+            for (int j = 0; j < kCols / 8; ++j) aux_nxt[j] = __ldg(ap + j);
           }
-          const __half* ah = reinterpret_cast<const __half*>(a4);
 #pragma unroll
           for (int i = 0; i < kCols; ++i) {
-            float nrm = fmaf(v[i], p.sq_inv, __ldg(p.bias + ch0 + i));
+            const uint32_t w = reinterpret_cast<const uint32_t*>(a4)[i >> 1];
+            const __half ah = __ushort_as_half(static_cast<unsigned short>((i & 1) ? (w >> 16) : (w & 0xFFFFu)));
+            float nrm = fmaf(v[i], p.sq_inv, bs[i]);
             float f = (p.epilogue == STEMB200_EPI_GDN) ? rsqrtf(nrm) : sqrtf(nrm);
-            v[i] = __half2float(ah[i]) * f;
+            v[i] = __half2float(ah) * f;
           }
         }
 
