@@ -132,3 +132,22 @@ def test_product_package_never_imports_oracle():
             if f.endswith(".py"):
                 src = open(os.path.join(root, f)).read()
                 assert "import oracle" not in src and "from oracle" not in src, f
+
+
+def test_compat_aliases_compressai_imports():
+    """The imports stem/evalSTEM.py:23-24 performs resolve to the B200 classes after compat.install()."""
+    import subprocess
+    import sys
+    code = (
+        "import sys; sys.path.insert(0, %r)\n"
+        "from spatiotemporalentropymodel_b200 import compat, models as M\n"
+        "compat.install()\n"
+        "import compressai\n"
+        "from compressai.zoo import models\n"
+        "from compressai.models.spatiotemporalpriors import *\n"
+        "assert SpatioTemporalPriorModel_Res is M.SpatioTemporalPriorModel_Res\n"
+        "assert models['mbt2018'] is M.mbt2018\n"
+        "assert 'ans' in compressai.available_entropy_coders(); compressai.set_entropy_coder('ans')\n"
+        "print('ok')\n" % REPO)
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and "ok" in out.stdout, out.stderr
