@@ -341,10 +341,10 @@ def main():
         recs = []
         orig = E.ConvOp.__call__
 
-        def timed_call(self, inputs, batch, h, w, out, aux=None, out_sq=None):
+        def timed_call(self, inputs, batch, h, w, out):
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record()
-            r = orig(self, inputs, batch, h, w, out, aux, out_sq)
+            r = orig(self, inputs, batch, h, w, out)
             b.record()
             recs.append((a, b))
             return r
@@ -361,7 +361,7 @@ def main():
         gflop_step = algorithmic_gflop_per_frame(variant, H, W) * T
         achieved = gflop_step / conv_ms  # GFLOP/ms == TFLOP/s
         peak = peaks["tf_sustained"]
-        roofline = {"bound": "tensor", "kernel": "stem::conv_igemm_kernel<BLOCK_N> (all dense contractions of the step)",
+        roofline = {"bound": "tensor", "kernel": "stem::conv_igemm_kernel<BLOCK_N> + stem::conv_gdn_kernel (all dense contractions of the step)",
                     "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                     "peak_kind": f"bf16 dense sustained, {peaks['source']}", "traffic": None,
                     "launches_per_step": len(recs), "kernel_ms_per_step": conv_ms,

@@ -31,11 +31,6 @@ extern "C" {
 #define STEMB200_DT_F16 0 /* IEEE half operands, fp32 accumulate (tcgen05 kind::f16) */
 #define STEMB200_DT_F32 1 /* fp32 storage (epilogue outputs that feed quantisation) */
 
-/* epilogue selectors for stemb200_conv2d_fwd */
-#define STEMB200_EPI_LINEAR 0 /* out = acc + bias, then LeakyReLU(slope) (slope = 1 -> identity) */
-#define STEMB200_EPI_GDN 1    /* out = aux * rsqrt(bias + sq_scale_inv * acc)   (GDN,  gdn.py:52-67) */
-#define STEMB200_EPI_IGDN 2   /* out = aux * sqrt (bias + sq_scale_inv * acc)   (IGDN, gdn.py:60-61) */
-
 const char* stemb200_version(void);
 const char* stemb200_last_error(void);
 /* number of kernels this library has launched since process start (bench.py: gpu_launches) */
@@ -58,12 +53,10 @@ typedef struct stemb200_conv_desc {
   int32_t stride;       /* 1 or 2 */
   int32_t transposed;   /* 1: ConvTranspose2d(k, stride 2, padding k/2, output_padding 1) */
   uint32_t tap_mask;    /* bit (r*kw+s) set = tap used; 0 = all taps (mask 'A' 5x5 = 0x00000FFF) */
-  int32_t epilogue;     /* STEMB200_EPI_* */
-  float lrelu_slope;    /* EPI_LINEAR: negative slope, 1.0f = no activation */
+  float lrelu_slope;    /* out = LeakyReLU(acc + bias, slope); 1.0f = no activation */
   int32_t out_dtype;    /* STEMB200_DT_F16 or STEMB200_DT_F32 (NHWC) */
-  int32_t write_sq;     /* 1: also write out_sq = (sq_scale * out)^2 as fp16 (input of the GDN contraction) */
-  float sq_scale;       /* prescale before squaring (keeps x^2 inside fp16 range); epilogue GDN multiplies
-                           acc by 1/sq_scale^2 */
+  float sq_scale;       /* conv2d_gdn_fwd only: x is prescaled by this before squaring so that x^2 stays inside
+                           the fp16 range; the normaliser is rescaled by 1/sq_scale^2 */
   int32_t tile_h, tile_w; /* output patch per 128-row MMA tile, tile_h*tile_w <= 128; 0 = choose */
   int32_t direct_store; /* 1: epilogue stores straight from registers (debug / c_out < 32) */
 } stemb200_conv_desc;
@@ -74,11 +67,19 @@ int64_t stemb200_conv2d_packed_k(const stemb200_conv_desc* d);
  * device, into the K-major fp16 matrix the kernel's TMA descriptor expects. Masked taps are dropped. */
 int stemb200_conv2d_pack_weight(const stemb200_conv_desc* d, const float* weight_f32, void* packed_f16,
                                 void* stream);
-/* in[s]: NHWC fp16 [batch][h_in][w_in][c_in[s]]; out: NHWC [batch][h_out][w_out][c_out];
- * bias: fp32 [c_out] (EPI_GDN/IGDN: beta); aux: NHWC fp16 like out (EPI_GDN/IGDN multiplicand) or NULL;
- * out_sq: NHWC fp16 like out or NULL. */
+/* in[s]: NHWC fp16 [batch][h_in][w_in][c_in[s]]; out: NHWC [batch][h_out][w_out][c_out]; bias: fp32 [c_out]. */
 int stemb200_conv2d_fwd(const stemb200_conv_desc* d, const void* const* in, const void* packed_weight,
-                        const float* bias, const void* aux, void* out, void* out_sq, void* stream);
+                        const float* bias, void* out, void* stream);
+
+/* Convolution / transposed convolution with GDN (inverse = 0) or IGDN (inverse = 1) fused into the epilogue:
+ *   x = conv(in) + bias;  out = x * rsqrt(beta + gamma . x^2)   |   x * sqrt(beta + gamma . x^2)
+ * (priors.py:421-439 conv/deconv followed by layers/gdn.py:52-67). c_out must be 192; packed_gamma is the
+ * [c_out][c_out] matrix produced by stemb200_conv2d_pack_weight for a 1x1 conv of the *re-parametrised* gamma
+ * (ops/parametrizers.py:42-45), beta the re-parametrised beta (fp32). d->sq_scale prescales x before squaring
+ * (fp16 range); out is NHWC fp16. x and x^2 never leave the SM. */
+int stemb200_conv2d_gdn_fwd(const stemb200_conv_desc* d, const void* const* in, const void* packed_weight,
+                            const float* bias, const void* packed_gamma, const float* beta, int32_t inverse,
+                            void* out, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------
  * Layout / staging kernels at the API boundary

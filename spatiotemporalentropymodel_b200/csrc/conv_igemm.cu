@@ -12,7 +12,7 @@
 // * torch.cat(..., 1) inputs are K-segments: the K loop walks (tap, source, 64-channel chunk) triples listed
 //   in a table carried in the kernel parameters.
 // * accumulators live in TMEM (double buffered, 2 x BLOCK_N columns), MMAs are issued by one thread,
-//   the epilogue (4 warps) overlaps the next tile's main loop; persistent CTAs, one per SM.
+//   the epilogue (8 warps) overlaps the next tile's main loop; persistent CTAs, one per SM.
 //
 // Reference call sites this replaces: compressai/models/utils.py:112-130, spatiotemporalpriors.py:523-554,
 // layers/layers.py:44-47, layers/gdn.py:52-67 (F.conv2d(x**2, gamma, beta) + rsqrt/sqrt + multiply).
@@ -37,14 +37,14 @@ constexpr int kMaxKSteps = 256;
 constexpr int kKChunk = 64;         // fp16 elements per 128-byte swizzle row
 constexpr int kAStageBytes = 128 * 128;
 constexpr int kOutStageBytes = 128 * 128;
-constexpr int kNumThreads = 256;
+constexpr int kNumThreads = 384;     // 4 control warps (TMA, MMA, TMEM alloc, spare) + 8 epilogue warps
+constexpr int kNumEpiThreads = 256;
 constexpr int kSmemLimit = 232448;  // 227 KB
 
 struct ConvKernelParams {
   alignas(64) CUtensorMap a_map[4];
   alignas(64) CUtensorMap b_map;
   alignas(64) CUtensorMap out_map[4];
-  alignas(64) CUtensorMap sq_map[4];
   uint32_t ksteps[kMaxKSteps];  // [1:0] map | [5:2] dh+8 | [9:6] dw+8 | [31:10] channel offset
   int sub_kbeg[4], sub_kend[4];
   int sub_p[4], sub_q[4];
@@ -53,21 +53,22 @@ struct ConvKernelParams {
   int tile_h, tile_w, tiles_h, tiles_w;
   int n_tiles_n, total_tiles;
   int c_out;
-  int epilogue;
   float slope, sq_scale, sq_inv;
-  int out_f32, write_sq, direct;
+  int out_f32, direct;
   int os, full_h, full_w;  // output phase stride and full output size (direct store / aux addressing)
   const float* bias;
-  const __half* aux;
   void* out;
+  // fused GDN / IGDN (conv_gdn_kernel only)
+  alignas(64) CUtensorMap g_map;  // gamma [c_out][c_out] fp16, K-major
+  const float* beta;
+  int igdn;
 };
 
 template <int BLOCK_N>
 struct ConvCfg {
   static constexpr int kBStageBytes = BLOCK_N * 128;
   static constexpr int kStageBytes = kAStageBytes + kBStageBytes;
-  static constexpr bool kSqAllowed = BLOCK_N <= 192;
-  static constexpr int kNumOutBufs = kSqAllowed ? 4 : 2;
+  static constexpr int kNumOutBufs = 2;
   static constexpr int kBarrierBytes = 256 + BLOCK_N * 4;  // mbarriers + TMEM slot, then the tile's bias slice
   static constexpr int kFree = kSmemLimit - 1024 - kNumOutBufs * kOutStageBytes - kBarrierBytes;
   static constexpr int kStagesRaw = kFree / kStageBytes;
@@ -103,6 +104,18 @@ __device__ __forceinline__ TileCoord decode_tile(const ConvKernelParams& p, int 
   return t;
 }
 
+// single-MUFU reciprocal square root / square root (rel. error ~2^-22; the result is rounded to fp16 anyway)
+__device__ __forceinline__ float approx_rsqrt(float x) {
+  float y;
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float approx_sqrt(float x) {
+  float y;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 __device__ __forceinline__ uint32_t pack_half2(float a, float b) {
   __half2 h = __floats2half2_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&h);
@@ -135,8 +148,6 @@ conv_igemm_kernel(const __grid_constant__ ConvKernelParams p) {
     tma_prefetch_desc(&p.b_map);
     if (!p.direct) {
       for (int i = 0; i < p.n_sub; ++i) tma_prefetch_desc(&p.out_map[i]);
-      if (p.write_sq)
-        for (int i = 0; i < p.n_sub; ++i) tma_prefetch_desc(&p.sq_map[i]);
     }
   }
   if (warp == 1 && lane == 0) {
@@ -146,7 +157,7 @@ conv_igemm_kernel(const __grid_constant__ ConvKernelParams p) {
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), 4);  // one arrival per epilogue warp
+      mbar_init(tempty_bar(a), 8);  // one arrival per epilogue warp
     }
     fence_barrier_init();
   }
@@ -222,11 +233,16 @@ conv_igemm_kernel(const __grid_constant__ ConvKernelParams p) {
     }
   } else if (warp >= 4) {
     // ===================== epilogue (TMEM -> registers -> smem -> TMA store) =====================
-    const int ew = warp - 4;            // == warp % 4: TMEM lane group
-    const int etid = threadIdx.x - 128;  // 0..127 == accumulator row
-    const int row = etid;
+    // 8 warps: warp w reads TMEM lane group w % 4; warps 4-7 take the even 32-column chunks, warps 8-11 the odd
+    // ones, so two warps per scheduler hide each other's dependency stalls (one warp per scheduler ran at
+    // ~0.2 IPC, profiles/r01_ncu_gdn_fused_epilogue.txt).
+    const int ew = warp & 3;
+    const int etid = threadIdx.x - 128;  // 0..255
+    const int row = etid & 127;          // accumulator row == pixel of the patch
+    const int half = etid >> 7;          // which 32-column chunk of each 64-column group
     const int npix = p.tile_h * p.tile_w;
-    uint32_t chunk_ctr = 0;
+    const uint32_t rsw = static_cast<uint32_t>(row & 7);
+    uint32_t group_ctr = 0;
     int it = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
       const TileCoord t = decode_tile(p, tile, BLOCK_N);
@@ -235,41 +251,29 @@ conv_igemm_kernel(const __grid_constant__ ConvKernelParams p) {
       const int th = row / p.tile_w, tw = row - th * p.tile_w;
       const int oh = t.h0 + th, ow = t.w0 + tw;
       const bool inb = (row < npix) && (oh < p.h_out) && (ow < p.w_out);
-      // flat pixel index in the full-resolution output (direct store / aux)
+      // flat pixel index in the full-resolution output (direct store)
       const long long pix =
           (static_cast<long long>(t.n_img) * p.full_h + (oh * p.os + p.sub_p[t.sub])) * p.full_w +
           (ow * p.os + p.sub_q[t.sub]);
 
-      // stage this tile's bias slice in smem (global loads per column were the epilogue's critical path:
-      // ~200 cycles of exposed latency each, see profiles/r01_ncu_gdn_epilogue.txt)
-      named_bar_sync(1, 128);  // every thread is done with the previous tile's slice
-      for (int i = etid; i < BLOCK_N; i += 128) {
+      // stage this tile's bias slice in smem (a global load per column used to be the epilogue's critical
+      // path: ~200 cycles of exposed latency each, profiles/r01_ncu_gdn_epilogue.txt)
+      named_bar_sync(1, kNumEpiThreads);  // every thread is done with the previous tile's slice
+      for (int i = etid; i < BLOCK_N; i += kNumEpiThreads) {
         const float b = __ldg(p.bias + t.n0 + i);
         asm volatile("st.shared.f32 [%0], %1;" ::"r"(bias_smem + 4u * i), "f"(b) : "memory");
       }
-      named_bar_sync(1, 128);
-      // GDN: prefetch the first aux chunk while waiting for the accumulator
-      constexpr int kColsPre = (BLOCK_N >= 32) ? 32 : 16;
-      uint4 aux_nxt[kColsPre / 8];
-      const bool is_gdn = p.epilogue != STEMB200_EPI_LINEAR;
-      if (is_gdn) {
-        if (inb) {
-          const uint4* ap = reinterpret_cast<const uint4*>(p.aux + pix * p.c_out + t.n0);
-#pragma unroll
-          for (int j = 0; j < kColsPre / 8; ++j) aux_nxt[j] = __ldg(ap + j);
-        } else {
-#pragma unroll
-          for (int j = 0; j < kColsPre / 8; ++j) aux_nxt[j] = make_uint4(0, 0, 0, 0);
-        }
-      }
+      named_bar_sync(1, kNumEpiThreads);
 
       mbar_wait(tfull_bar(acc), accph);
       tc_fence_after();
       const uint32_t t_row = tmem_base + acc * BLOCK_N + (static_cast<uint32_t>(ew * 32) << 16);
 
       constexpr int kCols = (BLOCK_N >= 32) ? 32 : 16;
+      constexpr int kChunks = BLOCK_N / kCols;
 #pragma unroll 1
-      for (int c = 0; c < BLOCK_N; c += kCols) {
+      for (int ci = half; ci < kChunks; ci += 2) {
+        const int c = ci * kCols;
         float v[kCols];
         {
           uint32_t r[kCols];
@@ -283,37 +287,17 @@ conv_igemm_kernel(const __grid_constant__ ConvKernelParams p) {
           for (int i = 0; i < kCols; ++i) v[i] = __uint_as_float(r[i]);
         }
         const int ch0 = t.n0 + c;
-        float bs[kCols];
 #pragma unroll
         for (int j = 0; j < kCols / 4; ++j) {
+          float b0, b1, b2, b3;
           asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
-                       : "=f"(bs[4 * j]), "=f"(bs[4 * j + 1]), "=f"(bs[4 * j + 2]), "=f"(bs[4 * j + 3])
+                       : "=f"(b0), "=f"(b1), "=f"(b2), "=f"(b3)
                        : "r"(bias_smem + 4u * (c + 4 * j)));
-        }
-        if (!is_gdn) {
-#pragma unroll
-          for (int i = 0; i < kCols; ++i) {
-            float x = v[i] + bs[i];
-            v[i] = x > 0.f ? x : x * p.slope;
-          }
-        } else {
-          // GDN / IGDN: aux * (r)sqrt(beta + acc / sq_scale^2); the next chunk's aux is prefetched
-          uint4 a4[kCols / 8];
-#pragma unroll
-          for (int j = 0; j < kCols / 8; ++j) a4[j] = aux_nxt[j];
-          if (c + kCols < BLOCK_N && inb) {
-            const uint4* ap = reinterpret_cast<const uint4*>(p.aux + pix * p.c_out + ch0 + kCols);
-#pragma unroll
-            for (int j = 0; j < kCols / 8; ++j) aux_nxt[j] = __ldg(ap + j);
-          }
-#pragma unroll
-          for (int i = 0; i < kCols; ++i) {
-            const uint32_t w = reinterpret_cast<const uint32_t*>(a4)[i >> 1];
-            const __half ah = __ushort_as_half(static_cast<unsigned short>((i & 1) ? (w >> 16) : (w & 0xFFFFu)));
-            float nrm = fmaf(v[i], p.sq_inv, bs[i]);
-            float f = (p.epilogue == STEMB200_EPI_GDN) ? rsqrtf(nrm) : sqrtf(nrm);
-            v[i] = __half2float(ah) * f;
-          }
+          const float x0 = v[4 * j] + b0, x1 = v[4 * j + 1] + b1, x2 = v[4 * j + 2] + b2, x3 = v[4 * j + 3] + b3;
+          v[4 * j] = x0 > 0.f ? x0 : x0 * p.slope;
+          v[4 * j + 1] = x1 > 0.f ? x1 : x1 * p.slope;
+          v[4 * j + 2] = x2 > 0.f ? x2 : x2 * p.slope;
+          v[4 * j + 3] = x3 > 0.f ? x3 : x3 * p.slope;
         }
 
         if (p.direct) {
@@ -333,17 +317,16 @@ conv_igemm_kernel(const __grid_constant__ ConvKernelParams p) {
             }
           }
         } else if constexpr (kCols == 32) {
-          // ---- staged TMA store. fp32: one 128-byte row = 32 columns; fp16: 64 columns (two loads). ----
-          const bool second_half = (!p.out_f32) && ((c & 32) != 0);
-          const uint32_t buf = chunk_ctr & 1u;
+          // ---- staged TMA store, one 64-column group (both halves) per iteration ----
+          //   fp16: the two halves fill pieces 0-3 / 4-7 of one 128-byte row; buffers alternate per group
+          //   fp32: each half fills its own buffer (32 columns = one 128-byte row)
+          const uint32_t buf = p.out_f32 ? static_cast<uint32_t>(half) : (group_ctr & 1u);
           const uint32_t obuf = out_base + buf * kOutStageBytes;
-          const uint32_t sbuf = out_base + (2u + buf) * kOutStageBytes;
-          if (!second_half) {
-            // the buffer was last used two chunks ago: its TMA store must have finished reading smem
-            if (etid == 0) tma_store_wait_read<1>();
-            named_bar_sync(1, 128);
+          if (etid == 0) {
+            if (p.out_f32) tma_store_wait_read<0>();
+            else tma_store_wait_read<1>();
           }
-          const uint32_t rsw = static_cast<uint32_t>(row & 7);
+          named_bar_sync(1, kNumEpiThreads);
           const uint32_t rbase = obuf + static_cast<uint32_t>(row) * 128u;
           if (p.out_f32) {
 #pragma unroll
@@ -354,7 +337,7 @@ conv_igemm_kernel(const __grid_constant__ ConvKernelParams p) {
                            : "memory");
             }
           } else {
-            const uint32_t jo = second_half ? 4u : 0u;
+            const uint32_t jo = half ? 4u : 0u;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               const uint32_t addr = rbase + (((static_cast<uint32_t>(j) + jo) ^ rsw) << 4);
@@ -365,43 +348,316 @@ conv_igemm_kernel(const __grid_constant__ ConvKernelParams p) {
                            "r"(pack_half2(v[8 * j + 6], v[8 * j + 7]))
                            : "memory");
             }
-            if (Cfg::kSqAllowed && p.write_sq) {
-              const uint32_t sbase = sbuf + static_cast<uint32_t>(row) * 128u;
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                float q[8];
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                  // square the value the next layer will actually read (the fp16-rounded one)
-                  float xr = __half2float(__float2half_rn(v[8 * j + i])) * p.sq_scale;
-                  q[i] = xr * xr;
-                }
-                const uint32_t addr = sbase + (((static_cast<uint32_t>(j) + jo) ^ rsw) << 4);
-                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr),
-                             "r"(pack_half2(q[0], q[1])), "r"(pack_half2(q[2], q[3])),
-                             "r"(pack_half2(q[4], q[5])), "r"(pack_half2(q[6], q[7]))
-                             : "memory");
-              }
-            }
           }
-          const bool chunk_done = p.out_f32 || second_half || (c + 32 >= BLOCK_N);
-          if (chunk_done) {
-            fence_proxy_async_smem();
-            named_bar_sync(1, 128);
-            if (etid == 0) {
-              const int cstart = p.out_f32 ? ch0 : (ch0 & ~63);
-              tma_store_4d(&p.out_map[t.sub], obuf, cstart, t.w0, t.h0, t.n_img);
-              if (Cfg::kSqAllowed && p.write_sq) tma_store_4d(&p.sq_map[t.sub], sbuf, cstart, t.w0, t.h0, t.n_img);
-              tma_store_commit();
+          fence_proxy_async_smem();
+          named_bar_sync(1, kNumEpiThreads);
+          if (etid == 0) {
+            const int cgrp = t.n0 + (c & ~63);
+            if (p.out_f32) {
+              tma_store_4d(&p.out_map[t.sub], out_base, cgrp, t.w0, t.h0, t.n_img);
+              tma_store_4d(&p.out_map[t.sub], out_base + kOutStageBytes, cgrp + 32, t.w0, t.h0, t.n_img);
+            } else {
+              tma_store_4d(&p.out_map[t.sub], obuf, cgrp, t.w0, t.h0, t.n_img);
             }
-            ++chunk_ctr;
+            tma_store_commit();
           }
+          ++group_ctr;
         }
       }
       // all TMEM reads of this accumulator are complete -> hand it back to the MMA warp
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar(acc));
+    }
+    if (etid == 0) tma_store_wait_all<0>();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, Cfg::kTmemCols);
+}
+
+// =====================================================================================================
+// conv / deconv with GDN or IGDN fused into the epilogue (C_out == 192 == one N tile)
+//
+//   x   = conv(in) + bias                    accumulator A in TMEM columns [0,192)
+//   n   = beta + gamma . x^2                 second contraction on the tensor core: x^2 (fp16, prescaled) is
+//                                            written by the epilogue warps into smem as a K-major operand, gamma
+//                                            chunks stream through the B slots of the same TMA ring; accumulator
+//                                            N in TMEM columns [192,384)
+//   out = x * rsqrt(n)  (GDN)  |  x * sqrt(n)  (IGDN); x is parked as packed fp16 in TMEM columns [384,480)
+//
+// Per tile the MMA thread issues: main loop -> commit(tfull) -> wait(a2rdy) -> 3 gamma k-steps -> commit(nfull)
+// -> next main loop. Phase 2 of the epilogue (normalise + store) overlaps the next tile's main loop; only phase 1
+// (reading A, producing x^2) sits on the tensor pipe's critical path. Replaces layers/gdn.py:52-67 + the producing
+// conv (priors.py:421-439) without x or x^2 ever reaching HBM.
+// =====================================================================================================
+struct GdnCfg {
+  static constexpr int kN = 192;
+  static constexpr int kBStageBytes = kN * 128;
+  static constexpr int kStageBytes = kAStageBytes + kBStageBytes;
+  static constexpr int kStages = 4;
+  static constexpr int kA2Bytes = 3 * kAStageBytes;  // x^2 operand (3 chunks of 64 channels); reused as output staging
+  static constexpr int kBarrierBytes = 256 + 2 * kN * 4;
+  static constexpr int kSmemBytes = 1024 + kStages * kStageBytes + kA2Bytes + kBarrierBytes;
+  static constexpr int kTmemCols = 512;
+  static constexpr uint32_t kAccCol = 0, kNormCol = 192, kStashCol = 384;
+  static_assert(kSmemBytes <= kSmemLimit, "smem overflow");
+};
+
+__global__ void __launch_bounds__(kNumThreads, 1)
+conv_gdn_kernel(const __grid_constant__ ConvKernelParams p) {
+  using Cfg = GdnCfg;
+  constexpr int kStages = Cfg::kStages;
+  constexpr int BLOCK_N = Cfg::kN;
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t stage_base = smem_base;
+  const uint32_t a2_base = smem_base + kStages * Cfg::kStageBytes;
+  const uint32_t bar_base = a2_base + Cfg::kA2Bytes;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (kStages + s); };
+  const uint32_t tfull_bar = bar_base + 8u * (2 * kStages);
+  const uint32_t a2rdy_bar = bar_base + 8u * (2 * kStages + 1);
+  const uint32_t nfull_bar = bar_base + 8u * (2 * kStages + 2);
+  const uint32_t tmem_slot = bar_base + 8u * (2 * kStages + 3);
+  const uint32_t bias_smem = bar_base + 256u;
+  const uint32_t beta_smem = bias_smem + 4u * BLOCK_N;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    for (int i = 0; i < 4; ++i) tma_prefetch_desc(&p.a_map[i]);
+    tma_prefetch_desc(&p.b_map);
+    tma_prefetch_desc(&p.g_map);
+    for (int i = 0; i < p.n_sub; ++i) tma_prefetch_desc(&p.out_map[i]);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    mbar_init(tfull_bar, 1);
+    mbar_init(a2rdy_bar, 8);
+    mbar_init(nfull_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, Cfg::kTmemCols);
+    tmem_relinquish();
+  }
+  if (warp >= 4) {
+    for (int i = threadIdx.x - 128; i < BLOCK_N; i += kNumEpiThreads) {
+      const float b = __ldg(p.bias + i), g = __ldg(p.beta + i);
+      asm volatile("st.shared.f32 [%0], %1;" ::"r"(bias_smem + 4u * i), "f"(b) : "memory");
+      asm volatile("st.shared.f32 [%0], %1;" ::"r"(beta_smem + 4u * i), "f"(g) : "memory");
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  const uint32_t a_tx_bytes = static_cast<uint32_t>(p.tile_h * p.tile_w) * 128u;
+
+  if (warp == 0 && lane == 0) {
+    // ===================== TMA producer =====================
+    int s = 0;
+    uint32_t ph = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      const TileCoord t = decode_tile(p, tile, BLOCK_N);
+      const int kbeg = p.sub_kbeg[t.sub], kend = p.sub_kend[t.sub];
+      for (int k = kbeg; k < kend; ++k) {
+        mbar_wait(empty_bar(s), ph ^ 1u);
+        const uint32_t e = p.ksteps[k];
+        const int map = e & 3;
+        const int dh = static_cast<int>((e >> 2) & 15u) - 8;
+        const int dw = static_cast<int>((e >> 6) & 15u) - 8;
+        const int c0 = static_cast<int>(e >> 10);
+        const uint32_t a_dst = stage_base + s * Cfg::kStageBytes;
+        mbar_arrive_expect_tx(full_bar(s), a_tx_bytes + Cfg::kBStageBytes);
+        tma_load_4d(a_dst, &p.a_map[map], full_bar(s), c0, t.w0 + dw, t.h0 + dh, t.n_img);
+        tma_load_2d(a_dst + kAStageBytes, &p.b_map, full_bar(s), k * kKChunk, 0);
+        if (++s == kStages) {
+          s = 0;
+          ph ^= 1u;
+        }
+      }
+      // gamma chunks for this tile's second contraction: only the B slot of the stage is used
+      for (int kc = 0; kc < BLOCK_N / kKChunk; ++kc) {
+        mbar_wait(empty_bar(s), ph ^ 1u);
+        const uint32_t a_dst = stage_base + s * Cfg::kStageBytes;
+        mbar_arrive_expect_tx(full_bar(s), Cfg::kBStageBytes);
+        tma_load_2d(a_dst + kAStageBytes, &p.g_map, full_bar(s), kc * kKChunk, 0);
+        if (++s == kStages) {
+          s = 0;
+          ph ^= 1u;
+        }
+      }
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ===================== MMA issuer =====================
+    constexpr uint32_t idesc = umma_idesc(/*F16*/ 0u, 128u, BLOCK_N);
+    int s = 0;
+    uint32_t ph = 0;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+      const TileCoord t = decode_tile(p, tile, BLOCK_N);
+      const int kbeg = p.sub_kbeg[t.sub], kend = p.sub_kend[t.sub];
+      // accumulator A is free: phase 1 of the previous tile completed before its gamma MMAs were issued
+      for (int k = kbeg; k < kend; ++k) {
+        mbar_wait(full_bar(s), ph);
+        tc_fence_after();
+        const uint32_t a_addr = stage_base + s * Cfg::kStageBytes;
+        const uint64_t adesc = umma_desc_sw128(a_addr);
+        const uint64_t bdesc = umma_desc_sw128(a_addr + kAStageBytes);
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk)
+          mma_f16_ss(tmem_base + Cfg::kAccCol, adesc + 2u * kk, bdesc + 2u * kk, idesc,
+                     (k > kbeg || kk > 0) ? 1u : 0u);
+        mma_commit(empty_bar(s));
+        if (++s == kStages) {
+          s = 0;
+          ph ^= 1u;
+        }
+      }
+      mma_commit(tfull_bar);
+      // second contraction: norm = gamma . x^2 once the epilogue has written x^2 (and drained A)
+      mbar_wait(a2rdy_bar, it & 1);
+      tc_fence_after();
+      for (int kc = 0; kc < BLOCK_N / kKChunk; ++kc) {
+        mbar_wait(full_bar(s), ph);
+        tc_fence_after();
+        const uint64_t adesc = umma_desc_sw128(a2_base + kc * kAStageBytes);
+        const uint64_t bdesc = umma_desc_sw128(stage_base + s * Cfg::kStageBytes + kAStageBytes);
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk)
+          mma_f16_ss(tmem_base + Cfg::kNormCol, adesc + 2u * kk, bdesc + 2u * kk, idesc,
+                     (kc > 0 || kk > 0) ? 1u : 0u);
+        mma_commit(empty_bar(s));
+        if (++s == kStages) {
+          s = 0;
+          ph ^= 1u;
+        }
+      }
+      mma_commit(nfull_bar);
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue (8 warps; see conv_igemm_kernel) =====================
+    const int ew = warp & 3;
+    const int etid = threadIdx.x - 128;
+    const int row = etid & 127;
+    const int half = etid >> 7;
+    const uint32_t lane_off = static_cast<uint32_t>(ew * 32) << 16;
+    const uint32_t rsw = static_cast<uint32_t>(row & 7);
+    const uint32_t row_off = static_cast<uint32_t>(row) * 128u;
+    const uint32_t jo = half ? 4u : 0u;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+      const TileCoord t = decode_tile(p, tile, BLOCK_N);
+      const uint32_t par = it & 1;
+      mbar_wait(tfull_bar, par);
+      tc_fence_after();
+      // ---- phase 1: x = A + bias -> stash (TMEM, packed fp16), x^2 -> smem operand
+#pragma unroll 1
+      for (int g = 0; g < BLOCK_N / 64; ++g) {
+        const int c = 64 * g + 32 * half;
+        // this 64-channel buffer was the staging of the previous tile's output store (groups complete in order)
+        if (etid == 0) {
+          if (g == 0) tma_store_wait_read<2>();
+          else if (g == 1) tma_store_wait_read<1>();
+          else tma_store_wait_read<0>();
+        }
+        named_bar_sync(1, kNumEpiThreads);
+        uint32_t r[32];
+        tmem_ld_32x32(tmem_base + lane_off + Cfg::kAccCol + c, r);
+        tmem_ld_wait();
+        uint32_t hx[16], hq[16];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float b0, b1, b2, b3;
+          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                       : "=f"(b0), "=f"(b1), "=f"(b2), "=f"(b3)
+                       : "r"(bias_smem + 4u * (c + 4 * j)));
+          const __half2 h0 = __floats2half2_rn(__uint_as_float(r[4 * j]) + b0, __uint_as_float(r[4 * j + 1]) + b1);
+          const __half2 h1 =
+              __floats2half2_rn(__uint_as_float(r[4 * j + 2]) + b2, __uint_as_float(r[4 * j + 3]) + b3);
+          hx[2 * j] = *reinterpret_cast<const uint32_t*>(&h0);
+          hx[2 * j + 1] = *reinterpret_cast<const uint32_t*>(&h1);
+          // square the value that is actually normalised (the fp16-rounded x), prescaled to stay in range
+          const float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
+          const float q0 = f0.x * p.sq_scale, q1 = f0.y * p.sq_scale, q2 = f1.x * p.sq_scale, q3 = f1.y * p.sq_scale;
+          hq[2 * j] = pack_half2(q0 * q0, q1 * q1);
+          hq[2 * j + 1] = pack_half2(q2 * q2, q3 * q3);
+        }
+        tmem_st_32x16(tmem_base + lane_off + Cfg::kStashCol + (c >> 1), hx);
+        const uint32_t cbase = a2_base + static_cast<uint32_t>(g) * kAStageBytes + row_off;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const uint32_t addr = cbase + (((static_cast<uint32_t>(j) + jo) ^ rsw) << 4);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(hq[4 * j]), "r"(hq[4 * j + 1]),
+                       "r"(hq[4 * j + 2]), "r"(hq[4 * j + 3])
+                       : "memory");
+        }
+      }
+      tmem_st_wait();
+      fence_proxy_async_smem();  // x^2 is read by the tensor core through the async proxy
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(a2rdy_bar);
+
+      // ---- phase 2: out = x * (r)sqrt(beta + gamma.x^2), staged per 64 channels, TMA store
+      mbar_wait(nfull_bar, par);
+      tc_fence_after();
+#pragma unroll 1
+      for (int g = 0; g < BLOCK_N / 64; ++g) {
+        const int c = 64 * g + 32 * half;
+        uint32_t r[32], hx[16];
+        tmem_ld_32x32(tmem_base + lane_off + Cfg::kNormCol + c, r);
+        tmem_ld_32x16(tmem_base + lane_off + Cfg::kStashCol + (c >> 1), hx);
+        tmem_ld_wait();
+        uint32_t ho[16];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float b0, b1, b2, b3;
+          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                       : "=f"(b0), "=f"(b1), "=f"(b2), "=f"(b3)
+                       : "r"(beta_smem + 4u * (c + 4 * j)));
+          const float2 x0 = __half22float2(*reinterpret_cast<const __half2*>(&hx[2 * j]));
+          const float2 x1 = __half22float2(*reinterpret_cast<const __half2*>(&hx[2 * j + 1]));
+          const float n0 = fmaf(__uint_as_float(r[4 * j]), p.sq_inv, b0);
+          const float n1 = fmaf(__uint_as_float(r[4 * j + 1]), p.sq_inv, b1);
+          const float n2 = fmaf(__uint_as_float(r[4 * j + 2]), p.sq_inv, b2);
+          const float n3 = fmaf(__uint_as_float(r[4 * j + 3]), p.sq_inv, b3);
+          float f0, f1, f2, f3;
+          if (p.igdn) {
+            f0 = approx_sqrt(n0), f1 = approx_sqrt(n1), f2 = approx_sqrt(n2), f3 = approx_sqrt(n3);
+          } else {
+            f0 = approx_rsqrt(n0), f1 = approx_rsqrt(n1), f2 = approx_rsqrt(n2), f3 = approx_rsqrt(n3);
+          }
+          ho[2 * j] = pack_half2(x0.x * f0, x0.y * f1);
+          ho[2 * j + 1] = pack_half2(x1.x * f2, x1.y * f3);
+        }
+        const uint32_t cbase = a2_base + static_cast<uint32_t>(g) * kAStageBytes + row_off;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const uint32_t addr = cbase + (((static_cast<uint32_t>(j) + jo) ^ rsw) << 4);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(ho[4 * j]), "r"(ho[4 * j + 1]),
+                       "r"(ho[4 * j + 2]), "r"(ho[4 * j + 3])
+                       : "memory");
+        }
+        fence_proxy_async_smem();
+        named_bar_sync(1, kNumEpiThreads);
+        if (etid == 0) {
+          tma_store_4d(&p.out_map[t.sub], a2_base + static_cast<uint32_t>(g) * kAStageBytes, 64 * g, t.w0, t.h0,
+                       t.n_img);
+          tma_store_commit();
+        }
+      }
+      tc_fence_before();
     }
     if (etid == 0) tma_store_wait_all<0>();
   }
@@ -463,8 +719,8 @@ struct Plan {
   int block_n = 0;
 };
 
-int pick_block_n(int c_out, bool write_sq) {
-  if (c_out % 256 == 0 && !write_sq) return 256;
+int pick_block_n(int c_out) {
+  if (c_out % 256 == 0) return 256;
   if (c_out % 192 == 0) return 192;
   if (c_out % 128 == 0) return 128;
   if (c_out % 64 == 0) return 64;
@@ -486,10 +742,8 @@ int build_plan(const stemb200_conv_desc& d, Plan& pl) {
     src_base[s] = pl.c_in_total;
     pl.c_in_total += d.c_in[s];
   }
-  pl.block_n = pick_block_n(d.c_out, d.write_sq != 0);
+  pl.block_n = pick_block_n(d.c_out);
   if (!pl.block_n) return set_error("conv: unsupported c_out");
-  if (d.write_sq && d.out_dtype != STEMB200_DT_F16) return set_error("conv: write_sq needs fp16 output");
-  if (d.write_sq && d.direct_store) return set_error("conv: write_sq needs the TMA store path");
   if (pl.block_n < 32 && !d.direct_store) return set_error("conv: c_out < 32 needs direct_store");
   if (!d.direct_store && d.out_dtype == STEMB200_DT_F16 && (d.c_out % 64)) return set_error("conv: c_out%64");
 
@@ -713,24 +967,15 @@ extern "C" int stemb200_conv2d_pack_weight(const stemb200_conv_desc* d, const fl
   return 0;
 }
 
-extern "C" int stemb200_conv2d_fwd(const stemb200_conv_desc* d, const void* const* in,
-                                   const void* packed_weight, const float* bias, const void* aux, void* out,
-                                   void* out_sq, void* stream) {
-  if (!d || !in || !packed_weight || !bias || !out) return set_error("conv2d_fwd: null argument");
-  Plan pl;
-  if (int rc = build_plan(*d, pl)) return rc;
-  if (d->epilogue != STEMB200_EPI_LINEAR && !aux) return set_error("conv2d_fwd: GDN epilogue needs aux");
-  if (d->write_sq && !out_sq) return set_error("conv2d_fwd: write_sq needs out_sq");
-  for (int s = 0; s < d->n_src; ++s)
-    if (!in[s]) return set_error("conv2d_fwd: null input");
-
-  ConvKernelParams kp;
+namespace {
+// geometry + pointers -> kernel parameters (tensor maps, k-step table, tiling)
+int setup_params(const stemb200_conv_desc* d, const Plan& pl, const void* const* in, const void* packed_weight,
+                 const float* bias, void* out, ConvKernelParams& kp) {
   memset(&kp, 0, sizeof(kp));
   int th = d->tile_h, tw = d->tile_w;
   if (th <= 0 || tw <= 0) pick_tile(pl.h_out, pl.w_out, th, tw);
   if (th * tw > 128 || tw > 256 || th > 256) return set_error("conv2d_fwd: tile_h*tile_w must be <= 128");
 
-  // A maps
   for (int m = 0; m < 4; ++m) {
     const int mm = m < pl.n_maps ? m : 0;
     const int src = pl.map_src[mm];
@@ -749,17 +994,8 @@ extern "C" int stemb200_conv2d_fwd(const stemb200_conv_desc* d, const void* cons
                                pl.sub_p[ss], pl.sub_q[ss], out_box_c, tw, th))
         return rc;
     }
-    for (int sp = 0; sp < 4; ++sp) {
-      const int ss = sp < pl.n_sub ? sp : 0;
-      if (d->write_sq) {
-        if (int rc = encode_nhwc(&kp.sq_map[sp], out_sq, 2, d->batch, pl.full_h, pl.full_w, d->c_out, pl.os,
-                                 pl.sub_p[ss], pl.sub_q[ss], 64, tw, th))
-          return rc;
-      } else {
-        kp.sq_map[sp] = kp.out_map[sp];
-      }
-    }
   }
+  kp.g_map = kp.b_map;
   for (size_t i = 0; i < pl.ksteps.size(); ++i) kp.ksteps[i] = pl.ksteps[i];
   for (int i = 0; i < 4; ++i) {
     kp.sub_kbeg[i] = pl.sub_kbeg[i];
@@ -781,20 +1017,31 @@ extern "C" int stemb200_conv2d_fwd(const stemb200_conv_desc* d, const void* cons
   if (total > 0x7fffffffLL) return set_error("conv2d_fwd: too many tiles");
   kp.total_tiles = static_cast<int>(total);
   kp.c_out = d->c_out;
-  kp.epilogue = d->epilogue;
   kp.slope = d->lrelu_slope;
   kp.sq_scale = d->sq_scale;
   kp.sq_inv = d->sq_scale != 0.f ? 1.0f / (d->sq_scale * d->sq_scale) : 1.0f;
   kp.out_f32 = d->out_dtype == STEMB200_DT_F32;
-  kp.write_sq = d->write_sq;
   kp.direct = d->direct_store;
   kp.os = pl.os;
   kp.full_h = pl.full_h;
   kp.full_w = pl.full_w;
   kp.bias = bias;
-  kp.aux = static_cast<const __half*>(aux);
   kp.out = out;
+  kp.beta = bias;
+  kp.igdn = 0;
+  return 0;
+}
+}  // namespace
 
+extern "C" int stemb200_conv2d_fwd(const stemb200_conv_desc* d, const void* const* in,
+                                   const void* packed_weight, const float* bias, void* out, void* stream) {
+  if (!d || !in || !packed_weight || !bias || !out) return set_error("conv2d_fwd: null argument");
+  Plan pl;
+  if (int rc = build_plan(*d, pl)) return rc;
+  for (int s = 0; s < d->n_src; ++s)
+    if (!in[s]) return set_error("conv2d_fwd: null input");
+  ConvKernelParams kp;
+  if (int rc = setup_params(d, pl, in, packed_weight, bias, out, kp)) return rc;
   const int grid = std::min(kp.total_tiles, num_sms());
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   switch (pl.block_n) {
@@ -805,4 +1052,38 @@ extern "C" int stemb200_conv2d_fwd(const stemb200_conv_desc* d, const void* cons
     case 256: return launch_conv<256>(kp, grid, st);
     default: return set_error("conv2d_fwd: no kernel for this c_out");
   }
+}
+
+extern "C" int stemb200_conv2d_gdn_fwd(const stemb200_conv_desc* d, const void* const* in,
+                                       const void* packed_weight, const float* bias, const void* packed_gamma,
+                                       const float* beta, int32_t inverse, void* out, void* stream) {
+  if (!d || !in || !packed_weight || !bias || !packed_gamma || !beta || !out)
+    return set_error("conv2d_gdn_fwd: null argument");
+  if (d->c_out != GdnCfg::kN) return set_error("conv2d_gdn_fwd: fused GDN needs c_out == 192");
+  if (d->out_dtype != STEMB200_DT_F16 || d->direct_store || d->lrelu_slope != 1.0f || d->sq_scale <= 0.f)
+    return set_error("conv2d_gdn_fwd: needs fp16 TMA-store output, no activation, sq_scale > 0");
+  stemb200_conv_desc dd = *d;
+  Plan pl;
+  if (int rc = build_plan(dd, pl)) return rc;
+  if (pl.block_n != GdnCfg::kN) return set_error("conv2d_gdn_fwd: unexpected N tile");
+  for (int s = 0; s < d->n_src; ++s)
+    if (!in[s]) return set_error("conv2d_gdn_fwd: null input");
+  ConvKernelParams kp;
+  if (int rc = setup_params(&dd, pl, in, packed_weight, bias, out, kp)) return rc;
+  if (int rc = encode_weight(&kp.g_map, packed_gamma, GdnCfg::kN, GdnCfg::kN, GdnCfg::kN)) return rc;
+  kp.beta = beta;
+  kp.igdn = inverse ? 1 : 0;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(conv_gdn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         GdnCfg::kSmemBytes);
+    if (e != cudaSuccess) return set_cuda_error("cudaFuncSetAttribute(conv_gdn)", e);
+    configured = true;
+  }
+  const int grid = std::min(kp.total_tiles, num_sms());
+  conv_gdn_kernel<<<grid, kNumThreads, GdnCfg::kSmemBytes, static_cast<cudaStream_t>(stream)>>>(kp);
+  count_launch();
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_cuda_error("conv_gdn launch", e);
+  return 0;
 }

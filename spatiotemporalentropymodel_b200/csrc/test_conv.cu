@@ -47,11 +47,11 @@ static stemb200_conv_desc mk(int n, int h, int w, std::vector<int> cin, int cout
   d.stride = stride;
   d.transposed = transposed;
   d.tap_mask = mask;
-  d.epilogue = epi;
   d.lrelu_slope = slope;
   d.out_dtype = odt;
-  d.write_sq = wsq;
-  d.sq_scale = 0.0625f;
+  d.sq_scale = 0.125f;
+  (void)epi;
+  (void)wsq;
   d.tile_h = th;
   d.tile_w = tw;
   d.direct_store = direct;
@@ -83,7 +83,7 @@ static int run_case(const Case& cs, bool timing) {
     size_t ne = (size_t)d.batch * d.h_in * d.w_in * d.c_in[s];
     hin[s].resize(ne);
     for (size_t i = 0; i < ne; ++i)
-      hin[s][i] = __float2half_rn(d.epilogue == STEMB200_EPI_LINEAR ? U(rng) : fabsf(U(rng)) * 0.004f);
+      hin[s][i] = __float2half_rn(U(rng));
     CK(cudaMalloc(&din[s], ne * 2));
     CK(cudaMemcpy(din[s], hin[s].data(), ne * 2, cudaMemcpyHostToDevice));
   }
@@ -96,10 +96,7 @@ static int run_case(const Case& cs, bool timing) {
   CK(cudaMalloc(&dw, nw * 4));
   CK(cudaMemcpy(dw, hw.data(), nw * 4, cudaMemcpyHostToDevice));
   std::vector<float> hb(d.c_out);
-  for (auto& b : hb) b = (d.epilogue == STEMB200_EPI_LINEAR) ? U(rng) * 0.5f : 1.0f + 0.5f * fabsf(U(rng));
-  if (d.epilogue != STEMB200_EPI_LINEAR)
-    for (auto& x : hw) x = fabsf(x);  // gamma >= 0
-  if (d.epilogue != STEMB200_EPI_LINEAR) CK(cudaMemcpy(dw, hw.data(), nw * 4, cudaMemcpyHostToDevice));
+  for (auto& b : hb) b = U(rng) * 0.5f;
   float* db;
   CK(cudaMalloc(&db, d.c_out * 4));
   CK(cudaMemcpy(db, hb.data(), d.c_out * 4, cudaMemcpyHostToDevice));
@@ -117,21 +114,10 @@ static int run_case(const Case& cs, bool timing) {
   }
   const size_t nout = (size_t)d.batch * ho * wo * d.c_out;
   const int obytes = d.out_dtype == STEMB200_DT_F32 ? 4 : 2;
-  void *dout, *dsq = nullptr, *daux = nullptr;
+  void* dout;
   CK(cudaMalloc(&dout, nout * obytes));
   CK(cudaMemset(dout, 0xFF, nout * obytes));  // NaN pattern: unwritten outputs are caught
-  if (d.write_sq) {
-    CK(cudaMalloc(&dsq, nout * 2));
-    CK(cudaMemset(dsq, 0xFF, nout * 2));
-  }
-  std::vector<__half> haux;
-  if (d.epilogue != STEMB200_EPI_LINEAR) {
-    haux.resize(nout);
-    for (auto& a : haux) a = __float2half_rn(U(rng) * 4.f);
-    CK(cudaMalloc(&daux, nout * 2));
-    CK(cudaMemcpy(daux, haux.data(), nout * 2, cudaMemcpyHostToDevice));
-  }
-  int rc = stemb200_conv2d_fwd(&d, din.data(), dpk, db, daux, dout, dsq, 0);
+  int rc = stemb200_conv2d_fwd(&d, din.data(), dpk, db, dout, 0);
   if (rc) {
     printf("[%s] conv2d_fwd failed: %s\n", cs.name.c_str(), stemb200_last_error());
     return 1;
@@ -143,11 +129,6 @@ static int run_case(const Case& cs, bool timing) {
   }
   std::vector<char> hout(nout * obytes);
   CK(cudaMemcpy(hout.data(), dout, nout * obytes, cudaMemcpyDeviceToHost));
-  std::vector<__half> hsq;
-  if (d.write_sq) {
-    hsq.resize(nout);
-    CK(cudaMemcpy(hsq.data(), dsq, nout * 2, cudaMemcpyDeviceToHost));
-  }
 
   auto in_at = [&](int n, int ih, int iw, int ci) -> float {
     if (ih < 0 || ih >= d.h_in || iw < 0 || iw >= d.w_in) return 0.f;
@@ -200,16 +181,8 @@ static int run_case(const Case& cs, bool timing) {
     int oh = (int)(px % ho);
     int n = (int)(px / ho);
     double acc = ref_at(n, oh, ow, co);
-    double ref;
-    if (d.epilogue == STEMB200_EPI_LINEAR) {
-      ref = acc + hb[co];
-      if (ref < 0) ref *= d.lrelu_slope;
-    } else {
-      // the test feeds unscaled "x^2" operands, so undo the kernel's 1/sq_scale^2 factor here
-      double nrm = hb[co] + acc / ((double)d.sq_scale * d.sq_scale);
-      double f = d.epilogue == STEMB200_EPI_GDN ? 1.0 / sqrt(nrm) : sqrt(nrm);
-      ref = h2f(haux[i]) * f;
-    }
+    double ref = acc + hb[co];
+    if (ref < 0) ref *= d.lrelu_slope;
     float got = obytes == 4 ? ((float*)hout.data())[i] : h2f(((__half*)hout.data())[i]);
     double err = fabs(got - ref);
     if (!(err <= max_err)) {
@@ -219,11 +192,6 @@ static int run_case(const Case& cs, bool timing) {
       }
     }
     if (fabs(ref) > max_ref) max_ref = fabs(ref);
-    if (d.write_sq) {
-      double xr = h2f(__float2half_rn((float)ref)) * d.sq_scale;
-      double sq_err = fabs(h2f(hsq[i]) - xr * xr);
-      if (!(sq_err <= max_sq_err)) max_sq_err = sq_err;
-    }
   }
   const double tol = (obytes == 4 ? 2e-3 : 6e-3) * (max_ref > 1 ? max_ref : 1.0);
   const bool ok = nan_count == 0 && max_err <= tol && max_sq_err <= 4e-3 * (max_ref * d.sq_scale) * (max_ref * d.sq_scale) + 1e-6;
@@ -235,10 +203,10 @@ static int run_case(const Case& cs, bool timing) {
     cudaEvent_t e0, e1;
     CK(cudaEventCreate(&e0));
     CK(cudaEventCreate(&e1));
-    for (int i = 0; i < 3; ++i) stemb200_conv2d_fwd(&d, din.data(), dpk, db, daux, dout, dsq, 0);
+    for (int i = 0; i < 3; ++i) stemb200_conv2d_fwd(&d, din.data(), dpk, db, dout, 0);
     CK(cudaEventRecord(e0));
     const int iters = 10;
-    for (int i = 0; i < iters; ++i) stemb200_conv2d_fwd(&d, din.data(), dpk, db, daux, dout, dsq, 0);
+    for (int i = 0; i < iters; ++i) stemb200_conv2d_fwd(&d, din.data(), dpk, db, dout, 0);
     CK(cudaEventRecord(e1));
     CK(cudaEventSynchronize(e1));
     float ms;
@@ -255,8 +223,105 @@ static int run_case(const Case& cs, bool timing) {
   cudaFree(db);
   cudaFree(dpk);
   cudaFree(dout);
-  if (dsq) cudaFree(dsq);
-  if (daux) cudaFree(daux);
+  return ok ? 0 : 1;
+}
+
+// fused conv/deconv + GDN/IGDN: reference evaluated for whole pixels (all 192 channels) at sampled positions
+static int run_gdn_case(const std::string& name, stemb200_conv_desc d, int inverse, int n_pixels, bool timing) {
+  const int k = d.kh, pad = k / 2, C = d.c_out, cin = d.c_in[0];
+  int ho, wo;
+  if (d.transposed) { ho = 2 * d.h_in; wo = 2 * d.w_in; }
+  else { ho = (d.h_in + 2 * pad - k) / d.stride + 1; wo = (d.w_in + 2 * pad - k) / d.stride + 1; }
+  std::mt19937 rng(4321);
+  std::uniform_real_distribution<float> U(-1.f, 1.f);
+  const size_t nin = (size_t)d.batch * d.h_in * d.w_in * cin;
+  std::vector<__half> hin(nin);
+  for (auto& v : hin) v = __float2half_rn(U(rng));
+  void* din; CK(cudaMalloc(&din, nin * 2)); CK(cudaMemcpy(din, hin.data(), nin * 2, cudaMemcpyHostToDevice));
+  const size_t nw = (size_t)C * cin * k * k;
+  std::vector<float> hw(nw);
+  const float wscale = 2.0f / sqrtf((float)cin * k * k / (d.transposed ? 4 : 1));
+  for (auto& v : hw) v = h2f(__float2half_rn(U(rng) * wscale));
+  float* dw; CK(cudaMalloc(&dw, nw * 4)); CK(cudaMemcpy(dw, hw.data(), nw * 4, cudaMemcpyHostToDevice));
+  std::vector<float> hb(C), hbeta(C), hg((size_t)C * C);
+  for (auto& v : hb) v = U(rng) * 0.5f;
+  for (auto& v : hbeta) v = 1.0f + 0.5f * fabsf(U(rng));
+  for (int i = 0; i < C; ++i) for (int j = 0; j < C; ++j)
+    hg[(size_t)i * C + j] = h2f(__float2half_rn((i == j ? 0.1f : 0.f) + 0.02f * fabsf(U(rng))));
+  float *db, *dbeta, *dg;
+  CK(cudaMalloc(&db, C * 4)); CK(cudaMemcpy(db, hb.data(), C * 4, cudaMemcpyHostToDevice));
+  CK(cudaMalloc(&dbeta, C * 4)); CK(cudaMemcpy(dbeta, hbeta.data(), C * 4, cudaMemcpyHostToDevice));
+  CK(cudaMalloc(&dg, (size_t)C * C * 4)); CK(cudaMemcpy(dg, hg.data(), (size_t)C * C * 4, cudaMemcpyHostToDevice));
+  const int64_t K = stemb200_conv2d_packed_k(&d);
+  void *dpk, *dgpk;
+  CK(cudaMalloc(&dpk, (size_t)K * C * 2));
+  if (stemb200_conv2d_pack_weight(&d, dw, dpk, 0)) { printf("[%s] pack failed: %s\n", name.c_str(), stemb200_last_error()); return 1; }
+  stemb200_conv_desc gd = mk(1, 8, 8, {C}, C, 1, 1, 0, 0, 0, 1.f, STEMB200_DT_F16, 0, 0);
+  CK(cudaMalloc(&dgpk, (size_t)C * C * 2));
+  if (stemb200_conv2d_pack_weight(&gd, dg, dgpk, 0)) { printf("[%s] gamma pack failed\n", name.c_str()); return 1; }
+  const size_t nout = (size_t)d.batch * ho * wo * C;
+  void* dout; CK(cudaMalloc(&dout, nout * 2)); CK(cudaMemset(dout, 0xFF, nout * 2));
+  const void* ins[1] = {din};
+  int rc = stemb200_conv2d_gdn_fwd(&d, ins, dpk, db, dgpk, dbeta, inverse, dout, 0);
+  if (rc) { printf("[%s] conv2d_gdn_fwd failed: %s\n", name.c_str(), stemb200_last_error()); return 1; }
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) { printf("[%s] kernel error: %s\n", name.c_str(), cudaGetErrorString(e)); return 2; }
+  std::vector<__half> hout(nout);
+  CK(cudaMemcpy(hout.data(), dout, nout * 2, cudaMemcpyDeviceToHost));
+  size_t nan_count = 0;
+  for (size_t i = 0; i < nout; ++i) { float v = h2f(hout[i]); if (v != v) ++nan_count; }
+  auto in_at = [&](int n, int ih, int iw, int ci) -> float {
+    if (ih < 0 || ih >= d.h_in || iw < 0 || iw >= d.w_in) return 0.f;
+    return h2f(hin[(((size_t)n * d.h_in + ih) * d.w_in + iw) * cin + ci]);
+  };
+  std::uniform_int_distribution<size_t> pick(0, (size_t)d.batch * ho * wo - 1);
+  double max_err = 0, max_ref = 0;
+  std::vector<double> x(C);
+  for (int t = 0; t < n_pixels; ++t) {
+    size_t px = pick(rng);
+    if (t == 0) px = 0;
+    if (t == 1) px = (size_t)d.batch * ho * wo - 1;
+    int ow = (int)(px % wo), oh = (int)((px / wo) % ho), n = (int)(px / ((size_t)wo * ho));
+    for (int co = 0; co < C; ++co) {
+      double acc = 0;
+      for (int r = 0; r < k; ++r) for (int s2 = 0; s2 < k; ++s2) {
+        int ih, iw;
+        if (d.transposed) {
+          if (((oh + pad - r) & 1) || ((ow + pad - s2) & 1) || oh + pad - r < 0 || ow + pad - s2 < 0) continue;
+          ih = (oh + pad - r) / 2; iw = (ow + pad - s2) / 2;
+        } else { ih = oh * d.stride + r - pad; iw = ow * d.stride + s2 - pad; }
+        for (int ci = 0; ci < cin; ++ci) {
+          const float wv = d.transposed ? hw[(((size_t)ci * C + co) * k + r) * k + s2] : hw[(((size_t)co * cin + ci) * k + r) * k + s2];
+          acc += (double)in_at(n, ih, iw, ci) * wv;
+        }
+      }
+      x[co] = h2f(__float2half_rn((float)(acc + hb[co])));
+    }
+    for (int co = 0; co < C; ++co) {
+      double nrm = hbeta[co];
+      for (int j = 0; j < C; ++j) nrm += (double)hg[(size_t)co * C + j] * x[j] * x[j];
+      double ref = x[co] * (inverse ? sqrt(nrm) : 1.0 / sqrt(nrm));
+      double got = h2f(hout[px * C + co]);
+      double err = fabs(got - ref);
+      if (!(err <= max_err)) max_err = err;
+      if (fabs(ref) > max_ref) max_ref = fabs(ref);
+    }
+  }
+  const bool ok = nan_count == 0 && max_err <= 4e-3 * (max_ref > 1 ? max_ref : 1.0);
+  printf("[%-28s] %s  max_err=%.3e (max|ref|=%.2f) unwritten/NaN=%zu out=%dx%dx%dx%d\n", name.c_str(), ok ? "PASS" : "FAIL",
+         max_err, max_ref, nan_count, d.batch, ho, wo, C);
+  if (timing) {
+    cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    for (int i = 0; i < 3; ++i) stemb200_conv2d_gdn_fwd(&d, ins, dpk, db, dgpk, dbeta, inverse, dout, 0);
+    CK(cudaEventRecord(e0));
+    for (int i = 0; i < 10; ++i) stemb200_conv2d_gdn_fwd(&d, ins, dpk, db, dgpk, dbeta, inverse, dout, 0);
+    CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1));
+    float ms; CK(cudaEventElapsedTime(&ms, e0, e1)); ms /= 10;
+    double px = d.transposed ? (double)d.batch * d.h_in * d.w_in : (double)d.batch * ho * wo;
+    double flops = 2.0 * px * cin * C * k * k + 2.0 * d.batch * ho * wo * (double)C * C;
+    printf("    time %.3f ms  %.1f TFLOP/s (conv + gamma contraction)\n", ms, flops / ms * 1e-9);
+  }
+  cudaFree(din); cudaFree(dw); cudaFree(db); cudaFree(dbeta); cudaFree(dg); cudaFree(dpk); cudaFree(dgpk); cudaFree(dout);
   return ok ? 0 : 1;
 }
 
@@ -268,7 +333,7 @@ int main(int argc, char** argv) {
     else filter = argv[i];
   }
   printf("%s\n", stemb200_version());
-  const int F16 = STEMB200_DT_F16, F32 = STEMB200_DT_F32, LIN = STEMB200_EPI_LINEAR;
+  const int F16 = STEMB200_DT_F16, F32 = STEMB200_DT_F32, LIN = 0;
   std::vector<Case> cases = {
       {"a_1x1_64_64_direct_f32", mk(1, 8, 16, {64}, 64, 1, 1, 0, 0, LIN, 1.f, F32, 0, 1), 1 << 30},
       {"b_1x1_64_64_tma_f32", mk(1, 8, 16, {64}, 64, 1, 1, 0, 0, LIN, 1.f, F32, 0, 0), 1 << 30},
@@ -279,8 +344,6 @@ int main(int argc, char** argv) {
       {"g_3x3_cat2_256", mk(1, 20, 36, {192, 192}, 256, 3, 1, 0, 0, LIN, 0.01f, F16, 0, 0), 20000},
       {"h_5x5s2_192_192_sq", mk(2, 40, 72, {192}, 192, 5, 2, 0, 0, LIN, 1.f, F16, 1, 0), 20000},
       {"i_5x5s2_odd", mk(1, 17, 30, {256}, 256, 5, 2, 0, 0, LIN, 1.f, F32, 0, 0), 20000},
-      {"j_gdn_192", mk(2, 20, 36, {192}, 192, 1, 1, 0, 0, STEMB200_EPI_GDN, 1.f, F16, 0, 0), 20000},
-      {"k_igdn_192", mk(1, 20, 36, {192}, 192, 1, 1, 0, 0, STEMB200_EPI_IGDN, 1.f, F16, 0, 0), 20000},
       {"l_deconv5_256_256", mk(2, 9, 15, {256}, 256, 5, 2, 1, 0, LIN, 0.01f, F16, 0, 0), 20000},
       {"m_deconv5_192_192_sq", mk(1, 17, 30, {192}, 192, 5, 2, 1, 0, LIN, 1.f, F16, 1, 0), 20000},
       {"n_masked5_192_384", mk(1, 20, 36, {192}, 384, 5, 1, 0, 0xFFFu, LIN, 1.f, F16, 0, 0), 20000},
@@ -296,7 +359,6 @@ int main(int argc, char** argv) {
       {"P_tpm0_5x5_192_256_b11", mk(11, 68, 120, {192}, 256, 5, 1, 0, 0, LIN, 0.01f, F16, 0, 0), 4000},
       {"P_ga2_5x5s2_192_192_b2", mk(2, 544, 960, {192}, 192, 5, 2, 0, 0, LIN, 1.f, F16, 1, 0), 4000},
       {"P_gs4_deconv_192_192_b2", mk(2, 272, 480, {192}, 192, 5, 2, 1, 0, LIN, 1.f, F16, 1, 0), 4000},
-      {"P_gdn_192_b2", mk(2, 544, 960, {192}, 192, 1, 1, 0, 0, STEMB200_EPI_GDN, 1.f, F16, 0, 0), 4000},
       {"P_epm0_cat3_768_b11", mk(11, 68, 120, {384, 384, 384}, 768, 1, 1, 0, 0, LIN, 0.01f, F16, 0, 0), 4000},
       {"P_gs6_3x3_192_16_b2", mk(2, 544, 960, {192}, 16, 3, 1, 0, 0, LIN, 1.f, F32, 0, 1), 4000},
   };
@@ -308,6 +370,22 @@ int main(int argc, char** argv) {
       printf("fatal CUDA error, stopping\n");
       return 2;
     }
+    fails += r;
+  }
+  struct GCase { std::string name; stemb200_conv_desc d; int inv; int px; bool perf; };
+  std::vector<GCase> gcases = {
+      {"G_conv5s2_gdn", mk(2, 40, 72, {192}, 192, 5, 2, 0, 0, LIN, 1.f, F16, 0, 0), 0, 150, false},
+      {"G_gemm128_gdn", mk(1, 24, 40, {128}, 192, 1, 1, 0, 0, LIN, 1.f, F16, 0, 0), 0, 300, false},
+      {"G_deconv5_igdn", mk(2, 17, 30, {192}, 192, 5, 2, 1, 0, LIN, 1.f, F16, 0, 0), 1, 150, false},
+      {"G_P_ga2_gdn_b2", mk(2, 544, 960, {192}, 192, 5, 2, 0, 0, LIN, 1.f, F16, 0, 0), 0, 40, true},
+      {"G_P_ga0_gemm_gdn_b2", mk(2, 544, 960, {128}, 192, 1, 1, 0, 0, LIN, 1.f, F16, 0, 0), 0, 100, true},
+      {"G_P_gs4_deconv_igdn_b2", mk(2, 272, 480, {192}, 192, 5, 2, 1, 0, LIN, 1.f, F16, 0, 0), 1, 40, true},
+  };
+  for (auto& c : gcases) {
+    if (filter && c.name.find(filter) == std::string::npos) continue;
+    if (c.perf && !timing) continue;
+    int r = run_gdn_case(c.name, c.d, c.inv, c.px, c.perf && timing);
+    if (r == 2) { printf("fatal CUDA error, stopping\n"); return 2; }
     fails += r;
   }
   if (timing)

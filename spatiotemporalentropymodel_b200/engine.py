@@ -5,9 +5,9 @@ streams and parameter storage only.  Nothing here falls back to torch ops for co
 missing library raises.
 
 Kernel chains (reference lines in parentheses):
-  analysis   g_a  (priors.py:421-429)      im2col -> [GEMM+x^2] -> GDN -> [conv s2+x^2] -> GDN -> ... -> conv s2 (fp32 y)
+  analysis   g_a  (priors.py:421-429)      im2col -> [GEMM+GDN] -> [conv s2+GDN] x2 -> conv s2 (fp32 y)
   STEM            (spatiotemporalpriors.py:561-585 and variants) HE -> EB -> HD, TPM, ctx, EPM -> GC
-  synthesis  g_s  (priors.py:431-439,397-402)  [deconv+x^2] -> IGDN -> ... -> merged-phase deconv -> tail (clamp, MSE)
+  synthesis  g_s  (priors.py:431-439,397-402)  [deconv+IGDN] x3 -> merged-phase deconv -> tail (clamp, MSE)
 """
 from __future__ import annotations
 
@@ -18,7 +18,7 @@ import torch
 import torch.nn.functional as F
 
 from . import _lib
-from ._lib import DT_F16, DT_F32, EPI_GDN, EPI_IGDN, EPI_LINEAR, ConvDesc
+from ._lib import DT_F16, DT_F32, ConvDesc
 
 Tensor = torch.Tensor
 MASK_A_5x5 = 0x00000FFF  # taps (r, s) with r < 2, or r == 2 and s < 2 (layers/layers.py:39-42)
@@ -63,14 +63,16 @@ class ConvOp:
     """One packed convolution: geometry + repacked fp16 weight matrix + fp32 bias on the device."""
 
     def __init__(self, weight: Tensor, bias: Tensor, *, c_in: Sequence[int], c_out: int, k: int, stride: int = 1,
-                 transposed: bool = False, tap_mask: int = 0, epilogue: int = EPI_LINEAR, slope: float = 1.0,
-                 out_dtype: int = DT_F16, write_sq: bool = False, direct_store: bool = False):
+                 transposed: bool = False, tap_mask: int = 0, slope: float = 1.0, out_dtype: int = DT_F16,
+                 direct_store: bool = False, gdn: Optional[Tuple[Tensor, Tensor, bool]] = None):
+        """gdn = (beta', gamma', inverse) with the re-parametrised beta (C,) / gamma (C, C): the layer is followed
+        by GDN / IGDN and both run in one kernel (stemb200_conv2d_gdn_fwd)."""
         _require_cuda(weight, bias)
         self.lib = _lib.load()
         self.c_in = list(c_in)
         self.c_out = c_out
         self.k, self.stride, self.transposed = k, stride, transposed
-        self.out_dtype, self.write_sq = out_dtype, write_sq
+        self.out_dtype = out_dtype
         d = ConvDesc()
         d.batch, d.h_in, d.w_in = 1, 16, 16
         d.n_src = len(c_in)
@@ -81,10 +83,8 @@ class ConvOp:
         d.stride = stride
         d.transposed = int(transposed)
         d.tap_mask = tap_mask
-        d.epilogue = epilogue
         d.lrelu_slope = slope
         d.out_dtype = out_dtype
-        d.write_sq = int(write_sq)
         d.sq_scale = SQ_SCALE
         d.tile_h = d.tile_w = 0
         d.direct_store = int(direct_store)
@@ -97,7 +97,20 @@ class ConvOp:
         _lib.check(self.lib.stemb200_conv2d_pack_weight(C.byref(d), w32.data_ptr(), self.packed.data_ptr(),
                                                         _stream()), "conv2d_pack_weight")
         self.bias = bias.detach().to(torch.float32).contiguous()
-        self.flops_per_pixel = 2 * K * c_out  # per output pixel of one sub-problem (upper bound for deconv)
+        self.gdn = None
+        if gdn is not None:
+            beta, gamma, inverse = gdn
+            gd = ConvDesc()
+            gd.batch, gd.h_in, gd.w_in, gd.n_src = 1, 8, 8, 1
+            gd.c_in[0] = c_out
+            gd.c_out, gd.kh, gd.kw, gd.stride = c_out, 1, 1, 1
+            gd.lrelu_slope, gd.out_dtype, gd.sq_scale = 1.0, DT_F16, SQ_SCALE
+            g32 = gamma.detach().to(weight.device, torch.float32).reshape(c_out, c_out, 1, 1).contiguous()
+            self.gamma_packed = torch.empty((c_out, c_out), dtype=torch.float16, device=weight.device)
+            _lib.check(self.lib.stemb200_conv2d_pack_weight(C.byref(gd), g32.data_ptr(), self.gamma_packed.data_ptr(),
+                                                            _stream()), "conv2d_pack_weight(gamma)")
+            self.beta = beta.detach().to(weight.device, torch.float32).contiguous()
+            self.gdn = bool(inverse)
 
     def out_hw(self, h: int, w: int) -> Tuple[int, int]:
         if self.transposed:
@@ -107,14 +120,17 @@ class ConvOp:
             return (h + 2 * p - self.k) // 2 + 1, (w + 2 * p - self.k) // 2 + 1
         return h, w
 
-    def __call__(self, inputs: Sequence[Tensor], batch: int, h: int, w: int, out: Tensor,
-                 aux: Optional[Tensor] = None, out_sq: Optional[Tensor] = None) -> Tensor:
+    def __call__(self, inputs: Sequence[Tensor], batch: int, h: int, w: int, out: Tensor) -> Tensor:
         d = self.desc
         d.batch, d.h_in, d.w_in = batch, h, w
         arr = (C.c_void_p * len(inputs))(*[t.data_ptr() for t in inputs])
-        _lib.check(self.lib.stemb200_conv2d_fwd(C.byref(d), arr, self.packed.data_ptr(), self.bias.data_ptr(),
-                                                _ptr(aux), out.data_ptr(), _ptr(out_sq), _stream()),
-                   "conv2d_fwd")
+        if self.gdn is None:
+            _lib.check(self.lib.stemb200_conv2d_fwd(C.byref(d), arr, self.packed.data_ptr(), self.bias.data_ptr(),
+                                                    out.data_ptr(), _stream()), "conv2d_fwd")
+        else:
+            _lib.check(self.lib.stemb200_conv2d_gdn_fwd(C.byref(d), arr, self.packed.data_ptr(), self.bias.data_ptr(),
+                                                        self.gamma_packed.data_ptr(), self.beta.data_ptr(),
+                                                        int(self.gdn), out.data_ptr(), _stream()), "conv2d_gdn_fwd")
         return out
 
 
@@ -188,25 +204,24 @@ class TransformsEngine:
         # --- analysis
         w0 = g("g_a.0.weight")  # (N, 3, 5, 5) -> (N, 128): k = (r*5+s)*3 + ch, zero padded
         w0 = F.pad(w0.permute(0, 2, 3, 1).reshape(N, 75), (0, 128 - 75)).reshape(N, 128, 1, 1).contiguous()
-        self.ga_conv = [ConvOp(w0, g("g_a.0.bias"), c_in=[128], c_out=N, k=1, write_sq=True)]
+        if N != 192:
+            raise ValueError("the fused conv+GDN kernel is built for N = 192 channels (mbt2018 quality 1-8)")
+
+        def gdn_of(name, inverse):
+            beta, gamma = _gdn_fold(g(f"{name}.beta"), g(f"{name}.gamma"))
+            return (beta, gamma, inverse)
+
+        self.ga_conv = [ConvOp(w0, g("g_a.0.bias"), c_in=[128], c_out=N, k=1, gdn=gdn_of("g_a.1", False))]
         for i in (2, 4):
             self.ga_conv.append(ConvOp(g(f"g_a.{i}.weight"), g(f"g_a.{i}.bias"), c_in=[N], c_out=N, k=5, stride=2,
-                                       write_sq=True))
+                                       gdn=gdn_of(f"g_a.{i + 1}", False)))
         self.ga_conv.append(ConvOp(g("g_a.6.weight"), g("g_a.6.bias"), c_in=[N], c_out=M, k=5, stride=2,
                                    out_dtype=DT_F32))
-        self.ga_gdn = []
-        for i in (1, 3, 5):
-            beta, gamma = _gdn_fold(g(f"g_a.{i}.beta"), g(f"g_a.{i}.gamma"))
-            self.ga_gdn.append(ConvOp(gamma.reshape(N, N, 1, 1), beta, c_in=[N], c_out=N, k=1, epilogue=EPI_GDN))
         # --- synthesis
         self.gs_conv = []
         for i, cin in ((0, M), (2, N), (4, N)):
             self.gs_conv.append(ConvOp(g(f"g_s.{i}.weight"), g(f"g_s.{i}.bias"), c_in=[cin], c_out=N, k=5, stride=2,
-                                       transposed=True, write_sq=True))
-        self.gs_gdn = []
-        for i in (1, 3, 5):
-            beta, gamma = _gdn_fold(g(f"g_s.{i}.beta"), g(f"g_s.{i}.gamma"))
-            self.gs_gdn.append(ConvOp(gamma.reshape(N, N, 1, 1), beta, c_in=[N], c_out=N, k=1, epilogue=EPI_IGDN))
+                                       transposed=True, gdn=gdn_of(f"g_s.{i + 1}", True)))
         # last deconv (N -> 3): the four output phases merged into one 3x3 conv with 12 (+4 pad) outputs:
         #   x_hat[c][2i+p][2j+q] = sum_{u,v} in[i+u-1][j+v-1] . W[:, c, p+4-2u, q+4-2v]
         wt = g("g_s.6.weight")  # (N, 3, 5, 5) ConvTranspose layout (in, out, kh, kw)
@@ -245,11 +260,7 @@ class TransformsEngine:
         for li in range(3):
             conv = self.ga_conv[li]
             ho, wo = conv.out_hw(h, w) if li else (h, w)
-            xb = ws.get(f"ga_x{li}", (B, ho, wo, N), torch.float16)
-            sq = ws.get(f"ga_sq{li}", (B, ho, wo, N), torch.float16)
-            conv([cur], B, h, w, xb, out_sq=sq)
-            gb = ws.get(f"ga_g{li}", (B, ho, wo, N), torch.float16)
-            self.ga_gdn[li]([sq], B, ho, wo, gb, aux=xb)
+            gb = conv([cur], B, h, w, ws.get(f"ga_g{li}", (B, ho, wo, N), torch.float16))
             cur, h, w = gb, ho, wo
         conv = self.ga_conv[3]
         ho, wo = conv.out_hw(h, w)
@@ -267,11 +278,7 @@ class TransformsEngine:
         cur = y_hat16
         for li in range(3):
             ho, wo = 2 * h, 2 * w
-            xb = ws.get(f"gs_x{li}", (B, ho, wo, N), torch.float16)
-            sq = ws.get(f"gs_sq{li}", (B, ho, wo, N), torch.float16)
-            self.gs_conv[li]([cur], B, h, w, xb, out_sq=sq)
-            gb = ws.get(f"gs_g{li}", (B, ho, wo, N), torch.float16)
-            self.gs_gdn[li]([sq], B, ho, wo, gb, aux=xb)
+            gb = self.gs_conv[li]([cur], B, h, w, ws.get(f"gs_g{li}", (B, ho, wo, N), torch.float16))
             cur, h, w = gb, ho, wo
         merged = ws.get("gs_merged", (B, h, w, 16), torch.float32)
         self.gs_last([cur], B, h, w, merged)
