@@ -47,7 +47,8 @@ typedef struct stemb200_conv_desc {
   int32_t batch;        /* N */
   int32_t h_in, w_in;   /* input spatial size (all sources share it) */
   int32_t n_src;        /* 1..3 inputs concatenated along channels (torch.cat(..., 1) folded into K) */
-  int32_t c_in[3];      /* channels per source, each a multiple of 64 */
+  int32_t c_in[3];      /* channels per source: multiples of 64 (one source may be any multiple of 8: the
+                           last 64-channel K chunk is then zero-filled by TMA) */
   int32_t c_out;        /* output channels (multiple of 16) */
   int32_t kh, kw;       /* kernel size (1, 3 or 5; square padding k/2) */
   int32_t stride;       /* 1 or 2 */
@@ -93,8 +94,9 @@ int stemb200_nhwc_f16_to_nchw_f32(const void* in, float* out, int32_t n, int32_t
 int stemb200_nhwc_f32_to_nchw_f32(const float* in, float* out, int32_t n, int32_t c, int32_t h, int32_t w,
                                   void* stream);
 /* First analysis conv (3 -> N, k5 s2 p2, priors.py:422) operand staging: im2col of the NCHW fp32 frame into
- * [n*h_out*w_out][128] fp16 rows (75 real taps*channels, zero padded), with the frame embedded at
- * (pad_top, pad_left) inside a zero canvas of h_pad x w_pad (evalSTEM.py:96-109 pads to a multiple of 64). */
+ * [n*h_out*w_out][80] fp16 rows (k = (r*5+s)*3+ch for the 75 real taps*channels, then 5 zeros), with the frame
+ * embedded at (pad_top, pad_left) inside a zero canvas of h_pad x w_pad (evalSTEM.py:96-109 pads to a multiple of
+ * 64). The rows are the NHWC input (C = 80) of a 1x1 stemb200_conv2d_gdn_fwd whose weight is the [N][75] reshape. */
 int stemb200_im2col_k5s2_c3(const float* x_nchw, void* out_rows, int32_t n, int32_t h, int32_t w,
                             int32_t h_pad, int32_t w_pad, int32_t pad_top, int32_t pad_left, void* stream);
 
@@ -140,13 +142,15 @@ int stemb200_entropy_bottleneck_fwd(const float* z_nhwc, const float* params, in
                                     int32_t h, int32_t w, float lik_bound, void* z_hat_nhwc_f16,
                                     float* z_hat_nchw, float* lik_nchw, double* bits, void* stream);
 
-/* Last synthesis step (priors.py:397-402 clamp; evalSTEM.py:29-31,127-129 crop + MSE):
- * in: NHWC fp32 [n][h2][w2][16], channel (p*2+q)*3+ch holds x_hat[ch][2*i+p][2*j+q] (merged-phase deconv);
- * out: x_hat NCHW fp32 [n][3][2*h2][2*w2] clamped to [0,1]; when x_ref != NULL (unpadded NCHW fp32
- * [n][3][h_ref][w_ref], embedded at pad_top/pad_left) sq_err[frame] (double) += sum (x_ref - x_hat)^2. */
-int stemb200_synthesis_tail(const float* in_nhwc16, float* x_hat_nchw, int32_t n, int32_t h2, int32_t w2,
-                            const float* x_ref, int32_t h_ref, int32_t w_ref, int32_t pad_top,
-                            int32_t pad_left, double* sq_err, void* stream);
+/* Last synthesis layer, second half (priors.py:438 deconv(N, 3) + :399 clamp; evalSTEM.py:29-31,127-129 crop +
+ * MSE). The transposed conv itself runs through stemb200_conv2d_fwd as a stride-2 conv over 2x2 input super pixels
+ * (k5 with the r = 0 / s = 0 taps masked = a 4x4 window, 48 (+16 pad) outputs: channel (u*4+v)*3 + c holds
+ * x_hat[c][4i+u][4j+v]); this entry point un-shuffles in: NHWC fp32 [n][h4][w4][64] to x_hat NCHW fp32
+ * [n][3][4*h4][4*w4] clamped to [0,1]. When x_ref != NULL (unpadded NCHW fp32 [n][3][h_ref][w_ref], embedded at
+ * pad_top/pad_left) sq_err[frame] (double) += sum (x_ref - x_hat)^2 over the un-padded area. */
+int stemb200_synthesis_tail(const float* in_nhwc64, float* x_hat_nchw, int32_t n, int32_t h4, int32_t w4,
+                            const float* x_ref, int32_t h_ref, int32_t w_ref, int32_t pad_top, int32_t pad_left,
+                            double* sq_err, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------
  * Host-side helper that the reference implements in C++ (compressai/cpp_exts/ops/ops.cpp:24-81)

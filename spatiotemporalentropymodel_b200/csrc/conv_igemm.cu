@@ -723,6 +723,7 @@ int pick_block_n(int c_out) {
   if (c_out % 256 == 0) return 256;
   if (c_out % 192 == 0) return 192;
   if (c_out % 128 == 0) return 128;
+  if (c_out == 96) return 96;
   if (c_out % 64 == 0) return 64;
   if (c_out == 16) return 16;
   return 0;
@@ -738,14 +739,16 @@ int build_plan(const stemb200_conv_desc& d, Plan& pl) {
   int src_base[3] = {0, 0, 0};
   pl.c_in_total = 0;
   for (int s = 0; s < d.n_src; ++s) {
-    if (d.c_in[s] < kKChunk || d.c_in[s] % kKChunk) return set_error("conv: c_in must be a multiple of 64");
+    const bool ragged_ok = d.n_src == 1 && d.c_in[s] >= 8 && d.c_in[s] % 8 == 0;
+    if ((d.c_in[s] < kKChunk || d.c_in[s] % kKChunk) && !ragged_ok)
+      return set_error("conv: c_in must be a multiple of 64 (or of 8 for a single source)");
     src_base[s] = pl.c_in_total;
     pl.c_in_total += d.c_in[s];
   }
   pl.block_n = pick_block_n(d.c_out);
   if (!pl.block_n) return set_error("conv: unsupported c_out");
   if (pl.block_n < 32 && !d.direct_store) return set_error("conv: c_out < 32 needs direct_store");
-  if (!d.direct_store && d.out_dtype == STEMB200_DT_F16 && (d.c_out % 64)) return set_error("conv: c_out%64");
+  if (!d.direct_store && (d.c_out % 64)) return set_error("conv: the TMA-store epilogue needs c_out % 64 == 0");
 
   const int k = d.kh, pad = k / 2;
   const uint32_t mask = d.tap_mask ? d.tap_mask : ((1u << (k * k)) - 1u);
@@ -1047,6 +1050,7 @@ extern "C" int stemb200_conv2d_fwd(const stemb200_conv_desc* d, const void* cons
   switch (pl.block_n) {
     case 16: return launch_conv<16>(kp, grid, st);
     case 64: return launch_conv<64>(kp, grid, st);
+    case 96: return launch_conv<96>(kp, grid, st);
     case 128: return launch_conv<128>(kp, grid, st);
     case 192: return launch_conv<192>(kp, grid, st);
     case 256: return launch_conv<256>(kp, grid, st);

@@ -86,38 +86,56 @@ __global__ void nhwc_to_nchw_f32_kernel(const TIn* __restrict__ in, float* __res
 }
 
 // ---------------------------------------------------------------------------------------------------
-// first analysis layer operand staging: one warp per output pixel, 128 fp16 per row
-// k = (r*5 + s)*3 + ch for k < 75, zero above
+// first analysis layer operand staging: rows of 80 fp16 per output pixel, k = (r*5 + s)*3 + ch for k < 75
+// (5 zero columns pad the row to 160 bytes; the conv kernel's TMA box zero-fills channels 80..127).
+// One block = 64 consecutive output pixels of one output row: the 5 x 131 x 3 input patch is staged in smem with
+// coalesced reads, then every 16-byte piece of the output rows is written by one thread (fully coalesced).
 // ---------------------------------------------------------------------------------------------------
-__global__ void im2col_k5s2_c3_kernel(const float* __restrict__ x, __half* __restrict__ rows, int n, int h,
-                                      int w, int h_out, int w_out, int pad_top, int pad_left) {
-  const int lane = threadIdx.x & 31;
-  const long long warp_global = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5;
-  const long long n_warps = (gridDim.x * static_cast<long long>(blockDim.x)) >> 5;
-  const long long total = static_cast<long long>(n) * h_out * w_out;
-  for (long long pix = warp_global; pix < total; pix += n_warps) {
-    const int ow = static_cast<int>(pix % w_out);
-    const long long t = pix / w_out;
-    const int oh = static_cast<int>(t % h_out);
-    const int img = static_cast<int>(t / h_out);
-    const float* xi = x + static_cast<long long>(img) * 3 * h * w;
-    __half v[4];
+constexpr int kIm2colRow = 80;
+constexpr int kIm2colPix = 64;
+constexpr int kIm2colInW = 2 * kIm2colPix + 3;  // 131 input columns feed 64 stride-2 outputs of a 5-tap filter
+
+__global__ void __launch_bounds__(256)
+im2col_k5s2_c3_kernel(const float* __restrict__ x, __half* __restrict__ rows, int h, int w, int h_out, int w_out,
+                      int pad_top, int pad_left) {
+  __shared__ float s_in[3][5][kIm2colInW + 1];
+  __shared__ unsigned short s_off[kIm2colRow];  // k -> offset of (ch, r, s) inside s_in, 0xFFFF for the padding
+  const int n = blockIdx.z, oh = blockIdx.y, ow0 = blockIdx.x * kIm2colPix;
+  if (threadIdx.x < kIm2colRow) {
+    const int k = threadIdx.x;
+    unsigned short off = 0xFFFF;
+    if (k < 75) {
+      const int tap = k / 3, ch = k - tap * 3, r = tap / 5, sx = tap - r * 5;
+      off = static_cast<unsigned short>((ch * 5 + r) * (kIm2colInW + 1) + sx);
+    }
+    s_off[k] = off;
+  }
+  const float* xi = x + static_cast<long long>(n) * 3 * h * w;
+  const int ih0 = 2 * oh - 2 - pad_top, iw0 = 2 * ow0 - 2 - pad_left;
+  for (int i = threadIdx.x; i < 3 * 5 * kIm2colInW; i += blockDim.x) {
+    const int col = i % kIm2colInW, rr = (i / kIm2colInW) % 5, ch = i / (5 * kIm2colInW);
+    const int ih = ih0 + rr, iw = iw0 + col;
+    float v = 0.f;
+    if (ih >= 0 && ih < h && iw >= 0 && iw < w) v = __ldg(xi + (static_cast<long long>(ch) * h + ih) * w + iw);
+    s_in[ch][rr][col] = v;
+  }
+  __syncthreads();
+  const float* sf = &s_in[0][0][0];
+  const int npix = min(kIm2colPix, w_out - ow0);
+  uint4* dst = reinterpret_cast<uint4*>(rows + (static_cast<long long>(n) * h_out + oh) * w_out * kIm2colRow +
+                                        static_cast<long long>(ow0) * kIm2colRow);
+  for (int q = threadIdx.x; q < npix * (kIm2colRow / 8); q += blockDim.x) {
+    const int px = q / (kIm2colRow / 8), piece = q - px * (kIm2colRow / 8);
+    uint32_t pk[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const int k = lane * 4 + j;
-      float f = 0.f;
-      if (k < 75) {
-        const int tap = k / 3, ch = k - tap * 3;
-        const int r = tap / 5, s = tap - r * 5;
-        const int ih = 2 * oh + r - 2 - pad_top, iw = 2 * ow + s - 2 - pad_left;
-        if (ih >= 0 && ih < h && iw >= 0 && iw < w) f = __ldg(xi + (static_cast<long long>(ch) * h + ih) * w + iw);
-      }
-      v[j] = __float2half_rn(f);
+      const unsigned short o0 = s_off[piece * 8 + 2 * j], o1 = s_off[piece * 8 + 2 * j + 1];
+      const float f0 = o0 == 0xFFFF ? 0.f : sf[o0 + 2 * px];
+      const float f1 = o1 == 0xFFFF ? 0.f : sf[o1 + 2 * px];
+      const __half2 hh = __floats2half2_rn(f0, f1);
+      pk[j] = *reinterpret_cast<const uint32_t*>(&hh);
     }
-    uint2 pk;
-    pk.x = static_cast<uint32_t>(__half_as_ushort(v[0])) | (static_cast<uint32_t>(__half_as_ushort(v[1])) << 16);
-    pk.y = static_cast<uint32_t>(__half_as_ushort(v[2])) | (static_cast<uint32_t>(__half_as_ushort(v[3])) << 16);
-    reinterpret_cast<uint2*>(rows + pix * 128)[lane] = pk;
+    dst[q] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
   }
 }
 
@@ -355,23 +373,29 @@ __global__ void eb_fwd_kernel(const float* __restrict__ z, const float* __restri
 }
 
 // ---------------------------------------------------------------------------------------------------
-// synthesis tail: merged-phase [n][h2][w2][16] -> NCHW [n][3][2*h2][2*w2], clamp, squared error
+// synthesis tail. The last transposed conv (N -> 3, k5 s2 p2 op1, priors.py:438) runs on the tensor cores as a
+// stride-2 conv over 2x2 input "super pixels" with 4x4x3 = 48 outputs each (channel (u*4+v)*3 + c holds
+// x_hat[c][4i+u][4j+v]); this kernel un-shuffles that to NCHW, clamps to [0, 1] (priors.py:399) and accumulates
+// the squared error against the unpadded frame (evalSTEM.py:29-31,127-129). One thread = one super pixel.
 // ---------------------------------------------------------------------------------------------------
-__global__ void synthesis_tail_kernel(const float* __restrict__ in, float* __restrict__ xhat, int h2, int w2,
-                                      const float* __restrict__ xref, int h_ref, int w_ref, int pad_top,
-                                      int pad_left, double* sq_err) {
+constexpr int kTailCh = 64;
+
+__global__ void __launch_bounds__(256)
+synthesis_tail_kernel(const float* __restrict__ in, float* __restrict__ xhat, int h4, int w4,
+                      const float* __restrict__ xref, int h_ref, int w_ref, int pad_top, int pad_left,
+                      double* sq_err) {
   __shared__ float red[32];
   const int n = blockIdx.y;
-  const long long per = static_cast<long long>(h2) * w2;
-  const int H = 2 * h2, W = 2 * w2;
+  const long long per = static_cast<long long>(h4) * w4;
+  const int H = 4 * h4, W = 4 * w4;
   float acc = 0.f;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < per;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int ii = static_cast<int>(i / w2), jj = static_cast<int>(i - static_cast<long long>(ii) * w2);
-    const float4* src = reinterpret_cast<const float4*>(in + (static_cast<long long>(n) * per + i) * 16);
-    float v[16];
+    const int ii = static_cast<int>(i / w4), jj = static_cast<int>(i - static_cast<long long>(ii) * w4);
+    const float4* src = reinterpret_cast<const float4*>(in + (static_cast<long long>(n) * per + i) * kTailCh);
+    float v[48];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
+    for (int k = 0; k < 12; ++k) {
       const float4 f = __ldg(src + k);
       v[4 * k] = f.x;
       v[4 * k + 1] = f.y;
@@ -381,24 +405,24 @@ __global__ void synthesis_tail_kernel(const float* __restrict__ in, float* __res
 #pragma unroll
     for (int ch = 0; ch < 3; ++ch) {
 #pragma unroll
-      for (int p = 0; p < 2; ++p) {
-        const int Y = 2 * ii + p;
-        float a = fminf(fmaxf(v[(p * 2 + 0) * 3 + ch], 0.f), 1.f);
-        float b = fminf(fmaxf(v[(p * 2 + 1) * 3 + ch], 0.f), 1.f);
-        const long long o = ((static_cast<long long>(n) * 3 + ch) * H + Y) * W + 2 * jj;
-        *reinterpret_cast<float2*>(xhat + o) = make_float2(a, b);
+      for (int u = 0; u < 4; ++u) {
+        const int Y = 4 * ii + u;
+        float o[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) o[q] = fminf(fmaxf(v[(u * 4 + q) * 3 + ch], 0.f), 1.f);
+        const long long off = ((static_cast<long long>(n) * 3 + ch) * H + Y) * W + 4 * jj;
+        *reinterpret_cast<float4*>(xhat + off) = make_float4(o[0], o[1], o[2], o[3]);
         if (xref) {
           const int yr = Y - pad_top;
           if (yr >= 0 && yr < h_ref) {
             const float* rrow = xref + ((static_cast<long long>(n) * 3 + ch) * h_ref + yr) * w_ref;
-            const int x0 = 2 * jj - pad_left;
-            if (x0 >= 0 && x0 < w_ref) {
-              const float d = rrow[x0] - a;
-              acc += d * d;
-            }
-            if (x0 + 1 >= 0 && x0 + 1 < w_ref) {
-              const float d = rrow[x0 + 1] - b;
-              acc += d * d;
+            const int x0 = 4 * jj - pad_left;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              if (x0 + q >= 0 && x0 + q < w_ref) {
+                const float d = __ldg(rrow + x0 + q) - o[q];
+                acc += d * d;
+              }
             }
           }
         }
@@ -457,10 +481,10 @@ extern "C" int stemb200_im2col_k5s2_c3(const float* x_nchw, void* out_rows, int3
   if (!x_nchw || !out_rows || n < 1 || h < 1 || w < 1 || h_pad < h || w_pad < w || pad_top < 0 || pad_left < 0)
     return set_error("im2col: bad argument");
   const int h_out = (h_pad - 1) / 2 + 1, w_out = (w_pad - 1) / 2 + 1;
-  const long long total = static_cast<long long>(n) * h_out * w_out;
-  const int blocks = static_cast<int>(std::min<long long>((total + 7) / 8, 148LL * 64));
-  im2col_k5s2_c3_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      x_nchw, static_cast<__half*>(out_rows), n, h, w, h_out, w_out, pad_top, pad_left);
+  if (h_out > 65535 || n > 65535) return set_error("im2col: frame too large");
+  dim3 grid((w_out + kIm2colPix - 1) / kIm2colPix, h_out, n);
+  im2col_k5s2_c3_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      x_nchw, static_cast<__half*>(out_rows), h, w, h_out, w_out, pad_top, pad_left);
   CHECK_LAUNCH("im2col_k5s2_c3");
   return 0;
 }
@@ -529,14 +553,14 @@ extern "C" int stemb200_entropy_bottleneck_fwd(const float* z_nhwc, const float*
   return 0;
 }
 
-extern "C" int stemb200_synthesis_tail(const float* in_nhwc16, float* x_hat_nchw, int32_t n, int32_t h2,
-                                       int32_t w2, const float* x_ref, int32_t h_ref, int32_t w_ref,
+extern "C" int stemb200_synthesis_tail(const float* in_nhwc64, float* x_hat_nchw, int32_t n, int32_t h4,
+                                       int32_t w4, const float* x_ref, int32_t h_ref, int32_t w_ref,
                                        int32_t pad_top, int32_t pad_left, double* sq_err, void* stream) {
-  if (!in_nhwc16 || !x_hat_nchw || n < 1 || h2 < 1 || w2 < 1) return set_error("synthesis_tail: bad argument");
-  const long long per = static_cast<long long>(h2) * w2;
-  dim3 grid(static_cast<unsigned>(std::min<long long>((per + 255) / 256, 148LL * 8)), n);
+  if (!in_nhwc64 || !x_hat_nchw || n < 1 || h4 < 1 || w4 < 1) return set_error("synthesis_tail: bad argument");
+  const long long per = static_cast<long long>(h4) * w4;
+  dim3 grid(static_cast<unsigned>(std::min<long long>((per + 255) / 256, 148LL * 16)), n);
   synthesis_tail_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      in_nhwc16, x_hat_nchw, h2, w2, x_ref, h_ref, w_ref, pad_top, pad_left, sq_err);
+      in_nhwc64, x_hat_nchw, h4, w4, x_ref, h_ref, w_ref, pad_top, pad_left, sq_err);
   CHECK_LAUNCH("synthesis_tail");
   return 0;
 }

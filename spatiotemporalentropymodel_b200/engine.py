@@ -202,8 +202,8 @@ class TransformsEngine:
         M = sd["g_a.6.weight"].shape[0]
         self.N, self.M = N, M
         # --- analysis
-        w0 = g("g_a.0.weight")  # (N, 3, 5, 5) -> (N, 128): k = (r*5+s)*3 + ch, zero padded
-        w0 = F.pad(w0.permute(0, 2, 3, 1).reshape(N, 75), (0, 128 - 75)).reshape(N, 128, 1, 1).contiguous()
+        w0 = g("g_a.0.weight")  # (N, 3, 5, 5) -> (N, 80): k = (r*5+s)*3 + ch, zero padded (im2col row layout)
+        w0 = F.pad(w0.permute(0, 2, 3, 1).reshape(N, 75), (0, 80 - 75)).reshape(N, 80, 1, 1).contiguous()
         if N != 192:
             raise ValueError("the fused conv+GDN kernel is built for N = 192 channels (mbt2018 quality 1-8)")
 
@@ -211,7 +211,7 @@ class TransformsEngine:
             beta, gamma = _gdn_fold(g(f"{name}.beta"), g(f"{name}.gamma"))
             return (beta, gamma, inverse)
 
-        self.ga_conv = [ConvOp(w0, g("g_a.0.bias"), c_in=[128], c_out=N, k=1, gdn=gdn_of("g_a.1", False))]
+        self.ga_conv = [ConvOp(w0, g("g_a.0.bias"), c_in=[80], c_out=N, k=1, gdn=gdn_of("g_a.1", False))]
         for i in (2, 4):
             self.ga_conv.append(ConvOp(g(f"g_a.{i}.weight"), g(f"g_a.{i}.bias"), c_in=[N], c_out=N, k=5, stride=2,
                                        gdn=gdn_of(f"g_a.{i + 1}", False)))
@@ -222,25 +222,31 @@ class TransformsEngine:
         for i, cin in ((0, M), (2, N), (4, N)):
             self.gs_conv.append(ConvOp(g(f"g_s.{i}.weight"), g(f"g_s.{i}.bias"), c_in=[cin], c_out=N, k=5, stride=2,
                                        transposed=True, gdn=gdn_of(f"g_s.{i + 1}", True)))
-        # last deconv (N -> 3): the four output phases merged into one 3x3 conv with 12 (+4 pad) outputs:
-        #   x_hat[c][2i+p][2j+q] = sum_{u,v} in[i+u-1][j+v-1] . W[:, c, p+4-2u, q+4-2v]
+        # last deconv (N -> 3, k5 s2 p2 op1) as a stride-2 conv over 2x2 input super pixels: output super pixel
+        # (i, j) holds the 4x4x3 block x_hat[c][4i+u][4j+v]; it reads input rows 2i + a, a = R - 2 in {-1, 0, 1, 2}
+        # (k5 taps with R = 0 / S = 0 masked), and the deconv tap is r = u + 2 - 2a = u + 6 - 2R (0 outside 0..4).
+        # Each input tile is then fetched for 16 taps per 4 pixels instead of 9 taps per pixel (L2 traffic / 2.25).
         wt = g("g_s.6.weight")  # (N, 3, 5, 5) ConvTranspose layout (in, out, kh, kw)
-        wm = torch.zeros((16, N, 3, 3), device=dev)
-        bm = torch.zeros(16, device=dev)
+        wm = torch.zeros((64, N, 5, 5), device=dev)
+        bm = torch.zeros(64, device=dev)
         b6 = g("g_s.6.bias")
-        for p in range(2):
-            for q in range(2):
-                for u in range(3):
-                    r = p + 4 - 2 * u
-                    if r > 4:
+        mask = 0
+        for R in range(1, 5):
+            for S in range(1, 5):
+                mask |= 1 << (R * 5 + S)
+                for u in range(4):
+                    r = u + 6 - 2 * R
+                    if r < 0 or r > 4:
                         continue
-                    for v in range(3):
-                        s = q + 4 - 2 * v
-                        if s > 4:
+                    for v in range(4):
+                        s_ = v + 6 - 2 * S
+                        if s_ < 0 or s_ > 4:
                             continue
-                        wm[(p * 2 + q) * 3:(p * 2 + q) * 3 + 3, :, u, v] = wt[:, :, r, s].t()
-                bm[(p * 2 + q) * 3:(p * 2 + q) * 3 + 3] = b6
-        self.gs_last = ConvOp(wm, bm, c_in=[N], c_out=16, k=3, out_dtype=DT_F32, direct_store=True)
+                        o = (u * 4 + v) * 3
+                        wm[o:o + 3, :, R, S] = wt[:, :, r, s_].t()
+        for uv in range(16):
+            bm[uv * 3:uv * 3 + 3] = b6
+        self.gs_last = ConvOp(wm, bm, c_in=[N], c_out=64, k=5, stride=2, tap_mask=mask, out_dtype=DT_F32)
 
     # -------------------------------------------------------------------------------------------------
     def analysis(self, x: Tensor, pad: Tuple[int, int, int, int] = (0, 0, 0, 0)) -> Tuple[Tensor, int, int]:
@@ -253,7 +259,7 @@ class TransformsEngine:
         Hp, Wp = H + top + bottom, W + left + right
         lib, ws, N = _lib.load(), self.ws, self.N
         h, w = (Hp - 1) // 2 + 1, (Wp - 1) // 2 + 1
-        rows = ws.get("ga_rows", (B, h, w, 128), torch.float16)
+        rows = ws.get("ga_rows", (B, h, w, 80), torch.float16)
         _lib.check(lib.stemb200_im2col_k5s2_c3(x.data_ptr(), rows.data_ptr(), B, H, W, Hp, Wp, top, left,
                                                _stream()), "im2col_k5s2_c3")
         cur = rows
@@ -280,7 +286,9 @@ class TransformsEngine:
             ho, wo = 2 * h, 2 * w
             gb = self.gs_conv[li]([cur], B, h, w, ws.get(f"gs_g{li}", (B, ho, wo, N), torch.float16))
             cur, h, w = gb, ho, wo
-        merged = ws.get("gs_merged", (B, h, w, 16), torch.float32)
+        if h % 2 or w % 2:
+            raise ValueError("synthesis needs an even latent size at the last layer")
+        merged = ws.get("gs_merged", (B, h // 2, w // 2, 64), torch.float32)
         self.gs_last([cur], B, h, w, merged)
         if out is None:
             out = ws.get("gs_xhat", (B, 3, 2 * h, 2 * w), torch.float32)
@@ -288,8 +296,8 @@ class TransformsEngine:
         href = wref = 0
         if x_ref is not None:
             href, wref = x_ref.shape[2], x_ref.shape[3]
-        _lib.check(lib.stemb200_synthesis_tail(merged.data_ptr(), out.data_ptr(), B, h, w, _ptr(x_ref), href, wref,
-                                               top, left, _ptr(sq_err), _stream()), "synthesis_tail")
+        _lib.check(lib.stemb200_synthesis_tail(merged.data_ptr(), out.data_ptr(), B, h // 2, w // 2, _ptr(x_ref), href,
+                                               wref, top, left, _ptr(sq_err), _stream()), "synthesis_tail")
         return out
 
 
