@@ -271,20 +271,22 @@ conv_igemm_kernel(const __grid_constant__ ConvKernelParams p) {
 
       constexpr int kCols = (BLOCK_N >= 32) ? 32 : 16;
       constexpr int kChunks = BLOCK_N / kCols;
+      // TMEM loads are software pipelined: chunk ci+2 is requested before chunk ci is processed
+      uint32_t rn[kCols];
+      if (half < kChunks) {
+        if constexpr (kCols == 32) tmem_ld_32x32(t_row + half * kCols, rn);
+        else tmem_ld_32x16(t_row + half * kCols, rn);
+      }
 #pragma unroll 1
       for (int ci = half; ci < kChunks; ci += 2) {
         const int c = ci * kCols;
         float v[kCols];
-        {
-          uint32_t r[kCols];
-          if constexpr (kCols == 32) {
-            tmem_ld_32x32(t_row + c, r);
-          } else {
-            tmem_ld_32x16(t_row + c, r);
-          }
-          tmem_ld_wait();
+        tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < kCols; ++i) v[i] = __uint_as_float(r[i]);
+        for (int i = 0; i < kCols; ++i) v[i] = __uint_as_float(rn[i]);
+        if (ci + 2 < kChunks) {
+          if constexpr (kCols == 32) tmem_ld_32x32(t_row + c + 2 * kCols, rn);
+          else tmem_ld_32x16(t_row + c + 2 * kCols, rn);
         }
         const int ch0 = t.n0 + c;
 #pragma unroll
@@ -561,46 +563,49 @@ conv_gdn_kernel(const __grid_constant__ ConvKernelParams p) {
       const uint32_t par = it & 1;
       mbar_wait(tfull_bar, par);
       tc_fence_after();
-      // ---- phase 1: x = A + bias -> stash (TMEM, packed fp16), x^2 -> smem operand
-#pragma unroll 1
-      for (int g = 0; g < BLOCK_N / 64; ++g) {
-        const int c = 64 * g + 32 * half;
-        // this 64-channel buffer was the staging of the previous tile's output store (groups complete in order)
-        if (etid == 0) {
-          if (g == 0) tma_store_wait_read<2>();
-          else if (g == 1) tma_store_wait_read<1>();
-          else tma_store_wait_read<0>();
-        }
-        named_bar_sync(1, kNumEpiThreads);
-        uint32_t r[32];
-        tmem_ld_32x32(tmem_base + lane_off + Cfg::kAccCol + c, r);
-        tmem_ld_wait();
-        uint32_t hx[16], hq[16];
+      // ---- phase 1: x = A + bias -> stash (TMEM, packed fp16), x^2 -> smem operand.
+      // The three 64-channel buffers were the staging of the previous tile's output stores: one wait covers them
+      // (those stores were issued a whole main loop ago). TMEM loads are double buffered in registers so the load
+      // of chunk g+1 overlaps the arithmetic of chunk g.
+      if (etid == 0) tma_store_wait_read<0>();
+      named_bar_sync(1, kNumEpiThreads);
+      {
+        uint32_t r[2][32];
+        tmem_ld_32x32(tmem_base + lane_off + Cfg::kAccCol + 32 * half, r[0]);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          float b0, b1, b2, b3;
-          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
-                       : "=f"(b0), "=f"(b1), "=f"(b2), "=f"(b3)
-                       : "r"(bias_smem + 4u * (c + 4 * j)));
-          const __half2 h0 = __floats2half2_rn(__uint_as_float(r[4 * j]) + b0, __uint_as_float(r[4 * j + 1]) + b1);
-          const __half2 h1 =
-              __floats2half2_rn(__uint_as_float(r[4 * j + 2]) + b2, __uint_as_float(r[4 * j + 3]) + b3);
-          hx[2 * j] = *reinterpret_cast<const uint32_t*>(&h0);
-          hx[2 * j + 1] = *reinterpret_cast<const uint32_t*>(&h1);
-          // square the value that is actually normalised (the fp16-rounded x), prescaled to stay in range
-          const float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
-          const float q0 = f0.x * p.sq_scale, q1 = f0.y * p.sq_scale, q2 = f1.x * p.sq_scale, q3 = f1.y * p.sq_scale;
-          hq[2 * j] = pack_half2(q0 * q0, q1 * q1);
-          hq[2 * j + 1] = pack_half2(q2 * q2, q3 * q3);
-        }
-        tmem_st_32x16(tmem_base + lane_off + Cfg::kStashCol + (c >> 1), hx);
-        const uint32_t cbase = a2_base + static_cast<uint32_t>(g) * kAStageBytes + row_off;
+        for (int g = 0; g < BLOCK_N / 64; ++g) {
+          const int c = 64 * g + 32 * half;
+          tmem_ld_wait();
+          if (g + 1 < BLOCK_N / 64) tmem_ld_32x32(tmem_base + lane_off + Cfg::kAccCol + c + 64, r[(g + 1) & 1]);
+          uint32_t hx[16], hq[16];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const uint32_t addr = cbase + (((static_cast<uint32_t>(j) + jo) ^ rsw) << 4);
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(hq[4 * j]), "r"(hq[4 * j + 1]),
-                       "r"(hq[4 * j + 2]), "r"(hq[4 * j + 3])
-                       : "memory");
+          for (int j = 0; j < 8; ++j) {
+            float b0, b1, b2, b3;
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                         : "=f"(b0), "=f"(b1), "=f"(b2), "=f"(b3)
+                         : "r"(bias_smem + 4u * (c + 4 * j)));
+            const uint32_t* rr = r[g & 1];
+            const __half2 h0 = __floats2half2_rn(__uint_as_float(rr[4 * j]) + b0, __uint_as_float(rr[4 * j + 1]) + b1);
+            const __half2 h1 =
+                __floats2half2_rn(__uint_as_float(rr[4 * j + 2]) + b2, __uint_as_float(rr[4 * j + 3]) + b3);
+            hx[2 * j] = *reinterpret_cast<const uint32_t*>(&h0);
+            hx[2 * j + 1] = *reinterpret_cast<const uint32_t*>(&h1);
+            // square the value that is actually normalised (the fp16-rounded x), prescaled to stay in range
+            const float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
+            const float q0 = f0.x * p.sq_scale, q1 = f0.y * p.sq_scale, q2 = f1.x * p.sq_scale,
+                        q3 = f1.y * p.sq_scale;
+            hq[2 * j] = pack_half2(q0 * q0, q1 * q1);
+            hq[2 * j + 1] = pack_half2(q2 * q2, q3 * q3);
+          }
+          tmem_st_32x16(tmem_base + lane_off + Cfg::kStashCol + (c >> 1), hx);
+          const uint32_t cbase = a2_base + static_cast<uint32_t>(g) * kAStageBytes + row_off;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const uint32_t addr = cbase + (((static_cast<uint32_t>(j) + jo) ^ rsw) << 4);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(hq[4 * j]), "r"(hq[4 * j + 1]),
+                         "r"(hq[4 * j + 2]), "r"(hq[4 * j + 3])
+                         : "memory");
+          }
         }
       }
       tmem_st_wait();
@@ -609,53 +614,63 @@ conv_gdn_kernel(const __grid_constant__ ConvKernelParams p) {
       __syncwarp();
       if (lane == 0) mbar_arrive(a2rdy_bar);
 
-      // ---- phase 2: out = x * (r)sqrt(beta + gamma.x^2), staged per 64 channels, TMA store
+      // ---- phase 2: out = x * (r)sqrt(beta + gamma.x^2) into the (now free) x^2 buffers, then three TMA stores
       mbar_wait(nfull_bar, par);
       tc_fence_after();
-#pragma unroll 1
-      for (int g = 0; g < BLOCK_N / 64; ++g) {
-        const int c = 64 * g + 32 * half;
-        uint32_t r[32], hx[16];
-        tmem_ld_32x32(tmem_base + lane_off + Cfg::kNormCol + c, r);
-        tmem_ld_32x16(tmem_base + lane_off + Cfg::kStashCol + (c >> 1), hx);
-        tmem_ld_wait();
-        uint32_t ho[16];
+      {
+        uint32_t r[2][32], hs[2][16];
+        tmem_ld_32x32(tmem_base + lane_off + Cfg::kNormCol + 32 * half, r[0]);
+        tmem_ld_32x16(tmem_base + lane_off + Cfg::kStashCol + 16 * half, hs[0]);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          float b0, b1, b2, b3;
-          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
-                       : "=f"(b0), "=f"(b1), "=f"(b2), "=f"(b3)
-                       : "r"(beta_smem + 4u * (c + 4 * j)));
-          const float2 x0 = __half22float2(*reinterpret_cast<const __half2*>(&hx[2 * j]));
-          const float2 x1 = __half22float2(*reinterpret_cast<const __half2*>(&hx[2 * j + 1]));
-          const float n0 = fmaf(__uint_as_float(r[4 * j]), p.sq_inv, b0);
-          const float n1 = fmaf(__uint_as_float(r[4 * j + 1]), p.sq_inv, b1);
-          const float n2 = fmaf(__uint_as_float(r[4 * j + 2]), p.sq_inv, b2);
-          const float n3 = fmaf(__uint_as_float(r[4 * j + 3]), p.sq_inv, b3);
-          float f0, f1, f2, f3;
-          if (p.igdn) {
-            f0 = approx_sqrt(n0), f1 = approx_sqrt(n1), f2 = approx_sqrt(n2), f3 = approx_sqrt(n3);
-          } else {
-            f0 = approx_rsqrt(n0), f1 = approx_rsqrt(n1), f2 = approx_rsqrt(n2), f3 = approx_rsqrt(n3);
+        for (int g = 0; g < BLOCK_N / 64; ++g) {
+          const int c = 64 * g + 32 * half;
+          tmem_ld_wait();
+          if (g + 1 < BLOCK_N / 64) {
+            tmem_ld_32x32(tmem_base + lane_off + Cfg::kNormCol + c + 64, r[(g + 1) & 1]);
+            tmem_ld_32x16(tmem_base + lane_off + Cfg::kStashCol + ((c + 64) >> 1), hs[(g + 1) & 1]);
           }
-          ho[2 * j] = pack_half2(x0.x * f0, x0.y * f1);
-          ho[2 * j + 1] = pack_half2(x1.x * f2, x1.y * f3);
-        }
-        const uint32_t cbase = a2_base + static_cast<uint32_t>(g) * kAStageBytes + row_off;
+          uint32_t ho[16];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const uint32_t addr = cbase + (((static_cast<uint32_t>(j) + jo) ^ rsw) << 4);
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(ho[4 * j]), "r"(ho[4 * j + 1]),
-                       "r"(ho[4 * j + 2]), "r"(ho[4 * j + 3])
-                       : "memory");
+          for (int j = 0; j < 8; ++j) {
+            float b0, b1, b2, b3;
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                         : "=f"(b0), "=f"(b1), "=f"(b2), "=f"(b3)
+                         : "r"(beta_smem + 4u * (c + 4 * j)));
+            const uint32_t* rr = r[g & 1];
+            const uint32_t* hx = hs[g & 1];
+            const float2 x0 = __half22float2(*reinterpret_cast<const __half2*>(&hx[2 * j]));
+            const float2 x1 = __half22float2(*reinterpret_cast<const __half2*>(&hx[2 * j + 1]));
+            const float n0 = fmaf(__uint_as_float(rr[4 * j]), p.sq_inv, b0);
+            const float n1 = fmaf(__uint_as_float(rr[4 * j + 1]), p.sq_inv, b1);
+            const float n2 = fmaf(__uint_as_float(rr[4 * j + 2]), p.sq_inv, b2);
+            const float n3 = fmaf(__uint_as_float(rr[4 * j + 3]), p.sq_inv, b3);
+            float f0, f1, f2, f3;
+            if (p.igdn) {
+              f0 = approx_sqrt(n0), f1 = approx_sqrt(n1), f2 = approx_sqrt(n2), f3 = approx_sqrt(n3);
+            } else {
+              f0 = approx_rsqrt(n0), f1 = approx_rsqrt(n1), f2 = approx_rsqrt(n2), f3 = approx_rsqrt(n3);
+            }
+            ho[2 * j] = pack_half2(x0.x * f0, x0.y * f1);
+            ho[2 * j + 1] = pack_half2(x1.x * f2, x1.y * f3);
+          }
+          const uint32_t cbase = a2_base + static_cast<uint32_t>(g) * kAStageBytes + row_off;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const uint32_t addr = cbase + (((static_cast<uint32_t>(j) + jo) ^ rsw) << 4);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(ho[4 * j]), "r"(ho[4 * j + 1]),
+                         "r"(ho[4 * j + 2]), "r"(ho[4 * j + 3])
+                         : "memory");
+          }
         }
-        fence_proxy_async_smem();
-        named_bar_sync(1, kNumEpiThreads);
-        if (etid == 0) {
+      }
+      fence_proxy_async_smem();
+      named_bar_sync(1, kNumEpiThreads);
+      if (etid == 0) {
+#pragma unroll
+        for (int g = 0; g < BLOCK_N / 64; ++g)
           tma_store_4d(&p.out_map[t.sub], a2_base + static_cast<uint32_t>(g) * kAStageBytes, 64 * g, t.w0, t.h0,
                        t.n_img);
-          tma_store_commit();
-        }
+        tma_store_commit();
       }
       tc_fence_before();
     }
