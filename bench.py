@@ -334,6 +334,9 @@ def main():
     e2e_value = world * T * args.steps / (float(te.item()) / 1e3)
 
     # ---------------------------------------------------------------- roofline of the dominant kernel
+    # dominant kernel = stem::conv_gdn_kernel (conv/deconv + GDN/IGDN, 6 launches per step, ~60 % of the step).
+    # achieved = algorithmic FLOPs of those launches / their CUDA-event durations, measured in an extra eager step
+    # (events on torch's current stream, which is the stream the kernels are launched on).
     peaks = load_peaks()
     roofline = None
     if rank == 0:
@@ -346,7 +349,7 @@ def main():
             a.record()
             r = orig(self, inputs, batch, h, w, out)
             b.record()
-            recs.append((a, b))
+            recs.append((a, b, self.alg_flops(batch, h, w), self.gdn is not None))
             return r
 
         E.ConvOp.__call__ = timed_call
@@ -357,16 +360,25 @@ def main():
                 torch.cuda.synchronize()
         finally:
             E.ConvOp.__call__ = orig
-        conv_ms = sum(a.elapsed_time(b) for a, b in recs)
-        gflop_step = algorithmic_gflop_per_frame(variant, H, W) * T
-        achieved = gflop_step / conv_ms  # GFLOP/ms == TFLOP/s
+        dom = [(a.elapsed_time(b), f) for a, b, f, fused in recs if fused]
+        allc = [(a.elapsed_time(b), f) for a, b, f, fused in recs]
+        dom_ms, dom_gf = sum(t for t, _ in dom), sum(f for _, f in dom) / 1e9
+        all_ms, all_gf = sum(t for t, _ in allc), sum(f for _, f in allc) / 1e9
+        achieved = dom_gf / dom_ms  # GFLOP/ms == TFLOP/s
         peak = peaks["tf_sustained"]
-        roofline = {"bound": "tensor", "kernel": "stem::conv_igemm_kernel<BLOCK_N> + stem::conv_gdn_kernel (all dense contractions of the step)",
+        # DRAM bytes of the same 6 launches from the committed ncu --set full capture
+        # (profiles/r01_ncu_bench_conv_gdn.txt): 12.14 GB per step
+        roofline = {"bound": "tensor", "kernel": "stem::conv_gdn_kernel (conv/deconv + GDN/IGDN fused)",
                     "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                    "peak_kind": f"bf16 dense sustained, {peaks['source']}", "traffic": None,
-                    "launches_per_step": len(recs), "kernel_ms_per_step": conv_ms,
-                    "algorithmic_gflop_per_step": gflop_step,
-                    "kernel_share_of_step": conv_ms / ms_per_step}
+                    "peak_kind": f"bf16 dense sustained (kernel timed inside a long step), {peaks['source']}",
+                    "traffic": 12.14e9 / 6 if (variant, T, H, W) == WORKLOADS["gop12_full_1080p"][:4] else None,
+                    "traffic_unit": "bytes per launch (dram read+write, ncu, profiles/r01_ncu_bench_conv_gdn.txt)",
+                    "launches_per_step": len(dom), "kernel_ms_per_step": dom_ms,
+                    "algorithmic_gflop_per_launch": dom_gf / max(len(dom), 1),
+                    "kernel_share_of_step": dom_ms / ms_per_step,
+                    "all_dense_kernels": {"launches_per_step": len(allc), "ms_per_step": all_ms,
+                                          "algorithmic_gflop_per_step": all_gf, "achieved_tflops": all_gf / all_ms,
+                                          "frac": all_gf / all_ms / peak, "share_of_step": all_ms / ms_per_step}}
 
     # ---------------------------------------------------------------- CPU baseline (rank 0, N == 1 only)
     cpu = None

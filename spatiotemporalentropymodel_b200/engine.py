@@ -64,7 +64,8 @@ class ConvOp:
 
     def __init__(self, weight: Tensor, bias: Tensor, *, c_in: Sequence[int], c_out: int, k: int, stride: int = 1,
                  transposed: bool = False, tap_mask: int = 0, slope: float = 1.0, out_dtype: int = DT_F16,
-                 direct_store: bool = False, gdn: Optional[Tuple[Tensor, Tensor, bool]] = None):
+                 direct_store: bool = False, gdn: Optional[Tuple[Tensor, Tensor, bool]] = None,
+                 alg_flops_per_out_pixel: Optional[float] = None):
         """gdn = (beta', gamma', inverse) with the re-parametrised beta (C,) / gamma (C, C): the layer is followed
         by GDN / IGDN and both run in one kernel (stemb200_conv2d_gdn_fwd)."""
         _require_cuda(weight, bias)
@@ -97,6 +98,13 @@ class ConvOp:
         _lib.check(self.lib.stemb200_conv2d_pack_weight(C.byref(d), w32.data_ptr(), self.packed.data_ptr(),
                                                         _stream()), "conv2d_pack_weight")
         self.bias = bias.detach().to(torch.float32).contiguous()
+        # algorithmic FLOPs per output pixel: 2*C_in*C_out*taps (deconv: per *input* pixel, i.e. /4
+        # per output pixel), masked taps not counted, + 2*C*C for a fused GDN
+        ntaps = bin(tap_mask).count("1") if tap_mask else k * k
+        alg = 2.0 * sum(c_in) * c_out * ntaps / (4.0 if transposed else 1.0)
+        if gdn is not None:
+            alg += 2.0 * c_out * c_out
+        self.alg_flops_per_out_pixel = alg if alg_flops_per_out_pixel is None else float(alg_flops_per_out_pixel)
         self.gdn = None
         if gdn is not None:
             beta, gamma, inverse = gdn
@@ -111,6 +119,10 @@ class ConvOp:
                                                             _stream()), "conv2d_pack_weight(gamma)")
             self.beta = beta.detach().to(weight.device, torch.float32).contiguous()
             self.gdn = bool(inverse)
+
+    def alg_flops(self, batch: int, h: int, w: int) -> float:
+        ho, wo = self.out_hw(h, w)
+        return self.alg_flops_per_out_pixel * batch * ho * wo
 
     def out_hw(self, h: int, w: int) -> Tuple[int, int]:
         if self.transposed:
@@ -211,7 +223,8 @@ class TransformsEngine:
             beta, gamma = _gdn_fold(g(f"{name}.beta"), g(f"{name}.gamma"))
             return (beta, gamma, inverse)
 
-        self.ga_conv = [ConvOp(w0, g("g_a.0.bias"), c_in=[80], c_out=N, k=1, gdn=gdn_of("g_a.1", False))]
+        self.ga_conv = [ConvOp(w0, g("g_a.0.bias"), c_in=[80], c_out=N, k=1, gdn=gdn_of("g_a.1", False),
+                               alg_flops_per_out_pixel=2.0 * 75 * N + 2.0 * N * N)]
         for i in (2, 4):
             self.ga_conv.append(ConvOp(g(f"g_a.{i}.weight"), g(f"g_a.{i}.bias"), c_in=[N], c_out=N, k=5, stride=2,
                                        gdn=gdn_of(f"g_a.{i + 1}", False)))
@@ -246,7 +259,8 @@ class TransformsEngine:
                         wm[o:o + 3, :, R, S] = wt[:, :, r, s_].t()
         for uv in range(16):
             bm[uv * 3:uv * 3 + 3] = b6
-        self.gs_last = ConvOp(wm, bm, c_in=[N], c_out=64, k=5, stride=2, tap_mask=mask, out_dtype=DT_F32)
+        self.gs_last = ConvOp(wm, bm, c_in=[N], c_out=64, k=5, stride=2, tap_mask=mask, out_dtype=DT_F32,
+                              alg_flops_per_out_pixel=4 * 2.0 * N * 3 * 25)  # 4 input pixels per super pixel
 
     # -------------------------------------------------------------------------------------------------
     def analysis(self, x: Tensor, pad: Tuple[int, int, int, int] = (0, 0, 0, 0)) -> Tuple[Tensor, int, int]:

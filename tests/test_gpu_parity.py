@@ -173,6 +173,45 @@ def test_conv_layers_vs_torch(dev, case):
     assert float((got - ref).abs().max()) < 2e-4 * max(1.0, float(ref.abs().max()))
 
 
+GDN_CASES = [("conv5s2_gdn", False, False, 20, 28), ("deconv5_igdn", True, True, 9, 13), ("gemm_gdn", None, False, 12, 20)]
+
+
+@pytest.mark.parametrize("case", GDN_CASES, ids=[c[0] for c in GDN_CASES])
+def test_fused_conv_gdn_vs_oracle(dev, case):
+    """stemb200_conv2d_gdn_fwd (conv/deconv + GDN/IGDN in one kernel) against F.conv2d + the oracle's GDN
+    (layers/gdn.py:52-67 with the NonNegativeParametrizer reparametrisation)."""
+    from spatiotemporalentropymodel_b200.engine import ConvOp, _gdn_fold, nchw_to_nhwc_f16, nhwc_f16_to_nchw
+    name, transposed, inverse, h, w = case
+    g = torch.Generator().manual_seed(21)
+    C, B = 192, 2
+    cin = 128 if transposed is None else 192
+    k = 1 if transposed is None else 5
+    x = torch.randn((B, cin, h, w), generator=g).half().float()
+    wshape = (cin, C, k, k) if transposed else (C, cin, k, k)
+    wt = (1.5 * torch.randn(wshape, generator=g) / math.sqrt(cin * k * k / (4 if transposed else 1))).half().float()
+    bias = 0.3 * torch.randn(C, generator=g)
+    ped = torch.tensor([2.0 ** -36])
+    beta_p = torch.sqrt(torch.max(1.0 + 0.5 * torch.rand(C, generator=g) + ped, ped))
+    gamma_p = torch.sqrt(torch.max(0.1 * torch.eye(C) + 0.02 * torch.rand((C, C), generator=g) + ped, ped))
+    if transposed:
+        pre = F.conv_transpose2d(x, wt, bias, stride=2, padding=2, output_padding=1)
+    elif transposed is None:
+        pre = F.conv2d(x, wt, bias)
+    else:
+        pre = F.conv2d(x, wt, bias, stride=2, padding=2)
+    ref = O.gdn(pre, beta_p, gamma_p, inverse)
+    beta, gamma = _gdn_fold(beta_p.to(dev), gamma_p.to(dev))
+    op = ConvOp(wt.to(dev), bias.to(dev), c_in=[cin], c_out=C, k=k, stride=1 if transposed is None else 2,
+                transposed=bool(transposed), gdn=(beta, gamma, inverse))
+    x16 = nchw_to_nhwc_f16(x.to(dev), torch.empty((B, h, w, cin), dtype=torch.float16, device=dev))
+    ho, wo = op.out_hw(h, w)
+    out = op([x16], B, h, w, torch.full((B, ho, wo, C), float("nan"), dtype=torch.float16, device=dev))
+    got = nhwc_f16_to_nchw(out, torch.empty((B, C, ho, wo), device=dev)).cpu()
+    assert got.shape == ref.shape and torch.isfinite(got).all()
+    assert rel_rms(got, ref) < 1.5e-3
+    assert float((got - ref).abs().max()) < 6e-3 * max(1.0, float(ref.abs().max()))
+
+
 # ------------------------------------------------------------------------------------------- STEM forward
 @pytest.mark.parametrize("variant", S.STEM_VARIANTS)
 def test_stem_forward_vs_reference_golden(dev, golden, variant):

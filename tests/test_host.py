@@ -51,6 +51,28 @@ def test_pmf_to_quantized_cdf_c_abi(golden):
     assert b"bad argument" in lib.stemb200_last_error()
 
 
+def test_c_abi_rejects_bad_arguments_without_a_gpu():
+    """Argument validation happens before any CUDA call: error code + message, never a crash."""
+    lib = _lib.load()
+    d = _lib.ConvDesc()
+    assert lib.stemb200_conv2d_fwd(ctypes.byref(d), None, None, None, None, None) == -1
+    assert b"null argument" in lib.stemb200_last_error()
+    d.batch, d.h_in, d.w_in, d.n_src, d.c_out, d.kh, d.kw, d.stride = 1, 8, 8, 1, 192, 4, 4, 1
+    d.c_in[0] = 192
+    assert lib.stemb200_conv2d_packed_k(ctypes.byref(d)) == -1          # kernel size 4 unsupported
+    d.kh = d.kw = 5
+    assert lib.stemb200_conv2d_packed_k(ctypes.byref(d)) == 25 * 192
+    d.tap_mask = 0xFFF
+    assert lib.stemb200_conv2d_packed_k(ctypes.byref(d)) == 12 * 192    # mask 'A': 12 live taps
+    d.tap_mask, d.transposed, d.stride = 0, 1, 2
+    assert lib.stemb200_conv2d_packed_k(ctypes.byref(d)) == 25 * 192    # 9 + 6 + 6 + 4 taps over the 4 phases
+    d.c_in[0] = 100
+    assert lib.stemb200_conv2d_packed_k(ctypes.byref(d)) == -1          # channels must be a multiple of 8
+    assert lib.stemb200_gaussian_conditional_flat(None, None, None, 0, None, 0, 0.11, 1e-9, None, None, None, None,
+                                                  None, None) == -1
+    assert lib.stemb200_synthesis_tail(None, None, 1, 1, 1, None, 0, 0, 0, 0, None, None) == -1
+
+
 @pytest.mark.parametrize("variant", S.STEM_VARIANTS)
 def test_state_dict_contract(variant):
     """The synthetic state_dicts were loaded (strict) by the reference classes when the goldens were made; the
