@@ -346,10 +346,10 @@ def main():
         recs = []
         orig = E.ConvOp.__call__
 
-        def timed_call(self, inputs, batch, h, w, out):
+        def timed_call(self, inputs, batch, h, w, out, aux=None):
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record()
-            r = orig(self, inputs, batch, h, w, out)
+            r = orig(self, inputs, batch, h, w, out, aux)
             b.record()
             recs.append((a, b, self.alg_flops(batch, h, w), self.gdn is not None))
             return r

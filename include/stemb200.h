@@ -28,6 +28,14 @@ extern "C" {
 #define STEMB200_E_CUDA -2      /* a CUDA runtime / driver call failed (see stemb200_last_error) */
 #define STEMB200_E_NODEVICE -3  /* no sm_100 device */
 
+/* epilogues of stemb200_conv2d_fwd */
+#define STEMB200_EPI_LINEAR 0 /* out = LeakyReLU(acc + bias) */
+#define STEMB200_EPI_SFT 1    /* spatial feature transform (stem_utils.py:36-43): the conv computes gamma and beta at
+                                 once (c_out = 2 x channels, per 128 accumulator columns [gamma(64) | beta(64)]),
+                                 out = LeakyReLU(aux * gamma + beta) with c_out/2 channels; fold the "+1" of
+                                 (1 + gamma) into gamma's bias */
+#define STEMB200_EPI_ADD 2    /* out = LeakyReLU(acc + bias) + aux (SFTResblk skip connection, stem_utils.py:55-60) */
+
 #define STEMB200_DT_F16 0 /* IEEE half operands, fp32 accumulate (tcgen05 kind::f16) */
 #define STEMB200_DT_F32 1 /* fp32 storage (epilogue outputs that feed quantisation) */
 
@@ -47,14 +55,15 @@ typedef struct stemb200_conv_desc {
   int32_t batch;        /* N */
   int32_t h_in, w_in;   /* input spatial size (all sources share it) */
   int32_t n_src;        /* 1..3 inputs concatenated along channels (torch.cat(..., 1) folded into K) */
-  int32_t c_in[3];      /* channels per source: multiples of 64 (one source may be any multiple of 8: the
-                           last 64-channel K chunk is then zero-filled by TMA) */
+  int32_t c_in[3];      /* channels per source, multiples of 8 (the last 64-channel K chunk of a source is
+                           zero-filled by TMA when the count is not a multiple of 64) */
   int32_t c_out;        /* output channels (multiple of 16) */
   int32_t kh, kw;       /* kernel size (1, 3 or 5; square padding k/2) */
   int32_t stride;       /* 1 or 2 */
   int32_t transposed;   /* 1: ConvTranspose2d(k, stride 2, padding k/2, output_padding 1) */
   uint32_t tap_mask;    /* bit (r*kw+s) set = tap used; 0 = all taps (mask 'A' 5x5 = 0x00000FFF) */
-  float lrelu_slope;    /* out = LeakyReLU(acc + bias, slope); 1.0f = no activation */
+  int32_t epilogue;     /* STEMB200_EPI_* */
+  float lrelu_slope;    /* LeakyReLU negative slope; 1.0f = no activation, 0.0f = ReLU */
   int32_t out_dtype;    /* STEMB200_DT_F16 or STEMB200_DT_F32 (NHWC) */
   float sq_scale;       /* conv2d_gdn_fwd only: x is prescaled by this before squaring so that x^2 stays inside
                            the fp16 range; the normaliser is rescaled by 1/sq_scale^2 */
@@ -68,13 +77,14 @@ int64_t stemb200_conv2d_packed_k(const stemb200_conv_desc* d);
  * device, into the K-major fp16 matrix the kernel's TMA descriptor expects. Masked taps are dropped. */
 int stemb200_conv2d_pack_weight(const stemb200_conv_desc* d, const float* weight_f32, void* packed_f16,
                                 void* stream);
-/* in[s]: NHWC fp16 [batch][h_in][w_in][c_in[s]]; out: NHWC [batch][h_out][w_out][c_out]; bias: fp32 [c_out]. */
+/* in[s]: NHWC fp16 [batch][h_in][w_in][c_in[s]]; out: NHWC [batch][h_out][w_out][c_out] (c_out/2 channels for
+ * EPI_SFT); bias: fp32 [c_out]; aux: NHWC fp16 with the output's shape (EPI_SFT: x, EPI_ADD: residual) or NULL. */
 int stemb200_conv2d_fwd(const stemb200_conv_desc* d, const void* const* in, const void* packed_weight,
-                        const float* bias, void* out, void* stream);
+                        const float* bias, const void* aux, void* out, void* stream);
 
 /* Convolution / transposed convolution with GDN (inverse = 0) or IGDN (inverse = 1) fused into the epilogue:
  *   x = conv(in) + bias;  out = x * rsqrt(beta + gamma . x^2)   |   x * sqrt(beta + gamma . x^2)
- * (priors.py:421-439 conv/deconv followed by layers/gdn.py:52-67). c_out must be 192; packed_gamma is the
+ * (priors.py:421-439 conv/deconv followed by layers/gdn.py:52-67). c_out must be 128 or 192; packed_gamma is the
  * [c_out][c_out] matrix produced by stemb200_conv2d_pack_weight for a 1x1 conv of the *re-parametrised* gamma
  * (ops/parametrizers.py:42-45), beta the re-parametrised beta (fp32). d->sq_scale prescales x before squaring
  * (fp16 range); out is NHWC fp16. x and x^2 never leave the SM. */
@@ -99,6 +109,20 @@ int stemb200_nhwc_f32_to_nchw_f32(const float* in, float* out, int32_t n, int32_
  * 64). The rows are the NHWC input (C = 80) of a 1x1 stemb200_conv2d_gdn_fwd whose weight is the [N][75] reshape. */
 int stemb200_im2col_k5s2_c3(const float* x_nchw, void* out_rows, int32_t n, int32_t h, int32_t w,
                             int32_t h_pad, int32_t w_pad, int32_t pad_top, int32_t pad_left, void* stream);
+
+/* stem_roi (compressai/models/stem_roi.py) staging kernels.
+ * im2col_k3s1_c4: operand rows of conv(4, 192, k3, s1) on cat[x (3 ch), Qmap (1 ch)] (:379, :586):
+ *   [n*h*w][40] fp16, k = (r*3+s)*4 + ch for 36 entries, then 4 zeros.
+ * avgpool_nhwc_f16: F.adaptive_avg_pool2d with divisible sizes (stem_utils.py:37), NHWC fp16, mean over
+ *   factor x factor blocks: in [n][h_out*f][w_out*f][c] -> out [n][h_out][w_out][c].
+ * qmap_pool: the hyper-encoder's pooled quality map (:563): NCHW fp32 [n][1][h_out*f][w_out*f] -> NHWC fp16
+ *   [n][h_out][w_out][8], channel 0 = block mean, channels 1..7 = 0 (so it can be a K segment of the next conv). */
+int stemb200_im2col_k3s1_c4(const float* x_nchw, const float* q_nchw, void* out_rows, int32_t n, int32_t h,
+                            int32_t w, void* stream);
+int stemb200_avgpool_nhwc_f16(const void* in, void* out, int32_t n, int32_t h_out, int32_t w_out, int32_t c,
+                              int32_t factor, void* stream);
+int stemb200_qmap_pool(const float* q_nchw, void* out_nhwc8_f16, int32_t n, int32_t h_out, int32_t w_out,
+                       int32_t factor, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------
  * Entropy-model elementwise kernels

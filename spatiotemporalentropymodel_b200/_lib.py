@@ -13,6 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libstemb200.so")
 
 DT_F16, DT_F32 = 0, 1
+EPI_LINEAR, EPI_SFT, EPI_ADD = 0, 1, 2
 
 
 class ConvDesc(C.Structure):
@@ -21,7 +22,7 @@ class ConvDesc(C.Structure):
     _fields_ = [
         ("batch", C.c_int32), ("h_in", C.c_int32), ("w_in", C.c_int32), ("n_src", C.c_int32),
         ("c_in", C.c_int32 * 3), ("c_out", C.c_int32), ("kh", C.c_int32), ("kw", C.c_int32),
-        ("stride", C.c_int32), ("transposed", C.c_int32), ("tap_mask", C.c_uint32),
+        ("stride", C.c_int32), ("transposed", C.c_int32), ("tap_mask", C.c_uint32), ("epilogue", C.c_int32),
         ("lrelu_slope", C.c_float), ("out_dtype", C.c_int32), ("sq_scale", C.c_float),
         ("tile_h", C.c_int32), ("tile_w", C.c_int32), ("direct_store", C.c_int32),
     ]
@@ -40,12 +41,15 @@ SIGNATURES = {
     "stemb200_launch_count": (C.c_uint64, []),
     "stemb200_conv2d_packed_k": (_i64, [C.POINTER(ConvDesc)]),
     "stemb200_conv2d_pack_weight": (C.c_int, [C.POINTER(ConvDesc), _vp, _vp, _vp]),
-    "stemb200_conv2d_fwd": (C.c_int, [C.POINTER(ConvDesc), C.POINTER(_vp), _vp, _vp, _vp, _vp]),
+    "stemb200_conv2d_fwd": (C.c_int, [C.POINTER(ConvDesc), C.POINTER(_vp), _vp, _vp, _vp, _vp, _vp]),
     "stemb200_conv2d_gdn_fwd": (C.c_int, [C.POINTER(ConvDesc), C.POINTER(_vp), _vp, _vp, _vp, _vp, _i32, _vp, _vp]),
     "stemb200_nchw_f32_to_nhwc_f16": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp]),
     "stemb200_nhwc_f16_to_nchw_f32": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _vp]),
     "stemb200_nhwc_f32_to_nchw_f32": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _vp]),
     "stemb200_im2col_k5s2_c3": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
+    "stemb200_im2col_k3s1_c4": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _vp]),
+    "stemb200_avgpool_nhwc_f16": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp]),
+    "stemb200_qmap_pool": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _vp]),
     "stemb200_latent_stage": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, _vp]),
     "stemb200_gaussian_conditional_fwd": (C.c_int, [_vp, _i32, _vp, _vp, _i32, _i32, _i32, _i32, _vp, _i32, _f32,
                                                     _f32, _i32, _vp, _vp, _vp, _vp, _vp, _vp]),

@@ -57,6 +57,7 @@ struct ConvKernelParams {
   int out_f32, direct;
   int os, full_h, full_w;  // output phase stride and full output size (direct store / aux addressing)
   const float* bias;
+  const __half* aux;  // EPI 1/2: NHWC fp16 multiplicand / residual with the output's geometry
   void* out;
   // fused GDN / IGDN (conv_gdn_kernel only)
   alignas(64) CUtensorMap g_map;  // gamma [c_out][c_out] fp16, K-major
@@ -121,7 +122,10 @@ __device__ __forceinline__ uint32_t pack_half2(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&h);
 }
 
-template <int BLOCK_N>
+// EPI: 0 = LeakyReLU(acc + bias); 1 = SFT: x * (acc_gamma + b_gamma) + (acc_beta + b_beta) then LeakyReLU, with the
+// accumulator columns laid out per 128-column block as [gamma(64 ch) | beta(64 ch)] and x read from `aux`
+// (stem_utils.py:36-43, the "+1" of (1 + gamma) is folded into b_gamma); 2 = LeakyReLU(acc + bias) + aux (residual).
+template <int BLOCK_N, int EPI>
 __global__ void __launch_bounds__(kNumThreads, 1)
 conv_igemm_kernel(const __grid_constant__ ConvKernelParams p) {
   using Cfg = ConvCfg<BLOCK_N>;
@@ -271,99 +275,196 @@ conv_igemm_kernel(const __grid_constant__ ConvKernelParams p) {
 
       constexpr int kCols = (BLOCK_N >= 32) ? 32 : 16;
       constexpr int kChunks = BLOCK_N / kCols;
-      // TMEM loads are software pipelined: chunk ci+2 is requested before chunk ci is processed
-      uint32_t rn[kCols];
-      if (half < kChunks) {
-        if constexpr (kCols == 32) tmem_ld_32x32(t_row + half * kCols, rn);
-        else tmem_ld_32x16(t_row + half * kCols, rn);
-      }
+      if constexpr (EPI == 1) {
+        // ================= SFT epilogue: 128 accumulator columns -> 64 output channels per group =================
+        const int c_half = p.c_out >> 1;  // channels of the output / aux tensors
 #pragma unroll 1
-      for (int ci = half; ci < kChunks; ci += 2) {
-        const int c = ci * kCols;
-        float v[kCols];
-        tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < kCols; ++i) v[i] = __uint_as_float(rn[i]);
-        if (ci + 2 < kChunks) {
-          if constexpr (kCols == 32) tmem_ld_32x32(t_row + c + 2 * kCols, rn);
-          else tmem_ld_32x16(t_row + c + 2 * kCols, rn);
-        }
-        const int ch0 = t.n0 + c;
-#pragma unroll
-        for (int j = 0; j < kCols / 4; ++j) {
-          float b0, b1, b2, b3;
-          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
-                       : "=f"(b0), "=f"(b1), "=f"(b2), "=f"(b3)
-                       : "r"(bias_smem + 4u * (c + 4 * j)));
-          const float x0 = v[4 * j] + b0, x1 = v[4 * j + 1] + b1, x2 = v[4 * j + 2] + b2, x3 = v[4 * j + 3] + b3;
-          v[4 * j] = x0 > 0.f ? x0 : x0 * p.slope;
-          v[4 * j + 1] = x1 > 0.f ? x1 : x1 * p.slope;
-          v[4 * j + 2] = x2 > 0.f ? x2 : x2 * p.slope;
-          v[4 * j + 3] = x3 > 0.f ? x3 : x3 * p.slope;
-        }
-
-        if (p.direct) {
+        for (int g = 0; g < BLOCK_N / 128; ++g) {
+          const int cg = 128 * g + 32 * half;  // gamma columns of this thread; beta columns are cg + 64
+          const int oc = ((t.n0 + 128 * g) >> 1) + 32 * half;  // first output channel of this thread
+          uint4 a4[4];
           if (inb) {
-            if (p.out_f32) {
-              float4* op = reinterpret_cast<float4*>(static_cast<float*>(p.out) + pix * p.c_out + ch0);
+            const uint4* ap = reinterpret_cast<const uint4*>(p.aux + pix * c_half + oc);
 #pragma unroll
-              for (int j = 0; j < kCols / 4; ++j)
-                op[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-            } else {
-              uint4* op = reinterpret_cast<uint4*>(static_cast<__half*>(p.out) + pix * p.c_out + ch0);
+            for (int j = 0; j < 4; ++j) a4[j] = __ldg(ap + j);
+          } else {
 #pragma unroll
-              for (int j = 0; j < kCols / 8; ++j)
-                op[j] = make_uint4(pack_half2(v[8 * j], v[8 * j + 1]), pack_half2(v[8 * j + 2], v[8 * j + 3]),
-                                   pack_half2(v[8 * j + 4], v[8 * j + 5]),
-                                   pack_half2(v[8 * j + 6], v[8 * j + 7]));
-            }
+            for (int j = 0; j < 4; ++j) a4[j] = make_uint4(0, 0, 0, 0);
           }
-        } else if constexpr (kCols == 32) {
-          // ---- staged TMA store, one 64-column group (both halves) per iteration ----
-          //   fp16: the two halves fill pieces 0-3 / 4-7 of one 128-byte row; buffers alternate per group
-          //   fp32: each half fills its own buffer (32 columns = one 128-byte row)
-          const uint32_t buf = p.out_f32 ? static_cast<uint32_t>(half) : (group_ctr & 1u);
-          const uint32_t obuf = out_base + buf * kOutStageBytes;
-          if (etid == 0) {
-            if (p.out_f32) tma_store_wait_read<0>();
-            else tma_store_wait_read<1>();
+          uint32_t rg[32], rb[32];
+          tmem_ld_32x32(t_row + cg, rg);
+          tmem_ld_32x32(t_row + cg + 64, rb);
+          tmem_ld_wait();
+          uint32_t ho[16];
+          const uint32_t* ax = reinterpret_cast<const uint32_t*>(a4);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float g0, g1, g2, g3, b0, b1, b2, b3;
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                         : "=f"(g0), "=f"(g1), "=f"(g2), "=f"(g3)
+                         : "r"(bias_smem + 4u * (cg + 4 * j)));
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                         : "=f"(b0), "=f"(b1), "=f"(b2), "=f"(b3)
+                         : "r"(bias_smem + 4u * (cg + 64 + 4 * j)));
+            const float2 x0 = __half22float2(*reinterpret_cast<const __half2*>(&ax[2 * j]));
+            const float2 x1 = __half22float2(*reinterpret_cast<const __half2*>(&ax[2 * j + 1]));
+            float o0 = fmaf(x0.x, __uint_as_float(rg[4 * j]) + g0, __uint_as_float(rb[4 * j]) + b0);
+            float o1 = fmaf(x0.y, __uint_as_float(rg[4 * j + 1]) + g1, __uint_as_float(rb[4 * j + 1]) + b1);
+            float o2 = fmaf(x1.x, __uint_as_float(rg[4 * j + 2]) + g2, __uint_as_float(rb[4 * j + 2]) + b2);
+            float o3 = fmaf(x1.y, __uint_as_float(rg[4 * j + 3]) + g3, __uint_as_float(rb[4 * j + 3]) + b3);
+            o0 = o0 > 0.f ? o0 : o0 * p.slope;
+            o1 = o1 > 0.f ? o1 : o1 * p.slope;
+            o2 = o2 > 0.f ? o2 : o2 * p.slope;
+            o3 = o3 > 0.f ? o3 : o3 * p.slope;
+            ho[2 * j] = pack_half2(o0, o1);
+            ho[2 * j + 1] = pack_half2(o2, o3);
           }
+          const uint32_t obuf = out_base + (group_ctr & 1u) * kOutStageBytes;
+          if (etid == 0) tma_store_wait_read<1>();
           named_bar_sync(1, kNumEpiThreads);
           const uint32_t rbase = obuf + static_cast<uint32_t>(row) * 128u;
-          if (p.out_f32) {
+          const uint32_t jo = half ? 4u : 0u;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const uint32_t addr = rbase + ((static_cast<uint32_t>(j) ^ rsw) << 4);
-              asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v[4 * j]),
-                           "f"(v[4 * j + 1]), "f"(v[4 * j + 2]), "f"(v[4 * j + 3])
-                           : "memory");
-            }
-          } else {
-            const uint32_t jo = half ? 4u : 0u;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const uint32_t addr = rbase + (((static_cast<uint32_t>(j) + jo) ^ rsw) << 4);
-              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr),
-                           "r"(pack_half2(v[8 * j], v[8 * j + 1])),
-                           "r"(pack_half2(v[8 * j + 2], v[8 * j + 3])),
-                           "r"(pack_half2(v[8 * j + 4], v[8 * j + 5])),
-                           "r"(pack_half2(v[8 * j + 6], v[8 * j + 7]))
-                           : "memory");
-            }
+          for (int j = 0; j < 4; ++j) {
+            const uint32_t addr = rbase + (((static_cast<uint32_t>(j) + jo) ^ rsw) << 4);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(ho[4 * j]), "r"(ho[4 * j + 1]),
+                         "r"(ho[4 * j + 2]), "r"(ho[4 * j + 3])
+                         : "memory");
           }
           fence_proxy_async_smem();
           named_bar_sync(1, kNumEpiThreads);
           if (etid == 0) {
-            const int cgrp = t.n0 + (c & ~63);
-            if (p.out_f32) {
-              tma_store_4d(&p.out_map[t.sub], out_base, cgrp, t.w0, t.h0, t.n_img);
-              tma_store_4d(&p.out_map[t.sub], out_base + kOutStageBytes, cgrp + 32, t.w0, t.h0, t.n_img);
-            } else {
-              tma_store_4d(&p.out_map[t.sub], obuf, cgrp, t.w0, t.h0, t.n_img);
-            }
+            tma_store_4d(&p.out_map[t.sub], obuf, (t.n0 + 128 * g) >> 1, t.w0, t.h0, t.n_img);
             tma_store_commit();
           }
           ++group_ctr;
+        }
+      } else {
+        // ================= linear (+ residual) epilogue =================
+        // TMEM loads are software pipelined: chunk ci+2 is requested before chunk ci is processed. Both halves
+        // run the same number of iterations (barriers!); with an odd chunk count (BLOCK_N = 160) the last
+        // iteration of half 1 is idle and its stale half-row lands on out-of-range channels, which TMA clips.
+        constexpr int kIters = (kChunks + 1) / 2;
+        uint32_t rn[kCols];
+        if (half < kChunks) {
+          if constexpr (kCols == 32) tmem_ld_32x32(t_row + half * kCols, rn);
+          else tmem_ld_32x16(t_row + half * kCols, rn);
+        }
+#pragma unroll 1
+        for (int gi = 0; gi < kIters; ++gi) {
+          const int ci = 2 * gi + half;
+          const bool active = ci < kChunks;
+          const int c = ci * kCols;
+          const int ch0 = t.n0 + c;
+          float v[kCols];
+          if (active) {
+            uint4 a4[kCols / 8];
+            if constexpr (EPI == 2) {
+              if (inb) {
+                const uint4* ap = reinterpret_cast<const uint4*>(p.aux + pix * p.c_out + ch0);
+#pragma unroll
+                for (int j = 0; j < kCols / 8; ++j) a4[j] = __ldg(ap + j);
+              } else {
+#pragma unroll
+                for (int j = 0; j < kCols / 8; ++j) a4[j] = make_uint4(0, 0, 0, 0);
+              }
+            }
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < kCols; ++i) v[i] = __uint_as_float(rn[i]);
+            if (ci + 2 < kChunks) {
+              if constexpr (kCols == 32) tmem_ld_32x32(t_row + c + 2 * kCols, rn);
+              else tmem_ld_32x16(t_row + c + 2 * kCols, rn);
+            }
+#pragma unroll
+            for (int j = 0; j < kCols / 4; ++j) {
+              float b0, b1, b2, b3;
+              asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                           : "=f"(b0), "=f"(b1), "=f"(b2), "=f"(b3)
+                           : "r"(bias_smem + 4u * (c + 4 * j)));
+              const float x0 = v[4 * j] + b0, x1 = v[4 * j + 1] + b1, x2 = v[4 * j + 2] + b2, x3 = v[4 * j + 3] + b3;
+              v[4 * j] = x0 > 0.f ? x0 : x0 * p.slope;
+              v[4 * j + 1] = x1 > 0.f ? x1 : x1 * p.slope;
+              v[4 * j + 2] = x2 > 0.f ? x2 : x2 * p.slope;
+              v[4 * j + 3] = x3 > 0.f ? x3 : x3 * p.slope;
+            }
+            if constexpr (EPI == 2) {
+              const uint32_t* ax = reinterpret_cast<const uint32_t*>(a4);
+#pragma unroll
+              for (int i = 0; i < kCols / 2; ++i) {
+                const float2 r2 = __half22float2(*reinterpret_cast<const __half2*>(&ax[i]));
+                v[2 * i] += r2.x;
+                v[2 * i + 1] += r2.y;
+              }
+            }
+          }
+
+          if (p.direct) {
+            if (inb && active) {
+              if (p.out_f32) {
+                float4* op = reinterpret_cast<float4*>(static_cast<float*>(p.out) + pix * p.c_out + ch0);
+#pragma unroll
+                for (int j = 0; j < kCols / 4; ++j)
+                  op[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+              } else {
+                uint4* op = reinterpret_cast<uint4*>(static_cast<__half*>(p.out) + pix * p.c_out + ch0);
+#pragma unroll
+                for (int j = 0; j < kCols / 8; ++j)
+                  op[j] = make_uint4(pack_half2(v[8 * j], v[8 * j + 1]), pack_half2(v[8 * j + 2], v[8 * j + 3]),
+                                     pack_half2(v[8 * j + 4], v[8 * j + 5]),
+                                     pack_half2(v[8 * j + 6], v[8 * j + 7]));
+              }
+            }
+          } else if constexpr (kCols == 32) {
+            // ---- staged TMA store, one 64-column group (both halves) per iteration ----
+            //   fp16: the two halves fill pieces 0-3 / 4-7 of one 128-byte row; buffers alternate per group
+            //   fp32: each half fills its own buffer (32 columns = one 128-byte row)
+            const uint32_t buf = p.out_f32 ? static_cast<uint32_t>(half) : (group_ctr & 1u);
+            const uint32_t obuf = out_base + buf * kOutStageBytes;
+            if (etid == 0) {
+              if (p.out_f32) tma_store_wait_read<0>();
+              else tma_store_wait_read<1>();
+            }
+            named_bar_sync(1, kNumEpiThreads);
+            const uint32_t rbase = obuf + static_cast<uint32_t>(row) * 128u;
+            if (active) {
+              if (p.out_f32) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                  const uint32_t addr = rbase + ((static_cast<uint32_t>(j) ^ rsw) << 4);
+                  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v[4 * j]),
+                               "f"(v[4 * j + 1]), "f"(v[4 * j + 2]), "f"(v[4 * j + 3])
+                               : "memory");
+                }
+              } else {
+                const uint32_t jo = half ? 4u : 0u;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  const uint32_t addr = rbase + (((static_cast<uint32_t>(j) + jo) ^ rsw) << 4);
+                  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr),
+                               "r"(pack_half2(v[8 * j], v[8 * j + 1])),
+                               "r"(pack_half2(v[8 * j + 2], v[8 * j + 3])),
+                               "r"(pack_half2(v[8 * j + 4], v[8 * j + 5])),
+                               "r"(pack_half2(v[8 * j + 6], v[8 * j + 7]))
+                               : "memory");
+                }
+              }
+            }
+            fence_proxy_async_smem();
+            named_bar_sync(1, kNumEpiThreads);
+            if (etid == 0) {
+              const int cgrp = t.n0 + 64 * gi;
+              if (p.out_f32) {
+                tma_store_4d(&p.out_map[t.sub], out_base, cgrp, t.w0, t.h0, t.n_img);
+                if (2 * gi + 1 < kChunks)
+                  tma_store_4d(&p.out_map[t.sub], out_base + kOutStageBytes, cgrp + 32, t.w0, t.h0, t.n_img);
+              } else {
+                tma_store_4d(&p.out_map[t.sub], obuf, cgrp, t.w0, t.h0, t.n_img);
+              }
+              tma_store_commit();
+            }
+            ++group_ctr;
+          }
         }
       }
       // all TMEM reads of this accumulator are complete -> hand it back to the MMA warp
@@ -394,22 +495,25 @@ conv_igemm_kernel(const __grid_constant__ ConvKernelParams p) {
 // (reading A, producing x^2) sits on the tensor pipe's critical path. Replaces layers/gdn.py:52-67 + the producing
 // conv (priors.py:421-439) without x or x^2 ever reaching HBM.
 // =====================================================================================================
-struct GdnCfg {
-  static constexpr int kN = 192;
+template <int kNT>
+struct GdnCfgT {
+  static constexpr int kN = kNT;
   static constexpr int kBStageBytes = kN * 128;
   static constexpr int kStageBytes = kAStageBytes + kBStageBytes;
   static constexpr int kStages = 4;
-  static constexpr int kA2Bytes = 3 * kAStageBytes;  // x^2 operand (3 chunks of 64 channels); reused as output staging
+  static constexpr int kA2Bytes = (kN / 64) * kAStageBytes;  // x^2 operand (64-channel chunks); reused as output staging
   static constexpr int kBarrierBytes = 256 + 2 * kN * 4;
   static constexpr int kSmemBytes = 1024 + kStages * kStageBytes + kA2Bytes + kBarrierBytes;
   static constexpr int kTmemCols = 512;
-  static constexpr uint32_t kAccCol = 0, kNormCol = 192, kStashCol = 384;
+  static constexpr uint32_t kAccCol = 0, kNormCol = kN, kStashCol = 2 * kN;
+  static_assert(kN % 64 == 0 && 2 * kN + kN / 2 <= 512, "TMEM budget");
   static_assert(kSmemBytes <= kSmemLimit, "smem overflow");
 };
 
+template <int kNT>
 __global__ void __launch_bounds__(kNumThreads, 1)
 conv_gdn_kernel(const __grid_constant__ ConvKernelParams p) {
-  using Cfg = GdnCfg;
+  using Cfg = GdnCfgT<kNT>;
   constexpr int kStages = Cfg::kStages;
   constexpr int BLOCK_N = Cfg::kN;
 
@@ -687,7 +791,7 @@ conv_gdn_kernel(const __grid_constant__ ConvKernelParams p) {
 // kernel's k-step table
 // =====================================================================================================
 struct PackParams {
-  uint32_t info[kMaxKSteps];  // [2:0] r | [5:3] s | [31:6] global input-channel base
+  uint32_t info[kMaxKSteps];  // [2:0] r | [5:3] s | [12:6] valid channels in this chunk - 1 | [31:13] channel base
   int n_steps;
   int c_out, c_in_total, kh, kw, transposed;
 };
@@ -702,9 +806,10 @@ __global__ void pack_weight_kernel(const __grid_constant__ PackParams pp, const 
     const int k = static_cast<int>(i - static_cast<long long>(o) * K);
     const uint32_t e = pp.info[k / kKChunk];
     const int r = e & 7, s = (e >> 3) & 7;
-    const int ci = static_cast<int>(e >> 6) + (k % kKChunk);
+    const int kc = k % kKChunk;
+    const int ci = static_cast<int>(e >> 13) + kc;
     float v = 0.f;
-    if (ci < pp.c_in_total) {
+    if (kc <= static_cast<int>((e >> 6) & 127u)) {
       const long long idx = pp.transposed
                                 ? ((static_cast<long long>(ci) * pp.c_out + o) * pp.kh + r) * pp.kw + s
                                 : ((static_cast<long long>(o) * pp.c_in_total + ci) * pp.kh + r) * pp.kw + s;
@@ -737,6 +842,7 @@ struct Plan {
 int pick_block_n(int c_out) {
   if (c_out % 256 == 0) return 256;
   if (c_out % 192 == 0) return 192;
+  if (c_out == 160) return 160;
   if (c_out % 128 == 0) return 128;
   if (c_out == 96) return 96;
   if (c_out % 64 == 0) return 64;
@@ -754,25 +860,34 @@ int build_plan(const stemb200_conv_desc& d, Plan& pl) {
   int src_base[3] = {0, 0, 0};
   pl.c_in_total = 0;
   for (int s = 0; s < d.n_src; ++s) {
-    const bool ragged_ok = d.n_src == 1 && d.c_in[s] >= 8 && d.c_in[s] % 8 == 0;
-    if ((d.c_in[s] < kKChunk || d.c_in[s] % kKChunk) && !ragged_ok)
-      return set_error("conv: c_in must be a multiple of 64 (or of 8 for a single source)");
+    if (d.c_in[s] < 8 || d.c_in[s] % 8) return set_error("conv: c_in must be a multiple of 8");
     src_base[s] = pl.c_in_total;
     pl.c_in_total += d.c_in[s];
   }
   pl.block_n = pick_block_n(d.c_out);
   if (!pl.block_n) return set_error("conv: unsupported c_out");
   if (pl.block_n < 32 && !d.direct_store) return set_error("conv: c_out < 32 needs direct_store");
-  if (!d.direct_store && (d.c_out % 64)) return set_error("conv: the TMA-store epilogue needs c_out % 64 == 0");
+  if (!d.direct_store && (d.c_out % 64) && d.c_out != 160)
+    return set_error("conv: the TMA-store epilogue needs c_out % 64 == 0 (or c_out == 160)");
+  if (d.epilogue < 0 || d.epilogue > 2) return set_error("conv: bad epilogue");
+  if (d.epilogue != STEMB200_EPI_LINEAR && (d.direct_store || d.out_dtype != STEMB200_DT_F16))
+    return set_error("conv: SFT / residual epilogues write fp16 through the TMA store path");
+  if (d.epilogue == STEMB200_EPI_SFT) {
+    pl.block_n = d.c_out % 256 == 0 ? 256 : (d.c_out % 128 == 0 ? 128 : 0);
+    if (!pl.block_n) return set_error("conv: SFT epilogue needs c_out (= 2 x channels) % 128 == 0");
+  }
+  if (d.epilogue == STEMB200_EPI_ADD && pl.block_n != 64 && pl.block_n != 128 && pl.block_n != 192 &&
+      pl.block_n != 256)
+    return set_error("conv: residual epilogue supports c_out % 64 == 0");
 
   const int k = d.kh, pad = k / 2;
   const uint32_t mask = d.tap_mask ? d.tap_mask : ((1u << (k * k)) - 1u);
   auto tap_on = [&](int r, int s) { return (mask >> (r * k + s)) & 1u; };
-  auto push = [&](int map, int dh, int dw, int c0, int r, int s, int cbase) {
+  auto push_v = [&](int map, int dh, int dw, int c0, int r, int s, int cbase, int valid) {
     pl.ksteps.push_back(static_cast<uint32_t>(map) | (static_cast<uint32_t>(dh + 8) << 2) |
                         (static_cast<uint32_t>(dw + 8) << 6) | (static_cast<uint32_t>(c0) << 10));
     pl.pack_info.push_back(static_cast<uint32_t>(r) | (static_cast<uint32_t>(s) << 3) |
-                           (static_cast<uint32_t>(cbase) << 6));
+                           (static_cast<uint32_t>(valid - 1) << 6) | (static_cast<uint32_t>(cbase) << 13));
   };
 
   if (!d.transposed && d.stride == 1) {
@@ -784,7 +899,7 @@ int build_plan(const stemb200_conv_desc& d, Plan& pl) {
       for (int s = 0; s < k; ++s) {
         if (!tap_on(r, s)) continue;
         for (int src = 0; src < d.n_src; ++src)
-          for (int c0 = 0; c0 < d.c_in[src]; c0 += kKChunk) push(src, r - pad, s - pad, c0, r, s, src_base[src] + c0);
+          for (int c0 = 0; c0 < d.c_in[src]; c0 += kKChunk) push_v(src, r - pad, s - pad, c0, r, s, src_base[src] + c0, std::min(kKChunk, d.c_in[src] - c0));
       }
     pl.n_sub = 1;
     pl.sub_kbeg[0] = 0;
@@ -807,7 +922,7 @@ int build_plan(const stemb200_conv_desc& d, Plan& pl) {
         const int a = r - pad, b = s - pad;
         const int ph = a & 1, pw = b & 1;
         const int dh = (a - ph) / 2, dw = (b - pw) / 2;
-        for (int c0 = 0; c0 < d.c_in[0]; c0 += kKChunk) push(ph * 2 + pw, dh, dw, c0, r, s, c0);
+        for (int c0 = 0; c0 < d.c_in[0]; c0 += kKChunk) push_v(ph * 2 + pw, dh, dw, c0, r, s, c0, std::min(kKChunk, d.c_in[0] - c0));
       }
     pl.n_sub = 1;
     pl.sub_kbeg[0] = 0;
@@ -835,7 +950,7 @@ int build_plan(const stemb200_conv_desc& d, Plan& pl) {
           if ((q + pad - s) & 1) continue;
           if (!tap_on(r, s)) continue;
           const int dh = (p + pad - r) / 2, dw = (q + pad - s) / 2;
-          for (int c0 = 0; c0 < d.c_in[0]; c0 += kKChunk) push(0, dh, dw, c0, r, s, c0);
+          for (int c0 = 0; c0 < d.c_in[0]; c0 += kKChunk) push_v(0, dh, dw, c0, r, s, c0, std::min(kKChunk, d.c_in[0] - c0));
         }
       }
       pl.sub_kend[sp] = static_cast<int>(pl.ksteps.size());
@@ -932,17 +1047,17 @@ int encode_weight(CUtensorMap* m, const void* base, long long K, int c_out, int 
   return 0;
 }
 
-template <int BLOCK_N>
+template <int BLOCK_N, int EPI = 0>
 int launch_conv(const ConvKernelParams& kp, int grid, cudaStream_t stream) {
   using Cfg = ConvCfg<BLOCK_N>;
   static bool configured = false;  // benign race: attribute set is idempotent
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(conv_igemm_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(conv_igemm_kernel<BLOCK_N, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          Cfg::kSmemBytes);
     if (e != cudaSuccess) return set_cuda_error("cudaFuncSetAttribute(conv)", e);
     configured = true;
   }
-  conv_igemm_kernel<BLOCK_N><<<grid, kNumThreads, Cfg::kSmemBytes, stream>>>(kp);
+  conv_igemm_kernel<BLOCK_N, EPI><<<grid, kNumThreads, Cfg::kSmemBytes, stream>>>(kp);
   count_launch();
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_cuda_error("conv_igemm launch", e);
@@ -988,7 +1103,7 @@ extern "C" int stemb200_conv2d_pack_weight(const stemb200_conv_desc* d, const fl
 namespace {
 // geometry + pointers -> kernel parameters (tensor maps, k-step table, tiling)
 int setup_params(const stemb200_conv_desc* d, const Plan& pl, const void* const* in, const void* packed_weight,
-                 const float* bias, void* out, ConvKernelParams& kp) {
+                 const float* bias, const void* aux, void* out, ConvKernelParams& kp) {
   memset(&kp, 0, sizeof(kp));
   int th = d->tile_h, tw = d->tile_w;
   if (th <= 0 || tw <= 0) pick_tile(pl.h_out, pl.w_out, th, tw);
@@ -1005,10 +1120,11 @@ int setup_params(const stemb200_conv_desc* d, const Plan& pl, const void* const*
   if (int rc = encode_weight(&kp.b_map, packed_weight, K, d->c_out, pl.block_n)) return rc;
   const int out_bytes = d->out_dtype == STEMB200_DT_F32 ? 4 : 2;
   const int out_box_c = d->out_dtype == STEMB200_DT_F32 ? 32 : 64;
+  const int out_c = d->epilogue == STEMB200_EPI_SFT ? d->c_out / 2 : d->c_out;
   if (!d->direct_store) {
     for (int sp = 0; sp < 4; ++sp) {
       const int ss = sp < pl.n_sub ? sp : 0;
-      if (int rc = encode_nhwc(&kp.out_map[sp], out, out_bytes, d->batch, pl.full_h, pl.full_w, d->c_out, pl.os,
+      if (int rc = encode_nhwc(&kp.out_map[sp], out, out_bytes, d->batch, pl.full_h, pl.full_w, out_c, pl.os,
                                pl.sub_p[ss], pl.sub_q[ss], out_box_c, tw, th))
         return rc;
     }
@@ -1044,6 +1160,7 @@ int setup_params(const stemb200_conv_desc* d, const Plan& pl, const void* const*
   kp.full_h = pl.full_h;
   kp.full_w = pl.full_w;
   kp.bias = bias;
+  kp.aux = static_cast<const __half*>(aux);
   kp.out = out;
   kp.beta = bias;
   kp.igdn = 0;
@@ -1052,57 +1169,82 @@ int setup_params(const stemb200_conv_desc* d, const Plan& pl, const void* const*
 }  // namespace
 
 extern "C" int stemb200_conv2d_fwd(const stemb200_conv_desc* d, const void* const* in,
-                                   const void* packed_weight, const float* bias, void* out, void* stream) {
+                                   const void* packed_weight, const float* bias, const void* aux, void* out,
+                                   void* stream) {
   if (!d || !in || !packed_weight || !bias || !out) return set_error("conv2d_fwd: null argument");
   Plan pl;
   if (int rc = build_plan(*d, pl)) return rc;
+  if (d->epilogue != STEMB200_EPI_LINEAR && !aux) return set_error("conv2d_fwd: SFT / residual epilogue needs aux");
   for (int s = 0; s < d->n_src; ++s)
     if (!in[s]) return set_error("conv2d_fwd: null input");
   ConvKernelParams kp;
-  if (int rc = setup_params(d, pl, in, packed_weight, bias, out, kp)) return rc;
+  if (int rc = setup_params(d, pl, in, packed_weight, bias, aux, out, kp)) return rc;
   const int grid = std::min(kp.total_tiles, num_sms());
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (d->epilogue == STEMB200_EPI_SFT) {
+    if (pl.block_n == 256) return launch_conv<256, 1>(kp, grid, st);
+    return launch_conv<128, 1>(kp, grid, st);
+  }
+  if (d->epilogue == STEMB200_EPI_ADD) {
+    switch (pl.block_n) {
+      case 64: return launch_conv<64, 2>(kp, grid, st);
+      case 128: return launch_conv<128, 2>(kp, grid, st);
+      case 192: return launch_conv<192, 2>(kp, grid, st);
+      default: return launch_conv<256, 2>(kp, grid, st);
+    }
+  }
   switch (pl.block_n) {
     case 16: return launch_conv<16>(kp, grid, st);
     case 64: return launch_conv<64>(kp, grid, st);
     case 96: return launch_conv<96>(kp, grid, st);
     case 128: return launch_conv<128>(kp, grid, st);
+    case 160: return launch_conv<160>(kp, grid, st);
     case 192: return launch_conv<192>(kp, grid, st);
     case 256: return launch_conv<256>(kp, grid, st);
     default: return set_error("conv2d_fwd: no kernel for this c_out");
   }
 }
 
+namespace {
+template <int kNT>
+int launch_gdn(const ConvKernelParams& kp, int grid, cudaStream_t stream) {
+  using Cfg = GdnCfgT<kNT>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(conv_gdn_kernel<kNT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         Cfg::kSmemBytes);
+    if (e != cudaSuccess) return set_cuda_error("cudaFuncSetAttribute(conv_gdn)", e);
+    configured = true;
+  }
+  conv_gdn_kernel<kNT><<<grid, kNumThreads, Cfg::kSmemBytes, stream>>>(kp);
+  count_launch();
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_cuda_error("conv_gdn launch", e);
+  return 0;
+}
+}  // namespace
+
 extern "C" int stemb200_conv2d_gdn_fwd(const stemb200_conv_desc* d, const void* const* in,
                                        const void* packed_weight, const float* bias, const void* packed_gamma,
                                        const float* beta, int32_t inverse, void* out, void* stream) {
   if (!d || !in || !packed_weight || !bias || !packed_gamma || !beta || !out)
     return set_error("conv2d_gdn_fwd: null argument");
-  if (d->c_out != GdnCfg::kN) return set_error("conv2d_gdn_fwd: fused GDN needs c_out == 192");
+  if (d->c_out != 192 && d->c_out != 128) return set_error("conv2d_gdn_fwd: fused GDN needs c_out == 128 or 192");
   if (d->out_dtype != STEMB200_DT_F16 || d->direct_store || d->lrelu_slope != 1.0f || d->sq_scale <= 0.f)
     return set_error("conv2d_gdn_fwd: needs fp16 TMA-store output, no activation, sq_scale > 0");
   stemb200_conv_desc dd = *d;
+  dd.epilogue = STEMB200_EPI_LINEAR;
   Plan pl;
   if (int rc = build_plan(dd, pl)) return rc;
-  if (pl.block_n != GdnCfg::kN) return set_error("conv2d_gdn_fwd: unexpected N tile");
+  pl.block_n = d->c_out;  // one N tile holds every channel of a pixel
   for (int s = 0; s < d->n_src; ++s)
     if (!in[s]) return set_error("conv2d_gdn_fwd: null input");
   ConvKernelParams kp;
-  if (int rc = setup_params(&dd, pl, in, packed_weight, bias, out, kp)) return rc;
-  if (int rc = encode_weight(&kp.g_map, packed_gamma, GdnCfg::kN, GdnCfg::kN, GdnCfg::kN)) return rc;
+  if (int rc = setup_params(&dd, pl, in, packed_weight, bias, nullptr, out, kp)) return rc;
+  if (int rc = encode_weight(&kp.g_map, packed_gamma, d->c_out, d->c_out, d->c_out)) return rc;
   kp.beta = beta;
   kp.igdn = inverse ? 1 : 0;
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(conv_gdn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         GdnCfg::kSmemBytes);
-    if (e != cudaSuccess) return set_cuda_error("cudaFuncSetAttribute(conv_gdn)", e);
-    configured = true;
-  }
   const int grid = std::min(kp.total_tiles, num_sms());
-  conv_gdn_kernel<<<grid, kNumThreads, GdnCfg::kSmemBytes, static_cast<cudaStream_t>(stream)>>>(kp);
-  count_launch();
-  cudaError_t e = cudaGetLastError();
-  if (e != cudaSuccess) return set_cuda_error("conv_gdn launch", e);
-  return 0;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  return d->c_out == 192 ? launch_gdn<192>(kp, grid, st) : launch_gdn<128>(kp, grid, st);
 }

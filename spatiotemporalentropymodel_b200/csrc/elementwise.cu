@@ -140,6 +140,106 @@ im2col_k5s2_c3_kernel(const float* __restrict__ x, __half* __restrict__ rows, in
 }
 
 // ---------------------------------------------------------------------------------------------------
+// stem_roi staging: im2col for conv(4, 192, k3, s1) on cat[x (3 ch), Qmap (1 ch)] (stem_roi.py:379, :586),
+// rows of 40 fp16: k = (r*3 + s)*4 + ch for the 36 real entries, then 4 zeros. Same scheme as above.
+// ---------------------------------------------------------------------------------------------------
+constexpr int kIm2col3Row = 40;
+constexpr int kIm2col3InW = kIm2colPix + 2;
+
+__global__ void __launch_bounds__(256)
+im2col_k3s1_c4_kernel(const float* __restrict__ x, const float* __restrict__ q, __half* __restrict__ rows, int h,
+                      int w) {
+  __shared__ float s_in[4][3][kIm2col3InW + 2];
+  const int n = blockIdx.z, oh = blockIdx.y, ow0 = blockIdx.x * kIm2colPix;
+  for (int i = threadIdx.x; i < 4 * 3 * kIm2col3InW; i += blockDim.x) {
+    const int col = i % kIm2col3InW, rr = (i / kIm2col3InW) % 3, ch = i / (3 * kIm2col3InW);
+    const int ih = oh - 1 + rr, iw = ow0 - 1 + col;
+    float v = 0.f;
+    if (ih >= 0 && ih < h && iw >= 0 && iw < w)
+      v = ch < 3 ? __ldg(x + ((static_cast<long long>(n) * 3 + ch) * h + ih) * w + iw)
+                 : __ldg(q + (static_cast<long long>(n) * h + ih) * w + iw);
+    s_in[ch][rr][col] = v;
+  }
+  __syncthreads();
+  const int npix = min(kIm2colPix, w - ow0);
+  uint4* dst = reinterpret_cast<uint4*>(rows + ((static_cast<long long>(n) * h + oh) * w + ow0) * kIm2col3Row);
+  for (int qd = threadIdx.x; qd < npix * (kIm2col3Row / 8); qd += blockDim.x) {
+    const int px = qd / (kIm2col3Row / 8), piece = qd - px * (kIm2col3Row / 8);
+    uint32_t pk[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float f[2];
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int k = piece * 8 + 2 * j + e;
+        const int tap = k >> 2, ch = k & 3, r = tap / 3, sx = tap - r * 3;
+        f[e] = k < 36 ? s_in[ch][r][px + sx] : 0.f;
+      }
+      const __half2 hh = __floats2half2_rn(f[0], f[1]);
+      pk[j] = *reinterpret_cast<const uint32_t*>(&hh);
+    }
+    dst[qd] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+  }
+}
+
+// mean pooling by an integer factor, NHWC fp16 (F.adaptive_avg_pool2d with divisible sizes, stem_utils.py:37)
+__global__ void avgpool_nhwc_f16_kernel(const __half* __restrict__ in, __half* __restrict__ out, int h_out, int w_out,
+                                        int c, int f, long long total) {
+  const int c8 = c >> 3;
+  const float inv = 1.0f / static_cast<float>(f * f);
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int piece = static_cast<int>(i % c8);
+    long long t = i / c8;
+    const int ow = static_cast<int>(t % w_out);
+    t /= w_out;
+    const int oh = static_cast<int>(t % h_out);
+    const long long n = t / h_out;
+    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int dy = 0; dy < f; ++dy)
+      for (int dx = 0; dx < f; ++dx) {
+        const long long pin = ((n * h_out * f + (oh * f + dy)) * static_cast<long long>(w_out) * f + (ow * f + dx));
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(in + pin * c) + piece);
+        const uint32_t* u = reinterpret_cast<const uint32_t*>(&v);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float2 f2 = __half22float2(*reinterpret_cast<const __half2*>(&u[k]));
+          acc[2 * k] += f2.x;
+          acc[2 * k + 1] += f2.y;
+        }
+      }
+    uint32_t pk[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const __half2 hh = __floats2half2_rn(acc[2 * k] * inv, acc[2 * k + 1] * inv);
+      pk[k] = *reinterpret_cast<const uint32_t*>(&hh);
+    }
+    reinterpret_cast<uint4*>(out + i / c8 * c)[piece] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+  }
+}
+
+// quality map staging for the hyper-encoder (stem_roi.py:563-564): (B,1,H,W) fp32 -> mean over f x f blocks ->
+// NHWC fp16 with 8 channels (channel 0 = pooled map, 1..7 = 0) so it can be a K-segment of the next conv
+__global__ void qmap_pool_kernel(const float* __restrict__ q, __half* __restrict__ out, int h_out, int w_out, int f,
+                                 long long total) {
+  const float inv = 1.0f / static_cast<float>(f * f);
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int ow = static_cast<int>(i % w_out);
+    long long t = i / w_out;
+    const int oh = static_cast<int>(t % h_out);
+    const long long n = t / h_out;
+    const float* base = q + (n * h_out * f + static_cast<long long>(oh) * f) * (static_cast<long long>(w_out) * f) +
+                        static_cast<long long>(ow) * f;
+    float acc = 0.f;
+    for (int dy = 0; dy < f; ++dy)
+      for (int dx = 0; dx < f; ++dx) acc += __ldg(base + static_cast<long long>(dy) * w_out * f + dx);
+    const __half2 hh = __floats2half2_rn(acc * inv, 0.f);
+    reinterpret_cast<uint4*>(out)[i] = make_uint4(*reinterpret_cast<const uint32_t*>(&hh), 0, 0, 0);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
 // latent staging
 // ---------------------------------------------------------------------------------------------------
 __global__ void latent_stage_kernel(const float* __restrict__ y, const __half* __restrict__ cond,
@@ -486,6 +586,41 @@ extern "C" int stemb200_im2col_k5s2_c3(const float* x_nchw, void* out_rows, int3
   im2col_k5s2_c3_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
       x_nchw, static_cast<__half*>(out_rows), h, w, h_out, w_out, pad_top, pad_left);
   CHECK_LAUNCH("im2col_k5s2_c3");
+  return 0;
+}
+
+extern "C" int stemb200_im2col_k3s1_c4(const float* x_nchw, const float* q_nchw, void* out_rows, int32_t n,
+                                       int32_t h, int32_t w, void* stream) {
+  if (!x_nchw || !q_nchw || !out_rows || n < 1 || h < 1 || w < 1 || h > 65535 || n > 65535)
+    return set_error("im2col_k3s1_c4: bad argument");
+  dim3 grid((w + kIm2colPix - 1) / kIm2colPix, h, n);
+  im2col_k3s1_c4_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(x_nchw, q_nchw,
+                                                                            static_cast<__half*>(out_rows), h, w);
+  CHECK_LAUNCH("im2col_k3s1_c4");
+  return 0;
+}
+
+extern "C" int stemb200_avgpool_nhwc_f16(const void* in, void* out, int32_t n, int32_t h_out, int32_t w_out,
+                                         int32_t c, int32_t factor, void* stream) {
+  if (!in || !out || n < 1 || h_out < 1 || w_out < 1 || c < 8 || c % 8 || factor < 1)
+    return set_error("avgpool_nhwc_f16: bad argument");
+  const long long total = static_cast<long long>(n) * h_out * w_out * (c / 8);
+  const int blocks = static_cast<int>(std::min<long long>((total + 255) / 256, 148LL * 32));
+  avgpool_nhwc_f16_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __half*>(in), static_cast<__half*>(out), h_out, w_out, c, factor, total);
+  CHECK_LAUNCH("avgpool_nhwc_f16");
+  return 0;
+}
+
+extern "C" int stemb200_qmap_pool(const float* q_nchw, void* out_nhwc8_f16, int32_t n, int32_t h_out, int32_t w_out,
+                                  int32_t factor, void* stream) {
+  if (!q_nchw || !out_nhwc8_f16 || n < 1 || h_out < 1 || w_out < 1 || factor < 1)
+    return set_error("qmap_pool: bad argument");
+  const long long total = static_cast<long long>(n) * h_out * w_out;
+  const int blocks = static_cast<int>(std::min<long long>((total + 255) / 256, 148LL * 16));
+  qmap_pool_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      q_nchw, static_cast<__half*>(out_nhwc8_f16), h_out, w_out, factor, total);
+  CHECK_LAUNCH("qmap_pool");
   return 0;
 }
 

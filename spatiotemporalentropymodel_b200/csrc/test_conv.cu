@@ -117,7 +117,7 @@ static int run_case(const Case& cs, bool timing) {
   void* dout;
   CK(cudaMalloc(&dout, nout * obytes));
   CK(cudaMemset(dout, 0xFF, nout * obytes));  // NaN pattern: unwritten outputs are caught
-  int rc = stemb200_conv2d_fwd(&d, din.data(), dpk, db, dout, 0);
+  int rc = stemb200_conv2d_fwd(&d, din.data(), dpk, db, nullptr, dout, 0);
   if (rc) {
     printf("[%s] conv2d_fwd failed: %s\n", cs.name.c_str(), stemb200_last_error());
     return 1;
@@ -203,10 +203,10 @@ static int run_case(const Case& cs, bool timing) {
     cudaEvent_t e0, e1;
     CK(cudaEventCreate(&e0));
     CK(cudaEventCreate(&e1));
-    for (int i = 0; i < 3; ++i) stemb200_conv2d_fwd(&d, din.data(), dpk, db, dout, 0);
+    for (int i = 0; i < 3; ++i) stemb200_conv2d_fwd(&d, din.data(), dpk, db, nullptr, dout, 0);
     CK(cudaEventRecord(e0));
     const int iters = 10;
-    for (int i = 0; i < iters; ++i) stemb200_conv2d_fwd(&d, din.data(), dpk, db, dout, 0);
+    for (int i = 0; i < iters; ++i) stemb200_conv2d_fwd(&d, din.data(), dpk, db, nullptr, dout, 0);
     CK(cudaEventRecord(e1));
     CK(cudaEventSynchronize(e1));
     float ms;

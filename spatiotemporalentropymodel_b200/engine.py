@@ -18,7 +18,7 @@ import torch
 import torch.nn.functional as F
 
 from . import _lib
-from ._lib import DT_F16, DT_F32, ConvDesc
+from ._lib import DT_F16, DT_F32, EPI_ADD, EPI_LINEAR, EPI_SFT, ConvDesc
 
 Tensor = torch.Tensor
 MASK_A_5x5 = 0x00000FFF  # taps (r, s) with r < 2, or r == 2 and s < 2 (layers/layers.py:39-42)
@@ -65,7 +65,7 @@ class ConvOp:
     def __init__(self, weight: Tensor, bias: Tensor, *, c_in: Sequence[int], c_out: int, k: int, stride: int = 1,
                  transposed: bool = False, tap_mask: int = 0, slope: float = 1.0, out_dtype: int = DT_F16,
                  direct_store: bool = False, gdn: Optional[Tuple[Tensor, Tensor, bool]] = None,
-                 alg_flops_per_out_pixel: Optional[float] = None):
+                 alg_flops_per_out_pixel: Optional[float] = None, epilogue: int = EPI_LINEAR):
         """gdn = (beta', gamma', inverse) with the re-parametrised beta (C,) / gamma (C, C): the layer is followed
         by GDN / IGDN and both run in one kernel (stemb200_conv2d_gdn_fwd)."""
         _require_cuda(weight, bias)
@@ -84,6 +84,7 @@ class ConvOp:
         d.stride = stride
         d.transposed = int(transposed)
         d.tap_mask = tap_mask
+        d.epilogue = epilogue
         d.lrelu_slope = slope
         d.out_dtype = out_dtype
         d.sq_scale = SQ_SCALE
@@ -132,18 +133,45 @@ class ConvOp:
             return (h + 2 * p - self.k) // 2 + 1, (w + 2 * p - self.k) // 2 + 1
         return h, w
 
-    def __call__(self, inputs: Sequence[Tensor], batch: int, h: int, w: int, out: Tensor) -> Tensor:
+    def __call__(self, inputs: Sequence[Tensor], batch: int, h: int, w: int, out: Tensor,
+                 aux: Optional[Tensor] = None) -> Tensor:
         d = self.desc
         d.batch, d.h_in, d.w_in = batch, h, w
         arr = (C.c_void_p * len(inputs))(*[t.data_ptr() for t in inputs])
         if self.gdn is None:
             _lib.check(self.lib.stemb200_conv2d_fwd(C.byref(d), arr, self.packed.data_ptr(), self.bias.data_ptr(),
-                                                    out.data_ptr(), _stream()), "conv2d_fwd")
+                                                    _ptr(aux), out.data_ptr(), _stream()), "conv2d_fwd")
         else:
             _lib.check(self.lib.stemb200_conv2d_gdn_fwd(C.byref(d), arr, self.packed.data_ptr(), self.bias.data_ptr(),
                                                         self.gamma_packed.data_ptr(), self.beta.data_ptr(),
                                                         int(self.gdn), out.data_ptr(), _stream()), "conv2d_gdn_fwd")
         return out
+
+
+def sft_op(w_gamma: Tensor, b_gamma: Tensor, w_beta: Tensor, b_beta: Tensor, c_in: int, slope: float = 1.0) -> ConvOp:
+    """SFT.mlp_gamma / mlp_beta (stem_utils.py:33-34) as ONE conv whose epilogue applies x*(1+gamma)+beta
+    (:41): output rows are interleaved per 64 channels as [gamma(64) | beta(64)], and the "+1" goes into the
+    gamma bias. Returns a ConvOp to be called with aux = x; its output has x's channel count."""
+    C = w_gamma.shape[0]
+    if C % 64:
+        raise ValueError("SFT channel count must be a multiple of 64")
+    k = w_gamma.shape[-1]
+    ws, bs = [], []
+    for g0 in range(0, C, 64):
+        ws += [w_gamma[g0:g0 + 64], w_beta[g0:g0 + 64]]
+        bs += [b_gamma[g0:g0 + 64] + 1.0, b_beta[g0:g0 + 64]]
+    op = ConvOp(torch.cat(ws, 0).contiguous(), torch.cat(bs, 0).contiguous(), c_in=[c_in], c_out=2 * C, k=k,
+                slope=slope, epilogue=EPI_SFT,
+                alg_flops_per_out_pixel=2.0 * c_in * 2 * C * k * k)
+    op.c_out_real = C
+    return op
+
+
+def avgpool_nhwc(x: Tensor, out: Tensor, factor: int) -> Tensor:
+    n, ho, wo, c = out.shape
+    _lib.check(_lib.load().stemb200_avgpool_nhwc_f16(x.data_ptr(), out.data_ptr(), n, ho, wo, c, factor, _stream()),
+               "avgpool_nhwc_f16")
+    return out
 
 
 # ------------------------------------------------------------------------------------------------------

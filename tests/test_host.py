@@ -55,7 +55,7 @@ def test_c_abi_rejects_bad_arguments_without_a_gpu():
     """Argument validation happens before any CUDA call: error code + message, never a crash."""
     lib = _lib.load()
     d = _lib.ConvDesc()
-    assert lib.stemb200_conv2d_fwd(ctypes.byref(d), None, None, None, None, None) == -1
+    assert lib.stemb200_conv2d_fwd(ctypes.byref(d), None, None, None, None, None, None) == -1
     assert b"null argument" in lib.stemb200_last_error()
     d.batch, d.h_in, d.w_in, d.n_src, d.c_out, d.kh, d.kw, d.stride = 1, 8, 8, 1, 192, 4, 4, 1
     d.c_in[0] = 192
@@ -68,6 +68,8 @@ def test_c_abi_rejects_bad_arguments_without_a_gpu():
     assert lib.stemb200_conv2d_packed_k(ctypes.byref(d)) == 25 * 192    # 9 + 6 + 6 + 4 taps over the 4 phases
     d.c_in[0] = 100
     assert lib.stemb200_conv2d_packed_k(ctypes.byref(d)) == -1          # channels must be a multiple of 8
+    d.c_in[0] = 80
+    assert lib.stemb200_conv2d_packed_k(ctypes.byref(d)) == 25 * 128    # ragged: 80 channels occupy two K chunks
     assert lib.stemb200_gaussian_conditional_flat(None, None, None, 0, None, 0, 0.11, 1e-9, None, None, None, None,
                                                   None, None) == -1
     assert lib.stemb200_synthesis_tail(None, None, 1, 1, 1, None, 0, 0, 0, 0, None, None) == -1
