@@ -31,6 +31,8 @@ WORKLOADS = {
     "nospm_1frame_1080p": ("SpatioTemporalPriorModelWithoutSPM", 1, 1080, 1920,
                            "configs[1]: SpatioTemporalPriorModelWithoutSPM P-frame forward, 1 frame"),
     "smoke_256": ("SpatioTemporalPriorModel", 2, 256, 256, "configs[0]-shaped quick run"),
+    "stem_roi_4k": ("stem_roi", 1, 2160, 3840, "configs[4]: variable-rate SFT STEM (stem_roi), 3840x2160 frame"),
+    "stem_roi_1080p": ("stem_roi", 2, 1080, 1920, "stem_roi at 1080p (2 frames per step)"),
 }
 
 METRIC = "1080p P-frames/sec (STEM fwd+likelihoods)"
@@ -177,6 +179,112 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def run_stem_roi(args):
+    """BASELINE.json configs[4]: stem_roi.forward (x_cur, x_conditioned, Qmap) on frames padded to a multiple of
+    64, one model replica per GPU, frames sharded over ranks (weak scaling), fps = frames / max-over-ranks time."""
+    import torch.distributed as dist
+    import torch.nn.functional as F
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"
+        dist.init_process_group("nccl", device_id=dev)
+    from spatiotemporalentropymodel_b200 import _lib, stem_roi as R, synthetic as S
+    from spatiotemporalentropymodel_b200.engine import ConvOp
+    _, T, H, W, desc = WORKLOADS[args.workload]
+    model = R.stem_roi()
+    model.load_state_dict(R.make_synthetic_state_dict(0))
+    model.update(force=True)
+    model = model.to(dev).eval()
+    Hp, Wp = (H + 63) // 64 * 64, (W + 63) // 64 * 64
+    frames = S.make_frames(T + 1, H, W, seed=77 + rank)
+    pad = (0, Wp - W, 0, Hp - H)
+    x_cur = F.pad(frames[1:], pad).to(dev)
+    x_cond = F.pad(frames[:-1], pad).to(dev)
+    qmap = R.make_qmap(T, Hp, Wp, "ramp").to(dev)
+    step = lambda: model(x_cur, x_cond, qmap)  # noqa: E731
+    for _ in range(max(args.warmup, 3)):
+        out = step()
+    torch.cuda.synchronize()
+    flops = []
+    orig = ConvOp.__call__
+
+    def counting(self, inputs, batch, h, w, out_, aux=None):
+        flops.append(self.alg_flops(batch, h, w))
+        return orig(self, inputs, batch, h, w, out_, aux)
+
+    ConvOp.__call__ = counting
+    try:
+        step()
+    finally:
+        ConvOp.__call__ = orig
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local_rank)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    if rank == 0:
+        sampler.start()
+    n0 = _lib.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        out = step()
+    e1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_total = float(ms.item())
+    clocks = sampler.stop() if rank == 0 else None
+    launches = _lib.launch_count() - n0
+    # e2e: pinned host frames + quality map in, bits out
+    hx, hc, hq = x_cur.cpu().pin_memory(), x_cond.cpu().pin_memory(), qmap.cpu().pin_memory()
+    hbits = torch.empty((2, T), dtype=torch.float64).pin_memory()
+
+    def e2e(n):
+        for _ in range(n):
+            o = model(hx.to(dev, non_blocking=True), hc.to(dev, non_blocking=True), hq.to(dev, non_blocking=True))
+            hbits.copy_(o["bits"], non_blocking=True)
+        torch.cuda.synchronize()
+
+    e2e(2)
+    t0 = time.perf_counter()
+    e2e(args.steps)
+    e2e_ms = torch.tensor([(time.perf_counter() - t0) * 1e3], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        peaks = load_peaks()
+        gflop_step = sum(flops) / 1e9
+        ms_step = ms_total / args.steps
+        print(json.dumps({
+            "metric": "frames/sec (stem_roi fwd+likelihoods)", "value": world * T * args.steps / (ms_total / 1e3),
+            "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f16 operands / f32 accumulate (tcgen05 kind::f16); entropy kernels f32", "data": "synthetic",
+            "config": {"workload": args.workload, "desc": desc, "variant": "stem_roi", "height": H, "width": W,
+                       "frames_per_step": T, "cuda_graph": False,
+                       "l2": "per-step working set (> 10 GB of activations at 4K) exceeds the 126 MB L2"},
+            "clocks": clocks,
+            "e2e": {"value": world * T * args.steps / (float(e2e_ms.item()) / 1e3), "unit": UNIT,
+                    "h2d_bytes_per_step": (hx.numel() + hc.numel() + hq.numel()) * 4, "d2h_bytes_per_step": hbits.numel() * 8},
+            "gpu_launches": launches,
+            "roofline": {"bound": "tensor", "kernel": "all dense contractions of the step (conv_igemm / conv_gdn)",
+                         "achieved": gflop_step / ms_step, "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
+                         "frac": gflop_step / ms_step / peaks["tf_sustained"], "traffic": None,
+                         "note": "whole-step time (includes the non-GEMM kernels), algorithmic FLOPs"},
+            "cpu_baseline": None, "algorithmic_gflop_per_frame": gflop_step / T}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -192,6 +300,10 @@ def main():
 
     if args.impl == "reference":
         run_reference(args)
+        return
+
+    if WORKLOADS[args.workload][0] == "stem_roi":
+        run_stem_roi(args)
         return
 
     rank = int(os.environ.get("RANK", "0"))

@@ -121,6 +121,8 @@ int stemb200_im2col_k3s1_c4(const float* x_nchw, const float* q_nchw, void* out_
                             int32_t w, void* stream);
 int stemb200_avgpool_nhwc_f16(const void* in, void* out, int32_t n, int32_t h_out, int32_t w_out, int32_t c,
                               int32_t factor, void* stream);
+/* fp16 -> fp32 element cast (numel % 8 == 0): latents produced by an fp16 epilogue that feed the entropy kernels */
+int stemb200_cast_f16_to_f32(const void* in, float* out, int64_t numel, void* stream);
 int stemb200_qmap_pool(const float* q_nchw, void* out_nhwc8_f16, int32_t n, int32_t h_out, int32_t w_out,
                        int32_t factor, void* stream);
 
@@ -170,11 +172,11 @@ int stemb200_entropy_bottleneck_fwd(const float* z_nhwc, const float* params, in
  * MSE). The transposed conv itself runs through stemb200_conv2d_fwd as a stride-2 conv over 2x2 input super pixels
  * (k5 with the r = 0 / s = 0 taps masked = a 4x4 window, 48 (+16 pad) outputs: channel (u*4+v)*3 + c holds
  * x_hat[c][4i+u][4j+v]); this entry point un-shuffles in: NHWC fp32 [n][h4][w4][64] to x_hat NCHW fp32
- * [n][3][4*h4][4*w4] clamped to [0,1]. When x_ref != NULL (unpadded NCHW fp32 [n][3][h_ref][w_ref], embedded at
+ * [n][3][4*h4][4*w4], clamped to [0,1] when clamp01 != 0 (stem_roi.forward returns it unclamped). When x_ref != NULL (unpadded NCHW fp32 [n][3][h_ref][w_ref], embedded at
  * pad_top/pad_left) sq_err[frame] (double) += sum (x_ref - x_hat)^2 over the un-padded area. */
 int stemb200_synthesis_tail(const float* in_nhwc64, float* x_hat_nchw, int32_t n, int32_t h4, int32_t w4,
                             const float* x_ref, int32_t h_ref, int32_t w_ref, int32_t pad_top, int32_t pad_left,
-                            double* sq_err, void* stream);
+                            double* sq_err, int32_t clamp01, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------
  * Host-side helper that the reference implements in C++ (compressai/cpp_exts/ops/ops.cpp:24-81)

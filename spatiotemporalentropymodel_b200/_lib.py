@@ -57,7 +57,8 @@ SIGNATURES = {
                                                      _vp, _vp, _vp]),
     "stemb200_entropy_bottleneck_fwd": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _f32, _vp, _vp, _vp, _vp,
                                                   _vp]),
-    "stemb200_synthesis_tail": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _vp, _i32, _i32, _i32, _i32, _vp, _vp]),
+    "stemb200_synthesis_tail": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _vp, _i32, _i32, _i32, _i32, _vp, _i32, _vp]),
+    "stemb200_cast_f16_to_f32": (C.c_int, [_vp, _vp, _i64, _vp]),
     "stemb200_pmf_to_quantized_cdf_host": (C.c_int, [C.POINTER(C.c_float), _i32, _i32, C.POINTER(C.c_int32)]),
 }
 

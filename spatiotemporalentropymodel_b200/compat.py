@@ -56,6 +56,10 @@ def install(force: bool = False) -> None:
         setattr(stp, n, getattr(m, n))
         setattr(models_pkg, n, getattr(m, n))
     stp.__all__ = names
+    from . import stem_roi as roi
+    roi_mod = types.ModuleType("compressai.models.stem_roi")
+    roi_mod.stem_roi = roi.stem_roi
+    models_pkg.stem_roi = roi_mod
     priors = types.ModuleType("compressai.models.priors")
     priors.CompressionModel = m.CompressionModel
     priors.JointAutoregressiveHierarchicalPriors = m.JointAutoregressiveHierarchicalPriors
@@ -75,5 +79,6 @@ def install(force: bool = False) -> None:
     models_pkg.spatiotemporalpriors, models_pkg.priors = stp, priors
     for name, mod in [("compressai", root), ("compressai.zoo", zoo), ("compressai.models", models_pkg),
                       ("compressai.models.spatiotemporalpriors", stp), ("compressai.models.priors", priors),
+                      ("compressai.models.stem_roi", roi_mod),
                       ("compressai.entropy_models", ent), ("compressai.layers", layers)]:
         sys.modules[name] = mod

@@ -239,6 +239,23 @@ __global__ void qmap_pool_kernel(const float* __restrict__ q, __half* __restrict
   }
 }
 
+__global__ void cast_f16_to_f32_kernel(const __half* __restrict__ in, float* __restrict__ out, long long n8) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n8;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const uint4 v = __ldg(reinterpret_cast<const uint4*>(in) + i);
+    const uint32_t* u = reinterpret_cast<const uint32_t*>(&v);
+    float4 a, b;
+    const float2 f0 = __half22float2(*reinterpret_cast<const __half2*>(&u[0]));
+    const float2 f1 = __half22float2(*reinterpret_cast<const __half2*>(&u[1]));
+    const float2 f2 = __half22float2(*reinterpret_cast<const __half2*>(&u[2]));
+    const float2 f3 = __half22float2(*reinterpret_cast<const __half2*>(&u[3]));
+    a = make_float4(f0.x, f0.y, f1.x, f1.y);
+    b = make_float4(f2.x, f2.y, f3.x, f3.y);
+    reinterpret_cast<float4*>(out)[2 * i] = a;
+    reinterpret_cast<float4*>(out)[2 * i + 1] = b;
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------
 // latent staging
 // ---------------------------------------------------------------------------------------------------
@@ -483,7 +500,7 @@ constexpr int kTailCh = 64;
 __global__ void __launch_bounds__(256)
 synthesis_tail_kernel(const float* __restrict__ in, float* __restrict__ xhat, int h4, int w4,
                       const float* __restrict__ xref, int h_ref, int w_ref, int pad_top, int pad_left,
-                      double* sq_err) {
+                      double* sq_err, int clamp01) {
   __shared__ float red[32];
   const int n = blockIdx.y;
   const long long per = static_cast<long long>(h4) * w4;
@@ -509,7 +526,10 @@ synthesis_tail_kernel(const float* __restrict__ in, float* __restrict__ xhat, in
         const int Y = 4 * ii + u;
         float o[4];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) o[q] = fminf(fmaxf(v[(u * 4 + q) * 3 + ch], 0.f), 1.f);
+        for (int q = 0; q < 4; ++q) {
+          const float raw = v[(u * 4 + q) * 3 + ch];
+          o[q] = clamp01 ? fminf(fmaxf(raw, 0.f), 1.f) : raw;
+        }
         const long long off = ((static_cast<long long>(n) * 3 + ch) * H + Y) * W + 4 * jj;
         *reinterpret_cast<float4*>(xhat + off) = make_float4(o[0], o[1], o[2], o[3]);
         if (xref) {
@@ -624,6 +644,16 @@ extern "C" int stemb200_qmap_pool(const float* q_nchw, void* out_nhwc8_f16, int3
   return 0;
 }
 
+extern "C" int stemb200_cast_f16_to_f32(const void* in, float* out, int64_t numel, void* stream) {
+  if (!in || !out || numel < 8 || numel % 8) return set_error("cast_f16_to_f32: bad argument");
+  const long long n8 = numel / 8;
+  const int blocks = static_cast<int>(std::min<long long>((n8 + 255) / 256, 148LL * 16));
+  cast_f16_to_f32_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const __half*>(in), out,
+                                                                               n8);
+  CHECK_LAUNCH("cast_f16_to_f32");
+  return 0;
+}
+
 extern "C" int stemb200_latent_stage(const float* y_nhwc, const void* cond_f16, void* y_f16, void* yq_f16,
                                      void* yhat_f16, int64_t numel, void* stream) {
   if (!y_nhwc || numel < 1) return set_error("latent_stage: bad argument");
@@ -690,12 +720,13 @@ extern "C" int stemb200_entropy_bottleneck_fwd(const float* z_nhwc, const float*
 
 extern "C" int stemb200_synthesis_tail(const float* in_nhwc64, float* x_hat_nchw, int32_t n, int32_t h4,
                                        int32_t w4, const float* x_ref, int32_t h_ref, int32_t w_ref,
-                                       int32_t pad_top, int32_t pad_left, double* sq_err, void* stream) {
+                                       int32_t pad_top, int32_t pad_left, double* sq_err, int32_t clamp01,
+                                       void* stream) {
   if (!in_nhwc64 || !x_hat_nchw || n < 1 || h4 < 1 || w4 < 1) return set_error("synthesis_tail: bad argument");
   const long long per = static_cast<long long>(h4) * w4;
   dim3 grid(static_cast<unsigned>(std::min<long long>((per + 255) / 256, 148LL * 16)), n);
   synthesis_tail_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      in_nhwc64, x_hat_nchw, h4, w4, x_ref, h_ref, w_ref, pad_top, pad_left, sq_err);
+      in_nhwc64, x_hat_nchw, h4, w4, x_ref, h_ref, w_ref, pad_top, pad_left, sq_err, clamp01);
   CHECK_LAUNCH("synthesis_tail");
   return 0;
 }

@@ -339,7 +339,7 @@ class TransformsEngine:
         if x_ref is not None:
             href, wref = x_ref.shape[2], x_ref.shape[3]
         _lib.check(lib.stemb200_synthesis_tail(merged.data_ptr(), out.data_ptr(), B, h // 2, w // 2, _ptr(x_ref), href,
-                                               wref, top, left, _ptr(sq_err), _stream()), "synthesis_tail")
+                                               wref, top, left, _ptr(sq_err), 1, _stream()), "synthesis_tail")
         return out
 
 

@@ -1,0 +1,515 @@
+"""Variable-rate / ROI STEM (`stem_roi`, compressai/models/stem_roi.py:353-700) on the B200 kernels.
+
+Same split as models.py: an nn.Module that only *holds* parameters under the reference's names (so reference
+checkpoints load) and an engine that runs the forward as a chain of libstemb200 kernels:
+
+  PEncoder (:520-538)        im2col -> GEMM+GDN, [conv s2 + GDN] x2, conv s2; SFT layers as ONE conv each
+                             (gamma|beta interleaved) with the x*(1+gamma)+beta epilogue; SFTResblk = 2 x
+                             (SFT+LeakyReLU(0.2) epilogue, 3x3 conv) with the skip add in the last conv's epilogue
+  quality-map pyramids       3x3 / 1x1 convs with LeakyReLU(0.1); adaptive_avg_pool2d = mean-pool kernel
+  ConditionEncoder (:493)    4 analysis layers (N = 128)
+  HE (:562-579), HD, TPM, EPM, EntropyBottleneck, GaussianConditional: as in the single-rate models
+  PDecoder (:540-560)        wmap generator, SFTResblk x2, [deconv + IGDN] + SFT x3, last deconv as super-pixel conv
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Tuple
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import _lib
+from ._lib import DT_F16, DT_F32, EPI_ADD
+from .engine import (ConvOp, Workspace, _gdn_fold, _ptr, _require_cuda, _stream, avgpool_nhwc, nchw_to_nhwc_f16,
+                     nhwc_f16_to_nchw, sft_op)
+from .entropy_models import GaussianConditional
+from .models import GDN, CompressionModel, _resize_registered_buffers, conv, deconv, get_scale_table
+
+Tensor = torch.Tensor
+
+
+# ------------------------------------------------------------------------------------------------------
+# parameter holders (stem_utils.py:24-63)
+# ------------------------------------------------------------------------------------------------------
+class SFT(nn.Module):
+    def __init__(self, x_nc, prior_nc=1, ks=3, nhidden=128):
+        super().__init__()
+        pw = ks // 2
+        self.mlp_shared = nn.Sequential(nn.Conv2d(prior_nc, nhidden, kernel_size=ks, padding=pw), nn.ReLU())
+        self.mlp_gamma = nn.Conv2d(nhidden, x_nc, kernel_size=ks, padding=pw)
+        self.mlp_beta = nn.Conv2d(nhidden, x_nc, kernel_size=ks, padding=pw)
+
+
+class SFTResblk(nn.Module):
+    def __init__(self, x_nc, prior_nc, ks=3):
+        super().__init__()
+        self.conv_0 = nn.Conv2d(x_nc, x_nc, kernel_size=3, padding=1)
+        self.conv_1 = nn.Conv2d(x_nc, x_nc, kernel_size=3, padding=1)
+        self.norm_0 = SFT(x_nc, prior_nc, ks=ks)
+        self.norm_1 = SFT(x_nc, prior_nc, ks=ks)
+
+
+def _qfeat(cin, mid, cout, first_k=3, stride2=True, transposed=False):
+    """qmap_feature_{ga,ha,gs}{2,3,4}: (de)conv k3 s2, LeakyReLU(0.1), conv 1x1"""
+    first = deconv(cin, mid, 3) if transposed else conv(cin, mid, 3)
+    return nn.Sequential(first, nn.LeakyReLU(0.1, True), conv(mid, cout, 1, 1))
+
+
+class stem_roi(CompressionModel):  # noqa: N801 (reference class name)
+    """stem_roi.py:353-700: same constructor, state_dict keys and forward signature."""
+
+    def __init__(self, entropy_bottleneck_channels=256, in_channels=192):
+        super().__init__(entropy_bottleneck_channels=entropy_bottleneck_channels)
+        C = in_channels
+        lre = lambda: nn.LeakyReLU(0.1, True)  # noqa: E731
+        self.ga1 = nn.Sequential(conv(3, 128), GDN(128))
+        self.ga1_SFT = SFT(128, 128)
+        self.ga2 = nn.Sequential(conv(128, 128), GDN(128))
+        self.ga2_SFT = SFT(128, 128)
+        self.ga3 = nn.Sequential(conv(128, 128), GDN(128))
+        self.ga3_SFT = SFT(128, 128)
+        self.ga4 = conv(128, C)
+        self.ga4_SFTResB1 = SFTResblk(C, C)
+        self.ga4_SFTResB2 = SFTResblk(C, C)
+        self.qmap_feature_ga1 = nn.Sequential(conv(4, 192, 3, 1), lre(), conv(192, 160, 3, 1), lre(), conv(160, 128, 3, 1))
+        self.qmap_feature_ga2 = _qfeat(128, 128, 128)
+        self.qmap_feature_ga3 = _qfeat(128, 128, 128)
+        self.qmap_feature_ga4 = _qfeat(128, 128, C)
+        self.ha1 = conv(C * 2, 256, 3, 1)
+        self.ha1_SFT = SFT(256, 256)
+        self.ha1_act = nn.LeakyReLU()
+        self.ha2 = conv(256, 256, 5, 2)
+        self.ha2_SFT = SFT(256, 256)
+        self.ha2_act = nn.LeakyReLU()
+        self.ha3 = conv(256, 256, 5, 2)
+        self.ha3_ResB1 = SFTResblk(256, 256)
+        self.ha3_ResB2 = SFTResblk(256, 256)
+        self.qmap_feature_ha1 = nn.Sequential(conv(C * 2 + 1, 128, 3, 1), lre(), conv(128, 192, 3, 1), lre(),
+                                              conv(192, 256, 3, 1))
+        self.qmap_feature_ha2 = _qfeat(256, 256, 256)
+        self.qmap_feature_ha3 = _qfeat(256, 256, 256)
+        self.hs = nn.Sequential(
+            nn.ConvTranspose2d(256, 256, 5, padding=2, stride=2, output_padding=1), nn.LeakyReLU(),
+            nn.ConvTranspose2d(256, 256, 5, padding=2, stride=2, output_padding=1), nn.LeakyReLU(),
+            nn.Conv2d(256, C * 2, 3, padding=1, stride=1))
+        self.wmap_generator = nn.Sequential(
+            nn.ConvTranspose2d(256, 192, 5, padding=2, stride=2, output_padding=1), nn.LeakyReLU(),
+            nn.ConvTranspose2d(192, 128, 5, padding=2, stride=2, output_padding=1), nn.LeakyReLU(),
+            nn.Conv2d(128, 64, 3, padding=1, stride=1))
+        self.gs0_SFTResB1 = SFTResblk(C, C)
+        self.gs0_SFTResB2 = SFTResblk(C, C)
+        self.gs1 = nn.Sequential(deconv(C, 128), GDN(128, inverse=True))
+        self.gs1_SFT = SFT(128, 128)
+        self.gs2 = nn.Sequential(deconv(128, 128), GDN(128, inverse=True))
+        self.gs2_SFT = SFT(128, 128)
+        self.gs3 = nn.Sequential(deconv(128, 128), GDN(128, inverse=True))
+        self.gs3_SFT = SFT(128, 128)
+        self.gs4 = deconv(128, 3)
+        self.qmap_feature_gs0 = nn.Sequential(conv(64 + C, 192, 3, 1), lre(), conv(192, 192, 3, 1), lre(),
+                                              conv(192, 192, 3, 1))
+        self.qmap_feature_gs1 = _qfeat(192, 128, 128, transposed=True)
+        self.qmap_feature_gs2 = _qfeat(128, 128, 128, transposed=True)
+        self.qmap_feature_gs3 = _qfeat(128, 128, 128, transposed=True)
+        self.ConditionEncoder = nn.Sequential(conv(3, 128), GDN(128), conv(128, 128), GDN(128), conv(128, 128),
+                                              GDN(128), conv(128, C))
+        self.TPM = nn.Sequential(nn.Conv2d(C, 256, 5, padding=2), nn.LeakyReLU(), nn.Conv2d(256, 320, 5, padding=2),
+                                 nn.LeakyReLU(), nn.Conv2d(320, C * 2, 5, padding=2))
+        self.EPM = nn.Sequential(nn.Conv2d(C * 4, 768, 1), nn.LeakyReLU(), nn.Conv2d(768, 576, 1), nn.LeakyReLU(),
+                                 nn.Conv2d(576, C * 2, 1))
+        self.gaussian_conditional = GaussianConditional(None)
+        self.in_channels = C
+
+    def engine(self) -> "RoiEngine":
+        dev = self._device()
+        if dev.type != "cuda":
+            raise RuntimeError("stem_roi of spatiotemporalentropymodel_b200 runs on CUDA only (no CPU fallback)")
+        if self._engine is None:
+            gc = self.gaussian_conditional
+            self._engine = RoiEngine(dict(self.state_dict()), dev, self.entropy_bottleneck.packed_params(),
+                                     scale_bound=float(gc.lower_bound_scale.bound.item()),
+                                     lik_bound=float(gc.likelihood_lower_bound.bound.item()))
+        return self._engine
+
+    def forward(self, x_cur: Tensor, x_conditioned: Tensor, Qmap: Tensor):  # noqa: N803
+        """-> {"x_hat", "y_hat", "likelihoods": {"y", "z"}}  (stem_roi.py:585-608), eval mode."""
+        if self.training:
+            raise NotImplementedError("training-mode forward is outside the inference hot path; call .eval()")
+        return self.engine().forward(x_cur, x_conditioned, Qmap)
+
+    def compress(self, x_cur, x_conditioned, Qmap):  # noqa: N803
+        raise NotImplementedError("compress(): entropy coding is a 'next' row (SURVEY.md §8f)")
+
+    def decompress(self, strings, shape, x_conditioned):
+        raise NotImplementedError("decompress(): entropy coding is a 'next' row (SURVEY.md §8f)")
+
+    def load_state_dict(self, state_dict, strict: bool = True):
+        _resize_registered_buffers(self.gaussian_conditional, "gaussian_conditional",
+                                   ["_quantized_cdf", "_offset", "_cdf_length", "scale_table"], state_dict)
+        return super().load_state_dict(state_dict, strict=strict)
+
+    def update(self, scale_table=None, force: bool = False) -> bool:
+        if scale_table is None:
+            scale_table = get_scale_table()
+        updated = self.gaussian_conditional.update_scale_table(scale_table, force=force)
+        updated |= super().update(force=force)
+        return updated
+
+
+# ------------------------------------------------------------------------------------------------------
+# engine
+# ------------------------------------------------------------------------------------------------------
+class _SftLayer:
+    """SFT.forward (stem_utils.py:36-43): mlp_shared (3x3 + ReLU) then the fused gamma|beta conv."""
+
+    def __init__(self, g, name: str, x_nc: int, prior_nc: int, slope: float = 1.0):
+        self.shared = ConvOp(g(f"{name}.mlp_shared.0.weight"), g(f"{name}.mlp_shared.0.bias"), c_in=[prior_nc], c_out=128,
+                             k=3, slope=0.0)  # nn.ReLU
+        self.mod = sft_op(g(f"{name}.mlp_gamma.weight"), g(f"{name}.mlp_gamma.bias"), g(f"{name}.mlp_beta.weight"),
+                          g(f"{name}.mlp_beta.bias"), c_in=128, slope=slope)
+        self.x_nc = x_nc
+
+    def __call__(self, ws: Workspace, tag: str, x: Tensor, q: Tensor, B: int, h: int, w: int) -> Tensor:
+        actv = self.shared([q], B, h, w, ws.get(f"{tag}_actv", (B, h, w, 128), torch.float16))
+        return self.mod([actv], B, h, w, ws.get(f"{tag}_out", (B, h, w, self.x_nc), torch.float16), aux=x)
+
+
+class _SftResblk:
+    """SFTResblk.forward (stem_utils.py:55-63): x + conv_1(lrelu(SFT_1(conv_0(lrelu(SFT_0(x)))))), slope 0.2."""
+
+    def __init__(self, g, name: str, x_nc: int, prior_nc: int):
+        self.n0 = _SftLayer(g, f"{name}.norm_0", x_nc, prior_nc, slope=0.2)
+        self.n1 = _SftLayer(g, f"{name}.norm_1", x_nc, prior_nc, slope=0.2)
+        self.c0 = ConvOp(g(f"{name}.conv_0.weight"), g(f"{name}.conv_0.bias"), c_in=[x_nc], c_out=x_nc, k=3)
+        self.c1 = ConvOp(g(f"{name}.conv_1.weight"), g(f"{name}.conv_1.bias"), c_in=[x_nc], c_out=x_nc, k=3,
+                         epilogue=EPI_ADD)
+        self.x_nc = x_nc
+
+    def __call__(self, ws: Workspace, tag: str, x: Tensor, q: Tensor, B: int, h: int, w: int) -> Tensor:
+        f16 = torch.float16
+        t = self.n0(ws, f"{tag}_n0", x, q, B, h, w)
+        t = self.c0([t], B, h, w, ws.get(f"{tag}_c0", (B, h, w, self.x_nc), f16))
+        t = self.n1(ws, f"{tag}_n1", t, q, B, h, w)
+        return self.c1([t], B, h, w, ws.get(f"{tag}_c1", (B, h, w, self.x_nc), f16), aux=x)
+
+
+class RoiEngine:
+    def __init__(self, sd: Dict[str, Tensor], device: torch.device, eb_packed: Tensor, scale_bound: float = 0.11,
+                 lik_bound: float = 1e-9):
+        dev = device
+        g = lambda k: sd[k].detach().to(dev, torch.float32)  # noqa: E731
+        self.device, self.ws = dev, Workspace(dev)
+        self.scale_bound, self.lik_bound = float(scale_bound), float(lik_bound)
+        self.C = C = sd["ga4.weight"].shape[0]
+        if C % 64:
+            raise ValueError("in_channels must be a multiple of 64")
+        l1, l01 = 0.1, 0.01
+
+        def gdn_of(name, inverse):
+            beta, gamma = _gdn_fold(g(f"{name}.beta"), g(f"{name}.gamma"))
+            return (beta, gamma, inverse)
+
+        def first_layer(prefix, gdn_name):
+            w0 = g(f"{prefix}.weight")  # (128, 3, 5, 5) -> im2col GEMM operand
+            n = w0.shape[0]
+            w0 = F.pad(w0.permute(0, 2, 3, 1).reshape(n, 75), (0, 5)).reshape(n, 80, 1, 1).contiguous()
+            return ConvOp(w0, g(f"{prefix}.bias"), c_in=[80], c_out=n, k=1, gdn=gdn_of(gdn_name, False),
+                          alg_flops_per_out_pixel=2.0 * 75 * n + 2.0 * n * n)
+
+        def plain(name, cin, cout, k, stride=1, slope=1.0, transposed=False, out_dtype=DT_F16):
+            return ConvOp(g(f"{name}.weight"), g(f"{name}.bias"), c_in=cin if isinstance(cin, list) else [cin],
+                          c_out=cout, k=k, stride=stride, slope=slope, transposed=transposed, out_dtype=out_dtype)
+
+        # ---- PEncoder
+        self.ga1 = first_layer("ga1.0", "ga1.1")
+        self.ga2 = ConvOp(g("ga2.0.weight"), g("ga2.0.bias"), c_in=[128], c_out=128, k=5, stride=2, gdn=gdn_of("ga2.1", False))
+        self.ga3 = ConvOp(g("ga3.0.weight"), g("ga3.0.bias"), c_in=[128], c_out=128, k=5, stride=2, gdn=gdn_of("ga3.1", False))
+        self.ga4 = plain("ga4", 128, C, 5, stride=2)
+        self.ga_sft = [_SftLayer(g, f"ga{i}_SFT", 128, 128) for i in (1, 2, 3)]
+        self.ga4_rb = [_SftResblk(g, f"ga4_SFTResB{i}", C, C) for i in (1, 2)]
+        wq = g("qmap_feature_ga1.0.weight")  # (192, 4, 3, 3) -> rows of 40: k = (r*3+s)*4 + ch
+        wq = F.pad(wq.permute(0, 2, 3, 1).reshape(192, 36), (0, 4)).reshape(192, 40, 1, 1).contiguous()
+        self.qga1 = [ConvOp(wq, g("qmap_feature_ga1.0.bias"), c_in=[40], c_out=192, k=1, slope=l1,
+                            alg_flops_per_out_pixel=2.0 * 36 * 192),
+                     plain("qmap_feature_ga1.2", 192, 160, 3, slope=l1), plain("qmap_feature_ga1.4", 160, 128, 3)]
+        self.qga = [[plain(f"qmap_feature_ga{i}.0", 128, 128, 3, stride=2, slope=l1),
+                     plain(f"qmap_feature_ga{i}.2", 128, 128 if i < 4 else C, 1)] for i in (2, 3, 4)]
+        # ---- ConditionEncoder
+        self.ce = [first_layer("ConditionEncoder.0", "ConditionEncoder.1"),
+                   ConvOp(g("ConditionEncoder.2.weight"), g("ConditionEncoder.2.bias"), c_in=[128], c_out=128, k=5,
+                          stride=2, gdn=gdn_of("ConditionEncoder.3", False)),
+                   ConvOp(g("ConditionEncoder.4.weight"), g("ConditionEncoder.4.bias"), c_in=[128], c_out=128, k=5,
+                          stride=2, gdn=gdn_of("ConditionEncoder.5", False)),
+                   plain("ConditionEncoder.6", 128, C, 5, stride=2)]
+        # ---- HE
+        wq = g("qmap_feature_ha1.0.weight")  # (128, 2C+1, 3, 3): Qmap channel padded to an 8-channel K segment
+        wq = torch.cat([wq[:, :1], torch.zeros((128, 7, 3, 3), device=dev), wq[:, 1:]], 1).contiguous()
+        self.qha1 = [ConvOp(wq, g("qmap_feature_ha1.0.bias"), c_in=[8, C, C], c_out=128, k=3, slope=l1,
+                            alg_flops_per_out_pixel=2.0 * (2 * C + 1) * 128 * 9),
+                     plain("qmap_feature_ha1.2", 128, 192, 3, slope=l1), plain("qmap_feature_ha1.4", 192, 256, 3)]
+        self.qha = [[plain(f"qmap_feature_ha{i}.0", 256, 256, 3, stride=2, slope=l1),
+                     plain(f"qmap_feature_ha{i}.2", 256, 256, 1)] for i in (2, 3)]
+        self.ha1 = plain("ha1", [C, C], 256, 3)
+        self.ha2 = plain("ha2", 256, 256, 5, stride=2)
+        self.ha3 = plain("ha3", 256, 256, 5, stride=2)
+        self.ha_sft = [_SftLayer(g, "ha1_SFT", 256, 256, slope=l01), _SftLayer(g, "ha2_SFT", 256, 256, slope=l01)]
+        self.ha3_rb = [_SftResblk(g, f"ha3_ResB{i}", 256, 256) for i in (1, 2)]
+        # ---- HD / TPM / EPM
+        self.hs = [plain("hs.0", 256, 256, 5, stride=2, slope=l01, transposed=True),
+                   plain("hs.2", 256, 256, 5, stride=2, slope=l01, transposed=True), plain("hs.4", 256, 2 * C, 3)]
+        self.tpm = [plain("TPM.0", C, 256, 5, slope=l01), plain("TPM.2", 256, 320, 5, slope=l01),
+                    plain("TPM.4", 320, 2 * C, 5)]
+        self.epm = [plain("EPM.0", [2 * C, 2 * C], 768, 1, slope=l01), plain("EPM.2", 768, 576, 1, slope=l01),
+                    plain("EPM.4", 576, 2 * C, 1, out_dtype=DT_F32)]
+        # ---- PDecoder
+        self.wgen = [plain("wmap_generator.0", 256, 192, 5, stride=2, slope=l01, transposed=True),
+                     plain("wmap_generator.2", 192, 128, 5, stride=2, slope=l01, transposed=True),
+                     plain("wmap_generator.4", 128, 64, 3)]
+        self.qgs0 = [plain("qmap_feature_gs0.0", [64, C], 192, 3, slope=l1), plain("qmap_feature_gs0.2", 192, 192, 3, slope=l1),
+                     plain("qmap_feature_gs0.4", 192, 192, 3)]
+        self.gs0_rb = [_SftResblk(g, f"gs0_SFTResB{i}", C, C) for i in (1, 2)]
+        self.qgs = [[plain(f"qmap_feature_gs{i}.0", 192 if i == 1 else 128, 128, 3, stride=2, slope=l1, transposed=True),
+                     plain(f"qmap_feature_gs{i}.2", 128, 128, 1)] for i in (1, 2, 3)]
+        self.gs = [ConvOp(g(f"gs{i}.0.weight"), g(f"gs{i}.0.bias"), c_in=[C if i == 1 else 128], c_out=128, k=5, stride=2,
+                          transposed=True, gdn=gdn_of(f"gs{i}.1", True)) for i in (1, 2, 3)]
+        self.gs_sft = [_SftLayer(g, f"gs{i}_SFT", 128, 128) for i in (1, 2, 3)]
+        # last deconv (128 -> 3) as the stride-2 super-pixel conv (see engine.TransformsEngine)
+        wt = g("gs4.weight")
+        wm = torch.zeros((64, 128, 5, 5), device=dev)
+        bm = torch.zeros(64, device=dev)
+        mask = 0
+        for R in range(1, 5):
+            for S in range(1, 5):
+                mask |= 1 << (R * 5 + S)
+                for u in range(4):
+                    r = u + 6 - 2 * R
+                    if r < 0 or r > 4:
+                        continue
+                    for v in range(4):
+                        s_ = v + 6 - 2 * S
+                        if s_ < 0 or s_ > 4:
+                            continue
+                        o = (u * 4 + v) * 3
+                        wm[o:o + 3, :, R, S] = wt[:, :, r, s_].t()
+        for uv in range(16):
+            bm[uv * 3:uv * 3 + 3] = g("gs4.bias")
+        self.gs4 = ConvOp(wm, bm, c_in=[128], c_out=64, k=5, stride=2, tap_mask=mask, out_dtype=DT_F32,
+                          alg_flops_per_out_pixel=4 * 2.0 * 128 * 3 * 25)
+        self.eb_params = eb_packed.detach().to(dev, torch.float32).contiguous()
+        self.all_ops: List[ConvOp] = []
+
+    # -------------------------------------------------------------------------------------------------
+    def _buf(self, name, shape, dtype=torch.float16):
+        return self.ws.get(name, shape, dtype)
+
+    def _analysis4(self, ops, tag, x: Tensor) -> Tuple[Tensor, int, int]:
+        """ConditionEncoder: four stride-2 layers on an image (B, 3, H, W) fp32 NCHW."""
+        B, _, H, W = x.shape
+        lib = _lib.load()
+        h, w = H // 2, W // 2
+        rows = self._buf(f"{tag}_rows", (B, h, w, 80))
+        _lib.check(lib.stemb200_im2col_k5s2_c3(x.data_ptr(), rows.data_ptr(), B, H, W, H, W, 0, 0, _stream()), "im2col")
+        cur = ops[0]([rows], B, h, w, self._buf(f"{tag}_0", (B, h, w, ops[0].c_out)))
+        for i in (1, 2, 3):
+            ho, wo = ops[i].out_hw(h, w)
+            cur = ops[i]([cur], B, h, w, self._buf(f"{tag}_{i}", (B, ho, wo, ops[i].c_out)))
+            h, w = ho, wo
+        return cur, h, w
+
+    def forward(self, x_cur: Tensor, x_cond: Tensor, qmap: Tensor):
+        _require_cuda(x_cur, x_cond, qmap)
+        x_cur, x_cond, qmap = x_cur.contiguous().float(), x_cond.contiguous().float(), qmap.contiguous().float()
+        B, _, H, W = x_cur.shape
+        if H % 64 or W % 64:
+            raise ValueError("stem_roi needs frame sizes that are multiples of 64 (the scripts pad to 64)")
+        lib, C, dev = _lib.load(), self.C, self.device
+        f16, f32 = torch.float16, torch.float32
+        bf = self._buf
+        # ================= PEncoder =================
+        rows_q = bf("q_rows", (B, H, W, 40))
+        _lib.check(lib.stemb200_im2col_k3s1_c4(x_cur.data_ptr(), qmap.data_ptr(), rows_q.data_ptr(), B, H, W, _stream()),
+                   "im2col_k3s1_c4")
+        q = self.qga1[0]([rows_q], B, H, W, bf("q1a", (B, H, W, 192)))
+        q = self.qga1[1]([q], B, H, W, bf("q1b", (B, H, W, 160)))
+        q = self.qga1[2]([q], B, H, W, bf("q1", (B, H, W, 128)))
+        h, w = H // 2, W // 2
+        rows = bf("ga_rows", (B, h, w, 80))
+        _lib.check(lib.stemb200_im2col_k5s2_c3(x_cur.data_ptr(), rows.data_ptr(), B, H, W, H, W, 0, 0, _stream()), "im2col")
+        x = self.ga1([rows], B, h, w, bf("ga1", (B, h, w, 128)))
+        qh, qw = H, W  # resolution of q
+        for lvl in range(3):
+            qp = avgpool_nhwc(q, bf(f"qpool{lvl}", (B, h, w, 128)), 2)
+            x = self.ga_sft[lvl](self.ws, f"ga{lvl + 1}sft", x, qp, B, h, w)
+            # next pyramid level of the quality features (stride-2 conv + 1x1) and of x
+            q = self.qga[lvl][0]([q], B, qh, qw, bf(f"q{lvl + 2}a", (B, qh // 2, qw // 2, 128)))
+            qh, qw = qh // 2, qw // 2
+            q = self.qga[lvl][1]([q], B, qh, qw, bf(f"q{lvl + 2}", (B, qh, qw, self.qga[lvl][1].c_out)))
+            nxt = (self.ga2, self.ga3, self.ga4)[lvl]
+            x = nxt([x], B, h, w, bf(f"ga{lvl + 2}", (B, h // 2, w // 2, nxt.c_out)))
+            h, w = h // 2, w // 2
+        qp = avgpool_nhwc(q, bf("qpool3", (B, h, w, C)), 2)
+        x = self.ga4_rb[0](self.ws, "ga4rb1", x, qp, B, h, w)
+        y16 = self.ga4_rb[1](self.ws, "ga4rb2", x, qp, B, h, w)  # y_cur (B, h, w, C) fp16
+        # ================= ConditionEncoder =================
+        yc16, hc, wc = self._analysis4(self.ce, "ce", x_cond)
+        assert (hc, wc) == (h, w)
+        # ================= HE =================
+        q8 = bf("q8", (B, h, w, 8))
+        _lib.check(lib.stemb200_qmap_pool(qmap.data_ptr(), q8.data_ptr(), B, h, w, H // h, _stream()), "qmap_pool")
+        qf = self.qha1[0]([q8, y16, yc16], B, h, w, bf("qh1a", (B, h, w, 128)))
+        qf = self.qha1[1]([qf], B, h, w, bf("qh1b", (B, h, w, 192)))
+        qf = self.qha1[2]([qf], B, h, w, bf("qh1", (B, h, w, 256)))
+        t = self.ha1([y16, yc16], B, h, w, bf("ha1", (B, h, w, 256)))
+        t = self.ha_sft[0](self.ws, "ha1sft", t, qf, B, h, w)
+        qf = self.qha[0][0]([qf], B, h, w, bf("qh2a", (B, h // 2, w // 2, 256)))
+        qf = self.qha[0][1]([qf], B, h // 2, w // 2, bf("qh2", (B, h // 2, w // 2, 256)))
+        t = self.ha2([t], B, h, w, bf("ha2", (B, h // 2, w // 2, 256)))
+        t = self.ha_sft[1](self.ws, "ha2sft", t, qf, B, h // 2, w // 2)
+        qf = self.qha[1][0]([qf], B, h // 2, w // 2, bf("qh3a", (B, h // 4, w // 4, 256)))
+        qf = self.qha[1][1]([qf], B, h // 4, w // 4, bf("qh3", (B, h // 4, w // 4, 256)))
+        t = self.ha3([t], B, h // 2, w // 2, bf("ha3", (B, h // 4, w // 4, 256)))
+        h4, w4 = h // 4, w // 4
+        t = self.ha3_rb[0](self.ws, "ha3rb1", t, qf, B, h4, w4)
+        z16 = self.ha3_rb[1](self.ws, "ha3rb2", t, qf, B, h4, w4)
+        z32 = bf("z32", (B, h4, w4, 256), f32)
+        _lib.check(lib.stemb200_cast_f16_to_f32(z16.data_ptr(), z32.data_ptr(), z16.numel(), _stream()), "cast")
+        # ================= entropy models =================
+        z_hat = torch.empty((B, 256, h4, w4), dtype=f32, device=dev)
+        z_lik = torch.empty((B, 256, h4, w4), dtype=f32, device=dev)
+        bits = torch.zeros((2, B), dtype=torch.float64, device=dev)
+        zhat16 = bf("zhat16", (B, h4, w4, 256))
+        _lib.check(lib.stemb200_entropy_bottleneck_fwd(z32.data_ptr(), self.eb_params.data_ptr(), B, 256, h4, w4,
+                                                       self.lik_bound, zhat16.data_ptr(), z_hat.data_ptr(),
+                                                       z_lik.data_ptr(), bits[1].data_ptr(), _stream()),
+                   "entropy_bottleneck_fwd")
+        d = self.hs[0]([zhat16], B, h4, w4, bf("hs0", (B, h // 2, w // 2, 256)))
+        d = self.hs[1]([d], B, h // 2, w // 2, bf("hs1", (B, h, w, 256)))
+        hp = self.hs[2]([d], B, h, w, bf("hp", (B, h, w, 2 * C)))
+        p = self.tpm[0]([yc16], B, h, w, bf("tp0", (B, h, w, 256)))
+        p = self.tpm[1]([p], B, h, w, bf("tp1", (B, h, w, 320)))
+        tp = self.tpm[2]([p], B, h, w, bf("tp", (B, h, w, 2 * C)))
+        e = self.epm[0]([tp, hp], B, h, w, bf("e0", (B, h, w, 768)))
+        e = self.epm[1]([e], B, h, w, bf("e1", (B, h, w, 576)))
+        params = self.epm[2]([e], B, h, w, bf("gparams", (B, h, w, 2 * C), f32))
+        y32 = bf("y32", (B, h, w, C), f32)
+        _lib.check(lib.stemb200_cast_f16_to_f32(y16.data_ptr(), y32.data_ptr(), y16.numel(), _stream()), "cast")
+        y_hat = torch.empty((B, C, h, w), dtype=f32, device=dev)
+        y_lik = torch.empty((B, C, h, w), dtype=f32, device=dev)
+        _lib.check(lib.stemb200_gaussian_conditional_fwd(y32.data_ptr(), 0, None, params.data_ptr(), B, C, h, w, None, 0,
+                                                         self.scale_bound, self.lik_bound, 0, y_hat.data_ptr(),
+                                                         y_lik.data_ptr(), None, None, bits[0].data_ptr(), _stream()),
+                   "gaussian_conditional_fwd")
+        yhat16 = nchw_to_nhwc_f16(y_hat, bf("yhat16", (B, h, w, C)))
+        # ================= PDecoder =================
+        wm = self.wgen[0]([zhat16], B, h4, w4, bf("wg0", (B, h // 2, w // 2, 192)))
+        wm = self.wgen[1]([wm], B, h // 2, w // 2, bf("wg1", (B, h, w, 128)))
+        wm = self.wgen[2]([wm], B, h, w, bf("wg2", (B, h, w, 64)))
+        wm = self.qgs0[0]([wm, yhat16], B, h, w, bf("qg0a", (B, h, w, 192)))
+        wm = self.qgs0[1]([wm], B, h, w, bf("qg0b", (B, h, w, 192)))
+        wm = self.qgs0[2]([wm], B, h, w, bf("qg0", (B, h, w, 192)))
+        x = self.gs0_rb[0](self.ws, "gs0rb1", yhat16, wm, B, h, w)
+        x = self.gs0_rb[1](self.ws, "gs0rb2", x, wm, B, h, w)
+        for lvl in range(3):
+            wm = self.qgs[lvl][0]([wm], B, h, w, bf(f"qg{lvl + 1}a", (B, 2 * h, 2 * w, 128)))
+            wm = self.qgs[lvl][1]([wm], B, 2 * h, 2 * w, bf(f"qg{lvl + 1}", (B, 2 * h, 2 * w, 128)))
+            x = self.gs[lvl]([x], B, h, w, bf(f"gs{lvl + 1}", (B, 2 * h, 2 * w, 128)))
+            h, w = 2 * h, 2 * w
+            x = self.gs_sft[lvl](self.ws, f"gs{lvl + 1}sft", x, wm, B, h, w)
+        merged = bf("gs_merged", (B, h // 2, w // 2, 64), f32)
+        self.gs4([x], B, h, w, merged)
+        x_hat = torch.empty((B, 3, 2 * h, 2 * w), dtype=f32, device=dev)
+        _lib.check(lib.stemb200_synthesis_tail(merged.data_ptr(), x_hat.data_ptr(), B, h // 2, w // 2, None, 0, 0, 0, 0,
+                                               None, 0, _stream()), "synthesis_tail")
+        return {"x_hat": x_hat, "y_hat": y_hat, "likelihoods": {"y": y_lik, "z": z_lik}, "bits": bits}
+
+
+# ------------------------------------------------------------------------------------------------------
+# seeded synthetic checkpoint (same purpose as synthetic.make_stem_state_dict)
+# ------------------------------------------------------------------------------------------------------
+def make_synthetic_state_dict(seed: int = 0, in_channels: int = 192) -> Dict[str, Tensor]:
+    """Calibrated random state_dict with exactly stem_roi's key set (verified by loading it, strict, into the
+    reference class in tests/golden/make_golden.py). Values come from a seeded CPU generator, keyed by parameter
+    name, so they do not depend on module construction order."""
+    import math
+    import zlib
+
+    from . import synthetic as S
+
+    model = stem_roi(in_channels=in_channels)
+    kinds = {}
+    for name, mod in model.named_modules():
+        if isinstance(mod, nn.ConvTranspose2d):
+            kinds[name] = "deconv"
+        elif isinstance(mod, nn.Conv2d):
+            kinds[name] = "conv"
+        elif isinstance(mod, GDN):
+            kinds[name] = "gdn"
+    sd: Dict[str, Tensor] = {}
+    for key, ref in model.state_dict().items():
+        mod_name, _, leaf = key.rpartition(".")
+        g = torch.Generator().manual_seed((zlib.crc32(key.encode()) + 7919 * seed) & 0x7FFFFFFF)
+        kind = kinds.get(mod_name)
+        if key.startswith("entropy_bottleneck.") or key.startswith("gaussian_conditional."):
+            continue
+        if kind in ("conv", "deconv"):
+            if leaf == "weight":
+                k = ref.shape[-1]
+                cin = ref.shape[0] if kind == "deconv" else ref.shape[1]
+                fan_in = cin * k * k / (4.0 if kind == "deconv" else 1.0)
+                gain = 1.0
+                top = key.split(".")[0]
+                if ".mlp_gamma" in key or ".mlp_beta" in key:
+                    gain = 0.3
+                elif mod_name in ("ga1.0", "ConditionEncoder.0"):
+                    gain = 3.0
+                elif mod_name in ("ga2.0", "ga3.0", "ConditionEncoder.2", "ConditionEncoder.4"):
+                    gain = 2.0
+                elif mod_name == "ConditionEncoder.6":
+                    gain = 5.0
+                elif mod_name == "ga4":
+                    gain = 3.5
+                elif mod_name.endswith(".conv_1") or mod_name.endswith(".conv_0"):
+                    gain = 0.5
+                elif top in ("ha1", "ha2", "ha3"):
+                    gain = 1.3
+                elif top in ("gs1", "gs2", "gs3"):
+                    gain = 0.45
+                elif top == "wmap_generator":
+                    gain = 0.7
+                elif top.startswith("qmap_feature_gs") or top.startswith("qmap_feature_ha"):
+                    gain = 1.0
+                elif mod_name == "gs4":
+                    gain = 0.25
+                elif mod_name == "EPM.4":
+                    gain = 0.7
+                elif top in ("TPM", "hs", "EPM"):
+                    gain = 1.4
+                sd[key] = S._u(g, tuple(ref.shape), gain * math.sqrt(3.0 / fan_in))
+            else:
+                sd[key] = S._u(g, tuple(ref.shape), 0.1)
+        elif kind == "gdn":
+            c = ref.shape[0]
+            ped = torch.tensor([S._PEDESTAL], dtype=torch.float32)
+            if leaf == "beta":
+                sd[key] = torch.sqrt(torch.max(1.0 + 0.5 * torch.rand(c, generator=g) + ped, ped))
+            else:
+                sd[key] = torch.sqrt(torch.max(0.1 * torch.eye(c) + 0.02 * torch.rand((c, c), generator=g) + ped, ped))
+        else:
+            sd[key] = ref.detach().clone()  # reparametrizer buffers (pedestal, bounds)
+    C = in_channels
+    b = sd["EPM.4.bias"]
+    b[:C] = torch.exp(torch.linspace(math.log(0.05), math.log(64.0), C))
+    sd["EPM.4.weight"][:C] *= 0.3
+    sd["gs4.bias"] = torch.tensor([0.45, 0.5, 0.55])
+    geb = torch.Generator().manual_seed(3000 + seed)
+    S._entropy_bottleneck(sd, geb, "entropy_bottleneck", 256)
+    S._gaussian_conditional(sd)
+    return sd
+
+
+def make_qmap(n: int, height: int, width: int, kind: str = "ramp", level: float = 0.5) -> Tensor:
+    """Quality maps of stem_roi/eval_stem_roi.py:81-93: uniform levels or a horizontal ramp, (n, 1, H, W) in [0, 1]."""
+    if kind == "uniform":
+        return torch.full((n, 1, height, width), float(level))
+    ramp = torch.linspace(0, 1, width).view(1, 1, 1, width).expand(n, 1, height, width)
+    return ramp.contiguous()

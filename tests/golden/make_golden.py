@@ -88,6 +88,27 @@ def main():
             bits = float((-torch.log2(out["likelihoods"]["y"])).sum() + (-torch.log2(out["likelihoods"]["z"])).sum())
             print(f"{variant}: size {size}, bpp {bits / (size * size):.4f}")
 
+    # ---------------------------------------------------------------- stem_roi (a13)
+    from compressai.models.stem_roi import stem_roi as ref_stem_roi
+    from spatiotemporalentropymodel_b200 import stem_roi as R
+    sd_r = R.make_synthetic_state_dict(seed=0)
+    roi = ref_stem_roi()
+    roi.load_state_dict(sd_r)
+    roi.update(force=True)
+    roi.eval()
+    frames = S.make_frames(2, 128, 128, seed=11)
+    rec = {}
+    with torch.no_grad():
+        for name, qmap in (("ramp", R.make_qmap(1, 128, 128, "ramp")), ("uniform", R.make_qmap(1, 128, 128, "uniform", 0.25))):
+            out = roi(frames[1:2], frames[0:1], qmap)
+            rec[f"{name}_x_hat"] = out["x_hat"].numpy()
+            rec[f"{name}_y_hat"] = out["y_hat"].numpy()
+            rec[f"{name}_lik_y"] = out["likelihoods"]["y"].numpy()
+            rec[f"{name}_lik_z"] = out["likelihoods"]["z"].numpy()
+            bits = float((-torch.log2(out["likelihoods"]["y"])).sum() + (-torch.log2(out["likelihoods"]["z"])).sum())
+            print(f"stem_roi[{name}]: bpp {bits / (128 * 128):.4f}")
+    np.savez_compressed(os.path.join(OUT, "stem_roi.npz"), **rec)
+
     # ---------------------------------------------------------------- isolated GaussianConditional (a9)
     table = ref_stem.get_scale_table()
     gc = GaussianConditional(None)

@@ -72,7 +72,7 @@ def test_c_abi_rejects_bad_arguments_without_a_gpu():
     assert lib.stemb200_conv2d_packed_k(ctypes.byref(d)) == 25 * 128    # ragged: 80 channels occupy two K chunks
     assert lib.stemb200_gaussian_conditional_flat(None, None, None, 0, None, 0, 0.11, 1e-9, None, None, None, None,
                                                   None, None) == -1
-    assert lib.stemb200_synthesis_tail(None, None, 1, 1, 1, None, 0, 0, 0, 0, None, None) == -1
+    assert lib.stemb200_synthesis_tail(None, None, 1, 1, 1, None, 0, 0, 0, 0, None, 1, None) == -1
 
 
 @pytest.mark.parametrize("variant", S.STEM_VARIANTS)

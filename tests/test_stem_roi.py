@@ -1,0 +1,101 @@
+"""stem_roi: oracle pinned against the reference-generated golden (CPU), state_dict contract
+(CPU), and the CUDA path against both (-m gpu)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import stem_roi_oracle as RO
+from spatiotemporalentropymodel_b200 import synthetic as S
+
+
+def t(a):
+    return torch.from_numpy(np.asarray(a))
+
+
+def bits(l):
+    return float((-torch.log2(l.double())).sum())
+
+
+def _inputs():
+    from spatiotemporalentropymodel_b200 import stem_roi as R
+    frames = S.make_frames(2, 128, 128, seed=11)
+    return frames[1:2], frames[0:1], {"ramp": R.make_qmap(1, 128, 128, "ramp"),
+                                      "uniform": R.make_qmap(1, 128, 128, "uniform", 0.25)}
+
+
+def test_oracle_matches_reference_golden(golden):
+    from spatiotemporalentropymodel_b200 import stem_roi as R
+    g = golden("stem_roi.npz")
+    sd = R.make_synthetic_state_dict(seed=0)
+    x_cur, x_cond, qmaps = _inputs()
+    for name, qmap in qmaps.items():
+        out = RO.stem_roi_forward(x_cur, x_cond, qmap, sd)
+        assert torch.equal(out["y_hat"], t(g[f"{name}_y_hat"])) or \
+            float((out["y_hat"] - t(g[f"{name}_y_hat"])).abs().max()) < 1e-4
+        assert torch.allclose(out["likelihoods"]["y"], t(g[f"{name}_lik_y"]), rtol=1e-4, atol=1e-9)
+        assert torch.allclose(out["likelihoods"]["z"], t(g[f"{name}_lik_z"]), rtol=1e-4, atol=1e-9)
+        assert torch.allclose(out["x_hat"], t(g[f"{name}_x_hat"]), rtol=1e-4, atol=1e-4)
+
+
+def test_state_dict_contract_and_no_cpu_fallback():
+    from spatiotemporalentropymodel_b200 import stem_roi as R
+    sd = R.make_synthetic_state_dict(seed=0)
+    assert len(sd) == 329 and sum(v.numel() for v in sd.values()) == 45700302  # reference stem_roi().state_dict()
+    model = R.stem_roi()
+    model.load_state_dict(sd)
+    out = model.state_dict()
+    assert set(out) == set(sd)
+    for k, v in sd.items():
+        assert out[k].shape == v.shape and out[k].dtype == v.dtype, k
+    assert model.update(force=True) is True
+    with pytest.raises(RuntimeError, match="CUDA"):
+        model.eval()(torch.zeros(1, 3, 64, 64), torch.zeros(1, 3, 64, 64), torch.zeros(1, 1, 64, 64))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["ramp", "uniform"])
+def test_cuda_forward_vs_reference_golden(golden, name):
+    from spatiotemporalentropymodel_b200 import stem_roi as R
+    dev = torch.device("cuda:0")
+    g = golden("stem_roi.npz")
+    model = R.stem_roi()
+    model.load_state_dict(R.make_synthetic_state_dict(seed=0))
+    model.update(force=True)
+    model = model.to(dev).eval()
+    x_cur, x_cond, qmaps = _inputs()
+    out = model(x_cur.to(dev), x_cond.to(dev), qmaps[name].to(dev))
+    assert set(out) >= {"x_hat", "y_hat", "likelihoods"}
+    ref_ly, ref_lz, ref_x, ref_y = (t(g[f"{name}_{k}"]) for k in ("lik_y", "lik_z", "x_hat", "y_hat"))
+    assert out["x_hat"].shape == ref_x.shape and out["y_hat"].shape == ref_y.shape
+    got_bits = bits(out["likelihoods"]["y"].cpu()) + bits(out["likelihoods"]["z"].cpu())
+    ref_bits = bits(ref_ly) + bits(ref_lz)
+    assert abs(got_bits - ref_bits) / ref_bits < 5e-3, (got_bits, ref_bits)            # bpp within 0.5 %
+    x = x_cur
+    psnr = lambda a: float(-10 * torch.log10(((x - a.clamp(0, 1)) ** 2).mean()))  # noqa: E731
+    assert abs(psnr(out["x_hat"].cpu()) - psnr(ref_x)) < 0.01                           # PSNR within 0.01 dB
+    # symbols differ only where fp16 operand rounding moves y - mu across a rounding boundary
+    mism = float((torch.round(out["y_hat"].cpu() - ref_y).abs() > 0.5).float().mean())
+    assert mism < 0.03, mism
+    rms = float(torch.sqrt(((out["x_hat"].cpu() - ref_x) ** 2).mean() / (ref_x ** 2).mean()))
+    assert rms < 3e-2, rms
+
+
+@pytest.mark.gpu
+def test_cuda_forward_batch_and_rectangular():
+    """B = 2, non-square 64-multiple frame, against the oracle (covers every pooling / stride path)."""
+    from spatiotemporalentropymodel_b200 import stem_roi as R
+    dev = torch.device("cuda:0")
+    sd = R.make_synthetic_state_dict(seed=0)
+    model = R.stem_roi()
+    model.load_state_dict(sd)
+    model = model.to(dev).eval()
+    frames = S.make_frames(3, 128, 192, seed=5)
+    x_cur, x_cond = frames[1:3], frames[0:2]
+    qmap = torch.cat([R.make_qmap(1, 128, 192, "ramp"), R.make_qmap(1, 128, 192, "uniform", 1.0)])
+    out = model(x_cur.to(dev), x_cond.to(dev), qmap.to(dev))
+    ref = RO.stem_roi_forward(x_cur, x_cond, qmap, sd)
+    got_bits = bits(out["likelihoods"]["y"].cpu()) + bits(out["likelihoods"]["z"].cpu())
+    ref_bits = bits(ref["likelihoods"]["y"]) + bits(ref["likelihoods"]["z"])
+    assert abs(got_bits - ref_bits) / ref_bits < 5e-3
+    rms = float(torch.sqrt(((out["x_hat"].cpu() - ref["x_hat"]) ** 2).mean() / (ref["x_hat"] ** 2).mean()))
+    assert rms < 3e-2, rms
