@@ -185,6 +185,20 @@ int stemb200_synthesis_tail(const float* in_nhwc64, float* x_hat_nchw, int32_t n
 int stemb200_pmf_to_quantized_cdf_host(const float* pmf, int32_t pmf_len, int32_t precision,
                                        int32_t* cdf_out);
 
+/* ---------------------------------------------------------------------------------------------------
+ * rANS entropy coder (host). Replaces compressai.ans.RansEncoder.encode_with_indexes /
+ * RansDecoder.decode_with_indexes (compressai/cpp_exts/rans/rans_interface.cpp:193-275, rans64.h) with flat int32
+ * arrays instead of Python lists; the byte stream is identical (little-endian u32 words written backwards, 64-bit
+ * state flushed as two words, 16-bit precision, 4-bit bypass nibbles for out-of-range values).
+ *   symbols, indexes: [n]; cdfs: [n_cdfs][cdf_stride] (row i valid for cdf_sizes[i] entries); offsets: [n_cdfs].
+ * encode returns the number of bytes written to out (<= out_capacity) or a negative error code. */
+int64_t stemb200_rans_encode_host(const int32_t* symbols, const int32_t* indexes, int64_t n, const int32_t* cdfs,
+                                  int32_t n_cdfs, int32_t cdf_stride, const int32_t* cdf_sizes,
+                                  const int32_t* offsets, uint8_t* out, int64_t out_capacity);
+int stemb200_rans_decode_host(const uint8_t* stream, int64_t nbytes, const int32_t* indexes, int64_t n,
+                              const int32_t* cdfs, int32_t n_cdfs, int32_t cdf_stride, const int32_t* cdf_sizes,
+                              const int32_t* offsets, int32_t* symbols_out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -59,6 +59,8 @@ SIGNATURES = {
                                                   _vp]),
     "stemb200_synthesis_tail": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _vp, _i32, _i32, _i32, _i32, _vp, _i32, _vp]),
     "stemb200_cast_f16_to_f32": (C.c_int, [_vp, _vp, _i64, _vp]),
+    "stemb200_rans_encode_host": (_i64, [_vp, _vp, _i64, _vp, _i32, _i32, _vp, _vp, _vp, _i64]),
+    "stemb200_rans_decode_host": (C.c_int, [_vp, _i64, _vp, _i64, _vp, _i32, _i32, _vp, _vp, _vp]),
     "stemb200_pmf_to_quantized_cdf_host": (C.c_int, [C.POINTER(C.c_float), _i32, _i32, C.POINTER(C.c_int32)]),
 }
 

@@ -396,24 +396,23 @@ class StemEngine:
             scale_table.detach().to(dev, torch.float32).contiguous()
 
     # -------------------------------------------------------------------------------------------------
-    def gaussian_params(self, y16: Tensor, cond16: Tensor, yq16: Optional[Tensor], B: int, h: int, w: int,
-                        z_hat_nchw: Optional[Tensor] = None, z_lik_nchw: Optional[Tensor] = None,
-                        bits_z: Optional[Tensor] = None) -> Tensor:
-        """HE -> EntropyBottleneck -> HD, TPM, context, EPM. Returns params NHWC fp32 (B, h, w, 2C)."""
-        lib, ws = _lib.load(), self.ws
+    def hyper_latent(self, y16: Tensor, cond16: Tensor, B: int, h: int, w: int) -> Tensor:
+        """z = HE(cat[y_cur, y_cond]) as NHWC fp32 (B, h/4, w/4, zc)  (spatiotemporalpriors.py:562)."""
+        ws = self.ws
         f16, f32 = torch.float16, torch.float32
         if h % 4 or w % 4:
             raise ValueError("latent height/width must be multiples of 4 (two stride-2 stages in HE/HD)")
         h2, w2, h4, w4 = h // 2, w // 2, h // 4, w // 4
-        # hyper encoder on cat[y_cur, y_cond]
         t1 = self.he[0]([y16, cond16], B, h, w, ws.get("he1", (B, h, w, 256), f16))
         t2 = self.he[1]([t1], B, h, w, ws.get("he2", (B, h2, w2, 256), f16))
-        z = self.he[2]([t2], B, h2, w2, ws.get("z", (B, h4, w4, self.zc), f32))
-        zhat16 = ws.get("zhat16", (B, h4, w4, self.zc), f16)
-        _lib.check(lib.stemb200_entropy_bottleneck_fwd(z.data_ptr(), self.eb_params.data_ptr(), B, self.zc, h4, w4,
-                                                       self.lik_bound, zhat16.data_ptr(), _ptr(z_hat_nchw),
-                                                       _ptr(z_lik_nchw), _ptr(bits_z), _stream()),
-                   "entropy_bottleneck_fwd")
+        return self.he[2]([t2], B, h2, w2, ws.get("z", (B, h4, w4, self.zc), f32))
+
+    def params_from_zhat(self, zhat16: Tensor, cond16: Tensor, yq16: Optional[Tensor], B: int, h: int,
+                         w: int) -> Tensor:
+        """HD(z_hat), TPM(y_cond), context(y_q), EPM -> (scales | means) NHWC fp32 (B, h, w, 2C)  (:564-577)."""
+        ws = self.ws
+        f16, f32 = torch.float16, torch.float32
+        h2, w2, h4, w4 = h // 2, w // 2, h // 4, w // 4
         d1 = self.hd[0]([zhat16], B, h4, w4, ws.get("hd1", (B, h2, w2, 256), f16))
         d2 = self.hd[1]([d1], B, h2, w2, ws.get("hd2", (B, h, w, 256), f16))
         hp = self.hd[2]([d2], B, h, w, ws.get("hp", (B, h, w, 2 * self.C), f16))
@@ -428,6 +427,20 @@ class StemEngine:
         e1 = self.epm[0](srcs, B, h, w, ws.get("e1", (B, h, w, 768), f16))
         e2 = self.epm[1]([e1], B, h, w, ws.get("e2", (B, h, w, 576), f16))
         return self.epm[2]([e2], B, h, w, ws.get("gparams", (B, h, w, 2 * self.C), f32))
+
+    def gaussian_params(self, y16: Tensor, cond16: Tensor, yq16: Optional[Tensor], B: int, h: int, w: int,
+                        z_hat_nchw: Optional[Tensor] = None, z_lik_nchw: Optional[Tensor] = None,
+                        bits_z: Optional[Tensor] = None) -> Tensor:
+        """HE -> EntropyBottleneck -> HD, TPM, context, EPM. Returns params NHWC fp32 (B, h, w, 2C)."""
+        lib, ws = _lib.load(), self.ws
+        z = self.hyper_latent(y16, cond16, B, h, w)
+        h4, w4 = h // 4, w // 4
+        zhat16 = ws.get("zhat16", (B, h4, w4, self.zc), torch.float16)
+        _lib.check(lib.stemb200_entropy_bottleneck_fwd(z.data_ptr(), self.eb_params.data_ptr(), B, self.zc, h4, w4,
+                                                       self.lik_bound, zhat16.data_ptr(), _ptr(z_hat_nchw),
+                                                       _ptr(z_lik_nchw), _ptr(bits_z), _stream()),
+                   "entropy_bottleneck_fwd")
+        return self.params_from_zhat(zhat16, cond16, yq16, B, h, w)
 
     def gaussian_conditional(self, y: Tensor, y_is_nchw: bool, cond16: Optional[Tensor], params: Tensor, B: int,
                              h: int, w: int, y_hat: Optional[Tensor], lik: Optional[Tensor],

@@ -43,6 +43,40 @@ def pmf_to_quantized_cdf(pmf: Tensor, precision: int = 16) -> Tensor:
     return torch.from_numpy(out)
 
 
+def rans_encode(symbols: Tensor, indexes: Tensor, cdf: Tensor, cdf_length: Tensor, offset: Tensor) -> bytes:
+    """compressai.ans.RansEncoder().encode_with_indexes (rans_interface.cpp:193-204) over flat int32 arrays."""
+    lib = _lib.load()
+    sym = np.ascontiguousarray(symbols.detach().reshape(-1).cpu().numpy(), dtype=np.int32)
+    idx = np.ascontiguousarray(indexes.detach().reshape(-1).cpu().numpy(), dtype=np.int32)
+    if sym.size != idx.size:
+        raise ValueError("symbols and indexes must have the same number of elements")
+    c = np.ascontiguousarray(cdf.detach().cpu().numpy(), dtype=np.int32)
+    ln = np.ascontiguousarray(cdf_length.detach().reshape(-1).cpu().numpy(), dtype=np.int32)
+    off = np.ascontiguousarray(offset.detach().reshape(-1).cpu().numpy(), dtype=np.int32)
+    cap = 4 * (2 * sym.size + 64)
+    out = np.empty(cap, dtype=np.uint8)
+    n = lib.stemb200_rans_encode_host(sym.ctypes.data, idx.ctypes.data, sym.size, c.ctypes.data, c.shape[0], c.shape[1],
+                                      ln.ctypes.data, off.ctypes.data, out.ctypes.data, cap)
+    if n < 0:
+        _lib.check(int(n), "rans_encode")
+    return out[:n].tobytes()
+
+
+def rans_decode(stream: bytes, indexes: Tensor, cdf: Tensor, cdf_length: Tensor, offset: Tensor) -> Tensor:
+    """compressai.ans.RansDecoder().decode_with_indexes (rans_interface.cpp:206-275) -> int32 CPU tensor."""
+    lib = _lib.load()
+    idx = np.ascontiguousarray(indexes.detach().reshape(-1).cpu().numpy(), dtype=np.int32)
+    c = np.ascontiguousarray(cdf.detach().cpu().numpy(), dtype=np.int32)
+    ln = np.ascontiguousarray(cdf_length.detach().reshape(-1).cpu().numpy(), dtype=np.int32)
+    off = np.ascontiguousarray(offset.detach().reshape(-1).cpu().numpy(), dtype=np.int32)
+    buf = np.frombuffer(stream, dtype=np.uint8)
+    out = np.empty(idx.size, dtype=np.int32)
+    _lib.check(lib.stemb200_rans_decode_host(buf.ctypes.data, buf.size, idx.ctypes.data, idx.size, c.ctypes.data,
+                                             c.shape[0], c.shape[1], ln.ctypes.data, off.ctypes.data, out.ctypes.data),
+               "rans_decode")
+    return torch.from_numpy(out)
+
+
 class EntropyModel(nn.Module):
     """entropy_models.py:66-199 (buffers, quantize/dequantize, CDF checks)."""
 
@@ -85,6 +119,45 @@ class EntropyModel(nn.Module):
         else:
             outputs = inputs.float()
         return outputs
+
+    def compress(self, inputs: Tensor, indexes: Tensor, means: Optional[Tensor] = None):
+        """entropy_models.py:201-233: one byte string per batch element (NCHW element order)."""
+        symbols = self.quantize(inputs, "symbols", means)
+        return self.compress_symbols(symbols, indexes)
+
+    def compress_symbols(self, symbols: Tensor, indexes: Tensor):
+        if len(symbols.size()) != 4:
+            raise ValueError("Invalid `inputs` size. Expected a 4-D tensor.")
+        if symbols.size() != indexes.size():
+            raise ValueError("`inputs` and `indexes` should have the same size.")
+        self._check_cdf_size()
+        self._check_cdf_length()
+        self._check_offsets_size()
+        sym, idx = symbols.detach().int().cpu(), indexes.detach().int().cpu()  # one D2H copy each, no Python lists
+        return [rans_encode(sym[i], idx[i], self._quantized_cdf, self._cdf_length, self._offset)
+                for i in range(sym.size(0))]
+
+    def decompress(self, strings, indexes: Tensor, means: Optional[Tensor] = None) -> Tensor:
+        """entropy_models.py:235-279"""
+        if not isinstance(strings, (tuple, list)):
+            raise ValueError("Invalid `strings` parameter type.")
+        if not len(strings) == indexes.size(0):
+            raise ValueError("Invalid strings or indexes parameters")
+        if len(indexes.size()) != 4:
+            raise ValueError("Invalid `indexes` size. Expected a 4-D tensor.")
+        self._check_cdf_size()
+        self._check_cdf_length()
+        self._check_offsets_size()
+        if means is not None:
+            if means.size()[:-2] != indexes.size()[:-2]:
+                raise ValueError("Invalid means or indexes parameters")
+            if means.size() != indexes.size() and (means.size(2) != 1 or means.size(3) != 1):
+                raise ValueError("Invalid means parameters")
+        idx = indexes.detach().int().cpu()
+        outputs = torch.empty(idx.size(), dtype=torch.int32)
+        for i, s in enumerate(strings):
+            outputs[i] = rans_decode(s, idx[i], self._quantized_cdf, self._cdf_length, self._offset).reshape(idx[i].size())
+        return self.dequantize(outputs.to(indexes.device), means)
 
     def _pmf_to_cdf(self, pmf, tail_mass, pmf_length, max_length):
         cdf = torch.zeros((len(pmf_length), max_length + 2), dtype=torch.int32, device=pmf.device)
@@ -198,6 +271,24 @@ class EntropyBottleneck(EntropyModel):
         self._quantized_cdf = self._pmf_to_cdf(pmf, tail_mass, pmf_length, max_length)
         self._cdf_length = pmf_length + 2
         return True
+
+    @staticmethod
+    def _build_indexes(size):
+        n, c, h, w = size
+        return torch.arange(c).view(1, -1, 1, 1).int().repeat(n, 1, h, w)
+
+    def compress(self, x: Tensor):
+        """:459-462"""
+        indexes = self._build_indexes(x.size()).to(x.device)
+        medians = self._get_medians().detach().expand(x.size(0), -1, 1, 1)
+        return super().compress(x, indexes, medians)
+
+    def decompress(self, strings, size):
+        """:464-468"""
+        output_size = (len(strings), self._quantized_cdf.size(0), size[0], size[1])
+        indexes = self._build_indexes(output_size).to(self._quantized_cdf.device)
+        medians = self._get_medians().detach().expand(len(strings), -1, 1, 1)
+        return super().decompress(strings, indexes, medians)
 
     def forward(self, x: Tensor):
         """:424-452, eval mode: (z_hat, likelihoods), NCHW fp32 CUDA."""

@@ -200,14 +200,60 @@ class _StemBase(CompressionModel):
         entropy_models.py:598-604) and symbols round(y - mu) (:148-150), from the same fused kernel."""
         return self.engine().forward_nchw(y_cur, y_conditioned, want_indexes=True)
 
-    def compress(self, y_cur, y_conditioned):
-        raise NotImplementedError(
-            "compress(): the rANS entropy coder (compressai/cpp_exts/rans, AR loops spatiotemporalpriors.py:588-678) "
-            "is a 'next' row of SURVEY.md §8(f), not part of the forward+likelihood hot path; "
-            "forward_with_indexes() returns the symbols and CDF indexes it would encode")
+    def _no_ar(self, what: str):
+        if self._flags[1]:
+            raise NotImplementedError(
+                f"{what}(): this variant codes y autoregressively (spatiotemporalpriors.py:633-678, :729-768: a "
+                "sequential scan over the latent grid); the wavefront-parallel coder is SURVEY.md §8f rank 2. "
+                "forward_with_indexes() returns the symbols and CDF indexes; the WithoutSPM* variants and the "
+                "entropy models themselves do compress / decompress")
 
-    def decompress(self, strings, shape, y_conditioned):
-        raise NotImplementedError("decompress(): see compress(); SURVEY.md §8(f) 'next' row")
+    def compress(self, y_cur: Tensor, y_conditioned: Tensor):
+        """Non-autoregressive variants (spatiotemporalpriors.py:86-96, :197-209):
+        -> {"strings": [y_strings, z_strings], "shape": z.size()[-2:]}. Symbols and CDF indexes come from the
+        fused GaussianConditional kernel; the rANS coder is the C ABI's (byte-compatible with compressai.ans)."""
+        self._no_ar("compress")
+        from .engine import nchw_to_nhwc_f16, nhwc_f32_to_nchw
+        eng = self.engine()
+        _require_cuda(y_cur, y_conditioned)
+        y_cur, y_conditioned = y_cur.contiguous().float(), y_conditioned.contiguous().float()
+        B, C, h, w = y_cur.shape
+        f16 = torch.float16
+        y16 = nchw_to_nhwc_f16(y_cur, eng.ws.get("y16", (B, h, w, C), f16))
+        cond16 = nchw_to_nhwc_f16(y_conditioned, eng.ws.get("cond16", (B, h, w, C), f16))
+        z_nhwc = eng.hyper_latent(y16, cond16, B, h, w)
+        z = nhwc_f32_to_nchw(z_nhwc, torch.empty((B, eng.zc, h // 4, w // 4), device=y_cur.device))
+        z_strings = self.entropy_bottleneck.compress(z)
+        z_hat = self.entropy_bottleneck.decompress(z_strings, z.size()[-2:])
+        zhat16 = nchw_to_nhwc_f16(z_hat.contiguous(), eng.ws.get("zhat16", (B, h // 4, w // 4, eng.zc), f16))
+        params = eng.params_from_zhat(zhat16, cond16, None, B, h, w)
+        idx = torch.empty(y_cur.shape, dtype=torch.int32, device=y_cur.device)
+        sym = torch.empty(y_cur.shape, dtype=torch.int32, device=y_cur.device)
+        eng.gaussian_conditional(y_cur, True, None, params, B, h, w, None, None, idx, sym)
+        y_strings = self.gaussian_conditional.compress_symbols(sym, idx)
+        return {"strings": [y_strings, z_strings], "shape": z.size()[-2:]}
+
+    def decompress(self, strings, shape, y_conditioned: Tensor):
+        """Non-autoregressive variants (spatiotemporalpriors.py:99-111, :212-225). Returns a dict with "y_hat" and
+        "entropy_params" (what stem/evalSTEM.py:120,152 reads; the reference returns the bare tensor)."""
+        self._no_ar("decompress")
+        assert isinstance(strings, list) and len(strings) == 2
+        from .engine import nchw_to_nhwc_f16
+        eng = self.engine()
+        _require_cuda(y_conditioned)
+        y_conditioned = y_conditioned.contiguous().float()
+        B, C, h, w = y_conditioned.shape
+        f16 = torch.float16
+        z_hat = self.entropy_bottleneck.decompress(strings[1], shape).to(y_conditioned.device)
+        cond16 = nchw_to_nhwc_f16(y_conditioned, eng.ws.get("cond16", (B, h, w, C), f16))
+        zhat16 = nchw_to_nhwc_f16(z_hat.contiguous(), eng.ws.get("zhat16", (B, h // 4, w // 4, eng.zc), f16))
+        params = eng.params_from_zhat(zhat16, cond16, None, B, h, w)
+        idx = torch.empty(y_conditioned.shape, dtype=torch.int32, device=y_conditioned.device)
+        eng.gaussian_conditional(torch.zeros_like(y_conditioned), True, None, params, B, h, w, None, None, idx, None)
+        gp = params.permute(0, 3, 1, 2)
+        scales_hat, means_hat = gp[:, :C].contiguous(), gp[:, C:].contiguous()
+        y_hat = self.gaussian_conditional.decompress(strings[0], idx, means=means_hat)
+        return {"y_hat": y_hat, "entropy_params": {"scales_hat": scales_hat, "means_hat": means_hat}}
 
     def load_state_dict(self, state_dict, strict: bool = True):
         _resize_registered_buffers(self.gaussian_conditional, "gaussian_conditional",

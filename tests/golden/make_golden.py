@@ -150,6 +150,24 @@ def main():
     np.savez_compressed(os.path.join(OUT, "entropy_bottleneck_kat.npz"), z=z.numpy(), z_hat=z_hat.numpy(),
                         lik=z_lik.numpy())
 
+    # ---------------------------------------------------------------- rANS byte streams (cpp_exts/rans)
+    from compressai.ans import RansDecoder, RansEncoder
+    gr = torch.Generator().manual_seed(31)
+    n_sym = 20000
+    ridx = torch.randint(0, 64, (n_sym,), generator=gr, dtype=torch.int32)
+    # symbols drawn per scale, with heavy tails so that the bypass (escape) path is exercised
+    rsym = torch.round(table[ridx.long()] * torch.randn(n_sym, generator=gr) * 1.5).int()
+    rsym[::97] += 4000
+    rsym[5::131] -= 7000
+    cdfs = gc._quantized_cdf.tolist()
+    sizes = gc._cdf_length.reshape(-1).int().tolist()
+    offs = gc._offset.reshape(-1).int().tolist()
+    stream = RansEncoder().encode_with_indexes(rsym.tolist(), ridx.tolist(), cdfs, sizes, offs)
+    assert RansDecoder().decode_with_indexes(stream, ridx.tolist(), cdfs, sizes, offs) == rsym.tolist()
+    np.savez_compressed(os.path.join(OUT, "rans_kat.npz"), symbols=rsym.numpy(), indexes=ridx.numpy(),
+                        stream=np.frombuffer(stream, dtype=np.uint8))
+    print(f"rANS KAT: {n_sym} symbols -> {len(stream)} bytes")
+
     # ---------------------------------------------------------------- pmf_to_quantized_cdf (ops.cpp)
     pmfs = [[0.1, 0.2, 0.3, 0.4], [1e-9, 0.5, 0.5, 1e-9], [0.25] * 4, [1e-12] * 6 + [1.0], [0.3, 1e-7, 0.7 - 1e-7]]
     gp = torch.Generator().manual_seed(7)

@@ -1,0 +1,112 @@
+"""Entropy-coder row: the C-ABI rANS coder against byte streams produced by the reference's
+own compressai.ans module (CPU), the module-level compress/decompress API and its error conventions (CPU), and the
+non-autoregressive STEM variants' compress -> decompress round trip on the GPU (-m gpu)."""
+import numpy as np
+import pytest
+import torch
+
+from spatiotemporalentropymodel_b200 import synthetic as S
+from spatiotemporalentropymodel_b200.entropy_models import (EntropyBottleneck, GaussianConditional, rans_decode,
+                                                            rans_encode)
+from spatiotemporalentropymodel_b200.models import get_scale_table
+
+
+def _gc():
+    gc = GaussianConditional(None)
+    gc.update_scale_table(get_scale_table(), force=True)
+    return gc.eval()
+
+
+def test_rans_stream_is_byte_identical_to_reference(golden):
+    g = golden("rans_kat.npz")
+    gc = _gc()
+    sym, idx = torch.from_numpy(g["symbols"]), torch.from_numpy(g["indexes"])
+    stream = rans_encode(sym, idx, gc._quantized_cdf, gc._cdf_length, gc._offset)
+    assert stream == g["stream"].tobytes()            # 14 740 bytes, includes bypass-coded outliers
+    assert torch.equal(rans_decode(stream, idx, gc._quantized_cdf, gc._cdf_length, gc._offset), sym)
+    # SURVEY.md §8c known answer
+    kat = rans_encode(torch.tensor([1, -2, 0, 2, 0, 11, -1, 0]), torch.tensor([13, 0, 0, 18, 1, 30, 63, 1]),
+                      gc._quantized_cdf, gc._cdf_length, gc._offset)
+    assert kat.hex() == "06e0d8ff156e00001152adf4"
+
+
+def test_rans_edge_cases():
+    gc = _gc()
+    empty = rans_encode(torch.zeros(0, dtype=torch.int32), torch.zeros(0, dtype=torch.int32), gc._quantized_cdf,
+                        gc._cdf_length, gc._offset)
+    assert len(empty) == 8                             # just the flushed 64-bit state
+    assert rans_decode(empty, torch.zeros(0, dtype=torch.int32), gc._quantized_cdf, gc._cdf_length,
+                       gc._offset).numel() == 0
+    big = torch.tensor([2 ** 20, -(2 ** 20), 0], dtype=torch.int32)   # deep bypass chains
+    idx = torch.tensor([0, 63, 5], dtype=torch.int32)
+    s = rans_encode(big, idx, gc._quantized_cdf, gc._cdf_length, gc._offset)
+    assert torch.equal(rans_decode(s, idx, gc._quantized_cdf, gc._cdf_length, gc._offset), big)
+    from spatiotemporalentropymodel_b200._lib import StemLibError
+    with pytest.raises(StemLibError, match="out of range"):
+        rans_encode(torch.tensor([0]), torch.tensor([64]), gc._quantized_cdf, gc._cdf_length, gc._offset)
+
+
+def test_module_compress_decompress_cpu_round_trip_and_errors():
+    """compressai_tests/test_entropy_models.py:96-144 conventions; compress/decompress are host code."""
+    gc = _gc()
+    g = torch.Generator().manual_seed(1)
+    x = 5 * torch.randn((2, 6, 4, 4), generator=g)
+    scales = torch.exp(torch.rand((2, 6, 4, 4), generator=g) * 6 - 2)
+    means = torch.randn((2, 6, 4, 4), generator=g)
+    from oracle import stem_oracle as O
+    indexes = O.build_indexes(scales)
+    strings = gc.compress(x, indexes, means)
+    assert len(strings) == 2 and all(isinstance(s, bytes) for s in strings)
+    assert torch.equal(gc.decompress(strings, indexes, means), torch.round(x - means) + means)
+    with pytest.raises(ValueError):
+        gc.compress(x.flatten(), indexes.flatten())
+    with pytest.raises(ValueError):
+        gc.compress(x, indexes[:, :3])
+    with pytest.raises(ValueError):
+        gc.decompress(strings[0], indexes)
+    with pytest.raises(ValueError):
+        gc.decompress(strings[:1], indexes)
+    with pytest.raises(ValueError):
+        GaussianConditional(None).compress(x, indexes)        # CDFs not initialised
+    eb = EntropyBottleneck(8)
+    eb.update(force=True)
+    eb.eval()
+    z = 3 * torch.randn((2, 8, 3, 5), generator=g)
+    zs = eb.compress(z)
+    med = eb.quantiles[:, 0, 1].detach().view(1, -1, 1, 1)
+    assert torch.equal(eb.decompress(zs, z.size()[-2:]), torch.round(z - med) + med)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("variant", ["SpatioTemporalPriorModelWithoutSPM", "SpatioTemporalPriorModelWithoutSPMTPM"])
+def test_compress_decompress_round_trip_gpu(golden, variant):
+    """Non-AR variants: the decoded y_hat equals the forward pass's y_hat exactly, and the real
+    bit count tracks the likelihood estimate."""
+    from spatiotemporalentropymodel_b200 import models as M
+    dev = torch.device("cuda:0")
+    g = golden(f"stem_{variant}.npz")
+    model = getattr(M, variant)()
+    model.load_state_dict(S.make_stem_state_dict(variant, seed=0))
+    model.update(force=True)
+    model = model.to(dev).eval()
+    y_cur, y_cond = torch.from_numpy(g["y_cur"]).to(dev), torch.from_numpy(g["y_cond"]).to(dev)
+    fwd = model(y_cur, y_cond)
+    enc = model.compress(y_cur, y_cond)
+    assert set(enc) == {"strings", "shape"} and len(enc["strings"]) == 2
+    assert tuple(enc["shape"]) == (y_cur.shape[2] // 4, y_cur.shape[3] // 4)
+    dec = model.decompress(enc["strings"], enc["shape"], y_cond)
+    assert torch.equal(dec["y_hat"], fwd["y_hat"])
+    assert set(dec["entropy_params"]) == {"scales_hat", "means_hat"}
+    real_bits = 8 * sum(len(s) for part in enc["strings"] for s in part)
+    est_bits = float((-torch.log2(fwd["likelihoods"]["y"].double())).sum() +
+                     (-torch.log2(fwd["likelihoods"]["z"].double())).sum())
+    assert abs(real_bits - est_bits) / est_bits < 0.02, (real_bits, est_bits)
+
+
+@pytest.mark.gpu
+def test_ar_variants_point_to_forward_with_indexes():
+    from spatiotemporalentropymodel_b200 import models as M
+    model = M.SpatioTemporalPriorModel().to("cuda:0").eval()
+    y = torch.zeros((1, 192, 8, 8), device="cuda:0")
+    with pytest.raises(NotImplementedError, match="wavefront"):
+        model.compress(y, y)
