@@ -459,7 +459,8 @@ conv_igemm_kernel(const __grid_constant__ ConvKernelParams p) {
                 if (2 * gi + 1 < kChunks)
                   tma_store_4d(&p.out_map[t.sub], out_base + kOutStageBytes, cgrp + 32, t.w0, t.h0, t.n_img);
               } else {
-                tma_store_4d(&p.out_map[t.sub], obuf, cgrp, t.w0, t.h0, t.n_img);
+                const int omap = (BLOCK_N == 160 && t.n0 + BLOCK_N < p.c_out) ? 1 : t.sub;
+                tma_store_4d(&p.out_map[omap], obuf, cgrp, t.w0, t.h0, t.n_img);
               }
               tma_store_commit();
             }
@@ -481,19 +482,25 @@ conv_igemm_kernel(const __grid_constant__ ConvKernelParams p) {
 }
 
 // =====================================================================================================
-// conv / deconv with GDN or IGDN fused into the epilogue (C_out == 192 == one N tile)
+// conv / deconv with GDN or IGDN fused into the epilogue (C_out == 192 or 128 == one N tile)
 //
-//   x   = conv(in) + bias                    accumulator A in TMEM columns [0,192)
-//   n   = beta + gamma . x^2                 second contraction on the tensor core: x^2 (fp16, prescaled) is
-//                                            written by the epilogue warps into smem as a K-major operand, gamma
-//                                            chunks stream through the B slots of the same TMA ring; accumulator
-//                                            N in TMEM columns [192,384)
-//   out = x * rsqrt(n)  (GDN)  |  x * sqrt(n)  (IGDN); x is parked as packed fp16 in TMEM columns [384,480)
+//   x   = conv(in) + bias                    accumulator A[it & 1] in TMEM (double buffered)
+//   n   = beta + gamma . x^2                 second contraction on the tensor core: (x s)^2 (fp16, s = sq_scale a
+//                                            power of two) is written by the epilogue warps into smem as a K-major
+//                                            operand, gamma chunks stream through the B slots of the same TMA ring;
+//                                            the result OVERWRITES A[it & 1] (phase 1 has drained it by then)
+//   out = x * rsqrt(n)  (GDN)  |  x * sqrt(n)  (IGDN); x s is parked as packed fp16 in TMEM columns [2N, 2.5N)
 //
-// Per tile the MMA thread issues: main loop -> commit(tfull) -> wait(a2rdy) -> 3 gamma k-steps -> commit(nfull)
-// -> next main loop. Phase 2 of the epilogue (normalise + store) overlaps the next tile's main loop; only phase 1
-// (reading A, producing x^2) sits on the tensor pipe's critical path. Replaces layers/gdn.py:52-67 + the producing
-// conv (priors.py:421-439) without x or x^2 ever reaching HBM.
+// Schedule (tile it of this CTA):
+//   MMA thread : wait accfree[it&1] -> first half of main(it) -> [wait a2rdy(it-1); gamma(it-1); commit nfull(it-1)]
+//                -> second half of main(it) -> commit tfull(it)            (gamma of the last tile trails the loop)
+//   epilogue   : wait tfull(it) -> phase 1 (A -> x s stash + (x s)^2 smem) -> arrive a2rdy(it)
+//                -> wait nfull(it) -> phase 2 (normalise, arrive accfree[it&1], TMA store)
+// so BOTH epilogue phases of tile it overlap the main loops of tiles it+1 / it+2; the tensor pipe only idles when
+// the epilogue chain itself (phase 1 + gamma latency + phase 2) is longer than a main loop (K <= ~20 k-steps).
+// With n' = s^2 n the normalisation is out = (x s) * rsqrt(s^2 beta + acc) for GDN and
+// (x s) * sqrt(beta / s^2 + acc / s^4) for IGDN: one FFMA + one MUFU + one FMUL per element.
+// Replaces layers/gdn.py:52-67 + the producing conv (priors.py:421-439) without x or x^2 ever reaching HBM.
 // =====================================================================================================
 template <int kNT>
 struct GdnCfgT {
@@ -505,17 +512,22 @@ struct GdnCfgT {
   static constexpr int kBarrierBytes = 256 + 2 * kN * 4;
   static constexpr int kSmemBytes = 1024 + kStages * kStageBytes + kA2Bytes + kBarrierBytes;
   static constexpr int kTmemCols = 512;
-  static constexpr uint32_t kAccCol = 0, kNormCol = kN, kStashCol = 2 * kN;
+  static constexpr uint32_t kStashCol = 2 * kN;
   static_assert(kN % 64 == 0 && 2 * kN + kN / 2 <= 512, "TMEM budget");
   static_assert(kSmemBytes <= kSmemLimit, "smem overflow");
 };
 
-template <int kNT>
-__global__ void __launch_bounds__(kNumThreads, 1)
+constexpr int kGdnEpiWarps = 16;                        // 4 per TMEM lane group, one 16-column quarter each
+constexpr int kGdnEpiThreads = kGdnEpiWarps * 32;       // 512
+constexpr int kGdnThreads = 128 + kGdnEpiThreads;       // 4 control warps + 16 epilogue warps
+
+template <int kNT, bool kInverse>
+__global__ void __launch_bounds__(kGdnThreads, 1)
 conv_gdn_kernel(const __grid_constant__ ConvKernelParams p) {
   using Cfg = GdnCfgT<kNT>;
   constexpr int kStages = Cfg::kStages;
   constexpr int BLOCK_N = Cfg::kN;
+  constexpr int kGChunks = BLOCK_N / kKChunk;
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -527,7 +539,8 @@ conv_gdn_kernel(const __grid_constant__ ConvKernelParams p) {
   const uint32_t tfull_bar = bar_base + 8u * (2 * kStages);
   const uint32_t a2rdy_bar = bar_base + 8u * (2 * kStages + 1);
   const uint32_t nfull_bar = bar_base + 8u * (2 * kStages + 2);
-  const uint32_t tmem_slot = bar_base + 8u * (2 * kStages + 3);
+  auto accfree_bar = [&](int a) { return bar_base + 8u * (2 * kStages + 3 + a); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * kStages + 5);
   const uint32_t bias_smem = bar_base + 256u;
   const uint32_t beta_smem = bias_smem + 4u * BLOCK_N;
 
@@ -546,8 +559,10 @@ conv_gdn_kernel(const __grid_constant__ ConvKernelParams p) {
       mbar_init(empty_bar(s), 1);
     }
     mbar_init(tfull_bar, 1);
-    mbar_init(a2rdy_bar, 8);
+    mbar_init(a2rdy_bar, kGdnEpiWarps);
     mbar_init(nfull_bar, 1);
+    mbar_init(accfree_bar(0), kGdnEpiWarps);
+    mbar_init(accfree_bar(1), kGdnEpiWarps);
     fence_barrier_init();
   }
   if (warp == 2) {
@@ -555,8 +570,10 @@ conv_gdn_kernel(const __grid_constant__ ConvKernelParams p) {
     tmem_relinquish();
   }
   if (warp >= 4) {
-    for (int i = threadIdx.x - 128; i < BLOCK_N; i += kNumEpiThreads) {
-      const float b = __ldg(p.bias + i), g = __ldg(p.beta + i);
+    // bias, and the folded normaliser offset: s^2 beta (GDN) or beta / s^2 (IGDN)
+    const float kb = kInverse ? p.sq_inv : p.sq_scale * p.sq_scale;
+    for (int i = threadIdx.x - 128; i < BLOCK_N; i += kGdnEpiThreads) {
+      const float b = __ldg(p.bias + i), g = __ldg(p.beta + i) * kb;
       asm volatile("st.shared.f32 [%0], %1;" ::"r"(bias_smem + 4u * i), "f"(b) : "memory");
       asm volatile("st.shared.f32 [%0], %1;" ::"r"(beta_smem + 4u * i), "f"(g) : "memory");
     }
@@ -573,27 +590,24 @@ conv_gdn_kernel(const __grid_constant__ ConvKernelParams p) {
     // ===================== TMA producer =====================
     int s = 0;
     uint32_t ph = 0;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-      const TileCoord t = decode_tile(p, tile, BLOCK_N);
-      const int kbeg = p.sub_kbeg[t.sub], kend = p.sub_kend[t.sub];
-      for (int k = kbeg; k < kend; ++k) {
-        mbar_wait(empty_bar(s), ph ^ 1u);
-        const uint32_t e = p.ksteps[k];
-        const int map = e & 3;
-        const int dh = static_cast<int>((e >> 2) & 15u) - 8;
-        const int dw = static_cast<int>((e >> 6) & 15u) - 8;
-        const int c0 = static_cast<int>(e >> 10);
-        const uint32_t a_dst = stage_base + s * Cfg::kStageBytes;
-        mbar_arrive_expect_tx(full_bar(s), a_tx_bytes + Cfg::kBStageBytes);
-        tma_load_4d(a_dst, &p.a_map[map], full_bar(s), c0, t.w0 + dw, t.h0 + dh, t.n_img);
-        tma_load_2d(a_dst + kAStageBytes, &p.b_map, full_bar(s), k * kKChunk, 0);
-        if (++s == kStages) {
-          s = 0;
-          ph ^= 1u;
-        }
+    auto load_main = [&](const TileCoord& t, int k) {
+      mbar_wait(empty_bar(s), ph ^ 1u);
+      const uint32_t e = p.ksteps[k];
+      const int map = e & 3;
+      const int dh = static_cast<int>((e >> 2) & 15u) - 8;
+      const int dw = static_cast<int>((e >> 6) & 15u) - 8;
+      const int c0 = static_cast<int>(e >> 10);
+      const uint32_t a_dst = stage_base + s * Cfg::kStageBytes;
+      mbar_arrive_expect_tx(full_bar(s), a_tx_bytes + Cfg::kBStageBytes);
+      tma_load_4d(a_dst, &p.a_map[map], full_bar(s), c0, t.w0 + dw, t.h0 + dh, t.n_img);
+      tma_load_2d(a_dst + kAStageBytes, &p.b_map, full_bar(s), k * kKChunk, 0);
+      if (++s == kStages) {
+        s = 0;
+        ph ^= 1u;
       }
-      // gamma chunks for this tile's second contraction: only the B slot of the stage is used
-      for (int kc = 0; kc < BLOCK_N / kKChunk; ++kc) {
+    };
+    auto load_gamma = [&]() {  // only the B slot of the stage is used
+      for (int kc = 0; kc < kGChunks; ++kc) {
         mbar_wait(empty_bar(s), ph ^ 1u);
         const uint32_t a_dst = stage_base + s * Cfg::kStageBytes;
         mbar_arrive_expect_tx(full_bar(s), Cfg::kBStageBytes);
@@ -603,46 +617,50 @@ conv_gdn_kernel(const __grid_constant__ ConvKernelParams p) {
           ph ^= 1u;
         }
       }
+    };
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+      const TileCoord t = decode_tile(p, tile, BLOCK_N);
+      const int kbeg = p.sub_kbeg[t.sub], kend = p.sub_kend[t.sub];
+      const int ksplit = kbeg + ((kend - kbeg) >> 1);
+      for (int k = kbeg; k < ksplit; ++k) load_main(t, k);
+      if (it > 0) load_gamma();
+      for (int k = ksplit; k < kend; ++k) load_main(t, k);
     }
+    if (it > 0) load_gamma();
   } else if (warp == 1 && lane == 0) {
     // ===================== MMA issuer =====================
     constexpr uint32_t idesc = umma_idesc(/*F16*/ 0u, 128u, BLOCK_N);
     int s = 0;
     uint32_t ph = 0;
-    int it = 0;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
-      const TileCoord t = decode_tile(p, tile, BLOCK_N);
-      const int kbeg = p.sub_kbeg[t.sub], kend = p.sub_kend[t.sub];
-      // accumulator A is free: phase 1 of the previous tile completed before its gamma MMAs were issued
-      for (int k = kbeg; k < kend; ++k) {
-        mbar_wait(full_bar(s), ph);
-        tc_fence_after();
-        const uint32_t a_addr = stage_base + s * Cfg::kStageBytes;
-        const uint64_t adesc = umma_desc_sw128(a_addr);
-        const uint64_t bdesc = umma_desc_sw128(a_addr + kAStageBytes);
-#pragma unroll
-        for (int kk = 0; kk < 4; ++kk)
-          mma_f16_ss(tmem_base + Cfg::kAccCol, adesc + 2u * kk, bdesc + 2u * kk, idesc,
-                     (k > kbeg || kk > 0) ? 1u : 0u);
-        mma_commit(empty_bar(s));
-        if (++s == kStages) {
-          s = 0;
-          ph ^= 1u;
-        }
-      }
-      mma_commit(tfull_bar);
-      // second contraction: norm = gamma . x^2 once the epilogue has written x^2 (and drained A)
-      mbar_wait(a2rdy_bar, it & 1);
+    auto mma_main = [&](uint32_t d_tmem, bool first) {
+      mbar_wait(full_bar(s), ph);
       tc_fence_after();
-      for (int kc = 0; kc < BLOCK_N / kKChunk; ++kc) {
+      const uint32_t a_addr = stage_base + s * Cfg::kStageBytes;
+      const uint64_t adesc = umma_desc_sw128(a_addr);
+      const uint64_t bdesc = umma_desc_sw128(a_addr + kAStageBytes);
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk)
+        mma_f16_ss(d_tmem, adesc + 2u * kk, bdesc + 2u * kk, idesc, (!first || kk > 0) ? 1u : 0u);
+      mma_commit(empty_bar(s));
+      if (++s == kStages) {
+        s = 0;
+        ph ^= 1u;
+      }
+    };
+    // norm(j) = gamma . (x s)^2 into the accumulator tile j just vacated
+    auto mma_gamma = [&](int j) {
+      mbar_wait(a2rdy_bar, j & 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + (j & 1) * BLOCK_N;
+      for (int kc = 0; kc < kGChunks; ++kc) {
         mbar_wait(full_bar(s), ph);
         tc_fence_after();
         const uint64_t adesc = umma_desc_sw128(a2_base + kc * kAStageBytes);
         const uint64_t bdesc = umma_desc_sw128(stage_base + s * Cfg::kStageBytes + kAStageBytes);
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk)
-          mma_f16_ss(tmem_base + Cfg::kNormCol, adesc + 2u * kk, bdesc + 2u * kk, idesc,
-                     (kc > 0 || kk > 0) ? 1u : 0u);
+          mma_f16_ss(d_tmem, adesc + 2u * kk, bdesc + 2u * kk, idesc, (kc > 0 || kk > 0) ? 1u : 0u);
         mma_commit(empty_bar(s));
         if (++s == kStages) {
           s = 0;
@@ -650,92 +668,120 @@ conv_gdn_kernel(const __grid_constant__ ConvKernelParams p) {
         }
       }
       mma_commit(nfull_bar);
+    };
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+      const TileCoord t = decode_tile(p, tile, BLOCK_N);
+      const int kbeg = p.sub_kbeg[t.sub], kend = p.sub_kend[t.sub];
+      const int ksplit = kbeg + ((kend - kbeg) >> 1);
+      const uint32_t d_tmem = tmem_base + (it & 1) * BLOCK_N;
+      if (it >= 2) {  // phase 2 of tile it-2 has finished reading this accumulator
+        mbar_wait(accfree_bar(it & 1), ((it >> 1) - 1) & 1);
+        tc_fence_after();
+      }
+      for (int k = kbeg; k < ksplit; ++k) mma_main(d_tmem, k == kbeg);
+      if (it > 0) mma_gamma(it - 1);
+      for (int k = ksplit; k < kend; ++k) mma_main(d_tmem, k == kbeg);
+      mma_commit(tfull_bar);
     }
+    if (it > 0) mma_gamma(it - 1);
   } else if (warp >= 4) {
-    // ===================== epilogue (8 warps; see conv_igemm_kernel) =====================
-    const int ew = warp & 3;
+    // ===================== epilogue: 16 warps =====================
+    // warp e reads TMEM lane group e % 4 (the hardware's warp -> lane-group rule) and the 16-column quarter e / 4
+    // of every 64-channel chunk: four warps per scheduler hide each other's TMEM / MUFU / LDS latencies (the
+    // 8-warp version ran at ~0.3 IPC per scheduler, profiles/r01_ncu_gdn_v2_epilogue.txt).
+    const int e = warp - 4;
     const int etid = threadIdx.x - 128;
-    const int row = etid & 127;
-    const int half = etid >> 7;
-    const uint32_t lane_off = static_cast<uint32_t>(ew * 32) << 16;
+    const int row = (e & 3) * 32 + lane;  // accumulator row == pixel of the patch
+    const int q = e >> 2;                 // 16-column quarter
+    const uint32_t lane_off = static_cast<uint32_t>((e & 3) * 32) << 16;
     const uint32_t rsw = static_cast<uint32_t>(row & 7);
     const uint32_t row_off = static_cast<uint32_t>(row) * 128u;
-    const uint32_t jo = half ? 4u : 0u;
+    const uint32_t p0 = ((2u * q) ^ rsw) << 4, p1 = ((2u * q + 1u) ^ rsw) << 4;  // swizzled 16-byte pieces
+    const __half2 s2 = __float2half2_rn(p.sq_scale);
+    const float ka = kInverse ? p.sq_inv * p.sq_inv : 1.0f;
     int it = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
       const TileCoord t = decode_tile(p, tile, BLOCK_N);
       const uint32_t par = it & 1;
+      const uint32_t acc_col = tmem_base + lane_off + (it & 1) * BLOCK_N + 16 * q;
+      const uint32_t stash_col = tmem_base + lane_off + Cfg::kStashCol + 8 * q;
       mbar_wait(tfull_bar, par);
       tc_fence_after();
-      // ---- phase 1: x = A + bias -> stash (TMEM, packed fp16), x^2 -> smem operand.
-      // The three 64-channel buffers were the staging of the previous tile's output stores: one wait covers them
-      // (those stores were issued a whole main loop ago). TMEM loads are double buffered in registers so the load
-      // of chunk g+1 overlaps the arithmetic of chunk g.
-      if (etid == 0) tma_store_wait_read<0>();
-      named_bar_sync(1, kNumEpiThreads);
+      // ---- phase 1: x = A + bias; x s -> stash (TMEM, packed fp16), (x s)^2 -> smem operand.
+      // Buffer g was the staging of the previous tile's g-th output store (one bulk group each, oldest first).
       {
-        uint32_t r[2][32];
-        tmem_ld_32x32(tmem_base + lane_off + Cfg::kAccCol + 32 * half, r[0]);
+        uint32_t r[2][16];
+        tmem_ld_32x16(acc_col, r[0]);
 #pragma unroll
-        for (int g = 0; g < BLOCK_N / 64; ++g) {
-          const int c = 64 * g + 32 * half;
+        for (int g = 0; g < kGChunks; ++g) {
+          const int c = 64 * g + 16 * q;
+          if (etid == 0) {
+            if (g == 0) tma_store_wait_read<kGChunks - 1>();
+            else if (g + 1 < kGChunks) tma_store_wait_read<1>();
+            else tma_store_wait_read<0>();
+          }
           tmem_ld_wait();
-          if (g + 1 < BLOCK_N / 64) tmem_ld_32x32(tmem_base + lane_off + Cfg::kAccCol + c + 64, r[(g + 1) & 1]);
-          uint32_t hx[16], hq[16];
+          if (g + 1 < kGChunks) tmem_ld_32x16(acc_col + 64 * (g + 1), r[(g + 1) & 1]);
+          uint32_t hx[8], hq[8];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
+          for (int j = 0; j < 4; ++j) {
             float b0, b1, b2, b3;
             asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
                          : "=f"(b0), "=f"(b1), "=f"(b2), "=f"(b3)
                          : "r"(bias_smem + 4u * (c + 4 * j)));
             const uint32_t* rr = r[g & 1];
-            const __half2 h0 = __floats2half2_rn(__uint_as_float(rr[4 * j]) + b0, __uint_as_float(rr[4 * j + 1]) + b1);
-            const __half2 h1 =
-                __floats2half2_rn(__uint_as_float(rr[4 * j + 2]) + b2, __uint_as_float(rr[4 * j + 3]) + b3);
+            // the value that is normalised is the fp16-rounded x; x s is exact (s is a power of two)
+            const __half2 h0 =
+                __hmul2(__floats2half2_rn(__uint_as_float(rr[4 * j]) + b0, __uint_as_float(rr[4 * j + 1]) + b1), s2);
+            const __half2 h1 = __hmul2(
+                __floats2half2_rn(__uint_as_float(rr[4 * j + 2]) + b2, __uint_as_float(rr[4 * j + 3]) + b3), s2);
+            const __half2 q0 = __hmul2(h0, h0), q1 = __hmul2(h1, h1);
             hx[2 * j] = *reinterpret_cast<const uint32_t*>(&h0);
             hx[2 * j + 1] = *reinterpret_cast<const uint32_t*>(&h1);
-            // square the value that is actually normalised (the fp16-rounded x), prescaled to stay in range
-            const float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
-            const float q0 = f0.x * p.sq_scale, q1 = f0.y * p.sq_scale, q2 = f1.x * p.sq_scale,
-                        q3 = f1.y * p.sq_scale;
-            hq[2 * j] = pack_half2(q0 * q0, q1 * q1);
-            hq[2 * j + 1] = pack_half2(q2 * q2, q3 * q3);
+            hq[2 * j] = *reinterpret_cast<const uint32_t*>(&q0);
+            hq[2 * j + 1] = *reinterpret_cast<const uint32_t*>(&q1);
           }
-          tmem_st_32x16(tmem_base + lane_off + Cfg::kStashCol + (c >> 1), hx);
+          tmem_st_32x8(stash_col + 32 * g, hx);
+          named_bar_sync(1, kGdnEpiThreads);  // buffer g is free (thread 0 saw its store drain)
           const uint32_t cbase = a2_base + static_cast<uint32_t>(g) * kAStageBytes + row_off;
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const uint32_t addr = cbase + (((static_cast<uint32_t>(j) + jo) ^ rsw) << 4);
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(hq[4 * j]), "r"(hq[4 * j + 1]),
-                         "r"(hq[4 * j + 2]), "r"(hq[4 * j + 3])
-                         : "memory");
-          }
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(cbase + p0), "r"(hq[0]), "r"(hq[1]),
+                       "r"(hq[2]), "r"(hq[3])
+                       : "memory");
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(cbase + p1), "r"(hq[4]), "r"(hq[5]),
+                       "r"(hq[6]), "r"(hq[7])
+                       : "memory");
         }
       }
       tmem_st_wait();
-      fence_proxy_async_smem();  // x^2 is read by the tensor core through the async proxy
+      fence_proxy_async_smem();  // (x s)^2 is read by the tensor core through the async proxy
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(a2rdy_bar);
 
-      // ---- phase 2: out = x * (r)sqrt(beta + gamma.x^2) into the (now free) x^2 buffers, then three TMA stores
+      // ---- phase 2: out = (x s) * (r)sqrt(.) into the (now free) x^2 buffers, one TMA store per 64 channels
       mbar_wait(nfull_bar, par);
       tc_fence_after();
       {
-        uint32_t r[2][32], hs[2][16];
-        tmem_ld_32x32(tmem_base + lane_off + Cfg::kNormCol + 32 * half, r[0]);
-        tmem_ld_32x16(tmem_base + lane_off + Cfg::kStashCol + 16 * half, hs[0]);
+        uint32_t r[2][16], hs[2][8];
+        tmem_ld_32x16(acc_col, r[0]);
+        tmem_ld_32x8(stash_col, hs[0]);
 #pragma unroll
-        for (int g = 0; g < BLOCK_N / 64; ++g) {
-          const int c = 64 * g + 32 * half;
+        for (int g = 0; g < kGChunks; ++g) {
+          const int c = 64 * g + 16 * q;
           tmem_ld_wait();
-          if (g + 1 < BLOCK_N / 64) {
-            tmem_ld_32x32(tmem_base + lane_off + Cfg::kNormCol + c + 64, r[(g + 1) & 1]);
-            tmem_ld_32x16(tmem_base + lane_off + Cfg::kStashCol + ((c + 64) >> 1), hs[(g + 1) & 1]);
+          if (g + 1 < kGChunks) {
+            tmem_ld_32x16(acc_col + 64 * (g + 1), r[(g + 1) & 1]);
+            tmem_ld_32x8(stash_col + 32 * (g + 1), hs[(g + 1) & 1]);
+          } else {
+            // every TMEM read of this tile has completed: hand the accumulator back to the MMA thread
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(accfree_bar(it & 1));
           }
-          uint32_t ho[16];
+          uint32_t ho[8];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
+          for (int j = 0; j < 4; ++j) {
             float b0, b1, b2, b3;
             asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
                          : "=f"(b0), "=f"(b1), "=f"(b2), "=f"(b3)
@@ -744,12 +790,12 @@ conv_gdn_kernel(const __grid_constant__ ConvKernelParams p) {
             const uint32_t* hx = hs[g & 1];
             const float2 x0 = __half22float2(*reinterpret_cast<const __half2*>(&hx[2 * j]));
             const float2 x1 = __half22float2(*reinterpret_cast<const __half2*>(&hx[2 * j + 1]));
-            const float n0 = fmaf(__uint_as_float(rr[4 * j]), p.sq_inv, b0);
-            const float n1 = fmaf(__uint_as_float(rr[4 * j + 1]), p.sq_inv, b1);
-            const float n2 = fmaf(__uint_as_float(rr[4 * j + 2]), p.sq_inv, b2);
-            const float n3 = fmaf(__uint_as_float(rr[4 * j + 3]), p.sq_inv, b3);
+            const float n0 = fmaf(__uint_as_float(rr[4 * j]), ka, b0);
+            const float n1 = fmaf(__uint_as_float(rr[4 * j + 1]), ka, b1);
+            const float n2 = fmaf(__uint_as_float(rr[4 * j + 2]), ka, b2);
+            const float n3 = fmaf(__uint_as_float(rr[4 * j + 3]), ka, b3);
             float f0, f1, f2, f3;
-            if (p.igdn) {
+            if constexpr (kInverse) {
               f0 = approx_sqrt(n0), f1 = approx_sqrt(n1), f2 = approx_sqrt(n2), f3 = approx_sqrt(n3);
             } else {
               f0 = approx_rsqrt(n0), f1 = approx_rsqrt(n1), f2 = approx_rsqrt(n2), f3 = approx_rsqrt(n3);
@@ -758,25 +804,21 @@ conv_gdn_kernel(const __grid_constant__ ConvKernelParams p) {
             ho[2 * j + 1] = pack_half2(x1.x * f2, x1.y * f3);
           }
           const uint32_t cbase = a2_base + static_cast<uint32_t>(g) * kAStageBytes + row_off;
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const uint32_t addr = cbase + (((static_cast<uint32_t>(j) + jo) ^ rsw) << 4);
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(ho[4 * j]), "r"(ho[4 * j + 1]),
-                         "r"(ho[4 * j + 2]), "r"(ho[4 * j + 3])
-                         : "memory");
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(cbase + p0), "r"(ho[0]), "r"(ho[1]),
+                       "r"(ho[2]), "r"(ho[3])
+                       : "memory");
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(cbase + p1), "r"(ho[4]), "r"(ho[5]),
+                       "r"(ho[6]), "r"(ho[7])
+                       : "memory");
+          fence_proxy_async_smem();
+          named_bar_sync(1, kGdnEpiThreads);
+          if (etid == 0) {
+            tma_store_4d(&p.out_map[t.sub], a2_base + static_cast<uint32_t>(g) * kAStageBytes, 64 * g, t.w0, t.h0,
+                         t.n_img);
+            tma_store_commit();
           }
         }
       }
-      fence_proxy_async_smem();
-      named_bar_sync(1, kNumEpiThreads);
-      if (etid == 0) {
-#pragma unroll
-        for (int g = 0; g < BLOCK_N / 64; ++g)
-          tma_store_4d(&p.out_map[t.sub], a2_base + static_cast<uint32_t>(g) * kAStageBytes, 64 * g, t.w0, t.h0,
-                       t.n_img);
-        tma_store_commit();
-      }
-      tc_fence_before();
     }
     if (etid == 0) tma_store_wait_all<0>();
   }
@@ -842,7 +884,7 @@ struct Plan {
 int pick_block_n(int c_out) {
   if (c_out % 256 == 0) return 256;
   if (c_out % 192 == 0) return 192;
-  if (c_out == 160) return 160;
+  if (c_out == 160 || c_out == 320) return 160;
   if (c_out % 128 == 0) return 128;
   if (c_out == 96) return 96;
   if (c_out % 64 == 0) return 64;
@@ -865,9 +907,11 @@ int build_plan(const stemb200_conv_desc& d, Plan& pl) {
     pl.c_in_total += d.c_in[s];
   }
   pl.block_n = pick_block_n(d.c_out);
+  // two 160-wide tiles need the clipped store map of the plain stride-1 / strided path (setup_params)
+  if (d.c_out == 320 && (d.transposed || d.epilogue != STEMB200_EPI_LINEAR)) pl.block_n = 64;
   if (!pl.block_n) return set_error("conv: unsupported c_out");
   if (pl.block_n < 32 && !d.direct_store) return set_error("conv: c_out < 32 needs direct_store");
-  if (!d.direct_store && (d.c_out % 64) && d.c_out != 160)
+  if (!d.direct_store && (d.c_out % 64) && d.c_out != 160 && d.c_out != 320)
     return set_error("conv: the TMA-store epilogue needs c_out % 64 == 0 (or c_out == 160)");
   if (d.epilogue < 0 || d.epilogue > 2) return set_error("conv: bad epilogue");
   if (d.epilogue != STEMB200_EPI_LINEAR && (d.direct_store || d.out_dtype != STEMB200_DT_F16))
@@ -1001,13 +1045,14 @@ EncodeTiledFn get_encode() {
 
 // NHWC view {C, W, H, N} with optional phase sub-sampling (mul) and origin (ph, pw)
 int encode_nhwc(CUtensorMap* m, const void* base, int elem_bytes, int n, int h, int w, int c, int mul, int ph,
-                int pw, int box_c, int box_w, int box_h) {
+                int pw, int box_c, int box_w, int box_h, int c_extent = 0) {
   EncodeTiledFn enc = get_encode();
   if (!enc) return set_error("cuTensorMapEncodeTiled unavailable");
   const int hv = (h - ph + mul - 1) / mul, wv = (w - pw + mul - 1) / mul;
   if (hv < 1 || wv < 1) return set_error("conv: empty phase view");
-  cuuint64_t dims[4] = {static_cast<cuuint64_t>(c), static_cast<cuuint64_t>(wv), static_cast<cuuint64_t>(hv),
-                        static_cast<cuuint64_t>(n)};
+  // c_extent < c clips the channel dimension (stores beyond it are dropped) while keeping the pixel pitch c
+  cuuint64_t dims[4] = {static_cast<cuuint64_t>(c_extent > 0 ? c_extent : c), static_cast<cuuint64_t>(wv),
+                        static_cast<cuuint64_t>(hv), static_cast<cuuint64_t>(n)};
   cuuint64_t strides[3] = {static_cast<cuuint64_t>(c) * elem_bytes * mul,
                            static_cast<cuuint64_t>(w) * c * elem_bytes * mul,
                            static_cast<cuuint64_t>(h) * w * c * elem_bytes};
@@ -1129,6 +1174,14 @@ int setup_params(const stemb200_conv_desc* d, const Plan& pl, const void* const*
         return rc;
     }
   }
+  if (!d->direct_store && pl.block_n == 160 && d->c_out == 320) {
+    // BLOCK_N = 160 has an odd number of 32-column chunks: the idle half of the last 64-channel store group would
+    // spill stale staging data into the next N tile's channels, so the first tile stores through a map clipped at 160
+    if (pl.n_sub != 1) return set_error("conv: c_out == 320 supports stride-1 / strided convs only");
+    if (int rc = encode_nhwc(&kp.out_map[1], out, out_bytes, d->batch, pl.full_h, pl.full_w, out_c, pl.os,
+                             pl.sub_p[0], pl.sub_q[0], out_box_c, tw, th, 160))
+      return rc;
+  }
   kp.g_map = kp.b_map;
   for (size_t i = 0; i < pl.ksteps.size(); ++i) kp.ksteps[i] = pl.ksteps[i];
   for (int i = 0; i < 4; ++i) {
@@ -1206,17 +1259,17 @@ extern "C" int stemb200_conv2d_fwd(const stemb200_conv_desc* d, const void* cons
 }
 
 namespace {
-template <int kNT>
+template <int kNT, bool kInverse>
 int launch_gdn(const ConvKernelParams& kp, int grid, cudaStream_t stream) {
   using Cfg = GdnCfgT<kNT>;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(conv_gdn_kernel<kNT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(conv_gdn_kernel<kNT, kInverse>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          Cfg::kSmemBytes);
     if (e != cudaSuccess) return set_cuda_error("cudaFuncSetAttribute(conv_gdn)", e);
     configured = true;
   }
-  conv_gdn_kernel<kNT><<<grid, kNumThreads, Cfg::kSmemBytes, stream>>>(kp);
+  conv_gdn_kernel<kNT, kInverse><<<grid, kGdnThreads, Cfg::kSmemBytes, stream>>>(kp);
   count_launch();
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_cuda_error("conv_gdn launch", e);
@@ -1246,5 +1299,6 @@ extern "C" int stemb200_conv2d_gdn_fwd(const stemb200_conv_desc* d, const void* 
   kp.igdn = inverse ? 1 : 0;
   const int grid = std::min(kp.total_tiles, num_sms());
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  return d->c_out == 192 ? launch_gdn<192>(kp, grid, st) : launch_gdn<128>(kp, grid, st);
+  if (d->c_out == 192) return inverse ? launch_gdn<192, true>(kp, grid, st) : launch_gdn<192, false>(kp, grid, st);
+  return inverse ? launch_gdn<128, true>(kp, grid, st) : launch_gdn<128, false>(kp, grid, st);
 }

@@ -357,6 +357,7 @@ int main(int argc, char** argv) {
   std::vector<Case> perf = {
       {"P_tpm4_5x5_320_384_b11", mk(11, 68, 120, {320}, 384, 5, 1, 0, 0, LIN, 1.f, F16, 0, 0), 4000},
       {"P_tpm0_5x5_192_256_b11", mk(11, 68, 120, {192}, 256, 5, 1, 0, 0, LIN, 0.01f, F16, 0, 0), 4000},
+      {"P_tpm2_5x5_256_320_b11", mk(11, 68, 120, {256}, 320, 5, 1, 0, 0, LIN, 0.01f, F16, 0, 0), 4000},
       {"P_ga2_5x5s2_192_192_b2", mk(2, 544, 960, {192}, 192, 5, 2, 0, 0, LIN, 1.f, F16, 1, 0), 4000},
       {"P_gs4_deconv_192_192_b2", mk(2, 272, 480, {192}, 192, 5, 2, 1, 0, LIN, 1.f, F16, 1, 0), 4000},
       {"P_epm0_cat3_768_b11", mk(11, 68, 120, {384, 384, 384}, 768, 1, 1, 0, 0, LIN, 0.01f, F16, 0, 0), 4000},
