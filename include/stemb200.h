@@ -69,6 +69,13 @@ typedef struct stemb200_conv_desc {
                            the fp16 range; the normaliser is rescaled by 1/sq_scale^2 */
   int32_t tile_h, tile_w; /* output patch per 128-row MMA tile, tile_h*tile_w <= 128; 0 = choose */
   int32_t direct_store; /* 1: epilogue stores straight from registers (debug / c_out < 32) */
+  int32_t row_taps;     /* 1: few-channel first layer (conv k x k, stride 2, c_in[0] == 8, k <= 8; priors.py:422).
+                           in[0] is the zero-bordered canvas written by stemb200_frame_to_nhwc8:
+                           [batch][h_in + 2*(k/2)][w_in + 2*(k/2)][8] fp16 (+ 64 elements of slack), h_in / w_in the
+                           logical (even) input size. One K step per kernel ROW: the k taps of a row are 8k
+                           contiguous fp16 of the canvas, fetched as one 64-element TMA box through a tensor map
+                           whose pixel stride (2 pixels) is smaller than its box (overlapping windows), so no
+                           im2col buffer exists. Packed weight: [c_out][k*64], K index = r*64 + s*8 + ch. */
 } stemb200_conv_desc;
 
 /* K extent of the packed weight matrix [c_out][K] for this geometry */
@@ -109,6 +116,12 @@ int stemb200_nhwc_f32_to_nchw_f32(const float* in, float* out, int32_t n, int32_
  * 64). The rows are the NHWC input (C = 80) of a 1x1 stemb200_conv2d_gdn_fwd whose weight is the [N][75] reshape. */
 int stemb200_im2col_k5s2_c3(const float* x_nchw, void* out_rows, int32_t n, int32_t h, int32_t w,
                             int32_t h_pad, int32_t w_pad, int32_t pad_top, int32_t pad_left, void* stream);
+/* Operand canvas of the row_taps first layer (priors.py:422 on the evalSTEM.py:96-109 padded frame): NCHW fp32
+ * (n, c <= 8, h, w) -> NHWC fp16 [n][h_pad + 2*border][w_pad + 2*border][8], the frame at (pad_top + border,
+ * pad_left + border), zeros elsewhere (conv padding, frame padding and channels c..7). */
+int stemb200_frame_to_nhwc8(const float* x_nchw, void* canvas, int32_t n, int32_t c, int32_t h, int32_t w,
+                            int32_t h_pad, int32_t w_pad, int32_t pad_top, int32_t pad_left, int32_t border,
+                            void* stream);
 
 /* stem_roi (compressai/models/stem_roi.py) staging kernels.
  * im2col_k3s1_c4: operand rows of conv(4, 192, k3, s1) on cat[x (3 ch), Qmap (1 ch)] (:379, :586):

@@ -24,7 +24,7 @@ class ConvDesc(C.Structure):
         ("c_in", C.c_int32 * 3), ("c_out", C.c_int32), ("kh", C.c_int32), ("kw", C.c_int32),
         ("stride", C.c_int32), ("transposed", C.c_int32), ("tap_mask", C.c_uint32), ("epilogue", C.c_int32),
         ("lrelu_slope", C.c_float), ("out_dtype", C.c_int32), ("sq_scale", C.c_float),
-        ("tile_h", C.c_int32), ("tile_w", C.c_int32), ("direct_store", C.c_int32),
+        ("tile_h", C.c_int32), ("tile_w", C.c_int32), ("direct_store", C.c_int32), ("row_taps", C.c_int32),
     ]
 
 
@@ -47,6 +47,7 @@ SIGNATURES = {
     "stemb200_nhwc_f16_to_nchw_f32": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _vp]),
     "stemb200_nhwc_f32_to_nchw_f32": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _vp]),
     "stemb200_im2col_k5s2_c3": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
+    "stemb200_frame_to_nhwc8": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
     "stemb200_im2col_k3s1_c4": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _vp]),
     "stemb200_avgpool_nhwc_f16": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp]),
     "stemb200_qmap_pool": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _vp]),

@@ -836,6 +836,7 @@ struct PackParams {
   uint32_t info[kMaxKSteps];  // [2:0] r | [5:3] s | [12:6] valid channels in this chunk - 1 | [31:13] channel base
   int n_steps;
   int c_out, c_in_total, kh, kw, transposed;
+  int row_taps;
 };
 
 __global__ void pack_weight_kernel(const __grid_constant__ PackParams pp, const float* __restrict__ w,
@@ -851,7 +852,11 @@ __global__ void pack_weight_kernel(const __grid_constant__ PackParams pp, const 
     const int kc = k % kKChunk;
     const int ci = static_cast<int>(e >> 13) + kc;
     float v = 0.f;
-    if (kc <= static_cast<int>((e >> 6) & 127u)) {
+    if (pp.row_taps) {
+      // one K step per kernel row r: k = s * 8 + ch (8 channels per tap, taps s >= kw are zero)
+      const int sx = kc >> 3, ch = kc & 7;
+      if (sx < pp.kw) v = w[((static_cast<long long>(o) * 8 + ch) * pp.kh + r) * pp.kw + sx];
+    } else if (kc <= static_cast<int>((e >> 6) & 127u)) {
       const long long idx = pp.transposed
                                 ? ((static_cast<long long>(ci) * pp.c_out + o) * pp.kh + r) * pp.kw + s
                                 : ((static_cast<long long>(o) * pp.c_in_total + ci) * pp.kh + r) * pp.kw + s;
@@ -879,6 +884,7 @@ struct Plan {
   int h_out = 0, w_out = 0, os = 1, full_h = 0, full_w = 0;
   int c_in_total = 0;
   int block_n = 0;
+  bool row_taps = false;
 };
 
 int pick_block_n(int c_out) {
@@ -934,7 +940,21 @@ int build_plan(const stemb200_conv_desc& d, Plan& pl) {
                            (static_cast<uint32_t>(valid - 1) << 6) | (static_cast<uint32_t>(cbase) << 13));
   };
 
-  if (!d.transposed && d.stride == 1) {
+  if (d.row_taps) {
+    if (d.transposed || d.stride != 2 || d.n_src != 1 || d.c_in[0] != 8 || d.tap_mask || (d.h_in & 1) || (d.w_in & 1))
+      return set_error("conv: row_taps needs a plain stride-2 conv with c_in == 8 and even h_in / w_in");
+    pl.row_taps = true;
+    pl.n_maps = 2;  // even / odd canvas rows
+    pl.h_out = d.h_in / 2;
+    pl.w_out = d.w_in / 2;
+    for (int r = 0; r < k; ++r) push_v(r & 1, r >> 1, 0, 0, r, 0, 0, kKChunk);
+    pl.n_sub = 1;
+    pl.sub_kbeg[0] = 0;
+    pl.sub_kend[0] = static_cast<int>(pl.ksteps.size());
+    pl.os = 1;
+    pl.full_h = pl.h_out;
+    pl.full_w = pl.w_out;
+  } else if (!d.transposed && d.stride == 1) {
     pl.n_maps = d.n_src;
     for (int s = 0; s < d.n_src; ++s) pl.map_src[s] = s;
     pl.h_out = d.h_in;
@@ -1074,6 +1094,33 @@ int encode_nhwc(CUtensorMap* m, const void* base, int elem_bytes, int n, int h, 
   return 0;
 }
 
+// row_taps first layer: view {64 contiguous fp16, w_out (stride 2 pixels = 32 B), rows of one parity (stride 2 canvas
+// rows), n} over the zero-bordered NHWC8 canvas [n][h + 2b][w + 2b][8]. The 64-element box starting at canvas pixel
+// 2*ow holds the 8 taps x 8 channels of one kernel row of output pixel ow (windows of neighbouring pixels overlap).
+int encode_row_taps(CUtensorMap* m, const void* base, int n, int h, int w, int border, int parity, int box_w,
+                    int box_h) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return set_error("cuTensorMapEncodeTiled unavailable");
+  const long long hc = h + 2 * border, wc = w + 2 * border;
+  const long long rows = (hc - parity + 1) / 2;
+  cuuint64_t dims[4] = {64, static_cast<cuuint64_t>(w / 2), static_cast<cuuint64_t>(rows),
+                        static_cast<cuuint64_t>(n)};
+  cuuint64_t strides[3] = {32, static_cast<cuuint64_t>(wc) * 8 * 2 * 2, static_cast<cuuint64_t>(hc * wc) * 8 * 2};
+  cuuint32_t box[4] = {64, static_cast<cuuint32_t>(box_w), static_cast<cuuint32_t>(box_h), 1u};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  const char* origin = static_cast<const char*>(base) + static_cast<size_t>(parity) * wc * 8 * 2;
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<char*>(origin), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    char buf[160];
+    snprintf(buf, sizeof(buf), "cuTensorMapEncodeTiled(row_taps) failed: %d (w=%d h=%d n=%d box=%d,%d)",
+             static_cast<int>(r), w, h, n, box_w, box_h);
+    return set_error(buf);
+  }
+  return 0;
+}
+
 int encode_weight(CUtensorMap* m, const void* base, long long K, int c_out, int block_n) {
   EncodeTiledFn enc = get_encode();
   if (!enc) return set_error("cuTensorMapEncodeTiled unavailable");
@@ -1135,6 +1182,7 @@ extern "C" int stemb200_conv2d_pack_weight(const stemb200_conv_desc* d, const fl
   pp.kh = d->kh;
   pp.kw = d->kw;
   pp.transposed = d->transposed;
+  pp.row_taps = pl.row_taps ? 1 : 0;
   const long long total = static_cast<long long>(pp.n_steps) * kKChunk * d->c_out;
   const int blocks = static_cast<int>(std::min<long long>((total + 255) / 256, 148 * 16));
   pack_weight_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
@@ -1156,6 +1204,10 @@ int setup_params(const stemb200_conv_desc* d, const Plan& pl, const void* const*
 
   for (int m = 0; m < 4; ++m) {
     const int mm = m < pl.n_maps ? m : 0;
+    if (pl.row_taps) {
+      if (int rc = encode_row_taps(&kp.a_map[m], in[0], d->batch, d->h_in, d->w_in, d->kh / 2, mm, tw, th)) return rc;
+      continue;
+    }
     const int src = pl.map_src[mm];
     if (int rc = encode_nhwc(&kp.a_map[m], in[src], 2, d->batch, d->h_in, d->w_in, d->c_in[src],
                              pl.in_stride_mul, pl.map_ph[mm], pl.map_pw[mm], kKChunk, tw, th))

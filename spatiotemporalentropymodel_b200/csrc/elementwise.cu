@@ -609,6 +609,50 @@ extern "C" int stemb200_im2col_k5s2_c3(const float* x_nchw, void* out_rows, int3
   return 0;
 }
 
+// NCHW fp32 frame -> zero-bordered NHWC8 fp16 canvas (operand of the row_taps first layer); one 16-byte store per
+// canvas pixel, reads coalesced per channel plane.
+__global__ void __launch_bounds__(256)
+frame_to_nhwc8_kernel(const float* __restrict__ x, uint4* __restrict__ canvas, int c, int h, int w, int hc, int wc,
+                      int off_top, int off_left, long long total) {
+  for (long long i = blockIdx.x * 256LL + threadIdx.x; i < total; i += gridDim.x * 256LL) {
+    const int cw = static_cast<int>(i % wc);
+    const long long t = i / wc;
+    const int chh = static_cast<int>(t % hc);
+    const long long n = t / hc;
+    const int ih = chh - off_top, iw = cw - off_left;
+    float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (ih >= 0 && ih < h && iw >= 0 && iw < w) {
+      const float* px = x + (n * c * h + ih) * static_cast<long long>(w) + iw;
+#pragma unroll
+      for (int ch = 0; ch < 8; ++ch)
+        if (ch < c) v[ch] = __ldg(px + static_cast<long long>(ch) * h * w);
+    }
+    uint4 o;
+    __half2 h0 = __floats2half2_rn(v[0], v[1]), h1 = __floats2half2_rn(v[2], v[3]);
+    __half2 h2 = __floats2half2_rn(v[4], v[5]), h3 = __floats2half2_rn(v[6], v[7]);
+    o.x = *reinterpret_cast<uint32_t*>(&h0);
+    o.y = *reinterpret_cast<uint32_t*>(&h1);
+    o.z = *reinterpret_cast<uint32_t*>(&h2);
+    o.w = *reinterpret_cast<uint32_t*>(&h3);
+    canvas[i] = o;
+  }
+}
+
+extern "C" int stemb200_frame_to_nhwc8(const float* x_nchw, void* canvas, int32_t n, int32_t c, int32_t h, int32_t w,
+                                       int32_t h_pad, int32_t w_pad, int32_t pad_top, int32_t pad_left,
+                                       int32_t border, void* stream) {
+  if (!x_nchw || !canvas || n < 1 || c < 1 || c > 8 || h < 1 || w < 1 || h_pad < h || w_pad < w || pad_top < 0 ||
+      pad_left < 0 || border < 0 || pad_top + h > h_pad || pad_left + w > w_pad)
+    return set_error("frame_to_nhwc8: bad argument");
+  const int hc = h_pad + 2 * border, wc = w_pad + 2 * border;
+  const long long total = static_cast<long long>(n) * hc * wc;
+  const int blocks = static_cast<int>(std::min<long long>((total + 255) / 256, 148LL * 32));
+  frame_to_nhwc8_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      x_nchw, static_cast<uint4*>(canvas), c, h, w, hc, wc, pad_top + border, pad_left + border, total);
+  CHECK_LAUNCH("frame_to_nhwc8");
+  return 0;
+}
+
 extern "C" int stemb200_im2col_k3s1_c4(const float* x_nchw, const float* q_nchw, void* out_rows, int32_t n,
                                        int32_t h, int32_t w, void* stream) {
   if (!x_nchw || !q_nchw || !out_rows || n < 1 || h < 1 || w < 1 || h > 65535 || n > 65535)

@@ -237,7 +237,23 @@ static int run_gdn_case(const std::string& name, stemb200_conv_desc d, int inver
   const size_t nin = (size_t)d.batch * d.h_in * d.w_in * cin;
   std::vector<__half> hin(nin);
   for (auto& v : hin) v = __float2half_rn(U(rng));
-  void* din; CK(cudaMalloc(&din, nin * 2)); CK(cudaMemcpy(din, hin.data(), nin * 2, cudaMemcpyHostToDevice));
+  void* din;
+  if (d.row_taps) {
+    // zero-bordered NHWC8 canvas [n][h + 2 pad][w + 2 pad][8] (+ slack), what stemb200_frame_to_nhwc8 writes
+    const int hc = d.h_in + 2 * pad, wc = d.w_in + 2 * pad;
+    std::vector<__half> canvas((size_t)d.batch * hc * wc * 8 + 64, __float2half_rn(0.f));
+    for (int n = 0; n < d.batch; ++n)
+      for (int ih = 0; ih < d.h_in; ++ih)
+        for (int iw = 0; iw < d.w_in; ++iw)
+          for (int ci = 0; ci < 8; ++ci)
+            canvas[(((size_t)n * hc + ih + pad) * wc + iw + pad) * 8 + ci] =
+                hin[(((size_t)n * d.h_in + ih) * d.w_in + iw) * 8 + ci];
+    CK(cudaMalloc(&din, canvas.size() * 2));
+    CK(cudaMemcpy(din, canvas.data(), canvas.size() * 2, cudaMemcpyHostToDevice));
+  } else {
+    CK(cudaMalloc(&din, nin * 2));
+    CK(cudaMemcpy(din, hin.data(), nin * 2, cudaMemcpyHostToDevice));
+  }
   const size_t nw = (size_t)C * cin * k * k;
   std::vector<float> hw(nw);
   const float wscale = 2.0f / sqrtf((float)cin * k * k / (d.transposed ? 4 : 1));
@@ -378,6 +394,9 @@ int main(int argc, char** argv) {
       {"G_conv5s2_gdn", mk(2, 40, 72, {192}, 192, 5, 2, 0, 0, LIN, 1.f, F16, 0, 0), 0, 150, false},
       {"G_gemm128_gdn", mk(1, 24, 40, {128}, 192, 1, 1, 0, 0, LIN, 1.f, F16, 0, 0), 0, 300, false},
       {"G_deconv5_igdn", mk(2, 17, 30, {192}, 192, 5, 2, 1, 0, LIN, 1.f, F16, 0, 0), 1, 150, false},
+      {"G_rowtaps5s2_gdn", [&] { auto d = mk(2, 40, 72, {8}, 192, 5, 2, 0, 0, LIN, 1.f, F16, 0, 0); d.row_taps = 1; return d; }(), 0, 300, false},
+      {"G_rowtaps5s2_ragged", [&] { auto d = mk(1, 34, 60, {8}, 192, 5, 2, 0, 0, LIN, 1.f, F16, 0, 0); d.row_taps = 1; return d; }(), 0, 300, false},
+      {"G_P_ga0_rowtaps_gdn_b2", [&] { auto d = mk(2, 1088, 1920, {8}, 192, 5, 2, 0, 0, LIN, 1.f, F16, 0, 0); d.row_taps = 1; return d; }(), 0, 100, true},
       {"G_P_ga2_gdn_b2", mk(2, 544, 960, {192}, 192, 5, 2, 0, 0, LIN, 1.f, F16, 0, 0), 0, 40, true},
       {"G_P_ga0_gemm_gdn_b2", mk(2, 544, 960, {128}, 192, 1, 1, 0, 0, LIN, 1.f, F16, 0, 0), 0, 100, true},
       {"G_P_gs4_deconv_igdn_b2", mk(2, 272, 480, {192}, 192, 5, 2, 1, 0, LIN, 1.f, F16, 0, 0), 1, 40, true},

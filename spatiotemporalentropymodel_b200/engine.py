@@ -65,7 +65,8 @@ class ConvOp:
     def __init__(self, weight: Tensor, bias: Tensor, *, c_in: Sequence[int], c_out: int, k: int, stride: int = 1,
                  transposed: bool = False, tap_mask: int = 0, slope: float = 1.0, out_dtype: int = DT_F16,
                  direct_store: bool = False, gdn: Optional[Tuple[Tensor, Tensor, bool]] = None,
-                 alg_flops_per_out_pixel: Optional[float] = None, epilogue: int = EPI_LINEAR):
+                 alg_flops_per_out_pixel: Optional[float] = None, epilogue: int = EPI_LINEAR,
+                 row_taps: bool = False):
         """gdn = (beta', gamma', inverse) with the re-parametrised beta (C,) / gamma (C, C): the layer is followed
         by GDN / IGDN and both run in one kernel (stemb200_conv2d_gdn_fwd)."""
         _require_cuda(weight, bias)
@@ -90,6 +91,7 @@ class ConvOp:
         d.sq_scale = SQ_SCALE
         d.tile_h = d.tile_w = 0
         d.direct_store = int(direct_store)
+        d.row_taps = int(row_taps)
         self.desc = d
         K = self.lib.stemb200_conv2d_packed_k(C.byref(d))
         if K <= 0:
@@ -242,8 +244,9 @@ class TransformsEngine:
         M = sd["g_a.6.weight"].shape[0]
         self.N, self.M = N, M
         # --- analysis
-        w0 = g("g_a.0.weight")  # (N, 3, 5, 5) -> (N, 80): k = (r*5+s)*3 + ch, zero padded (im2col row layout)
-        w0 = F.pad(w0.permute(0, 2, 3, 1).reshape(N, 75), (0, 80 - 75)).reshape(N, 80, 1, 1).contiguous()
+        # first layer (3 -> N, k5 s2): row_taps mode, one K step per kernel row straight from a zero-bordered NHWC8
+        # canvas of the frame (no im2col buffer); the weight is zero-padded to 8 input channels
+        w0 = F.pad(g("g_a.0.weight"), (0, 0, 0, 0, 0, 5)).contiguous()  # (N, 8, 5, 5)
         if N != 192:
             raise ValueError("the fused conv+GDN kernel is built for N = 192 channels (mbt2018 quality 1-8)")
 
@@ -251,7 +254,8 @@ class TransformsEngine:
             beta, gamma = _gdn_fold(g(f"{name}.beta"), g(f"{name}.gamma"))
             return (beta, gamma, inverse)
 
-        self.ga_conv = [ConvOp(w0, g("g_a.0.bias"), c_in=[80], c_out=N, k=1, gdn=gdn_of("g_a.1", False),
+        self.ga_conv = [ConvOp(w0, g("g_a.0.bias"), c_in=[8], c_out=N, k=5, stride=2, row_taps=True,
+                               gdn=gdn_of("g_a.1", False),
                                alg_flops_per_out_pixel=2.0 * 75 * N + 2.0 * N * N)]
         for i in (2, 4):
             self.ga_conv.append(ConvOp(g(f"g_a.{i}.weight"), g(f"g_a.{i}.bias"), c_in=[N], c_out=N, k=5, stride=2,
@@ -300,14 +304,16 @@ class TransformsEngine:
         left, right, top, bottom = pad
         Hp, Wp = H + top + bottom, W + left + right
         lib, ws, N = _lib.load(), self.ws, self.N
-        h, w = (Hp - 1) // 2 + 1, (Wp - 1) // 2 + 1
-        rows = ws.get("ga_rows", (B, h, w, 80), torch.float16)
-        _lib.check(lib.stemb200_im2col_k5s2_c3(x.data_ptr(), rows.data_ptr(), B, H, W, Hp, Wp, top, left,
-                                               _stream()), "im2col_k5s2_c3")
-        cur = rows
+        if Hp % 2 or Wp % 2:
+            raise ValueError("analysis needs an even padded frame size")
+        border = 2
+        canvas = ws.get("ga_canvas", (B * (Hp + 2 * border) * (Wp + 2 * border) * 8 + 64,), torch.float16)
+        _lib.check(lib.stemb200_frame_to_nhwc8(x.data_ptr(), canvas.data_ptr(), B, 3, H, W, Hp, Wp, top, left, border,
+                                               _stream()), "frame_to_nhwc8")
+        cur, h, w = canvas, Hp, Wp
         for li in range(3):
             conv = self.ga_conv[li]
-            ho, wo = conv.out_hw(h, w) if li else (h, w)
+            ho, wo = conv.out_hw(h, w)
             gb = conv([cur], B, h, w, ws.get(f"ga_g{li}", (B, ho, wo, N), torch.float16))
             cur, h, w = gb, ho, wo
         conv = self.ga_conv[3]
