@@ -192,6 +192,50 @@ int stemb200_synthesis_tail(const float* in_nhwc64, float* x_hat_nchw, int32_t n
                             double* sq_err, int32_t clamp01, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------
+ * Autoregressive coding of y for the variants with a spatial context model (SpatioTemporalPriorModel, _Res,
+ * WithoutTPM: spatiotemporalpriors.py:633-678 / :729-768 / :915-961 / :1016-1055) and for the I-frame model
+ * (JointAutoregressiveHierarchicalPriors, priors.py:556-600 / :651-684). The reference scans the latent grid in
+ * raster order on the CPU; here one persistent 64-CTA kernel (fp32 weights resident in shared memory) runs the same
+ * recurrence per latent position
+ *     ctx = context_prediction(t_hat)[h, w]            (12 causal taps of the masked 5x5 conv)
+ *     g   = L2(lrelu(L1(lrelu(e0[h, w] + L0_ctx . ctx))));  sigma = g[:c], mu = g[c:]
+ *     idx = build_indexes(sigma);  sym = round(t - mu);  t_hat[h, w] = sym + mu
+ * encode: wavefront order (w + 3h = const), all images of the batch per step; decode: raster order (the rANS stream
+ * dictates it) with the rANS state machine inside the kernel. All tensors NHWC fp32 ([batch][h][w][channels]), which is
+ * also the (h, w, c) symbol order of the reference's streams. e0 = the y_hat-independent part of the first EPM /
+ * entropy_parameters layer (prior columns + bias, no activation), a batched 1x1 conv done by stemb200_conv2d_fwd.
+ * ------------------------------------------------------------------------------------------------- */
+typedef struct stemb200_ar_desc {
+  int32_t batch;    /* images coded in parallel (<= 64) */
+  int32_t h, w;     /* latent grid */
+  int32_t c;        /* latent channels (multiple of 64, <= 256); context_prediction maps c -> 2c */
+  int32_t l1, l2;   /* widths of the two hidden layers of the parameter head (multiples of 64) */
+  float slope;      /* LeakyReLU slope of the head (0.01) */
+  int32_t n_scales; /* scale table length */
+} stemb200_ar_desc;
+/* Weights are packed on the host (fp32) as 64 consecutive per-CTA blocks; CTA j owns rows
+ *   [j*rc, (j+1)*rc) of context_prediction (rc = 2c/64; each row = 12 taps x c, tap-major, taps in mask order),
+ *   then its rc biases; rows [j*r1, ..) of the context columns of layer 0 (r1 = l1/64, 2c columns);
+ *   rows [j*r2, ..) of layer 1 (r2 = l2/64, l1 columns) and their biases; rows {j*rg + i} (sigma) then
+ *   {c + j*rg + i} (mu), i < rg = c/64, of layer 2 (l2 columns) and the 2 rg biases in the same order.
+ * stemb200_ar_packed_floats returns the total float count (64 blocks). */
+int64_t stemb200_ar_packed_floats(const stemb200_ar_desc* d);
+int64_t stemb200_ar_workspace_bytes(const stemb200_ar_desc* d);
+/* target: the coded quantity (y, or y - y_conditioned for _Res). Outputs: t_hat, symbols / indexes int32 in stream
+ * order, params_out [..][2c] = sigma | mu (may be NULL, symbols may be NULL). */
+int stemb200_ar_encode(const stemb200_ar_desc* d, const float* packed, const float* e0, const float* target,
+                       const float* scale_table, float* t_hat, int32_t* symbols, int32_t* indexes,
+                       float* params_out, void* workspace, void* stream);
+/* streams: the batch's rANS byte strings on the device, image b at [stream_off[b], +stream_len[b]) with 4-byte
+ * aligned offsets; cdfs / cdf_sizes / offsets: the GaussianConditional tables (int32, device).
+ * status[b] = 0, or 1 when stream b is corrupt. */
+int stemb200_ar_decode(const stemb200_ar_desc* d, const float* packed, const float* e0, const float* scale_table,
+                       const uint8_t* streams, const int64_t* stream_off, const int64_t* stream_len,
+                       const int32_t* cdfs, int32_t n_cdfs, int32_t cdf_stride, const int32_t* cdf_sizes,
+                       const int32_t* offsets, float* t_hat, int32_t* symbols, int32_t* indexes, float* params_out,
+                       int32_t* status, void* workspace, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------
  * Host-side helper that the reference implements in C++ (compressai/cpp_exts/ops/ops.cpp:24-81)
  * ------------------------------------------------------------------------------------------------- */
 /* cdf_out must hold pmf_len + 1 entries. */

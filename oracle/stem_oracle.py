@@ -357,3 +357,98 @@ def gaussian_conditional_tables(scale_table: Optional[Tensor] = None, tail_mass:
         c = torch.from_numpy(pmf_to_quantized_cdf(prob.numpy(), 16))
         cdf[i, : c.numel()] = c
     return cdf, -pmf_center, pmf_length + 2
+
+
+# ----------------------------------------------------------------------------------------------------
+# autoregressive coding: the per-position scans of the reference, restated
+# ----------------------------------------------------------------------------------------------------
+def ar_scan(target: Optional[Tensor], priors: Tensor, sd: SD, head: str = "EPM",
+            symbols: Optional[Tensor] = None, table: Optional[Tensor] = None):
+    """_compress_ar (spatiotemporalpriors.py:633-678, _Res :915-961, priors.py:556-600) when ``target`` is given,
+    _decompress_ar (:729-768 / :1016-1055 / priors.py:651-684) when ``symbols`` (1-D, (h, w, c) order) is given.
+    target: (1, C, H, W) quantity being coded (y, or y - y_cond); priors: (1, P, H, W) = cat of the EPM inputs that
+    precede the context features (tp | hp, hp, or h_s(z_hat)). Raster scan, one latent position at a time:
+    5x5 masked-conv crop -> 1x1 head -> (scales, means) -> build_indexes, round(t - mu), t_hat = sym + mu.
+    Returns (t_hat (1, C, H, W), symbols (H*W*C,), indexes (H*W*C,)) in the stream order of the reference."""
+    assert (target is None) != (symbols is None)
+    if table is None:
+        table = get_scale_table()
+    w_ctx, b_ctx = masked_weight(sd), sd["context_prediction.bias"]
+    _, _, H, W = priors.shape
+    C = w_ctx.shape[1]
+    pad = 2
+    t_hat = torch.zeros((1, C, H + 2 * pad, W + 2 * pad))
+    if target is not None:
+        t_hat = F.pad(target, (pad, pad, pad, pad)).clone()
+    sym_out, idx_out = [], []
+    k = 0
+    for h in range(H):
+        for w in range(W):
+            crop = t_hat[:, :, h:h + 5, w:w + 5]
+            ctx_p = F.conv2d(crop, w_ctx, bias=b_ctx)
+            p = priors[:, :, h:h + 1, w:w + 1]
+            g = _seq_conv(torch.cat((p, ctx_p), dim=1), sd, head, [(0, "conv", 1, 0), (2, "conv", 1, 0), (4, "conv", 1, 0)])
+            g = g.squeeze(3).squeeze(2)
+            scales, means = g.chunk(2, 1)
+            idx = build_indexes(scales, table)
+            if target is not None:
+                s = quantize_symbols(crop[:, :, pad, pad], means)
+            else:
+                s = symbols[k:k + C].reshape(1, C).to(torch.int32)
+            k += C
+            t_hat[:, :, h + pad, w + pad] = s.to(means.dtype) + means
+            sym_out.append(s.reshape(-1))
+            idx_out.append(idx.reshape(-1))
+    t_hat = t_hat[:, :, pad:-pad, pad:-pad].contiguous()
+    return t_hat, torch.cat(sym_out).to(torch.int32), torch.cat(idx_out).to(torch.int32)
+
+
+def eb_quantize(z: Tensor, sd: SD, prefix: str = "entropy_bottleneck") -> Tensor:
+    """EntropyBottleneck.compress -> decompress is lossless: z_hat = round(z - median) + median
+    (entropy_models.py:454-471 with the medians of :337-339)."""
+    med = sd[f"{prefix}.quantiles"][:, 0, 1].reshape(1, -1, 1, 1)
+    return torch.round(z - med) + med
+
+
+def stem_ar_code(variant: str, y_cur: Tensor, y_cond: Tensor, sd: SD):
+    """compress() of the SPM variants (spatiotemporalpriors.py:588-631, _Res :871-913, WithoutTPM :311-352):
+    -> dict(y_hat = what decompress() returns, symbols, indexes, z_hat)."""
+    has_tpm = variant != "SpatioTemporalPriorModelWithoutTPM"
+    res = variant == "SpatioTemporalPriorModel_Res"
+    z_hat = eb_quantize(HE(torch.cat([y_cur, y_cond], 1), sd), sd)
+    parts = ([TPM(y_cond, sd)] if has_tpm else []) + [HD(z_hat, sd)]
+    target = y_cur - y_cond if res else y_cur
+    t_hat, sym, idx = ar_scan(target, torch.cat(parts, 1), sd)
+    return {"y_hat": t_hat + y_cond if res else t_hat, "symbols": sym, "indexes": idx, "z_hat": z_hat}
+
+
+def iframe_hyper(y: Tensor, sd: SD) -> Tensor:
+    return _seq_conv(y, sd, "h_a", [(0, "conv", 1, 1), (2, "conv", 2, 2), (4, "conv", 2, 2)])
+
+
+def iframe_hyper_synthesis(z_hat: Tensor, sd: SD) -> Tensor:
+    return _seq_conv(z_hat, sd, "h_s", [(0, "deconv", 2, 2), (2, "deconv", 2, 2), (4, "conv", 1, 1)])
+
+
+def iframe_forward(x: Tensor, sd: SD) -> Dict[str, Tensor]:
+    """JointAutoregressiveHierarchicalPriors.forward, eval mode (priors.py:477-508)."""
+    y = g_a(x, sd)
+    z = iframe_hyper(y, sd)
+    z_hat, z_lik = entropy_bottleneck_forward(z, sd)
+    params = iframe_hyper_synthesis(z_hat, sd)
+    y_hat = quantize_dequantize(y)
+    ctx = context_prediction(y_hat, sd)
+    gp = _seq_conv(torch.cat((params, ctx), 1), sd, "entropy_parameters",
+                   [(0, "conv", 1, 0), (2, "conv", 1, 0), (4, "conv", 1, 0)])
+    scales, means = gp.chunk(2, 1)
+    _, y_lik = gaussian_conditional_forward(y, scales, means)
+    return {"y": y, "y_hat": y_hat, "x_hat": g_s(y_hat, sd, clamp=False), "lik_y": y_lik, "lik_z": z_lik,
+            "scales": scales, "means": means}
+
+
+def iframe_ar_code(x: Tensor, sd: SD):
+    """compress() + decompress() of the I-frame model (priors.py:510-644)."""
+    y = g_a(x, sd)
+    z_hat = eb_quantize(iframe_hyper(y, sd), sd)
+    t_hat, sym, idx = ar_scan(y, iframe_hyper_synthesis(z_hat, sd), sd, head="entropy_parameters")
+    return {"y_hat": t_hat, "x_hat": g_s(t_hat, sd, clamp=True), "symbols": sym, "indexes": idx, "z_hat": z_hat}

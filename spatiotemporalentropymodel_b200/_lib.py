@@ -28,6 +28,13 @@ class ConvDesc(C.Structure):
     ]
 
 
+class ArDesc(C.Structure):
+    """Mirror of ``stemb200_ar_desc``."""
+
+    _fields_ = [("batch", C.c_int32), ("h", C.c_int32), ("w", C.c_int32), ("c", C.c_int32), ("l1", C.c_int32),
+                ("l2", C.c_int32), ("slope", C.c_float), ("n_scales", C.c_int32)]
+
+
 class StemLibError(RuntimeError):
     pass
 
@@ -60,6 +67,11 @@ SIGNATURES = {
                                                   _vp]),
     "stemb200_synthesis_tail": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _vp, _i32, _i32, _i32, _i32, _vp, _i32, _vp]),
     "stemb200_cast_f16_to_f32": (C.c_int, [_vp, _vp, _i64, _vp]),
+    "stemb200_ar_packed_floats": (_i64, [C.POINTER(ArDesc)]),
+    "stemb200_ar_workspace_bytes": (_i64, [C.POINTER(ArDesc)]),
+    "stemb200_ar_encode": (C.c_int, [C.POINTER(ArDesc), _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "stemb200_ar_decode": (C.c_int, [C.POINTER(ArDesc), _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _vp, _vp,
+                                     _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "stemb200_rans_encode_host": (_i64, [_vp, _vp, _i64, _vp, _i32, _i32, _vp, _vp, _vp, _i64]),
     "stemb200_rans_decode_host": (C.c_int, [_vp, _i64, _vp, _i64, _vp, _i32, _i32, _vp, _vp, _vp]),
     "stemb200_pmf_to_quantized_cdf_host": (C.c_int, [C.POINTER(C.c_float), _i32, _i32, C.POINTER(C.c_int32)]),

@@ -1,0 +1,520 @@
+// Autoregressive latent coding of the SPM variants and the I-frame model on the GPU.
+//
+// The reference codes y one latent position at a time on the CPU (spatiotemporalpriors.py:633-678 / :729-768,
+// priors.py:556-600 / :651-684): for every (h, w) in raster order
+//     ctx   = masked 5x5 conv of the already coded y_hat around (h, w)          (12 causal taps x C channels)
+//     g     = EPM(cat(static priors at (h, w), ctx))                           (three 1x1 layers, LeakyReLU)
+//     sigma, mu = chunk(g);  idx = build_indexes(sigma);  sym = round(y - mu);  y_hat(h, w) = sym + mu
+// ~16 s (encode) / ~50 s (decode) per 1080p frame. Here one persistent kernel (64 CTAs, weights resident in shared
+// memory as fp32, software grid barrier between the four layers) runs the same recurrence:
+//   * encode: position (h, w) only needs (h, w-1), (h, w-2) and rows h-1, h-2 up to column w+2, so all positions with
+//     w + 3h = t are independent: W + 3(H-1) wavefront steps instead of H*W, every image of the batch in the same step;
+//     symbols / indexes come out in raster (h, w, c) order, i.e. the order the reference feeds its rANS encoder, and
+//     are coded on the host by stemb200_rans_encode_host (same byte stream format).
+//   * decode: the rANS stream fixes raster order, so one position per image per step; the rANS state machine runs
+//     inside the kernel (one warp per image, 32-ary CDF search with ballots) so no host round trip is needed.
+// The part of the first EPM layer that does not depend on y_hat (temporal prior + hyper prior columns, bias) is a
+// batched GEMM done beforehand by the tcgen05 conv kernel ("e0"). Encoder and decoder execute the same per-position
+// arithmetic in the same order, so the decoder reproduces the encoder's (idx, mu) bit for bit.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdint>
+#include <cstdio>
+
+#include "../../include/stemb200.h"
+#include "internal.h"
+
+namespace stem {
+namespace {
+
+constexpr int kArCtas = 64;
+constexpr int kArThreads = 256;
+constexpr int kArWarps = kArThreads / 32;
+constexpr int kArTaps = 12;  // mask 'A' of a 5x5 kernel: rows 0-1 complete, row 2 columns 0-1 (layers.py:39-42)
+constexpr uint64_t kRansL = 1ull << 31;
+
+struct ArParams {
+  int batch, h, w, c, l1, l2;
+  int rc, r1, r2, rg;  // rows per CTA: 2c/64 (ctx), l1/64, l2/64, c/64 (sigma + mu pairs)
+  int kmax;            // staging vector length: max(12c, 2c, l1, l2)
+  int n_scales, mode;  // mode 0 = encode, 1 = decode
+  float slope;
+  const float* packed;  // per-CTA weight blocks (stemb200_ar_packed_floats / 64 floats each)
+  int block_floats;
+  const float* e0;      // [B][h][w][l1]
+  const float* target;  // encode: [B][h][w][c]
+  const float* table;   // [n_scales]
+  float* t_hat;         // [B][h][w][c]
+  int32_t* sym;         // [B][h][w][c] (may be null)
+  int32_t* idx;         // [B][h][w][c]
+  float* params_out;    // [B][h][w][2c] sigma | mu (may be null)
+  float *ctx_buf, *h1_buf, *h2_buf, *mu_buf;  // scratch [pmax][2c | l1 | l2 | c]
+  unsigned int* sync;   // [0] barrier counter, [1] abort flag (zeroed before launch)
+  const uint8_t* streams;
+  const int64_t* stream_off;  // [B] byte offsets (multiples of 4) into streams
+  const int64_t* stream_len;  // [B] byte lengths
+  const int32_t* cdf;
+  const int32_t* cdf_size;
+  const int32_t* cdf_off;
+  int cdf_stride, n_cdfs;
+  int32_t* status;  // [B] decode status: 0 ok, 1 corrupt stream
+};
+
+__device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+// Sense-free counting barrier over the (co-resident, cooperative launch) grid. Returns false when the kernel must
+// abort (a peer timed out): spinning forever would take the GPU down with it.
+__device__ bool grid_barrier(unsigned int* sync, unsigned int& epoch, int* s_flag) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    epoch += 1;
+    atomicAdd(&sync[0], 1u);
+    const unsigned int target = epoch * gridDim.x;
+    unsigned long long spins = 0;
+    int ok = 1;
+    while (ld_acquire_u32(&sync[0]) < target) {
+      if ((++spins & 1023ull) == 0) {
+        if (ld_acquire_u32(&sync[1]) != 0u) {
+          ok = 0;
+          break;
+        }
+        if (spins > (1ull << 31)) {  // several seconds: something is wrong
+          atomicExch(&sync[1], 1u);
+          ok = 0;
+          break;
+        }
+      }
+    }
+    __threadfence();
+    *s_flag = ok;
+  }
+  __syncthreads();
+  return *s_flag != 0;
+}
+
+// RB dot products of length K against one staged vector, lanes striding K; the result is in every lane.
+template <int RB>
+__device__ __forceinline__ void dot_rows(const float* __restrict__ wrow, int ldw, const float* __restrict__ v, int K,
+                                         int lane, float* out) {
+  float acc[RB];
+#pragma unroll
+  for (int r = 0; r < RB; ++r) acc[r] = 0.f;
+  for (int k = lane; k < K; k += 32) {
+    const float x = v[k];
+#pragma unroll
+    for (int r = 0; r < RB; ++r) acc[r] = fmaf(wrow[r * ldw + k], x, acc[r]);
+  }
+#pragma unroll
+  for (int r = 0; r < RB; ++r) {
+    float a = acc[r];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+    out[r] = a;
+  }
+}
+
+// res[r] = W[r] . v for r < R (lane 0 writes), fixed evaluation order for a given (R, K)
+__device__ __forceinline__ void matvec(const float* W, int R, int K, const float* v, int lane, float* res) {
+  int r = 0;
+  float o[3];
+  while (R - r >= 3) {
+    dot_rows<3>(W + r * K, K, v, K, lane, o);
+    if (lane == 0) {
+      res[r] = o[0];
+      res[r + 1] = o[1];
+      res[r + 2] = o[2];
+    }
+    r += 3;
+  }
+  if (R - r == 2) {
+    dot_rows<2>(W + r * K, K, v, K, lane, o);
+    if (lane == 0) {
+      res[r] = o[0];
+      res[r + 1] = o[1];
+    }
+  } else if (R - r == 1) {
+    dot_rows<1>(W + r * K, K, v, K, lane, o);
+    if (lane == 0) res[r] = o[0];
+  }
+  __syncwarp();
+}
+
+struct Pix {
+  int b, hh, ww;
+  long long g;  // flat position index (b*h + hh)*w + ww
+};
+
+__global__ void __launch_bounds__(kArThreads, 1) ar_codec_kernel(const ArParams p) {
+  extern __shared__ float smem[];
+  __shared__ int s_flag;
+  __shared__ float s_res[kArWarps][16];
+  __shared__ int s_sym[256];  // decode: symbols of one position (c <= 256)
+
+  const int C = p.c, C2 = 2 * p.c, L1 = p.l1, L2 = p.l2;
+  const int KA = kArTaps * C;
+  float* w_ctx = smem;
+  float* b_ctx = w_ctx + p.rc * KA;
+  float* w0 = b_ctx + p.rc;
+  float* w1 = w0 + p.r1 * C2;
+  float* b1 = w1 + p.r2 * L1;
+  float* w2 = b1 + p.r2;
+  float* b2 = w2 + 2 * p.rg * L2;
+  float* vec = smem + ((p.block_floats + 3) & ~3);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int j = blockIdx.x;
+  float* myvec = vec + warp * p.kmax;
+
+  {
+    const float* src = p.packed + static_cast<long long>(j) * p.block_floats;
+    for (int i = threadIdx.x; i < p.block_floats; i += kArThreads) smem[i] = __ldg(src + i);
+  }
+  __syncthreads();
+
+  // rANS decoder state of image j (warp 0 of CTA j < batch), identical in every lane
+  uint64_t rx = 0;
+  long long rpos = 0, rwords = 0;
+  const uint32_t* rstream = nullptr;
+  bool rbad = false;
+  if (p.mode == 1 && j < p.batch && warp == 0) {
+    rstream = reinterpret_cast<const uint32_t*>(p.streams + p.stream_off[j]);
+    rwords = p.stream_len[j] / 4;
+    if (rwords >= 2) {
+      rx = static_cast<uint64_t>(__ldg(rstream)) | (static_cast<uint64_t>(__ldg(rstream + 1)) << 32);
+      rpos = 2;
+    } else {
+      rbad = true;
+    }
+  }
+
+  const int H = p.h, W = p.w;
+  const int n_steps = p.mode == 0 ? (W + 3 * (H - 1)) : H * W;
+  unsigned int epoch = 0;
+
+  for (int t = 0; t < n_steps; ++t) {
+    // ---- positions of this step
+    int lo = 0, nh = 1;
+    if (p.mode == 0) {
+      lo = t - W + 1 > 0 ? (t - W + 1 + 2) / 3 : 0;
+      int hi = t / 3;
+      if (hi > H - 1) hi = H - 1;
+      nh = hi - lo + 1;
+      if (nh < 0) nh = 0;
+    }
+    const int P = p.batch * nh;
+    auto pix = [&](int i) -> Pix {
+      Pix q;
+      if (p.mode == 0) {
+        q.b = i / nh;
+        q.hh = lo + (i - q.b * nh);
+        q.ww = t - 3 * q.hh;
+      } else {
+        q.b = i;
+        q.hh = t / W;
+        q.ww = t - q.hh * W;
+      }
+      q.g = (static_cast<long long>(q.b) * H + q.hh) * W + q.ww;
+      return q;
+    };
+
+    // ---- A: context rows of this CTA
+    for (int i = warp; i < P; i += kArWarps) {
+      const Pix q = pix(i);
+      for (int tap = 0; tap < kArTaps; ++tap) {
+        const int dh = tap < 5 ? -2 : (tap < 10 ? -1 : 0);
+        const int dw = (tap < 5 ? tap : (tap < 10 ? tap - 5 : tap - 10)) - 2;
+        const int h2 = q.hh + dh, w2c = q.ww + dw;
+        const bool inb = h2 >= 0 && w2c >= 0 && w2c < W;
+        const float* src = p.t_hat + ((static_cast<long long>(q.b) * H + h2) * W + w2c) * C;
+        for (int k = lane; k < C; k += 32) myvec[tap * C + k] = inb ? __ldcg(src + k) : 0.f;
+      }
+      __syncwarp();
+      matvec(w_ctx, p.rc, KA, myvec, lane, s_res[warp]);
+      if (lane < p.rc) p.ctx_buf[static_cast<long long>(i) * C2 + j * p.rc + lane] = s_res[warp][lane] + b_ctx[lane];
+      __syncwarp();
+    }
+    if (!grid_barrier(p.sync, epoch, &s_flag)) return;
+
+    // ---- B: first EPM layer, context columns + the precomputed static part
+    for (int i = warp; i < P; i += kArWarps) {
+      const Pix q = pix(i);
+      const float* src = p.ctx_buf + static_cast<long long>(i) * C2;
+      for (int k = lane; k < C2; k += 32) myvec[k] = __ldcg(src + k);
+      __syncwarp();
+      matvec(w0, p.r1, C2, myvec, lane, s_res[warp]);
+      if (lane < p.r1) {
+        float v = s_res[warp][lane] + __ldg(p.e0 + q.g * L1 + j * p.r1 + lane);
+        v = v > 0.f ? v : v * p.slope;
+        p.h1_buf[static_cast<long long>(i) * L1 + j * p.r1 + lane] = v;
+      }
+      __syncwarp();
+    }
+    if (!grid_barrier(p.sync, epoch, &s_flag)) return;
+
+    // ---- C: second EPM layer
+    for (int i = warp; i < P; i += kArWarps) {
+      const float* src = p.h1_buf + static_cast<long long>(i) * L1;
+      for (int k = lane; k < L1; k += 32) myvec[k] = __ldcg(src + k);
+      __syncwarp();
+      matvec(w1, p.r2, L1, myvec, lane, s_res[warp]);
+      if (lane < p.r2) {
+        float v = s_res[warp][lane] + b1[lane];
+        v = v > 0.f ? v : v * p.slope;
+        p.h2_buf[static_cast<long long>(i) * L2 + j * p.r2 + lane] = v;
+      }
+      __syncwarp();
+    }
+    if (!grid_barrier(p.sync, epoch, &s_flag)) return;
+
+    // ---- D: third EPM layer (sigma and mu of this CTA's channels), quantise / index
+    for (int i = warp; i < P; i += kArWarps) {
+      const Pix q = pix(i);
+      const float* src = p.h2_buf + static_cast<long long>(i) * L2;
+      for (int k = lane; k < L2; k += 32) myvec[k] = __ldcg(src + k);
+      __syncwarp();
+      matvec(w2, 2 * p.rg, L2, myvec, lane, s_res[warp]);
+      if (lane < p.rg) {
+        const int ch = j * p.rg + lane;
+        const float sigma = s_res[warp][lane] + b2[lane];
+        const float mu = s_res[warp][p.rg + lane] + b2[p.rg + lane];
+        int cnt = 0;
+        for (int k = 0; k + 1 < p.n_scales; ++k) cnt += (sigma <= __ldg(p.table + k)) ? 1 : 0;
+        const int index = p.n_scales - 1 - cnt;
+        const long long e = q.g * C + ch;
+        p.idx[e] = index;
+        if (p.params_out) {
+          p.params_out[q.g * C2 + ch] = sigma;
+          p.params_out[q.g * C2 + C + ch] = mu;
+        }
+        if (p.mode == 0) {
+          const float s = rintf(__ldg(p.target + e) - mu);  // torch.round: half to even (entropy_models.py:141)
+          p.t_hat[e] = s + mu;
+          if (p.sym) p.sym[e] = static_cast<int>(s);
+        } else {
+          p.mu_buf[static_cast<long long>(i) * C + ch] = mu;
+        }
+      }
+      __syncwarp();
+    }
+    if (!grid_barrier(p.sync, epoch, &s_flag)) return;
+
+    if (p.mode == 1) {
+      // ---- E: rANS decode of this position, image j, by warp 0 (rans_interface.cpp:226-275 semantics)
+      if (j < p.batch && warp == 0) {
+        const Pix q = pix(j);
+        const long long e0i = q.g * C;
+        for (int ch = 0; ch < C; ++ch) {
+          int value = 0;
+          if (!rbad) {
+            const int ci = __ldcg(p.idx + e0i + ch);
+            const int32_t* row = p.cdf + static_cast<long long>(ci) * p.cdf_stride;
+            const int size = __ldg(p.cdf_size + ci);
+            const uint32_t cum = static_cast<uint32_t>(rx & 0xFFFFu);
+            // 32-ary search for s with row[s] <= cum < row[s+1], s in [0, size-2]
+            int slo = 0, n = size - 1;
+            while (n > 1) {
+              const int step = (n + 31) >> 5;
+              const int off = lane * step;
+              const bool pred = off < n && static_cast<uint32_t>(__ldg(row + slo + off)) <= cum;
+              const unsigned int m = __ballot_sync(0xffffffffu, pred);
+              const int k = m ? 31 - __clz(m) : 0;
+              slo += k * step;
+              const int rem = n - k * step;
+              n = rem < step ? rem : step;
+            }
+            const uint32_t start = static_cast<uint32_t>(__ldg(row + slo));
+            const uint32_t freq = static_cast<uint32_t>(__ldg(row + slo + 1)) - start;
+            if (freq == 0 || cum < start || cum >= start + freq) rbad = true;
+            rx = static_cast<uint64_t>(freq) * (rx >> 16) + cum - start;
+            if (rx < kRansL && rpos < rwords) rx = (rx << 32) | __ldg(rstream + rpos++);
+            value = slo;
+            if (slo == size - 2) {
+              // bypass: nibble count (unary in chunks of 15), then the nibbles, least significant first
+              auto get4 = [&]() -> int {
+                const int v = static_cast<int>(rx & 15u);
+                rx >>= 4;
+                if (rx < kRansL && rpos < rwords) rx = (rx << 32) | __ldg(rstream + rpos++);
+                return v;
+              };
+              int v = get4();
+              int n_nib = v;
+              while (v == 15 && n_nib < 64) {
+                v = get4();
+                n_nib += v;
+              }
+              uint32_t raw = 0;
+              for (int k2 = 0; k2 < n_nib; ++k2) raw |= (k2 < 8 ? static_cast<uint32_t>(get4()) << (4 * k2) : (get4(), 0u));
+              value = static_cast<int>(raw >> 1);
+              if (raw & 1u) value = -value - 1;
+              else value += size - 2;
+            }
+            value += __ldg(p.cdf_off + ci);
+          }
+          if (lane == 0) s_sym[ch] = value;
+        }
+        __syncwarp();
+        for (int ch = lane; ch < C; ch += 32) {
+          const int s = s_sym[ch];
+          const float mu = __ldcg(p.mu_buf + static_cast<long long>(j) * C + ch);
+          p.t_hat[e0i + ch] = static_cast<float>(s) + mu;
+          if (p.sym) p.sym[e0i + ch] = s;
+        }
+      }
+      if (!grid_barrier(p.sync, epoch, &s_flag)) return;
+    }
+  }
+  if (p.mode == 1 && j < p.batch && warp == 0 && lane == 0) p.status[j] = rbad ? 1 : 0;
+}
+
+int fill_params(const stemb200_ar_desc* d, ArParams& p) {
+  if (!d) return set_error("ar: null descriptor");
+  if (d->batch < 1 || d->batch > kArCtas || d->h < 1 || d->w < 1) return set_error("ar: bad shape (batch <= 64)");
+  if (d->c < 64 || d->c % 64 || d->c > 256 || d->l1 < 64 || d->l1 % 64 || d->l2 < 64 || d->l2 % 64)
+    return set_error("ar: c (<= 256), l1, l2 must be multiples of 64");
+  if (d->n_scales < 2) return set_error("ar: scale table needs >= 2 entries");
+  p.batch = d->batch;
+  p.h = d->h;
+  p.w = d->w;
+  p.c = d->c;
+  p.l1 = d->l1;
+  p.l2 = d->l2;
+  p.rc = 2 * d->c / kArCtas;
+  p.r1 = d->l1 / kArCtas;
+  p.r2 = d->l2 / kArCtas;
+  p.rg = d->c / kArCtas;
+  if (p.rc > 16 || p.r1 > 16 || p.r2 > 16) return set_error("ar: layer too wide");
+  p.kmax = std::max(std::max(kArTaps * d->c, 2 * d->c), std::max(d->l1, d->l2));
+  p.n_scales = d->n_scales;
+  p.slope = d->slope;
+  p.block_floats = static_cast<int>(stemb200_ar_packed_floats(d) / kArCtas);
+  return 0;
+}
+
+long long pmax_of(const stemb200_ar_desc* d) { return static_cast<long long>(d->batch) * ((d->w + 2) / 3 + 1); }
+
+struct Scratch {
+  float *ctx, *h1, *h2, *mu;
+  unsigned int* sync;
+};
+
+Scratch carve(const stemb200_ar_desc* d, void* ws) {
+  const long long pm = pmax_of(d);
+  float* f = static_cast<float*>(ws);
+  Scratch s;
+  s.sync = reinterpret_cast<unsigned int*>(f);
+  f += 64;
+  s.ctx = f;
+  f += pm * 2 * d->c;
+  s.h1 = f;
+  f += pm * d->l1;
+  s.h2 = f;
+  f += pm * d->l2;
+  s.mu = f;
+  return s;
+}
+
+int launch_ar(ArParams& p, cudaStream_t st) {
+  const size_t smem = (static_cast<size_t>((p.block_floats + 3) & ~3) + static_cast<size_t>(kArWarps) * p.kmax) * 4;
+  if (smem > 227 * 1024) return set_error("ar: weights + staging exceed shared memory");
+  static size_t configured = 0;
+  if (configured < smem) {
+    cudaError_t e = cudaFuncSetAttribute(ar_codec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         static_cast<int>(smem));
+    if (e != cudaSuccess) return set_cuda_error("cudaFuncSetAttribute(ar_codec)", e);
+    configured = smem;
+  }
+  if (num_sms() < kArCtas) return set_error("ar: needs at least 64 SMs (co-resident persistent grid)");
+  cudaError_t e = cudaMemsetAsync(p.sync, 0, 64 * sizeof(float), st);
+  if (e != cudaSuccess) return set_cuda_error("ar: memset", e);
+  void* args[] = {&p};
+  e = cudaLaunchCooperativeKernel(reinterpret_cast<void*>(ar_codec_kernel), dim3(kArCtas), dim3(kArThreads), args, smem,
+                                  st);
+  count_launch();
+  if (e != cudaSuccess) return set_cuda_error("ar_codec launch", e);
+  return 0;
+}
+
+}  // namespace
+}  // namespace stem
+
+using namespace stem;
+
+extern "C" int64_t stemb200_ar_packed_floats(const stemb200_ar_desc* d) {
+  if (!d || d->c < 64 || d->c % 64 || d->l1 % 64 || d->l2 % 64 || d->l1 < 64 || d->l2 < 64) return STEMB200_E_INVALID;
+  const int64_t rc = 2 * d->c / kArCtas, r1 = d->l1 / kArCtas, r2 = d->l2 / kArCtas, rg = d->c / kArCtas;
+  const int64_t per = rc * kArTaps * d->c + rc + r1 * 2 * d->c + r2 * d->l1 + r2 + 2 * rg * d->l2 + 2 * rg;
+  return per * kArCtas;
+}
+
+extern "C" int64_t stemb200_ar_workspace_bytes(const stemb200_ar_desc* d) {
+  if (!d || d->batch < 1 || d->w < 1) return STEMB200_E_INVALID;
+  const long long pm = pmax_of(d);
+  return (64 + pm * (2LL * d->c + d->l1 + d->l2 + d->c)) * 4;
+}
+
+extern "C" int stemb200_ar_encode(const stemb200_ar_desc* d, const float* packed, const float* e0,
+                                  const float* target, const float* scale_table, float* t_hat, int32_t* symbols,
+                                  int32_t* indexes, float* params_out, void* workspace, void* stream) {
+  if (!packed || !e0 || !target || !scale_table || !t_hat || !indexes || !workspace)
+    return set_error("ar_encode: null argument");
+  ArParams p{};
+  if (int rc = fill_params(d, p)) return rc;
+  const Scratch s = carve(d, workspace);
+  p.mode = 0;
+  p.packed = packed;
+  p.e0 = e0;
+  p.target = target;
+  p.table = scale_table;
+  p.t_hat = t_hat;
+  p.sym = symbols;
+  p.idx = indexes;
+  p.params_out = params_out;
+  p.ctx_buf = s.ctx;
+  p.h1_buf = s.h1;
+  p.h2_buf = s.h2;
+  p.mu_buf = s.mu;
+  p.sync = s.sync;
+  return launch_ar(p, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int stemb200_ar_decode(const stemb200_ar_desc* d, const float* packed, const float* e0,
+                                  const float* scale_table, const uint8_t* streams, const int64_t* stream_off,
+                                  const int64_t* stream_len, const int32_t* cdfs, int32_t n_cdfs, int32_t cdf_stride,
+                                  const int32_t* cdf_sizes, const int32_t* offsets, float* t_hat, int32_t* symbols,
+                                  int32_t* indexes, float* params_out, int32_t* status, void* workspace,
+                                  void* stream) {
+  if (!packed || !e0 || !scale_table || !streams || !stream_off || !stream_len || !cdfs || !cdf_sizes || !offsets ||
+      !t_hat || !indexes || !status || !workspace || n_cdfs < 1 || cdf_stride < 2)
+    return set_error("ar_decode: null / bad argument");
+  ArParams p{};
+  if (int rc = fill_params(d, p)) return rc;
+  const Scratch s = carve(d, workspace);
+  p.mode = 1;
+  p.packed = packed;
+  p.e0 = e0;
+  p.table = scale_table;
+  p.t_hat = t_hat;
+  p.sym = symbols;
+  p.idx = indexes;
+  p.params_out = params_out;
+  p.ctx_buf = s.ctx;
+  p.h1_buf = s.h1;
+  p.h2_buf = s.h2;
+  p.mu_buf = s.mu;
+  p.sync = s.sync;
+  p.streams = streams;
+  p.stream_off = stream_off;
+  p.stream_len = stream_len;
+  p.cdf = cdfs;
+  p.cdf_size = cdf_sizes;
+  p.cdf_off = offsets;
+  p.cdf_stride = cdf_stride;
+  p.n_cdfs = n_cdfs;
+  p.status = status;
+  return launch_ar(p, static_cast<cudaStream_t>(stream));
+}

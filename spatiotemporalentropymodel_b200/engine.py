@@ -18,7 +18,7 @@ import torch
 import torch.nn.functional as F
 
 from . import _lib
-from ._lib import DT_F16, DT_F32, EPI_ADD, EPI_LINEAR, EPI_SFT, ConvDesc
+from ._lib import DT_F16, DT_F32, EPI_ADD, EPI_LINEAR, EPI_SFT, ArDesc, ConvDesc
 
 Tensor = torch.Tensor
 MASK_A_5x5 = 0x00000FFF  # taps (r, s) with r < 2, or r == 2 and s < 2 (layers/layers.py:39-42)
@@ -222,6 +222,117 @@ def gaussian_conditional_flat(y: Tensor, scales: Tensor, means: Optional[Tensor]
 
 
 # ------------------------------------------------------------------------------------------------------
+# autoregressive coding head (context_prediction + the three 1x1 layers) for compress() / decompress()
+# ------------------------------------------------------------------------------------------------------
+AR_CTAS = 64
+AR_TAPS = [(r, s_) for r in range(3) for s_ in range(5) if r < 2 or s_ < 2]  # mask 'A' order (layers.py:39-42)
+
+
+class ArHead:
+    """spatiotemporalpriors.py:633-678 / :729-768 and priors.py:556-600 / :651-684 on the persistent AR kernel
+    (csrc/ar_codec.cu). The prior columns of the first 1x1 layer are a batched GEMM ("e0", tcgen05 conv kernel);
+    context_prediction and the rest of the head run per latent position inside the kernel, fp32."""
+
+    def __init__(self, w_ctx: Tensor, b_ctx: Tensor, layers: Sequence[Tuple[Tensor, Tensor]], static_c: Sequence[int],
+                 device: torch.device, slope: float = 0.01):
+        f = lambda t: t.detach().to(device, torch.float32)
+        w_ctx, b_ctx = f(w_ctx), f(b_ctx)
+        (w0, b0), (w1, b1), (w2, b2) = [(f(w).flatten(1), f(b)) for w, b in layers]
+        C2, C = w_ctx.shape[0], w_ctx.shape[1]
+        L1, L2 = w0.shape[0], w1.shape[0]
+        n_static = sum(static_c)
+        if w0.shape[1] != n_static + C2 or w2.shape[0] != C2:
+            raise ValueError("ArHead: inconsistent layer shapes")
+        self.C, self.L1, self.L2, self.slope = C, L1, L2, float(slope)
+        self.device = device
+        self.lib = _lib.load()
+        # e0 = W0[:, :n_static] . priors + b0, no activation, fp32 (the context columns are added per position)
+        self.e0_conv = ConvOp(w0[:, :n_static].reshape(L1, n_static, 1, 1).contiguous(), b0, c_in=list(static_c),
+                              c_out=L1, k=1, out_dtype=DT_F32)
+        rc, r1, r2, rg = C2 // AR_CTAS, L1 // AR_CTAS, L2 // AR_CTAS, C // AR_CTAS
+        wc = torch.stack([w_ctx[:, :, r, s_] for r, s_ in AR_TAPS], dim=1).reshape(C2, len(AR_TAPS) * C)
+        blocks = torch.cat([
+            wc.reshape(AR_CTAS, rc * wc.shape[1]), b_ctx.reshape(AR_CTAS, rc),
+            w0[:, n_static:].reshape(AR_CTAS, r1 * C2),
+            w1.reshape(AR_CTAS, r2 * L1), b1.reshape(AR_CTAS, r2),
+            w2[:C].reshape(AR_CTAS, rg * L2), w2[C:].reshape(AR_CTAS, rg * L2),
+            b2[:C].reshape(AR_CTAS, rg), b2[C:].reshape(AR_CTAS, rg)], dim=1).contiguous()
+        self.packed = blocks
+        self._ws: Dict[Tuple[int, int, int], Tensor] = {}
+
+    def _desc(self, B: int, h: int, w: int, n_scales: int) -> ArDesc:
+        d = ArDesc()
+        d.batch, d.h, d.w, d.c, d.l1, d.l2, d.slope, d.n_scales = B, h, w, self.C, self.L1, self.L2, self.slope, n_scales
+        want = self.lib.stemb200_ar_packed_floats(C.byref(d))
+        if want != self.packed.numel():
+            raise _lib.StemLibError(f"AR weight block mismatch: packed {self.packed.numel()} floats, kernel wants {want}")
+        return d
+
+    def _workspace(self, d: ArDesc) -> Tensor:
+        n = int(self.lib.stemb200_ar_workspace_bytes(C.byref(d)))
+        if n <= 0:
+            _lib.check(n, "ar_workspace_bytes")
+        key = (d.batch, d.h, d.w)
+        if key not in self._ws:
+            self._ws[key] = torch.empty(n, dtype=torch.uint8, device=self.device)
+        return self._ws[key]
+
+    def static_part(self, priors: Sequence[Tensor], B: int, h: int, w: int) -> Tensor:
+        out = torch.empty((B, h, w, self.L1), dtype=torch.float32, device=self.device)
+        return self.e0_conv(list(priors), B, h, w, out)
+
+    def encode(self, target_nhwc: Tensor, priors: Sequence[Tensor], table: Tensor):
+        """target (B, h, w, C) fp32 NHWC -> t_hat, symbols, indexes (stream order), params (sigma | mu)."""
+        B, h, w, _ = target_nhwc.shape
+        d = self._desc(B, h, w, table.numel())
+        e0 = self.static_part(priors, B, h, w)
+        dev = self.device
+        t_hat = torch.empty_like(target_nhwc)
+        sym = torch.empty(target_nhwc.shape, dtype=torch.int32, device=dev)
+        idx = torch.empty(target_nhwc.shape, dtype=torch.int32, device=dev)
+        params = torch.empty((B, h, w, 2 * self.C), dtype=torch.float32, device=dev)
+        _lib.check(self.lib.stemb200_ar_encode(C.byref(d), self.packed.data_ptr(), e0.data_ptr(), target_nhwc.data_ptr(),
+                                               table.data_ptr(), t_hat.data_ptr(), sym.data_ptr(), idx.data_ptr(),
+                                               params.data_ptr(), self._workspace(d).data_ptr(), _stream()), "ar_encode")
+        return t_hat, sym, idx, params
+
+    def decode(self, strings: Sequence[bytes], priors: Sequence[Tensor], B: int, h: int, w: int, table: Tensor,
+               cdf: Tensor, cdf_length: Tensor, offset: Tensor):
+        """-> t_hat (B, h, w, C) fp32 NHWC, params (sigma | mu). Raises on a corrupt stream."""
+        import numpy as np
+        if len(strings) != B:
+            raise ValueError("one string per batch element expected")
+        d = self._desc(B, h, w, table.numel())
+        e0 = self.static_part(priors, B, h, w)
+        dev = self.device
+        offs, lens, pos = [], [], 0
+        for s_ in strings:
+            if len(s_) % 4 or len(s_) < 8:
+                raise ValueError("rANS strings are whole 32-bit words (>= 2)")
+            offs.append(pos)
+            lens.append(len(s_))
+            pos += len(s_)
+        blob = torch.from_numpy(np.frombuffer(b"".join(strings), dtype=np.uint8).copy()).to(dev)
+        t_off = torch.tensor(offs, dtype=torch.int64, device=dev)
+        t_len = torch.tensor(lens, dtype=torch.int64, device=dev)
+        cdf_d = cdf.detach().to(dev, torch.int32).contiguous()
+        len_d = cdf_length.detach().to(dev, torch.int32).contiguous()
+        off_d = offset.detach().to(dev, torch.int32).contiguous()
+        t_hat = torch.empty((B, h, w, self.C), dtype=torch.float32, device=dev)
+        idx = torch.empty((B, h, w, self.C), dtype=torch.int32, device=dev)
+        params = torch.empty((B, h, w, 2 * self.C), dtype=torch.float32, device=dev)
+        status = torch.zeros(B, dtype=torch.int32, device=dev)
+        _lib.check(self.lib.stemb200_ar_decode(
+            C.byref(d), self.packed.data_ptr(), e0.data_ptr(), table.data_ptr(), blob.data_ptr(), t_off.data_ptr(),
+            t_len.data_ptr(), cdf_d.data_ptr(), cdf_d.shape[0], cdf_d.shape[1], len_d.data_ptr(), off_d.data_ptr(),
+            t_hat.data_ptr(), None, idx.data_ptr(), params.data_ptr(), status.data_ptr(),
+            self._workspace(d).data_ptr(), _stream()), "ar_decode")
+        if int(status.max().item()) != 0:
+            raise _lib.StemLibError("ar_decode: corrupt rANS stream")
+        return t_hat, params
+
+
+# ------------------------------------------------------------------------------------------------------
 # g_a / g_s of the I-frame model (mbt2018), the transforms a P-frame goes through
 # ------------------------------------------------------------------------------------------------------
 def _gdn_fold(beta_p: Tensor, gamma_p: Tensor) -> Tuple[Tensor, Tensor]:
@@ -324,7 +435,7 @@ class TransformsEngine:
 
     def synthesis(self, y_hat16: Tensor, x_ref: Optional[Tensor] = None,
                   pad: Tuple[int, int, int, int] = (0, 0, 0, 0), sq_err: Optional[Tensor] = None,
-                  out: Optional[Tensor] = None) -> Tensor:
+                  out: Optional[Tensor] = None, clamp: bool = True) -> Tensor:
         """y_hat16: (B, h, w, M) fp16 NHWC -> x_hat (B, 3, 16h, 16w) fp32 NCHW clamped to [0, 1]; when x_ref
         (unpadded frames) is given, sq_err[b] += sum((x_ref - crop(x_hat))^2)."""
         B, h, w, _ = y_hat16.shape
@@ -345,7 +456,7 @@ class TransformsEngine:
         if x_ref is not None:
             href, wref = x_ref.shape[2], x_ref.shape[3]
         _lib.check(lib.stemb200_synthesis_tail(merged.data_ptr(), out.data_ptr(), B, h // 2, w // 2, _ptr(x_ref), href,
-                                               wref, top, left, _ptr(sq_err), 1, _stream()), "synthesis_tail")
+                                               wref, top, left, _ptr(sq_err), int(clamp), _stream()), "synthesis_tail")
         return out
 
 
@@ -397,6 +508,11 @@ class StemEngine:
             ConvOp(g("EPM.2.weight"), g("EPM.2.bias"), c_in=[768], c_out=576, k=1, slope=lre),
             ConvOp(g("EPM.4.weight"), g("EPM.4.bias"), c_in=[576], c_out=C2, k=1, out_dtype=DT_F32),
         ]
+        self._ar = None
+        if has_spm:
+            self._ar_spec = (g("context_prediction.weight") * g("context_prediction.mask"), g("context_prediction.bias"),
+                             [(g(f"EPM.{i}.weight"), g(f"EPM.{i}.bias")) for i in (0, 2, 4)],
+                             [C2] * (1 + int(has_tpm)))
         self.eb_params = eb_packed.detach().to(dev, torch.float32).contiguous()
         self.scale_table = None if scale_table is None or scale_table.numel() == 0 else \
             scale_table.detach().to(dev, torch.float32).contiguous()
@@ -409,18 +525,19 @@ class StemEngine:
         if h % 4 or w % 4:
             raise ValueError("latent height/width must be multiples of 4 (two stride-2 stages in HE/HD)")
         h2, w2, h4, w4 = h // 2, w // 2, h // 4, w // 4
-        t1 = self.he[0]([y16, cond16], B, h, w, ws.get("he1", (B, h, w, 256), f16))
-        t2 = self.he[1]([t1], B, h, w, ws.get("he2", (B, h2, w2, 256), f16))
+        srcs = [y16, cond16] if len(self.he[0].c_in) == 2 else [y16]
+        t1 = self.he[0](srcs, B, h, w, ws.get("he1", (B, h, w, self.he[0].c_out), f16))
+        t2 = self.he[1]([t1], B, h, w, ws.get("he2", (B, h2, w2, self.he[1].c_out), f16))
         return self.he[2]([t2], B, h2, w2, ws.get("z", (B, h4, w4, self.zc), f32))
 
-    def params_from_zhat(self, zhat16: Tensor, cond16: Tensor, yq16: Optional[Tensor], B: int, h: int,
-                         w: int) -> Tensor:
-        """HD(z_hat), TPM(y_cond), context(y_q), EPM -> (scales | means) NHWC fp32 (B, h, w, 2C)  (:564-577)."""
+    def static_priors(self, zhat16: Tensor, cond16: Optional[Tensor], B: int, h: int, w: int) -> List[Tensor]:
+        """[TPM(y_cond)] + [HD(z_hat)]: the EPM inputs that do not depend on the frame's own y_hat, NHWC fp16."""
         ws = self.ws
-        f16, f32 = torch.float16, torch.float32
+        f16 = torch.float16
         h2, w2, h4, w4 = h // 2, w // 2, h // 4, w // 4
-        d1 = self.hd[0]([zhat16], B, h4, w4, ws.get("hd1", (B, h2, w2, 256), f16))
-        d2 = self.hd[1]([d1], B, h2, w2, ws.get("hd2", (B, h, w, 256), f16))
+        c1, c2 = self.hd[0].c_out, self.hd[1].c_out
+        d1 = self.hd[0]([zhat16], B, h4, w4, ws.get("hd1", (B, h2, w2, c1), f16))
+        d2 = self.hd[1]([d1], B, h2, w2, ws.get("hd2", (B, h, w, c2), f16))
         hp = self.hd[2]([d2], B, h, w, ws.get("hp", (B, h, w, 2 * self.C), f16))
         srcs: List[Tensor] = []
         if self.has_tpm:
@@ -428,10 +545,26 @@ class StemEngine:
             p2 = self.tpm[1]([p1], B, h, w, ws.get("tp2", (B, h, w, 320), f16))
             srcs.append(self.tpm[2]([p2], B, h, w, ws.get("tp", (B, h, w, 2 * self.C), f16)))
         srcs.append(hp)
+        return srcs
+
+    def ar_head(self) -> "ArHead":
+        if not self.has_spm:
+            raise RuntimeError("this variant has no spatial context model")
+        if self._ar is None:
+            self._ar = ArHead(*self._ar_spec, device=self.device)
+        return self._ar
+
+    def params_from_zhat(self, zhat16: Tensor, cond16: Tensor, yq16: Optional[Tensor], B: int, h: int,
+                         w: int) -> Tensor:
+        """HD(z_hat), TPM(y_cond), context(y_q), EPM -> (scales | means) NHWC fp32 (B, h, w, 2C)  (:564-577)."""
+        ws = self.ws
+        f16, f32 = torch.float16, torch.float32
+        h2, w2, h4, w4 = h // 2, w // 2, h // 4, w // 4
+        srcs = self.static_priors(zhat16, cond16, B, h, w)
         if self.has_spm:
             srcs.append(self.ctx([yq16], B, h, w, ws.get("ctx", (B, h, w, 2 * self.C), f16)))
-        e1 = self.epm[0](srcs, B, h, w, ws.get("e1", (B, h, w, 768), f16))
-        e2 = self.epm[1]([e1], B, h, w, ws.get("e2", (B, h, w, 576), f16))
+        e1 = self.epm[0](srcs, B, h, w, ws.get("e1", (B, h, w, self.epm[0].c_out), f16))
+        e2 = self.epm[1]([e1], B, h, w, ws.get("e2", (B, h, w, self.epm[1].c_out), f16))
         return self.epm[2]([e2], B, h, w, ws.get("gparams", (B, h, w, 2 * self.C), f32))
 
     def gaussian_params(self, y16: Tensor, cond16: Tensor, yq16: Optional[Tensor], B: int, h: int, w: int,
@@ -492,6 +625,56 @@ class StemEngine:
         self.gaussian_conditional(y_cur, True, cond16, params, B, h, w, y_hat, y_lik, idx, sym, bits[0])
         return {"y_hat": y_hat, "likelihoods": {"y": y_lik, "z": z_lik}, "z_hat": z_hat, "bits": bits,
                 "indexes": idx, "symbols": sym, "params_nhwc": params}
+
+
+class IFrameEntropyEngine(StemEngine):
+    """h_a / h_s / context_prediction / entropy_parameters of JointAutoregressiveHierarchicalPriors
+    (priors.py:441-470): the STEM WithoutTPM topology without a conditioning latent and with the mbt2018 widths
+    (N, N, N | M, 3M/2, 2M | 4M -> 10M/3 -> 8M/3 -> 2M). h_s.2's 3M/2 = 288 outputs are zero-padded to 320 so that
+    they tile the 160-wide MMA N block."""
+
+    def __init__(self, sd: Dict[str, Tensor], device: torch.device, eb_packed: Tensor, scale_table: Optional[Tensor],
+                 scale_bound: float = 0.11, lik_bound: float = 1e-9):
+        dev = device
+        g = lambda k: sd[k].detach().to(dev, torch.float32)
+        self.device = dev
+        self.ws = Workspace(dev)
+        self.has_tpm, self.has_spm, self.residual = False, True, False
+        self.scale_bound, self.lik_bound = float(scale_bound), float(lik_bound)
+        N = sd["h_a.0.weight"].shape[0]
+        M = sd["h_a.0.weight"].shape[1]
+        self.C, self.zc = M, N
+        C2 = 2 * M
+        lre = 0.01
+        self.he = [
+            ConvOp(g("h_a.0.weight"), g("h_a.0.bias"), c_in=[M], c_out=N, k=3, slope=lre),
+            ConvOp(g("h_a.2.weight"), g("h_a.2.bias"), c_in=[N], c_out=N, k=5, stride=2, slope=lre),
+            ConvOp(g("h_a.4.weight"), g("h_a.4.bias"), c_in=[N], c_out=N, k=5, stride=2, out_dtype=DT_F32),
+        ]
+        mid = sd["h_s.2.weight"].shape[1]  # 3M/2
+        mid_p = (mid + 63) // 64 * 64 if mid % 64 else mid
+        w2 = F.pad(g("h_s.2.weight"), (0, 0, 0, 0, 0, mid_p - mid))      # ConvTranspose: (in, out, kh, kw)
+        b2 = F.pad(g("h_s.2.bias"), (0, mid_p - mid))
+        w4 = F.pad(g("h_s.4.weight"), (0, 0, 0, 0, 0, mid_p - mid, 0, 0))  # Conv: (out, in, kh, kw)
+        self.hd = [
+            ConvOp(g("h_s.0.weight"), g("h_s.0.bias"), c_in=[N], c_out=M, k=5, stride=2, transposed=True, slope=lre),
+            ConvOp(w2.contiguous(), b2, c_in=[M], c_out=mid_p, k=5, stride=2, transposed=True, slope=lre),
+            ConvOp(w4.contiguous(), g("h_s.4.bias"), c_in=[mid_p], c_out=C2, k=3),
+        ]
+        self.ctx = ConvOp(g("context_prediction.weight"), g("context_prediction.bias"), c_in=[M], c_out=C2, k=5,
+                          tap_mask=MASK_A_5x5)
+        ep = [(g(f"entropy_parameters.{i}.weight"), g(f"entropy_parameters.{i}.bias")) for i in (0, 2, 4)]
+        self.epm = [
+            ConvOp(ep[0][0], ep[0][1], c_in=[C2, C2], c_out=ep[0][0].shape[0], k=1, slope=lre),
+            ConvOp(ep[1][0], ep[1][1], c_in=[ep[0][0].shape[0]], c_out=ep[1][0].shape[0], k=1, slope=lre),
+            ConvOp(ep[2][0], ep[2][1], c_in=[ep[1][0].shape[0]], c_out=C2, k=1, out_dtype=DT_F32),
+        ]
+        self._ar = None
+        self._ar_spec = (g("context_prediction.weight") * g("context_prediction.mask"), g("context_prediction.bias"),
+                         ep, [C2])
+        self.eb_params = eb_packed.detach().to(dev, torch.float32).contiguous()
+        self.scale_table = None if scale_table is None or scale_table.numel() == 0 else \
+            scale_table.detach().to(dev, torch.float32).contiguous()
 
 
 def pad64(h: int, w: int) -> Tuple[int, int, int, int]:

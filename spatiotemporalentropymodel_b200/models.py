@@ -15,7 +15,8 @@ from typing import Dict, Optional
 import torch
 import torch.nn as nn
 
-from .engine import PFramePipeline, StemEngine, TransformsEngine, _require_cuda
+from . import _lib
+from .engine import IFrameEntropyEngine, PFramePipeline, StemEngine, TransformsEngine, _require_cuda
 from .entropy_models import EntropyBottleneck, GaussianConditional
 from .synthetic import variant_flags
 
@@ -200,19 +201,10 @@ class _StemBase(CompressionModel):
         entropy_models.py:598-604) and symbols round(y - mu) (:148-150), from the same fused kernel."""
         return self.engine().forward_nchw(y_cur, y_conditioned, want_indexes=True)
 
-    def _no_ar(self, what: str):
-        if self._flags[1]:
-            raise NotImplementedError(
-                f"{what}(): this variant codes y autoregressively (spatiotemporalpriors.py:633-678, :729-768: a "
-                "sequential scan over the latent grid); the wavefront-parallel coder is SURVEY.md §8f rank 2. "
-                "forward_with_indexes() returns the symbols and CDF indexes; the WithoutSPM* variants and the "
-                "entropy models themselves do compress / decompress")
-
     def compress(self, y_cur: Tensor, y_conditioned: Tensor):
         """Non-autoregressive variants (spatiotemporalpriors.py:86-96, :197-209):
         -> {"strings": [y_strings, z_strings], "shape": z.size()[-2:]}. Symbols and CDF indexes come from the
         fused GaussianConditional kernel; the rANS coder is the C ABI's (byte-compatible with compressai.ans)."""
-        self._no_ar("compress")
         from .engine import nchw_to_nhwc_f16, nhwc_f32_to_nchw
         eng = self.engine()
         _require_cuda(y_cur, y_conditioned)
@@ -226,6 +218,15 @@ class _StemBase(CompressionModel):
         z_strings = self.entropy_bottleneck.compress(z)
         z_hat = self.entropy_bottleneck.decompress(z_strings, z.size()[-2:])
         zhat16 = nchw_to_nhwc_f16(z_hat.contiguous(), eng.ws.get("zhat16", (B, h // 4, w // 4, eng.zc), f16))
+        if self._flags[1]:
+            # autoregressive variants (spatiotemporalpriors.py:588-678, _Res :871-961): wavefront kernel over the
+            # latent grid, symbols / indexes in the reference's raster (h, w, c) stream order
+            priors = eng.static_priors(zhat16, cond16, B, h, w)
+            target = (y_cur - y_conditioned) if self._flags[2] else y_cur
+            target = target.permute(0, 2, 3, 1).contiguous()
+            _, sym, idx, _ = eng.ar_head().encode(target, priors, eng.scale_table)
+            y_strings = self.gaussian_conditional.compress_symbols(sym, idx)
+            return {"strings": [y_strings, z_strings], "shape": z.size()[-2:]}
         params = eng.params_from_zhat(zhat16, cond16, None, B, h, w)
         idx = torch.empty(y_cur.shape, dtype=torch.int32, device=y_cur.device)
         sym = torch.empty(y_cur.shape, dtype=torch.int32, device=y_cur.device)
@@ -236,7 +237,6 @@ class _StemBase(CompressionModel):
     def decompress(self, strings, shape, y_conditioned: Tensor):
         """Non-autoregressive variants (spatiotemporalpriors.py:99-111, :212-225). Returns a dict with "y_hat" and
         "entropy_params" (what stem/evalSTEM.py:120,152 reads; the reference returns the bare tensor)."""
-        self._no_ar("decompress")
         assert isinstance(strings, list) and len(strings) == 2
         from .engine import nchw_to_nhwc_f16
         eng = self.engine()
@@ -247,6 +247,19 @@ class _StemBase(CompressionModel):
         z_hat = self.entropy_bottleneck.decompress(strings[1], shape).to(y_conditioned.device)
         cond16 = nchw_to_nhwc_f16(y_conditioned, eng.ws.get("cond16", (B, h, w, C), f16))
         zhat16 = nchw_to_nhwc_f16(z_hat.contiguous(), eng.ws.get("zhat16", (B, h // 4, w // 4, eng.zc), f16))
+        if self._flags[1]:
+            # autoregressive variants (spatiotemporalpriors.py:681-768, _Res :964-1055): raster-order kernel with the
+            # rANS decoder inside; the decoder repeats the encoder's arithmetic, so (idx, mu) match bit for bit
+            gc = self.gaussian_conditional
+            priors = eng.static_priors(zhat16, cond16, B, h, w)
+            t_hat, params = eng.ar_head().decode(strings[0], priors, B, h, w, eng.scale_table, gc.quantized_cdf,
+                                                 gc.cdf_length, gc.offset)
+            y_hat = t_hat.permute(0, 3, 1, 2).contiguous()
+            if self._flags[2]:
+                y_hat = y_hat + y_conditioned
+            gp = params.permute(0, 3, 1, 2)
+            return {"y_hat": y_hat, "entropy_params": {"scales_hat": gp[:, :C].contiguous(),
+                                                       "means_hat": gp[:, C:].contiguous()}}
         params = eng.params_from_zhat(zhat16, cond16, None, B, h, w)
         idx = torch.empty(y_conditioned.shape, dtype=torch.int32, device=y_conditioned.device)
         eng.gaussian_conditional(torch.zeros_like(y_conditioned), True, None, params, B, h, w, None, None, idx, None)
@@ -318,6 +331,12 @@ class JointAutoregressiveHierarchicalPriors(CompressionModel):
             nn.Conv2d(M * 8 // 3, M * 6 // 3, 1))
         self.context_prediction = MaskedConv2d(M, 2 * M, kernel_size=5, padding=2, stride=1)
         self.N, self.M = int(N), int(M)
+        self._entropy_engine = None
+        self._entropy_engine_src = None
+
+    @property
+    def downsampling_factor(self) -> int:
+        return 2 ** (4 + 2)
 
     def engine(self) -> TransformsEngine:
         dev = self._device()
@@ -347,15 +366,91 @@ class JointAutoregressiveHierarchicalPriors(CompressionModel):
         out = torch.empty((B, 3, 16 * h, 16 * w), dtype=torch.float32, device=y_hat.device)
         return eng.synthesis(y16, out=out)
 
+    def entropy_engine(self) -> IFrameEntropyEngine:
+        """h_a / h_s / context_prediction / entropy_parameters + EntropyBottleneck on the CUDA kernels."""
+        dev = self._device()
+        if dev.type != "cuda":
+            raise RuntimeError("the I-frame model of spatiotemporalentropymodel_b200 runs on CUDA only")
+        tr = self.engine()
+        if self._entropy_engine is None or self._entropy_engine_src is not tr:  # rebuilt after load / update / .to()
+            self._entropy_engine_src = tr
+            gc = self.gaussian_conditional
+            self._entropy_engine = IFrameEntropyEngine(
+                dict(self.state_dict()), dev, self.entropy_bottleneck.packed_params(), gc.scale_table,
+                scale_bound=float(gc.lower_bound_scale.bound.item()),
+                lik_bound=float(gc.likelihood_lower_bound.bound.item()))
+        return self._entropy_engine
+
+    def _latents(self, x: Tensor):
+        """g_a(x) as NHWC fp32 + fp16 copies; x must have sides that are multiples of 64 (downsampling_factor)."""
+        _require_cuda(x)
+        if x.shape[2] % 64 or x.shape[3] % 64:
+            raise ValueError("the I-frame model needs frame sides that are multiples of 64 (priors.py:473-475)")
+        eng, ee = self.engine(), self.entropy_engine()
+        y32, h, w = eng.analysis(x.float())
+        B = x.shape[0]
+        lib = _lib.load()
+        y16 = ee.ws.get("y16", (B, h, w, self.M), torch.float16)
+        yq16 = ee.ws.get("yq16", (B, h, w, self.M), torch.float16)
+        _lib.check(lib.stemb200_latent_stage(y32.data_ptr(), None, y16.data_ptr(), yq16.data_ptr(), None, y32.numel(),
+                                             torch.cuda.current_stream().cuda_stream), "latent_stage")
+        return y32, y16, yq16, B, h, w
+
     def forward(self, x):
-        raise NotImplementedError("I-frame coding (priors.py:477-508) is outside the P-frame hot path "
-                                  "(SURVEY.md §8f rank 3)")
+        """priors.py:477-508 (eval mode): -> {"y", "y_hat", "x_hat", "likelihoods", "entropy_params"};
+        y_hat = round(y), likelihoods of y at (sigma, mu) from the context of round(y), x_hat = g_s(y_hat)."""
+        if self.training:
+            raise NotImplementedError("training-mode forward is outside the inference path of this build; call .eval()")
+        from .engine import nhwc_f32_to_nchw
+        eng, ee = self.engine(), self.entropy_engine()
+        y32, y16, yq16, B, h, w = self._latents(x)
+        dev = x.device
+        zc, h4, w4 = ee.zc, h // 4, w // 4
+        z_lik = torch.empty((B, zc, h4, w4), dtype=torch.float32, device=dev)
+        bits = torch.zeros((2, B), dtype=torch.float64, device=dev)
+        params = ee.gaussian_params(y16, None, yq16, B, h, w, None, z_lik, bits[1])
+        y_hat = torch.empty((B, self.M, h, w), dtype=torch.float32, device=dev)
+        y_lik = torch.empty_like(y_hat)
+        ee.gaussian_conditional(y32, False, None, params, B, h, w, y_hat, y_lik, bits=bits[0])
+        y = nhwc_f32_to_nchw(y32, torch.empty_like(y_hat))
+        x_hat = torch.empty((B, 3, 16 * h, 16 * w), dtype=torch.float32, device=dev)
+        eng.synthesis(yq16, out=x_hat, clamp=False)
+        gp = params.permute(0, 3, 1, 2)
+        return {"y": y, "y_hat": y_hat, "x_hat": x_hat, "likelihoods": {"y": y_lik, "z": z_lik},
+                "entropy_params": {"scales_hat": gp[:, :self.M].contiguous(), "means_hat": gp[:, self.M:].contiguous()}}
 
     def compress(self, x):
-        raise NotImplementedError("I-frame compress (priors.py:510-600): SURVEY.md §8f rank 3")
+        """priors.py:510-600 -> {"strings": [y_strings, z_strings], "shape": z.size()[-2:]}; the per-position scan
+        (:556-600) runs as wavefronts on the GPU (csrc/ar_codec.cu)."""
+        from .engine import nchw_to_nhwc_f16, nhwc_f32_to_nchw
+        ee = self.entropy_engine()
+        y32, y16, _, B, h, w = self._latents(x)
+        z_nhwc = ee.hyper_latent(y16, None, B, h, w)
+        z = nhwc_f32_to_nchw(z_nhwc, torch.empty((B, ee.zc, h // 4, w // 4), device=x.device))
+        z_strings = self.entropy_bottleneck.compress(z)
+        z_hat = self.entropy_bottleneck.decompress(z_strings, z.size()[-2:])
+        zhat16 = nchw_to_nhwc_f16(z_hat.contiguous(), ee.ws.get("zhat16", (B, h // 4, w // 4, ee.zc), torch.float16))
+        priors = ee.static_priors(zhat16, None, B, h, w)
+        _, sym, idx, _ = ee.ar_head().encode(y32, priors, ee.scale_table)
+        y_strings = self.gaussian_conditional.compress_symbols(sym, idx)
+        return {"strings": [y_strings, z_strings], "shape": z.size()[-2:]}
 
     def decompress(self, strings, shape):
-        raise NotImplementedError("I-frame decompress (priors.py:602-644): SURVEY.md §8f rank 3")
+        """priors.py:602-644 -> {"x_hat" (clamped), "y_hat"}; raster-order GPU scan with the rANS decoder inside."""
+        from .engine import nchw_to_nhwc_f16
+        assert isinstance(strings, list) and len(strings) == 2
+        eng, ee = self.engine(), self.entropy_engine()
+        dev = self._device()
+        gc = self.gaussian_conditional
+        z_hat = self.entropy_bottleneck.decompress(strings[1], shape).to(dev)
+        B, _, h4, w4 = z_hat.shape
+        h, w = 4 * h4, 4 * w4
+        zhat16 = nchw_to_nhwc_f16(z_hat.contiguous(), ee.ws.get("zhat16", (B, h4, w4, ee.zc), torch.float16))
+        priors = ee.static_priors(zhat16, None, B, h, w)
+        t_hat, _ = ee.ar_head().decode(strings[0], priors, B, h, w, ee.scale_table, gc.quantized_cdf, gc.cdf_length,
+                                       gc.offset)
+        y_hat = t_hat.permute(0, 3, 1, 2).contiguous()
+        return {"x_hat": self.getX(y_hat), "y_hat": y_hat}
 
     def load_state_dict(self, state_dict, strict: bool = True):
         _resize_registered_buffers(self.gaussian_conditional, "gaussian_conditional",

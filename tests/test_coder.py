@@ -106,9 +106,11 @@ def test_compress_decompress_round_trip_gpu(golden, variant):
 
 
 @pytest.mark.gpu
-def test_ar_variants_point_to_forward_with_indexes():
+def test_compress_before_update_raises_like_the_reference():
+    """entropy_models.py:180-199: coding without update() is a ValueError (the AR variants code through
+    tests/test_ar_codec.py)."""
     from spatiotemporalentropymodel_b200 import models as M
     model = M.SpatioTemporalPriorModel().to("cuda:0").eval()
     y = torch.zeros((1, 192, 8, 8), device="cuda:0")
-    with pytest.raises(NotImplementedError, match="wavefront"):
+    with pytest.raises(ValueError, match="Uninitialized CDFs"):
         model.compress(y, y)
