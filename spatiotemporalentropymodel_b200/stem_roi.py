@@ -138,10 +138,58 @@ class stem_roi(CompressionModel):  # noqa: N801 (reference class name)
         return self.engine().forward(x_cur, x_conditioned, Qmap)
 
     def compress(self, x_cur, x_conditioned, Qmap):  # noqa: N803
-        raise NotImplementedError("compress(): entropy coding is a 'next' row (SURVEY.md §8f)")
+        """stem_roi.py:645-661 -> {"strings": [y_strings, z_strings], "shape": z.size()[-2:]}"""
+        from .engine import nchw_to_nhwc_f16, nhwc_f32_to_nchw
+        eng = self.engine()
+        y16, yc16, z32, (B, h, w) = eng.latents(x_cur, x_conditioned, Qmap)
+        dev = eng.device
+        z = nhwc_f32_to_nchw(z32, torch.empty((B, 256, h // 4, w // 4), device=dev))
+        z_strings = self.entropy_bottleneck.compress(z)
+        z_hat = self.entropy_bottleneck.decompress(z_strings, z.size()[-2:])
+        zhat16 = nchw_to_nhwc_f16(z_hat.contiguous(), eng._buf("zhat16", (B, h // 4, w // 4, 256)))
+        params = eng.gaussian_params(zhat16, yc16, B, h, w)
+        y32 = eng._buf("y32", (B, h, w, eng.C), torch.float32)
+        lib = _lib.load()
+        st = torch.cuda.current_stream().cuda_stream
+        _lib.check(lib.stemb200_cast_f16_to_f32(y16.data_ptr(), y32.data_ptr(), y16.numel(), st), "cast")
+        idx = torch.empty((B, eng.C, h, w), dtype=torch.int32, device=dev)
+        sym = torch.empty((B, eng.C, h, w), dtype=torch.int32, device=dev)
+        table = self.gaussian_conditional.scale_table.to(dev, torch.float32).contiguous()
+        _lib.check(lib.stemb200_gaussian_conditional_fwd(y32.data_ptr(), 0, None, params.data_ptr(), B, eng.C, h, w,
+                                                         table.data_ptr(), table.numel(), eng.scale_bound,
+                                                         eng.lik_bound, 0, None, None, idx.data_ptr(), sym.data_ptr(),
+                                                         None, st), "gaussian_conditional_fwd")
+        y_strings = self.gaussian_conditional.compress_symbols(sym, idx)
+        return {"strings": [y_strings, z_strings], "shape": z.size()[-2:]}
 
     def decompress(self, strings, shape, x_conditioned):
-        raise NotImplementedError("decompress(): entropy coding is a 'next' row (SURVEY.md §8f)")
+        """stem_roi.py:664-680 -> {"x_hat" (clamped), "y_hat", "entropy_params"}"""
+        from .engine import nchw_to_nhwc_f16
+        assert isinstance(strings, list) and len(strings) == 2
+        eng = self.engine()
+        dev = eng.device
+        z_hat = self.entropy_bottleneck.decompress(strings[1], shape).to(dev)
+        B, _, h4, w4 = z_hat.shape
+        h, w = 4 * h4, 4 * w4
+        zhat16 = nchw_to_nhwc_f16(z_hat.contiguous(), eng._buf("zhat16", (B, h4, w4, 256)))
+        yc16 = eng.condition(x_conditioned)
+        params = eng.gaussian_params(zhat16, yc16, B, h, w)
+        lib = _lib.load()
+        st = torch.cuda.current_stream().cuda_stream
+        C = eng.C
+        idx = torch.empty((B, C, h, w), dtype=torch.int32, device=dev)
+        table = self.gaussian_conditional.scale_table.to(dev, torch.float32).contiguous()
+        zeros = torch.zeros((B, h, w, C), dtype=torch.float32, device=dev)
+        _lib.check(lib.stemb200_gaussian_conditional_fwd(zeros.data_ptr(), 0, None, params.data_ptr(), B, C, h, w,
+                                                         table.data_ptr(), table.numel(), eng.scale_bound,
+                                                         eng.lik_bound, 0, None, None, idx.data_ptr(), None, None, st),
+                   "gaussian_conditional_fwd")
+        gp = params.permute(0, 3, 1, 2)
+        scales_hat, means_hat = gp[:, :C].contiguous(), gp[:, C:].contiguous()
+        y_hat = self.gaussian_conditional.decompress(strings[0], idx, means=means_hat)
+        yhat16 = nchw_to_nhwc_f16(y_hat.contiguous(), eng._buf("yhat16", (B, h, w, C)))
+        x_hat = eng.synthesis(yhat16, zhat16, B, h, w, clamp=True)
+        return {"x_hat": x_hat, "y_hat": y_hat, "entropy_params": {"scales_hat": scales_hat, "means_hat": means_hat}}
 
     def load_state_dict(self, state_dict, strict: bool = True):
         _resize_registered_buffers(self.gaussian_conditional, "gaussian_conditional",
@@ -316,7 +364,8 @@ class RoiEngine:
             h, w = ho, wo
         return cur, h, w
 
-    def forward(self, x_cur: Tensor, x_cond: Tensor, qmap: Tensor):
+    def latents(self, x_cur: Tensor, x_cond: Tensor, qmap: Tensor):
+        """PEncoder, ConditionEncoder, HE (stem_roi.py:586-589) -> y_cur fp16, y_conditioned fp16, z fp32 (NHWC)."""
         _require_cuda(x_cur, x_cond, qmap)
         x_cur, x_cond, qmap = x_cur.contiguous().float(), x_cond.contiguous().float(), qmap.contiguous().float()
         B, _, H, W = x_cur.shape
@@ -351,8 +400,7 @@ class RoiEngine:
         x = self.ga4_rb[0](self.ws, "ga4rb1", x, qp, B, h, w)
         y16 = self.ga4_rb[1](self.ws, "ga4rb2", x, qp, B, h, w)  # y_cur (B, h, w, C) fp16
         # ================= ConditionEncoder =================
-        yc16, hc, wc = self._analysis4(self.ce, "ce", x_cond)
-        assert (hc, wc) == (h, w)
+        yc16 = self.condition(x_cond)
         # ================= HE =================
         q8 = bf("q8", (B, h, w, 8))
         _lib.check(lib.stemb200_qmap_pool(qmap.data_ptr(), q8.data_ptr(), B, h, w, H // h, _stream()), "qmap_pool")
@@ -373,6 +421,33 @@ class RoiEngine:
         z16 = self.ha3_rb[1](self.ws, "ha3rb2", t, qf, B, h4, w4)
         z32 = bf("z32", (B, h4, w4, 256), f32)
         _lib.check(lib.stemb200_cast_f16_to_f32(z16.data_ptr(), z32.data_ptr(), z16.numel(), _stream()), "cast")
+        return y16, yc16, z32, (B, h, w)
+
+    def condition(self, x_cond: Tensor) -> Tensor:
+        """ConditionEncoder (stem_roi.py:493-501) -> y_conditioned NHWC fp16."""
+        _require_cuda(x_cond)
+        return self._analysis4(self.ce, "ce", x_cond.contiguous().float())[0]
+
+    def gaussian_params(self, zhat16: Tensor, yc16: Tensor, B: int, h: int, w: int) -> Tensor:
+        """HD(z_hat), TPM(y_conditioned), EPM (stem_roi.py:591-598) -> (scales | means) NHWC fp32."""
+        bf, C = self._buf, self.C
+        h4, w4 = h // 4, w // 4
+        d = self.hs[0]([zhat16], B, h4, w4, bf("hs0", (B, h // 2, w // 2, 256)))
+        d = self.hs[1]([d], B, h // 2, w // 2, bf("hs1", (B, h, w, 256)))
+        hp = self.hs[2]([d], B, h, w, bf("hp", (B, h, w, 2 * C)))
+        p = self.tpm[0]([yc16], B, h, w, bf("tp0", (B, h, w, 256)))
+        p = self.tpm[1]([p], B, h, w, bf("tp1", (B, h, w, 320)))
+        tp = self.tpm[2]([p], B, h, w, bf("tp", (B, h, w, 2 * C)))
+        e = self.epm[0]([tp, hp], B, h, w, bf("e0", (B, h, w, 768)))
+        e = self.epm[1]([e], B, h, w, bf("e1", (B, h, w, 576)))
+        return self.epm[2]([e], B, h, w, bf("gparams", (B, h, w, 2 * C), torch.float32))
+
+    def forward(self, x_cur: Tensor, x_cond: Tensor, qmap: Tensor):
+        y16, yc16, z32, (B, h, w) = self.latents(x_cur, x_cond, qmap)
+        lib, C, dev = _lib.load(), self.C, self.device
+        f16, f32 = torch.float16, torch.float32
+        bf = self._buf
+        h4, w4 = h // 4, w // 4
         # ================= entropy models =================
         z_hat = torch.empty((B, 256, h4, w4), dtype=f32, device=dev)
         z_lik = torch.empty((B, 256, h4, w4), dtype=f32, device=dev)
@@ -382,15 +457,7 @@ class RoiEngine:
                                                        self.lik_bound, zhat16.data_ptr(), z_hat.data_ptr(),
                                                        z_lik.data_ptr(), bits[1].data_ptr(), _stream()),
                    "entropy_bottleneck_fwd")
-        d = self.hs[0]([zhat16], B, h4, w4, bf("hs0", (B, h // 2, w // 2, 256)))
-        d = self.hs[1]([d], B, h // 2, w // 2, bf("hs1", (B, h, w, 256)))
-        hp = self.hs[2]([d], B, h, w, bf("hp", (B, h, w, 2 * C)))
-        p = self.tpm[0]([yc16], B, h, w, bf("tp0", (B, h, w, 256)))
-        p = self.tpm[1]([p], B, h, w, bf("tp1", (B, h, w, 320)))
-        tp = self.tpm[2]([p], B, h, w, bf("tp", (B, h, w, 2 * C)))
-        e = self.epm[0]([tp, hp], B, h, w, bf("e0", (B, h, w, 768)))
-        e = self.epm[1]([e], B, h, w, bf("e1", (B, h, w, 576)))
-        params = self.epm[2]([e], B, h, w, bf("gparams", (B, h, w, 2 * C), f32))
+        params = self.gaussian_params(zhat16, yc16, B, h, w)
         y32 = bf("y32", (B, h, w, C), f32)
         _lib.check(lib.stemb200_cast_f16_to_f32(y16.data_ptr(), y32.data_ptr(), y16.numel(), _stream()), "cast")
         y_hat = torch.empty((B, C, h, w), dtype=f32, device=dev)
@@ -400,6 +467,15 @@ class RoiEngine:
                                                          y_lik.data_ptr(), None, None, bits[0].data_ptr(), _stream()),
                    "gaussian_conditional_fwd")
         yhat16 = nchw_to_nhwc_f16(y_hat, bf("yhat16", (B, h, w, C)))
+        x_hat = self.synthesis(yhat16, zhat16, B, h, w, clamp=False)
+        return {"x_hat": x_hat, "y_hat": y_hat, "likelihoods": {"y": y_lik, "z": z_lik}, "bits": bits}
+
+    def synthesis(self, yhat16: Tensor, zhat16: Tensor, B: int, h: int, w: int, clamp: bool) -> Tensor:
+        """PDecoder (stem_roi.py:540-560): y_hat, z_hat (NHWC fp16) -> x_hat NCHW fp32."""
+        lib, dev = _lib.load(), self.device
+        f32 = torch.float32
+        bf = self._buf
+        h4, w4 = h // 4, w // 4
         # ================= PDecoder =================
         wm = self.wgen[0]([zhat16], B, h4, w4, bf("wg0", (B, h // 2, w // 2, 192)))
         wm = self.wgen[1]([wm], B, h // 2, w // 2, bf("wg1", (B, h, w, 128)))
@@ -419,8 +495,8 @@ class RoiEngine:
         self.gs4([x], B, h, w, merged)
         x_hat = torch.empty((B, 3, 2 * h, 2 * w), dtype=f32, device=dev)
         _lib.check(lib.stemb200_synthesis_tail(merged.data_ptr(), x_hat.data_ptr(), B, h // 2, w // 2, None, 0, 0, 0, 0,
-                                               None, 0, _stream()), "synthesis_tail")
-        return {"x_hat": x_hat, "y_hat": y_hat, "likelihoods": {"y": y_lik, "z": z_lik}, "bits": bits}
+                                               None, int(clamp), _stream()), "synthesis_tail")
+        return x_hat
 
 
 # ------------------------------------------------------------------------------------------------------

@@ -99,3 +99,27 @@ def test_cuda_forward_batch_and_rectangular():
     assert abs(got_bits - ref_bits) / ref_bits < 5e-3
     rms = float(torch.sqrt(((out["x_hat"].cpu() - ref["x_hat"]) ** 2).mean() / (ref["x_hat"] ** 2).mean()))
     assert rms < 3e-2, rms
+
+
+@pytest.mark.gpu
+def test_cuda_compress_decompress_round_trip():
+    """stem_roi.py:645-680: the decoded y_hat is the forward pass's y_hat exactly (non-autoregressive model), the
+    decoded frame is the clamped forward reconstruction, and the coded size tracks the likelihood estimate."""
+    from spatiotemporalentropymodel_b200 import stem_roi as R
+    dev = torch.device("cuda:0")
+    model = R.stem_roi()
+    model.load_state_dict(R.make_synthetic_state_dict(seed=0))
+    model.update(force=True)
+    model = model.to(dev).eval()
+    x_cur, x_cond, qmaps = _inputs()
+    x_cur, x_cond, q = x_cur.to(dev), x_cond.to(dev), qmaps["ramp"].to(dev)
+    fwd = model(x_cur, x_cond, q)
+    enc = model.compress(x_cur, x_cond, q)
+    assert set(enc) == {"strings", "shape"} and tuple(enc["shape"]) == (x_cur.shape[2] // 64, x_cur.shape[3] // 64)
+    dec = model.decompress(enc["strings"], enc["shape"], x_cond)
+    assert set(dec) == {"x_hat", "y_hat", "entropy_params"}
+    assert torch.equal(dec["y_hat"], fwd["y_hat"])
+    assert torch.allclose(dec["x_hat"], fwd["x_hat"].clamp(0, 1), atol=1e-6)
+    real_bits = 8 * sum(len(s) for part in enc["strings"] for s in part)
+    est_bits = bits(fwd["likelihoods"]["y"].cpu()) + bits(fwd["likelihoods"]["z"].cpu())
+    assert 0.6 * est_bits < real_bits < 1.02 * est_bits, (real_bits, est_bits)
