@@ -33,6 +33,9 @@ WORKLOADS = {
     "smoke_256": ("SpatioTemporalPriorModel", 2, 256, 256, "configs[0]-shaped quick run"),
     "stem_roi_4k": ("stem_roi", 1, 2160, 3840, "configs[4]: variable-rate SFT STEM (stem_roi), 3840x2160 frame"),
     "stem_roi_1080p": ("stem_roi", 2, 1080, 1920, "stem_roi at 1080p (2 frames per step)"),
+    "ar_codec_1080p": ("ar_codec", 1, 1080, 1920,
+                       "SURVEY §8f-2: SpatioTemporalPriorModel.compress + decompress (autoregressive y coding) of one "
+                       "1080p P-frame latent (192 x 68 x 120)"),
 }
 
 METRIC = "1080p P-frames/sec (STEM fwd+likelihoods)"
@@ -285,6 +288,82 @@ def run_stem_roi(args):
         dist.destroy_process_group()
 
 
+def run_ar_codec(args):
+    """bitstream coding of one 1080p P-frame latent through the model API
+    (compress -> strings -> decompress), host rANS / D2H / H2D included (wall clock around synchronised calls).
+    The reference codes this on the CPU one latent position at a time (spatiotemporalpriors.py:633-678, :729-768);
+    its cost is sampled on an 8 x 8 latent with the oracle port and scaled by the position count."""
+    from oracle import stem_oracle as O
+    from spatiotemporalentropymodel_b200 import _lib, models as M, synthetic as S
+    _, T, H, W, desc = WORKLOADS[args.workload]
+    variant = "SpatioTemporalPriorModel"
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+    torch.cuda.set_device(dev)
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    stem = getattr(M, variant)()
+    sd = S.make_stem_state_dict(variant, 0)
+    stem.load_state_dict(sd)
+    stem.update(force=True)
+    stem = stem.to(dev).eval()
+    h, w = (H + 63) // 64 * 64 // 16, (W + 63) // 64 * 64 // 16
+    y_cond = torch.round(S.make_latent(1, 192, h, w, seed=5)).to(dev)
+    y_cur = (y_cond + 0.7 * S.make_latent(1, 192, h, w, seed=6).to(dev)).contiguous()
+    for _ in range(max(1, min(args.warmup, 2))):
+        enc = stem.compress(y_cur, y_cond)
+        dec = stem.decompress(enc["strings"], enc["shape"], y_cond)
+    torch.cuda.synchronize()
+    assert float((dec["y_hat"] - y_cur).abs().max()) <= 0.5 + 1e-3
+    n0 = _lib.launch_count()
+    steps = max(1, min(args.steps, 10))
+    t_enc = t_dec = 0.0
+    for _ in range(steps):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        enc = stem.compress(y_cur, y_cond)
+        torch.cuda.synchronize()
+        t1 = time.perf_counter()
+        dec = stem.decompress(enc["strings"], enc["shape"], y_cond)
+        torch.cuda.synchronize()
+        t2 = time.perf_counter()
+        t_enc += t1 - t0
+        t_dec += t2 - t1
+    launches = _lib.launch_count() - n0
+    enc_ms, dec_ms = 1e3 * t_enc / steps, 1e3 * t_dec / steps
+    nbytes = sum(len(s_) for part in enc["strings"] for s_ in part)
+    # CPU reference sample: the raster scan on an 8 x 8 latent (64 positions), scaled to h * w positions
+    cpu = None
+    if not args.no_cpu_baseline:
+        torch.set_num_threads(os.cpu_count() or 1)
+        yc = torch.round(S.make_latent(1, 192, 8, 8, seed=5))
+        yy = yc + 0.7 * S.make_latent(1, 192, 8, 8, seed=6)
+        with torch.no_grad():
+            t0 = time.perf_counter()
+            out = O.stem_ar_code(variant, yy, yc, sd)
+            t1 = time.perf_counter()
+            z_hat = out["z_hat"]
+            pri = torch.cat([O.TPM(yc, sd), O.HD(z_hat, sd)], 1)
+            t2 = time.perf_counter()
+            O.ar_scan(None, pri, sd, symbols=out["symbols"])
+            t3 = time.perf_counter()
+        scale = h * w / 64.0
+        cpu_s = ((t1 - t0) + (t3 - t2)) * scale
+        cpu = {"value": 1.0 / cpu_s, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+               "sample": f"encode + decode scans of an 8x8 latent ({(t1 - t0) + (t3 - t2):.2f} s), scaled x{scale:.1f} "
+                         f"to {h}x{w} positions => {cpu_s:.0f} s per frame"}
+    print(json.dumps({
+        "metric": "1080p P-frame latents/sec (AR compress + decompress through the model API)",
+        "value": 1e3 / (enc_ms + dec_ms), "unit": UNIT, "n_gpus": 1, "steps": steps, "warmup": 2,
+        "ms_per_step": enc_ms + dec_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32 (AR head) / f16 operands f32 accumulate (priors)", "data": "synthetic",
+        "config": {"workload": args.workload, "desc": desc, "variant": variant, "latent": [192, h, w],
+                   "compress_ms": enc_ms, "decompress_ms": dec_ms, "coded_bytes": nbytes,
+                   "l2": "latency-bound persistent kernel; not a bandwidth measurement"},
+        "e2e": {"value": 1e3 / (enc_ms + dec_ms), "unit": UNIT, "h2d_bytes_per_step": nbytes,
+                "d2h_bytes_per_step": 2 * 4 * 192 * h * w},
+        "gpu_launches": launches, "roofline": None, "cpu_baseline": cpu}))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -304,6 +383,9 @@ def main():
 
     if WORKLOADS[args.workload][0] == "stem_roi":
         run_stem_roi(args)
+        return
+    if WORKLOADS[args.workload][0] == "ar_codec":
+        run_ar_codec(args)
         return
 
     rank = int(os.environ.get("RANK", "0"))

@@ -33,6 +33,7 @@ constexpr int kArThreads = 256;
 constexpr int kArWarps = kArThreads / 32;
 constexpr int kArTaps = 12;  // mask 'A' of a 5x5 kernel: rows 0-1 complete, row 2 columns 0-1 (layers.py:39-42)
 constexpr uint64_t kRansL = 1ull << 31;
+constexpr int kArMaxCdfs = 64;
 
 struct ArParams {
   int batch, h, w, c, l1, l2;
@@ -155,6 +156,11 @@ __global__ void __launch_bounds__(kArThreads, 1) ar_codec_kernel(const ArParams 
   __shared__ int s_flag;
   __shared__ float s_res[kArWarps][16];
   __shared__ int s_sym[256];  // decode: symbols of one position (c <= 256)
+  __shared__ int s_idx[256];  //         their CDF indexes
+  // decode: first level of the 32-ary CDF search for every table row (probe positions depend on the row only),
+  // row sizes and symbol offsets: the serial rANS loop then needs one round of (L1-resident) global loads per symbol
+  __shared__ int s_l1[kArMaxCdfs][32];
+  __shared__ int s_size[kArMaxCdfs], s_off[kArMaxCdfs];
 
   const int C = p.c, C2 = 2 * p.c, L1 = p.l1, L2 = p.l2;
   const int KA = kArTaps * C;
@@ -176,6 +182,20 @@ __global__ void __launch_bounds__(kArThreads, 1) ar_codec_kernel(const ArParams 
   }
   __syncthreads();
 
+  if (p.mode == 1 && j < p.batch) {
+    for (int i = threadIdx.x; i < p.n_cdfs * 32; i += kArThreads) {
+      const int row = i >> 5, ln = i & 31;
+      const int n = __ldg(p.cdf_size + row) - 1;
+      const int step = (n + 31) >> 5;
+      s_l1[row][ln] = (n >= 1 && ln * step < n) ? __ldg(p.cdf + static_cast<long long>(row) * p.cdf_stride + ln * step)
+                                                : 0x7fffffff;
+    }
+    for (int i = threadIdx.x; i < p.n_cdfs; i += kArThreads) {
+      s_size[i] = __ldg(p.cdf_size + i);
+      s_off[i] = __ldg(p.cdf_off + i);
+    }
+    __syncthreads();
+  }
   // rANS decoder state of image j (warp 0 of CTA j < batch), identical in every lane
   uint64_t rx = 0;
   long long rpos = 0, rwords = 0;
@@ -308,52 +328,79 @@ __global__ void __launch_bounds__(kArThreads, 1) ar_codec_kernel(const ArParams 
       if (j < p.batch && warp == 0) {
         const Pix q = pix(j);
         const long long e0i = q.g * C;
+        for (int ch = lane; ch < C; ch += 32) {
+          int ci = __ldcg(p.idx + e0i + ch);
+          s_idx[ch] = ci < 0 ? 0 : (ci >= p.n_cdfs ? p.n_cdfs - 1 : ci);
+        }
+        __syncwarp();
         for (int ch = 0; ch < C; ++ch) {
           int value = 0;
           if (!rbad) {
-            const int ci = __ldcg(p.idx + e0i + ch);
+            const int ci = s_idx[ch];
             const int32_t* row = p.cdf + static_cast<long long>(ci) * p.cdf_stride;
-            const int size = __ldg(p.cdf_size + ci);
+            const int size = s_size[ci];
+            const int n = size - 1;  // candidates s in [0, n): row[s] <= cum < row[s+1]
             const uint32_t cum = static_cast<uint32_t>(rx & 0xFFFFu);
-            // 32-ary search for s with row[s] <= cum < row[s+1], s in [0, size-2]
-            int slo = 0, n = size - 1;
-            while (n > 1) {
+            uint32_t start = 0, freq = 0;
+            int s_found = 0;
+            if (n >= 1) {
               const int step = (n + 31) >> 5;
-              const int off = lane * step;
-              const bool pred = off < n && static_cast<uint32_t>(__ldg(row + slo + off)) <= cum;
-              const unsigned int m = __ballot_sync(0xffffffffu, pred);
-              const int k = m ? 31 - __clz(m) : 0;
-              slo += k * step;
-              const int rem = n - k * step;
-              n = rem < step ? rem : step;
+              const unsigned int m1 = __ballot_sync(0xffffffffu, static_cast<uint32_t>(s_l1[ci][lane]) <= cum);
+              const int k = m1 ? 31 - __clz(m1) : 0;
+              const int slo = k * step;
+              const int rem = (n - slo) < step ? (n - slo) : step;  // 1 <= rem <= 98
+              uint32_t v[4];
+              int cnt = 0;
+#pragma unroll
+              for (int jj = 0; jj < 4; ++jj) {
+                const int o = lane + 32 * jj;
+                v[jj] = o <= rem ? static_cast<uint32_t>(__ldg(row + slo + o)) : 0xFFFFFFFFu;
+              }
+#pragma unroll
+              for (int jj = 0; jj < 4; ++jj)
+                cnt += __popc(__ballot_sync(0xffffffffu, (lane + 32 * jj) < rem && v[jj] <= cum));
+              if (cnt < 1) cnt = 1;  // corrupt table / stream: stay in range, flagged below
+              const int o0 = cnt - 1, o1 = cnt;
+              uint32_t a = 0, b = 0;
+#pragma unroll
+              for (int jj = 0; jj < 4; ++jj) {
+                const uint32_t t0 = __shfl_sync(0xffffffffu, v[jj], o0 & 31);
+                const uint32_t t1 = __shfl_sync(0xffffffffu, v[jj], o1 & 31);
+                if ((o0 >> 5) == jj) a = t0;
+                if ((o1 >> 5) == jj) b = t1;
+              }
+              start = a;
+              freq = b - a;
+              s_found = slo + o0;
             }
-            const uint32_t start = static_cast<uint32_t>(__ldg(row + slo));
-            const uint32_t freq = static_cast<uint32_t>(__ldg(row + slo + 1)) - start;
-            if (freq == 0 || cum < start || cum >= start + freq) rbad = true;
+            if (freq == 0 || freq > 65536u || cum < start || cum >= start + freq) rbad = true;
             rx = static_cast<uint64_t>(freq) * (rx >> 16) + cum - start;
             if (rx < kRansL && rpos < rwords) rx = (rx << 32) | __ldg(rstream + rpos++);
-            value = slo;
-            if (slo == size - 2) {
+            value = s_found;
+            if (s_found == size - 2) {
               // bypass: nibble count (unary in chunks of 15), then the nibbles, least significant first
               auto get4 = [&]() -> int {
-                const int v = static_cast<int>(rx & 15u);
+                const int v4 = static_cast<int>(rx & 15u);
                 rx >>= 4;
                 if (rx < kRansL && rpos < rwords) rx = (rx << 32) | __ldg(rstream + rpos++);
-                return v;
+                return v4;
               };
-              int v = get4();
-              int n_nib = v;
-              while (v == 15 && n_nib < 64) {
-                v = get4();
-                n_nib += v;
+              int v4 = get4();
+              int n_nib = v4;
+              while (v4 == 15 && n_nib < 64) {
+                v4 = get4();
+                n_nib += v4;
               }
               uint32_t raw = 0;
-              for (int k2 = 0; k2 < n_nib; ++k2) raw |= (k2 < 8 ? static_cast<uint32_t>(get4()) << (4 * k2) : (get4(), 0u));
+              for (int k2 = 0; k2 < n_nib; ++k2) {
+                const uint32_t nib = static_cast<uint32_t>(get4());
+                if (k2 < 8) raw |= nib << (4 * k2);
+              }
               value = static_cast<int>(raw >> 1);
               if (raw & 1u) value = -value - 1;
               else value += size - 2;
             }
-            value += __ldg(p.cdf_off + ci);
+            value += s_off[ci];
           }
           if (lane == 0) s_sym[ch] = value;
         }
@@ -489,8 +536,8 @@ extern "C" int stemb200_ar_decode(const stemb200_ar_desc* d, const float* packed
                                   int32_t* indexes, float* params_out, int32_t* status, void* workspace,
                                   void* stream) {
   if (!packed || !e0 || !scale_table || !streams || !stream_off || !stream_len || !cdfs || !cdf_sizes || !offsets ||
-      !t_hat || !indexes || !status || !workspace || n_cdfs < 1 || cdf_stride < 2)
-    return set_error("ar_decode: null / bad argument");
+      !t_hat || !indexes || !status || !workspace || n_cdfs < 1 || n_cdfs > kArMaxCdfs || cdf_stride < 2)
+    return set_error("ar_decode: null / bad argument (at most 64 CDF rows)");
   ArParams p{};
   if (int rc = fill_params(d, p)) return rc;
   const Scratch s = carve(d, workspace);
