@@ -227,13 +227,14 @@ int stemb200_ar_encode(const stemb200_ar_desc* d, const float* packed, const flo
                        const float* scale_table, float* t_hat, int32_t* symbols, int32_t* indexes,
                        float* params_out, void* workspace, void* stream);
 /* streams: the batch's rANS byte strings on the device, image b at [stream_off[b], +stream_len[b]) with 4-byte
- * aligned offsets; cdfs / cdf_sizes / offsets: the GaussianConditional tables (int32, device).
+ * aligned offsets; cdfs / cdf_sizes / offsets: the GaussianConditional tables (int32, device; at most 64 rows);
+ * cdf_total_entries = sum of cdf_sizes (the decoder keeps a compact 16-bit copy of the rows in shared memory).
  * status[b] = 0, or 1 when stream b is corrupt. */
 int stemb200_ar_decode(const stemb200_ar_desc* d, const float* packed, const float* e0, const float* scale_table,
                        const uint8_t* streams, const int64_t* stream_off, const int64_t* stream_len,
                        const int32_t* cdfs, int32_t n_cdfs, int32_t cdf_stride, const int32_t* cdf_sizes,
-                       const int32_t* offsets, float* t_hat, int32_t* symbols, int32_t* indexes, float* params_out,
-                       int32_t* status, void* workspace, void* stream);
+                       const int32_t* offsets, int32_t cdf_total_entries, float* t_hat, int32_t* symbols,
+                       int32_t* indexes, float* params_out, int32_t* status, void* workspace, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------
  * Host-side helper that the reference implements in C++ (compressai/cpp_exts/ops/ops.cpp:24-81)

@@ -71,7 +71,7 @@ SIGNATURES = {
     "stemb200_ar_workspace_bytes": (_i64, [C.POINTER(ArDesc)]),
     "stemb200_ar_encode": (C.c_int, [C.POINTER(ArDesc), _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "stemb200_ar_decode": (C.c_int, [C.POINTER(ArDesc), _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _vp, _vp,
-                                     _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+                                     _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "stemb200_rans_encode_host": (_i64, [_vp, _vp, _i64, _vp, _i32, _i32, _vp, _vp, _vp, _i64]),
     "stemb200_rans_decode_host": (C.c_int, [_vp, _i64, _vp, _i64, _vp, _i32, _i32, _vp, _vp, _vp]),
     "stemb200_pmf_to_quantized_cdf_host": (C.c_int, [C.POINTER(C.c_float), _i32, _i32, C.POINTER(C.c_int32)]),

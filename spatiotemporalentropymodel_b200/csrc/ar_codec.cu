@@ -34,6 +34,7 @@ constexpr int kArWarps = kArThreads / 32;
 constexpr int kArTaps = 12;  // mask 'A' of a 5x5 kernel: rows 0-1 complete, row 2 columns 0-1 (layers.py:39-42)
 constexpr uint64_t kRansL = 1ull << 31;
 constexpr int kArMaxCdfs = 64;
+constexpr int kArMaxScales = 256;
 
 struct ArParams {
   int batch, h, w, c, l1, l2;
@@ -60,6 +61,8 @@ struct ArParams {
   const int32_t* cdf_off;
   int cdf_stride, n_cdfs;
   int32_t* status;  // [B] decode status: 0 ok, 1 corrupt stream
+  int nstage;       // staging vectors: 8 when encoding (one per warp), 2 when decoding (position i + 1 in flight)
+  int cdf16_entries;  // decode: total entries of the compact 16-bit CDF table kept in shared memory
 };
 
 __device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int* p) {
@@ -99,33 +102,61 @@ __device__ bool grid_barrier(unsigned int* sync, unsigned int& epoch, int* s_fla
   return *s_flag != 0;
 }
 
-// RB dot products of length K against one staged vector, lanes striding K; the result is in every lane.
-template <int RB>
-__device__ __forceinline__ void dot_rows(const float* __restrict__ wrow, int ldw, const float* __restrict__ v, int K,
-                                         int lane, float* out) {
-  float acc[RB];
-#pragma unroll
-  for (int r = 0; r < RB; ++r) acc[r] = 0.f;
-  for (int k = lane; k < K; k += 32) {
-    const float x = v[k];
-#pragma unroll
-    for (int r = 0; r < RB; ++r) acc[r] = fmaf(wrow[r * ldw + k], x, acc[r]);
-  }
-#pragma unroll
-  for (int r = 0; r < RB; ++r) {
-    float a = acc[r];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
-    out[r] = a;
-  }
+// Asynchronous global -> shared staging (16-byte cp.async.cg: served from L2, so values written by other CTAs before
+// the grid barrier are seen; n_bytes = 0 zero-fills). All copies of a position are in flight together.
+__device__ __forceinline__ void cp_async16(float* dst_smem, const float* src, bool valid) {
+  const uint32_t d = static_cast<uint32_t>(__cvta_generic_to_shared(dst_smem));
+  const int n = valid ? 16 : 0;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(src), "r"(n) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 
-// res[r] = W[r] . v for r < R (lane 0 writes), fixed evaluation order for a given (R, K)
-__device__ __forceinline__ void matvec(const float* W, int R, int K, const float* v, int lane, float* res) {
+constexpr int kArMaxRows = 12;  // rows of one layer owned by a CTA
+
+// Canonical evaluation order of one dot product W[r] . v (K elements), shared by the encoder and the decoder so that
+// the decoder reproduces the encoder's (sigma, mu) bit for bit:
+//   a_s(lane) = fma chain over e = s*32 + lane + 256 i (i ascending),  s = 0..7
+//   b(lane)   = ((((a_0 + a_1) + a_2) + ...) + a_7)
+//   value     = xor-shuffle tree over the 32 lanes of b
+// The decoder (one position at a time) spreads the eight segments s over the eight warps of the CTA; the encoder
+// (many positions per step) lets every warp do all eight segments of its own position.
+__device__ __forceinline__ float lane_tree(float a) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+  return a;
+}
+
+// encoder: one warp, RB rows at a time; out[r] valid in every lane
+template <int RB>
+__device__ __forceinline__ void warp_rows(const float* __restrict__ wrow, int K, const float* __restrict__ v, int lane,
+                                          float* out) {
+  float b[RB];
+#pragma unroll
+  for (int s = 0; s < 8; ++s) {
+    float a[RB];
+#pragma unroll
+    for (int r = 0; r < RB; ++r) a[r] = 0.f;
+    for (int e = s * 32 + lane; e < K; e += kArThreads) {
+      const float x = v[e];
+#pragma unroll
+      for (int r = 0; r < RB; ++r) a[r] = fmaf(wrow[r * K + e], x, a[r]);
+    }
+#pragma unroll
+    for (int r = 0; r < RB; ++r) b[r] = s == 0 ? a[r] : b[r] + a[r];
+  }
+#pragma unroll
+  for (int r = 0; r < RB; ++r) out[r] = lane_tree(b[r]);
+}
+// res[r] = W[r] . v for r < R (lane 0 writes)
+__device__ __forceinline__ void warp_matvec(const float* Wm, int R, int K, const float* v, int lane, float* res) {
   int r = 0;
   float o[3];
   while (R - r >= 3) {
-    dot_rows<3>(W + r * K, K, v, K, lane, o);
+    warp_rows<3>(Wm + r * K, K, v, lane, o);
     if (lane == 0) {
       res[r] = o[0];
       res[r + 1] = o[1];
@@ -134,16 +165,40 @@ __device__ __forceinline__ void matvec(const float* W, int R, int K, const float
     r += 3;
   }
   if (R - r == 2) {
-    dot_rows<2>(W + r * K, K, v, K, lane, o);
+    warp_rows<2>(Wm + r * K, K, v, lane, o);
     if (lane == 0) {
       res[r] = o[0];
       res[r + 1] = o[1];
     }
   } else if (R - r == 1) {
-    dot_rows<1>(W + r * K, K, v, K, lane, o);
+    warp_rows<1>(Wm + r * K, K, v, lane, o);
     if (lane == 0) res[r] = o[0];
   }
   __syncwarp();
+}
+
+// decoder: segment s = warp; every thread leaves a_warp(lane) of each row in lp[r][warp][lane]
+__device__ __forceinline__ void cta_segments(const float* __restrict__ Wm, int R, int K, const float* __restrict__ v,
+                                             int warp, int lane, float (*lp)[kArWarps][32]) {
+  float acc[kArMaxRows];
+#pragma unroll
+  for (int r = 0; r < kArMaxRows; ++r) acc[r] = 0.f;
+  for (int e = warp * 32 + lane; e < K; e += kArThreads) {
+    const float x = v[e];
+#pragma unroll
+    for (int r = 0; r < kArMaxRows; ++r)
+      if (r < R) acc[r] = fmaf(Wm[r * K + e], x, acc[r]);
+  }
+#pragma unroll
+  for (int r = 0; r < kArMaxRows; ++r)
+    if (r < R) lp[r][warp][lane] = acc[r];
+}
+// value of row r (in every lane of the calling warp) once all segments are in lp
+__device__ __forceinline__ float cta_row(float (*lp)[kArWarps][32], int r, int lane) {
+  float b = lp[r][0][lane];
+#pragma unroll
+  for (int w = 1; w < kArWarps; ++w) b += lp[r][w][lane];
+  return lane_tree(b);
 }
 
 struct Pix {
@@ -154,13 +209,15 @@ struct Pix {
 __global__ void __launch_bounds__(kArThreads, 1) ar_codec_kernel(const ArParams p) {
   extern __shared__ float smem[];
   __shared__ int s_flag;
-  __shared__ float s_res[kArWarps][16];
-  __shared__ int s_sym[256];  // decode: symbols of one position (c <= 256)
-  __shared__ int s_idx[256];  //         their CDF indexes
-  // decode: first level of the 32-ary CDF search for every table row (probe positions depend on the row only),
-  // row sizes and symbol offsets: the serial rANS loop then needs one round of (L1-resident) global loads per symbol
+  __shared__ float s_lp[kArMaxRows][kArWarps][32];  // decode: per-lane segment sums of the rows of one position
+  __shared__ float s_res[kArWarps][16];             // encode: row values of the warp's position
+  __shared__ int s_sym[320];                 // decode: symbols of one position
+  __shared__ int s_idx[320];                 //         their CDF indexes
+  // decode: first level of the 32-ary CDF search for every table row (probe positions depend on the row only) and
+  // per-row {offset into the compact table, size, symbol offset, level-1 step}
   __shared__ int s_l1[kArMaxCdfs][32];
-  __shared__ int s_size[kArMaxCdfs], s_off[kArMaxCdfs];
+  __shared__ int4 s_meta[kArMaxCdfs];
+  __shared__ float s_table[kArMaxScales];
 
   const int C = p.c, C2 = 2 * p.c, L1 = p.l1, L2 = p.l2;
   const int KA = kArTaps * C;
@@ -171,50 +228,86 @@ __global__ void __launch_bounds__(kArThreads, 1) ar_codec_kernel(const ArParams 
   float* b1 = w1 + p.r2 * L1;
   float* w2 = b1 + p.r2;
   float* b2 = w2 + 2 * p.rg * L2;
-  float* vec = smem + ((p.block_floats + 3) & ~3);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* vec = smem + ((p.block_floats + 3) & ~3);  // two staging vectors of kmax floats
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int j = blockIdx.x;
-  float* myvec = vec + warp * p.kmax;
 
   {
     const float* src = p.packed + static_cast<long long>(j) * p.block_floats;
-    for (int i = threadIdx.x; i < p.block_floats; i += kArThreads) smem[i] = __ldg(src + i);
+    for (int i = tid; i < p.block_floats; i += kArThreads) smem[i] = __ldg(src + i);
+    for (int i = tid; i < p.n_scales; i += kArThreads) s_table[i] = __ldg(p.table + i);
   }
   __syncthreads();
 
+  // decode: compact 16-bit copy of the CDF rows (sum of the row sizes, ~27 k entries = 54 KB for the 64-level table;
+  // the final 65536 of a row wraps to 0 and is special-cased) + the first level of the 32-ary search of every row
+  uint16_t* cdf16 = reinterpret_cast<uint16_t*>(vec + p.nstage * p.kmax);
   if (p.mode == 1 && j < p.batch) {
-    for (int i = threadIdx.x; i < p.n_cdfs * 32; i += kArThreads) {
-      const int row = i >> 5, ln = i & 31;
-      const int n = __ldg(p.cdf_size + row) - 1;
-      const int step = (n + 31) >> 5;
-      s_l1[row][ln] = (n >= 1 && ln * step < n) ? __ldg(p.cdf + static_cast<long long>(row) * p.cdf_stride + ln * step)
-                                                : 0x7fffffff;
+    if (tid == 0) {
+      int acc = 0;
+      for (int r = 0; r < p.n_cdfs; ++r) {
+        const int sz = __ldg(p.cdf_size + r);
+        s_meta[r] = make_int4(acc, sz, __ldg(p.cdf_off + r), (sz - 1 + 31) >> 5);
+        acc += sz;
+      }
     }
-    for (int i = threadIdx.x; i < p.n_cdfs; i += kArThreads) {
-      s_size[i] = __ldg(p.cdf_size + i);
-      s_off[i] = __ldg(p.cdf_off + i);
+    __syncthreads();
+    for (int r = 0; r < p.n_cdfs; ++r) {
+      const int4 mt = s_meta[r];
+      const int32_t* row = p.cdf + static_cast<long long>(r) * p.cdf_stride;
+      for (int i = tid; i < mt.y; i += kArThreads) cdf16[mt.x + i] = static_cast<uint16_t>(__ldg(row + i));
+    }
+    __syncthreads();
+    for (int i = tid; i < p.n_cdfs * 32; i += kArThreads) {
+      const int row = i >> 5, ln = i & 31;
+      const int4 mt = s_meta[row];
+      const int n = mt.y - 1;
+      s_l1[row][ln] = (n >= 1 && ln * mt.w < n) ? static_cast<int>(cdf16[mt.x + ln * mt.w]) : 0x7fffffff;
     }
     __syncthreads();
   }
-  // rANS decoder state of image j (warp 0 of CTA j < batch), identical in every lane
+  // rANS decoder state of image j (warp 0 of CTA j < batch), identical in every lane; the stream is read 32 words at
+  // a time (lane l holds word wbase + l)
   uint64_t rx = 0;
-  long long rpos = 0, rwords = 0;
+  long long rpos = 0, rwords = 0, wbase = 0;
+  uint32_t wbuf = 0;
   const uint32_t* rstream = nullptr;
   bool rbad = false;
   if (p.mode == 1 && j < p.batch && warp == 0) {
     rstream = reinterpret_cast<const uint32_t*>(p.streams + p.stream_off[j]);
     rwords = p.stream_len[j] / 4;
+    wbuf = lane < rwords ? __ldg(rstream + lane) : 0u;
     if (rwords >= 2) {
-      rx = static_cast<uint64_t>(__ldg(rstream)) | (static_cast<uint64_t>(__ldg(rstream + 1)) << 32);
+      rx = static_cast<uint64_t>(__shfl_sync(0xffffffffu, wbuf, 0)) |
+           (static_cast<uint64_t>(__shfl_sync(0xffffffffu, wbuf, 1)) << 32);
       rpos = 2;
     } else {
       rbad = true;
     }
   }
+  auto next_word = [&]() -> uint32_t {  // warp-uniform
+    if (rpos - wbase >= 32) {
+      wbase += 32;
+      wbuf = (wbase + lane) < rwords ? __ldg(rstream + wbase + lane) : 0u;
+    }
+    const uint32_t wv = __shfl_sync(0xffffffffu, wbuf, static_cast<int>(rpos - wbase));
+    ++rpos;
+    return wv;
+  };
 
   const int H = p.h, W = p.w;
   const int n_steps = p.mode == 0 ? (W + 3 * (H - 1)) : H * W;
   unsigned int epoch = 0;
+  // per-phase SM-clock totals of CTA 0 (debug aid, workspace words [16, 36)): A, bar, B, bar, C, bar, D, bar, E, bar
+  long long prof[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+  long long tprev = clock64();
+  auto tick = [&](int slot) {
+    if (j == 0 && tid == 0) {
+      const long long now = clock64();
+      prof[slot] += now - tprev;
+      tprev = now;
+    }
+  };
 
   for (int t = 0; t < n_steps; ++t) {
     // ---- positions of this step
@@ -241,87 +334,235 @@ __global__ void __launch_bounds__(kArThreads, 1) ar_codec_kernel(const ArParams 
       q.g = (static_cast<long long>(q.b) * H + q.hh) * W + q.ww;
       return q;
     };
+    if (p.mode == 0) {
+      // ================= encode: one warp per position, eight positions in flight, staging vector per warp ==========
+      float* myvec = vec + warp * p.kmax;
+      // ---- A: context rows of this CTA
+      for (int i = warp; i < P; i += kArWarps) {
+        const Pix q = pix(i);
+        for (int tap = 0; tap < kArTaps; ++tap) {
+          const int dh = tap < 5 ? -2 : (tap < 10 ? -1 : 0);
+          const int dw = (tap < 5 ? tap : (tap < 10 ? tap - 5 : tap - 10)) - 2;
+          const int h2 = q.hh + dh, w2c = q.ww + dw;
+          const bool inb = h2 >= 0 && w2c >= 0 && w2c < W;
+          const float* src = inb ? p.t_hat + ((static_cast<long long>(q.b) * H + h2) * W + w2c) * C : p.t_hat;
+          for (int k = 4 * lane; k < C; k += 128) cp_async16(myvec + tap * C + k, src + k, inb);
+        }
+        cp_async_commit();
+        cp_async_wait<0>();
+        __syncwarp();
+        warp_matvec(w_ctx, p.rc, KA, myvec, lane, s_res[warp]);
+        if (lane < p.rc) p.ctx_buf[static_cast<long long>(i) * C2 + j * p.rc + lane] = s_res[warp][lane] + b_ctx[lane];
+        __syncwarp();
+      }
+      __syncthreads();
+      tick(0);
+      if (!grid_barrier(p.sync, epoch, &s_flag)) return;
+      tick(1);
+      // ---- B: first EPM layer, context columns + the precomputed static part
+      for (int i = warp; i < P; i += kArWarps) {
+        const Pix q = pix(i);
+        const float* src = p.ctx_buf + static_cast<long long>(i) * C2;
+        for (int k = 4 * lane; k < C2; k += 128) cp_async16(myvec + k, src + k, true);
+        cp_async_commit();
+        const float e0v = lane < p.r1 ? __ldg(p.e0 + q.g * L1 + j * p.r1 + lane) : 0.f;  // in flight with the staging
+        cp_async_wait<0>();
+        __syncwarp();
+        warp_matvec(w0, p.r1, C2, myvec, lane, s_res[warp]);
+        if (lane < p.r1) {
+          float v = s_res[warp][lane] + e0v;
+          v = v > 0.f ? v : v * p.slope;
+          p.h1_buf[static_cast<long long>(i) * L1 + j * p.r1 + lane] = v;
+        }
+        __syncwarp();
+      }
+      __syncthreads();
+      tick(2);
+      if (!grid_barrier(p.sync, epoch, &s_flag)) return;
+      tick(3);
+      // ---- C: second EPM layer
+      for (int i = warp; i < P; i += kArWarps) {
+        const float* src = p.h1_buf + static_cast<long long>(i) * L1;
+        for (int k = 4 * lane; k < L1; k += 128) cp_async16(myvec + k, src + k, true);
+        cp_async_commit();
+        cp_async_wait<0>();
+        __syncwarp();
+        warp_matvec(w1, p.r2, L1, myvec, lane, s_res[warp]);
+        if (lane < p.r2) {
+          float v = s_res[warp][lane] + b1[lane];
+          v = v > 0.f ? v : v * p.slope;
+          p.h2_buf[static_cast<long long>(i) * L2 + j * p.r2 + lane] = v;
+        }
+        __syncwarp();
+      }
+      __syncthreads();
+      tick(4);
+      if (!grid_barrier(p.sync, epoch, &s_flag)) return;
+      tick(5);
+      // ---- D: third EPM layer (sigma and mu of this CTA's channels), quantise / index
+      for (int i = warp; i < P; i += kArWarps) {
+        const Pix q = pix(i);
+        const float* src = p.h2_buf + static_cast<long long>(i) * L2;
+        for (int k = 4 * lane; k < L2; k += 128) cp_async16(myvec + k, src + k, true);
+        cp_async_commit();
+        const float tgt = lane < p.rg ? __ldg(p.target + q.g * C + j * p.rg + lane) : 0.f;
+        cp_async_wait<0>();
+        __syncwarp();
+        warp_matvec(w2, 2 * p.rg, L2, myvec, lane, s_res[warp]);
+        if (lane < p.rg) {
+          const int ch = j * p.rg + lane;
+          const float sigma = s_res[warp][lane] + b2[lane];
+          const float mu = s_res[warp][p.rg + lane] + b2[p.rg + lane];
+          int cnt = 0;
+          for (int k = 0; k + 1 < p.n_scales; ++k) cnt += (sigma <= s_table[k]) ? 1 : 0;
+          const long long e = q.g * C + ch;
+          p.idx[e] = p.n_scales - 1 - cnt;
+          if (p.params_out) {
+            p.params_out[q.g * C2 + ch] = sigma;
+            p.params_out[q.g * C2 + C + ch] = mu;
+          }
+          const float sq = rintf(tgt - mu);  // torch.round: half to even (entropy_models.py:141)
+          p.t_hat[e] = sq + mu;
+          if (p.sym) p.sym[e] = static_cast<int>(sq);
+        }
+        __syncwarp();
+      }
+      __syncthreads();
+      tick(6);
+      if (!grid_barrier(p.sync, epoch, &s_flag)) return;
+      tick(7);
+      continue;
+    }
+
+    // ================= decode: the whole CTA works on one position at a time (P = batch) =================
+    // staging of position i of a phase into vec[i & 1] (one cp.async group; i + 1 is in flight during i)
+    auto stage_ctx = [&](int i) {
+      if (i < P) {
+        const Pix q = pix(i);
+        float* dst = vec + (i & 1) * p.kmax;
+        const int per_tap = C >> 2;
+        for (int c = tid; c < kArTaps * per_tap; c += kArThreads) {
+          const int tap = c / per_tap, k = (c - tap * per_tap) << 2;
+          const int dh = tap < 5 ? -2 : (tap < 10 ? -1 : 0);
+          const int dw = (tap < 5 ? tap : (tap < 10 ? tap - 5 : tap - 10)) - 2;
+          const int h2 = q.hh + dh, w2c = q.ww + dw;
+          const bool inb = h2 >= 0 && w2c >= 0 && w2c < W;
+          const float* src = inb ? p.t_hat + ((static_cast<long long>(q.b) * H + h2) * W + w2c) * C + k : p.t_hat;
+          cp_async16(dst + tap * C + k, src, inb);
+        }
+      }
+      cp_async_commit();
+    };
+    auto stage_lin = [&](const float* buf, int K, int i) {
+      if (i < P) {
+        float* dst = vec + (i & 1) * p.kmax;
+        const float* src = buf + static_cast<long long>(i) * K;
+        for (int k = tid << 2; k < K; k += kArThreads << 2) cp_async16(dst + k, src + k, true);
+      }
+      cp_async_commit();
+    };
 
     // ---- A: context rows of this CTA
-    for (int i = warp; i < P; i += kArWarps) {
-      const Pix q = pix(i);
-      for (int tap = 0; tap < kArTaps; ++tap) {
-        const int dh = tap < 5 ? -2 : (tap < 10 ? -1 : 0);
-        const int dw = (tap < 5 ? tap : (tap < 10 ? tap - 5 : tap - 10)) - 2;
-        const int h2 = q.hh + dh, w2c = q.ww + dw;
-        const bool inb = h2 >= 0 && w2c >= 0 && w2c < W;
-        const float* src = p.t_hat + ((static_cast<long long>(q.b) * H + h2) * W + w2c) * C;
-        for (int k = lane; k < C; k += 32) myvec[tap * C + k] = inb ? __ldcg(src + k) : 0.f;
+    stage_ctx(0);
+    stage_ctx(1);
+    for (int i = 0; i < P; ++i) {
+      cp_async_wait<1>();
+      __syncthreads();
+      cta_segments(w_ctx, p.rc, KA, vec + (i & 1) * p.kmax, warp, lane, s_lp);
+      __syncthreads();
+      stage_ctx(i + 2);
+      for (int r = warp; r < p.rc; r += kArWarps) {
+        const float val = cta_row(s_lp, r, lane);
+        if (lane == 0) p.ctx_buf[static_cast<long long>(i) * C2 + j * p.rc + r] = val + b_ctx[r];
       }
-      __syncwarp();
-      matvec(w_ctx, p.rc, KA, myvec, lane, s_res[warp]);
-      if (lane < p.rc) p.ctx_buf[static_cast<long long>(i) * C2 + j * p.rc + lane] = s_res[warp][lane] + b_ctx[lane];
-      __syncwarp();
+      __syncthreads();
     }
+    cp_async_wait<0>();
+    __syncthreads();
+    tick(0);
     if (!grid_barrier(p.sync, epoch, &s_flag)) return;
+    tick(1);
 
     // ---- B: first EPM layer, context columns + the precomputed static part
-    for (int i = warp; i < P; i += kArWarps) {
-      const Pix q = pix(i);
-      const float* src = p.ctx_buf + static_cast<long long>(i) * C2;
-      for (int k = lane; k < C2; k += 32) myvec[k] = __ldcg(src + k);
-      __syncwarp();
-      matvec(w0, p.r1, C2, myvec, lane, s_res[warp]);
-      if (lane < p.r1) {
-        float v = s_res[warp][lane] + __ldg(p.e0 + q.g * L1 + j * p.r1 + lane);
+    stage_lin(p.ctx_buf, C2, 0);
+    stage_lin(p.ctx_buf, C2, 1);
+    for (int i = 0; i < P; ++i) {
+      const long long gpos = pix(i).g;
+      cp_async_wait<1>();
+      __syncthreads();
+      cta_segments(w0, p.r1, C2, vec + (i & 1) * p.kmax, warp, lane, s_lp);
+      __syncthreads();
+      stage_lin(p.ctx_buf, C2, i + 2);
+      for (int r = warp; r < p.r1; r += kArWarps) {
+        float v = cta_row(s_lp, r, lane) + __ldg(p.e0 + gpos * L1 + j * p.r1 + r);
         v = v > 0.f ? v : v * p.slope;
-        p.h1_buf[static_cast<long long>(i) * L1 + j * p.r1 + lane] = v;
+        if (lane == 0) p.h1_buf[static_cast<long long>(i) * L1 + j * p.r1 + r] = v;
       }
-      __syncwarp();
+      __syncthreads();
     }
+    cp_async_wait<0>();
+    __syncthreads();
+    tick(2);
     if (!grid_barrier(p.sync, epoch, &s_flag)) return;
+    tick(3);
 
     // ---- C: second EPM layer
-    for (int i = warp; i < P; i += kArWarps) {
-      const float* src = p.h1_buf + static_cast<long long>(i) * L1;
-      for (int k = lane; k < L1; k += 32) myvec[k] = __ldcg(src + k);
-      __syncwarp();
-      matvec(w1, p.r2, L1, myvec, lane, s_res[warp]);
-      if (lane < p.r2) {
-        float v = s_res[warp][lane] + b1[lane];
+    stage_lin(p.h1_buf, L1, 0);
+    stage_lin(p.h1_buf, L1, 1);
+    for (int i = 0; i < P; ++i) {
+      cp_async_wait<1>();
+      __syncthreads();
+      cta_segments(w1, p.r2, L1, vec + (i & 1) * p.kmax, warp, lane, s_lp);
+      __syncthreads();
+      stage_lin(p.h1_buf, L1, i + 2);
+      for (int r = warp; r < p.r2; r += kArWarps) {
+        float v = cta_row(s_lp, r, lane) + b1[r];
         v = v > 0.f ? v : v * p.slope;
-        p.h2_buf[static_cast<long long>(i) * L2 + j * p.r2 + lane] = v;
+        if (lane == 0) p.h2_buf[static_cast<long long>(i) * L2 + j * p.r2 + r] = v;
       }
-      __syncwarp();
+      __syncthreads();
     }
+    cp_async_wait<0>();
+    __syncthreads();
+    tick(4);
     if (!grid_barrier(p.sync, epoch, &s_flag)) return;
+    tick(5);
 
-    // ---- D: third EPM layer (sigma and mu of this CTA's channels), quantise / index
-    for (int i = warp; i < P; i += kArWarps) {
-      const Pix q = pix(i);
-      const float* src = p.h2_buf + static_cast<long long>(i) * L2;
-      for (int k = lane; k < L2; k += 32) myvec[k] = __ldcg(src + k);
-      __syncwarp();
-      matvec(w2, 2 * p.rg, L2, myvec, lane, s_res[warp]);
-      if (lane < p.rg) {
-        const int ch = j * p.rg + lane;
-        const float sigma = s_res[warp][lane] + b2[lane];
-        const float mu = s_res[warp][p.rg + lane] + b2[p.rg + lane];
+    // ---- D: third EPM layer (sigma and mu of this CTA's channels), index
+    stage_lin(p.h2_buf, L2, 0);
+    stage_lin(p.h2_buf, L2, 1);
+    for (int i = 0; i < P; ++i) {
+      const long long gpos = pix(i).g;
+      cp_async_wait<1>();
+      __syncthreads();
+      cta_segments(w2, 2 * p.rg, L2, vec + (i & 1) * p.kmax, warp, lane, s_lp);
+      __syncthreads();
+      stage_lin(p.h2_buf, L2, i + 2);
+      for (int r = warp; r < p.rg; r += kArWarps) {
+        const int ch = j * p.rg + r;
+        const float sigma = cta_row(s_lp, r, lane) + b2[r];
+        const float mu = cta_row(s_lp, p.rg + r, lane) + b2[p.rg + r];
+        // index = (n_scales - 1) - #{k < n_scales - 1 : sigma <= table[k]}, lanes share the table
         int cnt = 0;
-        for (int k = 0; k + 1 < p.n_scales; ++k) cnt += (sigma <= __ldg(p.table + k)) ? 1 : 0;
-        const int index = p.n_scales - 1 - cnt;
-        const long long e = q.g * C + ch;
-        p.idx[e] = index;
-        if (p.params_out) {
-          p.params_out[q.g * C2 + ch] = sigma;
-          p.params_out[q.g * C2 + C + ch] = mu;
-        }
-        if (p.mode == 0) {
-          const float s = rintf(__ldg(p.target + e) - mu);  // torch.round: half to even (entropy_models.py:141)
-          p.t_hat[e] = s + mu;
-          if (p.sym) p.sym[e] = static_cast<int>(s);
-        } else {
+        for (int k = lane; k + 1 < p.n_scales; k += 32) cnt += (sigma <= s_table[k]) ? 1 : 0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+        if (lane == 0) {
+          p.idx[gpos * C + ch] = p.n_scales - 1 - cnt;
+          if (p.params_out) {
+            p.params_out[gpos * C2 + ch] = sigma;
+            p.params_out[gpos * C2 + C + ch] = mu;
+          }
           p.mu_buf[static_cast<long long>(i) * C + ch] = mu;
         }
       }
-      __syncwarp();
+      __syncthreads();
     }
+    cp_async_wait<0>();
+    __syncthreads();
+    tick(6);
     if (!grid_barrier(p.sync, epoch, &s_flag)) return;
+    tick(7);
 
     if (p.mode == 1) {
       // ---- E: rANS decode of this position, image j, by warp 0 (rans_interface.cpp:226-275 semantics)
@@ -329,60 +570,52 @@ __global__ void __launch_bounds__(kArThreads, 1) ar_codec_kernel(const ArParams 
         const Pix q = pix(j);
         const long long e0i = q.g * C;
         for (int ch = lane; ch < C; ch += 32) {
-          int ci = __ldcg(p.idx + e0i + ch);
+          const int ci = __ldcg(p.idx + e0i + ch);
           s_idx[ch] = ci < 0 ? 0 : (ci >= p.n_cdfs ? p.n_cdfs - 1 : ci);
         }
         __syncwarp();
+        // row data of the next symbol is fetched while the current one is resolved (it does not depend on the state)
+        int ci = s_idx[0];
+        int4 mt = s_meta[ci];
+        uint32_t l1v = static_cast<uint32_t>(s_l1[ci][lane]);
         for (int ch = 0; ch < C; ++ch) {
+          const int ci_n = s_idx[ch + 1 < C ? ch + 1 : ch];
+          const int4 mt_n = s_meta[ci_n];
+          const uint32_t l1_n = static_cast<uint32_t>(s_l1[ci_n][lane]);
           int value = 0;
           if (!rbad) {
-            const int ci = s_idx[ch];
-            const int32_t* row = p.cdf + static_cast<long long>(ci) * p.cdf_stride;
-            const int size = s_size[ci];
-            const int n = size - 1;  // candidates s in [0, n): row[s] <= cum < row[s+1]
+            const uint16_t* row = cdf16 + mt.x;
+            const int size = mt.y, n = size - 1, step = mt.w;  // candidates s in [0, n): row[s] <= cum < row[s+1]
             const uint32_t cum = static_cast<uint32_t>(rx & 0xFFFFu);
-            uint32_t start = 0, freq = 0;
-            int s_found = 0;
-            if (n >= 1) {
-              const int step = (n + 31) >> 5;
-              const unsigned int m1 = __ballot_sync(0xffffffffu, static_cast<uint32_t>(s_l1[ci][lane]) <= cum);
-              const int k = m1 ? 31 - __clz(m1) : 0;
+            const unsigned int m1 = __ballot_sync(0xffffffffu, l1v <= cum);
+            const int k = m1 ? 31 - __clz(m1) : 0;
+            int s_found = k;
+            if (step > 1) {
               const int slo = k * step;
               const int rem = (n - slo) < step ? (n - slo) : step;  // 1 <= rem <= 98
-              uint32_t v[4];
               int cnt = 0;
-#pragma unroll
-              for (int jj = 0; jj < 4; ++jj) {
-                const int o = lane + 32 * jj;
-                v[jj] = o <= rem ? static_cast<uint32_t>(__ldg(row + slo + o)) : 0xFFFFFFFFu;
+              for (int o0 = 0; o0 < rem; o0 += 32) {
+                const int o = o0 + lane;
+                cnt += __popc(__ballot_sync(0xffffffffu, o < rem && static_cast<uint32_t>(row[slo + o]) <= cum));
               }
-#pragma unroll
-              for (int jj = 0; jj < 4; ++jj)
-                cnt += __popc(__ballot_sync(0xffffffffu, (lane + 32 * jj) < rem && v[jj] <= cum));
-              if (cnt < 1) cnt = 1;  // corrupt table / stream: stay in range, flagged below
-              const int o0 = cnt - 1, o1 = cnt;
-              uint32_t a = 0, b = 0;
-#pragma unroll
-              for (int jj = 0; jj < 4; ++jj) {
-                const uint32_t t0 = __shfl_sync(0xffffffffu, v[jj], o0 & 31);
-                const uint32_t t1 = __shfl_sync(0xffffffffu, v[jj], o1 & 31);
-                if ((o0 >> 5) == jj) a = t0;
-                if ((o1 >> 5) == jj) b = t1;
-              }
-              start = a;
-              freq = b - a;
-              s_found = slo + o0;
+              s_found = slo + (cnt > 0 ? cnt - 1 : 0);
             }
-            if (freq == 0 || freq > 65536u || cum < start || cum >= start + freq) rbad = true;
+            uint32_t start = 0, nxt = 0;
+            if (n >= 1) {
+              start = row[s_found];
+              nxt = (s_found + 1 >= n) ? 65536u : static_cast<uint32_t>(row[s_found + 1]);
+            }
+            const uint32_t freq = nxt - start;
+            if (freq == 0 || freq > 65536u || cum < start || cum >= nxt) rbad = true;
             rx = static_cast<uint64_t>(freq) * (rx >> 16) + cum - start;
-            if (rx < kRansL && rpos < rwords) rx = (rx << 32) | __ldg(rstream + rpos++);
+            if (rx < kRansL && rpos < rwords) rx = (rx << 32) | next_word();
             value = s_found;
             if (s_found == size - 2) {
               // bypass: nibble count (unary in chunks of 15), then the nibbles, least significant first
               auto get4 = [&]() -> int {
                 const int v4 = static_cast<int>(rx & 15u);
                 rx >>= 4;
-                if (rx < kRansL && rpos < rwords) rx = (rx << 32) | __ldg(rstream + rpos++);
+                if (rx < kRansL && rpos < rwords) rx = (rx << 32) | next_word();
                 return v4;
               };
               int v4 = get4();
@@ -400,20 +633,30 @@ __global__ void __launch_bounds__(kArThreads, 1) ar_codec_kernel(const ArParams 
               if (raw & 1u) value = -value - 1;
               else value += size - 2;
             }
-            value += s_off[ci];
+            value += mt.z;
           }
           if (lane == 0) s_sym[ch] = value;
+          ci = ci_n;
+          mt = mt_n;
+          l1v = l1_n;
         }
         __syncwarp();
         for (int ch = lane; ch < C; ch += 32) {
-          const int s = s_sym[ch];
+          const int sv = s_sym[ch];
           const float mu = __ldcg(p.mu_buf + static_cast<long long>(j) * C + ch);
-          p.t_hat[e0i + ch] = static_cast<float>(s) + mu;
-          if (p.sym) p.sym[e0i + ch] = s;
+          p.t_hat[e0i + ch] = static_cast<float>(sv) + mu;
+          if (p.sym) p.sym[e0i + ch] = sv;
         }
       }
+      __syncthreads();
+      tick(8);
       if (!grid_barrier(p.sync, epoch, &s_flag)) return;
+      tick(9);
     }
+  }
+  if (j == 0 && tid == 0) {
+    long long* out = reinterpret_cast<long long*>(p.sync + 16);
+    for (int i = 0; i < 10; ++i) out[i] = prof[i];
   }
   if (p.mode == 1 && j < p.batch && warp == 0 && lane == 0) p.status[j] = rbad ? 1 : 0;
 }
@@ -421,9 +664,9 @@ __global__ void __launch_bounds__(kArThreads, 1) ar_codec_kernel(const ArParams 
 int fill_params(const stemb200_ar_desc* d, ArParams& p) {
   if (!d) return set_error("ar: null descriptor");
   if (d->batch < 1 || d->batch > kArCtas || d->h < 1 || d->w < 1) return set_error("ar: bad shape (batch <= 64)");
-  if (d->c < 64 || d->c % 64 || d->c > 256 || d->l1 < 64 || d->l1 % 64 || d->l2 < 64 || d->l2 % 64)
+  if (d->c < 64 || d->c % 64 || d->c > 320 || d->l1 < 64 || d->l1 % 64 || d->l2 < 64 || d->l2 % 64)
     return set_error("ar: c (<= 256), l1, l2 must be multiples of 64");
-  if (d->n_scales < 2) return set_error("ar: scale table needs >= 2 entries");
+  if (d->n_scales < 2 || d->n_scales > kArMaxScales) return set_error("ar: scale table needs 2..256 entries");
   p.batch = d->batch;
   p.h = d->h;
   p.w = d->w;
@@ -434,7 +677,8 @@ int fill_params(const stemb200_ar_desc* d, ArParams& p) {
   p.r1 = d->l1 / kArCtas;
   p.r2 = d->l2 / kArCtas;
   p.rg = d->c / kArCtas;
-  if (p.rc > 16 || p.r1 > 16 || p.r2 > 16) return set_error("ar: layer too wide");
+  if (p.rc > kArMaxRows || p.r1 > kArMaxRows || p.r2 > kArMaxRows || 2 * p.rg > kArMaxRows)
+    return set_error("ar: layer too wide (at most 12 rows per CTA: 2c, l1, l2 <= 768)");
   p.kmax = std::max(std::max(kArTaps * d->c, 2 * d->c), std::max(d->l1, d->l2));
   p.n_scales = d->n_scales;
   p.slope = d->slope;
@@ -466,8 +710,10 @@ Scratch carve(const stemb200_ar_desc* d, void* ws) {
 }
 
 int launch_ar(ArParams& p, cudaStream_t st) {
-  const size_t smem = (static_cast<size_t>((p.block_floats + 3) & ~3) + static_cast<size_t>(kArWarps) * p.kmax) * 4;
+  const size_t smem = (static_cast<size_t>((p.block_floats + 3) & ~3) + static_cast<size_t>(p.nstage) * p.kmax) * 4 +
+                      static_cast<size_t>(p.cdf16_entries + 8) * 2;
   if (smem > 227 * 1024) return set_error("ar: weights + staging exceed shared memory");
+  if (smem > 215 * 1024) return set_error("ar: weights + staging + CDF table exceed shared memory");
   static size_t configured = 0;
   if (configured < smem) {
     cudaError_t e = cudaFuncSetAttribute(ar_codec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -513,6 +759,8 @@ extern "C" int stemb200_ar_encode(const stemb200_ar_desc* d, const float* packed
   if (int rc = fill_params(d, p)) return rc;
   const Scratch s = carve(d, workspace);
   p.mode = 0;
+  p.nstage = kArWarps;
+  p.cdf16_entries = 0;
   p.packed = packed;
   p.e0 = e0;
   p.target = target;
@@ -532,16 +780,19 @@ extern "C" int stemb200_ar_encode(const stemb200_ar_desc* d, const float* packed
 extern "C" int stemb200_ar_decode(const stemb200_ar_desc* d, const float* packed, const float* e0,
                                   const float* scale_table, const uint8_t* streams, const int64_t* stream_off,
                                   const int64_t* stream_len, const int32_t* cdfs, int32_t n_cdfs, int32_t cdf_stride,
-                                  const int32_t* cdf_sizes, const int32_t* offsets, float* t_hat, int32_t* symbols,
-                                  int32_t* indexes, float* params_out, int32_t* status, void* workspace,
-                                  void* stream) {
+                                  const int32_t* cdf_sizes, const int32_t* offsets, int32_t cdf_total_entries,
+                                  float* t_hat, int32_t* symbols, int32_t* indexes, float* params_out,
+                                  int32_t* status, void* workspace, void* stream) {
   if (!packed || !e0 || !scale_table || !streams || !stream_off || !stream_len || !cdfs || !cdf_sizes || !offsets ||
-      !t_hat || !indexes || !status || !workspace || n_cdfs < 1 || n_cdfs > kArMaxCdfs || cdf_stride < 2)
+      !t_hat || !indexes || !status || !workspace || n_cdfs < 1 || n_cdfs > kArMaxCdfs || cdf_stride < 2 ||
+      cdf_total_entries < 2 * n_cdfs || cdf_total_entries > n_cdfs * cdf_stride)
     return set_error("ar_decode: null / bad argument (at most 64 CDF rows)");
   ArParams p{};
   if (int rc = fill_params(d, p)) return rc;
   const Scratch s = carve(d, workspace);
   p.mode = 1;
+  p.nstage = 2;
+  p.cdf16_entries = cdf_total_entries;
   p.packed = packed;
   p.e0 = e0;
   p.table = scale_table;

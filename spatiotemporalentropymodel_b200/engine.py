@@ -325,7 +325,8 @@ class ArHead:
         _lib.check(self.lib.stemb200_ar_decode(
             C.byref(d), self.packed.data_ptr(), e0.data_ptr(), table.data_ptr(), blob.data_ptr(), t_off.data_ptr(),
             t_len.data_ptr(), cdf_d.data_ptr(), cdf_d.shape[0], cdf_d.shape[1], len_d.data_ptr(), off_d.data_ptr(),
-            t_hat.data_ptr(), None, idx.data_ptr(), params.data_ptr(), status.data_ptr(),
+            int(cdf_length.detach().sum().item()), t_hat.data_ptr(), None, idx.data_ptr(), params.data_ptr(),
+            status.data_ptr(),
             self._workspace(d).data_ptr(), _stream()), "ar_decode")
         if int(status.max().item()) != 0:
             raise _lib.StemLibError("ar_decode: corrupt rANS stream")
