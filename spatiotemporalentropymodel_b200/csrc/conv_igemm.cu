@@ -65,6 +65,7 @@ struct ConvKernelParams {
   alignas(64) CUtensorMap b_half_map;  // box {64, BLOCK_N / 2}
   alignas(64) CUtensorMap g_half_map;
   int csize;
+  int kk_main;  // K = 16 slices issued per main-loop k-step (4; 3 in row_taps mode: 5 taps x 8 channels = 40 <= 48)
   // fused GDN / IGDN (conv_gdn_kernel only)
   alignas(64) CUtensorMap g_map;  // gamma [c_out][c_out] fp16, K-major
   const float* beta;
@@ -674,7 +675,7 @@ conv_gdn_kernel(const __grid_constant__ ConvKernelParams p) {
       const uint64_t bdesc = umma_desc_sw128(a_addr + kAStageBytes);
 #pragma unroll
       for (int kk = 0; kk < 4; ++kk)
-        mma_f16_ss(d_tmem, adesc + 2u * kk, bdesc + 2u * kk, idesc, (!first || kk > 0) ? 1u : 0u);
+        if (kk < p.kk_main) mma_f16_ss(d_tmem, adesc + 2u * kk, bdesc + 2u * kk, idesc, (!first || kk > 0) ? 1u : 0u);
       if (pair) mma_commit_mc(empty_bar(s), 3);
       else mma_commit(empty_bar(s));
       if (++s == kStages) {
@@ -1344,6 +1345,7 @@ int setup_params(const stemb200_conv_desc* d, const Plan& pl, const void* const*
     kp.csize = 2;
     if (int rc = encode_weight(&kp.b_half_map, packed_weight, K, d->c_out, pl.block_n / 2)) return rc;
   }
+  kp.kk_main = (pl.row_taps && d->kw * 8 <= 48) ? 3 : 4;
   kp.c_out = d->c_out;
   kp.slope = d->lrelu_slope;
   kp.sq_scale = d->sq_scale;

@@ -75,6 +75,37 @@ def test_c_abi_rejects_bad_arguments_without_a_gpu():
     assert lib.stemb200_synthesis_tail(None, None, 1, 1, 1, None, 0, 0, 0, 0, None, 1, None) == -1
 
 
+def test_ar_and_row_taps_abi_validation_without_a_gpu():
+    """stemb200_ar_* and the row_taps first-layer mode validate their descriptors on the host."""
+    lib = _lib.load()
+    header = open(os.path.join(REPO, "include", "stemb200.h")).read()
+    body = header.split("typedef struct stemb200_ar_desc {")[1].split("} stemb200_ar_desc;")[0]
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    fields = [n.strip() for decl in body.split(";") if decl.strip() for n in decl.strip().split(None, 1)[1].split(",")]
+    assert fields == [f[0] for f in _lib.ArDesc._fields_]
+    a = _lib.ArDesc()
+    a.batch, a.h, a.w, a.c, a.l1, a.l2, a.slope, a.n_scales = 1, 68, 120, 192, 768, 576, 0.01, 64
+    per_cta = 6 * 12 * 192 + 6 + 12 * 384 + 9 * 768 + 9 + 6 * 576 + 6          # ctx | b | L0 ctx cols | L1 | b1 | L2 | b2
+    assert lib.stemb200_ar_packed_floats(ctypes.byref(a)) == 64 * per_cta
+    assert lib.stemb200_ar_workspace_bytes(ctypes.byref(a)) == 4 * (64 + 41 * (384 + 768 + 576 + 192))
+    a.l1 = 700
+    assert lib.stemb200_ar_packed_floats(ctypes.byref(a)) == -1                # widths are multiples of 64
+    a.l1 = 768
+    assert lib.stemb200_ar_encode(ctypes.byref(a), None, None, None, None, None, None, None, None, None, None) == -1
+    assert b"null argument" in lib.stemb200_last_error()
+    assert lib.stemb200_ar_decode(ctypes.byref(a), None, None, None, None, None, None, None, 64, 3133, None, None, 27256,
+                                  None, None, None, None, None, None, None) == -1
+    d = _lib.ConvDesc()
+    d.batch, d.h_in, d.w_in, d.n_src, d.c_out, d.kh, d.kw, d.stride, d.row_taps = 1, 64, 64, 1, 192, 5, 5, 2, 1
+    d.c_in[0] = 8
+    assert lib.stemb200_conv2d_packed_k(ctypes.byref(d)) == 5 * 64             # one 64-wide K step per kernel row
+    d.h_in = 63
+    assert lib.stemb200_conv2d_packed_k(ctypes.byref(d)) == -1                 # needs even input sides
+    d.h_in, d.c_in[0] = 64, 16
+    assert lib.stemb200_conv2d_packed_k(ctypes.byref(d)) == -1                 # canvas has exactly 8 channels
+    assert lib.stemb200_frame_to_nhwc8(None, None, 1, 3, 8, 8, 8, 8, 0, 0, 2, None) == -1
+
+
 @pytest.mark.parametrize("variant", S.STEM_VARIANTS)
 def test_state_dict_contract(variant):
     """The synthetic state_dicts were loaded (strict) by the reference classes when the goldens were made; the
