@@ -119,6 +119,24 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+def init_dist(dev):
+    """init_process_group + first collective with fd 1 pointed at stderr: NCCL prints its version banner on stdout
+    when the communicator is created, and stdout must carry exactly one JSON line."""
+    import torch.distributed as dist
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    try:
+        dist.init_process_group("nccl", device_id=dev)
+        t = torch.zeros(1, device=dev)
+        dist.all_reduce(t)
+        torch.cuda.synchronize()
+    finally:
+        sys.stdout.flush()
+        os.dup2(saved, 1)
+        os.close(saved)
+
+
 def load_peaks():
     p = os.path.join(REPO, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -193,9 +211,7 @@ def run_stem_roi(args):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"
-        dist.init_process_group("nccl", device_id=dev)
+        init_dist(dev)
     from spatiotemporalentropymodel_b200 import _lib, stem_roi as R, synthetic as S
     from spatiotemporalentropymodel_b200.engine import ConvOp
     _, T, H, W, desc = WORKLOADS[args.workload]
@@ -395,9 +411,7 @@ def main():
     dev = torch.device("cuda", local_rank)
     import torch.distributed as dist
     if world > 1:
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"  # keep stdout to the one JSON line (NCCL prints its version there)
-        dist.init_process_group("nccl", device_id=dev)
+        init_dist(dev)
 
     from spatiotemporalentropymodel_b200 import _lib, models as M, synthetic as S
     from spatiotemporalentropymodel_b200.dist import reduce_stats
