@@ -562,7 +562,20 @@ def main():
             recs.append((a, b, self.alg_flops(batch, h, w), self.gdn is not None))
             return r
 
+        orig_last = E.ConvOp.call_last
+
+        def timed_last(self, inputs, batch, h, w, w6, col, act=None):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            r = orig_last(self, inputs, batch, h, w, w6, col, act)
+            b.record()
+            # gs4 (deconv + IGDN) and the final deconv(N, 3) GEMM run in this one launch
+            fl = self.alg_flops(batch, h, w) + self.alg_flops_per_out_pixel_last * batch * 4 * h * w
+            recs.append((a, b, fl, True))
+            return r
+
         E.ConvOp.__call__ = timed_call
+        E.ConvOp.call_last = timed_last
         try:
             for _ in range(2):
                 recs.clear()
@@ -570,6 +583,7 @@ def main():
                 torch.cuda.synchronize()
         finally:
             E.ConvOp.__call__ = orig
+            E.ConvOp.call_last = orig_last
         dom = [(a.elapsed_time(b), f) for a, b, f, fused in recs if fused]
         allc = [(a.elapsed_time(b), f) for a, b, f, fused in recs]
         dom_ms, dom_gf = sum(t for t, _ in dom), sum(f for _, f in dom) / 1e9

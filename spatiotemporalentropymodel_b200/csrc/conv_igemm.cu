@@ -65,6 +65,11 @@ struct ConvKernelParams {
   alignas(64) CUtensorMap b_half_map;  // box {64, BLOCK_N / 2}
   alignas(64) CUtensorMap g_half_map;
   int csize;
+  // fused last synthesis layer (conv_gdn_kernel<.., kLast = true>): every output pixel of this layer is multiplied by
+  // W6 [96][c_out] (deconv(N, 3, k5 s2) as 75 (+21 zero) per-pixel contributions (r, s, c)), the "col" rows go to HBM
+  alignas(64) CUtensorMap w6_map;
+  __half* col_out;  // [batch][full_h][full_w][96] fp16
+  int store_act;    // 0: the layer's own activation is not written at all
   int kk_main;  // K = 16 slices issued per main-loop k-step (4; 3 in row_taps mode: 5 taps x 8 channels = 40 <= 48)
   // fused GDN / IGDN (conv_gdn_kernel only)
   alignas(64) CUtensorMap g_map;  // gamma [c_out][c_out] fp16, K-major
@@ -522,18 +527,22 @@ conv_igemm_kernel(const __grid_constant__ ConvKernelParams p) {
 // (x s) * sqrt(beta / s^2 + acc / s^4) for IGDN: one FFMA + one MUFU + one FMUL per element.
 // Replaces layers/gdn.py:52-67 + the producing conv (priors.py:421-439) without x or x^2 ever reaching HBM.
 // =====================================================================================================
-template <int kNT>
+constexpr int kLastN = 96;  // columns of the fused last-layer GEMM (75 real)
+
+template <int kNT, bool kLast = false>
 struct GdnCfgT {
   static constexpr int kN = kNT;
   static constexpr int kBStageBytes = kN * 128;
   static constexpr int kStageBytes = kAStageBytes + kBStageBytes;
-  static constexpr int kStages = 4;
+  static constexpr int kStages = kLast ? 3 : 4;  // the resident W6 operand takes one stage's worth of shared memory
   static constexpr int kA2Bytes = (kN / 64) * kAStageBytes;  // x^2 operand (64-channel chunks); reused as output staging
+  static constexpr int kW6Bytes = kLast ? (kN / 64) * kLastN * 128 : 0;
   static constexpr int kBarrierBytes = 256 + 2 * kN * 4;
-  static constexpr int kSmemBytes = 1024 + kStages * kStageBytes + kA2Bytes + kBarrierBytes;
+  static constexpr int kSmemBytes = 1024 + kStages * kStageBytes + kA2Bytes + kW6Bytes + kBarrierBytes;
   static constexpr int kTmemCols = 512;
   static constexpr uint32_t kStashCol = 2 * kN;
   static_assert(kN % 64 == 0 && 2 * kN + kN / 2 <= 512, "TMEM budget");
+  static_assert(!kLast || kN / 2 >= kLastN, "the last-layer accumulator reuses the stash columns");
   static_assert(kSmemBytes <= kSmemLimit, "smem overflow");
 };
 
@@ -541,10 +550,10 @@ constexpr int kGdnEpiWarps = 16;                        // 4 per TMEM lane group
 constexpr int kGdnEpiThreads = kGdnEpiWarps * 32;       // 512
 constexpr int kGdnThreads = 128 + kGdnEpiThreads;       // 4 control warps + 16 epilogue warps
 
-template <int kNT, bool kInverse>
+template <int kNT, bool kInverse, bool kLast = false>
 __global__ void __launch_bounds__(kGdnThreads, 1)
 conv_gdn_kernel(const __grid_constant__ ConvKernelParams p) {
-  using Cfg = GdnCfgT<kNT>;
+  using Cfg = GdnCfgT<kNT, kLast>;
   constexpr int kStages = Cfg::kStages;
   constexpr int BLOCK_N = Cfg::kN;
   constexpr int kGChunks = BLOCK_N / kKChunk;
@@ -553,7 +562,8 @@ conv_gdn_kernel(const __grid_constant__ ConvKernelParams p) {
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t stage_base = smem_base;
   const uint32_t a2_base = smem_base + kStages * Cfg::kStageBytes;
-  const uint32_t bar_base = a2_base + Cfg::kA2Bytes;
+  const uint32_t w6_base = a2_base + Cfg::kA2Bytes;  // kLast: W6 as K-major chunks [kN/64][96 rows][128 B]
+  const uint32_t bar_base = w6_base + Cfg::kW6Bytes;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (kStages + s); };
   const uint32_t tfull_bar = bar_base + 8u * (2 * kStages);
@@ -561,6 +571,9 @@ conv_gdn_kernel(const __grid_constant__ ConvKernelParams p) {
   const uint32_t nfull_bar = bar_base + 8u * (2 * kStages + 2);
   auto accfree_bar = [&](int a) { return bar_base + 8u * (2 * kStages + 3 + a); };
   const uint32_t tmem_slot = bar_base + 8u * (2 * kStages + 5);
+  const uint32_t w6full_bar = bar_base + 8u * (2 * kStages + 6);  // kLast only
+  const uint32_t a3rdy_bar = bar_base + 8u * (2 * kStages + 7);
+  const uint32_t d3full_bar = bar_base + 8u * (2 * kStages + 8);
   const uint32_t bias_smem = bar_base + 256u;
   const uint32_t beta_smem = bias_smem + 4u * BLOCK_N;
 
@@ -588,6 +601,11 @@ conv_gdn_kernel(const __grid_constant__ ConvKernelParams p) {
     mbar_init(nfull_bar, 1);
     mbar_init(accfree_bar(0), kGdnEpiWarps);
     mbar_init(accfree_bar(1), kGdnEpiWarps);
+    if constexpr (kLast) {
+      mbar_init(w6full_bar, 1);
+      mbar_init(a3rdy_bar, kGdnEpiWarps);
+      mbar_init(d3full_bar, 1);
+    }
     fence_barrier_init();
   }
   if (warp == 2) {
@@ -652,6 +670,12 @@ conv_gdn_kernel(const __grid_constant__ ConvKernelParams p) {
         }
       }
     };
+    if constexpr (kLast) {
+      tma_prefetch_desc(&p.w6_map);
+      mbar_arrive_expect_tx(w6full_bar, Cfg::kW6Bytes);
+      for (int kc = 0; kc < kGChunks; ++kc)
+        tma_load_2d(w6_base + kc * (kLastN * 128), &p.w6_map, w6full_bar, kc * kKChunk, 0);
+    }
     int it = 0;
     for (int tile = q_first; tile < n_items; tile += q_stride, ++it) {
       const TileCoord t = decode_tile(p, tile, crank, BLOCK_N);
@@ -667,8 +691,40 @@ conv_gdn_kernel(const __grid_constant__ ConvKernelParams p) {
     constexpr uint32_t idesc = umma_idesc(/*F16*/ 0u, 128u, BLOCK_N);
     int s = 0;
     uint32_t ph = 0;
+    // kLast: col(j) = out(j) . W6^T once phase 2 of tile j has left the layer's output in the x^2 buffers; it can
+    // become ready at any point of this thread's program, so every wait below polls for it.
+    int n3_done = 0;
+    bool w6_ready = false;
+    auto try_mma3 = [&]() {
+      if constexpr (kLast) {
+        if (!mbar_try_wait(a3rdy_bar, n3_done & 1)) return;
+        if (!w6_ready) {
+          mbar_wait(w6full_bar, 0);
+          w6_ready = true;
+        }
+        tc_fence_after();
+        constexpr uint32_t idesc3 = umma_idesc(/*F16*/ 0u, 128u, kLastN);
+        for (int kc = 0; kc < kGChunks; ++kc) {
+          const uint64_t adesc = umma_desc_sw128(a2_base + kc * kAStageBytes);
+          const uint64_t bdesc = umma_desc_sw128(w6_base + kc * (kLastN * 128));
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk)
+            mma_f16_ss(tmem_base + Cfg::kStashCol, adesc + 2u * kk, bdesc + 2u * kk, idesc3,
+                       (kc > 0 || kk > 0) ? 1u : 0u);
+        }
+        mma_commit(d3full_bar);
+        ++n3_done;
+      }
+    };
+    auto wait_bar = [&](uint32_t bar, uint32_t parity) {
+      if constexpr (kLast) {
+        while (!mbar_try_wait(bar, parity)) try_mma3();
+      } else {
+        mbar_wait(bar, parity);
+      }
+    };
     auto mma_main = [&](uint32_t d_tmem, bool first) {
-      mbar_wait(full_bar(s), ph);
+      wait_bar(full_bar(s), ph);
       tc_fence_after();
       const uint32_t a_addr = stage_base + s * Cfg::kStageBytes;
       const uint64_t adesc = umma_desc_sw128(a_addr);
@@ -682,14 +738,15 @@ conv_gdn_kernel(const __grid_constant__ ConvKernelParams p) {
         s = 0;
         ph ^= 1u;
       }
+      try_mma3();
     };
     // norm(j) = gamma . (x s)^2 into the accumulator tile j just vacated
     auto mma_gamma = [&](int j) {
-      mbar_wait(a2rdy_bar, j & 1);
+      wait_bar(a2rdy_bar, j & 1);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + (j & 1) * BLOCK_N;
       for (int kc = 0; kc < kGChunks; ++kc) {
-        mbar_wait(full_bar(s), ph);
+        wait_bar(full_bar(s), ph);
         tc_fence_after();
         const uint64_t adesc = umma_desc_sw128(a2_base + kc * kAStageBytes);
         const uint64_t bdesc = umma_desc_sw128(stage_base + s * Cfg::kStageBytes + kAStageBytes);
@@ -712,7 +769,7 @@ conv_gdn_kernel(const __grid_constant__ ConvKernelParams p) {
       const int ksplit = kbeg + ((kend - kbeg) >> 1);
       const uint32_t d_tmem = tmem_base + (it & 1) * BLOCK_N;
       if (it >= 2) {  // phase 2 of tile it-2 has finished reading this accumulator
-        mbar_wait(accfree_bar(it & 1), ((it >> 1) - 1) & 1);
+        wait_bar(accfree_bar(it & 1), ((it >> 1) - 1) & 1);
         tc_fence_after();
       }
       for (int k = kbeg; k < ksplit; ++k) mma_main(d_tmem, k == kbeg);
@@ -721,6 +778,9 @@ conv_gdn_kernel(const __grid_constant__ ConvKernelParams p) {
       mma_commit(tfull_bar);
     }
     if (it > 0) mma_gamma(it - 1);
+    if constexpr (kLast) {
+      while (n3_done < it) try_mma3();
+    }
   } else if (warp >= 4) {
     // ===================== epilogue: 16 warps =====================
     // warp e reads TMEM lane group e % 4 (the hardware's warp -> lane-group rule) and the 16-column quarter e / 4
@@ -848,12 +908,50 @@ conv_gdn_kernel(const __grid_constant__ ConvKernelParams p) {
                        : "memory");
           fence_proxy_async_smem();
           named_bar_sync(1, kGdnEpiThreads);
-          if (etid == 0) {
+          if (etid == 0 && (!kLast || p.store_act)) {
             tma_store_4d(&p.out_map[t.sub], a2_base + static_cast<uint32_t>(g) * kAStageBytes, 64 * g, t.w0, t.h0,
                          t.n_img);
             tma_store_commit();
           }
         }
+      }
+      if constexpr (kLast) {
+        // ---- phase 3: the layer's output tile (K-major in the x^2 buffers) times W6 on the tensor core, accumulator in
+        // the (dead) stash columns; this thread's 24 of the 96 columns go to the col buffer as fp16
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(a3rdy_bar);
+        mbar_wait(d3full_bar, par);
+        tc_fence_after();
+        uint32_t d[24];
+        {
+          uint32_t d16[16], d8[8];
+          const uint32_t d3_col = tmem_base + lane_off + Cfg::kStashCol + 24 * q;
+          tmem_ld_32x16(d3_col, d16);
+          tmem_ld_32x8(d3_col + 16, d8);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 16; ++i) d[i] = d16[i];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) d[16 + i] = d8[i];
+        }
+        const int th = row / p.tile_w, tw = row - th * p.tile_w;
+        const int oh = t.h0 + th, ow = t.w0 + tw;
+        if (row < p.tile_h * p.tile_w && oh < p.h_out && ow < p.w_out) {
+          const long long pix =
+              (static_cast<long long>(t.n_img) * p.full_h + (oh * p.os + p.sub_p[t.sub])) * p.full_w +
+              (ow * p.os + p.sub_q[t.sub]);
+          uint4* dst = reinterpret_cast<uint4*>(p.col_out + pix * kLastN + 24 * q);
+#pragma unroll
+          for (int i = 0; i < 3; ++i)
+            dst[i] = make_uint4(pack_half2(__uint_as_float(d[8 * i]), __uint_as_float(d[8 * i + 1])),
+                                pack_half2(__uint_as_float(d[8 * i + 2]), __uint_as_float(d[8 * i + 3])),
+                                pack_half2(__uint_as_float(d[8 * i + 4]), __uint_as_float(d[8 * i + 5])),
+                                pack_half2(__uint_as_float(d[8 * i + 6]), __uint_as_float(d[8 * i + 7])));
+        }
+        // the next tile's phase 1 writes its stash into these columns: every warp must be done reading them
+        tc_fence_before();
+        named_bar_sync(1, kGdnEpiThreads);
       }
     }
     if (etid == 0) tma_store_wait_all<0>();
@@ -1402,21 +1500,21 @@ extern "C" int stemb200_conv2d_fwd(const stemb200_conv_desc* d, const void* cons
 }
 
 namespace {
-template <int kNT, bool kInverse>
+template <int kNT, bool kInverse, bool kLast = false>
 int launch_gdn(const ConvKernelParams& kp, int grid, cudaStream_t stream) {
-  using Cfg = GdnCfgT<kNT>;
+  using Cfg = GdnCfgT<kNT, kLast>;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(conv_gdn_kernel<kNT, kInverse>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(conv_gdn_kernel<kNT, kInverse, kLast>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          Cfg::kSmemBytes);
     if (e != cudaSuccess) return set_cuda_error("cudaFuncSetAttribute(conv_gdn)", e);
     configured = true;
   }
   if (kp.csize == 2) {
     static int clusters = 0;
-    return launch_pairs(conv_gdn_kernel<kNT, kInverse>, kp, kGdnThreads, Cfg::kSmemBytes, stream, clusters);
+    return launch_pairs(conv_gdn_kernel<kNT, kInverse, kLast>, kp, kGdnThreads, Cfg::kSmemBytes, stream, clusters);
   }
-  conv_gdn_kernel<kNT, kInverse><<<grid, kGdnThreads, Cfg::kSmemBytes, stream>>>(kp);
+  conv_gdn_kernel<kNT, kInverse, kLast><<<grid, kGdnThreads, Cfg::kSmemBytes, stream>>>(kp);
   count_launch();
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_cuda_error("conv_gdn launch", e);
@@ -1424,11 +1522,15 @@ int launch_gdn(const ConvKernelParams& kp, int grid, cudaStream_t stream) {
 }
 }  // namespace
 
-extern "C" int stemb200_conv2d_gdn_fwd(const stemb200_conv_desc* d, const void* const* in,
-                                       const void* packed_weight, const float* bias, const void* packed_gamma,
-                                       const float* beta, int32_t inverse, void* out, void* stream) {
-  if (!d || !in || !packed_weight || !bias || !packed_gamma || !beta || !out)
-    return set_error("conv2d_gdn_fwd: null argument");
+namespace {
+int gdn_forward(const stemb200_conv_desc* d, const void* const* in, const void* packed_weight, const float* bias,
+                const void* packed_gamma, const float* beta, int32_t inverse, void* out, const void* packed_w6,
+                void* col_out, void* stream) {
+  if (!d || !in || !packed_weight || !bias || !packed_gamma || !beta) return set_error("conv2d_gdn_fwd: null argument");
+  const bool last = packed_w6 != nullptr;
+  if (!last && !out) return set_error("conv2d_gdn_fwd: null output");
+  if (last && (!col_out || d->c_out != 192 || !inverse))
+    return set_error("conv2d_gdn_last_fwd: needs col_out, c_out == 192 and IGDN");
   if (d->c_out != 192 && d->c_out != 128) return set_error("conv2d_gdn_fwd: fused GDN needs c_out == 128 or 192");
   if (d->out_dtype != STEMB200_DT_F16 || d->direct_store || d->lrelu_slope != 1.0f || d->sq_scale <= 0.f)
     return set_error("conv2d_gdn_fwd: needs fp16 TMA-store output, no activation, sq_scale > 0");
@@ -1440,7 +1542,8 @@ extern "C" int stemb200_conv2d_gdn_fwd(const stemb200_conv_desc* d, const void* 
   for (int s = 0; s < d->n_src; ++s)
     if (!in[s]) return set_error("conv2d_gdn_fwd: null input");
   ConvKernelParams kp;
-  if (int rc = setup_params(&dd, pl, in, packed_weight, bias, nullptr, out, kp)) return rc;
+  // without an activation output the store maps are built over the col buffer (never dereferenced)
+  if (int rc = setup_params(&dd, pl, in, packed_weight, bias, nullptr, out ? out : col_out, kp)) return rc;
   if (int rc = encode_weight(&kp.g_map, packed_gamma, d->c_out, d->c_out, d->c_out)) return rc;
   if (kp.csize == 2)
     if (int rc = encode_weight(&kp.g_half_map, packed_gamma, d->c_out, d->c_out, d->c_out / 2)) return rc;
@@ -1448,6 +1551,27 @@ extern "C" int stemb200_conv2d_gdn_fwd(const stemb200_conv_desc* d, const void* 
   kp.igdn = inverse ? 1 : 0;
   const int grid = std::min(kp.total_tiles, num_sms());
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (last) {
+    if (int rc = encode_weight(&kp.w6_map, packed_w6, d->c_out, kLastN, kLastN)) return rc;
+    kp.col_out = static_cast<__half*>(col_out);
+    kp.store_act = out ? 1 : 0;
+    return launch_gdn<192, true, true>(kp, grid, st);
+  }
   if (d->c_out == 192) return inverse ? launch_gdn<192, true>(kp, grid, st) : launch_gdn<192, false>(kp, grid, st);
   return inverse ? launch_gdn<128, true>(kp, grid, st) : launch_gdn<128, false>(kp, grid, st);
+}
+}  // namespace
+
+extern "C" int stemb200_conv2d_gdn_fwd(const stemb200_conv_desc* d, const void* const* in,
+                                       const void* packed_weight, const float* bias, const void* packed_gamma,
+                                       const float* beta, int32_t inverse, void* out, void* stream) {
+  return gdn_forward(d, in, packed_weight, bias, packed_gamma, beta, inverse, out, nullptr, nullptr, stream);
+}
+
+extern "C" int stemb200_conv2d_gdn_last_fwd(const stemb200_conv_desc* d, const void* const* in,
+                                            const void* packed_weight, const float* bias, const void* packed_gamma,
+                                            const float* beta, const void* packed_w6, void* col_out, void* act_out,
+                                            void* stream) {
+  if (!packed_w6) return set_error("conv2d_gdn_last_fwd: null W6");
+  return gdn_forward(d, in, packed_weight, bias, packed_gamma, beta, 1, act_out, packed_w6, col_out, stream);
 }

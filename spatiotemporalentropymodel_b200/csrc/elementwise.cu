@@ -552,6 +552,79 @@ synthesis_tail_kernel(const float* __restrict__ in, float* __restrict__ xhat, in
   if (sq_err) block_accumulate(acc, sq_err + n, red);
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Last synthesis layer as GEMM + col2im (priors.py:438 deconv(N, 3, k5, s2, p2, op1)): the producing layer's kernel
+// left, for every input pixel (i, j), the 75 products col[i][j][(r*5+s)*3 + c] = sum_ci x[ci][i][j] * w[ci][c][r][s]
+// (fp16, 96 per pixel). Output pixel (oh, ow) sums the taps with oh = 2 i - 2 + r, ow = 2 j - 2 + s (2-3 per axis),
+// adds the bias, clamps, and accumulates the squared error against the un-padded source frame.
+// One block = 16 x 32 output pixels; the 10 x 18 contributing col rows are staged in shared memory (cp.async).
+// ---------------------------------------------------------------------------------------------------
+constexpr int kC2iTH = 16, kC2iTW = 32;                    // output tile
+constexpr int kC2iIH = kC2iTH / 2 + 2, kC2iIW = kC2iTW / 2 + 2;  // input halo tile
+constexpr int kC2iPitch = 208;                             // bytes per staged pixel (192 + 16: spreads the banks)
+
+__global__ void __launch_bounds__(256)
+synthesis_col2im_kernel(const __half* __restrict__ col, const float* __restrict__ bias, float* __restrict__ xhat, int h2,
+                        int w2, const float* __restrict__ xref, int h_ref, int w_ref, int pad_top, int pad_left,
+                        double* sq_err, int clamp01) {
+  __shared__ __align__(16) unsigned char s_col[kC2iIH * kC2iIW * kC2iPitch];
+  __shared__ float red[32];
+  const int n = blockIdx.z;
+  const int oh0 = blockIdx.y * kC2iTH, ow0 = blockIdx.x * kC2iTW;
+  const int i0 = oh0 / 2 - 1, j0 = ow0 / 2 - 1;
+  for (int c = threadIdx.x; c < kC2iIH * kC2iIW * 12; c += 256) {
+    const int px = c / 12, part = c - px * 12;
+    const int ii = px / kC2iIW, jj = px - ii * kC2iIW;
+    const int i = i0 + ii, j = j0 + jj;
+    const bool inb = i >= 0 && i < h2 && j >= 0 && j < w2;
+    const __half* src = inb ? col + ((static_cast<long long>(n) * h2 + i) * w2 + j) * 96 + part * 8 : col;
+    const unsigned int dst = static_cast<unsigned int>(__cvta_generic_to_shared(s_col + px * kC2iPitch + part * 16));
+    const int nb = inb ? 16 : 0;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(nb) : "memory");
+  }
+  asm volatile("cp.async.wait_all;" ::: "memory");
+  __syncthreads();
+  const int H = 2 * h2, W = 2 * w2;
+  const float b0 = __ldg(bias), b1 = __ldg(bias + 1), b2 = __ldg(bias + 2);
+  float acc = 0.f;
+  for (int o = threadIdx.x; o < kC2iTH * kC2iTW; o += 256) {
+    const int ty = o / kC2iTW, tx = o - ty * kC2iTW;
+    const int oh = oh0 + ty, ow = ow0 + tx;
+    if (oh >= H || ow >= W) continue;
+    float v0 = b0, v1 = b1, v2 = b2;
+    for (int r = oh & 1; r < 5; r += 2) {
+      const int ii = (oh + 2 - r) / 2 - i0;  // staged row (out-of-frame rows were zero-filled)
+      for (int s_ = ow & 1; s_ < 5; s_ += 2) {
+        const int jj = (ow + 2 - s_) / 2 - j0;
+        const __half* e = reinterpret_cast<const __half*>(s_col + (ii * kC2iIW + jj) * kC2iPitch) + (r * 5 + s_) * 3;
+        v0 += __half2float(e[0]);
+        v1 += __half2float(e[1]);
+        v2 += __half2float(e[2]);
+      }
+    }
+    if (clamp01) {
+      v0 = fminf(fmaxf(v0, 0.f), 1.f);
+      v1 = fminf(fmaxf(v1, 0.f), 1.f);
+      v2 = fminf(fmaxf(v2, 0.f), 1.f);
+    }
+    const long long plane = static_cast<long long>(H) * W;
+    float* dst = xhat + static_cast<long long>(n) * 3 * plane + static_cast<long long>(oh) * W + ow;
+    dst[0] = v0;
+    dst[plane] = v1;
+    dst[2 * plane] = v2;
+    if (xref) {
+      const int yr = oh - pad_top, xr = ow - pad_left;
+      if (yr >= 0 && yr < h_ref && xr >= 0 && xr < w_ref) {
+        const long long rp = static_cast<long long>(h_ref) * w_ref;
+        const float* rr = xref + static_cast<long long>(n) * 3 * rp + static_cast<long long>(yr) * w_ref + xr;
+        const float d0 = __ldg(rr) - v0, d1 = __ldg(rr + rp) - v1, d2 = __ldg(rr + 2 * rp) - v2;
+        acc += d0 * d0 + d1 * d1 + d2 * d2;
+      }
+    }
+  }
+  if (sq_err) block_accumulate(acc, sq_err + n, red);
+}
+
 }  // namespace stem
 
 using namespace stem;
@@ -636,6 +709,23 @@ frame_to_nhwc8_kernel(const float* __restrict__ x, uint4* __restrict__ canvas, i
     o.w = *reinterpret_cast<uint32_t*>(&h3);
     canvas[i] = o;
   }
+}
+
+extern "C" int stemb200_synthesis_col2im(const void* col_f16, const float* bias3, float* x_hat_nchw, int32_t n,
+                                         int32_t h2, int32_t w2, const float* x_ref, int32_t h_ref, int32_t w_ref,
+                                         int32_t pad_top, int32_t pad_left, double* sq_err, int32_t clamp01,
+                                         void* stream) {
+  if (!col_f16 || !bias3 || !x_hat_nchw || n < 1 || h2 < 1 || w2 < 1 || n > 65535)
+    return set_error("synthesis_col2im: bad argument");
+  if (x_ref && (h_ref < 1 || w_ref < 1 || pad_top < 0 || pad_left < 0))
+    return set_error("synthesis_col2im: bad reference geometry");
+  dim3 grid((2 * w2 + kC2iTW - 1) / kC2iTW, (2 * h2 + kC2iTH - 1) / kC2iTH, n);
+  if (grid.y > 65535) return set_error("synthesis_col2im: frame too large");
+  synthesis_col2im_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __half*>(col_f16), bias3, x_hat_nchw, h2, w2, x_ref, h_ref, w_ref, pad_top, pad_left, sq_err,
+      clamp01);
+  CHECK_LAUNCH("synthesis_col2im");
+  return 0;
 }
 
 extern "C" int stemb200_frame_to_nhwc8(const float* x_nchw, void* canvas, int32_t n, int32_t c, int32_t h, int32_t w,

@@ -123,6 +123,20 @@ class ConvOp:
             self.beta = beta.detach().to(weight.device, torch.float32).contiguous()
             self.gdn = bool(inverse)
 
+    def call_last(self, inputs: Sequence[Tensor], batch: int, h: int, w: int, w6_packed: Tensor, col: Tensor,
+                  act: Optional[Tensor] = None) -> Tensor:
+        """deconv + IGDN with the final deconv(N, 3) GEMM fused behind it (stemb200_conv2d_gdn_last_fwd):
+        col = (B, 2h, 2w, 96) fp16 tap contributions; act = the layer's own activation or None (not written)."""
+        if self.gdn is not True:
+            raise ValueError("call_last needs a deconv + IGDN layer")
+        d = self.desc
+        d.batch, d.h_in, d.w_in = batch, h, w
+        arr = (C.c_void_p * len(inputs))(*[t.data_ptr() for t in inputs])
+        _lib.check(self.lib.stemb200_conv2d_gdn_last_fwd(
+            C.byref(d), arr, self.packed.data_ptr(), self.bias.data_ptr(), self.gamma_packed.data_ptr(),
+            self.beta.data_ptr(), w6_packed.data_ptr(), col.data_ptr(), _ptr(act), _stream()), "conv2d_gdn_last_fwd")
+        return col
+
     def alg_flops(self, batch: int, h: int, w: int) -> float:
         ho, wo = self.out_hw(h, w)
         return self.alg_flops_per_out_pixel * batch * ho * wo
@@ -405,6 +419,15 @@ class TransformsEngine:
             bm[uv * 3:uv * 3 + 3] = b6
         self.gs_last = ConvOp(wm, bm, c_in=[N], c_out=64, k=5, stride=2, tap_mask=mask, out_dtype=DT_F32,
                               alg_flops_per_out_pixel=4 * 2.0 * N * 3 * 25)  # 4 input pixels per super pixel
+        # default path: the same layer as a per-pixel GEMM fused behind gs4's IGDN epilogue, W6[(r*5+s)*3+c][ci] =
+        # w[ci][c][r][s] (75 rows + 21 zero rows), followed by a col2im kernel (STEMB200_FUSE_LAST=0 selects the
+        # stand-alone merged-phase conv above instead)
+        import os
+        self.fuse_last = os.environ.get("STEMB200_FUSE_LAST", "1") != "0" and N == 192
+        w6 = F.pad(wt.permute(2, 3, 1, 0).reshape(75, N), (0, 0, 0, 21)).reshape(96, N, 1, 1).contiguous()
+        self.w6 = ConvOp(w6, torch.zeros(96, device=dev), c_in=[N], c_out=96, k=1, direct_store=True).packed  # pack only
+        self.b6 = b6.contiguous()
+        self.gs_conv[2].alg_flops_per_out_pixel_last = 2.0 * N * 3 * 25  # final deconv, per gs4 output pixel
 
     # -------------------------------------------------------------------------------------------------
     def analysis(self, x: Tensor, pad: Tuple[int, int, int, int] = (0, 0, 0, 0)) -> Tuple[Tensor, int, int]:
@@ -442,8 +465,21 @@ class TransformsEngine:
         B, h, w, _ = y_hat16.shape
         lib, ws, N = _lib.load(), self.ws, self.N
         cur = y_hat16
+        left, right, top, bottom = pad
+        href = wref = 0
+        if x_ref is not None:
+            href, wref = x_ref.shape[2], x_ref.shape[3]
         for li in range(3):
             ho, wo = 2 * h, 2 * w
+            if li == 2 and self.fuse_last:
+                col = ws.get("gs_col", (B, ho, wo, 96), torch.float16)
+                self.gs_conv[2].call_last([cur], B, h, w, self.w6, col)
+                if out is None:
+                    out = ws.get("gs_xhat", (B, 3, 2 * ho, 2 * wo), torch.float32)
+                _lib.check(lib.stemb200_synthesis_col2im(col.data_ptr(), self.b6.data_ptr(), out.data_ptr(), B, ho, wo,
+                                                         _ptr(x_ref), href, wref, top, left, _ptr(sq_err), int(clamp),
+                                                         _stream()), "synthesis_col2im")
+                return out
             gb = self.gs_conv[li]([cur], B, h, w, ws.get(f"gs_g{li}", (B, ho, wo, N), torch.float16))
             cur, h, w = gb, ho, wo
         if h % 2 or w % 2:
@@ -452,10 +488,6 @@ class TransformsEngine:
         self.gs_last([cur], B, h, w, merged)
         if out is None:
             out = ws.get("gs_xhat", (B, 3, 2 * h, 2 * w), torch.float32)
-        left, right, top, bottom = pad
-        href = wref = 0
-        if x_ref is not None:
-            href, wref = x_ref.shape[2], x_ref.shape[3]
         _lib.check(lib.stemb200_synthesis_tail(merged.data_ptr(), out.data_ptr(), B, h // 2, w // 2, _ptr(x_ref), href,
                                                wref, top, left, _ptr(sq_err), int(clamp), _stream()), "synthesis_tail")
         return out

@@ -301,3 +301,35 @@ def test_pframe_pipeline_bpp_psnr(dev, variant):
     x_hat = out["x_hat_padded"][:, :, tp:tp + H, l:l + W].cpu()
     assert rel_rms(x_hat, torch.cat([o["x_hat"] for o in ref])) < 5e-2
     assert out["y_hat"].shape == (T, 192, 8, 16)
+
+
+@pytest.mark.gpu
+def test_fused_last_synthesis_layer_matches_standalone_and_oracle():
+    """g_s.4 + IGDN with the final deconv(N, 3) fused behind it (stemb200_conv2d_gdn_last_fwd + col2im) against the
+    stand-alone merged-phase conv path and against the oracle's g_s (priors.py:431-439), ragged frame incl. MSE."""
+    import os
+    from spatiotemporalentropymodel_b200.engine import TransformsEngine, nchw_to_nhwc_f16
+    dev = torch.device("cuda:0")
+    sd = S.make_iframe_state_dict(0)
+    y_hat = torch.round(S.make_latent(2, 192, 6, 10, seed=8))
+    x_ref = S.make_frames(2, 90, 150, seed=3)                     # un-padded frame inside the 96 x 160 canvas
+    pad = (5, 5, 3, 3)
+    outs = {}
+    for fuse in ("1", "0"):
+        os.environ["STEMB200_FUSE_LAST"] = fuse
+        try:
+            eng = TransformsEngine({k: v.to(dev) for k, v in sd.items()}, dev)
+        finally:
+            os.environ.pop("STEMB200_FUSE_LAST", None)
+        assert eng.fuse_last == (fuse == "1")
+        y16 = nchw_to_nhwc_f16(y_hat.to(dev), torch.empty((2, 6, 10, 192), dtype=torch.float16, device=dev))
+        sq = torch.zeros(2, dtype=torch.float64, device=dev)
+        x = eng.synthesis(y16, x_ref=x_ref.to(dev), pad=pad, sq_err=sq, out=torch.empty((2, 3, 96, 160), device=dev))
+        outs[fuse] = (x.cpu(), sq.cpu())
+    ref = O.g_s(y_hat, sd, clamp=True)
+    for fuse, (x, sq) in outs.items():
+        assert float((x - ref).abs().max()) < 4e-3, fuse
+        crop = x[:, :, 3:93, 5:155]
+        want = ((x_ref - crop).double() ** 2).sum(dim=(1, 2, 3))
+        assert torch.allclose(sq, want, rtol=1e-5), fuse
+    assert float((outs["1"][0] - outs["0"][0]).abs().max()) < 2e-3
