@@ -105,13 +105,23 @@ struct TileCoord {
 __device__ __forceinline__ TileCoord decode_tile(const ConvKernelParams& p, int q, int r, int block_n) {
   TileCoord t;
   int nt = q % p.n_tiles_n;
-  int m = (q / p.n_tiles_n) * p.csize + r;
+  int u = q / p.n_tiles_n;
+  int m;
+  if (p.n_sub == 4) {
+    // transposed conv: the four output phases of a pixel tile are neighbours in the work order (their input tile is
+    // read from L2, not four times from HBM); the phase rotates with the tile so that every CTA sees all four K lengths
+    const int g = u >> 2;
+    t.sub = ((u & 3) + g) & 3;
+    m = g * p.csize + r;
+  } else {
+    m = u * p.csize + r;
+    t.sub = 0;
+  }
   int twi = m % p.tiles_w;
   m /= p.tiles_w;
   int thi = m % p.tiles_h;
   m /= p.tiles_h;
   t.n_img = m % p.batch;
-  t.sub = m / p.batch;
   t.h0 = thi * p.tile_h;
   t.w0 = twi * p.tile_w;
   t.n0 = nt * block_n;
