@@ -167,7 +167,9 @@ conv_igemm_kernel(const __grid_constant__ ConvKernelParams p) {
   const uint32_t tmem_slot = bar_base + 8u * (2 * kStages + 4);
   const uint32_t bias_smem = bar_base + 256u;  // BLOCK_N floats: bias (or GDN beta) of the current N tile
 
-  const int warp = threadIdx.x >> 5;
+  // warp index through a shuffle: the compiler then knows the role branches are warp-uniform and keeps descriptors,
+  // barrier addresses and TMA / MMA operands in uniform registers (no per-instruction elect / broadcast loops)
+  const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
   const bool pair = p.csize == 2;
   const int crank = pair ? static_cast<int>(cluster_ctarank()) : 0;
@@ -203,11 +205,13 @@ conv_igemm_kernel(const __grid_constant__ ConvKernelParams p) {
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  tmem_base = __shfl_sync(0xffffffffu, tmem_base, 0);
 
   const uint32_t a_tx_bytes = static_cast<uint32_t>(p.tile_h * p.tile_w) * 128u;
 
-  if (warp == 0 && lane == 0) {
-    // ===================== TMA producer =====================
+  if (warp == 0) {
+    // ===================== TMA producer (whole warp walks the loop, one elected lane issues) =====================
+    const bool leader = elect_one();
     int s = 0;
     uint32_t ph = 0;
     for (int tile = q_first; tile < n_items; tile += q_stride) {
@@ -222,21 +226,24 @@ conv_igemm_kernel(const __grid_constant__ ConvKernelParams p) {
         const int c0 = static_cast<int>(e >> 10);
         const uint32_t a_dst = stage_base + s * Cfg::kStageBytes;
         const uint32_t b_dst = a_dst + kAStageBytes;
-        mbar_arrive_expect_tx(full_bar(s), a_tx_bytes + Cfg::kBStageBytes);
-        tma_load_4d(a_dst, &p.a_map[map], full_bar(s), c0, t.w0 + dw, t.h0 + dh, t.n_img);
-        if (pair)
-          tma_load_2d_mc(b_dst + crank * (Cfg::kBStageBytes / 2), &p.b_half_map, full_bar(s), k * kKChunk,
-                         t.n0 + crank * (BLOCK_N / 2), 3);
-        else
-          tma_load_2d(b_dst, &p.b_map, full_bar(s), k * kKChunk, t.n0);
+        if (leader) {
+          mbar_arrive_expect_tx(full_bar(s), a_tx_bytes + Cfg::kBStageBytes);
+          tma_load_4d(a_dst, &p.a_map[map], full_bar(s), c0, t.w0 + dw, t.h0 + dh, t.n_img);
+          if (pair)
+            tma_load_2d_mc(b_dst + crank * (Cfg::kBStageBytes / 2), &p.b_half_map, full_bar(s), k * kKChunk,
+                           t.n0 + crank * (BLOCK_N / 2), 3);
+          else
+            tma_load_2d(b_dst, &p.b_map, full_bar(s), k * kKChunk, t.n0);
+        }
         if (++s == kStages) {
           s = 0;
           ph ^= 1u;
         }
       }
     }
-  } else if (warp == 1 && lane == 0) {
-    // ===================== MMA issuer =====================
+  } else if (warp == 1) {
+    // ===================== MMA issuer (whole warp walks the loop, one elected lane issues) =====================
+    const bool leader = elect_one();
     constexpr uint32_t idesc = umma_idesc(/*F16*/ 0u, 128u, BLOCK_N);
     int s = 0;
     uint32_t ph = 0;
@@ -255,19 +262,21 @@ conv_igemm_kernel(const __grid_constant__ ConvKernelParams p) {
         const uint32_t a_addr = stage_base + s * Cfg::kStageBytes;
         const uint64_t adesc = umma_desc_sw128(a_addr);
         const uint64_t bdesc = umma_desc_sw128(a_addr + kAStageBytes);
+        if (leader) {
 #pragma unroll
-        for (int kk = 0; kk < 4; ++kk) {
-          // +32 bytes (one K=16 slice) inside the 128-byte swizzle row => +2 in the >>4 address field
-          mma_f16_ss(d_tmem, adesc + 2u * kk, bdesc + 2u * kk, idesc, (k > kbeg || kk > 0) ? 1u : 0u);
+          for (int kk = 0; kk < 4; ++kk) {
+            // +32 bytes (one K=16 slice) inside the 128-byte swizzle row => +2 in the >>4 address field
+            mma_f16_ss(d_tmem, adesc + 2u * kk, bdesc + 2u * kk, idesc, (k > kbeg || kk > 0) ? 1u : 0u);
+          }
+          if (pair) mma_commit_mc(empty_bar(s), 3);
+          else mma_commit(empty_bar(s));
         }
-        if (pair) mma_commit_mc(empty_bar(s), 3);
-        else mma_commit(empty_bar(s));
         if (++s == kStages) {
           s = 0;
           ph ^= 1u;
         }
       }
-      mma_commit(tfull_bar(acc));
+      if (leader) mma_commit(tfull_bar(acc));
     }
   } else if (warp >= 4) {
     // ===================== epilogue (TMEM -> registers -> smem -> TMA store) =====================
@@ -587,7 +596,9 @@ conv_gdn_kernel(const __grid_constant__ ConvKernelParams p) {
   const uint32_t bias_smem = bar_base + 256u;
   const uint32_t beta_smem = bias_smem + 4u * BLOCK_N;
 
-  const int warp = threadIdx.x >> 5;
+  // warp index through a shuffle: the compiler then knows the role branches are warp-uniform and keeps descriptors,
+  // barrier addresses and TMA / MMA operands in uniform registers (no per-instruction elect / broadcast loops)
+  const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
   const bool pair = p.csize == 2;
   const int crank = pair ? static_cast<int>(cluster_ctarank()) : 0;
@@ -637,11 +648,13 @@ conv_gdn_kernel(const __grid_constant__ ConvKernelParams p) {
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  tmem_base = __shfl_sync(0xffffffffu, tmem_base, 0);
 
   const uint32_t a_tx_bytes = static_cast<uint32_t>(p.tile_h * p.tile_w) * 128u;
 
-  if (warp == 0 && lane == 0) {
-    // ===================== TMA producer =====================
+  if (warp == 0) {
+    // ===================== TMA producer (whole warp walks the loop, one elected lane issues) =====================
+    const bool leader = elect_one();
     int s = 0;
     uint32_t ph = 0;
     auto load_main = [&](const TileCoord& t, int k) {
@@ -652,13 +665,15 @@ conv_gdn_kernel(const __grid_constant__ ConvKernelParams p) {
       const int dw = static_cast<int>((e >> 6) & 15u) - 8;
       const int c0 = static_cast<int>(e >> 10);
       const uint32_t a_dst = stage_base + s * Cfg::kStageBytes;
-      mbar_arrive_expect_tx(full_bar(s), a_tx_bytes + Cfg::kBStageBytes);
-      tma_load_4d(a_dst, &p.a_map[map], full_bar(s), c0, t.w0 + dw, t.h0 + dh, t.n_img);
-      if (pair)
-        tma_load_2d_mc(a_dst + kAStageBytes + crank * (Cfg::kBStageBytes / 2), &p.b_half_map, full_bar(s), k * kKChunk,
-                       crank * (BLOCK_N / 2), 3);
-      else
-        tma_load_2d(a_dst + kAStageBytes, &p.b_map, full_bar(s), k * kKChunk, 0);
+      if (leader) {
+        mbar_arrive_expect_tx(full_bar(s), a_tx_bytes + Cfg::kBStageBytes);
+        tma_load_4d(a_dst, &p.a_map[map], full_bar(s), c0, t.w0 + dw, t.h0 + dh, t.n_img);
+        if (pair)
+          tma_load_2d_mc(a_dst + kAStageBytes + crank * (Cfg::kBStageBytes / 2), &p.b_half_map, full_bar(s),
+                         k * kKChunk, crank * (BLOCK_N / 2), 3);
+        else
+          tma_load_2d(a_dst + kAStageBytes, &p.b_map, full_bar(s), k * kKChunk, 0);
+      }
       if (++s == kStages) {
         s = 0;
         ph ^= 1u;
@@ -668,12 +683,14 @@ conv_gdn_kernel(const __grid_constant__ ConvKernelParams p) {
       for (int kc = 0; kc < kGChunks; ++kc) {
         mbar_wait(empty_bar(s), ph ^ 1u);
         const uint32_t a_dst = stage_base + s * Cfg::kStageBytes;
-        mbar_arrive_expect_tx(full_bar(s), Cfg::kBStageBytes);
-        if (pair)
-          tma_load_2d_mc(a_dst + kAStageBytes + crank * (Cfg::kBStageBytes / 2), &p.g_half_map, full_bar(s),
-                         kc * kKChunk, crank * (BLOCK_N / 2), 3);
-        else
-          tma_load_2d(a_dst + kAStageBytes, &p.g_map, full_bar(s), kc * kKChunk, 0);
+        if (leader) {
+          mbar_arrive_expect_tx(full_bar(s), Cfg::kBStageBytes);
+          if (pair)
+            tma_load_2d_mc(a_dst + kAStageBytes + crank * (Cfg::kBStageBytes / 2), &p.g_half_map, full_bar(s),
+                           kc * kKChunk, crank * (BLOCK_N / 2), 3);
+          else
+            tma_load_2d(a_dst + kAStageBytes, &p.g_map, full_bar(s), kc * kKChunk, 0);
+        }
         if (++s == kStages) {
           s = 0;
           ph ^= 1u;
@@ -681,10 +698,12 @@ conv_gdn_kernel(const __grid_constant__ ConvKernelParams p) {
       }
     };
     if constexpr (kLast) {
-      tma_prefetch_desc(&p.w6_map);
-      mbar_arrive_expect_tx(w6full_bar, Cfg::kW6Bytes);
-      for (int kc = 0; kc < kGChunks; ++kc)
-        tma_load_2d(w6_base + kc * (kLastN * 128), &p.w6_map, w6full_bar, kc * kKChunk, 0);
+      if (leader) {
+        tma_prefetch_desc(&p.w6_map);
+        mbar_arrive_expect_tx(w6full_bar, Cfg::kW6Bytes);
+        for (int kc = 0; kc < kGChunks; ++kc)
+          tma_load_2d(w6_base + kc * (kLastN * 128), &p.w6_map, w6full_bar, kc * kKChunk, 0);
+      }
     }
     int it = 0;
     for (int tile = q_first; tile < n_items; tile += q_stride, ++it) {
@@ -696,8 +715,9 @@ conv_gdn_kernel(const __grid_constant__ ConvKernelParams p) {
       for (int k = ksplit; k < kend; ++k) load_main(t, k);
     }
     if (it > 0) load_gamma();
-  } else if (warp == 1 && lane == 0) {
-    // ===================== MMA issuer =====================
+  } else if (warp == 1) {
+    // ===================== MMA issuer (whole warp walks the loop, one elected lane issues) =====================
+    const bool leader = elect_one();
     constexpr uint32_t idesc = umma_idesc(/*F16*/ 0u, 128u, BLOCK_N);
     int s = 0;
     uint32_t ph = 0;
@@ -707,28 +727,32 @@ conv_gdn_kernel(const __grid_constant__ ConvKernelParams p) {
     bool w6_ready = false;
     auto try_mma3 = [&]() {
       if constexpr (kLast) {
-        if (!mbar_try_wait(a3rdy_bar, n3_done & 1)) return;
+        // one lane's probe decides for the warp (n3_done must stay warp-uniform)
+        if (!__shfl_sync(0xffffffffu, static_cast<int>(mbar_try_wait(a3rdy_bar, n3_done & 1)), 0)) return;
         if (!w6_ready) {
           mbar_wait(w6full_bar, 0);
           w6_ready = true;
         }
         tc_fence_after();
         constexpr uint32_t idesc3 = umma_idesc(/*F16*/ 0u, 128u, kLastN);
-        for (int kc = 0; kc < kGChunks; ++kc) {
-          const uint64_t adesc = umma_desc_sw128(a2_base + kc * kAStageBytes);
-          const uint64_t bdesc = umma_desc_sw128(w6_base + kc * (kLastN * 128));
+        if (leader) {
 #pragma unroll
-          for (int kk = 0; kk < 4; ++kk)
-            mma_f16_ss(tmem_base + Cfg::kStashCol, adesc + 2u * kk, bdesc + 2u * kk, idesc3,
-                       (kc > 0 || kk > 0) ? 1u : 0u);
+          for (int kc = 0; kc < kGChunks; ++kc) {
+            const uint64_t adesc = umma_desc_sw128(a2_base + kc * kAStageBytes);
+            const uint64_t bdesc = umma_desc_sw128(w6_base + kc * (kLastN * 128));
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk)
+              mma_f16_ss(tmem_base + Cfg::kStashCol, adesc + 2u * kk, bdesc + 2u * kk, idesc3,
+                         (kc > 0 || kk > 0) ? 1u : 0u);
+          }
+          mma_commit(d3full_bar);
         }
-        mma_commit(d3full_bar);
         ++n3_done;
       }
     };
     auto wait_bar = [&](uint32_t bar, uint32_t parity) {
       if constexpr (kLast) {
-        while (!mbar_try_wait(bar, parity)) try_mma3();
+        while (!__shfl_sync(0xffffffffu, static_cast<int>(mbar_try_wait(bar, parity)), 0)) try_mma3();
       } else {
         mbar_wait(bar, parity);
       }
@@ -739,11 +763,13 @@ conv_gdn_kernel(const __grid_constant__ ConvKernelParams p) {
       const uint32_t a_addr = stage_base + s * Cfg::kStageBytes;
       const uint64_t adesc = umma_desc_sw128(a_addr);
       const uint64_t bdesc = umma_desc_sw128(a_addr + kAStageBytes);
+      if (leader) {
 #pragma unroll
-      for (int kk = 0; kk < 4; ++kk)
-        if (kk < p.kk_main) mma_f16_ss(d_tmem, adesc + 2u * kk, bdesc + 2u * kk, idesc, (!first || kk > 0) ? 1u : 0u);
-      if (pair) mma_commit_mc(empty_bar(s), 3);
-      else mma_commit(empty_bar(s));
+        for (int kk = 0; kk < 4; ++kk)
+          if (kk < p.kk_main) mma_f16_ss(d_tmem, adesc + 2u * kk, bdesc + 2u * kk, idesc, (!first || kk > 0) ? 1u : 0u);
+        if (pair) mma_commit_mc(empty_bar(s), 3);
+        else mma_commit(empty_bar(s));
+      }
       if (++s == kStages) {
         s = 0;
         ph ^= 1u;
@@ -760,17 +786,19 @@ conv_gdn_kernel(const __grid_constant__ ConvKernelParams p) {
         tc_fence_after();
         const uint64_t adesc = umma_desc_sw128(a2_base + kc * kAStageBytes);
         const uint64_t bdesc = umma_desc_sw128(stage_base + s * Cfg::kStageBytes + kAStageBytes);
+        if (leader) {
 #pragma unroll
-        for (int kk = 0; kk < 4; ++kk)
-          mma_f16_ss(d_tmem, adesc + 2u * kk, bdesc + 2u * kk, idesc, (kc > 0 || kk > 0) ? 1u : 0u);
-        if (pair) mma_commit_mc(empty_bar(s), 3);
-        else mma_commit(empty_bar(s));
+          for (int kk = 0; kk < 4; ++kk)
+            mma_f16_ss(d_tmem, adesc + 2u * kk, bdesc + 2u * kk, idesc, (kc > 0 || kk > 0) ? 1u : 0u);
+          if (pair) mma_commit_mc(empty_bar(s), 3);
+          else mma_commit(empty_bar(s));
+        }
         if (++s == kStages) {
           s = 0;
           ph ^= 1u;
         }
       }
-      mma_commit(nfull_bar);
+      if (leader) mma_commit(nfull_bar);
     };
     int it = 0;
     for (int tile = q_first; tile < n_items; tile += q_stride, ++it) {
@@ -785,7 +813,7 @@ conv_gdn_kernel(const __grid_constant__ ConvKernelParams p) {
       for (int k = kbeg; k < ksplit; ++k) mma_main(d_tmem, k == kbeg);
       if (it > 0) mma_gamma(it - 1);
       for (int k = ksplit; k < kend; ++k) mma_main(d_tmem, k == kbeg);
-      mma_commit(tfull_bar);
+      if (leader) mma_commit(tfull_bar);
     }
     if (it > 0) mma_gamma(it - 1);
     if constexpr (kLast) {

@@ -52,13 +52,13 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       : "memory");
 }
 
-// non-blocking probe (returns after at most the hardware's try_wait time slice)
+// non-blocking probe (test_wait returns at once; try_wait may suspend the thread for a hardware time slice)
 __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
       "{\n\t"
       ".reg .pred P1;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
       "selp.u32 %0, 1, 0, P1;\n\t"
       "}\n"
       : "=r"(ok)
