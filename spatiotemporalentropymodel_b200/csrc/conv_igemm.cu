@@ -637,7 +637,7 @@ conv_gdn_kernel(const __grid_constant__ ConvKernelParams p) {
     // bias, and the folded normaliser offset: s^2 beta (GDN) or beta / s^2 (IGDN)
     const float kb = kInverse ? p.sq_inv : p.sq_scale * p.sq_scale;
     for (int i = threadIdx.x - 128; i < BLOCK_N; i += kGdnEpiThreads) {
-      const float b = __ldg(p.bias + i), g = __ldg(p.beta + i) * kb;
+      const float b = __ldg(p.bias + i) * p.sq_scale, g = __ldg(p.beta + i) * kb;  // bias pre-scaled: x s = fma(acc, s, b s)
       asm volatile("st.shared.f32 [%0], %1;" ::"r"(bias_smem + 4u * i), "f"(b) : "memory");
       asm volatile("st.shared.f32 [%0], %1;" ::"r"(beta_smem + 4u * i), "f"(g) : "memory");
     }
@@ -832,7 +832,7 @@ conv_gdn_kernel(const __grid_constant__ ConvKernelParams p) {
     const uint32_t rsw = static_cast<uint32_t>(row & 7);
     const uint32_t row_off = static_cast<uint32_t>(row) * 128u;
     const uint32_t p0 = ((2u * q) ^ rsw) << 4, p1 = ((2u * q + 1u) ^ rsw) << 4;  // swizzled 16-byte pieces
-    const __half2 s2 = __float2half2_rn(p.sq_scale);
+    const float sc = p.sq_scale;  // power of two: fma(acc, s, b s) rounds exactly like (acc + b) s
     const float ka = kInverse ? p.sq_inv * p.sq_inv : 1.0f;
     int it = 0;
     for (int tile = q_first; tile < n_items; tile += q_stride, ++it) {
@@ -866,10 +866,10 @@ conv_gdn_kernel(const __grid_constant__ ConvKernelParams p) {
                          : "r"(bias_smem + 4u * (c + 4 * j)));
             const uint32_t* rr = r[g & 1];
             // the value that is normalised is the fp16-rounded x; x s is exact (s is a power of two)
-            const __half2 h0 =
-                __hmul2(__floats2half2_rn(__uint_as_float(rr[4 * j]) + b0, __uint_as_float(rr[4 * j + 1]) + b1), s2);
-            const __half2 h1 = __hmul2(
-                __floats2half2_rn(__uint_as_float(rr[4 * j + 2]) + b2, __uint_as_float(rr[4 * j + 3]) + b3), s2);
+            const __half2 h0 = __floats2half2_rn(fmaf(__uint_as_float(rr[4 * j]), sc, b0),
+                                                 fmaf(__uint_as_float(rr[4 * j + 1]), sc, b1));
+            const __half2 h1 = __floats2half2_rn(fmaf(__uint_as_float(rr[4 * j + 2]), sc, b2),
+                                                 fmaf(__uint_as_float(rr[4 * j + 3]), sc, b3));
             const __half2 q0 = __hmul2(h0, h0), q1 = __hmul2(h1, h1);
             hx[2 * j] = *reinterpret_cast<const uint32_t*>(&h0);
             hx[2 * j + 1] = *reinterpret_cast<const uint32_t*>(&h1);
@@ -922,8 +922,6 @@ conv_gdn_kernel(const __grid_constant__ ConvKernelParams p) {
                          : "r"(beta_smem + 4u * (c + 4 * j)));
             const uint32_t* rr = r[g & 1];
             const uint32_t* hx = hs[g & 1];
-            const float2 x0 = __half22float2(*reinterpret_cast<const __half2*>(&hx[2 * j]));
-            const float2 x1 = __half22float2(*reinterpret_cast<const __half2*>(&hx[2 * j + 1]));
             const float n0 = fmaf(__uint_as_float(rr[4 * j]), ka, b0);
             const float n1 = fmaf(__uint_as_float(rr[4 * j + 1]), ka, b1);
             const float n2 = fmaf(__uint_as_float(rr[4 * j + 2]), ka, b2);
@@ -934,6 +932,9 @@ conv_gdn_kernel(const __grid_constant__ ConvKernelParams p) {
             } else {
               f0 = approx_rsqrt(n0), f1 = approx_rsqrt(n1), f2 = approx_rsqrt(n2), f3 = approx_rsqrt(n3);
             }
+            // (a packed-half product (x s) * fp16(f) was measured: no faster, one more rounding - not used)
+            const float2 x0 = __half22float2(*reinterpret_cast<const __half2*>(&hx[2 * j]));
+            const float2 x1 = __half22float2(*reinterpret_cast<const __half2*>(&hx[2 * j + 1]));
             ho[2 * j] = pack_half2(x0.x * f0, x0.y * f1);
             ho[2 * j + 1] = pack_half2(x1.x * f2, x1.y * f3);
           }
@@ -1083,7 +1084,7 @@ conv_gdn_pp_kernel(const __grid_constant__ ConvKernelParams p) {
   if (warp >= 4) {
     const float kb = kInverse ? p.sq_inv : p.sq_scale * p.sq_scale;
     for (int i = threadIdx.x - 128; i < BLOCK_N; i += kGdnEpiThreads) {
-      const float b = __ldg(p.bias + i), g = __ldg(p.beta + i) * kb;
+      const float b = __ldg(p.bias + i) * p.sq_scale, g = __ldg(p.beta + i) * kb;  // bias pre-scaled: x s = fma(acc, s, b s)
       asm volatile("st.shared.f32 [%0], %1;" ::"r"(bias_smem + 4u * i), "f"(b) : "memory");
       asm volatile("st.shared.f32 [%0], %1;" ::"r"(beta_smem + 4u * i), "f"(g) : "memory");
     }
@@ -1233,7 +1234,7 @@ conv_gdn_pp_kernel(const __grid_constant__ ConvKernelParams p) {
     const uint32_t a2_base = a2_base0 + G * Cfg::kA2Bytes;
     const uint32_t acc_col = tmem_base + lane_off + G * BLOCK_N + 32 * half;
     const uint32_t bar_id = 1 + G;
-    const __half2 s2 = __float2half2_rn(p.sq_scale);
+    const float sc = p.sq_scale;  // power of two: fma(acc, s, b s) rounds exactly like (acc + b) s
     const float ka = kInverse ? p.sq_inv * p.sq_inv : 1.0f;
     int n = 0;
     for (int tile = q_first + G * q_stride; tile < n_items; tile += 2 * q_stride, ++n) {
@@ -1265,9 +1266,9 @@ conv_gdn_pp_kernel(const __grid_constant__ ConvKernelParams p) {
                          : "=f"(b0), "=f"(b1), "=f"(b2), "=f"(b3)
                          : "r"(bias_smem + 4u * (c + 4 * j)));
             const __half2 h0 =
-                __hmul2(__floats2half2_rn(__uint_as_float(r[4 * j]) + b0, __uint_as_float(r[4 * j + 1]) + b1), s2);
-            const __half2 h1 =
-                __hmul2(__floats2half2_rn(__uint_as_float(r[4 * j + 2]) + b2, __uint_as_float(r[4 * j + 3]) + b3), s2);
+                __floats2half2_rn(fmaf(__uint_as_float(r[4 * j]), sc, b0), fmaf(__uint_as_float(r[4 * j + 1]), sc, b1));
+            const __half2 h1 = __floats2half2_rn(fmaf(__uint_as_float(r[4 * j + 2]), sc, b2),
+                                                 fmaf(__uint_as_float(r[4 * j + 3]), sc, b3));
             const __half2 q0 = __hmul2(h0, h0), q1 = __hmul2(h1, h1);
             hx[g * 16 + sub * 8 + 2 * j] = *reinterpret_cast<const uint32_t*>(&h0);
             hx[g * 16 + sub * 8 + 2 * j + 1] = *reinterpret_cast<const uint32_t*>(&h1);
@@ -1313,8 +1314,6 @@ conv_gdn_pp_kernel(const __grid_constant__ ConvKernelParams p) {
             asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
                          : "=f"(b0), "=f"(b1), "=f"(b2), "=f"(b3)
                          : "r"(beta_smem + 4u * (c + 4 * j)));
-            const float2 x0 = __half22float2(*reinterpret_cast<const __half2*>(&hx[g * 16 + sub * 8 + 2 * j]));
-            const float2 x1 = __half22float2(*reinterpret_cast<const __half2*>(&hx[g * 16 + sub * 8 + 2 * j + 1]));
             const float n0 = fmaf(__uint_as_float(r[4 * j]), ka, b0);
             const float n1 = fmaf(__uint_as_float(r[4 * j + 1]), ka, b1);
             const float n2 = fmaf(__uint_as_float(r[4 * j + 2]), ka, b2);
@@ -1325,6 +1324,8 @@ conv_gdn_pp_kernel(const __grid_constant__ ConvKernelParams p) {
             } else {
               f0 = approx_rsqrt(n0), f1 = approx_rsqrt(n1), f2 = approx_rsqrt(n2), f3 = approx_rsqrt(n3);
             }
+            const float2 x0 = __half22float2(*reinterpret_cast<const __half2*>(&hx[g * 16 + sub * 8 + 2 * j]));
+            const float2 x1 = __half22float2(*reinterpret_cast<const __half2*>(&hx[g * 16 + sub * 8 + 2 * j + 1]));
             ho[2 * j] = pack_half2(x0.x * f0, x0.y * f1);
             ho[2 * j + 1] = pack_half2(x1.x * f2, x1.y * f3);
           }
