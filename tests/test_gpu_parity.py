@@ -135,6 +135,10 @@ CONV_CASES = [
     ("ctx_masked", [192], 384, 5, 1, False, True, 16, 24),
     ("epm0_1x1_cat3", [384, 384, 384], 768, 1, 1, False, False, 16, 24),
     ("tpm2_320", [256], 320, 5, 1, False, False, 12, 20),
+    # >= 2 x 148 tiles: pair mode (2-CTA clusters, weight tiles multicast) and the interleaved deconv phases
+    ("tpm0_5x5_pairs", [192], 256, 5, 1, False, False, 136, 240),
+    ("hd0_deconv_pairs", [256], 256, 5, 2, True, False, 68, 120),
+    ("tpm2_320_big", [256], 320, 5, 1, False, False, 136, 240),
 ]
 
 
@@ -173,7 +177,10 @@ def test_conv_layers_vs_torch(dev, case):
     assert float((got - ref).abs().max()) < 2e-4 * max(1.0, float(ref.abs().max()))
 
 
-GDN_CASES = [("conv5s2_gdn", False, False, 20, 28), ("deconv5_igdn", True, True, 9, 13), ("gemm_gdn", None, False, 12, 20)]
+GDN_CASES = [("conv5s2_gdn", False, False, 20, 28), ("deconv5_igdn", True, True, 9, 13), ("gemm_gdn", None, False, 12, 20),
+             # pair mode / many tiles per CTA (double-buffered accumulators, ping-pong groups wrap around)
+             ("conv5s2_gdn_pairs", False, False, 272, 480), ("deconv5_igdn_pairs", True, True, 68, 120),
+             ("gemm_gdn_pairs", None, False, 160, 256)]
 
 
 @pytest.mark.parametrize("case", GDN_CASES, ids=[c[0] for c in GDN_CASES])
