@@ -128,6 +128,13 @@ __device__ __forceinline__ TileCoord decode_tile(const ConvKernelParams& p, int 
   return t;
 }
 
+// the MMA warp only needs the sub-problem (K range) of a work item: no divisions on the tensor pipe's critical path
+__device__ __forceinline__ int tile_sub(const ConvKernelParams& p, int q) {
+  if (p.n_sub != 4) return 0;
+  const int u = p.n_tiles_n == 1 ? q : q / p.n_tiles_n;
+  return ((u & 3) + (u >> 2)) & 3;
+}
+
 // single-MUFU reciprocal square root / square root (rel. error ~2^-22; the result is rounded to fp16 anyway)
 __device__ __forceinline__ float approx_rsqrt(float x) {
   float y;
@@ -249,8 +256,8 @@ conv_igemm_kernel(const __grid_constant__ ConvKernelParams p) {
     uint32_t ph = 0;
     int it = 0;
     for (int tile = q_first; tile < n_items; tile += q_stride, ++it) {
-      const TileCoord t = decode_tile(p, tile, crank, BLOCK_N);
-      const int kbeg = p.sub_kbeg[t.sub], kend = p.sub_kend[t.sub];
+      const int sub = tile_sub(p, tile);
+      const int kbeg = p.sub_kbeg[sub], kend = p.sub_kend[sub];
       const int acc = it & 1;
       const uint32_t accph = (it >> 1) & 1;
       mbar_wait(tempty_bar(acc), accph ^ 1u);
@@ -802,8 +809,8 @@ conv_gdn_kernel(const __grid_constant__ ConvKernelParams p) {
     };
     int it = 0;
     for (int tile = q_first; tile < n_items; tile += q_stride, ++it) {
-      const TileCoord t = decode_tile(p, tile, crank, BLOCK_N);
-      const int kbeg = p.sub_kbeg[t.sub], kend = p.sub_kend[t.sub];
+      const int sub = tile_sub(p, tile);
+      const int kbeg = p.sub_kbeg[sub], kend = p.sub_kend[sub];
       const int ksplit = kbeg + ((kend - kbeg) >> 1);
       const uint32_t d_tmem = tmem_base + (it & 1) * BLOCK_N;
       if (it >= 2) {  // phase 2 of tile it-2 has finished reading this accumulator
@@ -1206,8 +1213,8 @@ conv_gdn_pp_kernel(const __grid_constant__ ConvKernelParams p) {
     };
     int it = 0;
     for (int tile = q_first; tile < n_items; tile += q_stride, ++it) {
-      const TileCoord t = decode_tile(p, tile, crank, BLOCK_N);
-      const int kbeg = p.sub_kbeg[t.sub], kend = p.sub_kend[t.sub];
+      const int sub = tile_sub(p, tile);
+      const int kbeg = p.sub_kbeg[sub], kend = p.sub_kend[sub];
       const int ksplit = kbeg + ((kend - kbeg) >> 1);
       const int g = it & 1;
       const uint32_t d_tmem = tmem_base + g * BLOCK_N;
