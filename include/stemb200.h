@@ -101,17 +101,23 @@ int stemb200_conv2d_gdn_fwd(const stemb200_conv_desc* d, const void* const* in, 
 
 /* The last two synthesis layers in one pass (priors.py:436-438: deconv(N, N) + IGDN, then deconv(N, 3)): as
  * stemb200_conv2d_gdn_fwd with inverse = 1 and c_out = 192, plus, while a tile of the layer's output is still in
- * shared memory, its product with packed_w6 = the [96][192] fp16 matrix W6[(r*5+s)*3 + c][ci] = w[ci][c][r][s] of the
- * final ConvTranspose2d(192, 3, 5, stride 2) (rows 75..95 zero; pack it with stemb200_conv2d_pack_weight as a 1x1
- * conv 192 -> 96). col_out: NHWC fp16 [batch][2 h_in][2 w_in][96], the per-pixel tap contributions that
+ * shared memory, its product with packed_w6 = the [96][192] fp16 matrix
+ * W6[stemb200_synthesis_col_index(r, s, c)][ci] = w[ci][c][r][s] of the final ConvTranspose2d(192, 3, 5, stride 2)
+ * (the other 21 rows zero; pack it with stemb200_conv2d_pack_weight as a 1x1 conv 192 -> 96). col_out: NHWC fp16 [batch][2 h_in][2 w_in][96], the per-pixel tap contributions that
  * stemb200_synthesis_col2im sums; act_out: the layer's own activation (NHWC fp16) or NULL to skip writing it
  * (it is then never in HBM). */
 int stemb200_conv2d_gdn_last_fwd(const stemb200_conv_desc* d, const void* const* in, const void* packed_weight,
                                  const float* bias, const void* packed_gamma, const float* beta,
                                  const void* packed_w6, void* col_out, void* act_out, void* stream);
+/* Column of the col rows that holds tap (r, s) of output channel c (0 <= r, s <= 4, 0 <= c <= 2), in [0, 96), or a
+ * negative error code. The order groups the taps by the 2x2 output quad they land in, so that the col2im kernel sums
+ * a quad from aligned vector loads: taps r in {0,1} / {2,3} / {4} reach the quad one row above / in / below the
+ * input pixel, likewise s for columns; inside a group the order is [r & 1][s & 1][c]. */
+int stemb200_synthesis_col_index(int32_t r, int32_t s, int32_t c);
 /* col2im + bias + clamp + squared error of the final deconv (k5, s2, p2, op1): x_hat[c][oh][ow] = bias[c] +
- * sum over taps (r, s) with oh = 2 i - 2 + r, ow = 2 j - 2 + s of col[i][j][(r*5+s)*3 + c]; col: NHWC fp16
- * [n][h2][w2][96]; x_hat: NCHW fp32 [n][3][2 h2][2 w2]; x_ref / sq_err as in stemb200_synthesis_tail. */
+ * sum over taps (r, s) with oh = 2 i - 2 + r, ow = 2 j - 2 + s of col[i][j][stemb200_synthesis_col_index(r, s, c)];
+ * col: NHWC fp16 [n][h2][w2][96], 16-byte aligned; x_hat: NCHW fp32 [n][3][2 h2][2 w2], 8-byte aligned; x_ref /
+ * sq_err as in stemb200_synthesis_tail. */
 int stemb200_synthesis_col2im(const void* col_f16, const float* bias3, float* x_hat_nchw, int32_t n, int32_t h2,
                               int32_t w2, const float* x_ref, int32_t h_ref, int32_t w_ref, int32_t pad_top,
                               int32_t pad_left, double* sq_err, int32_t clamp01, void* stream);

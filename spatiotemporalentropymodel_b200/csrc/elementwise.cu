@@ -338,9 +338,53 @@ __global__ void gc_flat_kernel(const float* __restrict__ y, const float* __restr
   if (bits) block_accumulate(acc, bits, red);
 }
 
-// NHWC inputs -> NCHW outputs. Block = 32 pixels x 64 channels; reads are 256-byte channel runs,
-// writes are 128-byte pixel runs.
-constexpr int kGcPix = 32, kGcCh = 64;
+constexpr int kGcPix = 32, kGcCh = 64, kGcIter = kGcPix / 4;
+// One thread's 8 positions of a gc_nhwc_kernel tile (pixel slots 0, 4, ..., 28 of one channel). kFull: all 8 slots
+// are inside the frame, so the operand loads are unguarded and issue back to back.
+template <bool kIdx, bool kFull>
+__device__ __forceinline__ float gc_tile_eval(const float* __restrict__ yp, const __half* __restrict__ cp,
+                                              const float* __restrict__ sp, int c, int lim, int y_is_nchw,
+                                              int yhat_mode, bool want_idx, const float* table, int n_scales,
+                                              float scale_bound, float lik_bound, float* s_yhat, float* s_lik,
+                                              int* s_idx, int* s_sym) {
+  constexpr int kIter = 8;
+  float yv[kIter], cv[kIter], sg[kIter], mu[kIter];
+  const int step = 4 * c;
+#pragma unroll
+  for (int k = 0; k < kIter; ++k) {
+    const bool ok = kFull || 4 * k < lim;
+    yv[k] = y_is_nchw ? s_yhat[4 * k] : (ok ? __ldg(yp) : 0.f);
+    cv[k] = (cp && ok) ? __half2float(*cp) : 0.f;
+    sg[k] = ok ? __ldg(sp) : 1.f;
+    mu[k] = ok ? __ldg(sp + c) : 0.f;
+    yp += step;
+    if (cp) cp += step;
+    sp += 2 * step;
+  }
+  float acc = 0.f;
+#pragma unroll
+  for (int k = 0; k < kIter; ++k) {
+    if (kFull || 4 * k < lim) {
+      const float v = yv[k] - cv[k];  // _Res: the coded quantity is y_cur - y_conditioned (:852)
+      GcOut o = gc_eval(v, sg[k], mu[k], table, n_scales, scale_bound, lik_bound, want_idx);
+      // SPM variants return y_hat = round(y [- cond]) [+ cond] (:570, :856-868), not the GC output
+      if (yhat_mode == 1) o.y_hat = rintf(v) + cv[k];
+      s_yhat[4 * k] = o.y_hat;
+      s_lik[4 * k] = o.lik;
+      if (kIdx) {
+        s_idx[4 * k] = o.idx;
+        s_sym[4 * k] = o.sym;
+      }
+      acc -= __log2f(o.lik);  // lik >= 1e-9: no denormals; the bit count is a statistic (0.5 % gate)
+    }
+  }
+  return acc;
+}
+
+// NHWC inputs -> NCHW outputs. Block = 32 pixels x 64 channels; reads are 256-byte channel runs, writes are 128-byte
+// pixel runs. Thread (ch, q) evaluates pixels q, q + 4, ..., q + 28 of channel ch: all operands of the 8 positions
+// are fetched up front through pointers that advance by a constant, then the tile is transposed through smem.
+template <bool kIdx>
 __global__ void __launch_bounds__(256)
 gc_nhwc_kernel(const float* __restrict__ y, int y_is_nchw, const __half* __restrict__ cond,
                const float* __restrict__ params, int c, int hw, int yhat_mode,
@@ -349,19 +393,18 @@ gc_nhwc_kernel(const float* __restrict__ y, int y_is_nchw, const __half* __restr
                double* bits) {
   __shared__ float s_yhat[kGcCh][kGcPix + 1];
   __shared__ float s_lik[kGcCh][kGcPix + 1];
-  __shared__ int s_idx[kGcCh][kGcPix + 1];
-  __shared__ int s_sym[kGcCh][kGcPix + 1];
-  __shared__ float table[256];
+  __shared__ int s_idx[kIdx ? kGcCh : 1][kGcPix + 1];
+  __shared__ int s_sym[kIdx ? kGcCh : 1][kGcPix + 1];
+  __shared__ float table[kIdx ? 256 : 1];
   __shared__ float red[32];
   const int n = blockIdx.z;
   const int p0 = blockIdx.x * kGcPix, c0 = blockIdx.y * kGcCh;
-  const bool want_idx = idx != nullptr;
-  if (want_idx)
+  const bool want_idx = kIdx && idx != nullptr;
+  if (want_idx) {
     for (int i = threadIdx.x; i < n_scales; i += blockDim.x) table[i] = table_g[i];
-  __syncthreads();
+    __syncthreads();
+  }
   const float* yb = y + static_cast<long long>(n) * hw * c;
-  const __half* cb = cond ? cond + static_cast<long long>(n) * hw * c : nullptr;
-  const float* pb = params + static_cast<long long>(n) * hw * 2 * c;
   float acc = 0.f;
   if (y_is_nchw) {
     // stage the NCHW tile through smem so the channel-major phase below reads it conflict-free
@@ -374,39 +417,44 @@ gc_nhwc_kernel(const float* __restrict__ y, int y_is_nchw, const __half* __restr
     __syncthreads();
   }
   {
-    const int ch = threadIdx.x & (kGcCh - 1);
+    const int ch = threadIdx.x & (kGcCh - 1), q = threadIdx.x / kGcCh;
     const int cc = c0 + ch;
-    for (int pi = threadIdx.x / kGcCh; pi < kGcPix; pi += 256 / kGcCh) {
-      const int pp = p0 + pi;
-      if (pp < hw && cc < c) {
-        float yv = y_is_nchw ? s_yhat[ch][pi] : yb[static_cast<long long>(pp) * c + cc];
-        const float cv = cb ? __half2float(cb[static_cast<long long>(pp) * c + cc]) : 0.f;
-        yv -= cv;  // _Res: the coded quantity is y_cur - y_conditioned (spatiotemporalpriors.py:852)
-        const float sg = pb[static_cast<long long>(pp) * 2 * c + cc];
-        const float mu = pb[static_cast<long long>(pp) * 2 * c + c + cc];
-        GcOut o = gc_eval(yv, sg, mu, table, n_scales, scale_bound, lik_bound, want_idx);
-        // SPM variants return y_hat = round(y [- cond]) [+ cond] (:570, :856-868), not the GC output
-        if (yhat_mode == 1) o.y_hat = rintf(yv) + cv;
-        s_yhat[ch][pi] = o.y_hat;
-        s_lik[ch][pi] = o.lik;
-        s_idx[ch][pi] = o.idx;
-        s_sym[ch][pi] = o.sym;
-        acc -= log2f(o.lik);
-      }
+    if (cc < c) {
+      const long long e0 = (static_cast<long long>(n) * hw + p0 + q) * c + cc;  // NHWC element of the first pixel
+      const float* yp = y + e0;
+      const __half* cp = cond ? cond + e0 : nullptr;
+      const float* sp = params + 2 * e0 - cc;  // sigma of (pixel, cc); mu is c floats further
+      const int lim = hw - p0 - q;             // pixel slot 4 k of this thread is inside the frame iff 4 k < lim
+      if (lim > 4 * (kGcIter - 1))
+        acc = gc_tile_eval<kIdx, true>(yp, cp, sp, c, lim, y_is_nchw, yhat_mode, want_idx, table, n_scales,
+                                       scale_bound, lik_bound, &s_yhat[ch][q], &s_lik[ch][q], &s_idx[kIdx ? ch : 0][q],
+                                       &s_sym[kIdx ? ch : 0][q]);
+      else
+        acc = gc_tile_eval<kIdx, false>(yp, cp, sp, c, lim, y_is_nchw, yhat_mode, want_idx, table, n_scales,
+                                        scale_bound, lik_bound, &s_yhat[ch][q], &s_lik[ch][q], &s_idx[kIdx ? ch : 0][q],
+                                        &s_sym[kIdx ? ch : 0][q]);
     }
   }
   __syncthreads();
   {
-    const int pi = threadIdx.x & (kGcPix - 1);
+    const int pi = threadIdx.x & (kGcPix - 1), chq = threadIdx.x / kGcPix;
     const int pp = p0 + pi;
-    for (int ch = threadIdx.x / kGcPix; ch < kGcCh; ch += 256 / kGcPix) {
-      const int cc = c0 + ch;
-      if (pp < hw && cc < c) {
-        const long long o = (static_cast<long long>(n) * c + cc) * hw + pp;
-        if (y_hat) y_hat[o] = s_yhat[ch][pi];
-        if (lik) lik[o] = s_lik[ch][pi];
-        if (idx) idx[o] = s_idx[ch][pi];
-        if (sym) sym[o] = s_sym[ch][pi];
+    if (pp < hw) {
+      long long o = (static_cast<long long>(n) * c + c0 + chq) * hw + pp;
+      const long long ostep = static_cast<long long>(256 / kGcPix) * hw;
+      const bool ch_full = c0 + kGcCh <= c;
+#pragma unroll
+      for (int k = 0; k < kGcCh / (256 / kGcPix); ++k) {
+        const int ch = chq + k * (256 / kGcPix);
+        if (ch_full || c0 + ch < c) {
+          if (y_hat) y_hat[o] = s_yhat[ch][pi];
+          if (lik) lik[o] = s_lik[ch][pi];
+          if (kIdx) {
+            if (idx) idx[o] = s_idx[ch][pi];
+            if (sym) sym[o] = s_sym[ch][pi];
+          }
+        }
+        o += ostep;
       }
     }
   }
@@ -554,75 +602,151 @@ synthesis_tail_kernel(const float* __restrict__ in, float* __restrict__ xhat, in
 
 // ---------------------------------------------------------------------------------------------------
 // Last synthesis layer as GEMM + col2im (priors.py:438 deconv(N, 3, k5, s2, p2, op1)): the producing layer's kernel
-// left, for every input pixel (i, j), the 75 products col[i][j][(r*5+s)*3 + c] = sum_ci x[ci][i][j] * w[ci][c][r][s]
-// (fp16, 96 per pixel). Output pixel (oh, ow) sums the taps with oh = 2 i - 2 + r, ow = 2 j - 2 + s (2-3 per axis),
-// adds the bias, clamps, and accumulates the squared error against the un-padded source frame.
-// One block = 16 x 32 output pixels; the 10 x 18 contributing col rows are staged in shared memory (cp.async).
+// left, for every input pixel (i, j), the 75 products sum_ci x[ci][i][j] * w[ci][c][r][s] (fp16, 96 per pixel).
+// Output pixel (oh, ow) sums the taps with oh = 2 i - 2 + r, ow = 2 j - 2 + s (2-3 per axis), adds the bias, clamps,
+// and accumulates the squared error against the un-padded source frame.
+//
+// Column order ("quad-grouped", col_index below): the 2x2 output quad (2 i' + a, 2 j' + b) takes from input pixel
+// (i' + di, j' + dj), di, dj in {+1, 0, -1}, exactly the taps r in R(di), s in S(dj) with R(+1) = {0, 1},
+// R(0) = {2, 3}, R(-1) = {4} (a = r & 1, b = s & 1). The 9 groups are stored contiguously, 8-byte aligned and ordered
+// [a][b][c], so one thread sums a whole quad from 13 vector loads of shared memory with compile-time offsets.
+// One block = 16 x 16 quads (32 x 32 output pixels); the 18 x 18 contributing col rows are staged with cp.async at a
+// 208-byte pitch (13 x 16 B: LDS.128 of 8 consecutive lanes fall into 8 different bank groups).
 // ---------------------------------------------------------------------------------------------------
-constexpr int kC2iTH = 16, kC2iTW = 32;                    // output tile
-constexpr int kC2iIH = kC2iTH / 2 + 2, kC2iIW = kC2iTW / 2 + 2;  // input halo tile
-constexpr int kC2iPitch = 208;                             // bytes per staged pixel (192 + 16: spreads the banks)
+constexpr int kC2iQ = 16;            // quads per tile side
+constexpr int kC2iI = kC2iQ + 2;     // staged input pixels per side
+constexpr int kC2iPitch = 208;       // bytes per staged pixel
+constexpr int kC2iChunks = 11;       // 16-byte chunks of a col row that hold data (88 of 96 columns)
+constexpr int kC2iSmem = kC2iI * kC2iI * kC2iPitch;
+
+__host__ __device__ constexpr int c2i_group_base(int di, int dj) {
+  return di == 1 ? (dj == 1 ? 0 : dj == 0 ? 12 : 48)
+       : di == 0 ? (dj == 1 ? 24 : dj == 0 ? 36 : 56)
+                 : (dj == 1 ? 64 : dj == 0 ? 72 : 80);
+}
+__host__ __device__ constexpr int c2i_tap_d(int r) { return r < 2 ? 1 : r < 4 ? 0 : -1; }
+__host__ __device__ constexpr int c2i_col_index(int r, int s, int c) {
+  const int di = c2i_tap_d(r), dj = c2i_tap_d(s);
+  const int nb = dj == -1 ? 1 : 2;
+  return c2i_group_base(di, dj) + (((r & 1) * nb) + (s & 1)) * 3 + c;
+}
+
+// adds group (DI, DJ) of the staged pixel `px` to the quad accumulators acc[a][b][c]
+template <int DI, int DJ>
+__device__ __forceinline__ void c2i_add_group(const unsigned char* px, float (&acc)[2][2][3]) {
+  constexpr int NA = DI == -1 ? 1 : 2, NB = DJ == -1 ? 1 : 2, N = NA * NB * 3;
+  constexpr int BASE = c2i_group_base(DI, DJ);  // halves, multiple of 4
+  uint32_t w[(N + 1) / 2 + 3];
+  const unsigned char* p = px + BASE * 2;
+  if constexpr (N == 12 && BASE % 8 == 0) {
+    const uint4 q = *reinterpret_cast<const uint4*>(p);
+    const uint2 d = *reinterpret_cast<const uint2*>(p + 16);
+    w[0] = q.x; w[1] = q.y; w[2] = q.z; w[3] = q.w; w[4] = d.x; w[5] = d.y;
+  } else if constexpr (N == 12) {
+    const uint2 d = *reinterpret_cast<const uint2*>(p);
+    const uint4 q = *reinterpret_cast<const uint4*>(p + 8);
+    w[0] = d.x; w[1] = d.y; w[2] = q.x; w[3] = q.y; w[4] = q.z; w[5] = q.w;
+  } else if constexpr (N == 6) {
+    const uint4 q = *reinterpret_cast<const uint4*>(p);
+    w[0] = q.x; w[1] = q.y; w[2] = q.z;
+  } else {
+    const uint2 d = *reinterpret_cast<const uint2*>(p);
+    w[0] = d.x; w[1] = d.y;
+  }
+#pragma unroll
+  for (int k = 0; k < N; ++k) {
+    const __half2 h2 = *reinterpret_cast<const __half2*>(&w[k >> 1]);
+    const float f = (k & 1) ? __high2float(h2) : __low2float(h2);
+    const int c = k % 3, ab = k / 3, b = ab % NB, a = ab / NB;
+    acc[a][b][c] += f;
+  }
+}
 
 __global__ void __launch_bounds__(256)
 synthesis_col2im_kernel(const __half* __restrict__ col, const float* __restrict__ bias, float* __restrict__ xhat, int h2,
                         int w2, const float* __restrict__ xref, int h_ref, int w_ref, int pad_top, int pad_left,
                         double* sq_err, int clamp01) {
-  __shared__ __align__(16) unsigned char s_col[kC2iIH * kC2iIW * kC2iPitch];
+  extern __shared__ __align__(16) unsigned char s_col[];
   __shared__ float red[32];
   const int n = blockIdx.z;
-  const int oh0 = blockIdx.y * kC2iTH, ow0 = blockIdx.x * kC2iTW;
-  const int i0 = oh0 / 2 - 1, j0 = ow0 / 2 - 1;
-  for (int c = threadIdx.x; c < kC2iIH * kC2iIW * 12; c += 256) {
-    const int px = c / 12, part = c - px * 12;
-    const int ii = px / kC2iIW, jj = px - ii * kC2iIW;
-    const int i = i0 + ii, j = j0 + jj;
-    const bool inb = i >= 0 && i < h2 && j >= 0 && j < w2;
-    const __half* src = inb ? col + ((static_cast<long long>(n) * h2 + i) * w2 + j) * 96 + part * 8 : col;
-    const unsigned int dst = static_cast<unsigned int>(__cvta_generic_to_shared(s_col + px * kC2iPitch + part * 16));
-    const int nb = inb ? 16 : 0;
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(nb) : "memory");
+  const int i0 = blockIdx.y * kC2iQ - 1, j0 = blockIdx.x * kC2iQ - 1;  // staged origin (one halo pixel)
+  // staging: thread t < 18 * 11 owns (column jj, chunk part) of every staged row
+  if (threadIdx.x < kC2iI * kC2iChunks) {
+    const int jj = threadIdx.x / kC2iChunks, part = threadIdx.x - jj * kC2iChunks;
+    const int j = j0 + jj;
+    const bool j_in = j >= 0 && j < w2;
+    const __half* src = col + ((static_cast<long long>(n) * h2 + i0) * w2 + (j_in ? j : 0)) * 96 + part * 8;
+    unsigned int dst = static_cast<unsigned int>(__cvta_generic_to_shared(s_col + jj * kC2iPitch + part * 16));
+#pragma unroll 6
+    for (int ii = 0; ii < kC2iI; ++ii) {
+      const int i = i0 + ii;
+      const bool inb = j_in && i >= 0 && i < h2;
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(inb ? src : col), "r"(inb ? 16 : 0)
+                   : "memory");
+      src += static_cast<long long>(w2) * 96;
+      dst += kC2iI * kC2iPitch;
+    }
   }
   asm volatile("cp.async.wait_all;" ::: "memory");
   __syncthreads();
-  const int H = 2 * h2, W = 2 * w2;
-  const float b0 = __ldg(bias), b1 = __ldg(bias + 1), b2 = __ldg(bias + 2);
-  float acc = 0.f;
-  for (int o = threadIdx.x; o < kC2iTH * kC2iTW; o += 256) {
-    const int ty = o / kC2iTW, tx = o - ty * kC2iTW;
-    const int oh = oh0 + ty, ow = ow0 + tx;
-    if (oh >= H || ow >= W) continue;
-    float v0 = b0, v1 = b1, v2 = b2;
-    for (int r = oh & 1; r < 5; r += 2) {
-      const int ii = (oh + 2 - r) / 2 - i0;  // staged row (out-of-frame rows were zero-filled)
-      for (int s_ = ow & 1; s_ < 5; s_ += 2) {
-        const int jj = (ow + 2 - s_) / 2 - j0;
-        const __half* e = reinterpret_cast<const __half*>(s_col + (ii * kC2iIW + jj) * kC2iPitch) + (r * 5 + s_) * 3;
-        v0 += __half2float(e[0]);
-        v1 += __half2float(e[1]);
-        v2 += __half2float(e[2]);
+  const int qi = threadIdx.x >> 4, qj = threadIdx.x & 15;
+  const int qi_g = blockIdx.y * kC2iQ + qi, qj_g = blockIdx.x * kC2iQ + qj;
+  float err = 0.f;
+  if (qi_g < h2 && qj_g < w2) {
+    float acc[2][2][3];
+    const float b0 = __ldg(bias), b1 = __ldg(bias + 1), b2 = __ldg(bias + 2);
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+      for (int b = 0; b < 2; ++b) {
+        acc[a][b][0] = b0;
+        acc[a][b][1] = b1;
+        acc[a][b][2] = b2;
       }
-    }
-    if (clamp01) {
-      v0 = fminf(fmaxf(v0, 0.f), 1.f);
-      v1 = fminf(fmaxf(v1, 0.f), 1.f);
-      v2 = fminf(fmaxf(v2, 0.f), 1.f);
-    }
+    const unsigned char* ctr = s_col + ((qi + 1) * kC2iI + (qj + 1)) * kC2iPitch;
+    constexpr int kRow = kC2iI * kC2iPitch;
+    c2i_add_group<1, 1>(ctr + kRow + kC2iPitch, acc);
+    c2i_add_group<1, 0>(ctr + kRow, acc);
+    c2i_add_group<1, -1>(ctr + kRow - kC2iPitch, acc);
+    c2i_add_group<0, 1>(ctr + kC2iPitch, acc);
+    c2i_add_group<0, 0>(ctr, acc);
+    c2i_add_group<0, -1>(ctr - kC2iPitch, acc);
+    c2i_add_group<-1, 1>(ctr - kRow + kC2iPitch, acc);
+    c2i_add_group<-1, 0>(ctr - kRow, acc);
+    c2i_add_group<-1, -1>(ctr - kRow - kC2iPitch, acc);
+    const int H = 2 * h2, W = 2 * w2;
     const long long plane = static_cast<long long>(H) * W;
+    const int oh = 2 * qi_g, ow = 2 * qj_g;
     float* dst = xhat + static_cast<long long>(n) * 3 * plane + static_cast<long long>(oh) * W + ow;
-    dst[0] = v0;
-    dst[plane] = v1;
-    dst[2 * plane] = v2;
-    if (xref) {
-      const int yr = oh - pad_top, xr = ow - pad_left;
-      if (yr >= 0 && yr < h_ref && xr >= 0 && xr < w_ref) {
-        const long long rp = static_cast<long long>(h_ref) * w_ref;
-        const float* rr = xref + static_cast<long long>(n) * 3 * rp + static_cast<long long>(yr) * w_ref + xr;
-        const float d0 = __ldg(rr) - v0, d1 = __ldg(rr + rp) - v1, d2 = __ldg(rr + 2 * rp) - v2;
-        acc += d0 * d0 + d1 * d1 + d2 * d2;
+    const long long rp = static_cast<long long>(h_ref) * w_ref;
+    const int xr = ow - pad_left;
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+#pragma unroll
+      for (int a = 0; a < 2; ++a) {
+        float v0 = acc[a][0][c], v1 = acc[a][1][c];
+        if (clamp01) {
+          v0 = fminf(fmaxf(v0, 0.f), 1.f);
+          v1 = fminf(fmaxf(v1, 0.f), 1.f);
+        }
+        *reinterpret_cast<float2*>(dst + c * plane + a * W) = make_float2(v0, v1);
+        if (xref) {
+          const int yr = oh + a - pad_top;
+          if (yr >= 0 && yr < h_ref) {
+            const float* rr = xref + (static_cast<long long>(n) * 3 + c) * rp + static_cast<long long>(yr) * w_ref;
+            if (xr >= 0 && xr < w_ref) {
+              const float d = __ldg(rr + xr) - v0;
+              err += d * d;
+            }
+            if (xr + 1 >= 0 && xr + 1 < w_ref) {
+              const float d = __ldg(rr + xr + 1) - v1;
+              err += d * d;
+            }
+          }
+        }
       }
-    }
   }
-  if (sq_err) block_accumulate(acc, sq_err + n, red);
+  if (sq_err) block_accumulate(err, sq_err + n, red);
 }
 
 }  // namespace stem
@@ -682,33 +806,67 @@ extern "C" int stemb200_im2col_k5s2_c3(const float* x_nchw, void* out_rows, int3
   return 0;
 }
 
-// NCHW fp32 frame -> zero-bordered NHWC8 fp16 canvas (operand of the row_taps first layer); one 16-byte store per
-// canvas pixel, reads coalesced per channel plane.
-__global__ void __launch_bounds__(256)
+// NCHW fp32 frame -> zero-bordered NHWC8 fp16 canvas (operand of the row_taps first layer). One block row = one canvas
+// row; one thread = 4 consecutive canvas pixels whose source pixels start at a multiple of 4 in the frame row, so
+// the c channel planes are read with one 16-byte load each and the 4 canvas pixels leave as 64 contiguous bytes.
+__device__ __forceinline__ uint4 pack_nhwc8(const float (&v)[8]) {
+  const __half2 h0 = __floats2half2_rn(v[0], v[1]), h1 = __floats2half2_rn(v[2], v[3]);
+  const __half2 h2 = __floats2half2_rn(v[4], v[5]), h3 = __floats2half2_rn(v[6], v[7]);
+  uint4 o;
+  o.x = *reinterpret_cast<const uint32_t*>(&h0);
+  o.y = *reinterpret_cast<const uint32_t*>(&h1);
+  o.z = *reinterpret_cast<const uint32_t*>(&h2);
+  o.w = *reinterpret_cast<const uint32_t*>(&h3);
+  return o;
+}
+
+__global__ void __launch_bounds__(128)
 frame_to_nhwc8_kernel(const float* __restrict__ x, uint4* __restrict__ canvas, int c, int h, int w, int hc, int wc,
-                      int off_top, int off_left, long long total) {
-  for (long long i = blockIdx.x * 256LL + threadIdx.x; i < total; i += gridDim.x * 256LL) {
-    const int cw = static_cast<int>(i % wc);
-    const long long t = i / wc;
-    const int chh = static_cast<int>(t % hc);
-    const long long n = t / hc;
-    const int ih = chh - off_top, iw = cw - off_left;
-    float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    if (ih >= 0 && ih < h && iw >= 0 && iw < w) {
-      const float* px = x + (n * c * h + ih) * static_cast<long long>(w) + iw;
+                      int off_top, int off_left, int groups, int vec_ok) {
+  const int row = blockIdx.x;  // n * hc + canvas row
+  const int n = row / hc, chh = row - n * hc;
+  const int ih = chh - off_top;
+  const int g = blockIdx.y * 128 + threadIdx.x;
+  if (g >= groups) return;
+  const int iw0 = 4 * g - ((off_left + 3) & ~3);  // multiple of 4 (may start left of the frame)
+  const int cw0 = iw0 + off_left;
+  uint4* dst = canvas + static_cast<long long>(row) * wc;
+  float v[4][8];
+#pragma unroll
+  for (int p = 0; p < 4; ++p)
+#pragma unroll
+    for (int ch = 0; ch < 8; ++ch) v[p][ch] = 0.f;
+  if (ih >= 0 && ih < h) {
+    const float* px = x + (static_cast<long long>(n) * c * h + ih) * w;
+    const long long plane = static_cast<long long>(h) * w;
+    if (vec_ok && iw0 >= 0 && iw0 + 3 < w) {
 #pragma unroll
       for (int ch = 0; ch < 8; ++ch)
-        if (ch < c) v[ch] = __ldg(px + static_cast<long long>(ch) * h * w);
+        if (ch < c) {
+          const float4 f = __ldg(reinterpret_cast<const float4*>(px + ch * plane + iw0));
+          v[0][ch] = f.x;
+          v[1][ch] = f.y;
+          v[2][ch] = f.z;
+          v[3][ch] = f.w;
+        }
+    } else {
+#pragma unroll
+      for (int p = 0; p < 4; ++p)
+        if (iw0 + p >= 0 && iw0 + p < w) {
+#pragma unroll
+          for (int ch = 0; ch < 8; ++ch)
+            if (ch < c) v[p][ch] = __ldg(px + ch * plane + iw0 + p);
+        }
     }
-    uint4 o;
-    __half2 h0 = __floats2half2_rn(v[0], v[1]), h1 = __floats2half2_rn(v[2], v[3]);
-    __half2 h2 = __floats2half2_rn(v[4], v[5]), h3 = __floats2half2_rn(v[6], v[7]);
-    o.x = *reinterpret_cast<uint32_t*>(&h0);
-    o.y = *reinterpret_cast<uint32_t*>(&h1);
-    o.z = *reinterpret_cast<uint32_t*>(&h2);
-    o.w = *reinterpret_cast<uint32_t*>(&h3);
-    canvas[i] = o;
   }
+#pragma unroll
+  for (int p = 0; p < 4; ++p)
+    if (cw0 + p >= 0 && cw0 + p < wc) dst[cw0 + p] = pack_nhwc8(v[p]);
+}
+
+extern "C" int stemb200_synthesis_col_index(int32_t r, int32_t s, int32_t c) {
+  if (r < 0 || r > 4 || s < 0 || s > 4 || c < 0 || c > 2) return set_error("synthesis_col_index: bad argument");
+  return c2i_col_index(r, s, c);
 }
 
 extern "C" int stemb200_synthesis_col2im(const void* col_f16, const float* bias3, float* x_hat_nchw, int32_t n,
@@ -719,9 +877,17 @@ extern "C" int stemb200_synthesis_col2im(const void* col_f16, const float* bias3
     return set_error("synthesis_col2im: bad argument");
   if (x_ref && (h_ref < 1 || w_ref < 1 || pad_top < 0 || pad_left < 0))
     return set_error("synthesis_col2im: bad reference geometry");
-  dim3 grid((2 * w2 + kC2iTW - 1) / kC2iTW, (2 * h2 + kC2iTH - 1) / kC2iTH, n);
+  if (reinterpret_cast<uintptr_t>(x_hat_nchw) & 7) return set_error("synthesis_col2im: x_hat must be 8-byte aligned");
+  if (reinterpret_cast<uintptr_t>(col_f16) & 15) return set_error("synthesis_col2im: col must be 16-byte aligned");
+  dim3 grid((w2 + kC2iQ - 1) / kC2iQ, (h2 + kC2iQ - 1) / kC2iQ, n);
   if (grid.y > 65535) return set_error("synthesis_col2im: frame too large");
-  synthesis_col2im_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(synthesis_col2im_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kC2iSmem);
+    if (e != cudaSuccess) return set_cuda_error("synthesis_col2im: smem attribute", e);
+    attr_set = true;
+  }
+  synthesis_col2im_kernel<<<grid, 256, kC2iSmem, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const __half*>(col_f16), bias3, x_hat_nchw, h2, w2, x_ref, h_ref, w_ref, pad_top, pad_left, sq_err,
       clamp01);
   CHECK_LAUNCH("synthesis_col2im");
@@ -735,10 +901,14 @@ extern "C" int stemb200_frame_to_nhwc8(const float* x_nchw, void* canvas, int32_
       pad_left < 0 || border < 0 || pad_top + h > h_pad || pad_left + w > w_pad)
     return set_error("frame_to_nhwc8: bad argument");
   const int hc = h_pad + 2 * border, wc = w_pad + 2 * border;
-  const long long total = static_cast<long long>(n) * hc * wc;
-  const int blocks = static_cast<int>(std::min<long long>((total + 255) / 256, 148LL * 32));
-  frame_to_nhwc8_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      x_nchw, static_cast<uint4*>(canvas), c, h, w, hc, wc, pad_top + border, pad_left + border, total);
+  const int off_top = pad_top + border, off_left = pad_left + border;
+  if (static_cast<long long>(n) * hc > 0x7fffffffLL) return set_error("frame_to_nhwc8: frame too large");
+  // groups of 4 canvas pixels, the first one starting at canvas column off_left - roundup4(off_left) <= 0
+  const int groups = (wc + ((off_left + 3) & ~3) - off_left + 3) / 4;
+  const int vec_ok = (w % 4 == 0) && (reinterpret_cast<uintptr_t>(x_nchw) % 16 == 0);
+  dim3 grid(n * hc, (groups + 127) / 128);
+  frame_to_nhwc8_kernel<<<grid, 128, 0, static_cast<cudaStream_t>(stream)>>>(
+      x_nchw, static_cast<uint4*>(canvas), c, h, w, hc, wc, off_top, off_left, groups, vec_ok);
   CHECK_LAUNCH("frame_to_nhwc8");
   return 0;
 }
@@ -825,9 +995,14 @@ extern "C" int stemb200_gaussian_conditional_fwd(const float* y_nhwc, int32_t y_
     return set_error("gaussian_conditional_fwd: idx needs a scale table of 1..256 entries");
   const int hw = h * w;
   dim3 grid((hw + kGcPix - 1) / kGcPix, (c + kGcCh - 1) / kGcCh, n);
-  gc_nhwc_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      y_nhwc, y_is_nchw, static_cast<const __half*>(cond_f16), params_nhwc, c, hw, yhat_mode, scale_table,
-      n_scales, scale_bound, lik_bound, y_hat_nchw, lik_nchw, idx_nchw, sym_nchw, bits);
+  if (idx_nchw || sym_nchw)
+    gc_nhwc_kernel<true><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        y_nhwc, y_is_nchw, static_cast<const __half*>(cond_f16), params_nhwc, c, hw, yhat_mode, scale_table,
+        n_scales, scale_bound, lik_bound, y_hat_nchw, lik_nchw, idx_nchw, sym_nchw, bits);
+  else
+    gc_nhwc_kernel<false><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        y_nhwc, y_is_nchw, static_cast<const __half*>(cond_f16), params_nhwc, c, hw, yhat_mode, scale_table,
+        n_scales, scale_bound, lik_bound, y_hat_nchw, lik_nchw, idx_nchw, sym_nchw, bits);
   CHECK_LAUNCH("gaussian_conditional_fwd");
   return 0;
 }

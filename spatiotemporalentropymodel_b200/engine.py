@@ -419,12 +419,21 @@ class TransformsEngine:
             bm[uv * 3:uv * 3 + 3] = b6
         self.gs_last = ConvOp(wm, bm, c_in=[N], c_out=64, k=5, stride=2, tap_mask=mask, out_dtype=DT_F32,
                               alg_flops_per_out_pixel=4 * 2.0 * N * 3 * 25)  # 4 input pixels per super pixel
-        # default path: the same layer as a per-pixel GEMM fused behind gs4's IGDN epilogue, W6[(r*5+s)*3+c][ci] =
-        # w[ci][c][r][s] (75 rows + 21 zero rows), followed by a col2im kernel (STEMB200_FUSE_LAST=0 selects the
-        # stand-alone merged-phase conv above instead)
+        # default path: the same layer as a per-pixel GEMM fused behind gs4's IGDN epilogue,
+        # W6[col_index(r, s, c)][ci] = w[ci][c][r][s] (75 of 96 rows, quad-grouped order of the col2im kernel),
+        # followed by that col2im kernel (STEMB200_FUSE_LAST=0 selects the stand-alone merged-phase conv above)
         import os
         self.fuse_last = os.environ.get("STEMB200_FUSE_LAST", "1") != "0" and N == 192
-        w6 = F.pad(wt.permute(2, 3, 1, 0).reshape(75, N), (0, 0, 0, 21)).reshape(96, N, 1, 1).contiguous()
+        lib = _lib.load()
+        w6 = torch.zeros((96, N), device=dev)
+        for r in range(5):
+            for s_ in range(5):
+                for c in range(3):
+                    k = lib.stemb200_synthesis_col_index(r, s_, c)
+                    if k < 0:
+                        _lib.check(k, "synthesis_col_index")
+                    w6[k] = wt[:, c, r, s_]
+        w6 = w6.reshape(96, N, 1, 1).contiguous()
         self.w6 = ConvOp(w6, torch.zeros(96, device=dev), c_in=[N], c_out=96, k=1, direct_store=True).packed  # pack only
         self.b6 = b6.contiguous()
         self.gs_conv[2].alg_flops_per_out_pixel_last = 2.0 * N * 3 * 25  # final deconv, per gs4 output pixel
