@@ -1673,6 +1673,31 @@ int encode_weight(CUtensorMap* m, const void* base, long long K, int c_out, int 
   return 0;
 }
 
+}  // namespace
+
+int encode_nhwc_plain(CUtensorMap* m, const void* base, int n, int h, int w, int c, int box_c, int box_w, int box_h) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return set_error("cuTensorMapEncodeTiled unavailable");
+  cuuint64_t dims[4] = {static_cast<cuuint64_t>(c), static_cast<cuuint64_t>(w), static_cast<cuuint64_t>(h),
+                        static_cast<cuuint64_t>(n)};
+  cuuint64_t strides[3] = {static_cast<cuuint64_t>(c) * 2, static_cast<cuuint64_t>(w) * c * 2,
+                           static_cast<cuuint64_t>(h) * w * c * 2};
+  cuuint32_t box[4] = {static_cast<cuuint32_t>(box_c), static_cast<cuuint32_t>(box_w),
+                       static_cast<cuuint32_t>(box_h), 1u};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    char buf[160];
+    snprintf(buf, sizeof(buf), "cuTensorMapEncodeTiled(plain nhwc) failed: %d (c=%d w=%d h=%d n=%d box=%d,%d,%d)",
+             static_cast<int>(r), c, w, h, n, box_c, box_w, box_h);
+    return set_error(buf);
+  }
+  return 0;
+}
+
+namespace {
 // STEMB200_PAIR=0 in the environment disables pair mode (A/B measurements)
 bool pair_mode_enabled() {
   static int v = -1;

@@ -10,6 +10,7 @@
 
 #include "../../include/stemb200.h"
 #include "internal.h"
+#include "ptx.cuh"
 
 namespace stem {
 
@@ -465,7 +466,7 @@ gc_nhwc_kernel(const float* __restrict__ y, int y_is_nchw, const __half* __restr
 // EntropyBottleneck forward (eval): one thread per channel, 16 pixels per block
 // ---------------------------------------------------------------------------------------------------
 constexpr int kEbParams = 59;
-constexpr int kEbPix = 16;
+constexpr int kEbPix = 8;
 
 __device__ __forceinline__ float eb_logits(float x, const float* __restrict__ q) {
   float l[3], m[3];
@@ -507,21 +508,31 @@ __global__ void eb_fwd_kernel(const float* __restrict__ z, const float* __restri
 #pragma unroll
     for (int i = 0; i < kEbParams; ++i) q[i] = params[ch * kEbParams + i];
     const float med = q[58];
-    for (int pi = 0; pi < kEbPix; ++pi) {
-      const int pp = p0 + pi;
-      if (pp >= hw) break;
-      const long long off = (static_cast<long long>(n) * hw + pp) * c + ch;
-      const float zq = rintf(z[off] - med) + med;
-      const float lo = eb_logits(zq - 0.5f, q);
-      const float up = eb_logits(zq + 0.5f, q);
-      const float sum = lo + up;
-      const float sgn = sum > 0.f ? -1.f : (sum < 0.f ? 1.f : 0.f);
-      float lk = fabsf(sigmoidf_(sgn * up) - sigmoidf_(sgn * lo));
-      lk = lower_bound(lk, lik_bound);
-      if (zhat16) zhat16[off] = __float2half_rn(zq);
-      s_z[ch * (kEbPix + 1) + pi] = zq;
-      s_l[ch * (kEbPix + 1) + pi] = lk;
-      acc -= log2f(lk);
+    // 4 positions per round: their (independent) tanh chains interleave, which is what hides the latency here
+    for (int pb = 0; pb < kEbPix; pb += 4) {
+      float zv[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int pp = p0 + pb + u;
+        zv[u] = pp < hw ? z[(static_cast<long long>(n) * hw + pp) * c + ch] : 0.f;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int pi = pb + u, pp = p0 + pi;
+        const float zq = rintf(zv[u] - med) + med;
+        const float lo = eb_logits(zq - 0.5f, q);
+        const float up = eb_logits(zq + 0.5f, q);
+        const float sum = lo + up;
+        const float sgn = sum > 0.f ? -1.f : (sum < 0.f ? 1.f : 0.f);
+        float lk = fabsf(sigmoidf_(sgn * up) - sigmoidf_(sgn * lo));
+        lk = lower_bound(lk, lik_bound);
+        if (pp < hw) {
+          if (zhat16) zhat16[(static_cast<long long>(n) * hw + pp) * c + ch] = __float2half_rn(zq);
+          s_z[ch * (kEbPix + 1) + pi] = zq;
+          s_l[ch * (kEbPix + 1) + pi] = lk;
+          acc -= log2f(lk);
+        }
+      }
     }
   }
   __syncthreads();
@@ -610,14 +621,20 @@ synthesis_tail_kernel(const float* __restrict__ in, float* __restrict__ xhat, in
 // (i' + di, j' + dj), di, dj in {+1, 0, -1}, exactly the taps r in R(di), s in S(dj) with R(+1) = {0, 1},
 // R(0) = {2, 3}, R(-1) = {4} (a = r & 1, b = s & 1). The 9 groups are stored contiguously, 8-byte aligned and ordered
 // [a][b][c], so one thread sums a whole quad from 13 vector loads of shared memory with compile-time offsets.
-// One block = 16 x 16 quads (32 x 32 output pixels); the 18 x 18 contributing col rows are staged with cp.async at a
-// 208-byte pitch (13 x 16 B: LDS.128 of 8 consecutive lanes fall into 8 different bank groups).
+// Persistent CTAs (one per SM, 512 threads = 16 x 32 quads = 32 x 64 output pixels per tile): the 18 x 34 contributing
+// col rows (88 of the 96 columns) arrive as ONE 4-D TMA box per tile - frame borders are the box's out-of-range zero
+// fill - into a two-stage mbarrier ring, so the next tile streams in while this one is summed. Staged pixel pitch
+// 176 B = 11 x 16 B: the LDS.128 of 8 consecutive lanes fall into 8 different bank groups.
 // ---------------------------------------------------------------------------------------------------
-constexpr int kC2iQ = 16;            // quads per tile side
-constexpr int kC2iI = kC2iQ + 2;     // staged input pixels per side
-constexpr int kC2iPitch = 208;       // bytes per staged pixel
-constexpr int kC2iChunks = 11;       // 16-byte chunks of a col row that hold data (88 of 96 columns)
-constexpr int kC2iSmem = kC2iI * kC2iI * kC2iPitch;
+constexpr int kC2iQH = 16, kC2iQW = 32;                    // quads per tile
+constexpr int kC2iIH = kC2iQH + 2, kC2iIW = kC2iQW + 2;    // staged input pixels
+constexpr int kC2iCols = 88;                               // staged columns (11 chunks of 8)
+constexpr int kC2iPitch = kC2iCols * 2;                    // bytes per staged pixel
+constexpr int kC2iStageBytes = kC2iIH * kC2iIW * kC2iPitch;
+constexpr int kC2iStageStride = (kC2iStageBytes + 127) & ~127;
+constexpr int kC2iStages = 2;
+constexpr int kC2iThreads = kC2iQH * kC2iQW;
+constexpr int kC2iSmem = 128 + kC2iStages * kC2iStageStride;
 
 __host__ __device__ constexpr int c2i_group_base(int di, int dj) {
   return di == 1 ? (dj == 1 ? 0 : dj == 0 ? 12 : 48)
@@ -662,39 +679,87 @@ __device__ __forceinline__ void c2i_add_group(const unsigned char* px, float (&a
   }
 }
 
-__global__ void __launch_bounds__(256)
-synthesis_col2im_kernel(const __half* __restrict__ col, const float* __restrict__ bias, float* __restrict__ xhat, int h2,
-                        int w2, const float* __restrict__ xref, int h_ref, int w_ref, int pad_top, int pad_left,
-                        double* sq_err, int clamp01) {
-  extern __shared__ __align__(16) unsigned char s_col[];
+__global__ void __launch_bounds__(kC2iThreads, 1)
+synthesis_col2im_kernel(const __grid_constant__ CUtensorMap col_map, const float* __restrict__ bias,
+                        float* __restrict__ xhat, int h2, int w2, int tiles_x, int tiles_per_img, int total_tiles,
+                        const float* __restrict__ xref, int h_ref, int w_ref, int pad_top, int pad_left,
+                        double* sq_err, int clamp01, int ref_vec) {
+  extern __shared__ uint8_t c2i_smem[];
+  __shared__ __align__(8) uint64_t bars[kC2iStages];
   __shared__ float red[32];
-  const int n = blockIdx.z;
-  const int i0 = blockIdx.y * kC2iQ - 1, j0 = blockIdx.x * kC2iQ - 1;  // staged origin (one halo pixel)
-  // staging: thread t < 18 * 11 owns (column jj, chunk part) of every staged row
-  if (threadIdx.x < kC2iI * kC2iChunks) {
-    const int jj = threadIdx.x / kC2iChunks, part = threadIdx.x - jj * kC2iChunks;
-    const int j = j0 + jj;
-    const bool j_in = j >= 0 && j < w2;
-    const __half* src = col + ((static_cast<long long>(n) * h2 + i0) * w2 + (j_in ? j : 0)) * 96 + part * 8;
-    unsigned int dst = static_cast<unsigned int>(__cvta_generic_to_shared(s_col + jj * kC2iPitch + part * 16));
-#pragma unroll 6
-    for (int ii = 0; ii < kC2iI; ++ii) {
-      const int i = i0 + ii;
-      const bool inb = j_in && i >= 0 && i < h2;
-      asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(inb ? src : col), "r"(inb ? 16 : 0)
-                   : "memory");
-      src += static_cast<long long>(w2) * 96;
-      dst += kC2iI * kC2iPitch;
-    }
+  const uint32_t pad128 = (128u - (smem_u32(c2i_smem) & 127u)) & 127u;
+  const uint8_t* stage_ptr = c2i_smem + pad128;
+  const uint32_t stage_u32 = smem_u32(stage_ptr);
+  const int tid = threadIdx.x;
+  auto issue = [&](int tile, int s) {  // thread 0: one box = the whole halo tile
+    const int n = tile / tiles_per_img, rem = tile - n * tiles_per_img;
+    const int ty = rem / tiles_x, tx = rem - ty * tiles_x;
+    const uint32_t bar = smem_u32(&bars[s]);
+    mbar_arrive_expect_tx(bar, kC2iStageBytes);
+    tma_load_4d(stage_u32 + s * kC2iStageStride, &col_map, bar, 0, tx * kC2iQW - 1, ty * kC2iQH - 1, n);
+  };
+  if (tid == 0) {
+    tma_prefetch_desc(&col_map);
+    for (int s = 0; s < kC2iStages; ++s) mbar_init(smem_u32(&bars[s]), 1);
+    fence_barrier_init();
   }
-  asm volatile("cp.async.wait_all;" ::: "memory");
   __syncthreads();
-  const int qi = threadIdx.x >> 4, qj = threadIdx.x & 15;
-  const int qi_g = blockIdx.y * kC2iQ + qi, qj_g = blockIdx.x * kC2iQ + qj;
+  if (tid == 0)
+    for (int s = 0; s < kC2iStages; ++s) {
+      const int tile = blockIdx.x + s * gridDim.x;
+      if (tile < total_tiles) issue(tile, s);
+    }
+  const float b0 = __ldg(bias), b1 = __ldg(bias + 1), b2 = __ldg(bias + 2);
+  const int qi = tid >> 5, qj = tid & 31;
+  const unsigned char* ctr0 = stage_ptr + ((qi + 1) * kC2iIW + (qj + 1)) * kC2iPitch;
+  constexpr int kRow = kC2iIW * kC2iPitch;
+  const int H = 2 * h2, W = 2 * w2;
+  const long long plane = static_cast<long long>(H) * W;
+  const long long rp = static_cast<long long>(h_ref) * w_ref;
   float err = 0.f;
-  if (qi_g < h2 && qj_g < w2) {
+  int err_n = -1;
+  int it = 0;
+  for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+    const int s = it % kC2iStages;
+    const uint32_t ph = (it / kC2iStages) & 1;
+    const int n = tile / tiles_per_img, rem = tile - n * tiles_per_img;
+    const int ty = rem / tiles_x, tx = rem - ty * tiles_x;
+    if (n != err_n) {  // block-uniform: the squared error is kept per frame
+      if (err_n >= 0 && sq_err) block_accumulate(err, sq_err + err_n, red);
+      err = 0.f;
+      err_n = n;
+    }
+    const int qi_g = ty * kC2iQH + qi, qj_g = tx * kC2iQW + qj;
+    const bool valid = qi_g < h2 && qj_g < w2;
+    const int oh = 2 * qi_g, ow = 2 * qj_g;
+    // reference pixels of this quad: fetched before the tile is awaited
+    float rv[3][2][2];
+    bool rok[2] = {false, false};
+    const int xr = ow - pad_left;
+    const bool cok0 = xr >= 0 && xr < w_ref, cok1 = xr + 1 >= 0 && xr + 1 < w_ref;
+    if (xref && valid) {
+#pragma unroll
+      for (int a = 0; a < 2; ++a) {
+        const int yr = oh + a - pad_top;
+        rok[a] = yr >= 0 && yr < h_ref;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          rv[c][a][0] = rv[c][a][1] = 0.f;
+          if (rok[a]) {
+            const float* rr = xref + (static_cast<long long>(n) * 3 + c) * rp + static_cast<long long>(yr) * w_ref + xr;
+            if (ref_vec && cok0 && cok1) {
+              const float2 f = __ldg(reinterpret_cast<const float2*>(rr));
+              rv[c][a][0] = f.x;
+              rv[c][a][1] = f.y;
+            } else {
+              if (cok0) rv[c][a][0] = __ldg(rr);
+              if (cok1) rv[c][a][1] = __ldg(rr + 1);
+            }
+          }
+        }
+      }
+    }
     float acc[2][2][3];
-    const float b0 = __ldg(bias), b1 = __ldg(bias + 1), b2 = __ldg(bias + 2);
 #pragma unroll
     for (int a = 0; a < 2; ++a)
 #pragma unroll
@@ -703,50 +768,45 @@ synthesis_col2im_kernel(const __half* __restrict__ col, const float* __restrict_
         acc[a][b][1] = b1;
         acc[a][b][2] = b2;
       }
-    const unsigned char* ctr = s_col + ((qi + 1) * kC2iI + (qj + 1)) * kC2iPitch;
-    constexpr int kRow = kC2iI * kC2iPitch;
-    c2i_add_group<1, 1>(ctr + kRow + kC2iPitch, acc);
-    c2i_add_group<1, 0>(ctr + kRow, acc);
-    c2i_add_group<1, -1>(ctr + kRow - kC2iPitch, acc);
-    c2i_add_group<0, 1>(ctr + kC2iPitch, acc);
-    c2i_add_group<0, 0>(ctr, acc);
-    c2i_add_group<0, -1>(ctr - kC2iPitch, acc);
-    c2i_add_group<-1, 1>(ctr - kRow + kC2iPitch, acc);
-    c2i_add_group<-1, 0>(ctr - kRow, acc);
-    c2i_add_group<-1, -1>(ctr - kRow - kC2iPitch, acc);
-    const int H = 2 * h2, W = 2 * w2;
-    const long long plane = static_cast<long long>(H) * W;
-    const int oh = 2 * qi_g, ow = 2 * qj_g;
-    float* dst = xhat + static_cast<long long>(n) * 3 * plane + static_cast<long long>(oh) * W + ow;
-    const long long rp = static_cast<long long>(h_ref) * w_ref;
-    const int xr = ow - pad_left;
+    mbar_wait(smem_u32(&bars[s]), ph);
+    if (valid) {
+      const unsigned char* ctr = ctr0 + s * kC2iStageStride;
+      c2i_add_group<1, 1>(ctr + kRow + kC2iPitch, acc);
+      c2i_add_group<1, 0>(ctr + kRow, acc);
+      c2i_add_group<1, -1>(ctr + kRow - kC2iPitch, acc);
+      c2i_add_group<0, 1>(ctr + kC2iPitch, acc);
+      c2i_add_group<0, 0>(ctr, acc);
+      c2i_add_group<0, -1>(ctr - kC2iPitch, acc);
+      c2i_add_group<-1, 1>(ctr - kRow + kC2iPitch, acc);
+      c2i_add_group<-1, 0>(ctr - kRow, acc);
+      c2i_add_group<-1, -1>(ctr - kRow - kC2iPitch, acc);
+    }
+    __syncthreads();  // every thread has read stage s: refill it with the tile two rounds ahead
+    if (tid == 0) {
+      const int next = tile + kC2iStages * static_cast<int>(gridDim.x);
+      if (next < total_tiles) issue(next, s);
+    }
+    if (valid) {
+      float* dst = xhat + static_cast<long long>(n) * 3 * plane + static_cast<long long>(oh) * W + ow;
 #pragma unroll
-    for (int c = 0; c < 3; ++c)
+      for (int c = 0; c < 3; ++c)
 #pragma unroll
-      for (int a = 0; a < 2; ++a) {
-        float v0 = acc[a][0][c], v1 = acc[a][1][c];
-        if (clamp01) {
-          v0 = fminf(fmaxf(v0, 0.f), 1.f);
-          v1 = fminf(fmaxf(v1, 0.f), 1.f);
-        }
-        *reinterpret_cast<float2*>(dst + c * plane + a * W) = make_float2(v0, v1);
-        if (xref) {
-          const int yr = oh + a - pad_top;
-          if (yr >= 0 && yr < h_ref) {
-            const float* rr = xref + (static_cast<long long>(n) * 3 + c) * rp + static_cast<long long>(yr) * w_ref;
-            if (xr >= 0 && xr < w_ref) {
-              const float d = __ldg(rr + xr) - v0;
-              err += d * d;
-            }
-            if (xr + 1 >= 0 && xr + 1 < w_ref) {
-              const float d = __ldg(rr + xr + 1) - v1;
-              err += d * d;
-            }
+        for (int a = 0; a < 2; ++a) {
+          float v0 = acc[a][0][c], v1 = acc[a][1][c];
+          if (clamp01) {
+            v0 = fminf(fmaxf(v0, 0.f), 1.f);
+            v1 = fminf(fmaxf(v1, 0.f), 1.f);
+          }
+          *reinterpret_cast<float2*>(dst + c * plane + a * W) = make_float2(v0, v1);
+          if (xref && rok[a]) {
+            const float d0 = rv[c][a][0] - v0, d1 = rv[c][a][1] - v1;
+            if (cok0) err += d0 * d0;
+            if (cok1) err += d1 * d1;
           }
         }
-      }
+    }
   }
-  if (sq_err) block_accumulate(err, sq_err + n, red);
+  if (err_n >= 0 && sq_err) block_accumulate(err, sq_err + err_n, red);
 }
 
 }  // namespace stem
@@ -879,17 +939,22 @@ extern "C" int stemb200_synthesis_col2im(const void* col_f16, const float* bias3
     return set_error("synthesis_col2im: bad reference geometry");
   if (reinterpret_cast<uintptr_t>(x_hat_nchw) & 7) return set_error("synthesis_col2im: x_hat must be 8-byte aligned");
   if (reinterpret_cast<uintptr_t>(col_f16) & 15) return set_error("synthesis_col2im: col must be 16-byte aligned");
-  dim3 grid((w2 + kC2iQ - 1) / kC2iQ, (h2 + kC2iQ - 1) / kC2iQ, n);
-  if (grid.y > 65535) return set_error("synthesis_col2im: frame too large");
-  static bool attr_set = false;
+  const int tiles_x = (w2 + kC2iQW - 1) / kC2iQW, tiles_y = (h2 + kC2iQH - 1) / kC2iQH;
+  const long long total = static_cast<long long>(tiles_x) * tiles_y * n;
+  if (total > 0x7fffffffLL - 2LL * 65536) return set_error("synthesis_col2im: frame too large");
+  CUtensorMap col_map;
+  if (int rc = encode_nhwc_plain(&col_map, col_f16, n, h2, w2, 96, kC2iCols, kC2iIW, kC2iIH)) return rc;
+  static bool attr_set = false;  // benign race: the attribute set is idempotent
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(synthesis_col2im_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kC2iSmem);
     if (e != cudaSuccess) return set_cuda_error("synthesis_col2im: smem attribute", e);
     attr_set = true;
   }
-  synthesis_col2im_kernel<<<grid, 256, kC2iSmem, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const __half*>(col_f16), bias3, x_hat_nchw, h2, w2, x_ref, h_ref, w_ref, pad_top, pad_left, sq_err,
-      clamp01);
+  const int ref_vec = x_ref && pad_left % 2 == 0 && w_ref % 2 == 0 && (reinterpret_cast<uintptr_t>(x_ref) & 7) == 0;
+  const int grid = static_cast<int>(std::min<long long>(total, num_sms()));
+  synthesis_col2im_kernel<<<grid, kC2iThreads, kC2iSmem, static_cast<cudaStream_t>(stream)>>>(
+      col_map, bias3, x_hat_nchw, h2, w2, tiles_x, tiles_x * tiles_y, static_cast<int>(total), x_ref, h_ref, w_ref,
+      pad_top, pad_left, sq_err, clamp01, ref_vec);
   CHECK_LAUNCH("synthesis_col2im");
   return 0;
 }

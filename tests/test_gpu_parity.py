@@ -340,3 +340,22 @@ def test_fused_last_synthesis_layer_matches_standalone_and_oracle():
         want = ((x_ref - crop).double() ** 2).sum(dim=(1, 2, 3))
         assert torch.allclose(sq, want, rtol=1e-5), fuse
     assert float((outs["1"][0] - outs["0"][0]).abs().max()) < 2e-3
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("geom", [(2, 3, 37, 53, 3, 5, 48, 64), (1, 3, 40, 64, 0, 0, 40, 64), (1, 4, 16, 24, 4, 6, 24, 36),
+                                  (1, 3, 30, 52, 1, 3, 32, 58)])
+def test_frame_to_nhwc8_canvas(dev, geom):
+    """Operand canvas of the first analysis layer (priors.py:422 on the evalSTEM.py:96-109 padded frame): vectorised
+    (w % 4 == 0) and scalar paths, every left-offset residue, channels 3..7 and the border zero - bit-exact."""
+    from spatiotemporalentropymodel_b200 import _lib
+    n, c, h, w, top, left, hp, wp = geom
+    border = 2
+    x = torch.rand(n, c, h, w, generator=torch.Generator().manual_seed(5)).to(dev)
+    canvas = torch.full((n, hp + 2 * border, wp + 2 * border, 8), 7.0, dtype=torch.float16, device=dev)
+    lib = _lib.load()
+    _lib.check(lib.stemb200_frame_to_nhwc8(x.data_ptr(), canvas.data_ptr(), n, c, h, w, hp, wp, top, left, border,
+                                           torch.cuda.current_stream().cuda_stream), "frame_to_nhwc8")
+    want = torch.zeros_like(canvas)
+    want[:, border + top:border + top + h, border + left:border + left + w, :c] = x.permute(0, 2, 3, 1).half()
+    assert torch.equal(canvas, want)

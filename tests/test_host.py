@@ -106,6 +106,31 @@ def test_ar_and_row_taps_abi_validation_without_a_gpu():
     assert lib.stemb200_frame_to_nhwc8(None, None, 1, 3, 8, 8, 8, 8, 0, 0, 2, None) == -1
 
 
+def test_col_index_is_a_quad_grouped_injection():
+    """stemb200_synthesis_col_index (layout of the fused last layer's col rows, priors.py:438): the 75 (tap, channel)
+    pairs land on 75 distinct columns below 88 (the staged part of a row), taps are grouped by the neighbour quad they
+    reach, every group starts on an 8-byte boundary, and bad arguments are rejected."""
+    lib = _lib.load()
+    pos = {}
+    for r in range(5):
+        for s_ in range(5):
+            for c in range(3):
+                pos[(r, s_, c)] = lib.stemb200_synthesis_col_index(r, s_, c)
+    vals = sorted(pos.values())
+    assert len(set(vals)) == 75 and vals[0] == 0 and vals[-1] < 88
+    d = lambda t: 1 if t < 2 else (0 if t < 4 else -1)
+    groups = {}
+    for (r, s_, c), k in pos.items():
+        groups.setdefault((d(r), d(s_)), []).append(k)
+    assert len(groups) == 9
+    for ks in groups.values():
+        ks.sort()
+        assert ks == list(range(ks[0], ks[0] + len(ks))) and ks[0] % 4 == 0      # contiguous, 8-byte aligned
+    assert pos[(2, 2, 0)] + 1 == pos[(2, 2, 1)] and pos[(2, 2, 2)] + 1 == pos[(2, 3, 0)]  # [r & 1][s & 1][c] inside
+    for bad in ((5, 0, 0), (0, -1, 0), (0, 0, 3)):
+        assert lib.stemb200_synthesis_col_index(*bad) < 0
+
+
 @pytest.mark.parametrize("variant", S.STEM_VARIANTS)
 def test_state_dict_contract(variant):
     """The synthetic state_dicts were loaded (strict) by the reference classes when the goldens were made; the
