@@ -598,6 +598,7 @@ def main():
                     "traffic": 8.30e9 / 6 if (variant, T, H, W) == WORKLOADS["gop12_full_1080p"][:4] else None,
                     "traffic_unit": "bytes per launch (dram read+write, ncu, profiles/r01_ncu_bench_conv_gdn_v6.txt)",
                     "launches_per_step": len(dom), "kernel_ms_per_step": dom_ms,
+                    "launch_ms": [round(t, 4) for t, _ in dom],
                     "algorithmic_gflop_per_launch": dom_gf / max(len(dom), 1),
                     "kernel_share_of_step": dom_ms / ms_per_step,
                     "all_dense_kernels": {"launches_per_step": len(allc), "ms_per_step": all_ms,

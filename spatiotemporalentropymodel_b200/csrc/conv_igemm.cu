@@ -68,6 +68,8 @@ struct ConvKernelParams {
   // fused last synthesis layer (conv_gdn_kernel<.., kLast = true>): every output pixel of this layer is multiplied by
   // W6 [96][c_out] (deconv(N, 3, k5 s2) as 75 (+21 zero) per-pixel contributions (r, s, c)), the "col" rows go to HBM
   alignas(64) CUtensorMap w6_map;
+  alignas(64) CUtensorMap w6_half_map;  // duo mode: box {64, 48}
+  int duo;  // conv_gdn_kernel, csize == 2: cta_group::2 MMAs (see ptx.cuh)
   __half* col_out;  // [batch][full_h][full_w][96] fp16
   int store_act;    // 0: the layer's own activation is not written at all
   int kk_main;  // K = 16 slices issued per main-loop k-step (4; 3 in row_taps mode: 5 taps x 8 channels = 40 <= 48)
@@ -155,7 +157,7 @@ __device__ __forceinline__ uint32_t pack_half2(float a, float b) {
 // EPI: 0 = LeakyReLU(acc + bias); 1 = SFT: x * (acc_gamma + b_gamma) + (acc_beta + b_beta) then LeakyReLU, with the
 // accumulator columns laid out per 128-column block as [gamma(64 ch) | beta(64 ch)] and x read from `aux`
 // (stem_utils.py:36-43, the "+1" of (1 + gamma) is folded into b_gamma); 2 = LeakyReLU(acc + bias) + aux (residual).
-template <int BLOCK_N, int EPI>
+template <int BLOCK_N, int EPI, bool kDuo = false>
 __global__ void __launch_bounds__(kNumThreads, 1)
 conv_igemm_kernel(const __grid_constant__ ConvKernelParams p) {
   using Cfg = ConvCfg<BLOCK_N>;
@@ -180,6 +182,8 @@ conv_igemm_kernel(const __grid_constant__ ConvKernelParams p) {
   const int lane = threadIdx.x & 31;
   const bool pair = p.csize == 2;
   const int crank = pair ? static_cast<int>(cluster_ctarank()) : 0;
+  // duo mode (ptx.cuh): one cta_group::2 MMA per k-step for the pair, issued by rank 0; half a B tile per CTA
+  constexpr bool duo = kDuo;
   const int q_first = pair ? static_cast<int>(cluster_id_x()) : static_cast<int>(blockIdx.x);
   const int q_stride = pair ? static_cast<int>(cluster_count_x()) : static_cast<int>(gridDim.x);
   const int n_items = p.total_tiles / p.csize;
@@ -194,17 +198,23 @@ conv_igemm_kernel(const __grid_constant__ ConvKernelParams p) {
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < kStages; ++s) {
       mbar_init(full_bar(s), 1);
-      mbar_init(empty_bar(s), p.csize);  // pair mode: the peer's MMAs must also be done with the slot it multicasts into
+      // pair mode: the peer's MMAs must also be done with the slot it multicasts into; duo: one (multicast) commit
+      mbar_init(empty_bar(s), duo ? 1 : p.csize);
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), 8);  // one arrival per epilogue warp
+      mbar_init(tempty_bar(a), duo ? 16 : 8);  // one arrival per epilogue warp (duo: of both CTAs, at the leader)
     }
     fence_barrier_init();
   }
   if (warp == 2) {
-    tmem_alloc(tmem_slot, Cfg::kTmemCols);
-    tmem_relinquish();
+    if (duo) {
+      tmem_alloc2(tmem_slot, Cfg::kTmemCols);
+      tmem_relinquish2();
+    } else {
+      tmem_alloc(tmem_slot, Cfg::kTmemCols);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -233,7 +243,12 @@ conv_igemm_kernel(const __grid_constant__ ConvKernelParams p) {
         const int c0 = static_cast<int>(e >> 10);
         const uint32_t a_dst = stage_base + s * Cfg::kStageBytes;
         const uint32_t b_dst = a_dst + kAStageBytes;
-        if (leader) {
+        if (leader && duo) {
+          const uint32_t lbar = mapa_shared(full_bar(s), 0);
+          if (crank == 0) mbar_arrive_expect_tx(full_bar(s), 2u * (a_tx_bytes + Cfg::kBStageBytes / 2));
+          tma_load_4d_2sm(a_dst, &p.a_map[map], lbar, c0, t.w0 + dw, t.h0 + dh, t.n_img);
+          tma_load_2d_2sm(b_dst, &p.b_half_map, lbar, k * kKChunk, t.n0 + crank * (BLOCK_N / 2));
+        } else if (leader) {
           mbar_arrive_expect_tx(full_bar(s), a_tx_bytes + Cfg::kBStageBytes);
           tma_load_4d(a_dst, &p.a_map[map], full_bar(s), c0, t.w0 + dw, t.h0 + dh, t.n_img);
           if (pair)
@@ -248,10 +263,11 @@ conv_igemm_kernel(const __grid_constant__ ConvKernelParams p) {
         }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == 1 && (!duo || crank == 0)) {
     // ===================== MMA issuer (whole warp walks the loop, one elected lane issues) =====================
+    // (duo mode: only the cluster's rank 0 issues; its MMAs write the accumulators of both CTAs)
     const bool leader = elect_one();
-    constexpr uint32_t idesc = umma_idesc(/*F16*/ 0u, 128u, BLOCK_N);
+    constexpr uint32_t idesc = umma_idesc(/*F16*/ 0u, duo ? 256u : 128u, BLOCK_N);
     int s = 0;
     uint32_t ph = 0;
     int it = 0;
@@ -260,7 +276,8 @@ conv_igemm_kernel(const __grid_constant__ ConvKernelParams p) {
       const int kbeg = p.sub_kbeg[sub], kend = p.sub_kend[sub];
       const int acc = it & 1;
       const uint32_t accph = (it >> 1) & 1;
-      mbar_wait(tempty_bar(acc), accph ^ 1u);
+      if (duo) mbar_wait_cluster(tempty_bar(acc), accph ^ 1u);
+      else mbar_wait(tempty_bar(acc), accph ^ 1u);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
       for (int k = kbeg; k < kend; ++k) {
@@ -273,9 +290,11 @@ conv_igemm_kernel(const __grid_constant__ ConvKernelParams p) {
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk) {
             // +32 bytes (one K=16 slice) inside the 128-byte swizzle row => +2 in the >>4 address field
-            mma_f16_ss(d_tmem, adesc + 2u * kk, bdesc + 2u * kk, idesc, (k > kbeg || kk > 0) ? 1u : 0u);
+            if (duo) mma_f16_ss2(d_tmem, adesc + 2u * kk, bdesc + 2u * kk, idesc, (k > kbeg || kk > 0) ? 1u : 0u);
+            else mma_f16_ss(d_tmem, adesc + 2u * kk, bdesc + 2u * kk, idesc, (k > kbeg || kk > 0) ? 1u : 0u);
           }
-          if (pair) mma_commit_mc(empty_bar(s), 3);
+          if (duo) mma_commit2_mc(empty_bar(s), 3);
+          else if (pair) mma_commit_mc(empty_bar(s), 3);
           else mma_commit(empty_bar(s));
         }
         if (++s == kStages) {
@@ -283,7 +302,10 @@ conv_igemm_kernel(const __grid_constant__ ConvKernelParams p) {
           ph ^= 1u;
         }
       }
-      if (leader) mma_commit(tfull_bar(acc));
+      if (leader) {
+        if (duo) mma_commit2_mc(tfull_bar(acc), 3);
+        else mma_commit(tfull_bar(acc));
+      }
     }
   } else if (warp >= 4) {
     // ===================== epilogue (TMEM -> registers -> smem -> TMA store) =====================
@@ -521,7 +543,10 @@ conv_igemm_kernel(const __grid_constant__ ConvKernelParams p) {
       // all TMEM reads of this accumulator are complete -> hand it back to the MMA warp
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(tempty_bar(acc));
+      if (lane == 0) {
+        if (duo) mbar_arrive_cluster(mapa_shared(tempty_bar(acc), 0));
+        else mbar_arrive(tempty_bar(acc));
+      }
     }
     if (etid == 0) tma_store_wait_all<0>();
   }
@@ -529,7 +554,10 @@ conv_igemm_kernel(const __grid_constant__ ConvKernelParams p) {
   tc_fence_before();
   __syncthreads();
   if (pair) cluster_sync_all();  // no CTA leaves while its peer may still multicast into it
-  if (warp == 2) tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  if (warp == 2) {
+    if (duo) tmem_dealloc2(tmem_base, Cfg::kTmemCols);
+    else tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
 }
 
 // =====================================================================================================
@@ -576,7 +604,7 @@ constexpr int kGdnEpiWarps = 16;                        // 4 per TMEM lane group
 constexpr int kGdnEpiThreads = kGdnEpiWarps * 32;       // 512
 constexpr int kGdnThreads = 128 + kGdnEpiThreads;       // 4 control warps + 16 epilogue warps
 
-template <int kNT, bool kInverse, bool kLast = false>
+template <int kNT, bool kInverse, bool kLast = false, bool kDuo = false>
 __global__ void __launch_bounds__(kGdnThreads, 1)
 conv_gdn_kernel(const __grid_constant__ ConvKernelParams p) {
   using Cfg = GdnCfgT<kNT, kLast>;
@@ -609,6 +637,10 @@ conv_gdn_kernel(const __grid_constant__ ConvKernelParams p) {
   const int lane = threadIdx.x & 31;
   const bool pair = p.csize == 2;
   const int crank = pair ? static_cast<int>(cluster_ctarank()) : 0;
+  // duo mode: one cta_group::2 MMA (M = 256) per k-step for the pair, issued by rank 0; each CTA stages its own A tile
+  // and half of every B tile. The leader's barriers collect the TMA bytes and the epilogue arrivals of both CTAs.
+  // (a template parameter: a kernel that contains cta_group::2 instructions can only be launched as a cluster)
+  constexpr bool duo = kDuo;
   const int q_first = pair ? static_cast<int>(cluster_id_x()) : static_cast<int>(blockIdx.x);
   const int q_stride = pair ? static_cast<int>(cluster_count_x()) : static_cast<int>(gridDim.x);
   const int n_items = p.total_tiles / p.csize;
@@ -622,23 +654,30 @@ conv_gdn_kernel(const __grid_constant__ ConvKernelParams p) {
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < kStages; ++s) {
       mbar_init(full_bar(s), 1);
-      mbar_init(empty_bar(s), p.csize);  // pair mode: the peer's MMAs must also be done with the slot it multicasts into
+      // pair mode: the peer's MMAs must also be done with the slot it multicasts into; duo: one (multicast) commit
+      mbar_init(empty_bar(s), duo ? 1 : p.csize);
     }
+    const uint32_t epi_arrivals = duo ? 2 * kGdnEpiWarps : kGdnEpiWarps;
     mbar_init(tfull_bar, 1);
-    mbar_init(a2rdy_bar, kGdnEpiWarps);
+    mbar_init(a2rdy_bar, epi_arrivals);
     mbar_init(nfull_bar, 1);
-    mbar_init(accfree_bar(0), kGdnEpiWarps);
-    mbar_init(accfree_bar(1), kGdnEpiWarps);
+    mbar_init(accfree_bar(0), epi_arrivals);
+    mbar_init(accfree_bar(1), epi_arrivals);
     if constexpr (kLast) {
       mbar_init(w6full_bar, 1);
-      mbar_init(a3rdy_bar, kGdnEpiWarps);
+      mbar_init(a3rdy_bar, epi_arrivals);
       mbar_init(d3full_bar, 1);
     }
     fence_barrier_init();
   }
   if (warp == 2) {
-    tmem_alloc(tmem_slot, Cfg::kTmemCols);
-    tmem_relinquish();
+    if (duo) {
+      tmem_alloc2(tmem_slot, Cfg::kTmemCols);
+      tmem_relinquish2();
+    } else {
+      tmem_alloc(tmem_slot, Cfg::kTmemCols);
+      tmem_relinquish();
+    }
   }
   if (warp >= 4) {
     // bias, and the folded normaliser offset: s^2 beta (GDN) or beta / s^2 (IGDN)
@@ -672,7 +711,12 @@ conv_gdn_kernel(const __grid_constant__ ConvKernelParams p) {
       const int dw = static_cast<int>((e >> 6) & 15u) - 8;
       const int c0 = static_cast<int>(e >> 10);
       const uint32_t a_dst = stage_base + s * Cfg::kStageBytes;
-      if (leader) {
+      if (leader && duo) {
+        const uint32_t lbar = mapa_shared(full_bar(s), 0);
+        if (crank == 0) mbar_arrive_expect_tx(full_bar(s), 2u * (a_tx_bytes + Cfg::kBStageBytes / 2));
+        tma_load_4d_2sm(a_dst, &p.a_map[map], lbar, c0, t.w0 + dw, t.h0 + dh, t.n_img);
+        tma_load_2d_2sm(a_dst + kAStageBytes, &p.b_half_map, lbar, k * kKChunk, crank * (BLOCK_N / 2));
+      } else if (leader) {
         mbar_arrive_expect_tx(full_bar(s), a_tx_bytes + Cfg::kBStageBytes);
         tma_load_4d(a_dst, &p.a_map[map], full_bar(s), c0, t.w0 + dw, t.h0 + dh, t.n_img);
         if (pair)
@@ -690,7 +734,11 @@ conv_gdn_kernel(const __grid_constant__ ConvKernelParams p) {
       for (int kc = 0; kc < kGChunks; ++kc) {
         mbar_wait(empty_bar(s), ph ^ 1u);
         const uint32_t a_dst = stage_base + s * Cfg::kStageBytes;
-        if (leader) {
+        if (leader && duo) {
+          const uint32_t lbar = mapa_shared(full_bar(s), 0);
+          if (crank == 0) mbar_arrive_expect_tx(full_bar(s), Cfg::kBStageBytes);
+          tma_load_2d_2sm(a_dst + kAStageBytes, &p.g_half_map, lbar, kc * kKChunk, crank * (BLOCK_N / 2));
+        } else if (leader) {
           mbar_arrive_expect_tx(full_bar(s), Cfg::kBStageBytes);
           if (pair)
             tma_load_2d_mc(a_dst + kAStageBytes + crank * (Cfg::kBStageBytes / 2), &p.g_half_map, full_bar(s),
@@ -705,7 +753,14 @@ conv_gdn_kernel(const __grid_constant__ ConvKernelParams p) {
       }
     };
     if constexpr (kLast) {
-      if (leader) {
+      if (leader && duo) {
+        // each CTA holds 48 of W6's 96 rows (the first 48 row slots of every K chunk)
+        tma_prefetch_desc(&p.w6_half_map);
+        const uint32_t lbar = mapa_shared(w6full_bar, 0);
+        if (crank == 0) mbar_arrive_expect_tx(w6full_bar, Cfg::kW6Bytes);
+        for (int kc = 0; kc < kGChunks; ++kc)
+          tma_load_2d_2sm(w6_base + kc * (kLastN * 128), &p.w6_half_map, lbar, kc * kKChunk, crank * (kLastN / 2));
+      } else if (leader) {
         tma_prefetch_desc(&p.w6_map);
         mbar_arrive_expect_tx(w6full_bar, Cfg::kW6Bytes);
         for (int kc = 0; kc < kGChunks; ++kc)
@@ -722,10 +777,24 @@ conv_gdn_kernel(const __grid_constant__ ConvKernelParams p) {
       for (int k = ksplit; k < kend; ++k) load_main(t, k);
     }
     if (it > 0) load_gamma();
-  } else if (warp == 1) {
+  } else if (warp == 1 && (!duo || crank == 0)) {
     // ===================== MMA issuer (whole warp walks the loop, one elected lane issues) =====================
+    // (duo mode: only the cluster's rank 0 issues; its MMAs write the accumulators of both CTAs)
     const bool leader = elect_one();
-    constexpr uint32_t idesc = umma_idesc(/*F16*/ 0u, 128u, BLOCK_N);
+    const uint32_t idesc = duo ? umma_idesc(/*F16*/ 0u, 256u, BLOCK_N) : umma_idesc(/*F16*/ 0u, 128u, BLOCK_N);
+    auto mma = [&](uint32_t d, uint64_t ad, uint64_t bd, uint32_t id, uint32_t acc) {
+      if (duo) mma_f16_ss2(d, ad, bd, id, acc);
+      else mma_f16_ss(d, ad, bd, id, acc);
+    };
+    auto release_slot = [&](uint32_t bar) {
+      if (duo) mma_commit2_mc(bar, 3);
+      else if (pair) mma_commit_mc(bar, 3);
+      else mma_commit(bar);
+    };
+    auto commit_local = [&](uint32_t bar) {  // accumulator-ready barriers: every CTA's epilogue waits on its own copy
+      if (duo) mma_commit2_mc(bar, 3);
+      else mma_commit(bar);
+    };
     int s = 0;
     uint32_t ph = 0;
     // kLast: col(j) = out(j) . W6^T once phase 2 of tile j has left the layer's output in the x^2 buffers; it can
@@ -735,13 +804,14 @@ conv_gdn_kernel(const __grid_constant__ ConvKernelParams p) {
     auto try_mma3 = [&]() {
       if constexpr (kLast) {
         // one lane's probe decides for the warp (n3_done must stay warp-uniform)
-        if (!__shfl_sync(0xffffffffu, static_cast<int>(mbar_try_wait(a3rdy_bar, n3_done & 1)), 0)) return;
+        const bool rdy = duo ? mbar_try_wait_cluster(a3rdy_bar, n3_done & 1) : mbar_try_wait(a3rdy_bar, n3_done & 1);
+        if (!__shfl_sync(0xffffffffu, static_cast<int>(rdy), 0)) return;
         if (!w6_ready) {
           mbar_wait(w6full_bar, 0);
           w6_ready = true;
         }
         tc_fence_after();
-        constexpr uint32_t idesc3 = umma_idesc(/*F16*/ 0u, 128u, kLastN);
+        const uint32_t idesc3 = duo ? umma_idesc(/*F16*/ 0u, 256u, kLastN) : umma_idesc(/*F16*/ 0u, 128u, kLastN);
         if (leader) {
 #pragma unroll
           for (int kc = 0; kc < kGChunks; ++kc) {
@@ -749,19 +819,21 @@ conv_gdn_kernel(const __grid_constant__ ConvKernelParams p) {
             const uint64_t bdesc = umma_desc_sw128(w6_base + kc * (kLastN * 128));
 #pragma unroll
             for (int kk = 0; kk < 4; ++kk)
-              mma_f16_ss(tmem_base + Cfg::kStashCol, adesc + 2u * kk, bdesc + 2u * kk, idesc3,
-                         (kc > 0 || kk > 0) ? 1u : 0u);
+              mma(tmem_base + Cfg::kStashCol, adesc + 2u * kk, bdesc + 2u * kk, idesc3, (kc > 0 || kk > 0) ? 1u : 0u);
           }
-          mma_commit(d3full_bar);
+          commit_local(d3full_bar);
         }
         ++n3_done;
       }
     };
     auto wait_bar = [&](uint32_t bar, uint32_t parity) {
       if constexpr (kLast) {
-        while (!__shfl_sync(0xffffffffu, static_cast<int>(mbar_try_wait(bar, parity)), 0)) try_mma3();
+        while (!__shfl_sync(0xffffffffu,
+                            static_cast<int>(duo ? mbar_try_wait_cluster(bar, parity) : mbar_try_wait(bar, parity)), 0))
+          try_mma3();
       } else {
-        mbar_wait(bar, parity);
+        if (duo) mbar_wait_cluster(bar, parity);
+        else mbar_wait(bar, parity);
       }
     };
     auto mma_main = [&](uint32_t d_tmem, bool first) {
@@ -773,9 +845,8 @@ conv_gdn_kernel(const __grid_constant__ ConvKernelParams p) {
       if (leader) {
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk)
-          if (kk < p.kk_main) mma_f16_ss(d_tmem, adesc + 2u * kk, bdesc + 2u * kk, idesc, (!first || kk > 0) ? 1u : 0u);
-        if (pair) mma_commit_mc(empty_bar(s), 3);
-        else mma_commit(empty_bar(s));
+          if (kk < p.kk_main) mma(d_tmem, adesc + 2u * kk, bdesc + 2u * kk, idesc, (!first || kk > 0) ? 1u : 0u);
+        release_slot(empty_bar(s));
       }
       if (++s == kStages) {
         s = 0;
@@ -796,16 +867,15 @@ conv_gdn_kernel(const __grid_constant__ ConvKernelParams p) {
         if (leader) {
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk)
-            mma_f16_ss(d_tmem, adesc + 2u * kk, bdesc + 2u * kk, idesc, (kc > 0 || kk > 0) ? 1u : 0u);
-          if (pair) mma_commit_mc(empty_bar(s), 3);
-          else mma_commit(empty_bar(s));
+            mma(d_tmem, adesc + 2u * kk, bdesc + 2u * kk, idesc, (kc > 0 || kk > 0) ? 1u : 0u);
+          release_slot(empty_bar(s));
         }
         if (++s == kStages) {
           s = 0;
           ph ^= 1u;
         }
       }
-      if (leader) mma_commit(nfull_bar);
+      if (leader) commit_local(nfull_bar);
     };
     int it = 0;
     for (int tile = q_first; tile < n_items; tile += q_stride, ++it) {
@@ -820,7 +890,7 @@ conv_gdn_kernel(const __grid_constant__ ConvKernelParams p) {
       for (int k = kbeg; k < ksplit; ++k) mma_main(d_tmem, k == kbeg);
       if (it > 0) mma_gamma(it - 1);
       for (int k = ksplit; k < kend; ++k) mma_main(d_tmem, k == kbeg);
-      if (leader) mma_commit(tfull_bar);
+      if (leader) commit_local(tfull_bar);
     }
     if (it > 0) mma_gamma(it - 1);
     if constexpr (kLast) {
@@ -841,6 +911,11 @@ conv_gdn_kernel(const __grid_constant__ ConvKernelParams p) {
     const uint32_t p0 = ((2u * q) ^ rsw) << 4, p1 = ((2u * q + 1u) ^ rsw) << 4;  // swizzled 16-byte pieces
     const float sc = p.sq_scale;  // power of two: fma(acc, s, b s) rounds exactly like (acc + b) s
     const float ka = kInverse ? p.sq_inv * p.sq_inv : 1.0f;
+    // duo mode: "operand ready" / "accumulator free" arrivals of both CTAs go to the leader's barriers
+    auto arrive_mma = [&](uint32_t bar) {
+      if (duo) mbar_arrive_cluster(mapa_shared(bar, 0));
+      else mbar_arrive(bar);
+    };
     int it = 0;
     for (int tile = q_first; tile < n_items; tile += q_stride, ++it) {
       const TileCoord t = decode_tile(p, tile, crank, BLOCK_N);
@@ -898,7 +973,7 @@ conv_gdn_kernel(const __grid_constant__ ConvKernelParams p) {
       fence_proxy_async_smem();  // (x s)^2 is read by the tensor core through the async proxy
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(a2rdy_bar);
+      if (lane == 0) arrive_mma(a2rdy_bar);
 
       // ---- phase 2: out = (x s) * (r)sqrt(.) into the (now free) x^2 buffers, one TMA store per 64 channels
       mbar_wait(nfull_bar, par);
@@ -918,7 +993,7 @@ conv_gdn_kernel(const __grid_constant__ ConvKernelParams p) {
             // every TMEM read of this tile has completed: hand the accumulator back to the MMA thread
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(accfree_bar(it & 1));
+            if (lane == 0) arrive_mma(accfree_bar(it & 1));
           }
           uint32_t ho[8];
 #pragma unroll
@@ -966,7 +1041,7 @@ conv_gdn_kernel(const __grid_constant__ ConvKernelParams p) {
         // the (dead) stash columns; this thread's 24 of the 96 columns go to the col buffer as fp16
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(a3rdy_bar);
+        if (lane == 0) arrive_mma(a3rdy_bar);
         mbar_wait(d3full_bar, par);
         tc_fence_after();
         uint32_t d[24];
@@ -1006,7 +1081,10 @@ conv_gdn_kernel(const __grid_constant__ ConvKernelParams p) {
   tc_fence_before();
   __syncthreads();
   if (pair) cluster_sync_all();  // no CTA leaves while its peer may still multicast into it
-  if (warp == 2) tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  if (warp == 2) {
+    if (duo) tmem_dealloc2(tmem_base, Cfg::kTmemCols);
+    else tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
 }
 
 // =====================================================================================================
@@ -1698,6 +1776,17 @@ int encode_nhwc_plain(CUtensorMap* m, const void* base, int n, int h, int w, int
 }
 
 namespace {
+// STEMB200_DUO=0 in the environment turns duo mode (cta_group::2 MMAs) off: the clusters then run in pair mode
+// (weight tiles multicast, one cta_group::1 MMA per CTA) - for A/B measurements
+bool duo_mode_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("STEMB200_DUO");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v != 0;
+}
+
 // STEMB200_PAIR=0 in the environment disables pair mode (A/B measurements)
 bool pair_mode_enabled() {
   static int v = -1;
@@ -1738,9 +1827,26 @@ int launch_pairs(Kern kernel, const ConvKernelParams& kp, int threads, size_t sm
   return 0;
 }
 
+template <int BLOCK_N, int EPI>
+int launch_conv_duo(const ConvKernelParams& kp, cudaStream_t stream) {
+  using Cfg = ConvCfg<BLOCK_N>;
+  static bool configured = false;  // benign race: attribute set is idempotent
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(conv_igemm_kernel<BLOCK_N, EPI, true>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+    if (e != cudaSuccess) return set_cuda_error("cudaFuncSetAttribute(conv duo)", e);
+    configured = true;
+  }
+  static int clusters = 0;
+  return launch_pairs(conv_igemm_kernel<BLOCK_N, EPI, true>, kp, kNumThreads, Cfg::kSmemBytes, stream, clusters);
+}
+
 template <int BLOCK_N, int EPI = 0>
 int launch_conv(const ConvKernelParams& kp, int grid, cudaStream_t stream) {
   using Cfg = ConvCfg<BLOCK_N>;
+  if constexpr (BLOCK_N >= 64) {
+    if (kp.csize == 2 && kp.duo) return launch_conv_duo<BLOCK_N, EPI>(kp, stream);
+  }
   static bool configured = false;  // benign race: attribute set is idempotent
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(conv_igemm_kernel<BLOCK_N, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -1862,7 +1968,9 @@ int setup_params(const stemb200_conv_desc* d, const Plan& pl, const void* const*
   kp.csize = 1;
   const long long tiles_per_sub = static_cast<long long>(d->batch) * kp.tiles_h * kp.tiles_w;
   // (measured +2 % on the MMA-bound 5x5 layers, -2 % on the 160-wide tiles and the epilogue-bound first layer)
-  if (pair_mode_enabled() && pl.block_n >= 64 && pl.block_n != 160 && !pl.row_taps && (tiles_per_sub % 2) == 0 &&
+  // (the 160-wide tiles lose 2 % in pair mode but gain in duo mode, where each CTA stages 80 of the 160 weight rows)
+  if (pair_mode_enabled() && pl.block_n >= 64 && (pl.block_n != 160 || duo_mode_enabled()) && !pl.row_taps &&
+      (tiles_per_sub % 2) == 0 &&
       total >= 2LL * num_sms()) {
     kp.csize = 2;
     if (int rc = encode_weight(&kp.b_half_map, packed_weight, K, d->c_out, pl.block_n / 2)) return rc;
@@ -1897,6 +2005,7 @@ extern "C" int stemb200_conv2d_fwd(const stemb200_conv_desc* d, const void* cons
     if (!in[s]) return set_error("conv2d_fwd: null input");
   ConvKernelParams kp;
   if (int rc = setup_params(d, pl, in, packed_weight, bias, aux, out, kp)) return rc;
+  kp.duo = (kp.csize == 2 && duo_mode_enabled()) ? 1 : 0;
   const int grid = std::min(kp.total_tiles, num_sms());
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (d->epilogue == STEMB200_EPI_SFT) {
@@ -1924,25 +2033,30 @@ extern "C" int stemb200_conv2d_fwd(const stemb200_conv_desc* d, const void* cons
 }
 
 namespace {
-template <int kNT, bool kInverse, bool kLast = false>
+template <int kNT, bool kInverse, bool kLast = false, bool kDuo = false>
 int launch_gdn(const ConvKernelParams& kp, int grid, cudaStream_t stream) {
   using Cfg = GdnCfgT<kNT, kLast>;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(conv_gdn_kernel<kNT, kInverse, kLast>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         Cfg::kSmemBytes);
+    cudaError_t e = cudaFuncSetAttribute(conv_gdn_kernel<kNT, kInverse, kLast, kDuo>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
     if (e != cudaSuccess) return set_cuda_error("cudaFuncSetAttribute(conv_gdn)", e);
     configured = true;
   }
   if (kp.csize == 2) {
     static int clusters = 0;
-    return launch_pairs(conv_gdn_kernel<kNT, kInverse, kLast>, kp, kGdnThreads, Cfg::kSmemBytes, stream, clusters);
+    return launch_pairs(conv_gdn_kernel<kNT, kInverse, kLast, kDuo>, kp, kGdnThreads, Cfg::kSmemBytes, stream,
+                        clusters);
   }
-  conv_gdn_kernel<kNT, kInverse, kLast><<<grid, kGdnThreads, Cfg::kSmemBytes, stream>>>(kp);
-  count_launch();
-  cudaError_t e = cudaGetLastError();
-  if (e != cudaSuccess) return set_cuda_error("conv_gdn launch", e);
-  return 0;
+  if constexpr (kDuo) {
+    return set_error("conv_gdn: duo mode needs a cluster launch");
+  } else {
+    conv_gdn_kernel<kNT, kInverse, kLast><<<grid, kGdnThreads, Cfg::kSmemBytes, stream>>>(kp);
+    count_launch();
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return set_cuda_error("conv_gdn launch", e);
+    return 0;
+  }
 }
 }  // namespace
 
@@ -2005,17 +2119,28 @@ int gdn_forward(const stemb200_conv_desc* d, const void* const* in, const void* 
   kp.igdn = inverse ? 1 : 0;
   const int grid = std::min(kp.total_tiles, num_sms());
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (last) {
-    if (int rc = encode_weight(&kp.w6_map, packed_w6, d->c_out, kLastN, kLastN)) return rc;
-    kp.col_out = static_cast<__half*>(col_out);
-    kp.store_act = out ? 1 : 0;
-    return launch_gdn<192, true, true>(kp, grid, st);
-  }
   // short main loops are epilogue-bound: ping-pong variant (GDN only: the transposed layers have long enough loops)
   int max_k = 0;
   for (int i = 0; i < pl.n_sub; ++i) max_k = std::max(max_k, pl.sub_kend[i] - pl.sub_kbeg[i]);
-  if (pp_mode_enabled() && !inverse && max_k <= 8)
+  const bool use_pp = !last && pp_mode_enabled() && !inverse && max_k <= 8;
+  // (the fused-last variant stays in pair mode: its epilogue chain has three hand-offs to the MMA warp per tile, and
+  // routing them through the leader CTA costs more than the halved B reads give back: measured 2.9 -> 3.3 ms)
+  kp.duo = (kp.csize == 2 && !use_pp && !last && duo_mode_enabled()) ? 1 : 0;
+  if (last) {
+    if (kp.duo)
+      if (int rc = encode_weight(&kp.w6_half_map, packed_w6, d->c_out, kLastN, kLastN / 2)) return rc;
+    if (int rc = encode_weight(&kp.w6_map, packed_w6, d->c_out, kLastN, kLastN)) return rc;
+    kp.col_out = static_cast<__half*>(col_out);
+    kp.store_act = out ? 1 : 0;
+    return kp.duo ? launch_gdn<192, true, true, true>(kp, grid, st) : launch_gdn<192, true, true>(kp, grid, st);
+  }
+  if (use_pp)
     return d->c_out == 192 ? launch_gdn_pp<192, false>(kp, grid, st) : launch_gdn_pp<128, false>(kp, grid, st);
+  if (kp.duo) {
+    if (d->c_out == 192)
+      return inverse ? launch_gdn<192, true, false, true>(kp, grid, st) : launch_gdn<192, false, false, true>(kp, grid, st);
+    return inverse ? launch_gdn<128, true, false, true>(kp, grid, st) : launch_gdn<128, false, false, true>(kp, grid, st);
+  }
   if (d->c_out == 192) return inverse ? launch_gdn<192, true>(kp, grid, st) : launch_gdn<192, false>(kp, grid, st);
   return inverse ? launch_gdn<128, true>(kp, grid, st) : launch_gdn<128, false>(kp, grid, st);
 }

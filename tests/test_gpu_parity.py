@@ -311,16 +311,20 @@ def test_pframe_pipeline_bpp_psnr(dev, variant):
 
 
 @pytest.mark.gpu
-def test_fused_last_synthesis_layer_matches_standalone_and_oracle():
+@pytest.mark.parametrize("geom", [(2, 6, 10, 90, 150, (5, 5, 3, 3)), (1, 34, 60, 540, 950, (5, 5, 2, 2))],
+                         ids=["ragged_small", "pairs"])
+def test_fused_last_synthesis_layer_matches_standalone_and_oracle(geom):
     """g_s.4 + IGDN with the final deconv(N, 3) fused behind it (stemb200_conv2d_gdn_last_fwd + col2im) against the
-    stand-alone merged-phase conv path and against the oracle's g_s (priors.py:431-439), ragged frame incl. MSE."""
+    stand-alone merged-phase conv path and against the oracle's g_s (priors.py:431-439), ragged frame incl. MSE; the
+    second size has enough tiles for 2-CTA clusters and many col2im tiles per CTA."""
     import os
     from spatiotemporalentropymodel_b200.engine import TransformsEngine, nchw_to_nhwc_f16
+    B, h, w, Hr, Wr, pad = geom
     dev = torch.device("cuda:0")
     sd = S.make_iframe_state_dict(0)
-    y_hat = torch.round(S.make_latent(2, 192, 6, 10, seed=8))
-    x_ref = S.make_frames(2, 90, 150, seed=3)                     # un-padded frame inside the 96 x 160 canvas
-    pad = (5, 5, 3, 3)
+    y_hat = torch.round(S.make_latent(B, 192, h, w, seed=8))
+    x_ref = S.make_frames(B, Hr, Wr, seed=3)                     # un-padded frame inside the 16h x 16w canvas
+    assert Hr + pad[2] + pad[3] == 16 * h and Wr + pad[0] + pad[1] == 16 * w
     outs = {}
     for fuse in ("1", "0"):
         os.environ["STEMB200_FUSE_LAST"] = fuse
@@ -329,14 +333,15 @@ def test_fused_last_synthesis_layer_matches_standalone_and_oracle():
         finally:
             os.environ.pop("STEMB200_FUSE_LAST", None)
         assert eng.fuse_last == (fuse == "1")
-        y16 = nchw_to_nhwc_f16(y_hat.to(dev), torch.empty((2, 6, 10, 192), dtype=torch.float16, device=dev))
-        sq = torch.zeros(2, dtype=torch.float64, device=dev)
-        x = eng.synthesis(y16, x_ref=x_ref.to(dev), pad=pad, sq_err=sq, out=torch.empty((2, 3, 96, 160), device=dev))
+        y16 = nchw_to_nhwc_f16(y_hat.to(dev), torch.empty((B, h, w, 192), dtype=torch.float16, device=dev))
+        sq = torch.zeros(B, dtype=torch.float64, device=dev)
+        x = eng.synthesis(y16, x_ref=x_ref.to(dev), pad=pad, sq_err=sq,
+                          out=torch.empty((B, 3, 16 * h, 16 * w), device=dev))
         outs[fuse] = (x.cpu(), sq.cpu())
     ref = O.g_s(y_hat, sd, clamp=True)
     for fuse, (x, sq) in outs.items():
         assert float((x - ref).abs().max()) < 4e-3, fuse
-        crop = x[:, :, 3:93, 5:155]
+        crop = x[:, :, pad[2]:pad[2] + Hr, pad[0]:pad[0] + Wr]
         want = ((x_ref - crop).double() ** 2).sum(dim=(1, 2, 3))
         assert torch.allclose(sq, want, rtol=1e-5), fuse
     assert float((outs["1"][0] - outs["0"][0]).abs().max()) < 2e-3

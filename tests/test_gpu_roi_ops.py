@@ -175,3 +175,44 @@ def test_avgpool_and_im2col_k3(dev):
     out = op([rows], B, h, w, torch.empty((B, h, w, 192), dtype=torch.float16, device=dev))
     ref = F.leaky_relu(F.conv2d(torch.cat([img, q], 1).half().float(), wt, b, padding=1), 0.1)
     assert rel_rms(to_nchw(out), ref) < 1.5e-3
+
+
+# ------------------------------------------------------------------------------------------------------
+# the same epilogues at sizes with >= 2 x 148 tiles: 2-CTA clusters (cta_group::2 MMAs, half a weight tile per CTA),
+# every CTA pair walks several tiles (accumulator double buffering and the cross-CTA barriers wrap around)
+# ------------------------------------------------------------------------------------------------------
+def test_sft_epilogue_cluster_size(dev):
+    from spatiotemporalentropymodel_b200.engine import sft_op
+    g = torch.Generator().manual_seed(31)
+    B, C, h, w, nh = 1, 128, 160, 256, 128
+    x, a = rnd(g, (B, C, h, w)), rnd(g, (B, nh, h, w))
+    wg, wb = rnd(g, (C, nh, 3, 3), 1 / math.sqrt(nh * 9)), rnd(g, (C, nh, 3, 3), 1 / math.sqrt(nh * 9))
+    bg, bb = 0.1 * torch.randn(C, generator=g), 0.1 * torch.randn(C, generator=g)
+    ref = F.leaky_relu(x * (1 + F.conv2d(a, wg, bg, padding=1)) + F.conv2d(a, wb, bb, padding=1), 0.2)
+    op = sft_op(wg.to(dev), bg.to(dev), wb.to(dev), bb.to(dev), c_in=nh, slope=0.2)
+    out = op([to_nhwc16(a, dev)], B, h, w, torch.full((B, h, w, C), float("nan"), dtype=torch.float16, device=dev),
+             aux=to_nhwc16(x, dev))
+    got = to_nchw(out)
+    assert torch.isfinite(got).all() and rel_rms(got, ref) < 1.5e-3
+
+
+@pytest.mark.parametrize("c_out", [192, 160])
+def test_residual_and_odd_widths_cluster_size(dev, c_out):
+    """residual epilogue (C_out = 192) and the 160-wide tile (80 weight rows per CTA) at cluster size"""
+    from spatiotemporalentropymodel_b200.engine import ConvOp
+    from spatiotemporalentropymodel_b200._lib import EPI_ADD
+    g = torch.Generator().manual_seed(32 + c_out)
+    B, C, h, w = 1, 192, 160, 256
+    x, r = rnd(g, (B, C, h, w)), rnd(g, (B, c_out, h, w))
+    wt, b = rnd(g, (c_out, C, 3, 3), 1 / math.sqrt(C * 9)), 0.1 * torch.randn(c_out, generator=g)
+    out_buf = torch.full((B, h, w, c_out), float("nan"), dtype=torch.float16, device=dev)
+    if c_out == 192:
+        op = ConvOp(wt.to(dev), b.to(dev), c_in=[C], c_out=c_out, k=3, epilogue=EPI_ADD)
+        out = op([to_nhwc16(x, dev)], B, h, w, out_buf, aux=to_nhwc16(r, dev))
+        ref = F.conv2d(x, wt, b, padding=1) + r
+    else:
+        op = ConvOp(wt.to(dev), b.to(dev), c_in=[C], c_out=c_out, k=3, slope=0.1)
+        out = op([to_nhwc16(x, dev)], B, h, w, out_buf)
+        ref = F.leaky_relu(F.conv2d(x, wt, b, padding=1), 0.1)
+    got = to_nchw(out)
+    assert torch.isfinite(got).all() and rel_rms(got, ref) < 1.5e-3
