@@ -591,12 +591,12 @@ def main():
         achieved = dom_gf / dom_ms  # GFLOP/ms == TFLOP/s
         peak = peaks["tf_sustained"]
         # DRAM bytes of the same 6 launches from the committed ncu --set full capture
-        # (profiles/r01_ncu_bench_conv_gdn_v6.txt): 8.30 GB per step (algorithmic fp16 in + out: 8.54 GB)
+        # (profiles/r01_ncu_bench_conv_gdn_v8.txt): 8.30 GB per step (algorithmic fp16 in + out: 8.54 GB)
         roofline = {"bound": "tensor", "kernel": "stem::conv_gdn_kernel (conv/deconv + GDN/IGDN fused; the last launch also carries the final deconv as a GEMM)",
                     "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                     "peak_kind": f"bf16 dense sustained (kernel timed inside a long step), {peaks['source']}",
-                    "traffic": 8.30e9 / 6 if (variant, T, H, W) == WORKLOADS["gop12_full_1080p"][:4] else None,
-                    "traffic_unit": "bytes per launch (dram read+write, ncu, profiles/r01_ncu_bench_conv_gdn_v6.txt)",
+                    "traffic": 8.29e9 / 6 if (variant, T, H, W) == WORKLOADS["gop12_full_1080p"][:4] else None,
+                    "traffic_unit": "bytes per launch (dram read+write, ncu, profiles/r01_ncu_bench_conv_gdn_v8.txt)",
                     "launches_per_step": len(dom), "kernel_ms_per_step": dom_ms,
                     "launch_ms": [round(t, 4) for t, _ in dom],
                     "algorithmic_gflop_per_launch": dom_gf / max(len(dom), 1),

@@ -804,8 +804,8 @@ conv_gdn_kernel(const __grid_constant__ ConvKernelParams p) {
     auto try_mma3 = [&]() {
       if constexpr (kLast) {
         // one lane's probe decides for the warp (n3_done must stay warp-uniform)
-        const bool rdy = duo ? mbar_try_wait_cluster(a3rdy_bar, n3_done & 1) : mbar_try_wait(a3rdy_bar, n3_done & 1);
-        if (!__shfl_sync(0xffffffffu, static_cast<int>(rdy), 0)) return;
+        if (!__shfl_sync(0xffffffffu, static_cast<int>(mbar_try_wait(a3rdy_bar, n3_done & 1)), 0)) return;
+        if (duo) (void)mbar_try_wait_cluster(a3rdy_bar, n3_done & 1);  // one cluster-scope acquire (peer's arrivals)
         if (!w6_ready) {
           mbar_wait(w6full_bar, 0);
           w6_ready = true;
@@ -826,15 +826,15 @@ conv_gdn_kernel(const __grid_constant__ ConvKernelParams p) {
         ++n3_done;
       }
     };
-    auto wait_bar = [&](uint32_t bar, uint32_t parity) {
+    // `remote`: the barrier also collects arrivals of the peer CTA (duo mode). The polls stay CTA-scope; one
+    // cluster-scope acquire follows once the phase has completed (a cluster-scope acquire per poll stalls this warp)
+    auto wait_bar = [&](uint32_t bar, uint32_t parity, bool remote = false) {
       if constexpr (kLast) {
-        while (!__shfl_sync(0xffffffffu,
-                            static_cast<int>(duo ? mbar_try_wait_cluster(bar, parity) : mbar_try_wait(bar, parity)), 0))
-          try_mma3();
+        while (!__shfl_sync(0xffffffffu, static_cast<int>(mbar_try_wait(bar, parity)), 0)) try_mma3();
       } else {
-        if (duo) mbar_wait_cluster(bar, parity);
-        else mbar_wait(bar, parity);
+        mbar_wait(bar, parity);
       }
+      if (duo && remote) (void)mbar_try_wait_cluster(bar, parity);
     };
     auto mma_main = [&](uint32_t d_tmem, bool first) {
       wait_bar(full_bar(s), ph);
@@ -856,7 +856,7 @@ conv_gdn_kernel(const __grid_constant__ ConvKernelParams p) {
     };
     // norm(j) = gamma . (x s)^2 into the accumulator tile j just vacated
     auto mma_gamma = [&](int j) {
-      wait_bar(a2rdy_bar, j & 1);
+      wait_bar(a2rdy_bar, j & 1, true);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + (j & 1) * BLOCK_N;
       for (int kc = 0; kc < kGChunks; ++kc) {
@@ -884,7 +884,7 @@ conv_gdn_kernel(const __grid_constant__ ConvKernelParams p) {
       const int ksplit = kbeg + ((kend - kbeg) >> 1);
       const uint32_t d_tmem = tmem_base + (it & 1) * BLOCK_N;
       if (it >= 2) {  // phase 2 of tile it-2 has finished reading this accumulator
-        wait_bar(accfree_bar(it & 1), ((it >> 1) - 1) & 1);
+        wait_bar(accfree_bar(it & 1), ((it >> 1) - 1) & 1, true);
         tc_fence_after();
       }
       for (int k = kbeg; k < ksplit; ++k) mma_main(d_tmem, k == kbeg);
@@ -2125,7 +2125,8 @@ int gdn_forward(const stemb200_conv_desc* d, const void* const* in, const void* 
   const bool use_pp = !last && pp_mode_enabled() && !inverse && max_k <= 8;
   // (the fused-last variant stays in pair mode: its epilogue chain has three hand-offs to the MMA warp per tile, and
   // routing them through the leader CTA costs more than the halved B reads give back: measured 2.9 -> 3.3 ms)
-  kp.duo = (kp.csize == 2 && !use_pp && !last && duo_mode_enabled()) ? 1 : 0;
+  static const bool duo_last = [] { const char* e = getenv("STEMB200_DUO_LAST"); return e && e[0] == '1'; }();
+  kp.duo = (kp.csize == 2 && !use_pp && (!last || duo_last) && duo_mode_enabled()) ? 1 : 0;
   if (last) {
     if (kp.duo)
       if (int rc = encode_weight(&kp.w6_half_map, packed_w6, d->c_out, kLastN, kLastN / 2)) return rc;
