@@ -11,6 +11,8 @@
 //   (p, q): a stride-1 conv with the taps kh == p+pad (mod 2), written through a strided output tensor map.
 // * torch.cat(..., 1) inputs are K-segments: the K loop walks (tap, source, 64-channel chunk) triples listed
 //   in a table carried in the kernel parameters.
+// * layers with enough tiles run as 2-CTA clusters in duo mode: one tcgen05 cta_group::2 MMA (M = 256) per K slice for
+//   the pair, half a weight tile staged per CTA (ptx.cuh); STEMB200_DUO=0 selects pair mode (multicast weight tiles).
 // * accumulators live in TMEM (double buffered, 2 x BLOCK_N columns), MMAs are issued by one thread,
 //   the epilogue (8 warps) overlaps the next tile's main loop; persistent CTAs, one per SM.
 //
@@ -2124,7 +2126,8 @@ int gdn_forward(const stemb200_conv_desc* d, const void* const* in, const void* 
   for (int i = 0; i < pl.n_sub; ++i) max_k = std::max(max_k, pl.sub_kend[i] - pl.sub_kbeg[i]);
   const bool use_pp = !last && pp_mode_enabled() && !inverse && max_k <= 8;
   // (the fused-last variant stays in pair mode: its epilogue chain has three hand-offs to the MMA warp per tile, and
-  // routing them through the leader CTA costs more than the halved B reads give back: measured 2.9 -> 3.3 ms)
+  // routing them through the leader CTA costs more than the halved B reads give back: measured 2.9 -> 3.3 ms;
+  // STEMB200_DUO_LAST=1 selects duo mode for it anyway, for A/B measurements)
   static const bool duo_last = [] { const char* e = getenv("STEMB200_DUO_LAST"); return e && e[0] == '1'; }();
   kp.duo = (kp.csize == 2 && !use_pp && (!last || duo_last) && duo_mode_enabled()) ? 1 : 0;
   if (last) {
