@@ -1,5 +1,6 @@
 """Entropy-coder row: the C-ABI rANS coder against byte streams produced by the reference's
-own compressai.ans module (CPU), the module-level compress/decompress API and its error conventions (CPU), and the
+own compressai.ans module (CPU; committed fixtures, and live against the module compiled from the reference's sources
+into oracle/_ref/ when present), the module-level compress/decompress API and its error conventions (CPU), and the
 non-autoregressive STEM variants' compress -> decompress round trip on the GPU (-m gpu)."""
 import numpy as np
 import pytest
@@ -28,6 +29,66 @@ def test_rans_stream_is_byte_identical_to_reference(golden):
     kat = rans_encode(torch.tensor([1, -2, 0, 2, 0, 11, -1, 0]), torch.tensor([13, 0, 0, 18, 1, 30, 63, 1]),
                       gc._quantized_cdf, gc._cdf_length, gc._offset)
     assert kat.hex() == "06e0d8ff156e00001152adf4"
+
+
+def _ref_native():
+    """the reference's OWN compiled coder (oracle/Makefile -> oracle/_ref/), when it has been built"""
+    from oracle import ref_native
+    mods = ref_native.load()
+    if mods is None:
+        pytest.skip("oracle/_ref not built (make -C oracle needs /root/reference)")
+    return mods
+
+
+def _random_symbols(seed, n=20000):
+    g = torch.Generator().manual_seed(seed)
+    idx = torch.randint(0, 64, (n,), generator=g, dtype=torch.int32)
+    scale = get_scale_table()[idx.long()]
+    outlier = 1 + 6 * (torch.rand(n, generator=g) < 0.02)          # a few symbols beyond the CDF support: bypass coding
+    sym = torch.round(torch.randn(n, generator=g) * scale * outlier).to(torch.int32)
+    return sym, idx
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_rans_against_the_reference_binary(seed):
+    """C-ABI rANS coder vs compressai.ans compiled from the reference's own sources (rans_interface.cpp:99-275):
+    byte-identical streams, and each side decodes the other's stream."""
+    ans, _ = _ref_native()
+    gc = _gc()
+    sym, idx = _random_symbols(seed)
+    cdf, lens, offs = gc._quantized_cdf.tolist(), gc._cdf_length.tolist(), gc._offset.tolist()
+    ref_stream = ans.RansEncoder().encode_with_indexes(sym.tolist(), idx.tolist(), cdf, lens, offs)
+    ours = rans_encode(sym, idx, gc._quantized_cdf, gc._cdf_length, gc._offset)
+    assert ours == ref_stream
+    assert ans.RansDecoder().decode_with_indexes(ours, idx.tolist(), cdf, lens, offs) == sym.tolist()
+    assert torch.equal(rans_decode(ref_stream, idx, gc._quantized_cdf, gc._cdf_length, gc._offset), sym)
+    # the buffered encoder / streaming decoder pair the autoregressive paths use (rans_interface.cpp:43-48, 79-92):
+    # chunks pushed in coding order and flushed once == one call on the concatenation
+    enc = ans.BufferedRansEncoder()
+    for a in range(0, len(sym), 4096):
+        enc.encode_with_indexes(sym[a:a + 4096].tolist(), idx[a:a + 4096].tolist(), cdf, lens, offs)
+    assert enc.flush() == ours
+    dec = ans.RansDecoder()
+    dec.set_stream(ours)
+    got = []
+    for a in range(0, len(sym), 4096):
+        got += dec.decode_stream(idx[a:a + 4096].tolist(), cdf, lens, offs)
+    assert got == sym.tolist()
+
+
+def test_pmf_to_quantized_cdf_against_the_reference_binary():
+    """stemb200_pmf_to_quantized_cdf_host vs compressai._CXX.pmf_to_quantized_cdf (ops.cpp:24-81) on random pmfs,
+    including near-zero bins that have to steal probability mass."""
+    from spatiotemporalentropymodel_b200.entropy_models import pmf_to_quantized_cdf
+    _, cxx = _ref_native()
+    g = torch.Generator().manual_seed(11)
+    for trial in range(200):
+        n = int(torch.randint(2, 400, (1,), generator=g))
+        pmf = torch.rand(n, generator=g) ** (1 + trial % 7)
+        if trial % 3 == 0:
+            pmf[torch.rand(n, generator=g) < 0.3] *= 1e-9
+        pmf = (pmf / pmf.sum()).float()
+        assert pmf_to_quantized_cdf(pmf, 16).tolist() == cxx.pmf_to_quantized_cdf(pmf.tolist(), 16)
 
 
 def test_rans_edge_cases():
