@@ -1996,12 +1996,41 @@ int setup_params(const stemb200_conv_desc* d, const Plan& pl, const void* const*
 }
 }  // namespace
 
+namespace {
+// Less than one wave of work items (small batches: one 1080p latent is 64 pixel tiles): a 256-wide layer leaves more
+// than half of the SMs idle. Narrower N tiles over the same packed weights ([c_out][K] does not depend on the tiling)
+// create more items; pick the width that minimises rounds x tile width, ties towards the wider tile (fewer re-reads of
+// the A operand). 64-wide tiles are not considered: their k-steps are bound by shared-memory reads, not by the MMA.
+void adapt_block_n(const stemb200_conv_desc& d, Plan& pl) {
+  if (d.epilogue == STEMB200_EPI_SFT || d.direct_store || d.out_dtype != STEMB200_DT_F16) return;
+  if (pl.block_n != 256 && pl.block_n != 192) return;
+  int th = d.tile_h, tw = d.tile_w;
+  if (th <= 0 || tw <= 0) pick_tile(pl.h_out, pl.w_out, th, tw);
+  const long long tiles_m = static_cast<long long>(pl.n_sub) * d.batch * ((pl.h_out + th - 1) / th) *
+                            ((pl.w_out + tw - 1) / tw);
+  const int sms = num_sms();
+  if (tiles_m * (d.c_out / pl.block_n) >= sms) return;
+  int best = pl.block_n;
+  long long best_cost = ((tiles_m * (d.c_out / pl.block_n) + sms - 1) / sms) * pl.block_n;
+  for (int bn : {256, 192, 128}) {
+    if (d.c_out % bn) continue;
+    const long long cost = ((tiles_m * (d.c_out / bn) + sms - 1) / sms) * bn;
+    if (cost < best_cost) {
+      best_cost = cost;
+      best = bn;
+    }
+  }
+  pl.block_n = best;
+}
+}  // namespace
+
 extern "C" int stemb200_conv2d_fwd(const stemb200_conv_desc* d, const void* const* in,
                                    const void* packed_weight, const float* bias, const void* aux, void* out,
                                    void* stream) {
   if (!d || !in || !packed_weight || !bias || !out) return set_error("conv2d_fwd: null argument");
   Plan pl;
   if (int rc = build_plan(*d, pl)) return rc;
+  adapt_block_n(*d, pl);
   if (d->epilogue != STEMB200_EPI_LINEAR && !aux) return set_error("conv2d_fwd: SFT / residual epilogue needs aux");
   for (int s = 0; s < d->n_src; ++s)
     if (!in[s]) return set_error("conv2d_fwd: null input");
