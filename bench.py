@@ -500,31 +500,17 @@ def main():
     value = world * T * args.steps / (ms_total / 1e3)
 
     # ---------------------------------------------------------------- end-to-end: pinned host frames in, stats out
-    copy_stream = torch.cuda.Stream(device=dev)
-    bufs = [torch.empty_like(frames_dev), torch.empty_like(frames_dev)]
+    # the public streaming call: PFramePipeline.run_gop copies the pinned host frames into one of its two device slots
+    # on a copy stream (overlapping the previous call's kernels) and replays the captured graph of that slot
     host_stats = torch.empty((3, T), dtype=torch.float64).pin_memory()
 
     def e2e_loop(n):
-        """double-buffered: the H2D copy of step i+1 overlaps the kernels of step i"""
-        ready = [torch.cuda.Event(), torch.cuda.Event()]
-        done = [torch.cuda.Event(), torch.cuda.Event()]
-        with torch.cuda.stream(copy_stream):
-            bufs[0].copy_(frames_host, non_blocking=True)
-            ready[0].record(copy_stream)
-        for i in range(n):
-            b = i & 1
-            if i + 1 < n:
-                with torch.cuda.stream(copy_stream):
-                    copy_stream.wait_event(done[b ^ 1]) if i >= 1 else None
-                    bufs[b ^ 1].copy_(frames_host, non_blocking=True)
-                    ready[b ^ 1].record(copy_stream)
-            torch.cuda.current_stream().wait_event(ready[b])
-            out = pipe.forward_gop(bufs[b], y_cond0, want_outputs=True)
+        for _ in range(n):
+            out = pipe.run_gop(frames_host, y_cond0, want_outputs=True)
             st = out["stats"]
             if world > 1:
                 reduce_stats(st)
             host_stats.copy_(st, non_blocking=True)
-            done[b].record()
         torch.cuda.synchronize()
 
     e2e_loop(3)

@@ -739,6 +739,60 @@ class PFramePipeline:
     def __init__(self, transforms: TransformsEngine, stem: StemEngine):
         self.tr, self.stem = transforms, stem
         self.ws = Workspace(stem.device)
+        self._graphed: Dict[tuple, dict] = {}
+
+    def run_gop(self, frames: Tensor, y_cond0: Tensor, want_outputs: bool = True):
+        """`forward_gop` for a stream of GOPs of one shape (an evaluation loop): the kernel chain is captured once
+        per shape as a CUDA graph over two static input slots and replayed. `frames` may live on the host (pinned
+        memory makes the copy asynchronous): it is copied into the free slot on a copy stream, so the host-to-device
+        copy of call i+1 overlaps the kernels of call i; device-resident frames are copied on the current stream.
+        Everything is stream-ordered, nothing synchronises the host. The returned tensors are static: `stats`,
+        `y_hat`, `lik_*` belong to the slot and are overwritten by the call after next, `x_hat_padded` is a workspace
+        buffer overwritten by the next call. Results are bit-identical to `forward_gop`."""
+        if y_cond0.device.type != "cuda":
+            raise ValueError("run_gop: y_cond0 must be a CUDA tensor")
+        key = (tuple(frames.shape), tuple(y_cond0.shape), bool(want_outputs))
+        st = self._graphed.get(key)
+        if st is None:
+            st = self._graphed[key] = self._capture(frames, y_cond0, want_outputs)
+        slot = st["slots"][st["next"]]
+        st["next"] ^= 1
+        cur = torch.cuda.current_stream()
+        if frames.is_cuda:
+            slot["frames"].copy_(frames, non_blocking=True)
+        else:
+            cs = st["copy_stream"]
+            cs.wait_event(slot["done"])  # the replay that last read this slot has finished
+            with torch.cuda.stream(cs):
+                slot["frames"].copy_(frames, non_blocking=True)
+                slot["ready"].record(cs)
+            cur.wait_event(slot["ready"])
+        slot["cond"].copy_(y_cond0, non_blocking=True)
+        slot["graph"].replay()
+        slot["done"].record(cur)
+        return slot["outs"]
+
+    def _capture(self, frames: Tensor, y_cond0: Tensor, want_outputs: bool) -> dict:
+        dev = self.stem.device
+        slots = []
+        for _ in range(2):
+            fr = torch.empty(tuple(frames.shape), dtype=torch.float32, device=dev)
+            cd = torch.empty(tuple(y_cond0.shape), dtype=torch.float32, device=dev)
+            fr.copy_(frames)
+            cd.copy_(y_cond0)
+            slots.append({"frames": fr, "cond": cd, "ready": torch.cuda.Event(), "done": torch.cuda.Event()})
+        # one eager pass first: workspaces, function attributes and cluster occupancy queries are set up outside capture
+        self.forward_gop(slots[0]["frames"], slots[0]["cond"], want_outputs)
+        torch.cuda.synchronize()
+        for sl in slots:
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                sl["outs"] = self.forward_gop(sl["frames"], sl["cond"], want_outputs)
+            sl["graph"] = g
+        # the graphs address the workspace buffers of this moment: keep them alive even if a later call with another
+        # shape makes the workspaces re-allocate under the same names
+        keep = [list(w._bufs.values()) for w in (self.ws, self.tr.ws, self.stem.ws)]
+        return {"slots": slots, "next": 0, "copy_stream": torch.cuda.Stream(device=dev), "keep": keep}
 
     def forward_gop(self, frames: Tensor, y_cond0: Tensor, want_outputs: bool = True):
         """frames: (T, 3, H, W) fp32 NCHW CUDA (unpadded); y_cond0: (1, C, h, w) fp32 NCHW (previous decoded

@@ -364,3 +364,31 @@ def test_frame_to_nhwc8_canvas(dev, geom):
     want = torch.zeros_like(canvas)
     want[:, border + top:border + top + h, border + left:border + left + w, :c] = x.permute(0, 2, 3, 1).half()
     assert torch.equal(canvas, want)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("variant", ["SpatioTemporalPriorModel", "SpatioTemporalPriorModelWithoutSPM"])
+def test_run_gop_streams_graph_replays_bit_identical_to_forward_gop(dev, variant):
+    """PFramePipeline.run_gop (captured CUDA graph per input slot, host frames copied on a side stream) against the
+    eager forward_gop on a stream of different GOPs: same statistics and latents, bit for bit, in call order."""
+    from spatiotemporalentropymodel_b200 import models as M
+    net = M.models["mbt2018"](quality=4)
+    net.load_state_dict(S.make_iframe_state_dict(seed=0))
+    stem = getattr(M, variant)()
+    stem.load_state_dict(S.make_stem_state_dict(variant, seed=0))
+    net, stem = net.to(dev).eval(), stem.to(dev).eval()
+    H, W, T = 120, 200, 2
+    gops = [S.make_frames(T, H, W, seed=100 + i).pin_memory() for i in range(5)]
+    conds = [S.make_latent(1, 192, 8, 16, seed=200 + i).to(dev) for i in range(5)]
+    pipe = M.make_pipeline(net, stem)
+    want = []
+    for fr, cd in zip(gops, conds):
+        o = pipe.forward_gop(fr.to(dev), cd)
+        want.append((o["stats"].clone(), o["y_hat"].clone(), o["lik_y"].clone(), o["x_hat_padded"].clone()))
+    for i, (fr, cd) in enumerate(zip(gops, conds)):
+        src = fr if i % 2 == 0 else fr.to(dev)            # host (copy stream) and device-resident inputs
+        o = pipe.run_gop(src, cd)
+        got = (o["stats"].clone(), o["y_hat"].clone(), o["lik_y"].clone(), o["x_hat_padded"].clone())
+        for a, b in zip(got, want[i]):
+            assert torch.equal(a, b), (variant, i)
+    assert len(pipe._graphed) == 1
