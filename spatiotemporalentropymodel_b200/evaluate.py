@@ -103,7 +103,15 @@ def code_gop(net, stem, frames: Tensor, mode: str = "estimate", all_intra: bool 
         return rows
     from .models import make_pipeline
     H, W = frames.size(2), frames.size(3)
-    stats = make_pipeline(net, stem).forward_gop(frames[1:].contiguous(), y_cond, want_outputs=False)["stats"].cpu()
+    # one pipeline per (I-frame model, STEM model) pair: GOPs of a repeating shape replay its captured CUDA graph
+    # (keyed by the engines, which the models rebuild on load_state_dict / .to(); the pipeline keeps them alive)
+    pipes = stem.__dict__.setdefault("_stemb200_pipelines", {})
+    key = (id(net.engine()), id(stem.engine()))
+    if key not in pipes:
+        pipes.clear()
+        pipes[key] = make_pipeline(net, stem)
+    pipe = pipes[key]
+    stats = pipe.run_gop(frames[1:].contiguous(), y_cond, want_outputs=False)["stats"].cpu()
     for t in range(T - 1):
         mse = float(stats[2, t]) / (3 * H * W)
         rows.append((float(stats[0, t] + stats[1, t]) / (H * W), float("inf") if mse == 0 else -10 * math.log10(mse)))
