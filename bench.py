@@ -5,11 +5,18 @@
 
 One "step" = one GOP's worth of P-frames (default 11 = GOP 12 minus the I-frame, BASELINE.json configs[2]) through
 pad -> g_a -> STEM forward + likelihoods -> g_s -> clamp/crop -> bit and squared-error sums.  Prints ONE JSON
-line (rank 0).  `value` has the frames resident in HBM; `e2e` feeds pinned HOST frames through the same public
-call (H2D inside the timed region, per-frame bpp/PSNR sums read back).  Under torchrun every rank processes its
-own GOPs (weak scaling) and the 3 x T statistics are all-reduced over NCCL each step.
+line (rank 0).  Frames are 8-bit images (as the PNG frames of stem/evalSTEM.py:185), evaluated as v / 255 on the
+device - bit-identical to uploading ToTensor's fp32 output.  `value` has the frames resident in HBM; `e2e` feeds
+pinned HOST frames through the public streaming call `PFramePipeline.run_gop` (H2D inside the timed region, per-frame
+bpp/PSNR sums read back every step).  Under torchrun every rank processes its own GOPs (weak scaling); the per-frame
+statistics are accumulated on each rank and all-reduced over NCCL ONCE per run, inside the timed
+region (`--reduce-every-step` restores the lock-step variant).
+
+Extra keys of the line: `parity` (the timed GPU output and a low-rate checkpoint checked against the CPU oracle at
+1080p), `other_workloads` (short runs of the other BASELINE.json configs), `roofline`, `cpu_baseline`, `clocks`.
 """
 import argparse
+import hashlib
 import json
 import os
 import statistics
@@ -37,9 +44,11 @@ WORKLOADS = {
                        "SURVEY §8f-2: SpatioTemporalPriorModel.compress + decompress (autoregressive y coding) of one "
                        "1080p P-frame latent (192 x 68 x 120)"),
 }
+OTHER_WORKLOADS = ("nospm_1frame_1080p", "gop12_res_1080p", "stem_roi_4k")
 
 METRIC = "1080p P-frames/sec (STEM fwd+likelihoods)"
 UNIT = "frames/s"
+DTYPE = "f16 operands / f32 accumulate (tcgen05 kind::f16); entropy kernels f32"
 
 
 def algorithmic_gflop_per_frame(variant: str, H: int, W: int) -> float:
@@ -146,21 +155,76 @@ def load_peaks():
     return {"hbm_gbs": 6650.0, "tf_burst": 1590.0, "tf_sustained": 1400.0, "source": "B200_PROFILING.md fallback"}
 
 
-def cpu_reference_fps(variant, H, W, n_frames, threads=None):
-    """The reference's CPU path (oracle port = same torch CPU ops as the reference classes) on n_frames frames."""
-    from oracle import stem_oracle as O
+def measured_traffic():
+    """DRAM bytes per launch of the dominant kernel from the committed ncu capture, valid only for the kernel source it
+    was taken from (profiles/traffic.json is keyed on the sha256 of csrc/conv_igemm.cu); None when stale."""
+    p = os.path.join(REPO, "profiles", "traffic.json")
+    src = os.path.join(REPO, "spatiotemporalentropymodel_b200", "csrc", "conv_igemm.cu")
+    try:
+        rec = json.load(open(p))
+        sha = hashlib.sha256(open(src, "rb").read()).hexdigest()
+    except (OSError, ValueError):
+        return None, "no committed ncu capture"
+    if rec.get("conv_igemm_cu_sha256") != sha:
+        return None, f"stale: {rec.get('source')} was captured on another build of conv_igemm.cu"
+    return rec.get("dram_bytes_per_launch"), rec.get("source")
+
+
+# ----------------------------------------------------------------------------------------------------------
+# inputs
+# ----------------------------------------------------------------------------------------------------------
+def quantize_frames(frames: torch.Tensor) -> torch.Tensor:
+    """fp32 [0, 1] -> 8-bit samples, as a PNG would hold them."""
+    return torch.round(frames * 255.0).clamp_(0, 255).to(torch.uint8)
+
+
+def to_float(frames8: torch.Tensor) -> torch.Tensor:
+    """torchvision ToTensor on 8-bit frames (evalSTEM.py:185)."""
+    return frames8.to(torch.float32).div(255.0)
+
+
+def make_models(variant, calibration, dev):
+    from spatiotemporalentropymodel_b200 import models as M, synthetic as S
+    sd_i = S.make_iframe_state_dict(0, calibration=calibration)
+    sd_s = S.make_stem_state_dict(variant, 0, calibration=calibration)
+    net = M.models["mbt2018"](quality=4)
+    net.load_state_dict(sd_i)
+    stem = getattr(M, variant)()
+    stem.load_state_dict(sd_s)
+    stem.update(force=True)
+    net, stem = net.to(dev).eval(), stem.to(dev).eval()
+    return net, stem, M.make_pipeline(net, stem), sd_i, sd_s
+
+
+def make_inputs(T, H, W, seed, calibration, net=None, dev=None):
+    """-> (frames8 (T, 3, H, W) uint8 on the host, y_cond0 (1, 192, h, w) fp32 on the host).  default calibration: an
+    integer random latent stands for the I-frame codec's output; lowrate: the checkpoint is an auto-encoder whose
+    means follow the previous latent, so y_cond0 = round(g_a(previous frame)) computed by the CUDA g_a."""
     from spatiotemporalentropymodel_b200 import synthetic as S
+    from spatiotemporalentropymodel_b200.evaluate import pad_to_64
+    hp, wp = (H + 63) // 64 * 64 // 16, (W + 63) // 64 * 64 // 16
+    if calibration == "default":
+        return quantize_frames(S.make_frames(T, H, W, seed=seed)), S.make_latent(1, 192, hp, wp, seed=seed - 1229)
+    lo, hi = S.LOWRATE_FRAME_RANGE
+    fr8 = quantize_frames(S.make_frames(T + 1, H, W, seed=seed, lo=lo, hi=hi))
+    xp, _ = pad_to_64(to_float(fr8[0:1]).to(dev))
+    y0, _ = net.getY(xp)
+    return fr8[1:].contiguous(), torch.round(y0).cpu()
+
+
+# ----------------------------------------------------------------------------------------------------------
+# reference arm / CPU baseline
+# ----------------------------------------------------------------------------------------------------------
+def cpu_reference_gop(variant, frames, y_cond0, sd_i, sd_s, threads=None):
+    """The reference's CPU path (oracle port = same torch CPU ops as the reference classes) on the given frames.
+    Returns (per-frame oracle outputs, seconds, threads)."""
+    from oracle import stem_oracle as O
     threads = threads or os.cpu_count() or 1
     torch.set_num_threads(threads)
-    sd_i, sd_s = S.make_iframe_state_dict(0), S.make_stem_state_dict(variant, 0)
-    frames = S.make_frames(n_frames, H, W, seed=1234)
-    hp, wp = (H + 63) // 64 * 64 // 16, (W + 63) // 64 * 64 // 16
-    y_cond = S.make_latent(1, 192, hp, wp, seed=5)
     t0 = time.perf_counter()
     with torch.no_grad():
-        O.gop_forward(frames, y_cond, sd_i, sd_s, variant)
-    dt = time.perf_counter() - t0
-    return n_frames / dt, dt, torch.get_num_threads()
+        ref = O.gop_forward(frames, y_cond0, sd_i, sd_s, variant, return_params=True)
+    return ref, time.perf_counter() - t0, torch.get_num_threads()
 
 
 def run_reference(args):
@@ -169,14 +233,16 @@ def run_reference(args):
     if rank != 0:
         return
     variant, T, H, W, desc = WORKLOADS[args.workload]
+    if variant in ("stem_roi", "ar_codec"):
+        variant, T, H, W, desc = WORKLOADS["gop12_full_1080p"]
+        args.workload = "gop12_full_1080p"
     from oracle import stem_oracle as O
     from spatiotemporalentropymodel_b200 import synthetic as S
     threads = os.cpu_count() or 1
     torch.set_num_threads(threads)
     sd_i, sd_s = S.make_iframe_state_dict(0), S.make_stem_state_dict(variant, 0)
-    frames = S.make_frames(2, H, W, seed=1234)
-    hp, wp = (H + 63) // 64 * 64 // 16, (W + 63) // 64 * 64 // 16
-    y_cond = S.make_latent(1, 192, hp, wp, seed=5)
+    frames8, y_cond = make_inputs(2, H, W, 1234, "default")
+    frames = to_float(frames8)
     times = []
     with torch.no_grad():
         for i in range(args.warmup + args.steps):
@@ -200,23 +266,265 @@ def run_reference(args):
     print(json.dumps(line))
 
 
-def run_stem_roi(args):
+# ----------------------------------------------------------------------------------------------------------
+# P-frame workloads
+# ----------------------------------------------------------------------------------------------------------
+class Ctx:
+    def __init__(self):
+        import torch.distributed as dist
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        torch.cuda.set_device(self.local_rank)
+        self.dev = torch.device("cuda", self.local_rank)
+        self.dist = dist
+        if self.world > 1:
+            init_dist(self.dev)
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+
+    def max_ms(self, ms: float) -> float:
+        t = torch.tensor([ms], dtype=torch.float64, device=self.dev)
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+
+def time_pframes(ctx, pipe, frames8_host, y_cond0, steps, warmup, graph=True, reduce_every_step=False,
+                 sample_clocks=False):
+    """Device-resident and end-to-end timing of one P-frame workload on this rank; times are max over ranks."""
+    from spatiotemporalentropymodel_b200 import _lib
+    from spatiotemporalentropymodel_b200.dist import reduce_stats
+    dev, world = ctx.dev, ctx.world
+    T = frames8_host.shape[0]
+    frames_dev = frames8_host.to(dev)
+    y_cond0 = y_cond0.to(dev)
+
+    def step_resident():
+        return pipe.forward_gop(frames_dev, y_cond0, want_outputs=True)
+
+    for _ in range(warmup):
+        out = step_resident()
+    torch.cuda.synchronize()
+    g = None
+    if graph:
+        try:
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                g_out = step_resident()
+            g.replay()
+            torch.cuda.synchronize()
+        except Exception as e:  # graph capture is an optimisation, not a requirement
+            if ctx.rank == 0:
+                print(f"[bench] CUDA graph capture failed ({type(e).__name__}: {e}); timing eager launches",
+                      file=sys.stderr)
+            g = None
+            torch.cuda.synchronize()
+
+    def run_step():
+        if g is not None:
+            g.replay()
+            return g_out
+        return step_resident()
+
+    for _ in range(2):
+        out = run_step()
+    torch.cuda.synchronize()
+    acc = torch.zeros((3, T), dtype=torch.float64, device=dev)
+    sampler = ClockSampler(ctx.local_rank) if (sample_clocks and ctx.rank == 0) else None
+    ctx.barrier()
+    torch.cuda.synchronize()
+    if sampler:
+        sampler.start()
+    n0 = _lib.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(steps):
+        out = run_step()
+        acc += out["stats"]          # per-rank accumulation; one all-reduce per run (SURVEY.md §5.8)
+        if reduce_every_step and world > 1:
+            reduce_stats(out["stats"])
+    if world > 1 and not reduce_every_step:
+        reduce_stats(acc)
+    ev1.record()
+    torch.cuda.synchronize()
+    ctx.barrier()
+    ms_total = ctx.max_ms(ev0.elapsed_time(ev1))
+    clocks = sampler.stop() if sampler else None
+    launches = _lib.launch_count() - n0
+    if g is not None:
+        # a replayed graph re-issues the kernels captured once: count them from an eager step
+        n1 = _lib.launch_count()
+        step_resident()
+        torch.cuda.synchronize()
+        launches = (_lib.launch_count() - n1) * steps
+
+    # end to end: pinned host frames (8-bit) in through the public streaming call, per-frame statistics out every step
+    frames_pin = frames8_host.pin_memory()
+    host_stats = torch.empty((3, T), dtype=torch.float64).pin_memory()
+    acc.zero_()
+
+    def e2e_loop(n):
+        for _ in range(n):
+            o = pipe.run_gop(frames_pin, y_cond0, want_outputs=True)
+            st = o["stats"]
+            acc.add_(st)
+            if reduce_every_step and world > 1:
+                reduce_stats(st)
+            host_stats.copy_(st, non_blocking=True)
+        if world > 1 and not reduce_every_step:
+            reduce_stats(acc)
+        torch.cuda.synchronize()
+
+    e2e_loop(3)
+    ctx.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    e2e_loop(steps)
+    e1.record()
+    torch.cuda.synchronize()
+    e2e_ms = ctx.max_ms(max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3))
+    return {"ms_per_step": ms_total / steps, "e2e_ms_per_step": e2e_ms / steps, "launches": launches, "clocks": clocks,
+            "cuda_graph": g is not None, "h2d_bytes_per_step": frames8_host.numel() * frames8_host.element_size(),
+            "d2h_bytes_per_step": host_stats.numel() * 8, "step_resident": step_resident, "last_out": out}
+
+
+def parity_report(pipe, variant, frames8_host, y_cond0_host, sd_i, sd_s, out, n_frames, H, W):
+    """Compare the first n_frames of a GPU GOP output with the CPU oracle on the same frames (oracle/parity.py)."""
+    from oracle import parity as P
+    serial = "WithoutSPM" in variant
+    n = min(n_frames, frames8_host.shape[0])
+    ref, dt, cores = cpu_reference_gop(variant, to_float(frames8_host[:n]), y_cond0_host, sd_i, sd_s)
+    params = None if serial else pipe.stem.ws._bufs.get("gparams")
+    rep = P.gop_parity(out, ref, H, W, params)
+    keep = ("ok", "max_bpp_rel_err", "max_psnr_abs_err", "max_y_hat_mismatch_frac", "max_sigma_rel_rms",
+            "max_mu_err_over_sigma_rms", "gates")
+    short = {k: rep[k] for k in keep if k in rep}
+    short.update(frames_checked=n, height=H, width=W, bpp_ref=[f["bpp_ref"] for f in rep["frames"]],
+                 psnr_ref=[f["psnr_ref"] for f in rep["frames"]],
+                 ref_floored_lik_frac=max(f["ref_floored_lik_frac"] for f in rep["frames"]))
+    return short, n / dt, dt, cores
+
+
+def run_pframe_workload(ctx, name, steps, warmup, args, full):
+    """One P-frame workload -> dict.  full: the headline line (kernel roofline, clocks, CPU baseline, both parity
+    legs); otherwise a short run for `other_workloads`."""
+    variant, T, H, W, desc = WORKLOADS[name]
+    dev, rank, world = ctx.dev, ctx.rank, ctx.world
+    net, stem, pipe, sd_i, sd_s = make_models(variant, "default", dev)
+    frames8, y_cond0 = make_inputs(T, H, W, 1234 + rank, "default")
+    tm = time_pframes(ctx, pipe, frames8, y_cond0, steps, warmup, graph=not args.no_graph,
+                      reduce_every_step=args.reduce_every_step, sample_clocks=full)
+    ms_step = tm["ms_per_step"]
+    gflop_frame = algorithmic_gflop_per_frame(variant, H, W)
+    peaks = load_peaks()
+    res = {
+        "workload": name, "desc": desc, "variant": variant, "value": world * T / (ms_step / 1e3), "unit": UNIT,
+        "ms_per_step": ms_step, "frames_per_step": T, "steps": steps,
+        "e2e": {"value": world * T / (tm["e2e_ms_per_step"] / 1e3), "unit": UNIT,
+                "h2d_bytes_per_step": tm["h2d_bytes_per_step"], "d2h_bytes_per_step": tm["d2h_bytes_per_step"]},
+        "gpu_launches": tm["launches"], "cuda_graph": tm["cuda_graph"], "clocks": tm["clocks"],
+        "whole_step_roofline": {"bound": "tensor", "achieved": gflop_frame * T / ms_step, "peak": peaks["tf_sustained"],
+                                "unit": "TFLOP/s", "frac": gflop_frame * T / ms_step / peaks["tf_sustained"],
+                                "note": "algorithmic FLOPs of the whole step / step time (non-GEMM kernels included)"},
+        "algorithmic_gflop_per_frame": gflop_frame,
+    }
+    step_resident = tm["step_resident"]
+
+    # ------------------------------------------------------------ roofline of the dominant kernel (headline only)
+    if full and rank == 0:
+        from spatiotemporalentropymodel_b200 import engine as E
+        recs = []
+        orig, orig_last = E.ConvOp.__call__, E.ConvOp.call_last
+
+        def timed_call(self, inputs, batch, h, w, out, aux=None):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            r = orig(self, inputs, batch, h, w, out, aux)
+            b.record()
+            recs.append((a, b, self.alg_flops(batch, h, w), self.gdn is not None))
+            return r
+
+        def timed_last(self, inputs, batch, h, w, w6, col, act=None):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            r = orig_last(self, inputs, batch, h, w, w6, col, act)
+            b.record()
+            # gs4 (deconv + IGDN) and the final deconv(N, 3) GEMM run in this one launch
+            fl = self.alg_flops(batch, h, w) + self.alg_flops_per_out_pixel_last * batch * 4 * h * w
+            recs.append((a, b, fl, True))
+            return r
+
+        E.ConvOp.__call__, E.ConvOp.call_last = timed_call, timed_last
+        try:
+            for _ in range(2):
+                recs.clear()
+                step_resident()
+                torch.cuda.synchronize()
+        finally:
+            E.ConvOp.__call__, E.ConvOp.call_last = orig, orig_last
+        dom = [(a.elapsed_time(b), f) for a, b, f, fused in recs if fused]
+        allc = [(a.elapsed_time(b), f) for a, b, f, fused in recs]
+        dom_ms, dom_gf = sum(t for t, _ in dom), sum(f for _, f in dom) / 1e9
+        all_ms, all_gf = sum(t for t, _ in allc), sum(f for _, f in allc) / 1e9
+        achieved = dom_gf / dom_ms  # GFLOP/ms == TFLOP/s
+        peak = peaks["tf_sustained"]
+        traffic, traffic_src = measured_traffic()
+        res["roofline"] = {
+            "bound": "tensor",
+            "kernel": "stem::conv_gdn_kernel (conv/deconv + GDN/IGDN fused; the last launch also carries the final "
+                      "deconv as a GEMM)",
+            "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+            "peak_kind": f"bf16 dense sustained (kernel timed inside a long step), {peaks['source']}",
+            "traffic": traffic, "traffic_unit": "bytes per launch (dram read+write, ncu --set full)",
+            "traffic_source": traffic_src,
+            "launches_per_step": len(dom), "kernel_ms_per_step": dom_ms, "launch_ms": [round(t, 4) for t, _ in dom],
+            "algorithmic_gflop_per_launch": dom_gf / max(len(dom), 1), "kernel_share_of_step": dom_ms / ms_step,
+            "all_dense_kernels": {"launches_per_step": len(allc), "ms_per_step": all_ms,
+                                  "algorithmic_gflop_per_step": all_gf, "achieved_tflops": all_gf / all_ms,
+                                  "frac": all_gf / all_ms / peak, "share_of_step": all_ms / ms_step}}
+
+    # ------------------------------------------------------------ parity + CPU baseline (rank 0)
+    if rank == 0 and not args.no_cpu_baseline and (world == 1 or args.parity):
+        n_par = args.cpu_frames if full else 1
+        out = step_resident()
+        torch.cuda.synchronize()
+        par, fps, dt, cores = parity_report(pipe, variant, frames8, y_cond0, sd_i, sd_s, out, n_par, H, W)
+        par["checkpoint"] = "default"
+        res["parity"] = {"default": par}
+        res["cpu_baseline"] = {"value": fps, "unit": UNIT, "cores": cores, "kind": "port",
+                               "sample": f"{par['frames_checked']} P-frames of the same workload ({dt:.1f} s), torch CPU "
+                                         f"fp32 oracle port; the same run is the parity check of the timed GPU output"}
+        if full:
+            # second checkpoint: the low-rate auto-encoder calibration, where sigma / mu / x_hat errors are visible
+            net2, stem2, pipe2, sd_i2, sd_s2 = make_models(variant, "lowrate", dev)
+            fr2, yc2 = make_inputs(n_par, H, W, 4321, "lowrate", net2, dev)
+            out2 = pipe2.forward_gop(fr2.to(dev), yc2.to(dev))
+            torch.cuda.synchronize()
+            par2, _, _, _ = parity_report(pipe2, variant, fr2, yc2, sd_i2, sd_s2, out2, n_par, H, W)
+            par2["checkpoint"] = "lowrate"
+            res["parity"]["lowrate"] = par2
+            del net2, stem2, pipe2
+        res["parity"]["ok"] = all(p["ok"] for p in res["parity"].values())
+    ctx.barrier()
+    return res
+
+
+def run_stem_roi(ctx, name, steps, warmup, args, full):
     """BASELINE.json configs[4]: stem_roi.forward (x_cur, x_conditioned, Qmap) on frames padded to a multiple of
     64, one model replica per GPU, frames sharded over ranks (weak scaling), fps = frames / max-over-ranks time."""
-    import torch.distributed as dist
     import torch.nn.functional as F
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    if world > 1:
-        init_dist(dev)
     from spatiotemporalentropymodel_b200 import _lib, stem_roi as R, synthetic as S
     from spatiotemporalentropymodel_b200.engine import ConvOp
-    _, T, H, W, desc = WORKLOADS[args.workload]
+    dev, rank, world = ctx.dev, ctx.rank, ctx.world
+    _, T, H, W, desc = WORKLOADS[name]
+    sd = R.make_synthetic_state_dict(0)
     model = R.stem_roi()
-    model.load_state_dict(R.make_synthetic_state_dict(0))
+    model.load_state_dict(sd)
     model.update(force=True)
     model = model.to(dev).eval()
     Hp, Wp = (H + 63) // 64 * 64, (W + 63) // 64 * 64
@@ -226,7 +534,7 @@ def run_stem_roi(args):
     x_cond = F.pad(frames[:-1], pad).to(dev)
     qmap = R.make_qmap(T, Hp, Wp, "ramp").to(dev)
     step = lambda: model(x_cur, x_cond, qmap)  # noqa: E731
-    for _ in range(max(args.warmup, 3)):
+    for _ in range(max(warmup, 3)):
         out = step()
     torch.cuda.synchronize()
     flops = []
@@ -242,26 +550,21 @@ def run_stem_roi(args):
     finally:
         ConvOp.__call__ = orig
     torch.cuda.synchronize()
-    sampler = ClockSampler(local_rank)
-    if world > 1:
-        dist.barrier()
+    sampler = ClockSampler(ctx.local_rank) if (full and rank == 0) else None
+    ctx.barrier()
     torch.cuda.synchronize()
-    if rank == 0:
+    if sampler:
         sampler.start()
     n0 = _lib.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(args.steps):
+    for _ in range(steps):
         out = step()
     e1.record()
     torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    ms_total = float(ms.item())
-    clocks = sampler.stop() if rank == 0 else None
+    ctx.barrier()
+    ms_total = ctx.max_ms(e0.elapsed_time(e1))
+    clocks = sampler.stop() if sampler else None
     launches = _lib.launch_count() - n0
     # e2e: pinned host frames + quality map in, bits out
     hx, hc, hq = x_cur.cpu().pin_memory(), x_cond.cpu().pin_memory(), qmap.cpu().pin_memory()
@@ -274,34 +577,54 @@ def run_stem_roi(args):
         torch.cuda.synchronize()
 
     e2e(2)
+    ctx.barrier()
     t0 = time.perf_counter()
-    e2e(args.steps)
-    e2e_ms = torch.tensor([(time.perf_counter() - t0) * 1e3], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
-    if rank == 0:
-        peaks = load_peaks()
-        gflop_step = sum(flops) / 1e9
-        ms_step = ms_total / args.steps
-        print(json.dumps({
-            "metric": "frames/sec (stem_roi fwd+likelihoods)", "value": world * T * args.steps / (ms_total / 1e3),
-            "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f16 operands / f32 accumulate (tcgen05 kind::f16); entropy kernels f32", "data": "synthetic",
-            "config": {"workload": args.workload, "desc": desc, "variant": "stem_roi", "height": H, "width": W,
-                       "frames_per_step": T, "cuda_graph": False,
-                       "l2": "per-step working set (> 10 GB of activations at 4K) exceeds the 126 MB L2"},
-            "clocks": clocks,
-            "e2e": {"value": world * T * args.steps / (float(e2e_ms.item()) / 1e3), "unit": UNIT,
-                    "h2d_bytes_per_step": (hx.numel() + hc.numel() + hq.numel()) * 4, "d2h_bytes_per_step": hbits.numel() * 8},
-            "gpu_launches": launches,
-            "roofline": {"bound": "tensor", "kernel": "all dense contractions of the step (conv_igemm / conv_gdn)",
-                         "achieved": gflop_step / ms_step, "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
-                         "frac": gflop_step / ms_step / peaks["tf_sustained"], "traffic": None,
-                         "note": "whole-step time (includes the non-GEMM kernels), algorithmic FLOPs"},
-            "cpu_baseline": None, "algorithmic_gflop_per_frame": gflop_step / T}))
-    if world > 1:
-        dist.destroy_process_group()
+    e2e(steps)
+    e2e_ms = ctx.max_ms((time.perf_counter() - t0) * 1e3)
+    peaks = load_peaks()
+    gflop_step = sum(flops) / 1e9
+    ms_step = ms_total / steps
+    res = {
+        "workload": name, "desc": desc, "variant": "stem_roi", "metric": "frames/sec (stem_roi fwd+likelihoods)",
+        "value": world * T * steps / (ms_total / 1e3), "unit": UNIT, "ms_per_step": ms_step, "frames_per_step": T,
+        "steps": steps, "cuda_graph": False, "clocks": clocks,
+        "e2e": {"value": world * T * steps / (e2e_ms / 1e3), "unit": UNIT,
+                "h2d_bytes_per_step": (hx.numel() + hc.numel() + hq.numel()) * 4, "d2h_bytes_per_step": hbits.numel() * 8},
+        "gpu_launches": launches,
+        "whole_step_roofline": {"bound": "tensor", "achieved": gflop_step / ms_step, "peak": peaks["tf_sustained"],
+                                "unit": "TFLOP/s", "frac": gflop_step / ms_step / peaks["tf_sustained"],
+                                "note": "algorithmic FLOPs of all dense contractions / step time (non-GEMM kernels "
+                                        "included)"},
+        "algorithmic_gflop_per_frame": gflop_step / T,
+    }
+    if rank == 0 and not args.no_cpu_baseline and (world == 1 or args.parity):
+        # CPU reference + parity on ONE 1080p-class frame (a 4K frame costs ~4x on the host): bpp 0.5 %, PSNR 0.01 dB
+        from oracle import stem_roi_oracle as RO
+        h1, w1 = (1088, 1920) if H > 1088 else (Hp, Wp)
+        fr = S.make_frames(2, h1, w1, seed=78)
+        q1 = R.make_qmap(1, h1, w1, "ramp")
+        torch.set_num_threads(os.cpu_count() or 1)
+        t0 = time.perf_counter()
+        with torch.no_grad():
+            ref = RO.stem_roi_forward(fr[1:2], fr[0:1], q1, sd)
+        dt = time.perf_counter() - t0
+        got = model(fr[1:2].to(dev), fr[0:1].to(dev), q1.to(dev))
+        bits = lambda l: float((-torch.log2(l.double())).sum())  # noqa: E731
+        gb = bits(got["likelihoods"]["y"].cpu()) + bits(got["likelihoods"]["z"].cpu())
+        rb = bits(ref["likelihoods"]["y"]) + bits(ref["likelihoods"]["z"])
+        psnr = lambda a: float(-10 * torch.log10(((fr[1:2] - a.clamp(0, 1)) ** 2).mean()))  # noqa: E731
+        pe = abs(psnr(got["x_hat"].cpu()) - psnr(ref["x_hat"]))
+        res["parity"] = {"default": {"ok": bool(abs(gb - rb) / rb <= 5e-3 and pe <= 0.01),
+                                     "max_bpp_rel_err": abs(gb - rb) / rb, "max_psnr_abs_err": pe, "frames_checked": 1,
+                                     "height": h1, "width": w1, "checkpoint": "default"}}
+        res["parity"]["ok"] = res["parity"]["default"]["ok"]
+        scale = (Hp * Wp) / float(h1 * w1)
+        res["cpu_baseline"] = {"value": 1.0 / (dt * scale), "unit": UNIT, "cores": torch.get_num_threads(),
+                               "kind": "port",
+                               "sample": f"one {h1}x{w1} frame through the torch CPU fp32 oracle port ({dt:.1f} s), "
+                                         f"scaled x{scale:.2f} by pixel count to {Hp}x{Wp}"}
+    ctx.barrier()
+    return res
 
 
 def run_ar_codec(args):
@@ -388,238 +711,62 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="gop12_full_1080p", choices=sorted(WORKLOADS))
     ap.add_argument("--no-graph", action="store_true", help="do not capture the step in a CUDA graph")
-    ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--cpu-frames", type=int, default=2)
+    ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU oracle legs (cpu_baseline and parity)")
+    ap.add_argument("--cpu-frames", type=int, default=2, help="frames of the workload the CPU oracle runs (and checks)")
+    ap.add_argument("--no-other-workloads", action="store_true", help="only the headline workload")
+    ap.add_argument("--other-steps", type=int, default=5)
+    ap.add_argument("--parity", action="store_true", help="run the parity legs also under torchrun (rank 0)")
+    ap.add_argument("--reduce-every-step", action="store_true",
+                    help="all-reduce the statistics after every step instead of once per run")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
     if args.impl == "reference":
         run_reference(args)
         return
-
-    if WORKLOADS[args.workload][0] == "stem_roi":
-        run_stem_roi(args)
-        return
     if WORKLOADS[args.workload][0] == "ar_codec":
         run_ar_codec(args)
         return
 
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    import torch.distributed as dist
-    if world > 1:
-        init_dist(dev)
+    ctx = Ctx()
+    runner = lambda name: run_stem_roi if WORKLOADS[name][0] == "stem_roi" else run_pframe_workload  # noqa: E731
+    res = runner(args.workload)(ctx, args.workload, args.steps, args.warmup, args, True)
+    others = {}
+    if not args.no_other_workloads:
+        for name in OTHER_WORKLOADS:
+            if name == args.workload:
+                continue
+            torch.cuda.empty_cache()
+            try:
+                o = runner(name)(ctx, name, args.other_steps, args.warmup, args, False)
+                others[name] = {k: o[k] for k in ("desc", "value", "unit", "ms_per_step", "frames_per_step", "steps", "e2e",
+                                                  "gpu_launches", "whole_step_roofline", "parity", "cpu_baseline")
+                                if k in o}
+            except Exception as e:  # a secondary workload must not take the headline line down
+                others[name] = {"error": f"{type(e).__name__}: {e}"}
 
-    from spatiotemporalentropymodel_b200 import _lib, models as M, synthetic as S
-    from spatiotemporalentropymodel_b200.dist import reduce_stats
-
-    variant, T, H, W, desc = WORKLOADS[args.workload]
-    sd_i, sd_s = S.make_iframe_state_dict(0), S.make_stem_state_dict(variant, 0)
-    net = M.models["mbt2018"](quality=4)
-    net.load_state_dict(sd_i)
-    stem = getattr(M, variant)()
-    stem.load_state_dict(sd_s)
-    stem.update(force=True)
-    net, stem = net.to(dev).eval(), stem.to(dev).eval()
-    pipe = M.make_pipeline(net, stem)
-
-    # every rank gets its own GOP (different seed): weak scaling over independent GOPs
-    frames_host = S.make_frames(T, H, W, seed=1234 + rank).pin_memory()
-    hp, wp = (H + 63) // 64 * 64 // 16, (W + 63) // 64 * 64 // 16
-    y_cond0 = S.make_latent(1, 192, hp, wp, seed=5 + rank).to(dev)
-    frames_dev = frames_host.to(dev)
-
-    def step_resident():
-        out = pipe.forward_gop(frames_dev, y_cond0, want_outputs=True)
-        return out["stats"]
-
-    # ---------------------------------------------------------------- device-resident timing ("value")
-    for _ in range(args.warmup):
-        stats = step_resident()
-        if world > 1:
-            reduce_stats(stats)
-    torch.cuda.synchronize()
-    graph = None
-    if not args.no_graph:
-        try:
-            graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph):
-                g_stats = step_resident()
-            graph.replay()
-            torch.cuda.synchronize()
-        except Exception as e:  # graph capture is an optimisation, not a requirement
-            if rank == 0:
-                print(f"[bench] CUDA graph capture failed ({type(e).__name__}: {e}); timing eager launches",
-                      file=sys.stderr)
-            graph = None
-            torch.cuda.synchronize()
-
-    def run_step():
-        if graph is not None:
-            graph.replay()
-            return g_stats
-        return step_resident()
-
-    for _ in range(2):
-        run_step()
-    torch.cuda.synchronize()
-    sampler = ClockSampler(local_rank)
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    if rank == 0:
-        sampler.start()
-    n0 = _lib.launch_count()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ev0.record()
-    for _ in range(args.steps):
-        stats = run_step()
-        if world > 1:
-            reduce_stats(stats)
-    ev1.record()
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    ms_total = ev0.elapsed_time(ev1)
-    clocks = sampler.stop() if rank == 0 else None
-    launches_timed = _lib.launch_count() - n0
-    if graph is not None:
-        # a replayed graph re-issues the kernels captured once: count them from an eager step
-        n1 = _lib.launch_count()
-        step_resident()
-        torch.cuda.synchronize()
-        launches_timed = (_lib.launch_count() - n1) * args.steps
-    tmax = torch.tensor([ms_total], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-    ms_total = float(tmax.item())
-    ms_per_step = ms_total / args.steps
-    value = world * T * args.steps / (ms_total / 1e3)
-
-    # ---------------------------------------------------------------- end-to-end: pinned host frames in, stats out
-    # the public streaming call: PFramePipeline.run_gop copies the pinned host frames into one of its two device slots
-    # on a copy stream (overlapping the previous call's kernels) and replays the captured graph of that slot
-    host_stats = torch.empty((3, T), dtype=torch.float64).pin_memory()
-
-    def e2e_loop(n):
-        for _ in range(n):
-            out = pipe.run_gop(frames_host, y_cond0, want_outputs=True)
-            st = out["stats"]
-            if world > 1:
-                reduce_stats(st)
-            host_stats.copy_(st, non_blocking=True)
-        torch.cuda.synchronize()
-
-    e2e_loop(3)
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    e2e_loop(args.steps)
-    e1.record()
-    torch.cuda.synchronize()
-    e2e_ms = max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3)
-    te = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_value = world * T * args.steps / (float(te.item()) / 1e3)
-
-    # ---------------------------------------------------------------- roofline of the dominant kernel
-    # dominant kernel = stem::conv_gdn_kernel (conv/deconv + GDN/IGDN, 6 launches per step, ~60 % of the step).
-    # achieved = algorithmic FLOPs of those launches / their CUDA-event durations, measured in an extra eager step
-    # (events on torch's current stream, which is the stream the kernels are launched on).
-    peaks = load_peaks()
-    roofline = None
-    if rank == 0:
-        from spatiotemporalentropymodel_b200 import engine as E
-        recs = []
-        orig = E.ConvOp.__call__
-
-        def timed_call(self, inputs, batch, h, w, out, aux=None):
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record()
-            r = orig(self, inputs, batch, h, w, out, aux)
-            b.record()
-            recs.append((a, b, self.alg_flops(batch, h, w), self.gdn is not None))
-            return r
-
-        orig_last = E.ConvOp.call_last
-
-        def timed_last(self, inputs, batch, h, w, w6, col, act=None):
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record()
-            r = orig_last(self, inputs, batch, h, w, w6, col, act)
-            b.record()
-            # gs4 (deconv + IGDN) and the final deconv(N, 3) GEMM run in this one launch
-            fl = self.alg_flops(batch, h, w) + self.alg_flops_per_out_pixel_last * batch * 4 * h * w
-            recs.append((a, b, fl, True))
-            return r
-
-        E.ConvOp.__call__ = timed_call
-        E.ConvOp.call_last = timed_last
-        try:
-            for _ in range(2):
-                recs.clear()
-                step_resident()
-                torch.cuda.synchronize()
-        finally:
-            E.ConvOp.__call__ = orig
-            E.ConvOp.call_last = orig_last
-        dom = [(a.elapsed_time(b), f) for a, b, f, fused in recs if fused]
-        allc = [(a.elapsed_time(b), f) for a, b, f, fused in recs]
-        dom_ms, dom_gf = sum(t for t, _ in dom), sum(f for _, f in dom) / 1e9
-        all_ms, all_gf = sum(t for t, _ in allc), sum(f for _, f in allc) / 1e9
-        achieved = dom_gf / dom_ms  # GFLOP/ms == TFLOP/s
-        peak = peaks["tf_sustained"]
-        # DRAM bytes of the same 6 launches from the committed ncu --set full capture
-        # (profiles/r01_ncu_bench_conv_gdn_v8.txt): 8.30 GB per step (algorithmic fp16 in + out: 8.54 GB)
-        roofline = {"bound": "tensor", "kernel": "stem::conv_gdn_kernel (conv/deconv + GDN/IGDN fused; the last launch also carries the final deconv as a GEMM)",
-                    "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                    "peak_kind": f"bf16 dense sustained (kernel timed inside a long step), {peaks['source']}",
-                    "traffic": 8.29e9 / 6 if (variant, T, H, W) == WORKLOADS["gop12_full_1080p"][:4] else None,
-                    "traffic_unit": "bytes per launch (dram read+write, ncu, profiles/r01_ncu_bench_conv_gdn_v8.txt)",
-                    "launches_per_step": len(dom), "kernel_ms_per_step": dom_ms,
-                    "launch_ms": [round(t, 4) for t, _ in dom],
-                    "algorithmic_gflop_per_launch": dom_gf / max(len(dom), 1),
-                    "kernel_share_of_step": dom_ms / ms_per_step,
-                    "all_dense_kernels": {"launches_per_step": len(allc), "ms_per_step": all_ms,
-                                          "algorithmic_gflop_per_step": all_gf, "achieved_tflops": all_gf / all_ms,
-                                          "frac": all_gf / all_ms / peak, "share_of_step": all_ms / ms_per_step}}
-
-    # ---------------------------------------------------------------- CPU baseline (rank 0, N == 1 only)
-    cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        fps, dt, cores = cpu_reference_fps(variant, H, W, args.cpu_frames)
-        cpu = {"value": fps, "unit": UNIT, "cores": cores, "kind": "port",
-               "sample": f"{args.cpu_frames} P-frames of the same workload ({dt:.1f} s), torch CPU fp32 oracle port"}
-
-    if rank == 0:
-        h2d = frames_host.numel() * 4
+    if ctx.rank == 0:
+        variant, T, H, W, desc = WORKLOADS[args.workload]
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f16 operands / f32 accumulate (tcgen05 kind::f16); entropy kernels f32",
-            "data": "synthetic",
+            "metric": res.get("metric", METRIC), "value": res["value"], "unit": UNIT, "n_gpus": ctx.world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": res["ms_per_step"], "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": DTYPE, "data": "synthetic",
             "config": {"workload": args.workload, "desc": desc, "variant": variant, "height": H, "width": W,
-                       "frames_per_step": T, "per_gpu_frames_per_step": T, "cuda_graph": graph is not None,
+                       "frames_per_step": T, "per_gpu_frames_per_step": T, "cuda_graph": res["cuda_graph"],
+                       "frame_dtype": "uint8 (8-bit samples, v / 255 on the device)" if variant != "stem_roi" else "f32",
+                       "stats_reduction": "every step" if args.reduce_every_step else "once per run (inside the timed region)",
                        "l2": "per-step working set (several GB of activations) exceeds the 126 MB L2; no flush needed",
                        "checkpoint": "seeded synthetic (spatiotemporalentropymodel_b200.synthetic)"},
-            "clocks": clocks,
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d,
-                    "d2h_bytes_per_step": host_stats.numel() * 8},
-            "gpu_launches": launches_timed,
-            "roofline": roofline,
-            "cpu_baseline": cpu,
-            "algorithmic_gflop_per_frame": algorithmic_gflop_per_frame(variant, H, W),
+            "clocks": res["clocks"], "e2e": res["e2e"], "gpu_launches": res["gpu_launches"],
+            "roofline": res.get("roofline") or res.get("whole_step_roofline"),
+            "whole_step_roofline": res["whole_step_roofline"],
+            "cpu_baseline": res.get("cpu_baseline"), "parity": res.get("parity"),
+            "algorithmic_gflop_per_frame": res["algorithmic_gflop_per_frame"],
+            "other_workloads": others,
         }
         print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
+    if ctx.world > 1:
+        ctx.dist.destroy_process_group()
 
 
 if __name__ == "__main__":

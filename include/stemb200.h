@@ -121,6 +121,13 @@ int stemb200_synthesis_col_index(int32_t r, int32_t s, int32_t c);
 int stemb200_synthesis_col2im(const void* col_f16, const float* bias3, float* x_hat_nchw, int32_t n, int32_t h2,
                               int32_t w2, const float* x_ref, int32_t h_ref, int32_t w_ref, int32_t pad_top,
                               int32_t pad_left, double* sq_err, int32_t clamp01, void* stream);
+/* Same with the reference frame as 8-bit samples [n][3][h_ref][w_ref]: the pixel value is float(v) / 255 (IEEE
+ * division), i.e. what torchvision's ToTensor hands to the model for the PNG frames of stem/evalSTEM.py:185 -
+ * results are bit-identical to stemb200_synthesis_col2im on the converted frame, with a quarter of the bytes
+ * crossing PCIe and HBM. */
+int stemb200_synthesis_col2im_u8(const void* col_f16, const float* bias3, float* x_hat_nchw, int32_t n, int32_t h2,
+                                 int32_t w2, const uint8_t* x_ref, int32_t h_ref, int32_t w_ref, int32_t pad_top,
+                                 int32_t pad_left, double* sq_err, int32_t clamp01, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------
  * Layout / staging kernels at the API boundary
@@ -145,6 +152,10 @@ int stemb200_im2col_k5s2_c3(const float* x_nchw, void* out_rows, int32_t n, int3
 int stemb200_frame_to_nhwc8(const float* x_nchw, void* canvas, int32_t n, int32_t c, int32_t h, int32_t w,
                             int32_t h_pad, int32_t w_pad, int32_t pad_top, int32_t pad_left, int32_t border,
                             void* stream);
+/* Same from an 8-bit NCHW frame (pixel = float(v) / 255, see stemb200_synthesis_col2im_u8). */
+int stemb200_frame_u8_to_nhwc8(const uint8_t* x_nchw, void* canvas, int32_t n, int32_t c, int32_t h, int32_t w,
+                               int32_t h_pad, int32_t w_pad, int32_t pad_top, int32_t pad_left, int32_t border,
+                               void* stream);
 
 /* stem_roi (compressai/models/stem_roi.py) staging kernels.
  * im2col_k3s1_c4: operand rows of conv(4, 192, k3, s1) on cat[x (3 ch), Qmap (1 ch)] (:379, :586):
@@ -213,6 +224,9 @@ int stemb200_entropy_bottleneck_fwd(const float* z_nhwc, const float* params, in
 int stemb200_synthesis_tail(const float* in_nhwc64, float* x_hat_nchw, int32_t n, int32_t h4, int32_t w4,
                             const float* x_ref, int32_t h_ref, int32_t w_ref, int32_t pad_top, int32_t pad_left,
                             double* sq_err, int32_t clamp01, void* stream);
+int stemb200_synthesis_tail_u8(const float* in_nhwc64, float* x_hat_nchw, int32_t n, int32_t h4, int32_t w4,
+                               const uint8_t* x_ref, int32_t h_ref, int32_t w_ref, int32_t pad_top, int32_t pad_left,
+                               double* sq_err, int32_t clamp01, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------
  * Autoregressive coding of y for the variants with a spatial context model (SpatioTemporalPriorModel, _Res,

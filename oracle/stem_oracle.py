@@ -274,12 +274,13 @@ def pad_to_64(x: Tensor) -> Tuple[Tensor, Tuple[int, int, int, int]]:
     return F.pad(x, (left, right, top, bottom), mode="constant", value=0), (left, right, top, bottom)
 
 
-def pframe_forward(x: Tensor, y_cond: Tensor, sd_i: SD, sd_stem: SD, variant: str) -> Dict[str, Tensor]:
+def pframe_forward(x: Tensor, y_cond: Tensor, sd_i: SD, sd_stem: SD, variant: str,
+                   return_params: bool = False) -> Dict[str, Tensor]:
     """evalSTEM.py:93-154 minus the entropy coder: pad -> g_a -> STEM forward -> g_s on the forward pass's
     y_hat -> crop -> estimated bpp (:133-136) and PSNR (:29-31,146)."""
     x_pad, (l, r, t, b) = pad_to_64(x)
     y = g_a(x_pad, sd_i)
-    out = stem_forward(variant, y, y_cond, sd_stem)
+    out = stem_forward(variant, y, y_cond, sd_stem, return_params=return_params)
     x_hat = g_s(out["y_hat"], sd_i)
     x_hat = F.pad(x_hat, (-l, -r, -t, -b))
     n, _, h, w = x.shape
@@ -287,19 +288,20 @@ def pframe_forward(x: Tensor, y_cond: Tensor, sd_i: SD, sd_stem: SD, variant: st
     bits_y = (torch.log(out["likelihoods"]["y"]).flatten(1).sum(1) / -math.log(2))
     bits_z = (torch.log(out["likelihoods"]["z"]).flatten(1).sum(1) / -math.log(2))
     mse = ((x - x_hat) ** 2).flatten(1).mean(1)
+    extra = {k: out[k] for k in ("scales", "means", "z_hat") if k in out}
     return {
-        "y": y, "y_hat": out["y_hat"], "x_hat": x_hat,
+        **extra, "y": y, "y_hat": out["y_hat"], "x_hat": x_hat,
         "lik_y": out["likelihoods"]["y"], "lik_z": out["likelihoods"]["z"],
         "bpp": (bits_y + bits_z) / num_pixels, "bpp_y": bits_y / num_pixels, "bpp_z": bits_z / num_pixels,
         "psnr": -10 * torch.log10(mse), "mse": mse,
     }
 
 
-def gop_forward(frames: Tensor, y_cond0: Tensor, sd_i: SD, sd_stem: SD, variant: str):
+def gop_forward(frames: Tensor, y_cond0: Tensor, sd_i: SD, sd_stem: SD, variant: str, return_params: bool = False):
     """evalSTEM.py:184-209 P-frame loop: y_conditioned <- y_hat of the previous frame."""
     outs, y_cond = [], y_cond0
     for t in range(frames.shape[0]):
-        o = pframe_forward(frames[t:t + 1], y_cond, sd_i, sd_stem, variant)
+        o = pframe_forward(frames[t:t + 1], y_cond, sd_i, sd_stem, variant, return_params=return_params)
         outs.append(o)
         y_cond = o["y_hat"]
     return outs

@@ -55,11 +55,14 @@ SIGNATURES = {
     "stemb200_synthesis_col_index": (C.c_int, [_i32, _i32, _i32]),
     "stemb200_synthesis_col2im": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _vp, _i32, _i32, _i32, _i32, _vp, _i32,
                                             _vp]),
+    "stemb200_synthesis_col2im_u8": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _vp, _i32, _i32, _i32, _i32, _vp, _i32,
+                                               _vp]),
     "stemb200_nchw_f32_to_nhwc_f16": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp]),
     "stemb200_nhwc_f16_to_nchw_f32": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _vp]),
     "stemb200_nhwc_f32_to_nchw_f32": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _vp]),
     "stemb200_im2col_k5s2_c3": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
     "stemb200_frame_to_nhwc8": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
+    "stemb200_frame_u8_to_nhwc8": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
     "stemb200_im2col_k3s1_c4": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _vp]),
     "stemb200_avgpool_nhwc_f16": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp]),
     "stemb200_qmap_pool": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _vp]),
@@ -71,6 +74,7 @@ SIGNATURES = {
     "stemb200_entropy_bottleneck_fwd": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _f32, _vp, _vp, _vp, _vp,
                                                   _vp]),
     "stemb200_synthesis_tail": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _vp, _i32, _i32, _i32, _i32, _vp, _i32, _vp]),
+    "stemb200_synthesis_tail_u8": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _vp, _i32, _i32, _i32, _i32, _vp, _i32, _vp]),
     "stemb200_cast_f16_to_f32": (C.c_int, [_vp, _vp, _i64, _vp]),
     "stemb200_ar_packed_floats": (_i64, [C.POINTER(ArDesc)]),
     "stemb200_ar_workspace_bytes": (_i64, [C.POINTER(ArDesc)]),

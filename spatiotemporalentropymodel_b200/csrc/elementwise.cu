@@ -38,6 +38,37 @@ __device__ __forceinline__ void block_accumulate(float v, double* dst, float* re
 }
 
 // ---------------------------------------------------------------------------------------------------
+// frame pixel loads: fp32 frames as they are, 8-bit frames as float(v) / 255 (IEEE division), which is what
+// torchvision's ToTensor computes for the PNG frames of stem/evalSTEM.py:185 - bit-identical to uploading fp32
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float px_load(const float* p) { return __ldg(p); }
+__device__ __forceinline__ float px_load(const uint8_t* p) { return __fdiv_rn(static_cast<float>(__ldg(p)), 255.0f); }
+__device__ __forceinline__ void px_load2(const float* p, float& a, float& b) {  // 8-byte aligned
+  const float2 f = __ldg(reinterpret_cast<const float2*>(p));
+  a = f.x;
+  b = f.y;
+}
+__device__ __forceinline__ void px_load2(const uint8_t* p, float& a, float& b) {  // 2-byte aligned
+  const uchar2 u = __ldg(reinterpret_cast<const uchar2*>(p));
+  a = __fdiv_rn(static_cast<float>(u.x), 255.0f);
+  b = __fdiv_rn(static_cast<float>(u.y), 255.0f);
+}
+__device__ __forceinline__ void px_load4(const float* p, float (&v)[4]) {  // 16-byte aligned
+  const float4 f = __ldg(reinterpret_cast<const float4*>(p));
+  v[0] = f.x;
+  v[1] = f.y;
+  v[2] = f.z;
+  v[3] = f.w;
+}
+__device__ __forceinline__ void px_load4(const uint8_t* p, float (&v)[4]) {  // 4-byte aligned
+  const uchar4 u = __ldg(reinterpret_cast<const uchar4*>(p));
+  v[0] = __fdiv_rn(static_cast<float>(u.x), 255.0f);
+  v[1] = __fdiv_rn(static_cast<float>(u.y), 255.0f);
+  v[2] = __fdiv_rn(static_cast<float>(u.z), 255.0f);
+  v[3] = __fdiv_rn(static_cast<float>(u.w), 255.0f);
+}
+
+// ---------------------------------------------------------------------------------------------------
 // layout kernels (32x32 smem transposes)
 // ---------------------------------------------------------------------------------------------------
 // in: [n][c][hw] fp32 -> out: [n][hw][c] fp16
@@ -556,9 +587,10 @@ __global__ void eb_fwd_kernel(const float* __restrict__ z, const float* __restri
 // ---------------------------------------------------------------------------------------------------
 constexpr int kTailCh = 64;
 
+template <typename TRef>
 __global__ void __launch_bounds__(256)
 synthesis_tail_kernel(const float* __restrict__ in, float* __restrict__ xhat, int h4, int w4,
-                      const float* __restrict__ xref, int h_ref, int w_ref, int pad_top, int pad_left,
+                      const TRef* __restrict__ xref, int h_ref, int w_ref, int pad_top, int pad_left,
                       double* sq_err, int clamp01) {
   __shared__ float red[32];
   const int n = blockIdx.y;
@@ -594,12 +626,12 @@ synthesis_tail_kernel(const float* __restrict__ in, float* __restrict__ xhat, in
         if (xref) {
           const int yr = Y - pad_top;
           if (yr >= 0 && yr < h_ref) {
-            const float* rrow = xref + ((static_cast<long long>(n) * 3 + ch) * h_ref + yr) * w_ref;
+            const TRef* rrow = xref + ((static_cast<long long>(n) * 3 + ch) * h_ref + yr) * w_ref;
             const int x0 = 4 * jj - pad_left;
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
               if (x0 + q >= 0 && x0 + q < w_ref) {
-                const float d = __ldg(rrow + x0 + q) - o[q];
+                const float d = px_load(rrow + x0 + q) - o[q];
                 acc += d * d;
               }
             }
@@ -679,10 +711,11 @@ __device__ __forceinline__ void c2i_add_group(const unsigned char* px, float (&a
   }
 }
 
+template <typename TRef>
 __global__ void __launch_bounds__(kC2iThreads, 1)
 synthesis_col2im_kernel(const __grid_constant__ CUtensorMap col_map, const float* __restrict__ bias,
                         float* __restrict__ xhat, int h2, int w2, int tiles_x, int tiles_per_img, int total_tiles,
-                        const float* __restrict__ xref, int h_ref, int w_ref, int pad_top, int pad_left,
+                        const TRef* __restrict__ xref, int h_ref, int w_ref, int pad_top, int pad_left,
                         double* sq_err, int clamp01, int ref_vec) {
   extern __shared__ uint8_t c2i_smem[];
   __shared__ __align__(8) uint64_t bars[kC2iStages];
@@ -746,14 +779,12 @@ synthesis_col2im_kernel(const __grid_constant__ CUtensorMap col_map, const float
         for (int c = 0; c < 3; ++c) {
           rv[c][a][0] = rv[c][a][1] = 0.f;
           if (rok[a]) {
-            const float* rr = xref + (static_cast<long long>(n) * 3 + c) * rp + static_cast<long long>(yr) * w_ref + xr;
+            const TRef* rr = xref + (static_cast<long long>(n) * 3 + c) * rp + static_cast<long long>(yr) * w_ref + xr;
             if (ref_vec && cok0 && cok1) {
-              const float2 f = __ldg(reinterpret_cast<const float2*>(rr));
-              rv[c][a][0] = f.x;
-              rv[c][a][1] = f.y;
+              px_load2(rr, rv[c][a][0], rv[c][a][1]);
             } else {
-              if (cok0) rv[c][a][0] = __ldg(rr);
-              if (cok1) rv[c][a][1] = __ldg(rr + 1);
+              if (cok0) rv[c][a][0] = px_load(rr);
+              if (cok1) rv[c][a][1] = px_load(rr + 1);
             }
           }
         }
@@ -880,8 +911,9 @@ __device__ __forceinline__ uint4 pack_nhwc8(const float (&v)[8]) {
   return o;
 }
 
+template <typename TIn>
 __global__ void __launch_bounds__(128)
-frame_to_nhwc8_kernel(const float* __restrict__ x, uint4* __restrict__ canvas, int c, int h, int w, int hc, int wc,
+frame_to_nhwc8_kernel(const TIn* __restrict__ x, uint4* __restrict__ canvas, int c, int h, int w, int hc, int wc,
                       int off_top, int off_left, int groups, int vec_ok) {
   const int row = blockIdx.x;  // n * hc + canvas row
   const int n = row / hc, chh = row - n * hc;
@@ -897,17 +929,18 @@ frame_to_nhwc8_kernel(const float* __restrict__ x, uint4* __restrict__ canvas, i
 #pragma unroll
     for (int ch = 0; ch < 8; ++ch) v[p][ch] = 0.f;
   if (ih >= 0 && ih < h) {
-    const float* px = x + (static_cast<long long>(n) * c * h + ih) * w;
+    const TIn* px = x + (static_cast<long long>(n) * c * h + ih) * w;
     const long long plane = static_cast<long long>(h) * w;
     if (vec_ok && iw0 >= 0 && iw0 + 3 < w) {
 #pragma unroll
       for (int ch = 0; ch < 8; ++ch)
         if (ch < c) {
-          const float4 f = __ldg(reinterpret_cast<const float4*>(px + ch * plane + iw0));
-          v[0][ch] = f.x;
-          v[1][ch] = f.y;
-          v[2][ch] = f.z;
-          v[3][ch] = f.w;
+          float f[4];
+          px_load4(px + ch * plane + iw0, f);
+          v[0][ch] = f[0];
+          v[1][ch] = f[1];
+          v[2][ch] = f[2];
+          v[3][ch] = f[3];
         }
     } else {
 #pragma unroll
@@ -915,7 +948,7 @@ frame_to_nhwc8_kernel(const float* __restrict__ x, uint4* __restrict__ canvas, i
         if (iw0 + p >= 0 && iw0 + p < w) {
 #pragma unroll
           for (int ch = 0; ch < 8; ++ch)
-            if (ch < c) v[p][ch] = __ldg(px + ch * plane + iw0 + p);
+            if (ch < c) v[p][ch] = px_load(px + ch * plane + iw0 + p);
         }
     }
   }
@@ -929,10 +962,10 @@ extern "C" int stemb200_synthesis_col_index(int32_t r, int32_t s, int32_t c) {
   return c2i_col_index(r, s, c);
 }
 
-extern "C" int stemb200_synthesis_col2im(const void* col_f16, const float* bias3, float* x_hat_nchw, int32_t n,
-                                         int32_t h2, int32_t w2, const float* x_ref, int32_t h_ref, int32_t w_ref,
-                                         int32_t pad_top, int32_t pad_left, double* sq_err, int32_t clamp01,
-                                         void* stream) {
+template <typename TRef>
+static int synthesis_col2im_impl(const void* col_f16, const float* bias3, float* x_hat_nchw, int32_t n, int32_t h2,
+                                 int32_t w2, const TRef* x_ref, int32_t h_ref, int32_t w_ref, int32_t pad_top,
+                                 int32_t pad_left, double* sq_err, int32_t clamp01, void* stream) {
   if (!col_f16 || !bias3 || !x_hat_nchw || n < 1 || h2 < 1 || w2 < 1 || n > 65535)
     return set_error("synthesis_col2im: bad argument");
   if (x_ref && (h_ref < 1 || w_ref < 1 || pad_top < 0 || pad_left < 0))
@@ -944,24 +977,44 @@ extern "C" int stemb200_synthesis_col2im(const void* col_f16, const float* bias3
   if (total > 0x7fffffffLL - 2LL * 65536) return set_error("synthesis_col2im: frame too large");
   CUtensorMap col_map;
   if (int rc = encode_nhwc_plain(&col_map, col_f16, n, h2, w2, 96, kC2iCols, kC2iIW, kC2iIH)) return rc;
-  static bool attr_set = false;  // benign race: the attribute set is idempotent
+  static bool attr_set = false;  // benign race: the attribute set is idempotent (one flag per instantiation)
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(synthesis_col2im_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kC2iSmem);
+    cudaError_t e = cudaFuncSetAttribute(synthesis_col2im_kernel<TRef>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         kC2iSmem);
     if (e != cudaSuccess) return set_cuda_error("synthesis_col2im: smem attribute", e);
     attr_set = true;
   }
-  const int ref_vec = x_ref && pad_left % 2 == 0 && w_ref % 2 == 0 && (reinterpret_cast<uintptr_t>(x_ref) & 7) == 0;
+  // a pixel pair is loaded with one access when it is aligned to 2 pixels of TRef
+  const int ref_vec = x_ref && pad_left % 2 == 0 && w_ref % 2 == 0 &&
+                      (reinterpret_cast<uintptr_t>(x_ref) & (2 * sizeof(TRef) - 1)) == 0;
   const int grid = static_cast<int>(std::min<long long>(total, num_sms()));
-  synthesis_col2im_kernel<<<grid, kC2iThreads, kC2iSmem, static_cast<cudaStream_t>(stream)>>>(
+  synthesis_col2im_kernel<TRef><<<grid, kC2iThreads, kC2iSmem, static_cast<cudaStream_t>(stream)>>>(
       col_map, bias3, x_hat_nchw, h2, w2, tiles_x, tiles_x * tiles_y, static_cast<int>(total), x_ref, h_ref, w_ref,
       pad_top, pad_left, sq_err, clamp01, ref_vec);
   CHECK_LAUNCH("synthesis_col2im");
   return 0;
 }
 
-extern "C" int stemb200_frame_to_nhwc8(const float* x_nchw, void* canvas, int32_t n, int32_t c, int32_t h, int32_t w,
-                                       int32_t h_pad, int32_t w_pad, int32_t pad_top, int32_t pad_left,
-                                       int32_t border, void* stream) {
+extern "C" int stemb200_synthesis_col2im(const void* col_f16, const float* bias3, float* x_hat_nchw, int32_t n,
+                                         int32_t h2, int32_t w2, const float* x_ref, int32_t h_ref, int32_t w_ref,
+                                         int32_t pad_top, int32_t pad_left, double* sq_err, int32_t clamp01,
+                                         void* stream) {
+  return synthesis_col2im_impl<float>(col_f16, bias3, x_hat_nchw, n, h2, w2, x_ref, h_ref, w_ref, pad_top, pad_left,
+                                      sq_err, clamp01, stream);
+}
+
+extern "C" int stemb200_synthesis_col2im_u8(const void* col_f16, const float* bias3, float* x_hat_nchw, int32_t n,
+                                            int32_t h2, int32_t w2, const uint8_t* x_ref, int32_t h_ref,
+                                            int32_t w_ref, int32_t pad_top, int32_t pad_left, double* sq_err,
+                                            int32_t clamp01, void* stream) {
+  return synthesis_col2im_impl<uint8_t>(col_f16, bias3, x_hat_nchw, n, h2, w2, x_ref, h_ref, w_ref, pad_top,
+                                        pad_left, sq_err, clamp01, stream);
+}
+
+template <typename TIn>
+static int frame_to_nhwc8_impl(const TIn* x_nchw, void* canvas, int32_t n, int32_t c, int32_t h, int32_t w,
+                               int32_t h_pad, int32_t w_pad, int32_t pad_top, int32_t pad_left, int32_t border,
+                               void* stream) {
   if (!x_nchw || !canvas || n < 1 || c < 1 || c > 8 || h < 1 || w < 1 || h_pad < h || w_pad < w || pad_top < 0 ||
       pad_left < 0 || border < 0 || pad_top + h > h_pad || pad_left + w > w_pad)
     return set_error("frame_to_nhwc8: bad argument");
@@ -970,12 +1023,24 @@ extern "C" int stemb200_frame_to_nhwc8(const float* x_nchw, void* canvas, int32_
   if (static_cast<long long>(n) * hc > 0x7fffffffLL) return set_error("frame_to_nhwc8: frame too large");
   // groups of 4 canvas pixels, the first one starting at canvas column off_left - roundup4(off_left) <= 0
   const int groups = (wc + ((off_left + 3) & ~3) - off_left + 3) / 4;
-  const int vec_ok = (w % 4 == 0) && (reinterpret_cast<uintptr_t>(x_nchw) % 16 == 0);
+  const int vec_ok = (w % 4 == 0) && (reinterpret_cast<uintptr_t>(x_nchw) % (4 * sizeof(TIn)) == 0);
   dim3 grid(n * hc, (groups + 127) / 128);
-  frame_to_nhwc8_kernel<<<grid, 128, 0, static_cast<cudaStream_t>(stream)>>>(
+  frame_to_nhwc8_kernel<TIn><<<grid, 128, 0, static_cast<cudaStream_t>(stream)>>>(
       x_nchw, static_cast<uint4*>(canvas), c, h, w, hc, wc, off_top, off_left, groups, vec_ok);
   CHECK_LAUNCH("frame_to_nhwc8");
   return 0;
+}
+
+extern "C" int stemb200_frame_to_nhwc8(const float* x_nchw, void* canvas, int32_t n, int32_t c, int32_t h, int32_t w,
+                                       int32_t h_pad, int32_t w_pad, int32_t pad_top, int32_t pad_left,
+                                       int32_t border, void* stream) {
+  return frame_to_nhwc8_impl<float>(x_nchw, canvas, n, c, h, w, h_pad, w_pad, pad_top, pad_left, border, stream);
+}
+
+extern "C" int stemb200_frame_u8_to_nhwc8(const uint8_t* x_nchw, void* canvas, int32_t n, int32_t c, int32_t h,
+                                          int32_t w, int32_t h_pad, int32_t w_pad, int32_t pad_top, int32_t pad_left,
+                                          int32_t border, void* stream) {
+  return frame_to_nhwc8_impl<uint8_t>(x_nchw, canvas, n, c, h, w, h_pad, w_pad, pad_top, pad_left, border, stream);
 }
 
 extern "C" int stemb200_im2col_k3s1_c4(const float* x_nchw, const float* q_nchw, void* out_rows, int32_t n,
@@ -1092,15 +1157,31 @@ extern "C" int stemb200_entropy_bottleneck_fwd(const float* z_nhwc, const float*
   return 0;
 }
 
+template <typename TRef>
+static int synthesis_tail_impl(const float* in_nhwc64, float* x_hat_nchw, int32_t n, int32_t h4, int32_t w4,
+                               const TRef* x_ref, int32_t h_ref, int32_t w_ref, int32_t pad_top, int32_t pad_left,
+                               double* sq_err, int32_t clamp01, void* stream) {
+  if (!in_nhwc64 || !x_hat_nchw || n < 1 || h4 < 1 || w4 < 1) return set_error("synthesis_tail: bad argument");
+  const long long per = static_cast<long long>(h4) * w4;
+  dim3 grid(static_cast<unsigned>(std::min<long long>((per + 255) / 256, 148LL * 16)), n);
+  synthesis_tail_kernel<TRef><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      in_nhwc64, x_hat_nchw, h4, w4, x_ref, h_ref, w_ref, pad_top, pad_left, sq_err, clamp01);
+  CHECK_LAUNCH("synthesis_tail");
+  return 0;
+}
+
 extern "C" int stemb200_synthesis_tail(const float* in_nhwc64, float* x_hat_nchw, int32_t n, int32_t h4,
                                        int32_t w4, const float* x_ref, int32_t h_ref, int32_t w_ref,
                                        int32_t pad_top, int32_t pad_left, double* sq_err, int32_t clamp01,
                                        void* stream) {
-  if (!in_nhwc64 || !x_hat_nchw || n < 1 || h4 < 1 || w4 < 1) return set_error("synthesis_tail: bad argument");
-  const long long per = static_cast<long long>(h4) * w4;
-  dim3 grid(static_cast<unsigned>(std::min<long long>((per + 255) / 256, 148LL * 16)), n);
-  synthesis_tail_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      in_nhwc64, x_hat_nchw, h4, w4, x_ref, h_ref, w_ref, pad_top, pad_left, sq_err, clamp01);
-  CHECK_LAUNCH("synthesis_tail");
-  return 0;
+  return synthesis_tail_impl<float>(in_nhwc64, x_hat_nchw, n, h4, w4, x_ref, h_ref, w_ref, pad_top, pad_left, sq_err,
+                                    clamp01, stream);
+}
+
+extern "C" int stemb200_synthesis_tail_u8(const float* in_nhwc64, float* x_hat_nchw, int32_t n, int32_t h4,
+                                          int32_t w4, const uint8_t* x_ref, int32_t h_ref, int32_t w_ref,
+                                          int32_t pad_top, int32_t pad_left, double* sq_err, int32_t clamp01,
+                                          void* stream) {
+  return synthesis_tail_impl<uint8_t>(in_nhwc64, x_hat_nchw, n, h4, w4, x_ref, h_ref, w_ref, pad_top, pad_left,
+                                      sq_err, clamp01, stream);
 }

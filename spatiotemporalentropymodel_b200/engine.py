@@ -440,9 +440,12 @@ class TransformsEngine:
 
     # -------------------------------------------------------------------------------------------------
     def analysis(self, x: Tensor, pad: Tuple[int, int, int, int] = (0, 0, 0, 0)) -> Tuple[Tensor, int, int]:
-        """x: (B, 3, H, W) fp32 NCHW; pad = (left, right, top, bottom) zero canvas (evalSTEM.py:96-109).
+        """x: (B, 3, H, W) NCHW, fp32 or uint8 (8-bit samples, used as v / 255 like torchvision's ToTensor);
+        pad = (left, right, top, bottom) zero canvas (evalSTEM.py:96-109).
         Returns y as NHWC fp32 (B, h, w, M) plus (h, w)."""
         _require_cuda(x)
+        if x.dtype not in (torch.float32, torch.uint8):
+            raise TypeError(f"analysis: frames must be float32 or uint8, got {x.dtype}")
         x = x.contiguous()
         B, _, H, W = x.shape
         left, right, top, bottom = pad
@@ -452,8 +455,9 @@ class TransformsEngine:
             raise ValueError("analysis needs an even padded frame size")
         border = 2
         canvas = ws.get("ga_canvas", (B * (Hp + 2 * border) * (Wp + 2 * border) * 8 + 64,), torch.float16)
-        _lib.check(lib.stemb200_frame_to_nhwc8(x.data_ptr(), canvas.data_ptr(), B, 3, H, W, Hp, Wp, top, left, border,
-                                               _stream()), "frame_to_nhwc8")
+        stage = lib.stemb200_frame_u8_to_nhwc8 if x.dtype == torch.uint8 else lib.stemb200_frame_to_nhwc8
+        _lib.check(stage(x.data_ptr(), canvas.data_ptr(), B, 3, H, W, Hp, Wp, top, left, border, _stream()),
+                   "frame_to_nhwc8")
         cur, h, w = canvas, Hp, Wp
         for li in range(3):
             conv = self.ga_conv[li]
@@ -476,8 +480,12 @@ class TransformsEngine:
         cur = y_hat16
         left, right, top, bottom = pad
         href = wref = 0
+        ref_u8 = False
         if x_ref is not None:
+            if x_ref.dtype not in (torch.float32, torch.uint8):
+                raise TypeError(f"synthesis: x_ref must be float32 or uint8, got {x_ref.dtype}")
             href, wref = x_ref.shape[2], x_ref.shape[3]
+            ref_u8 = x_ref.dtype == torch.uint8
         for li in range(3):
             ho, wo = 2 * h, 2 * w
             if li == 2 and self.fuse_last:
@@ -485,9 +493,9 @@ class TransformsEngine:
                 self.gs_conv[2].call_last([cur], B, h, w, self.w6, col)
                 if out is None:
                     out = ws.get("gs_xhat", (B, 3, 2 * ho, 2 * wo), torch.float32)
-                _lib.check(lib.stemb200_synthesis_col2im(col.data_ptr(), self.b6.data_ptr(), out.data_ptr(), B, ho, wo,
-                                                         _ptr(x_ref), href, wref, top, left, _ptr(sq_err), int(clamp),
-                                                         _stream()), "synthesis_col2im")
+                c2i = lib.stemb200_synthesis_col2im_u8 if ref_u8 else lib.stemb200_synthesis_col2im
+                _lib.check(c2i(col.data_ptr(), self.b6.data_ptr(), out.data_ptr(), B, ho, wo, _ptr(x_ref), href, wref, top,
+                               left, _ptr(sq_err), int(clamp), _stream()), "synthesis_col2im")
                 return out
             gb = self.gs_conv[li]([cur], B, h, w, ws.get(f"gs_g{li}", (B, ho, wo, N), torch.float16))
             cur, h, w = gb, ho, wo
@@ -497,8 +505,9 @@ class TransformsEngine:
         self.gs_last([cur], B, h, w, merged)
         if out is None:
             out = ws.get("gs_xhat", (B, 3, 2 * h, 2 * w), torch.float32)
-        _lib.check(lib.stemb200_synthesis_tail(merged.data_ptr(), out.data_ptr(), B, h // 2, w // 2, _ptr(x_ref), href,
-                                               wref, top, left, _ptr(sq_err), int(clamp), _stream()), "synthesis_tail")
+        tail = lib.stemb200_synthesis_tail_u8 if ref_u8 else lib.stemb200_synthesis_tail
+        _lib.check(tail(merged.data_ptr(), out.data_ptr(), B, h // 2, w // 2, _ptr(x_ref), href, wref, top, left,
+                        _ptr(sq_err), int(clamp), _stream()), "synthesis_tail")
         return out
 
 
@@ -751,7 +760,7 @@ class PFramePipeline:
         buffer overwritten by the next call. Results are bit-identical to `forward_gop`."""
         if y_cond0.device.type != "cuda":
             raise ValueError("run_gop: y_cond0 must be a CUDA tensor")
-        key = (tuple(frames.shape), tuple(y_cond0.shape), bool(want_outputs))
+        key = (tuple(frames.shape), frames.dtype, tuple(y_cond0.shape), bool(want_outputs))
         st = self._graphed.get(key)
         if st is None:
             st = self._graphed[key] = self._capture(frames, y_cond0, want_outputs)
@@ -776,7 +785,7 @@ class PFramePipeline:
         dev = self.stem.device
         slots = []
         for _ in range(2):
-            fr = torch.empty(tuple(frames.shape), dtype=torch.float32, device=dev)
+            fr = torch.empty(tuple(frames.shape), dtype=frames.dtype, device=dev)
             cd = torch.empty(tuple(y_cond0.shape), dtype=torch.float32, device=dev)
             fr.copy_(frames)
             cd.copy_(y_cond0)
@@ -795,7 +804,8 @@ class PFramePipeline:
         return {"slots": slots, "next": 0, "copy_stream": torch.cuda.Stream(device=dev), "keep": keep}
 
     def forward_gop(self, frames: Tensor, y_cond0: Tensor, want_outputs: bool = True):
-        """frames: (T, 3, H, W) fp32 NCHW CUDA (unpadded); y_cond0: (1, C, h, w) fp32 NCHW (previous decoded
+        """frames: (T, 3, H, W) NCHW CUDA (unpadded), fp32 in [0, 1] or uint8 (8-bit samples, evaluated as v / 255:
+        bit-identical to feeding ToTensor's output, evalSTEM.py:185); y_cond0: (1, C, h, w) fp32 NCHW (previous decoded
         latent). Returns dict with per-frame bits_y, bits_z, sq_err (fp64 device tensors) and, optionally,
         x_hat / y_hat / likelihood tensors."""
         _require_cuda(frames, y_cond0)

@@ -6,6 +6,19 @@ builders produce *calibrated* state_dicts with exactly the reference's key set /
 (`SpatioTemporalPriorModel*.state_dict()` and `models["mbt2018"](quality=4).state_dict()`) from a
 seed, so that the reference classes (tests/golden/make_golden.py), the oracle and the CUDA path all load the same
 weights without any weight file being stored.  CPU `torch.Generator` streams are platform independent.
+
+Two calibrations exist (argument ``calibration``):
+
+* ``"default"``  - dense random weights with gains chosen so that activations stay O(1) and sigma covers the whole
+  scale table.  Every tap / channel carries weight, but the operating point is far from a trained codec's: 16-18 % of
+  the y likelihoods sit on the 1e-9 floor, x_hat is unrelated to x (PSNR ~9 dB) and 8 % of its pixels are clamped.
+* ``"lowrate"``  - an analytic auto-encoder (space-to-depth analysis, 2x2 pooling bottleneck with per-channel
+  quantisation step, mirrored synthesis, GDN / IGDN pairs that invert each other to first order) plus a small dense
+  random part in every layer, and an entropy model whose means follow the latent (identity routes through TPM, the
+  hyperprior and the causal context into EPM) with scales proportional to the channel's quantisation gain.  This
+  puts the path where a trained model operates - PSNR ~30 dB, < 1 % floored likelihoods, < 1 % clamped pixels,
+  latents with a large predictable DC part - which is where the parity gates (bpp 0.5 %, PSNR 0.01 dB) have teeth:
+  an error in sigma / mu moves every likelihood, and an error in x_hat is not buried under a 9 dB reconstruction.
 """
 from __future__ import annotations
 
@@ -19,6 +32,7 @@ import torch.nn.functional as F
 Tensor = torch.Tensor
 
 _PEDESTAL = (2.0 ** -18) ** 2
+CALIBRATIONS = ("default", "lowrate")
 
 
 def _u(g, shape, bound):
@@ -83,8 +97,155 @@ def _mask_a(cout, cin, k=5):
     return m
 
 
-def make_iframe_state_dict(seed: int = 0, N: int = 192, M: int = 192) -> Dict[str, Tensor]:
+# ----------------------------------------------------------------------------------------------------
+# "lowrate" calibration: analytic auto-encoder + identity routes for the means (module docstring)
+# ----------------------------------------------------------------------------------------------------
+LOWRATE_GAIN_RANGE = (6.0, 64.0)   # quantisation gain of a latent channel: y_c = g_c * (2x2-pooled pixel) + ...
+LOWRATE_PIX_RMS = 0.55             # rms of a pixel value of make_frames()
+
+
+def lowrate_gains(seed: int = 0, C: int = 192) -> Tensor:
+    """Per-channel quantisation gains g_c (log-spaced over LOWRATE_GAIN_RANGE, shuffled); shared by the transforms
+    and the entropy model of one seed."""
+    g = torch.Generator().manual_seed(3000 + seed)
+    lo, hi = LOWRATE_GAIN_RANGE
+    vals = torch.exp(torch.linspace(math.log(lo), math.log(hi), C))
+    return vals[torch.randperm(C, generator=g)]
+
+
+def _rand(g, cout, cin, k, gain, in_scale=None, transposed=False):
+    """Dense random block: uniform, variance gain^2 / fan_in, optionally scaled per input channel."""
+    bound = gain * math.sqrt(3.0 / (cin * k * k))
+    w = _u(g, (cout, cin, k, k), bound)
+    if in_scale is not None:
+        w = w * in_scale.reshape(1, cin, 1, 1)
+    return w.permute(1, 0, 2, 3).contiguous() if transposed else w
+
+
+def _gdn_lowrate(sd, g, name, c, like: str = ""):
+    if like:  # IGDN that undoes GDN `like` to first order: same beta / gamma
+        for k in ("beta", "gamma", "beta_reparam.pedestal", "beta_reparam.lower_bound.bound", "gamma_reparam.pedestal",
+                  "gamma_reparam.lower_bound.bound"):
+            sd[f"{name}.{k}"] = sd[f"{like}.{k}"].clone()
+        return
+    beta = 1.0 + 0.1 * torch.rand(c, generator=g)
+    gamma = 0.05 * torch.eye(c) + 0.002 * torch.rand((c, c), generator=g)
+    ped = torch.tensor([_PEDESTAL], dtype=torch.float32)
+    sd[f"{name}.beta"] = torch.sqrt(torch.max(beta + ped, ped))
+    sd[f"{name}.gamma"] = torch.sqrt(torch.max(gamma + ped, ped))
+    sd[f"{name}.beta_reparam.pedestal"] = ped.clone()
+    sd[f"{name}.beta_reparam.lower_bound.bound"] = torch.tensor([(1e-6 + _PEDESTAL) ** 0.5], dtype=torch.float32)
+    sd[f"{name}.gamma_reparam.pedestal"] = ped.clone()
+    sd[f"{name}.gamma_reparam.lower_bound.bound"] = torch.tensor([_PEDESTAL ** 0.5], dtype=torch.float32)
+
+
+def _lowrate_transforms(sd, g, seed: int, N: int, eps: float = 0.015) -> None:
+    """g_a = 2x2 mean pooling (3 channels) + 3 x space-to-depth (3 -> 12 -> 48 -> 192 channels), the last one times
+    the channel's gain g_c; g_s = 3 x depth-to-space (the first one divided by g_c) + nearest 2x up-sampling;
+    GDN k of g_a and IGDN k of g_s share their parameters. Every layer also has a dense random part of relative
+    size ~eps."""
+    gains = lowrate_gains(seed, N)
+    n_act = [3, 3, 12, 48, 192]  # channels that carry the image after layer k
+    # analysis: Conv2d(k5, s2, p2): out[i][j] = sum w[r][s] x[2i-2+r][2j-2+s]; tap (2+dy, 2+dx) reads pixel (2i+dy, 2j+dx)
+    for li, name in enumerate(("g_a.0", "g_a.2", "g_a.4", "g_a.6")):
+        cin = 3 if li == 0 else N
+        w = _rand(g, N, cin, 5, eps * math.sqrt(cin / n_act[li]))   # only n_act[li] input channels carry signal
+        b = _u(g, (N,), 0.01)
+        if li == 0:
+            for c in range(3):
+                w[c, c, 2:4, 2:4] += 0.25
+        else:
+            for c in range(n_act[li]):
+                for d in range(4):
+                    w[c * 4 + d, c, 2 + d // 2, 2 + d % 2] += 1.0
+        if li == 3:
+            w, b = w * gains.reshape(N, 1, 1, 1), b * gains
+        else:
+            _gdn_lowrate(sd, g, f"g_a.{2 * li + 1}", N)
+        sd[f"{name}.weight"], sd[f"{name}.bias"] = w, b
+    # synthesis: ConvTranspose2d(k5, s2, p2, op1): out[2i-2+r][2j-2+s] += in[i][j] w[r][s]; weight (in, out, kh, kw)
+    for li, name in enumerate(("g_s.0", "g_s.2", "g_s.4", "g_s.6")):
+        cout = 3 if li == 3 else N
+        act_in = n_act[4 - li]
+        w = _rand(g, cout, N, 5, 2 * eps * math.sqrt(N / act_in), transposed=True)
+        if li == 3:
+            for c in range(3):
+                w[c, c, 2:4, 2:4] += 1.0
+        else:
+            for c in range(n_act[3 - li]):
+                for d in range(4):
+                    w[c * 4 + d, c, 2 + d // 2, 2 + d % 2] += 1.0
+        if li == 0:
+            w = w / gains.reshape(N, 1, 1, 1)
+        sd[f"{name}.weight"], sd[f"{name}.bias"] = w, _u(g, (cout,), 0.01)
+        if li < 3:
+            _gdn_lowrate(sd, g, f"g_s.{2 * li + 1}", N, like=f"g_a.{5 - 2 * li}")
+
+
+def _t_gdn(x, sd, name, inverse):
+    beta = torch.clamp_min(sd[f"{name}.beta"], (1e-6 + _PEDESTAL) ** 0.5) ** 2 - _PEDESTAL
+    gamma = torch.clamp_min(sd[f"{name}.gamma"], _PEDESTAL ** 0.5) ** 2 - _PEDESTAL
+    norm = F.conv2d(x * x, gamma.reshape(*gamma.shape, 1, 1), beta)
+    return x * (torch.sqrt(norm) if inverse else torch.rsqrt(norm))
+
+
+def _t_analysis(x, sd):
+    for i in (0, 2, 4, 6):
+        x = F.conv2d(x, sd[f"g_a.{i}.weight"], sd[f"g_a.{i}.bias"], stride=2, padding=2)
+        if i < 6:
+            x = _t_gdn(x, sd, f"g_a.{i + 1}", False)
+    return x
+
+
+def _t_synthesis(y, sd):
+    for i in (0, 2, 4, 6):
+        y = F.conv_transpose2d(y, sd[f"g_s.{i}.weight"], sd[f"g_s.{i}.bias"], stride=2, padding=2, output_padding=1)
+        if i < 6:
+            y = _t_gdn(y, sd, f"g_s.{i + 1}", True)
+    return y
+
+
+def _lowrate_refit(sd, seed: int, N: int, iters: int = 4) -> None:
+    """Make the synthetic decoder behave like a trained one in the respect that matters for the PSNR gate: an
+    MSE-trained model sits at a stationary point of its loss - d MSE / d (any weight) = 0 - so rounding its weights to
+    fp16 changes the PSNR only in second order.  The analytic auto-encoder above is not at such a point (its GDN / IGDN
+    pairs invert each other only approximately: E[x_hat (x_hat - x)] is twice the MSE), which would turn the 0.01 dB
+    gate into a test of weight-rounding luck.  A few least-squares passes on seeded calibration frames fix the part
+    that matters: per latent channel c (= one pixel position of the 8 x 8 x 3 block) the gain a_c that minimises
+    |x - a_c x_hat|^2 is folded into the rows of the first synthesis layer that read channel c, which makes the error
+    orthogonal to the reconstruction channel by channel.  Plain torch CPU ops on the state_dict being built
+    (checkpoint synthesis, not the product's compute path)."""
+    lo, hi = LOWRATE_FRAME_RANGE
+    frames = make_frames(3, 128, 256, seed=77000 + seed, lo=lo, hi=hi)
+
+    def to_channels(img):  # (B, 3, H, W) -> (192, samples); pixel_unshuffle's channel order c * 4 + dy * 2 + dx is
+        t = F.avg_pool2d(img, 2)  # the order of the space-to-depth layers; the route is constant inside a 2x2 block
+        for _ in range(3):
+            t = F.pixel_unshuffle(t, 2)
+        return t.permute(1, 0, 2, 3).reshape(N, -1)
+
+    with torch.no_grad():
+        y_hat = torch.round(_t_analysis(frames, sd))
+        xc = to_channels(frames)
+        for _ in range(iters):
+            hc = to_channels(_t_synthesis(y_hat, sd))
+            a = (xc * hc).sum(1) / (hc * hc).sum(1).clamp_min(1e-12)
+            sd["g_s.0.weight"] = sd["g_s.0.weight"] * a.reshape(N, 1, 1, 1)   # (in, out, kh, kw): rows of input channel c
+
+
+def make_iframe_state_dict(seed: int = 0, N: int = 192, M: int = 192, calibration: str = "default") -> Dict[str, Tensor]:
     """Key set of JointAutoregressiveHierarchicalPriors(N, M) (priors.py:418-475), i.e. models["mbt2018"](4)."""
+    if calibration not in CALIBRATIONS:
+        raise ValueError(f"unknown calibration {calibration!r}")
+    if calibration == "lowrate":
+        if N != 192 or M != 192:
+            raise ValueError("the lowrate calibration is built for N = M = 192 (8 x 8 x 3 space-to-depth)")
+        ref = make_iframe_state_dict(seed, N, M)  # hyper / context nets and key order as in the default one
+        g = torch.Generator().manual_seed(1500 + seed)
+        tr: Dict[str, Tensor] = {}
+        _lowrate_transforms(tr, g, seed, N)
+        _lowrate_refit(tr, seed, N)
+        return {k: tr.get(k, v) for k, v in ref.items()}
     g = torch.Generator().manual_seed(1000 + seed)
     sd: Dict[str, Tensor] = {}
     _entropy_bottleneck(sd, g, "entropy_bottleneck", N)
@@ -138,9 +299,145 @@ def variant_flags(variant: str) -> Tuple[bool, bool, bool]:
     return has_tpm, has_spm, variant == "SpatioTemporalPriorModel_Res"
 
 
+def _make_stem_lowrate(variant: str, seed: int) -> Dict[str, Tensor]:
+    """Entropy model matched to the lowrate transforms: mu_c = a * TPM route (y_cond_c) + b * hyperprior route
+    (4x4-pooled y_c, quantised in z) + d * context route (mean of the left and upper neighbour of y_hat_c), through
+    identity blocks of TPM / HE / HD / context_prediction / EPM (all route values are positive, so LeakyReLU passes
+    them unchanged), sigma_c = s_c * (1 + dense random features), s_c proportional to the channel's gain; every
+    layer keeps dense random rows next to the routes. _Res codes y - y_cond, whose mean is ~0: no mean routes."""
+    has_tpm, has_spm, res = variant_flags(variant)
+    C, R = 192, 192                      # latent channels, route width
+    g = torch.Generator().manual_seed(2500 + seed)
+    gains = lowrate_gains(seed, C)
+    y_norm = 1.0 / (LOWRATE_PIX_RMS * gains)       # scales a latent channel to rms ~1 for the random rows
+    s0 = (0.06 if has_tpm else 0.2) * gains        # sigma level: std of y - mu (temporal route: ~0.06 g)
+    kappa = 0.5 / (0.06 * gains)                   # z_c = kappa_c * pooled y_c: |z| ~ 4
+    sd: Dict[str, Tensor] = {}
+    zc = 256
+    _entropy_bottleneck(sd, g, "entropy_bottleneck", zc)
+    ones = torch.ones
+
+    def put(name, w, b=None, transposed=False):
+        sd[f"{name}.weight"] = w
+        sd[f"{name}.bias"] = _u(g, (w.shape[1 if transposed else 0],), 0.1) if b is None else b
+
+    def zero_route_bias(name):
+        sd[f"{name}.bias"][:R] = 0.0
+
+    if has_tpm:
+        w = _rand(g, 256, C, 5, 1.4, in_scale=y_norm)
+        w[:R] = 0
+        for c in range(R):
+            w[c, c, 2, 2] = 1.0
+        put("TPM.0", w)
+        zero_route_bias("TPM.0")
+        w = _rand(g, 320, 256, 5, 1.4, in_scale=torch.cat([y_norm, ones(64)]))
+        w[:R] = 0
+        for c in range(R):
+            w[c, c, 2, 2] = 1.0
+        put("TPM.2", w)
+        zero_route_bias("TPM.2")
+        w = _rand(g, 2 * C, 320, 5, 1.4, in_scale=torch.cat([y_norm, ones(128)]))
+        w[C:] = 0
+        for c in range(R):
+            w[C + c, c, 2, 2] = 1.0
+        put("TPM.4", w)
+        sd["TPM.4.bias"][C:] = 0.0
+    # hyper-encoder: route = y_cur -> 2x2 mean -> 2x2 mean * kappa
+    w = _rand(g, 256, 2 * C, 3, 1.4, in_scale=torch.cat([y_norm, y_norm]))
+    w[:R] = 0
+    for c in range(R):
+        w[c, c, 1, 1] = 1.0
+    put("HE.0", w)
+    zero_route_bias("HE.0")
+    w = _rand(g, 256, 256, 5, 1.4, in_scale=torch.cat([y_norm, ones(64)]))
+    w[:R] = 0
+    for c in range(R):
+        w[c, c, 2:4, 2:4] = 0.25
+    put("HE.2", w)
+    zero_route_bias("HE.2")
+    w = _rand(g, zc, 256, 5, 2.0, in_scale=torch.cat([y_norm, ones(64)]))
+    w[:R] = 0
+    for c in range(R):
+        w[c, c, 2:4, 2:4] = 0.25 * kappa[c]
+    put("HE.4", w)
+    zero_route_bias("HE.4")
+    # hyper-decoder: route = z_hat / kappa, nearest 4x up-sampling
+    z_norm = torch.cat([torch.full((R,), 0.25), ones(zc - R) * 0.5])
+    w = _rand(g, 256, zc, 5, 2 * 1.4, in_scale=z_norm, transposed=True)   # (in, out, kh, kw)
+    w[:, :R] = 0
+    for c in range(R):
+        w[c, c, 2:4, 2:4] = 1.0 / kappa[c]
+    put("HD.0", w, transposed=True)
+    zero_route_bias("HD.0")
+    w = _rand(g, 256, 256, 5, 2 * 1.4, in_scale=torch.cat([y_norm, ones(64)]), transposed=True)
+    w[:, :R] = 0
+    for c in range(R):
+        w[c, c, 2:4, 2:4] = 1.0
+    put("HD.2", w, transposed=True)
+    zero_route_bias("HD.2")
+    w = _rand(g, 2 * C, 256, 3, 1.4, in_scale=torch.cat([y_norm, ones(64)]))
+    w[C:] = 0
+    for c in range(R):
+        w[C + c, c, 1, 1] = 1.0
+    put("HD.4", w)
+    sd["HD.4.bias"][C:] = 0.0
+    if has_spm:
+        # context input: y_hat (rms ~ 0.55 g) or, for _Res, round(y - y_cond) (rms ~ 0.06 g)
+        w = _rand(g, 2 * C, C, 5, 1.4 * math.sqrt(25.0 / 12.0), in_scale=(1.0 / (0.08 * gains)) if res else y_norm)
+        w[C:] = 0
+        if not res:
+            for c in range(R):
+                w[C + c, c, 2, 1] = 0.5   # left neighbour
+                w[C + c, c, 1, 2] = 0.5   # upper neighbour
+        put("context_prediction", w)
+        sd["context_prediction.bias"][C:] = 0.0
+        sd["context_prediction.mask"] = _mask_a(2 * C, C)
+    # EPM.0: cat order tp | hp | ctx (each: C random features, then C route channels)
+    parts = (["tp"] if has_tpm else []) + ["hp"] + (["ctx"] if has_spm else [])
+    mix = {("tp", "hp", "ctx"): (0.8, 0.1, 0.1), ("tp", "hp"): (0.9, 0.1), ("hp", "ctx"): (0.5, 0.5), ("hp",): (1.0,)}[
+        tuple(parts)]
+    if res:
+        mix = tuple(0.0 for _ in mix)
+    n_prior = 2 * C * len(parts)
+    w = _rand(g, 768, n_prior, 1, 1.4, in_scale=torch.cat([torch.cat([ones(C), y_norm]) for _ in parts]))
+    w[:R] = 0
+    for k, a in enumerate(mix):
+        for c in range(R):
+            w[c, k * 2 * C + C + c, 0, 0] = a
+    put("EPM.0", w)
+    zero_route_bias("EPM.0")
+    w = _rand(g, 576, 768, 1, 1.4, in_scale=torch.cat([y_norm, ones(768 - R)]))
+    w[:R] = 0
+    for c in range(R):
+        w[c, c, 0, 0] = 1.0
+    put("EPM.2", w)
+    zero_route_bias("EPM.2")
+    # EPM.4: rows [0, C) = scales, [C, 2C) = means; random parts read the 384 dense features only
+    w = _rand(g, 2 * C, 576, 1, 1.0, in_scale=torch.cat([torch.zeros(R), ones(576 - R)]))
+    w[:C] *= (0.25 * s0).reshape(C, 1, 1, 1)
+    w[C:] *= (0.30 * s0).reshape(C, 1, 1, 1)
+    for c in range(R):
+        w[C + c, c, 0, 0] = 1.0
+    b = torch.zeros(2 * C)
+    b[:C] = s0
+    put("EPM.4", w, b)
+    _gaussian_conditional(sd)
+    return sd
+
+
 def make_stem_state_dict(variant: str = "SpatioTemporalPriorModel", seed: int = 0, in_channels: int = 192,
-                         eb_channels: int = 256) -> Dict[str, Tensor]:
+                         eb_channels: int = 256, calibration: str = "default") -> Dict[str, Tensor]:
     """Key set of the five classes in compressai/models/spatiotemporalpriors.py (ctor :516)."""
+    if calibration not in CALIBRATIONS:
+        raise ValueError(f"unknown calibration {calibration!r}")
+    if calibration == "lowrate":
+        if in_channels != 192 or eb_channels != 256:
+            raise ValueError("the lowrate calibration is built for 192 latent / 256 hyper-latent channels")
+        low = _make_stem_lowrate(variant, seed)
+        ref = make_stem_state_dict(variant, seed, in_channels, eb_channels)   # key order / shapes of the default one
+        assert set(low) == set(ref) and all(low[k].shape == ref[k].shape for k in ref)
+        return {k: low[k] for k in ref}
     has_tpm, has_spm, _ = variant_flags(variant)
     g = torch.Generator().manual_seed(2000 + seed)
     C = in_channels
@@ -172,9 +469,10 @@ def make_stem_state_dict(variant: str = "SpatioTemporalPriorModel", seed: int = 
     return sd
 
 
-def make_frames(n_frames: int, height: int, width: int, seed: int = 1234) -> Tensor:
+def make_frames(n_frames: int, height: int, width: int, seed: int = 1234, lo: float = 0.0, hi: float = 1.0) -> Tensor:
     """Smooth, temporally correlated frames in [0, 1]: bicubic-upsampled noise, shifted per
-    frame, plus 0.02 sigma noise. Returns (n_frames, 3, H, W) fp32."""
+    frame, plus 0.02 sigma noise. Returns (n_frames, 3, H, W) fp32. (lo, hi) compresses the range (a frame without
+    clipped blacks / whites, used with the lowrate calibration)."""
     g = torch.Generator().manual_seed(seed)
     hb, wb = max(height // 16, 2), max(width // 16, 2)
     base = F.interpolate(torch.rand((1, 3, hb, wb), generator=g), size=(height, width), mode="bicubic",
@@ -184,7 +482,11 @@ def make_frames(n_frames: int, height: int, width: int, seed: int = 1234) -> Ten
         f = torch.roll(base, shifts=(t, 2 * t), dims=(2, 3))
         f = (f + 0.02 * torch.randn(f.shape, generator=g)).clamp(0, 1)
         frames.append(f)
-    return torch.cat(frames, 0)
+    out = torch.cat(frames, 0)
+    return out if (lo, hi) == (0.0, 1.0) else lo + (hi - lo) * out
+
+
+LOWRATE_FRAME_RANGE = (0.08, 0.92)
 
 
 def make_latent(n: int, c: int, h: int, w: int, seed: int = 4321, std: float = 3.0) -> Tensor:

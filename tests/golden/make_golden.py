@@ -53,40 +53,53 @@ def main():
     torch.manual_seed(0)
 
     # ---------------------------------------------------------------- I-frame transforms + STEM variants
-    sd_i = S.make_iframe_state_dict(seed=0)
-    iframe = ref_models["mbt2018"](quality=4)
-    iframe.load_state_dict(sd_i)
-    iframe.update(force=True)
-    iframe.eval()
-    with torch.no_grad():
-        for variant in S.STEM_VARIANTS:
-            size = 256 if variant == "SpatioTemporalPriorModel" else 128
-            frames = S.make_frames(2, size, size, seed=1234)
-            y0, _ = iframe.getY(frames[0:1])
-            y_cond = torch.round(y0)  # stand-in for the I-frame codec's decoded latent
-            y_cur, _ = iframe.getY(frames[1:2])
-            sd_s = S.make_stem_state_dict(variant, seed=0)
-            stem = getattr(ref_stem, variant)()
-            stem.load_state_dict(sd_s)
-            stem.update(force=True)
-            stem.eval()
-            out = stem(y_cur, y_cond)
-            rec = {
-                "y_cur": y_cur.numpy(), "y_cond": y_cond.numpy(), "y_hat": out["y_hat"].numpy(),
-                "lik_y": out["likelihoods"]["y"].numpy(), "lik_z": out["likelihoods"]["z"].numpy(),
-            }
-            if variant == "SpatioTemporalPriorModel":
+    # two synthetic checkpoints (synthetic.py): "default" -> stem_<variant>.npz, "lowrate" -> stem_lowrate_<variant>.npz
+    for calibration in S.CALIBRATIONS:
+        sd_i = S.make_iframe_state_dict(seed=0, calibration=calibration)
+        iframe = ref_models["mbt2018"](quality=4)
+        iframe.load_state_dict(sd_i)
+        iframe.update(force=True)
+        iframe.eval()
+        tag = "" if calibration == "default" else f"{calibration}_"
+        rng = (0.0, 1.0) if calibration == "default" else S.LOWRATE_FRAME_RANGE
+        with torch.no_grad():
+            for variant in S.STEM_VARIANTS:
+                size = 256 if variant == "SpatioTemporalPriorModel" else 128
+                frames = S.make_frames(2, size, size, seed=1234, lo=rng[0], hi=rng[1])
+                y0, _ = iframe.getY(frames[0:1])
+                y_cond = torch.round(y0)  # stand-in for the I-frame codec's decoded latent
+                y_cur, _ = iframe.getY(frames[1:2])
+                sd_s = S.make_stem_state_dict(variant, seed=0, calibration=calibration)
+                stem = getattr(ref_stem, variant)()
+                stem.load_state_dict(sd_s)
+                stem.update(force=True)
+                stem.eval()
+                out = stem(y_cur, y_cond)
+                rec = {
+                    "y_cur": y_cur.numpy(), "y_cond": y_cond.numpy(), "y_hat": out["y_hat"].numpy(),
+                    "lik_y": out["likelihoods"]["y"].numpy(), "lik_z": out["likelihoods"]["z"].numpy(),
+                }
                 x_hat = iframe.getX(out["y_hat"])
-                rec["x_hat"] = x_hat.numpy()
-                rec["gc_quantized_cdf"] = stem.gaussian_conditional._quantized_cdf.numpy()
-                rec["gc_offset"] = stem.gaussian_conditional._offset.numpy()
-                rec["gc_cdf_length"] = stem.gaussian_conditional._cdf_length.numpy()
-                rec["eb_quantized_cdf"] = stem.entropy_bottleneck._quantized_cdf.numpy()
-                rec["eb_offset"] = stem.entropy_bottleneck._offset.numpy()
-                rec["eb_cdf_length"] = stem.entropy_bottleneck._cdf_length.numpy()
-            np.savez_compressed(os.path.join(OUT, f"stem_{variant}.npz"), **rec)
-            bits = float((-torch.log2(out["likelihoods"]["y"])).sum() + (-torch.log2(out["likelihoods"]["z"])).sum())
-            print(f"{variant}: size {size}, bpp {bits / (size * size):.4f}")
+                if variant == "SpatioTemporalPriorModel":
+                    rec["x_hat"] = x_hat.numpy()
+                if variant == "SpatioTemporalPriorModel" and calibration == "default":
+                    rec["gc_quantized_cdf"] = stem.gaussian_conditional._quantized_cdf.numpy()
+                    rec["gc_offset"] = stem.gaussian_conditional._offset.numpy()
+                    rec["gc_cdf_length"] = stem.gaussian_conditional._cdf_length.numpy()
+                    rec["eb_quantized_cdf"] = stem.entropy_bottleneck._quantized_cdf.numpy()
+                    rec["eb_offset"] = stem.entropy_bottleneck._offset.numpy()
+                    rec["eb_cdf_length"] = stem.entropy_bottleneck._cdf_length.numpy()
+                if calibration != "default":
+                    # evalSTEM.py:127-136 statistics of this frame, as the reference computes them
+                    mse = float(((frames[1:2] - x_hat) ** 2).mean())
+                    rec["psnr"] = np.float64(-10 * np.log10(mse))
+                np.savez_compressed(os.path.join(OUT, f"stem_{tag}{variant}.npz"), **rec)
+                ly, lz = out["likelihoods"]["y"], out["likelihoods"]["z"]
+                bits = float((-torch.log2(ly)).sum() + (-torch.log2(lz)).sum())
+                mse = float(((frames[1:2] - x_hat) ** 2).mean())
+                print(f"[{calibration}] {variant}: size {size}, bpp {bits / (size * size):.4f}, PSNR "
+                      f"{-10 * np.log10(mse):.2f} dB, floored y likelihoods {float((ly <= 1.0001e-9).float().mean()):.4f}, "
+                      f"clamped x_hat pixels {float(((x_hat <= 0) | (x_hat >= 1)).float().mean()):.4f}")
 
     # ---------------------------------------------------------------- stem_roi (a13)
     from compressai.models.stem_roi import stem_roi as ref_stem_roi

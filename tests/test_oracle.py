@@ -80,25 +80,59 @@ def test_pmf_to_quantized_cdf_kat(golden):
     assert O.pmf_to_quantized_cdf([1e-9, 0.5, 0.5, 1e-9]).tolist() == [0, 1, 32767, 65535, 65536]
 
 
+CAL_TAG = {"default": "", "lowrate": "lowrate_"}
+
+
+@pytest.mark.parametrize("calibration", S.CALIBRATIONS)
 @pytest.mark.parametrize("variant", S.STEM_VARIANTS)
-def test_stem_forward_matches_reference(golden, variant):
-    g = golden(f"stem_{variant}.npz")
-    sd = S.make_stem_state_dict(variant, seed=0)
+def test_stem_forward_matches_reference(golden, variant, calibration):
+    g = golden(f"stem_{CAL_TAG[calibration]}{variant}.npz")
+    sd = S.make_stem_state_dict(variant, seed=0, calibration=calibration)
     out = O.stem_forward(variant, t(g["y_cur"]), t(g["y_cond"]), sd)
     assert torch.equal(out["y_hat"], t(g["y_hat"]))
     assert torch.allclose(out["likelihoods"]["y"], t(g["lik_y"]), rtol=1e-5, atol=0)
     assert torch.allclose(out["likelihoods"]["z"], t(g["lik_z"]), rtol=1e-5, atol=0)
 
 
-def test_transforms_match_reference(golden):
-    g = golden("stem_SpatioTemporalPriorModel.npz")
-    sd_i = S.make_iframe_state_dict(seed=0)
-    frames = S.make_frames(2, 256, 256, seed=1234)
+@pytest.mark.parametrize("calibration", S.CALIBRATIONS)
+def test_transforms_match_reference(golden, calibration):
+    g = golden(f"stem_{CAL_TAG[calibration]}SpatioTemporalPriorModel.npz")
+    sd_i = S.make_iframe_state_dict(seed=0, calibration=calibration)
+    lo, hi = (0.0, 1.0) if calibration == "default" else S.LOWRATE_FRAME_RANGE
+    frames = S.make_frames(2, 256, 256, seed=1234, lo=lo, hi=hi)
     y = O.g_a(frames[1:2], sd_i)
-    assert torch.allclose(y, t(g["y_cur"]), rtol=1e-5, atol=1e-5)
-    assert torch.equal(torch.round(O.g_a(frames[0:1], sd_i)), t(g["y_cond"]))
+    assert torch.allclose(y, t(g["y_cur"]), rtol=1e-5, atol=2e-5)
+    y0 = O.g_a(frames[0:1], sd_i)
+    ties = (y0 - torch.floor(y0) - 0.5).abs() < 1e-4     # a latent within 1e-4 of a rounding tie may flip across builds
+    assert torch.equal(torch.round(y0)[~ties], t(g["y_cond"])[~ties]) and float(ties.float().mean()) < 1e-3
     x_hat = O.g_s(t(g["y_hat"]), sd_i)
     assert torch.allclose(x_hat, t(g["x_hat"]), rtol=1e-5, atol=1e-5)
+    if calibration == "lowrate":
+        mse = float(((frames[1:2] - x_hat) ** 2).mean())
+        assert abs(-10 * np.log10(mse) - float(g["psnr"])) < 1e-3
+
+
+def test_lowrate_calibration_operating_point(golden):
+    """The second synthetic checkpoint must sit where the parity gates can see errors:
+    < 1 % of the y likelihoods on the 1e-9 floor (and < 5 % of the bits from floored elements), < 1 % of the
+    reconstructed pixels clamped, PSNR in the range of a trained codec, |y - mu| of the order of sigma."""
+    for variant in S.STEM_VARIANTS:
+        g = golden(f"stem_lowrate_{variant}.npz")
+        ly = t(g["lik_y"]).double()
+        floored = ly <= 1.0001e-9
+        bits = -torch.log2(ly)
+        assert float(floored.float().mean()) < 0.01, variant
+        assert float(bits[floored].sum() / bits.sum()) < 0.05, variant
+        assert 20.0 < float(g["psnr"]) < 40.0, variant
+        sd = S.make_stem_state_dict(variant, seed=0, calibration="lowrate")
+        out = O.stem_forward(variant, t(g["y_cur"]), t(g["y_cond"]), sd, return_params=True)
+        target = t(g["y_cur"]) - t(g["y_cond"]) if variant.endswith("_Res") else t(g["y_cur"])
+        r = (target - out["means"]) / out["scales"].clamp_min(0.11)
+        assert 0.5 < float(r.std()) < 1.5, variant
+        assert float(out["scales"].std() / out["scales"].mean()) > 0.3, variant   # sigma really varies
+    g = golden("stem_lowrate_SpatioTemporalPriorModel.npz")
+    x_hat = t(g["x_hat"])
+    assert float(((x_hat <= 0) | (x_hat >= 1)).float().mean()) < 0.01
 
 
 def test_cdf_tables_match_reference(golden):
