@@ -1534,8 +1534,11 @@ int build_plan(const stemb200_conv_desc& d, Plan& pl) {
   if (!d.direct_store && (d.c_out % 64) && d.c_out != 160 && d.c_out != 320)
     return set_error("conv: the TMA-store epilogue needs c_out % 64 == 0 (or c_out == 160)");
   if (d.epilogue < 0 || d.epilogue > 2) return set_error("conv: bad epilogue");
-  if (d.epilogue != STEMB200_EPI_LINEAR && (d.direct_store || d.out_dtype != STEMB200_DT_F16))
-    return set_error("conv: SFT / residual epilogues write fp16 through the TMA store path");
+  if (d.epilogue != STEMB200_EPI_LINEAR && d.direct_store)
+    return set_error("conv: SFT / residual epilogues store through the TMA path");
+  // the residual epilogue may write fp32 (acc + bias + fp16 residual, not rounded: tensors that feed quantisation)
+  if (d.epilogue == STEMB200_EPI_SFT && d.out_dtype != STEMB200_DT_F16)
+    return set_error("conv: the SFT epilogue writes fp16");
   if (d.epilogue == STEMB200_EPI_SFT) {
     pl.block_n = d.c_out % 256 == 0 ? 256 : (d.c_out % 128 == 0 ? 128 : 0);
     if (!pl.block_n) return set_error("conv: SFT epilogue needs c_out (= 2 x channels) % 128 == 0");

@@ -141,17 +141,15 @@ class stem_roi(CompressionModel):  # noqa: N801 (reference class name)
         """stem_roi.py:645-661 -> {"strings": [y_strings, z_strings], "shape": z.size()[-2:]}"""
         from .engine import nchw_to_nhwc_f16, nhwc_f32_to_nchw
         eng = self.engine()
-        y16, yc16, z32, (B, h, w) = eng.latents(x_cur, x_conditioned, Qmap)
+        y32, yc16, z32, (B, h, w) = eng.latents(x_cur, x_conditioned, Qmap)
         dev = eng.device
         z = nhwc_f32_to_nchw(z32, torch.empty((B, 256, h // 4, w // 4), device=dev))
         z_strings = self.entropy_bottleneck.compress(z)
         z_hat = self.entropy_bottleneck.decompress(z_strings, z.size()[-2:])
         zhat16 = nchw_to_nhwc_f16(z_hat.contiguous(), eng._buf("zhat16", (B, h // 4, w // 4, 256)))
         params = eng.gaussian_params(zhat16, yc16, B, h, w)
-        y32 = eng._buf("y32", (B, h, w, eng.C), torch.float32)
         lib = _lib.load()
         st = torch.cuda.current_stream().cuda_stream
-        _lib.check(lib.stemb200_cast_f16_to_f32(y16.data_ptr(), y32.data_ptr(), y16.numel(), st), "cast")
         idx = torch.empty((B, eng.C, h, w), dtype=torch.int32, device=dev)
         sym = torch.empty((B, eng.C, h, w), dtype=torch.int32, device=dev)
         table = self.gaussian_conditional.scale_table.to(dev, torch.float32).contiguous()
@@ -225,20 +223,23 @@ class _SftLayer:
 class _SftResblk:
     """SFTResblk.forward (stem_utils.py:55-63): x + conv_1(lrelu(SFT_1(conv_0(lrelu(SFT_0(x)))))), slope 0.2."""
 
-    def __init__(self, g, name: str, x_nc: int, prior_nc: int):
+    def __init__(self, g, name: str, x_nc: int, prior_nc: int, out_f32: bool = False):
+        """out_f32: the block's result x + dx leaves the residual epilogue as fp32 (not rounded to fp16): used for the
+        blocks that produce y and z, the tensors that are quantised (stem_roi.py:537, :578)."""
         self.n0 = _SftLayer(g, f"{name}.norm_0", x_nc, prior_nc, slope=0.2)
         self.n1 = _SftLayer(g, f"{name}.norm_1", x_nc, prior_nc, slope=0.2)
         self.c0 = ConvOp(g(f"{name}.conv_0.weight"), g(f"{name}.conv_0.bias"), c_in=[x_nc], c_out=x_nc, k=3)
         self.c1 = ConvOp(g(f"{name}.conv_1.weight"), g(f"{name}.conv_1.bias"), c_in=[x_nc], c_out=x_nc, k=3,
-                         epilogue=EPI_ADD)
+                         epilogue=EPI_ADD, out_dtype=DT_F32 if out_f32 else DT_F16)
         self.x_nc = x_nc
+        self.out_dtype = torch.float32 if out_f32 else torch.float16
 
     def __call__(self, ws: Workspace, tag: str, x: Tensor, q: Tensor, B: int, h: int, w: int) -> Tensor:
         f16 = torch.float16
         t = self.n0(ws, f"{tag}_n0", x, q, B, h, w)
         t = self.c0([t], B, h, w, ws.get(f"{tag}_c0", (B, h, w, self.x_nc), f16))
         t = self.n1(ws, f"{tag}_n1", t, q, B, h, w)
-        return self.c1([t], B, h, w, ws.get(f"{tag}_c1", (B, h, w, self.x_nc), f16), aux=x)
+        return self.c1([t], B, h, w, ws.get(f"{tag}_c1", (B, h, w, self.x_nc), self.out_dtype), aux=x)
 
 
 class RoiEngine:
@@ -274,7 +275,7 @@ class RoiEngine:
         self.ga3 = ConvOp(g("ga3.0.weight"), g("ga3.0.bias"), c_in=[128], c_out=128, k=5, stride=2, gdn=gdn_of("ga3.1", False))
         self.ga4 = plain("ga4", 128, C, 5, stride=2)
         self.ga_sft = [_SftLayer(g, f"ga{i}_SFT", 128, 128) for i in (1, 2, 3)]
-        self.ga4_rb = [_SftResblk(g, f"ga4_SFTResB{i}", C, C) for i in (1, 2)]
+        self.ga4_rb = [_SftResblk(g, f"ga4_SFTResB{i}", C, C, out_f32=(i == 2)) for i in (1, 2)]
         wq = g("qmap_feature_ga1.0.weight")  # (192, 4, 3, 3) -> rows of 40: k = (r*3+s)*4 + ch
         wq = F.pad(wq.permute(0, 2, 3, 1).reshape(192, 36), (0, 4)).reshape(192, 40, 1, 1).contiguous()
         self.qga1 = [ConvOp(wq, g("qmap_feature_ga1.0.bias"), c_in=[40], c_out=192, k=1, slope=l1,
@@ -301,7 +302,7 @@ class RoiEngine:
         self.ha2 = plain("ha2", 256, 256, 5, stride=2)
         self.ha3 = plain("ha3", 256, 256, 5, stride=2)
         self.ha_sft = [_SftLayer(g, "ha1_SFT", 256, 256, slope=l01), _SftLayer(g, "ha2_SFT", 256, 256, slope=l01)]
-        self.ha3_rb = [_SftResblk(g, f"ha3_ResB{i}", 256, 256) for i in (1, 2)]
+        self.ha3_rb = [_SftResblk(g, f"ha3_ResB{i}", 256, 256, out_f32=(i == 2)) for i in (1, 2)]
         # ---- HD / TPM / EPM
         self.hs = [plain("hs.0", 256, 256, 5, stride=2, slope=l01, transposed=True),
                    plain("hs.2", 256, 256, 5, stride=2, slope=l01, transposed=True), plain("hs.4", 256, 2 * C, 3)]
@@ -365,7 +366,8 @@ class RoiEngine:
         return cur, h, w
 
     def latents(self, x_cur: Tensor, x_cond: Tensor, qmap: Tensor):
-        """PEncoder, ConditionEncoder, HE (stem_roi.py:586-589) -> y_cur fp16, y_conditioned fp16, z fp32 (NHWC)."""
+        """PEncoder, ConditionEncoder, HE (stem_roi.py:586-589) -> y_cur fp32 (what is quantised) and its fp16 copy
+        (operand of the hyper-encoder), y_conditioned fp16, z fp32 (all NHWC)."""
         _require_cuda(x_cur, x_cond, qmap)
         x_cur, x_cond, qmap = x_cur.contiguous().float(), x_cond.contiguous().float(), qmap.contiguous().float()
         B, _, H, W = x_cur.shape
@@ -398,7 +400,10 @@ class RoiEngine:
             h, w = h // 2, w // 2
         qp = avgpool_nhwc(q, bf("qpool3", (B, h, w, C)), 2)
         x = self.ga4_rb[0](self.ws, "ga4rb1", x, qp, B, h, w)
-        y16 = self.ga4_rb[1](self.ws, "ga4rb2", x, qp, B, h, w)  # y_cur (B, h, w, C) fp16
+        y32 = self.ga4_rb[1](self.ws, "ga4rb2", x, qp, B, h, w)  # y_cur (B, h, w, C) fp32, straight from the epilogue
+        y16 = bf("y16", (B, h, w, C))
+        _lib.check(lib.stemb200_latent_stage(y32.data_ptr(), None, y16.data_ptr(), None, None, y32.numel(), _stream()),
+                   "latent_stage")
         # ================= ConditionEncoder =================
         yc16 = self.condition(x_cond)
         # ================= HE =================
@@ -418,10 +423,8 @@ class RoiEngine:
         t = self.ha3([t], B, h // 2, w // 2, bf("ha3", (B, h // 4, w // 4, 256)))
         h4, w4 = h // 4, w // 4
         t = self.ha3_rb[0](self.ws, "ha3rb1", t, qf, B, h4, w4)
-        z16 = self.ha3_rb[1](self.ws, "ha3rb2", t, qf, B, h4, w4)
-        z32 = bf("z32", (B, h4, w4, 256), f32)
-        _lib.check(lib.stemb200_cast_f16_to_f32(z16.data_ptr(), z32.data_ptr(), z16.numel(), _stream()), "cast")
-        return y16, yc16, z32, (B, h, w)
+        z32 = self.ha3_rb[1](self.ws, "ha3rb2", t, qf, B, h4, w4)  # fp32 from the residual epilogue
+        return y32, yc16, z32, (B, h, w)
 
     def condition(self, x_cond: Tensor) -> Tensor:
         """ConditionEncoder (stem_roi.py:493-501) -> y_conditioned NHWC fp16."""
@@ -443,7 +446,7 @@ class RoiEngine:
         return self.epm[2]([e], B, h, w, bf("gparams", (B, h, w, 2 * C), torch.float32))
 
     def forward(self, x_cur: Tensor, x_cond: Tensor, qmap: Tensor):
-        y16, yc16, z32, (B, h, w) = self.latents(x_cur, x_cond, qmap)
+        y32, yc16, z32, (B, h, w) = self.latents(x_cur, x_cond, qmap)
         lib, C, dev = _lib.load(), self.C, self.device
         f16, f32 = torch.float16, torch.float32
         bf = self._buf
@@ -458,8 +461,6 @@ class RoiEngine:
                                                        z_lik.data_ptr(), bits[1].data_ptr(), _stream()),
                    "entropy_bottleneck_fwd")
         params = self.gaussian_params(zhat16, yc16, B, h, w)
-        y32 = bf("y32", (B, h, w, C), f32)
-        _lib.check(lib.stemb200_cast_f16_to_f32(y16.data_ptr(), y32.data_ptr(), y16.numel(), _stream()), "cast")
         y_hat = torch.empty((B, C, h, w), dtype=f32, device=dev)
         y_lik = torch.empty((B, C, h, w), dtype=f32, device=dev)
         _lib.check(lib.stemb200_gaussian_conditional_fwd(y32.data_ptr(), 0, None, params.data_ptr(), B, C, h, w, None, 0,
