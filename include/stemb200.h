@@ -201,6 +201,14 @@ int stemb200_gaussian_conditional_fwd(const float* y, int32_t y_is_nchw, const v
                                       const float* scale_table, int32_t n_scales, float scale_bound,
                                       float lik_bound, int32_t yhat_mode, float* y_hat_nchw, float* lik_nchw,
                                       int32_t* idx_nchw, int32_t* sym_nchw, double* bits, void* stream);
+/* Same for the drop-in forward of the _Res variant (spatiotemporalpriors.py:845-868) with API tensors: y and the
+ * conditioning latent both NCHW fp32; the coded quantity is y - cond in fp32 and y_hat (mode 1) = round(y - cond) + cond
+ * in fp32, exactly the reference's arithmetic whatever values y_conditioned holds. */
+int stemb200_gaussian_conditional_fwd_cond32(const float* y_nchw, const float* cond_f32_nchw, const float* params_nhwc,
+                                             int32_t n, int32_t c, int32_t h, int32_t w, const float* scale_table,
+                                             int32_t n_scales, float scale_bound, float lik_bound, int32_t yhat_mode,
+                                             float* y_hat_nchw, float* lik_nchw, int32_t* idx_nchw, int32_t* sym_nchw,
+                                             double* bits, void* stream);
 /* Same arithmetic on flat arrays (no layout change); the isolated parity test of a9 runs through this. */
 int stemb200_gaussian_conditional_flat(const float* y, const float* scales, const float* means,
                                        int64_t numel, const float* scale_table, int32_t n_scales,
@@ -249,6 +257,8 @@ typedef struct stemb200_ar_desc {
   int32_t l1, l2;   /* widths of the two hidden layers of the parameter head (multiples of 64) */
   float slope;      /* LeakyReLU slope of the head (0.01) */
   int32_t n_scales; /* scale table length */
+  float scale_bound; /* GaussianConditional.lower_bound_scale (0.11): sigma is clamped to it before the table search
+                        (entropy_models.py:598-604), as in stemb200_gaussian_conditional_fwd */
 } stemb200_ar_desc;
 /* Weights are packed on the host (fp32) as 64 consecutive per-CTA blocks; CTA j owns rows
  *   [j*rc, (j+1)*rc) of context_prediction (rc = 2c/64; each row = 12 taps x c, tap-major, taps in mask order),
@@ -258,6 +268,10 @@ typedef struct stemb200_ar_desc {
  * stemb200_ar_packed_floats returns the total float count (64 blocks). */
 int64_t stemb200_ar_packed_floats(const stemb200_ar_desc* d);
 int64_t stemb200_ar_workspace_bytes(const stemb200_ar_desc* d);
+/* Both kernels are persistent cooperative grids whose layers are separated by a grid barrier with a watchdog: if a
+ * barrier times out the grid aborts and leaves its outputs undefined. The first three 32-bit words of the workspace
+ * tell the caller: [0] barrier counter, [1] abort flag (non-zero = aborted), [2] completion flag (1 = ran to the end);
+ * they are zeroed by the launch, so after the stream has drained a caller must see [1] == 0 and [2] == 1. */
 /* target: the coded quantity (y, or y - y_conditioned for _Res). Outputs: t_hat, symbols / indexes int32 in stream
  * order, params_out [..][2c] = sigma | mu (may be NULL, symbols may be NULL). */
 int stemb200_ar_encode(const stemb200_ar_desc* d, const float* packed, const float* e0, const float* target,

@@ -32,7 +32,7 @@ class ArDesc(C.Structure):
     """Mirror of ``stemb200_ar_desc``."""
 
     _fields_ = [("batch", C.c_int32), ("h", C.c_int32), ("w", C.c_int32), ("c", C.c_int32), ("l1", C.c_int32),
-                ("l2", C.c_int32), ("slope", C.c_float), ("n_scales", C.c_int32)]
+                ("l2", C.c_int32), ("slope", C.c_float), ("n_scales", C.c_int32), ("scale_bound", C.c_float)]
 
 
 class StemLibError(RuntimeError):
@@ -69,6 +69,8 @@ SIGNATURES = {
     "stemb200_latent_stage": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, _vp]),
     "stemb200_gaussian_conditional_fwd": (C.c_int, [_vp, _i32, _vp, _vp, _i32, _i32, _i32, _i32, _vp, _i32, _f32,
                                                     _f32, _i32, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "stemb200_gaussian_conditional_fwd_cond32": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp, _i32, _f32, _f32,
+                                                           _i32, _vp, _vp, _vp, _vp, _vp, _vp]),
     "stemb200_gaussian_conditional_flat": (C.c_int, [_vp, _vp, _vp, _i64, _vp, _i32, _f32, _f32, _vp, _vp, _vp,
                                                      _vp, _vp, _vp]),
     "stemb200_entropy_bottleneck_fwd": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _f32, _vp, _vp, _vp, _vp,

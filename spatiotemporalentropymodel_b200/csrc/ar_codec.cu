@@ -42,6 +42,7 @@ struct ArParams {
   int kmax;            // staging vector length: max(12c, 2c, l1, l2)
   int n_scales, mode;  // mode 0 = encode, 1 = decode
   float slope;
+  float scale_bound;  // lower_bound_scale of build_indexes (entropy_models.py:598-604)
   const float* packed;  // per-CTA weight blocks (stemb200_ar_packed_floats / 64 floats each)
   int block_floats;
   const float* e0;      // [B][h][w][l1]
@@ -52,7 +53,7 @@ struct ArParams {
   int32_t* idx;         // [B][h][w][c]
   float* params_out;    // [B][h][w][2c] sigma | mu (may be null)
   float *ctx_buf, *h1_buf, *h2_buf, *mu_buf;  // scratch [pmax][2c | l1 | l2 | c]
-  unsigned int* sync;   // [0] barrier counter, [1] abort flag (zeroed before launch)
+  unsigned int* sync;   // [0] barrier counter, [1] abort flag, [2] completion flag (zeroed before launch)
   const uint8_t* streams;
   const int64_t* stream_off;  // [B] byte offsets (multiples of 4) into streams
   const int64_t* stream_len;  // [B] byte lengths
@@ -413,8 +414,10 @@ __global__ void __launch_bounds__(kArThreads, 1) ar_codec_kernel(const ArParams 
           const int ch = j * p.rg + lane;
           const float sigma = s_res[warp][lane] + b2[lane];
           const float mu = s_res[warp][p.rg + lane] + b2[p.rg + lane];
+          // build_indexes clamps the scale first (torch.max(scales, bound): NaN passes through)
+          const float sb = (sigma != sigma) ? sigma : fmaxf(sigma, p.scale_bound);
           int cnt = 0;
-          for (int k = 0; k + 1 < p.n_scales; ++k) cnt += (sigma <= s_table[k]) ? 1 : 0;
+          for (int k = 0; k + 1 < p.n_scales; ++k) cnt += (sb <= s_table[k]) ? 1 : 0;
           const long long e = q.g * C + ch;
           p.idx[e] = p.n_scales - 1 - cnt;
           if (p.params_out) {
@@ -543,8 +546,9 @@ __global__ void __launch_bounds__(kArThreads, 1) ar_codec_kernel(const ArParams 
         const float sigma = cta_row(s_lp, r, lane) + b2[r];
         const float mu = cta_row(s_lp, p.rg + r, lane) + b2[p.rg + r];
         // index = (n_scales - 1) - #{k < n_scales - 1 : sigma <= table[k]}, lanes share the table
+        const float sb = (sigma != sigma) ? sigma : fmaxf(sigma, p.scale_bound);
         int cnt = 0;
-        for (int k = lane; k + 1 < p.n_scales; k += 32) cnt += (sigma <= s_table[k]) ? 1 : 0;
+        for (int k = lane; k + 1 < p.n_scales; k += 32) cnt += (sb <= s_table[k]) ? 1 : 0;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
         if (lane == 0) {
@@ -659,6 +663,8 @@ __global__ void __launch_bounds__(kArThreads, 1) ar_codec_kernel(const ArParams 
     for (int i = 0; i < 10; ++i) out[i] = prof[i];
   }
   if (p.mode == 1 && j < p.batch && warp == 0 && lane == 0) p.status[j] = rbad ? 1 : 0;
+  // normal completion (every early return above is an aborted grid barrier): the host checks this flag
+  if (j == 0 && tid == 0) p.sync[2] = 1u;
 }
 
 int fill_params(const stemb200_ar_desc* d, ArParams& p) {
@@ -682,6 +688,7 @@ int fill_params(const stemb200_ar_desc* d, ArParams& p) {
   p.kmax = std::max(std::max(kArTaps * d->c, 2 * d->c), std::max(d->l1, d->l2));
   p.n_scales = d->n_scales;
   p.slope = d->slope;
+  p.scale_bound = d->scale_bound;
   p.block_floats = static_cast<int>(stemb200_ar_packed_floats(d) / kArCtas);
   return 0;
 }

@@ -375,7 +375,8 @@ constexpr int kGcPix = 32, kGcCh = 64, kGcIter = kGcPix / 4;
 // are inside the frame, so the operand loads are unguarded and issue back to back.
 template <bool kIdx, bool kFull>
 __device__ __forceinline__ float gc_tile_eval(const float* __restrict__ yp, const __half* __restrict__ cp,
-                                              const float* __restrict__ sp, int c, int lim, int y_is_nchw,
+                                              const float* s_cond, const float* __restrict__ sp, int c, int lim,
+                                              int y_is_nchw,
                                               int yhat_mode, bool want_idx, const float* table, int n_scales,
                                               float scale_bound, float lik_bound, float* s_yhat, float* s_lik,
                                               int* s_idx, int* s_sym) {
@@ -386,7 +387,7 @@ __device__ __forceinline__ float gc_tile_eval(const float* __restrict__ yp, cons
   for (int k = 0; k < kIter; ++k) {
     const bool ok = kFull || 4 * k < lim;
     yv[k] = y_is_nchw ? s_yhat[4 * k] : (ok ? __ldg(yp) : 0.f);
-    cv[k] = (cp && ok) ? __half2float(*cp) : 0.f;
+    cv[k] = s_cond ? s_cond[4 * k] : ((cp && ok) ? __half2float(*cp) : 0.f);
     sg[k] = ok ? __ldg(sp) : 1.f;
     mu[k] = ok ? __ldg(sp + c) : 0.f;
     yp += step;
@@ -419,12 +420,12 @@ __device__ __forceinline__ float gc_tile_eval(const float* __restrict__ yp, cons
 template <bool kIdx>
 __global__ void __launch_bounds__(256)
 gc_nhwc_kernel(const float* __restrict__ y, int y_is_nchw, const __half* __restrict__ cond,
-               const float* __restrict__ params, int c, int hw, int yhat_mode,
+               const float* __restrict__ cond32_nchw, const float* __restrict__ params, int c, int hw, int yhat_mode,
                const float* __restrict__ table_g, int n_scales, float scale_bound, float lik_bound,
                float* __restrict__ y_hat, float* __restrict__ lik, int* __restrict__ idx, int* __restrict__ sym,
                double* bits) {
   __shared__ float s_yhat[kGcCh][kGcPix + 1];
-  __shared__ float s_lik[kGcCh][kGcPix + 1];
+  __shared__ float s_lik[kGcCh][kGcPix + 1];  // with cond32_nchw: holds the fp32 conditioning tile until it is consumed
   __shared__ int s_idx[kIdx ? kGcCh : 1][kGcPix + 1];
   __shared__ int s_sym[kIdx ? kGcCh : 1][kGcPix + 1];
   __shared__ float table[kIdx ? 256 : 1];
@@ -444,7 +445,9 @@ gc_nhwc_kernel(const float* __restrict__ y, int y_is_nchw, const __half* __restr
     const int pp = p0 + pi;
     for (int ch = threadIdx.x / kGcPix; ch < kGcCh; ch += 256 / kGcPix) {
       const int cc = c0 + ch;
-      s_yhat[ch][pi] = (pp < hw && cc < c) ? yb[static_cast<long long>(cc) * hw + pp] : 0.f;
+      const bool ok = pp < hw && cc < c;
+      s_yhat[ch][pi] = ok ? yb[static_cast<long long>(cc) * hw + pp] : 0.f;
+      if (cond32_nchw) s_lik[ch][pi] = ok ? cond32_nchw[(static_cast<long long>(n) * c + cc) * hw + pp] : 0.f;
     }
     __syncthreads();
   }
@@ -457,12 +460,15 @@ gc_nhwc_kernel(const float* __restrict__ y, int y_is_nchw, const __half* __restr
       const __half* cp = cond ? cond + e0 : nullptr;
       const float* sp = params + 2 * e0 - cc;  // sigma of (pixel, cc); mu is c floats further
       const int lim = hw - p0 - q;             // pixel slot 4 k of this thread is inside the frame iff 4 k < lim
+      // fp32 NCHW conditioning (drop-in forward of the _Res variant): its tile was staged in s_lik; a thread reads
+      // its 8 values before it writes its 8 likelihoods into the same slots
+      const float* sc = (y_is_nchw && cond32_nchw) ? &s_lik[ch][q] : nullptr;
       if (lim > 4 * (kGcIter - 1))
-        acc = gc_tile_eval<kIdx, true>(yp, cp, sp, c, lim, y_is_nchw, yhat_mode, want_idx, table, n_scales,
+        acc = gc_tile_eval<kIdx, true>(yp, cp, sc, sp, c, lim, y_is_nchw, yhat_mode, want_idx, table, n_scales,
                                        scale_bound, lik_bound, &s_yhat[ch][q], &s_lik[ch][q], &s_idx[kIdx ? ch : 0][q],
                                        &s_sym[kIdx ? ch : 0][q]);
       else
-        acc = gc_tile_eval<kIdx, false>(yp, cp, sp, c, lim, y_is_nchw, yhat_mode, want_idx, table, n_scales,
+        acc = gc_tile_eval<kIdx, false>(yp, cp, sc, sp, c, lim, y_is_nchw, yhat_mode, want_idx, table, n_scales,
                                         scale_bound, lik_bound, &s_yhat[ch][q], &s_lik[ch][q], &s_idx[kIdx ? ch : 0][q],
                                         &s_sym[kIdx ? ch : 0][q]);
     }
@@ -1113,6 +1119,30 @@ extern "C" int stemb200_gaussian_conditional_flat(const float* y, const float* s
   return 0;
 }
 
+extern "C" int stemb200_gaussian_conditional_fwd_cond32(const float* y_nchw, const float* cond_f32_nchw,
+                                                        const float* params_nhwc, int32_t n, int32_t c, int32_t h,
+                                                        int32_t w, const float* scale_table, int32_t n_scales,
+                                                        float scale_bound, float lik_bound, int32_t yhat_mode,
+                                                        float* y_hat_nchw, float* lik_nchw, int32_t* idx_nchw,
+                                                        int32_t* sym_nchw, double* bits, void* stream) {
+  if (!y_nchw || !cond_f32_nchw || !params_nhwc || n < 1 || c < 1 || h < 1 || w < 1)
+    return set_error("gaussian_conditional_fwd_cond32: bad argument");
+  if (idx_nchw && (!scale_table || n_scales < 1 || n_scales > 256))
+    return set_error("gaussian_conditional_fwd_cond32: idx needs a scale table of 1..256 entries");
+  const int hw = h * w;
+  dim3 grid((hw + kGcPix - 1) / kGcPix, (c + kGcCh - 1) / kGcCh, n);
+  if (idx_nchw || sym_nchw)
+    gc_nhwc_kernel<true><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        y_nchw, 1, nullptr, cond_f32_nchw, params_nhwc, c, hw, yhat_mode, scale_table, n_scales, scale_bound, lik_bound,
+        y_hat_nchw, lik_nchw, idx_nchw, sym_nchw, bits);
+  else
+    gc_nhwc_kernel<false><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        y_nchw, 1, nullptr, cond_f32_nchw, params_nhwc, c, hw, yhat_mode, scale_table, n_scales, scale_bound, lik_bound,
+        y_hat_nchw, lik_nchw, idx_nchw, sym_nchw, bits);
+  CHECK_LAUNCH("gaussian_conditional_fwd_cond32");
+  return 0;
+}
+
 extern "C" int stemb200_gaussian_conditional_fwd(const float* y_nhwc, int32_t y_is_nchw, const void* cond_f16,
                                                  const float* params_nhwc, int32_t n, int32_t c, int32_t h,
                                                  int32_t w, const float* scale_table, int32_t n_scales,
@@ -1127,11 +1157,11 @@ extern "C" int stemb200_gaussian_conditional_fwd(const float* y_nhwc, int32_t y_
   dim3 grid((hw + kGcPix - 1) / kGcPix, (c + kGcCh - 1) / kGcCh, n);
   if (idx_nchw || sym_nchw)
     gc_nhwc_kernel<true><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        y_nhwc, y_is_nchw, static_cast<const __half*>(cond_f16), params_nhwc, c, hw, yhat_mode, scale_table,
+        y_nhwc, y_is_nchw, static_cast<const __half*>(cond_f16), nullptr, params_nhwc, c, hw, yhat_mode, scale_table,
         n_scales, scale_bound, lik_bound, y_hat_nchw, lik_nchw, idx_nchw, sym_nchw, bits);
   else
     gc_nhwc_kernel<false><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        y_nhwc, y_is_nchw, static_cast<const __half*>(cond_f16), params_nhwc, c, hw, yhat_mode, scale_table,
+        y_nhwc, y_is_nchw, static_cast<const __half*>(cond_f16), nullptr, params_nhwc, c, hw, yhat_mode, scale_table,
         n_scales, scale_bound, lik_bound, y_hat_nchw, lik_nchw, idx_nchw, sym_nchw, bits);
   CHECK_LAUNCH("gaussian_conditional_fwd");
   return 0;

@@ -40,6 +40,49 @@ def _require_cuda(*ts: Tensor) -> None:
                                "there is no CPU fallback")
 
 
+def overlap_level() -> int:
+    """STEMB200_OVERLAP: 0 = one stream; 1 = the temporal-prior / context chain runs beside the hyper-prior chain;
+    2 (default) = in addition the synthesis transform of a GOP runs beside its entropy model (SPM variants, where
+    y_hat = round(y) is known before the entropy parameters are)."""
+    import os
+    try:
+        return int(os.environ.get("STEMB200_OVERLAP", "2"))
+    except ValueError:
+        return 2
+
+
+class SideStream:
+    """Fork / join of a second CUDA stream around a block of launches.  The launches under the `with` go to the side
+    stream, which first waits for everything issued so far on the current stream; `join()` makes the current stream
+    wait for them.  Under stream capture the two branches become parallel branches of the CUDA graph.  Kernels of the
+    path are persistent (one CTA per SM), so what this buys is the tails: SMs a small launch leaves idle run the other
+    branch's tiles."""
+
+    def __init__(self, device: torch.device):
+        self.stream = torch.cuda.Stream(device=device)
+        self._joined = True
+
+    def __enter__(self):
+        self.main = torch.cuda.current_stream()
+        ev = torch.cuda.Event()
+        ev.record(self.main)
+        self.stream.wait_event(ev)
+        self._ctx = torch.cuda.stream(self.stream)
+        self._ctx.__enter__()
+        return self
+
+    def __exit__(self, *exc):
+        self._done = torch.cuda.Event()
+        self._done.record(self.stream)
+        self._joined = False
+        return self._ctx.__exit__(*exc)
+
+    def join(self):
+        if not self._joined:
+            torch.cuda.current_stream().wait_event(self._done)
+            self._joined = True
+
+
 class Workspace:
     """Named, shape-keyed device buffers that persist across calls (so CUDA graphs can capture the chain)."""
 
@@ -248,7 +291,7 @@ class ArHead:
     context_prediction and the rest of the head run per latent position inside the kernel, fp32."""
 
     def __init__(self, w_ctx: Tensor, b_ctx: Tensor, layers: Sequence[Tuple[Tensor, Tensor]], static_c: Sequence[int],
-                 device: torch.device, slope: float = 0.01):
+                 device: torch.device, slope: float = 0.01, scale_bound: float = 0.11):
         f = lambda t: t.detach().to(device, torch.float32)
         w_ctx, b_ctx = f(w_ctx), f(b_ctx)
         (w0, b0), (w1, b1), (w2, b2) = [(f(w).flatten(1), f(b)) for w, b in layers]
@@ -258,6 +301,7 @@ class ArHead:
         if w0.shape[1] != n_static + C2 or w2.shape[0] != C2:
             raise ValueError("ArHead: inconsistent layer shapes")
         self.C, self.L1, self.L2, self.slope = C, L1, L2, float(slope)
+        self.scale_bound = float(scale_bound)
         self.device = device
         self.lib = _lib.load()
         # e0 = W0[:, :n_static] . priors + b0, no activation, fp32 (the context columns are added per position)
@@ -277,6 +321,7 @@ class ArHead:
     def _desc(self, B: int, h: int, w: int, n_scales: int) -> ArDesc:
         d = ArDesc()
         d.batch, d.h, d.w, d.c, d.l1, d.l2, d.slope, d.n_scales = B, h, w, self.C, self.L1, self.L2, self.slope, n_scales
+        d.scale_bound = self.scale_bound
         want = self.lib.stemb200_ar_packed_floats(C.byref(d))
         if want != self.packed.numel():
             raise _lib.StemLibError(f"AR weight block mismatch: packed {self.packed.numel()} floats, kernel wants {want}")
@@ -291,23 +336,38 @@ class ArHead:
             self._ws[key] = torch.empty(n, dtype=torch.uint8, device=self.device)
         return self._ws[key]
 
+    def _check_completed(self, ws: Tensor, what: str) -> None:
+        """The persistent grid aborts when one of its grid barriers times out and then leaves its outputs undefined:
+        words [1] (abort) and [2] (completed) of the workspace say which (include/stemb200.h)."""
+        flags = ws[:12].view(torch.int32).cpu()
+        if int(flags[1]) != 0 or int(flags[2]) != 1:
+            raise _lib.StemLibError(f"{what}: the autoregressive kernel aborted (grid barrier watchdog; abort flag "
+                                    f"{int(flags[1])}, completion flag {int(flags[2])}); its outputs are invalid")
+
     def static_part(self, priors: Sequence[Tensor], B: int, h: int, w: int) -> Tensor:
         out = torch.empty((B, h, w, self.L1), dtype=torch.float32, device=self.device)
         return self.e0_conv(list(priors), B, h, w, out)
 
-    def encode(self, target_nhwc: Tensor, priors: Sequence[Tensor], table: Tensor):
-        """target (B, h, w, C) fp32 NHWC -> t_hat, symbols, indexes (stream order), params (sigma | mu)."""
+    def encode(self, target_nhwc: Tensor, priors: Sequence[Tensor], table: Tensor, e0: Optional[Tensor] = None):
+        """target (B, h, w, C) fp32 NHWC -> t_hat, symbols, indexes (stream order), params (sigma | mu).
+        e0 (B, h, w, L1) fp32: the prior part of the first head layer computed elsewhere (tests feed the oracle's fp32
+        value to separate the fp16 tensor-core priors from the head's own summation order); default: static_part."""
         B, h, w, _ = target_nhwc.shape
         d = self._desc(B, h, w, table.numel())
-        e0 = self.static_part(priors, B, h, w)
+        if e0 is None:
+            e0 = self.static_part(priors, B, h, w)
+        elif tuple(e0.shape) != (B, h, w, self.L1) or e0.dtype != torch.float32 or not e0.is_contiguous():
+            raise ValueError("e0 must be a contiguous (B, h, w, L1) fp32 tensor")
         dev = self.device
         t_hat = torch.empty_like(target_nhwc)
         sym = torch.empty(target_nhwc.shape, dtype=torch.int32, device=dev)
         idx = torch.empty(target_nhwc.shape, dtype=torch.int32, device=dev)
         params = torch.empty((B, h, w, 2 * self.C), dtype=torch.float32, device=dev)
+        ws = self._workspace(d)
         _lib.check(self.lib.stemb200_ar_encode(C.byref(d), self.packed.data_ptr(), e0.data_ptr(), target_nhwc.data_ptr(),
                                                table.data_ptr(), t_hat.data_ptr(), sym.data_ptr(), idx.data_ptr(),
-                                               params.data_ptr(), self._workspace(d).data_ptr(), _stream()), "ar_encode")
+                                               params.data_ptr(), ws.data_ptr(), _stream()), "ar_encode")
+        self._check_completed(ws, "ar_encode")
         return t_hat, sym, idx, params
 
     def decode(self, strings: Sequence[bytes], priors: Sequence[Tensor], B: int, h: int, w: int, table: Tensor,
@@ -336,12 +396,14 @@ class ArHead:
         idx = torch.empty((B, h, w, self.C), dtype=torch.int32, device=dev)
         params = torch.empty((B, h, w, 2 * self.C), dtype=torch.float32, device=dev)
         status = torch.zeros(B, dtype=torch.int32, device=dev)
+        ws = self._workspace(d)
         _lib.check(self.lib.stemb200_ar_decode(
             C.byref(d), self.packed.data_ptr(), e0.data_ptr(), table.data_ptr(), blob.data_ptr(), t_off.data_ptr(),
             t_len.data_ptr(), cdf_d.data_ptr(), cdf_d.shape[0], cdf_d.shape[1], len_d.data_ptr(), off_d.data_ptr(),
             int(cdf_length.detach().sum().item()), t_hat.data_ptr(), None, idx.data_ptr(), params.data_ptr(),
             status.data_ptr(),
-            self._workspace(d).data_ptr(), _stream()), "ar_decode")
+            ws.data_ptr(), _stream()), "ar_decode")
+        self._check_completed(ws, "ar_decode")
         if int(status.max().item()) != 0:
             raise _lib.StemLibError("ar_decode: corrupt rANS stream")
         return t_hat, params
@@ -567,6 +629,7 @@ class StemEngine:
         self.eb_params = eb_packed.detach().to(dev, torch.float32).contiguous()
         self.scale_table = None if scale_table is None or scale_table.numel() == 0 else \
             scale_table.detach().to(dev, torch.float32).contiguous()
+        self._side = None
 
     # -------------------------------------------------------------------------------------------------
     def hyper_latent(self, y16: Tensor, cond16: Tensor, B: int, h: int, w: int) -> Tensor:
@@ -581,28 +644,32 @@ class StemEngine:
         t2 = self.he[1]([t1], B, h, w, ws.get("he2", (B, h2, w2, self.he[1].c_out), f16))
         return self.he[2]([t2], B, h2, w2, ws.get("z", (B, h4, w4, self.zc), f32))
 
-    def static_priors(self, zhat16: Tensor, cond16: Optional[Tensor], B: int, h: int, w: int) -> List[Tensor]:
-        """[TPM(y_cond)] + [HD(z_hat)]: the EPM inputs that do not depend on the frame's own y_hat, NHWC fp16."""
-        ws = self.ws
-        f16 = torch.float16
+    def temporal_prior(self, cond16: Tensor, B: int, h: int, w: int) -> Tensor:
+        """TPM(y_cond) (spatiotemporalpriors.py:565), NHWC fp16."""
+        ws, f16 = self.ws, torch.float16
+        p1 = self.tpm[0]([cond16], B, h, w, ws.get("tp1", (B, h, w, 256), f16))
+        p2 = self.tpm[1]([p1], B, h, w, ws.get("tp2", (B, h, w, 320), f16))
+        return self.tpm[2]([p2], B, h, w, ws.get("tp", (B, h, w, 2 * self.C), f16))
+
+    def hyper_prior(self, zhat16: Tensor, B: int, h: int, w: int) -> Tensor:
+        """HD(z_hat) (:564), NHWC fp16."""
+        ws, f16 = self.ws, torch.float16
         h2, w2, h4, w4 = h // 2, w // 2, h // 4, w // 4
         c1, c2 = self.hd[0].c_out, self.hd[1].c_out
         d1 = self.hd[0]([zhat16], B, h4, w4, ws.get("hd1", (B, h2, w2, c1), f16))
         d2 = self.hd[1]([d1], B, h2, w2, ws.get("hd2", (B, h, w, c2), f16))
-        hp = self.hd[2]([d2], B, h, w, ws.get("hp", (B, h, w, 2 * self.C), f16))
-        srcs: List[Tensor] = []
-        if self.has_tpm:
-            p1 = self.tpm[0]([cond16], B, h, w, ws.get("tp1", (B, h, w, 256), f16))
-            p2 = self.tpm[1]([p1], B, h, w, ws.get("tp2", (B, h, w, 320), f16))
-            srcs.append(self.tpm[2]([p2], B, h, w, ws.get("tp", (B, h, w, 2 * self.C), f16)))
-        srcs.append(hp)
-        return srcs
+        return self.hd[2]([d2], B, h, w, ws.get("hp", (B, h, w, 2 * self.C), f16))
+
+    def static_priors(self, zhat16: Tensor, cond16: Optional[Tensor], B: int, h: int, w: int) -> List[Tensor]:
+        """[TPM(y_cond)] + [HD(z_hat)]: the EPM inputs that do not depend on the frame's own y_hat, NHWC fp16."""
+        hp = self.hyper_prior(zhat16, B, h, w)
+        return ([self.temporal_prior(cond16, B, h, w)] if self.has_tpm else []) + [hp]
 
     def ar_head(self) -> "ArHead":
         if not self.has_spm:
             raise RuntimeError("this variant has no spatial context model")
         if self._ar is None:
-            self._ar = ArHead(*self._ar_spec, device=self.device)
+            self._ar = ArHead(*self._ar_spec, device=self.device, scale_bound=self.scale_bound)
         return self._ar
 
     def params_from_zhat(self, zhat16: Tensor, cond16: Tensor, yq16: Optional[Tensor], B: int, h: int,
@@ -614,31 +681,64 @@ class StemEngine:
         srcs = self.static_priors(zhat16, cond16, B, h, w)
         if self.has_spm:
             srcs.append(self.ctx([yq16], B, h, w, ws.get("ctx", (B, h, w, 2 * self.C), f16)))
-        e1 = self.epm[0](srcs, B, h, w, ws.get("e1", (B, h, w, self.epm[0].c_out), f16))
-        e2 = self.epm[1]([e1], B, h, w, ws.get("e2", (B, h, w, self.epm[1].c_out), f16))
-        return self.epm[2]([e2], B, h, w, ws.get("gparams", (B, h, w, 2 * self.C), f32))
+        return self.entropy_parameters(srcs, B, h, w)
 
     def gaussian_params(self, y16: Tensor, cond16: Tensor, yq16: Optional[Tensor], B: int, h: int, w: int,
                         z_hat_nchw: Optional[Tensor] = None, z_lik_nchw: Optional[Tensor] = None,
                         bits_z: Optional[Tensor] = None) -> Tensor:
-        """HE -> EntropyBottleneck -> HD, TPM, context, EPM. Returns params NHWC fp32 (B, h, w, 2C)."""
+        """HE -> EntropyBottleneck -> HD, TPM, context, EPM. Returns params NHWC fp32 (B, h, w, 2C).
+        TPM(y_cond) and context(y_q) depend only on the inputs, HE -> EB -> HD is a chain of small launches (55-148
+        tiles at 1080p): the two branches run on two streams and meet at EPM.0 (STEMB200_OVERLAP >= 1)."""
         lib, ws = _lib.load(), self.ws
+        f16 = torch.float16
+        side = None
+        tp = ctx = None
+        if overlap_level() >= 1 and (self.has_tpm or self.has_spm):
+            if self._side is None:
+                self._side = SideStream(self.device)
+            side = self._side
+            with side:
+                if self.has_tpm:
+                    tp = self.temporal_prior(cond16, B, h, w)
+                if self.has_spm:
+                    ctx = self.ctx([yq16], B, h, w, ws.get("ctx", (B, h, w, 2 * self.C), f16))
         z = self.hyper_latent(y16, cond16, B, h, w)
         h4, w4 = h // 4, w // 4
-        zhat16 = ws.get("zhat16", (B, h4, w4, self.zc), torch.float16)
+        zhat16 = ws.get("zhat16", (B, h4, w4, self.zc), f16)
         _lib.check(lib.stemb200_entropy_bottleneck_fwd(z.data_ptr(), self.eb_params.data_ptr(), B, self.zc, h4, w4,
                                                        self.lik_bound, zhat16.data_ptr(), _ptr(z_hat_nchw),
                                                        _ptr(z_lik_nchw), _ptr(bits_z), _stream()),
                    "entropy_bottleneck_fwd")
-        return self.params_from_zhat(zhat16, cond16, yq16, B, h, w)
+        if side is None:
+            return self.params_from_zhat(zhat16, cond16, yq16, B, h, w)
+        hp = self.hyper_prior(zhat16, B, h, w)
+        side.join()
+        return self.entropy_parameters([t for t in (tp, hp, ctx) if t is not None], B, h, w)
+
+    def entropy_parameters(self, srcs: Sequence[Tensor], B: int, h: int, w: int) -> Tensor:
+        """EPM on cat(tp | hp | ctx) (:576-577) -> (scales | means) NHWC fp32."""
+        ws, f16 = self.ws, torch.float16
+        e1 = self.epm[0](list(srcs), B, h, w, ws.get("e1", (B, h, w, self.epm[0].c_out), f16))
+        e2 = self.epm[1]([e1], B, h, w, ws.get("e2", (B, h, w, self.epm[1].c_out), f16))
+        return self.epm[2]([e2], B, h, w, ws.get("gparams", (B, h, w, 2 * self.C), torch.float32))
 
     def gaussian_conditional(self, y: Tensor, y_is_nchw: bool, cond16: Optional[Tensor], params: Tensor, B: int,
                              h: int, w: int, y_hat: Optional[Tensor], lik: Optional[Tensor],
                              idx: Optional[Tensor] = None, sym: Optional[Tensor] = None,
-                             bits: Optional[Tensor] = None) -> None:
+                             bits: Optional[Tensor] = None, cond32_nchw: Optional[Tensor] = None) -> None:
+        """cond32_nchw (only with an NCHW y): the _Res conditioning latent as the API hands it over, fp32 NCHW - the
+        residual y - cond and y_hat = round(y - cond) + cond are then formed in fp32 like the reference does."""
         if idx is not None and self.scale_table is None:
             raise ValueError("build_indexes needs the scale table: call update() first")
         n_scales = 0 if self.scale_table is None else self.scale_table.numel()
+        if self.residual and cond32_nchw is not None:
+            if not y_is_nchw:
+                raise ValueError("cond32_nchw needs an NCHW y")
+            _lib.check(_lib.load().stemb200_gaussian_conditional_fwd_cond32(
+                y.data_ptr(), cond32_nchw.data_ptr(), params.data_ptr(), B, self.C, h, w, _ptr(self.scale_table),
+                n_scales, self.scale_bound, self.lik_bound, 1 if self.has_spm else 0, _ptr(y_hat), _ptr(lik), _ptr(idx),
+                _ptr(sym), _ptr(bits), _stream()), "gaussian_conditional_fwd_cond32")
+            return
         _lib.check(_lib.load().stemb200_gaussian_conditional_fwd(
             y.data_ptr(), int(y_is_nchw), _ptr(cond16 if self.residual else None), params.data_ptr(), B, self.C, h, w,
             _ptr(self.scale_table), n_scales, self.scale_bound, self.lik_bound, 1 if self.has_spm else 0,
@@ -673,7 +773,9 @@ class StemEngine:
         if want_indexes:
             idx = torch.empty(y_cur.shape, dtype=torch.int32, device=dev)
             sym = torch.empty(y_cur.shape, dtype=torch.int32, device=dev)
-        self.gaussian_conditional(y_cur, True, cond16, params, B, h, w, y_hat, y_lik, idx, sym, bits[0])
+        # _Res: one definition of the residual everywhere - fp32 y_cur - y_cond, as yq16 above and as compress() use
+        self.gaussian_conditional(y_cur, True, cond16, params, B, h, w, y_hat, y_lik, idx, sym, bits[0],
+                                  cond32_nchw=y_cond if self.residual else None)
         return {"y_hat": y_hat, "likelihoods": {"y": y_lik, "z": z_lik}, "z_hat": z_hat, "bits": bits,
                 "indexes": idx, "symbols": sym, "params_nhwc": params}
 
@@ -721,6 +823,7 @@ class IFrameEntropyEngine(StemEngine):
             ConvOp(ep[2][0], ep[2][1], c_in=[ep[1][0].shape[0]], c_out=C2, k=1, out_dtype=DT_F32),
         ]
         self._ar = None
+        self._side = None
         self._ar_spec = (g("context_prediction.weight") * g("context_prediction.mask"), g("context_prediction.bias"),
                          ep, [C2])
         self.eb_params = eb_packed.detach().to(dev, torch.float32).contiguous()
@@ -749,6 +852,7 @@ class PFramePipeline:
         self.tr, self.stem = transforms, stem
         self.ws = Workspace(stem.device)
         self._graphed: Dict[tuple, dict] = {}
+        self._side = None
 
     def run_gop(self, frames: Tensor, y_cond0: Tensor, want_outputs: bool = True):
         """`forward_gop` for a stream of GOPs of one shape (an evaluation loop): the kernel chain is captured once
@@ -839,9 +943,21 @@ class PFramePipeline:
                 _lib.check(lib.stemb200_latent_stage(y32.data_ptr(), None, y16.data_ptr(), yq16.data_ptr(),
                                                      yhat_all[1:].data_ptr(), per * T, _stream()), "latent_stage")
             cond16 = yhat_all[0:T]
+            side = None
+            if overlap_level() >= 2:
+                # y_hat = round(y [- cond]) [+ cond] is complete: g_s (45 % of the step) does not wait for sigma / mu
+                if self._side is None:
+                    self._side = SideStream(dev)
+                side = self._side
+                with side:
+                    x_hat = tr.synthesis(yhat_all[1:], x_ref=frames.contiguous(), pad=pad, sq_err=stats[2], out=None)
             params = st.gaussian_params(y16, cond16, yq16, T, h, w, None, outs.get("lik_z"), stats[1])
             st.gaussian_conditional(y32, False, cond16, params, T, h, w, outs.get("y_hat"), outs.get("lik_y"),
                                     bits=stats[0])
+            if side is not None:
+                side.join()
+                outs.update(x_hat_padded=x_hat, pad=pad, stats=stats, num_pixels=H * W)
+                return outs
         else:
             # y_hat[t] = round(y - mu) + mu depends on the whole network applied to y_hat[t-1]: serial
             _lib.check(lib.stemb200_latent_stage(y32.data_ptr(), None, y16.data_ptr(), None, None, per * T,

@@ -371,6 +371,12 @@ class JointAutoregressiveHierarchicalPriors(CompressionModel):
         dev = self._device()
         if dev.type != "cuda":
             raise RuntimeError("the I-frame model of spatiotemporalentropymodel_b200 runs on CUDA only")
+        if self.M != 192:
+            # entropy_parameters widths 10M/3 and 8M/3 (1066 / 853 for M = 320) are not multiples of 64, which the
+            # tensor-core tiles and the autoregressive kernel's 64-CTA row split need
+            raise NotImplementedError(
+                f"the I-frame entropy model (forward / compress / decompress) is built for M = 192 (mbt2018 quality "
+                f"1-4); this model has M = {self.M} (quality 5-8). getY / getX work for every quality.")
         tr = self.engine()
         if self._entropy_engine is None or self._entropy_engine_src is not tr:  # rebuilt after load / update / .to()
             self._entropy_engine_src = tr

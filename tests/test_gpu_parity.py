@@ -142,19 +142,11 @@ CONV_CASES = [
 ]
 
 
-@pytest.mark.parametrize("case", CONV_CASES, ids=[c[0] for c in CONV_CASES])
-def test_conv_layers_vs_torch(dev, case):
-    """Each geometry of the path through stemb200_conv2d_fwd against F.conv2d / F.conv_transpose2d (fp32, CPU)
-    on fp16-representable operands: then the only difference is fp32 accumulation order."""
+def _run_conv_case(dev, case, x, wt, bias):
     from spatiotemporalentropymodel_b200.engine import ConvOp, MASK_A_5x5, nchw_to_nhwc_f16, nhwc_f32_to_nchw
     from spatiotemporalentropymodel_b200._lib import DT_F32
     name, cins, cout, k, stride, transposed, masked, h, w = case
-    g = torch.Generator().manual_seed(11)
-    B, cin = 2, sum(cins)
-    x = (torch.randn((B, cin, h, w), generator=g)).half().float()
-    wshape = (cin, cout, k, k) if transposed else (cout, cin, k, k)
-    wt = (torch.randn(wshape, generator=g) / math.sqrt(cin * k * k)).half().float()
-    bias = torch.randn(cout, generator=g)
+    B = x.shape[0]
     if masked:
         ref = F.conv2d(x, O.masked_weight({"context_prediction.weight": wt}), bias, padding=2)
     elif transposed:
@@ -174,7 +166,68 @@ def test_conv_layers_vs_torch(dev, case):
     got = nhwc_f32_to_nchw(out, torch.empty((B, cout, ho, wo), device=dev)).cpu()
     assert got.shape == ref.shape
     assert torch.isfinite(got).all()
+    return got, ref
+
+
+@pytest.mark.parametrize("case", CONV_CASES, ids=[c[0] for c in CONV_CASES])
+def test_conv_layers_vs_torch(dev, case):
+    """Each geometry of the path through stemb200_conv2d_fwd against F.conv2d / F.conv_transpose2d (fp32, CPU).
+    (a) fp16-representable operands: the only difference left is the fp32 accumulation order - tight absolute bound
+    (catches any indexing / tap / padding error); (b) arbitrary fp32 operands, as a checkpoint and real activations
+    have them: the operands are rounded to fp16 on the way to the tensor core (kind::f16, 11-bit significands), and
+    the result must stay within the error that rounding allows - relative RMS ~ 2^-11 * sqrt(2/3) ~ 4e-4 against the
+    exact fp32 convolution, with no bias (mean error << RMS error)."""
+    name, cins, cout, k, stride, transposed, masked, h, w = case
+    g = torch.Generator().manual_seed(11)
+    B, cin = 2, sum(cins)
+    x32 = torch.randn((B, cin, h, w), generator=g)
+    wshape = (cin, cout, k, k) if transposed else (cout, cin, k, k)
+    wt32 = torch.randn(wshape, generator=g) / math.sqrt(cin * k * k)
+    bias = torch.randn(cout, generator=g)
+    got, ref = _run_conv_case(dev, case, x32.half().float(), wt32.half().float(), bias)
     assert float((got - ref).abs().max()) < 2e-4 * max(1.0, float(ref.abs().max()))
+    got, ref = _run_conv_case(dev, case, x32, wt32, bias)
+    d = (got - ref).double()
+    noise = ref - bias.reshape(1, -1, 1, 1)   # the part of the output the rounded operands produce
+    rel = float(torch.sqrt((d ** 2).mean() / (noise.double() ** 2).mean()))
+    assert rel < 6e-4, rel
+    assert abs(float(d.mean())) < 0.1 * float(d.std()) + 1e-7, (float(d.mean()), float(d.std()))
+
+
+@pytest.mark.parametrize("scale", [1.0, 100.0, 400.0])
+def test_activation_range_of_the_fused_gdn_layers(dev, scale):
+    """fp16 range check: conv + GDN / deconv + IGDN with activations `scale` times larger than the
+    synthetic checkpoints produce. The kernel carries x^2 as (x/8)^2 in fp16, so |x| up to ~2047 stays finite; GDN
+    output is bounded by 1/sqrt(gamma_ii) whatever the input, IGDN grows quadratically (and a trained IGDN sees the
+    small, normalised values GDN made). Outputs must stay finite and within the fp16-operand error of the oracle."""
+    from spatiotemporalentropymodel_b200.engine import ConvOp, _gdn_fold, nchw_to_nhwc_f16, nhwc_f16_to_nchw
+    g = torch.Generator().manual_seed(5)
+    C, B, h, w = 192, 1, 24, 40
+    ped = torch.tensor([2.0 ** -36])
+    beta_p = torch.sqrt(torch.max(1.0 + 0.5 * torch.rand(C, generator=g) + ped, ped))
+    gamma_p = torch.sqrt(torch.max(0.1 * torch.eye(C) + 0.02 * torch.rand((C, C), generator=g) + ped, ped))
+    beta, gamma = _gdn_fold(beta_p.to(dev), gamma_p.to(dev))
+    for inverse in (False, True):
+        # pre-activation |x| ~ scale (GDN) / ~ scale / 30 (IGDN: output ~ x^2 * sqrt(sum gamma) must fit fp16)
+        amp = scale if not inverse else scale / 30.0
+        x = torch.randn((B, C, h, w), generator=g)
+        wt = amp * torch.randn((C, C, 5, 5), generator=g) / math.sqrt(C * 25 / (4 if inverse else 1))
+        bias = 0.3 * amp * torch.randn(C, generator=g)
+        if inverse:
+            pre = F.conv_transpose2d(x.half().float(), wt.half().float(), bias, stride=2, padding=2, output_padding=1)
+        else:
+            pre = F.conv2d(x.half().float(), wt.half().float(), bias, stride=2, padding=2)
+        assert float(pre.abs().max()) < 2000.0          # inside the range the (x/8)^2 trick covers
+        ref = O.gdn(pre, beta_p, gamma_p, inverse)
+        op = ConvOp(wt.to(dev), bias.to(dev), c_in=[C], c_out=C, k=5, stride=2, transposed=inverse,
+                    gdn=(beta, gamma, inverse))
+        x16 = nchw_to_nhwc_f16(x.to(dev), torch.empty((B, h, w, C), dtype=torch.float16, device=dev))
+        ho, wo = op.out_hw(h, w)
+        out = op([x16], B, h, w, torch.full((B, ho, wo, C), float("nan"), dtype=torch.float16, device=dev))
+        got = nhwc_f16_to_nchw(out, torch.empty((B, C, ho, wo), device=dev)).cpu()
+        assert torch.isfinite(got).all(), (scale, inverse)
+        assert float(ref.abs().max()) < 6.0e4
+        assert rel_rms(got, ref) < 1.5e-3, (scale, inverse, rel_rms(got, ref))
 
 
 GDN_CASES = [("conv5s2_gdn", False, False, 20, 28), ("deconv5_igdn", True, True, 9, 13), ("gemm_gdn", None, False, 12, 20),
@@ -479,3 +532,31 @@ def test_run_gop_streams_graph_replays_bit_identical_to_forward_gop(dev, variant
         for a, b in zip(got, want[i]):
             assert torch.equal(a, b), (variant, i)
     assert len(pipe._graphed) == 1
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("variant", ["SpatioTemporalPriorModel", "SpatioTemporalPriorModel_Res",
+                                     "SpatioTemporalPriorModelWithoutSPM"])
+def test_stream_overlap_levels_are_bit_identical(dev, variant, monkeypatch):
+    """STEMB200_OVERLAP = 0 (one stream) / 1 (TPM + context beside HE -> EB -> HD) / 2 (+ synthesis beside the entropy
+    model): the same kernels on the same buffers, only their stream assignment changes - identical results, eagerly and
+    through the captured graph of run_gop."""
+    net, stem, pipe, _, _ = _models(variant, "default", dev)
+    H, W, T = 120, 200, 3
+    frames = S.make_frames(T, H, W, seed=41).to(dev)
+    cond = S.make_latent(1, 192, 8, 16, seed=6).to(dev)
+    keys = ("stats", "y_hat", "lik_y", "lik_z", "x_hat_padded")
+    want = None
+    for level in ("0", "1", "2"):
+        monkeypatch.setenv("STEMB200_OVERLAP", level)
+        got = {k: v.clone() for k, v in pipe.forward_gop(frames, cond).items() if k in keys}
+        torch.cuda.synchronize()
+        if want is None:
+            want = got
+        for k in keys:
+            assert torch.equal(got[k], want[k]), (level, k)
+    monkeypatch.setenv("STEMB200_OVERLAP", "2")
+    for _ in range(3):
+        got = pipe.run_gop(frames, cond)
+        for k in keys:
+            assert torch.equal(got[k], want[k]), ("run_gop", k)
