@@ -399,7 +399,22 @@ def parity_report(pipe, variant, frames8_host, y_cond0_host, sd_i, sd_s, out, n_
     serial = "WithoutSPM" in variant
     n = min(n_frames, frames8_host.shape[0])
     ref, dt, cores = cpu_reference_gop(variant, to_float(frames8_host[:n]), y_cond0_host, sd_i, sd_s)
-    params = None if serial else pipe.stem.ws._bufs.get("gparams")
+    params = None
+    if not serial:
+        # sigma | mu are not in HBM on the shipped (fused) path: one extra pass with the separate kernels for the report
+        out = {k: (v.clone() if torch.is_tensor(v) else v) for k, v in out.items()}
+        prev = os.environ.get("STEMB200_FUSE_GC")
+        os.environ["STEMB200_FUSE_GC"] = "0"
+        try:
+            dev = out["stats"].device
+            pipe.forward_gop(frames8_host[:n].to(dev), y_cond0_host.to(dev))
+            torch.cuda.synchronize()
+        finally:
+            if prev is None:
+                os.environ.pop("STEMB200_FUSE_GC")
+            else:
+                os.environ["STEMB200_FUSE_GC"] = prev
+        params = pipe.stem.ws._bufs.get("gparams")
     rep = P.gop_parity(out, ref, H, W, params)
     keep = ("ok", "max_bpp_rel_err", "max_psnr_abs_err", "max_y_hat_mismatch_frac", "max_sigma_rel_rms",
             "max_mu_err_over_sigma_rms", "gates")

@@ -209,6 +209,17 @@ int stemb200_gaussian_conditional_fwd_cond32(const float* y_nchw, const float* c
                                              int32_t n_scales, float scale_bound, float lik_bound, int32_t yhat_mode,
                                              float* y_hat_nchw, float* lik_nchw, int32_t* idx_nchw, int32_t* sym_nchw,
                                              double* bits, void* stream);
+/* entropy_parameters' last 1x1 layer and GaussianConditional in ONE kernel (BASELINE north_star item 2; reference:
+ * spatiotemporalpriors.py:577-579 = EPM[4] -> chunk -> gaussian_conditional): (sigma | mu) stay in TMEM / registers and
+ * never reach HBM. d: the 1x1 layer (c_in = 576, c_out = 2 C, no activation); packed_weight / bias: the layer's rows
+ * INTERLEAVED per 64 channels - rows [128 t, 128 t + 64) = sigma of channels [64 t, 64 t + 64), rows [128 t + 64,
+ * 128 t + 128) = mu of the same channels (pack them with stemb200_conv2d_pack_weight after reordering). y: NHWC fp32
+ * [batch][h][w][C]; cond_f16 / yhat_mode / outputs / bits as in stemb200_gaussian_conditional_fwd (no indexes /
+ * symbols: the forward pass). Bit-identical to stemb200_conv2d_fwd (fp32 out) + stemb200_gaussian_conditional_fwd. */
+int stemb200_conv2d_gc_fwd(const stemb200_conv_desc* d, const void* const* in, const void* packed_weight,
+                           const float* bias, const float* y_nhwc, const void* cond_f16, float scale_bound,
+                           float lik_bound, int32_t yhat_mode, float* y_hat_nchw, float* lik_nchw, double* bits,
+                           void* stream);
 /* Same arithmetic on flat arrays (no layout change); the isolated parity test of a9 runs through this. */
 int stemb200_gaussian_conditional_flat(const float* y, const float* scales, const float* means,
                                        int64_t numel, const float* scale_table, int32_t n_scales,

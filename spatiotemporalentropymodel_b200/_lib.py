@@ -52,6 +52,8 @@ SIGNATURES = {
     "stemb200_conv2d_gdn_fwd": (C.c_int, [C.POINTER(ConvDesc), C.POINTER(_vp), _vp, _vp, _vp, _vp, _i32, _vp, _vp]),
     "stemb200_conv2d_gdn_last_fwd": (C.c_int, [C.POINTER(ConvDesc), C.POINTER(_vp), _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                                                _vp]),
+    "stemb200_conv2d_gc_fwd": (C.c_int, [C.POINTER(ConvDesc), C.POINTER(_vp), _vp, _vp, _vp, _vp, _f32, _f32, _i32, _vp, _vp,
+                                         _vp, _vp]),
     "stemb200_synthesis_col_index": (C.c_int, [_i32, _i32, _i32]),
     "stemb200_synthesis_col2im": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _vp, _i32, _i32, _i32, _i32, _vp, _i32,
                                             _vp]),

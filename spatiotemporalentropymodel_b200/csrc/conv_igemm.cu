@@ -31,6 +31,7 @@
 #include <vector>
 
 #include "../../include/stemb200.h"
+#include "gc_math.cuh"
 #include "internal.h"
 #include "ptx.cuh"
 
@@ -1443,6 +1444,226 @@ conv_gdn_pp_kernel(const __grid_constant__ ConvKernelParams p) {
 }
 
 // =====================================================================================================
+// entropy_parameters' last layer fused with GaussianConditional (BASELINE.json north_star item 2: "the means and
+// scales never round-trip HBM").
+//
+//   (sigma | mu) = EPM.4(e2) + bias           1x1 contraction, accumulator in TMEM (double buffered)
+//   y_hat, L, -sum log2 L = GaussianConditional(y [- cond], sigma, mu)      in the epilogue, straight from TMEM
+//
+// The weight rows are interleaved on the host per 64 channels: N tile nt (BLOCK_N = 128 accumulator columns) holds
+// sigma of channels [64 nt, 64 nt + 64) in columns [0, 64) and mu of the same channels in columns [64, 128), so a
+// thread owns both parameters of its elements. 16 epilogue warps (warp e: TMEM lane group e % 4 = 32 pixels, channel
+// quarter e / 4 = 16 channels): the GaussianConditional arithmetic is ~200 instructions per element (two erfcf, two
+// IEEE divisions - gc_math.cuh, the reference's formula), 20x the MMA time of the tile, so the epilogue is what the
+// kernel runs at and it needs every issue slot it can get. Outputs go to NCHW fp32 (the API layout) directly from
+// registers: a warp's 32 pixels are consecutive along the tile's rows. Replaces entropy_models.py:588-596 behind
+// spatiotemporalpriors.py:577-579 without sigma / mu (2 x 4 B per element written + read) ever reaching HBM.
+// Single-CTA mode only (EPM.4 has an odd tile count per frame batch at 1080p, so it never ran in cluster mode).
+// =====================================================================================================
+constexpr int kGcFuseEpiWarps = 16;
+constexpr int kGcFuseEpiThreads = kGcFuseEpiWarps * 32;
+constexpr int kGcFuseThreads = 128 + kGcFuseEpiThreads;
+constexpr int kGcFuseN = 128;
+
+struct GcFuseParams {
+  const float* y;       // NHWC fp32 [batch][h][w][C]
+  const __half* cond;   // NHWC fp16 or null: the coded quantity is y - cond (_Res)
+  float* y_hat;         // NCHW fp32 or null
+  float* lik;           // NCHW fp32 or null
+  double* bits;         // [batch] or null: += sum(-log2 lik)
+  int C, hw;
+  float scale_bound, lik_bound;
+  int yhat_mode;
+};
+
+__global__ void __launch_bounds__(kGcFuseThreads, 1)
+conv_gc_kernel(const __grid_constant__ ConvKernelParams p, const __grid_constant__ GcFuseParams g) {
+  constexpr int BLOCK_N = kGcFuseN;
+  using Cfg = ConvCfg<BLOCK_N>;
+  constexpr int kStages = Cfg::kStages;
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t stage_base = smem_base;
+  const uint32_t bar_base = smem_base + kStages * Cfg::kStageBytes;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (kStages + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * kStages + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * kStages + 2 + a); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * kStages + 4);
+
+  const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);
+  const int lane = threadIdx.x & 31;
+  const int q_first = static_cast<int>(blockIdx.x), q_stride = static_cast<int>(gridDim.x);
+  const int n_items = p.total_tiles;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.a_map[0]);
+    tma_prefetch_desc(&p.b_map);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull_bar(a), 1);
+      mbar_init(tempty_bar(a), kGcFuseEpiWarps);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, Cfg::kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  tmem_base = __shfl_sync(0xffffffffu, tmem_base, 0);
+
+  const uint32_t a_tx_bytes = static_cast<uint32_t>(p.tile_h * p.tile_w) * 128u;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    const bool leader = elect_one();
+    int s = 0;
+    uint32_t ph = 0;
+    for (int tile = q_first; tile < n_items; tile += q_stride) {
+      const TileCoord t = decode_tile(p, tile, 0, BLOCK_N);
+      const int kbeg = p.sub_kbeg[0], kend = p.sub_kend[0];
+      for (int k = kbeg; k < kend; ++k) {
+        mbar_wait(empty_bar(s), ph ^ 1u);
+        const uint32_t e = p.ksteps[k];
+        const int map = e & 3;
+        const int dh = static_cast<int>((e >> 2) & 15u) - 8;
+        const int dw = static_cast<int>((e >> 6) & 15u) - 8;
+        const int c0 = static_cast<int>(e >> 10);
+        const uint32_t a_dst = stage_base + s * Cfg::kStageBytes;
+        if (leader) {
+          mbar_arrive_expect_tx(full_bar(s), a_tx_bytes + Cfg::kBStageBytes);
+          tma_load_4d(a_dst, &p.a_map[map], full_bar(s), c0, t.w0 + dw, t.h0 + dh, t.n_img);
+          tma_load_2d(a_dst + kAStageBytes, &p.b_map, full_bar(s), k * kKChunk, t.n0);
+        }
+        if (++s == kStages) {
+          s = 0;
+          ph ^= 1u;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    const bool leader = elect_one();
+    constexpr uint32_t idesc = umma_idesc(/*F16*/ 0u, 128u, BLOCK_N);
+    int s = 0;
+    uint32_t ph = 0;
+    int it = 0;
+    for (int tile = q_first; tile < n_items; tile += q_stride, ++it) {
+      const int kbeg = p.sub_kbeg[0], kend = p.sub_kend[0];
+      const int acc = it & 1;
+      const uint32_t accph = (it >> 1) & 1;
+      mbar_wait(tempty_bar(acc), accph ^ 1u);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+      for (int k = kbeg; k < kend; ++k) {
+        mbar_wait(full_bar(s), ph);
+        tc_fence_after();
+        const uint32_t a_addr = stage_base + s * Cfg::kStageBytes;
+        const uint64_t adesc = umma_desc_sw128(a_addr);
+        const uint64_t bdesc = umma_desc_sw128(a_addr + kAStageBytes);
+        if (leader) {
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk)
+            mma_f16_ss(d_tmem, adesc + 2u * kk, bdesc + 2u * kk, idesc, (k > kbeg || kk > 0) ? 1u : 0u);
+          mma_commit(empty_bar(s));
+        }
+        if (++s == kStages) {
+          s = 0;
+          ph ^= 1u;
+        }
+      }
+      if (leader) mma_commit(tfull_bar(acc));
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue: GaussianConditional on the accumulator =====================
+    const int e = warp - 4;
+    const int row = (e & 3) * 32 + lane;  // accumulator row == pixel of the patch
+    const int q = e >> 2;                 // 16-channel quarter of the tile's 64 channels
+    const uint32_t lane_off = static_cast<uint32_t>((e & 3) * 32) << 16;
+    const int npix = p.tile_h * p.tile_w;
+    const int C = g.C;
+    int it = 0;
+    for (int tile = q_first; tile < n_items; tile += q_stride, ++it) {
+      const TileCoord t = decode_tile(p, tile, 0, BLOCK_N);
+      const int acc = it & 1;
+      const uint32_t accph = (it >> 1) & 1;
+      const int th = row / p.tile_w, tw = row - th * p.tile_w;
+      const int oh = t.h0 + th, ow = t.w0 + tw;
+      const bool inb = (row < npix) && (oh < p.h_out) && (ow < p.w_out);
+      const int pix = oh * p.w_out + ow;               // pixel inside the frame
+      const int ch0 = (t.n0 >> 1) + 16 * q;            // first latent channel of this thread
+      mbar_wait(tfull_bar(acc), accph);
+      tc_fence_after();
+      uint32_t rs[16], rm[16];
+      const uint32_t t_row = tmem_base + lane_off + acc * BLOCK_N;
+      tmem_ld_32x16(t_row + 16 * q, rs);
+      tmem_ld_32x16(t_row + 64 + 16 * q, rm);
+      tmem_ld_wait();
+      // the accumulator is in registers: hand it back to the MMA warp before the long arithmetic starts
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(acc));
+      float bits = 0.f;
+      if (inb) {
+        const long long e0 = (static_cast<long long>(t.n_img) * g.hw + pix) * C + ch0;
+        const long long o0 = (static_cast<long long>(t.n_img) * C + ch0) * g.hw + pix;
+        const float4* bsp = reinterpret_cast<const float4*>(p.bias + t.n0 + 16 * q);
+        const float4* bmp = reinterpret_cast<const float4*>(p.bias + t.n0 + 64 + 16 * q);
+        const float4* yp = reinterpret_cast<const float4*>(g.y + e0);
+        const uint2* cp = g.cond ? reinterpret_cast<const uint2*>(g.cond + e0) : nullptr;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {  // 4 channels per round: one 16-byte load of y, sigma bias, mu bias each
+          const float4 y4 = __ldg(yp + j), bs4 = __ldg(bsp + j), bm4 = __ldg(bmp + j);
+          float c4[4] = {0.f, 0.f, 0.f, 0.f};
+          if (cp) {
+            const uint2 u = __ldg(cp + j);
+            const float2 f0 = __half22float2(*reinterpret_cast<const __half2*>(&u.x));
+            const float2 f1 = __half22float2(*reinterpret_cast<const __half2*>(&u.y));
+            c4[0] = f0.x, c4[1] = f0.y, c4[2] = f1.x, c4[3] = f1.y;
+          }
+          const float yy[4] = {y4.x, y4.y, y4.z, y4.w};
+          const float bsv[4] = {bs4.x, bs4.y, bs4.z, bs4.w};
+          const float bmv[4] = {bm4.x, bm4.y, bm4.z, bm4.w};
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const int i = 4 * j + k;
+            const float sigma = __fadd_rn(__uint_as_float(rs[i]), bsv[k]);
+            const float mu = __fadd_rn(__uint_as_float(rm[i]), bmv[k]);
+            const float v = __fsub_rn(yy[k], c4[k]);
+            GcOut o = gc_eval(v, sigma, mu, nullptr, 0, g.scale_bound, g.lik_bound, false);
+            if (g.yhat_mode == 1) o.y_hat = __fadd_rn(rintf(v), c4[k]);
+            const long long oi = o0 + static_cast<long long>(i) * g.hw;
+            if (g.y_hat) g.y_hat[oi] = o.y_hat;
+            if (g.lik) g.lik[oi] = o.lik;
+            bits -= __log2f(o.lik);
+          }
+        }
+      }
+      if (g.bits) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) bits += __shfl_xor_sync(0xffffffffu, bits, o);
+        if (lane == 0) atomicAdd(g.bits + t.n_img, static_cast<double>(bits));
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, Cfg::kTmemCols);
+}
+
+// =====================================================================================================
 // weight repack: PyTorch OIHW (or IOHW for ConvTranspose2d) fp32 -> [c_out][K] fp16, K ordered like the
 // kernel's k-step table
 // =====================================================================================================
@@ -2194,4 +2415,54 @@ extern "C" int stemb200_conv2d_gdn_last_fwd(const stemb200_conv_desc* d, const v
                                             void* stream) {
   if (!packed_w6) return set_error("conv2d_gdn_last_fwd: null W6");
   return gdn_forward(d, in, packed_weight, bias, packed_gamma, beta, 1, act_out, packed_w6, col_out, stream);
+}
+
+// entropy_parameters' last layer + GaussianConditional in one kernel (conv_gc_kernel above)
+extern "C" int stemb200_conv2d_gc_fwd(const stemb200_conv_desc* d, const void* const* in, const void* packed_weight,
+                                      const float* bias, const float* y_nhwc, const void* cond_f16, float scale_bound,
+                                      float lik_bound, int32_t yhat_mode, float* y_hat_nchw, float* lik_nchw,
+                                      double* bits, void* stream) {
+  if (!d || !in || !in[0] || !packed_weight || !bias || !y_nhwc) return set_error("conv2d_gc_fwd: null argument");
+  if (d->kh != 1 || d->stride != 1 || d->transposed || d->n_src != 1 || d->c_out % 128 || d->tap_mask ||
+      d->epilogue != STEMB200_EPI_LINEAR || d->lrelu_slope != 1.0f || d->direct_store)
+    return set_error("conv2d_gc_fwd: needs a plain 1x1 layer with c_out = 2 C, C % 64 == 0, no activation");
+  if (reinterpret_cast<uintptr_t>(y_nhwc) & 15 || reinterpret_cast<uintptr_t>(cond_f16) & 15 ||
+      reinterpret_cast<uintptr_t>(bias) & 15)
+    return set_error("conv2d_gc_fwd: y, cond and bias must be 16-byte aligned");
+  stemb200_conv_desc dd = *d;
+  dd.out_dtype = STEMB200_DT_F32;
+  Plan pl;
+  if (int rc = build_plan(dd, pl)) return rc;
+  pl.block_n = kGcFuseN;
+  ConvKernelParams kp;
+  // no activation tensor is written: the store maps are built over y (never dereferenced)
+  dd.direct_store = 1;
+  if (int rc = setup_params(&dd, pl, in, packed_weight, bias, nullptr, const_cast<float*>(y_nhwc), kp)) return rc;
+  kp.csize = 1;
+  kp.duo = 0;
+  GcFuseParams g;
+  g.y = y_nhwc;
+  g.cond = static_cast<const __half*>(cond_f16);
+  g.y_hat = y_hat_nchw;
+  g.lik = lik_nchw;
+  g.bits = bits;
+  g.C = d->c_out / 2;
+  g.hw = d->h_in * d->w_in;
+  g.scale_bound = scale_bound;
+  g.lik_bound = lik_bound;
+  g.yhat_mode = yhat_mode;
+  using Cfg = ConvCfg<kGcFuseN>;
+  constexpr int kSmem = 1024 + Cfg::kStages * Cfg::kStageBytes + 256;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(conv_gc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
+    if (e != cudaSuccess) return set_cuda_error("cudaFuncSetAttribute(conv_gc)", e);
+    configured = true;
+  }
+  const int grid = std::min(kp.total_tiles, num_sms());
+  conv_gc_kernel<<<grid, kGcFuseThreads, kSmem, static_cast<cudaStream_t>(stream)>>>(kp, g);
+  count_launch();
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_cuda_error("conv_gc launch", e);
+  return 0;
 }

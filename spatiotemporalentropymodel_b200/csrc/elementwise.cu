@@ -9,6 +9,7 @@
 #include <cstdint>
 
 #include "../../include/stemb200.h"
+#include "gc_math.cuh"
 #include "internal.h"
 #include "ptx.cuh"
 
@@ -308,43 +309,6 @@ __global__ void latent_stage_kernel(const float* __restrict__ y, const __half* _
 // ---------------------------------------------------------------------------------------------------
 // GaussianConditional arithmetic (entropy_models.py:122-150, 521-526, 570-604; bound_ops.py:50-53)
 // ---------------------------------------------------------------------------------------------------
-struct GcOut {
-  float y_hat, lik;
-  int idx, sym;
-};
-
-__device__ __forceinline__ float lower_bound(float x, float b) {
-  // torch.max(x, bound): NaN propagates
-  return (x != x) ? x : fmaxf(x, b);
-}
-
-__device__ __forceinline__ GcOut gc_eval(float y, float sigma, float mu, const float* __restrict__ table,
-                                         int n_scales, float scale_bound, float lik_bound, bool want_idx) {
-  GcOut o;
-  const float t = rintf(y - mu);  // torch.round: half to even
-  o.sym = static_cast<int>(t);
-  o.y_hat = t + mu;
-  const float v = fabsf(o.y_hat - mu);  // likelihood is evaluated at the de-quantised value
-  const float s = lower_bound(sigma, scale_bound);
-  const float c = -0.70710678118654752440f;  // float(-(2 ** -0.5))
-  const float upper = 0.5f * erfcf(c * ((0.5f - v) / s));
-  const float lower = 0.5f * erfcf(c * ((-0.5f - v) / s));
-  o.lik = lower_bound(upper - lower, lik_bound);
-  o.idx = 0;
-  if (want_idx) {
-    // idx = (n-1) - #{k < n-1 : s <= table[k]} == first k in [0, n-1) with s <= table[k] (table ascending),
-    // n-1 when there is none (also for NaN, where every comparison is false)
-    int lo = 0, hi = n_scales - 1;
-    while (lo < hi) {
-      const int mid = (lo + hi) >> 1;
-      if (s <= table[mid]) hi = mid;
-      else lo = mid + 1;
-    }
-    o.idx = lo;
-  }
-  return o;
-}
-
 __global__ void gc_flat_kernel(const float* __restrict__ y, const float* __restrict__ scales,
                                const float* __restrict__ means, long long numel,
                                const float* __restrict__ table_g, int n_scales, float scale_bound,
@@ -398,10 +362,10 @@ __device__ __forceinline__ float gc_tile_eval(const float* __restrict__ yp, cons
 #pragma unroll
   for (int k = 0; k < kIter; ++k) {
     if (kFull || 4 * k < lim) {
-      const float v = yv[k] - cv[k];  // _Res: the coded quantity is y_cur - y_conditioned (:852)
+      const float v = __fsub_rn(yv[k], cv[k]);  // _Res: the coded quantity is y_cur - y_conditioned (:852)
       GcOut o = gc_eval(v, sg[k], mu[k], table, n_scales, scale_bound, lik_bound, want_idx);
       // SPM variants return y_hat = round(y [- cond]) [+ cond] (:570, :856-868), not the GC output
-      if (yhat_mode == 1) o.y_hat = rintf(v) + cv[k];
+      if (yhat_mode == 1) o.y_hat = __fadd_rn(rintf(v), cv[k]);
       s_yhat[4 * k] = o.y_hat;
       s_lik[4 * k] = o.lik;
       if (kIdx) {

@@ -40,6 +40,15 @@ def _require_cuda(*ts: Tensor) -> None:
                                "there is no CPU fallback")
 
 
+def fuse_gc_enabled() -> bool:
+    """entropy_parameters' last layer and GaussianConditional run as one kernel in the GOP pipeline (sigma, mu never in
+    HBM; BASELINE north_star item 2). On by default: bit-identical to the two separate kernels, 155 us instead of
+    65 + 119 us per 11 x 1080p latents and 226 MB less DRAM traffic (profiles/r02_ncu_fused_gc.txt). STEMB200_FUSE_GC=0
+    selects the separate kernels (which also leave sigma | mu in the workspace buffer "gparams")."""
+    import os
+    return os.environ.get("STEMB200_FUSE_GC", "1") != "0"
+
+
 def overlap_level() -> int:
     """STEMB200_OVERLAP: 0 = one stream; 1 = the temporal-prior / context chain runs beside the hyper-prior chain;
     2 (default) = in addition the synthesis transform of a GOP runs beside its entropy model (SPM variants, where
@@ -621,6 +630,12 @@ class StemEngine:
             ConvOp(g("EPM.2.weight"), g("EPM.2.bias"), c_in=[768], c_out=576, k=1, slope=lre),
             ConvOp(g("EPM.4.weight"), g("EPM.4.bias"), c_in=[576], c_out=C2, k=1, out_dtype=DT_F32),
         ]
+        # EPM.4 with its rows interleaved per 64 channels (sigma 64 | mu 64) for the fused EPM.4 + GaussianConditional kernel
+        w4, b4 = g("EPM.4.weight"), g("EPM.4.bias")
+        order = torch.cat([torch.cat([torch.arange(c0, c0 + 64), torch.arange(Cc + c0, Cc + c0 + 64)])
+                           for c0 in range(0, Cc, 64)]).to(dev) if Cc % 64 == 0 else None
+        self.epm4_gc = None if order is None else ConvOp(w4[order].contiguous(), b4[order].contiguous(), c_in=[576],
+                                                         c_out=C2, k=1, out_dtype=DT_F32)
         self._ar = None
         if has_spm:
             self._ar_spec = (g("context_prediction.weight") * g("context_prediction.mask"), g("context_prediction.bias"),
@@ -685,7 +700,7 @@ class StemEngine:
 
     def gaussian_params(self, y16: Tensor, cond16: Tensor, yq16: Optional[Tensor], B: int, h: int, w: int,
                         z_hat_nchw: Optional[Tensor] = None, z_lik_nchw: Optional[Tensor] = None,
-                        bits_z: Optional[Tensor] = None) -> Tensor:
+                        bits_z: Optional[Tensor] = None, fused_gc: Optional[dict] = None) -> Optional[Tensor]:
         """HE -> EntropyBottleneck -> HD, TPM, context, EPM. Returns params NHWC fp32 (B, h, w, 2C).
         TPM(y_cond) and context(y_q) depend only on the inputs, HE -> EB -> HD is a chain of small launches (55-148
         tiles at 1080p): the two branches run on two streams and meet at EPM.0 (STEMB200_OVERLAP >= 1)."""
@@ -710,17 +725,36 @@ class StemEngine:
                                                        _ptr(z_lik_nchw), _ptr(bits_z), _stream()),
                    "entropy_bottleneck_fwd")
         if side is None:
-            return self.params_from_zhat(zhat16, cond16, yq16, B, h, w)
+            srcs = self.static_priors(zhat16, cond16, B, h, w)
+            if self.has_spm:
+                srcs.append(self.ctx([yq16], B, h, w, ws.get("ctx", (B, h, w, 2 * self.C), f16)))
+            return self.entropy_parameters(srcs, B, h, w, fused_gc)
         hp = self.hyper_prior(zhat16, B, h, w)
         side.join()
-        return self.entropy_parameters([t for t in (tp, hp, ctx) if t is not None], B, h, w)
+        return self.entropy_parameters([t for t in (tp, hp, ctx) if t is not None], B, h, w, fused_gc)
 
-    def entropy_parameters(self, srcs: Sequence[Tensor], B: int, h: int, w: int) -> Tensor:
-        """EPM on cat(tp | hp | ctx) (:576-577) -> (scales | means) NHWC fp32."""
+    def entropy_parameters(self, srcs: Sequence[Tensor], B: int, h: int, w: int,
+                           fused_gc: Optional[dict] = None) -> Optional[Tensor]:
+        """EPM on cat(tp | hp | ctx) (:576-577) -> (scales | means) NHWC fp32.  fused_gc = {"y": NHWC fp32, "cond16",
+        "y_hat", "lik", "bits"}: the last layer runs with GaussianConditional in its epilogue (:578-579,
+        stemb200_conv2d_gc_fwd), nothing is returned and sigma / mu never exist in HBM."""
         ws, f16 = self.ws, torch.float16
         e1 = self.epm[0](list(srcs), B, h, w, ws.get("e1", (B, h, w, self.epm[0].c_out), f16))
         e2 = self.epm[1]([e1], B, h, w, ws.get("e2", (B, h, w, self.epm[1].c_out), f16))
-        return self.epm[2]([e2], B, h, w, ws.get("gparams", (B, h, w, 2 * self.C), torch.float32))
+        if fused_gc is None:
+            return self.epm[2]([e2], B, h, w, ws.get("gparams", (B, h, w, 2 * self.C), torch.float32))
+        op = self.epm4_gc
+        if op is None:
+            raise ValueError("the fused EPM.4 + GaussianConditional kernel needs a channel count that is a multiple of 64")
+        d = op.desc
+        d.batch, d.h_in, d.w_in = B, h, w
+        arr = (C.c_void_p * 1)(e2.data_ptr())
+        _lib.check(op.lib.stemb200_conv2d_gc_fwd(
+            C.byref(d), arr, op.packed.data_ptr(), op.bias.data_ptr(), fused_gc["y"].data_ptr(),
+            _ptr(fused_gc.get("cond16") if self.residual else None), self.scale_bound, self.lik_bound,
+            1 if self.has_spm else 0, _ptr(fused_gc.get("y_hat")), _ptr(fused_gc.get("lik")), _ptr(fused_gc.get("bits")),
+            _stream()), "conv2d_gc_fwd")
+        return None
 
     def gaussian_conditional(self, y: Tensor, y_is_nchw: bool, cond16: Optional[Tensor], params: Tensor, B: int,
                              h: int, w: int, y_hat: Optional[Tensor], lik: Optional[Tensor],
@@ -824,6 +858,7 @@ class IFrameEntropyEngine(StemEngine):
         ]
         self._ar = None
         self._side = None
+        self.epm4_gc = None
         self._ar_spec = (g("context_prediction.weight") * g("context_prediction.mask"), g("context_prediction.bias"),
                          ep, [C2])
         self.eb_params = eb_packed.detach().to(dev, torch.float32).contiguous()
@@ -951,9 +986,14 @@ class PFramePipeline:
                 side = self._side
                 with side:
                     x_hat = tr.synthesis(yhat_all[1:], x_ref=frames.contiguous(), pad=pad, sq_err=stats[2], out=None)
-            params = st.gaussian_params(y16, cond16, yq16, T, h, w, None, outs.get("lik_z"), stats[1])
-            st.gaussian_conditional(y32, False, cond16, params, T, h, w, outs.get("y_hat"), outs.get("lik_y"),
-                                    bits=stats[0])
+            if fuse_gc_enabled() and st.epm4_gc is not None:
+                st.gaussian_params(y16, cond16, yq16, T, h, w, None, outs.get("lik_z"), stats[1],
+                                   fused_gc={"y": y32, "cond16": cond16, "y_hat": outs.get("y_hat"),
+                                             "lik": outs.get("lik_y"), "bits": stats[0]})
+            else:
+                params = st.gaussian_params(y16, cond16, yq16, T, h, w, None, outs.get("lik_z"), stats[1])
+                st.gaussian_conditional(y32, False, cond16, params, T, h, w, outs.get("y_hat"), outs.get("lik_y"),
+                                        bits=stats[0])
             if side is not None:
                 side.join()
                 outs.update(x_hat_padded=x_hat, pad=pad, stats=stats, num_pixels=H * W)
@@ -965,13 +1005,19 @@ class PFramePipeline:
             yh = outs.get("y_hat")
             if yh is None:
                 yh = ws.get("yhat_nchw", (T, Cc, h, w), f32)
+            fuse = fuse_gc_enabled() and st.epm4_gc is not None
             for t in range(T):
                 lz = outs["lik_z"][t:t + 1] if want_outputs else None
-                params = st.gaussian_params(y16[t:t + 1], yhat_all[t:t + 1], None, 1, h, w, None, lz,
-                                            stats[1, t:t + 1])
                 ly = outs["lik_y"][t:t + 1] if want_outputs else None
-                st.gaussian_conditional(y32[t:t + 1], False, None, params, 1, h, w, yh[t:t + 1], ly,
-                                        bits=stats[0, t:t + 1])
+                if fuse:
+                    st.gaussian_params(y16[t:t + 1], yhat_all[t:t + 1], None, 1, h, w, None, lz, stats[1, t:t + 1],
+                                       fused_gc={"y": y32[t:t + 1], "y_hat": yh[t:t + 1], "lik": ly,
+                                                 "bits": stats[0, t:t + 1]})
+                else:
+                    params = st.gaussian_params(y16[t:t + 1], yhat_all[t:t + 1], None, 1, h, w, None, lz,
+                                                stats[1, t:t + 1])
+                    st.gaussian_conditional(y32[t:t + 1], False, None, params, 1, h, w, yh[t:t + 1], ly,
+                                            bits=stats[0, t:t + 1])
                 nchw_to_nhwc_f16(yh[t:t + 1], yhat_all[t + 1:t + 2])
         x_hat = tr.synthesis(yhat_all[1:], x_ref=frames.contiguous(), pad=pad, sq_err=stats[2],
                              out=None)

@@ -83,14 +83,23 @@ def code_pframe_real(net, stem, x: Tensor, y_conditioned: Tensor) -> Dict[str, o
             "bpp": sum(len(s[0]) for s in enc["strings"]) * 8.0 / n_pix}
 
 
+def as_float(frames: Tensor) -> Tensor:
+    """8-bit frames -> what torchvision's ToTensor hands the reference (evalSTEM.py:185): float(v) / 255."""
+    return frames.to(torch.float32).div(255.0) if frames.dtype == torch.uint8 else frames
+
+
 def code_gop(net, stem, frames: Tensor, mode: str = "estimate", all_intra: bool = False) -> List[Tuple[float, float]]:
-    """One GOP (T, 3, H, W) on the models' device -> [(bpp, psnr)] per frame (I-frame first)."""
+    """One GOP (T, 3, H, W) on the models' device -> [(bpp, psnr)] per frame (I-frame first). frames: fp32 in [0, 1]
+    or uint8 (8-bit samples): the batched P-frame pipeline takes the bytes as they are (a quarter of the upload) and
+    evaluates v / 255 on the device, bit-identical to converting first."""
     if mode not in ("estimate", "real"):
         raise ValueError('mode must be "estimate" or "real"')
     T = frames.size(0)
+    if all_intra or mode == "real":
+        frames = as_float(frames)
     if all_intra:
         return [(o["bpp"], o["psnr"]) for o in (code_iframe(net, frames[t:t + 1]) for t in range(T))]
-    out_i = code_iframe(net, frames[0:1])
+    out_i = code_iframe(net, as_float(frames[0:1]))
     rows = [(out_i["bpp"], out_i["psnr"])]
     y_cond = out_i["y_conditioned"]
     if T == 1:
@@ -152,7 +161,8 @@ def eval_dataset(sequences: Sequence[Tuple[str, Callable[[int, int], Tensor], in
 
 
 def png_sequence(path: str, max_index: int) -> Tuple[str, Callable[[int, int], Tensor], int]:
-    """f001.png ... as evalSTEM.py:186 reads them (PIL + ToTensor: uint8 RGB -> fp32 [0, 1] CHW)."""
+    """f001.png ... as evalSTEM.py:186 reads them (PIL RGB); returned as uint8 CHW, ToTensor's scaling happens on
+    the device."""
     import numpy as np
     from PIL import Image
 
@@ -160,8 +170,8 @@ def png_sequence(path: str, max_index: int) -> Tuple[str, Callable[[int, int], T
         out = []
         for i in range(first + 1, first + count + 1):
             img = np.asarray(Image.open(os.path.join(path, f"f{i:03d}.png")).convert("RGB"), dtype=np.uint8)
-            out.append(torch.from_numpy(img.copy()).permute(2, 0, 1).float().div_(255.0))
-        return torch.stack(out)
+            out.append(torch.from_numpy(img.copy()).permute(2, 0, 1))
+        return torch.stack(out).contiguous()   # uint8: code_gop / the CUDA pipeline apply ToTensor's v / 255
 
     return os.path.basename(os.path.normpath(path)), load, max_index
 

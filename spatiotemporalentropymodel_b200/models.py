@@ -347,14 +347,15 @@ class JointAutoregressiveHierarchicalPriors(CompressionModel):
         return self._engine
 
     def getY(self, x: Tensor):
-        """priors.py:686-694: (y, y_quantized). The reference adds U(-1/2, 1/2) noise to the second output even
-        in eval mode and evalSTEM ignores it (:113); here the second output is round(y)."""
+        """priors.py:686-694: (y, y_quantized) with y_quantized = gaussian_conditional.quantize(y, "noise") =
+        y + U(-1/2, 1/2) (entropy_models.py:128-131) - the reference adds the noise even in eval mode; evalSTEM ignores
+        the second output (:113)."""
         from .engine import nhwc_f32_to_nchw
         eng = self.engine()
-        y_nhwc, h, w = eng.analysis(x.float())
+        y_nhwc, h, w = eng.analysis(x if x.dtype == torch.uint8 else x.float())
         y = torch.empty((x.shape[0], self.M, h, w), dtype=torch.float32, device=x.device)
         nhwc_f32_to_nchw(y_nhwc, y)
-        return y, torch.round(y)
+        return y, y + torch.empty_like(y).uniform_(-0.5, 0.5)
 
     def getX(self, y_hat: Tensor) -> Tensor:
         """priors.py:397-402: g_s(y_hat).clamp_(0, 1)"""

@@ -328,9 +328,11 @@ def test_transforms_vs_oracle(dev, golden, calibration):
     net = net.to(dev).eval()
     lo, hi = frame_range(calibration)
     frames = S.make_frames(2, 256, 256, seed=1234, lo=lo, hi=hi)
-    y, yq = net.getY(frames[1:2].to(dev))
+    y, y_noisy = net.getY(frames[1:2].to(dev))
     assert rel_rms(y.cpu(), t(g["y_cur"])) < 2e-3
-    assert float((yq.cpu() != torch.round(t(g["y_cur"]))).float().mean()) < 0.02  # rounding flips stay rare
+    assert float((torch.round(y).cpu() != torch.round(t(g["y_cur"]))).float().mean()) < 0.02  # rounding flips stay rare
+    d = (y_noisy - y).cpu()                                  # quantize(y, "noise"): y + U(-1/2, 1/2) (priors.py:691)
+    assert float(d.abs().max()) <= 0.5 and abs(float(d.mean())) < 0.01 and abs(float(d.std()) - 12 ** -0.5) < 0.01
     x_hat = net.getX(t(g["y_hat"]).to(dev))
     ref = t(g["x_hat"])
     assert x_hat.shape == ref.shape and float(x_hat.min()) >= 0 and float(x_hat.max()) <= 1
@@ -391,7 +393,7 @@ PARITY_1080P = [(v, c) for c in S.CALIBRATIONS for v in ("SpatioTemporalPriorMod
 
 
 @pytest.mark.parametrize("variant,calibration", PARITY_1080P, ids=[f"{v[24:] or 'full'}-{c}" for v, c in PARITY_1080P])
-def test_parity_at_benchmark_size_1080p(dev, variant, calibration):
+def test_parity_at_benchmark_size_1080p(dev, variant, calibration, monkeypatch):
     """The benchmarked workloads at their real size (1080 x 1920, BASELINE.json configs[1-3]) against the oracle's
     evalSTEM loop (stem/evalSTEM.py:93-154, spatiotemporalpriors.py:561-585): per-frame bpp within 0.5 %, PSNR within
     0.01 dB, for both synthetic checkpoints; the serial WithoutSPM chain over 3 frames (y_hat feeds the next frame
@@ -403,9 +405,15 @@ def test_parity_at_benchmark_size_1080p(dev, variant, calibration):
     serial = "WithoutSPM" in variant
     T = 3 if serial else 2
     frames, y_cond0 = _gop_inputs(T, H, W, 1234, calibration, sd_i)
-    out = pipe.forward_gop(frames.to(dev), y_cond0.to(dev))
+    out = pipe.forward_gop(frames.to(dev), y_cond0.to(dev))       # the shipped path (fused EPM.4 + GaussianConditional)
     torch.cuda.synchronize()
-    params = None if serial else pipe.stem.ws._bufs["gparams"]
+    out = {k: (v.clone() if torch.is_tensor(v) else v) for k, v in out.items()}
+    params = None
+    if not serial:  # sigma | mu only exist in HBM when the two kernels run separately
+        monkeypatch.setenv("STEMB200_FUSE_GC", "0")
+        pipe.forward_gop(frames.to(dev), y_cond0.to(dev))
+        torch.cuda.synchronize()
+        params = pipe.stem.ws._bufs["gparams"]
     torch.set_num_threads(max(1, __import__("os").cpu_count() or 1))
     with torch.no_grad():
         ref = O.gop_forward(frames, y_cond0, sd_i, sd_s, variant, return_params=True)
@@ -560,3 +568,32 @@ def test_stream_overlap_levels_are_bit_identical(dev, variant, monkeypatch):
         got = pipe.run_gop(frames, cond)
         for k in keys:
             assert torch.equal(got[k], want[k]), ("run_gop", k)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("variant", ["SpatioTemporalPriorModel", "SpatioTemporalPriorModel_Res",
+                                     "SpatioTemporalPriorModelWithoutSPM"])
+@pytest.mark.parametrize("size", [(120, 200, 3), (272, 480, 2)], ids=["ragged", "many_tiles"])
+def test_fused_entropy_parameters_gaussian_conditional_is_bit_identical(dev, variant, size, monkeypatch):
+    """BASELINE north_star item 2: entropy_parameters' last layer with GaussianConditional in its epilogue
+    (stemb200_conv2d_gc_fwd; sigma and mu never reach HBM) against the two separate kernels - the same MMAs in the same
+    order and the same gc_math.cuh arithmetic, so y_hat and the likelihoods must be identical bit for bit (the bit count,
+    a sum, to 1e-6)."""
+    net, stem, pipe, _, _ = _models(variant, "lowrate", dev)
+    H, W, T = size
+    lo, hi = S.LOWRATE_FRAME_RANGE
+    frames = S.make_frames(T + 1, H, W, seed=43, lo=lo, hi=hi).to(dev)
+    from spatiotemporalentropymodel_b200.evaluate import pad_to_64
+    y0, _ = net.getY(pad_to_64(frames[0:1])[0])
+    cond = torch.round(y0)
+    keys = ("stats", "y_hat", "lik_y", "lik_z", "x_hat_padded")
+    monkeypatch.setenv("STEMB200_FUSE_GC", "0")
+    want = {k: v.clone() for k, v in pipe.forward_gop(frames[1:], cond).items() if k in keys}
+    monkeypatch.delenv("STEMB200_FUSE_GC")   # the default: fused
+    got = pipe.forward_gop(frames[1:], cond)
+    torch.cuda.synchronize()
+    assert float(want["lik_y"].min()) > 0 and torch.isfinite(want["stats"]).all()
+    for k in keys[1:]:
+        assert torch.equal(got[k], want[k]), (k, float((got[k] - want[k]).abs().max()))
+    # the bit counts are sums of the same fp32 terms grouped differently (per warp here, per 256-thread block there)
+    assert torch.allclose(got["stats"], want["stats"], rtol=1e-6, atol=0), (got["stats"], want["stats"])
