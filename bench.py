@@ -475,6 +475,8 @@ def run_pframe_workload(ctx, name, steps, warmup, args, full):
             return r
 
         E.ConvOp.__call__, E.ConvOp.call_last = timed_call, timed_last
+        prev_overlap = os.environ.get("STEMB200_OVERLAP")
+        os.environ["STEMB200_OVERLAP"] = "0"   # one stream: every launch is timed alone, not sharing SMs with a branch
         try:
             for _ in range(2):
                 recs.clear()
@@ -482,6 +484,10 @@ def run_pframe_workload(ctx, name, steps, warmup, args, full):
                 torch.cuda.synchronize()
         finally:
             E.ConvOp.__call__, E.ConvOp.call_last = orig, orig_last
+            if prev_overlap is None:
+                os.environ.pop("STEMB200_OVERLAP")
+            else:
+                os.environ["STEMB200_OVERLAP"] = prev_overlap
         dom = [(a.elapsed_time(b), f) for a, b, f, fused in recs if fused]
         allc = [(a.elapsed_time(b), f) for a, b, f, fused in recs]
         dom_ms, dom_gf = sum(t for t, _ in dom), sum(f for _, f in dom) / 1e9
@@ -495,6 +501,7 @@ def run_pframe_workload(ctx, name, steps, warmup, args, full):
                       "deconv as a GEMM)",
             "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
             "peak_kind": f"bf16 dense sustained (kernel timed inside a long step), {peaks['source']}",
+            "timing": "CUDA events around each launch in an extra eager, single-stream step (STEMB200_OVERLAP=0)",
             "traffic": traffic, "traffic_unit": "bytes per launch (dram read+write, ncu --set full)",
             "traffic_source": traffic_src,
             "launches_per_step": len(dom), "kernel_ms_per_step": dom_ms, "launch_ms": [round(t, 4) for t, _ in dom],

@@ -2195,10 +2195,16 @@ int setup_params(const stemb200_conv_desc* d, const Plan& pl, const void* const*
   const long long tiles_per_sub = static_cast<long long>(d->batch) * kp.tiles_h * kp.tiles_w;
   // (measured +2 % on the MMA-bound 5x5 layers, -2 % on the 160-wide tiles and the epilogue-bound first layer)
   // (the 160-wide tiles lose 2 % in pair mode but gain in duo mode, where each CTA stages 80 of the 160 weight rows)
+  // An odd tile count per sub-problem (11 frames: 2805 tiles in g_a.4 / g_s.2) used to keep a layer out of cluster
+  // mode. The last cluster then gets a phantom second tile: its index runs one past the end and decode_tile wraps it
+  // to tile (0, 0) of image 0, which is simply computed and stored twice with identical values (one tile in thousands;
+  // STEMB200_PHANTOM=0 restores the old rule).
+  static const bool phantom = [] { const char* e = getenv("STEMB200_PHANTOM"); return !(e && e[0] == '0'); }();
+  const bool odd = (tiles_per_sub % 2) != 0;
   if (pair_mode_enabled() && pl.block_n >= 64 && (pl.block_n != 160 || duo_mode_enabled()) && !pl.row_taps &&
-      (tiles_per_sub % 2) == 0 &&
-      total >= 2LL * num_sms()) {
+      (!odd || (phantom && tiles_per_sub >= 255)) && total >= 2LL * num_sms()) {
     kp.csize = 2;
+    if (odd) kp.total_tiles = static_cast<int>(static_cast<long long>(pl.n_sub) * (tiles_per_sub + 1) * kp.n_tiles_n);
     if (int rc = encode_weight(&kp.b_half_map, packed_weight, K, d->c_out, pl.block_n / 2)) return rc;
   }
   kp.kk_main = (pl.row_taps && d->kw * 8 <= 48) ? 3 : 4;

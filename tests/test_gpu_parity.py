@@ -139,13 +139,16 @@ CONV_CASES = [
     ("tpm0_5x5_pairs", [192], 256, 5, 1, False, False, 136, 240),
     ("hd0_deconv_pairs", [256], 256, 5, 2, True, False, 68, 120),
     ("tpm2_320_big", [256], 320, 5, 1, False, False, 136, 240),
+    # 3 x 255 tiles: odd tile count, cluster mode with a phantom last tile
+    ("tpm0_5x5_phantom", [192], 256, 5, 1, False, False, 136, 240, 3),
+    ("hd2_deconv_phantom", [256], 256, 5, 2, True, False, 136, 240, 1),
 ]
 
 
 def _run_conv_case(dev, case, x, wt, bias):
     from spatiotemporalentropymodel_b200.engine import ConvOp, MASK_A_5x5, nchw_to_nhwc_f16, nhwc_f32_to_nchw
     from spatiotemporalentropymodel_b200._lib import DT_F32
-    name, cins, cout, k, stride, transposed, masked, h, w = case
+    name, cins, cout, k, stride, transposed, masked, h, w = case[:9]
     B = x.shape[0]
     if masked:
         ref = F.conv2d(x, O.masked_weight({"context_prediction.weight": wt}), bias, padding=2)
@@ -177,9 +180,9 @@ def test_conv_layers_vs_torch(dev, case):
     have them: the operands are rounded to fp16 on the way to the tensor core (kind::f16, 11-bit significands), and
     the result must stay within the error that rounding allows - relative RMS ~ 2^-11 * sqrt(2/3) ~ 4e-4 against the
     exact fp32 convolution, with no bias (mean error << RMS error)."""
-    name, cins, cout, k, stride, transposed, masked, h, w = case
+    name, cins, cout, k, stride, transposed, masked, h, w = case[:9]
     g = torch.Generator().manual_seed(11)
-    B, cin = 2, sum(cins)
+    B, cin = (case[9] if len(case) > 9 else 2), sum(cins)
     x32 = torch.randn((B, cin, h, w), generator=g)
     wshape = (cin, cout, k, k) if transposed else (cout, cin, k, k)
     wt32 = torch.randn(wshape, generator=g) / math.sqrt(cin * k * k)
@@ -233,7 +236,9 @@ def test_activation_range_of_the_fused_gdn_layers(dev, scale):
 GDN_CASES = [("conv5s2_gdn", False, False, 20, 28), ("deconv5_igdn", True, True, 9, 13), ("gemm_gdn", None, False, 12, 20),
              # pair mode / many tiles per CTA (double-buffered accumulators, ping-pong groups wrap around)
              ("conv5s2_gdn_pairs", False, False, 272, 480), ("deconv5_igdn_pairs", True, True, 68, 120),
-             ("gemm_gdn_pairs", None, False, 160, 256)]
+             ("gemm_gdn_pairs", None, False, 160, 256),
+             # odd tile count per sub-problem (3 x 255 / 1 x 255 tiles): cluster mode with a phantom last tile
+             ("conv5s2_gdn_phantom", False, False, 272, 480, 3), ("deconv5_igdn_phantom", True, True, 136, 240, 1)]
 
 
 @pytest.mark.parametrize("case", GDN_CASES, ids=[c[0] for c in GDN_CASES])
@@ -241,9 +246,9 @@ def test_fused_conv_gdn_vs_oracle(dev, case):
     """stemb200_conv2d_gdn_fwd (conv/deconv + GDN/IGDN in one kernel) against F.conv2d + the oracle's GDN
     (layers/gdn.py:52-67 with the NonNegativeParametrizer reparametrisation)."""
     from spatiotemporalentropymodel_b200.engine import ConvOp, _gdn_fold, nchw_to_nhwc_f16, nhwc_f16_to_nchw
-    name, transposed, inverse, h, w = case
+    name, transposed, inverse, h, w = case[:5]
     g = torch.Generator().manual_seed(21)
-    C, B = 192, 2
+    C, B = 192, (case[5] if len(case) > 5 else 2)
     cin = 128 if transposed is None else 192
     k = 1 if transposed is None else 5
     x = torch.randn((B, cin, h, w), generator=g).half().float()
