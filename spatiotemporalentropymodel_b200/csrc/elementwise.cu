@@ -39,11 +39,21 @@ __device__ __forceinline__ void block_accumulate(float v, double* dst, float* re
 }
 
 // ---------------------------------------------------------------------------------------------------
-// frame pixel loads: fp32 frames as they are, 8-bit frames as float(v) / 255 (IEEE division), which is what
+// frame pixel loads: fp32 frames as they are, 8-bit frames as float(v) / 255 (the IEEE quotient), which is what
 // torchvision's ToTensor computes for the PNG frames of stem/evalSTEM.py:185 - bit-identical to uploading fp32
 // ---------------------------------------------------------------------------------------------------
+// float(v) / 255 for a byte v, correctly rounded, without the division subroutine (whose range checks and slow path
+// made the 8-bit frame kernels ALU-bound: col2im 246 -> 474 us): one Newton step on q0 = v * fp32(1 / 255) -
+// q = fma(fma(-q0, 255, v), r, q0) - equals the IEEE quotient for all 256 inputs (checked exhaustively, and by the
+// bit-identity tests against torch's division).
+__device__ __forceinline__ float u8_unit(uint32_t v) {
+  const float x = static_cast<float>(v);
+  const float r = 0.0039215688593685627f;  // fp32(1 / 255)
+  const float q0 = __fmul_rn(x, r);
+  return __fmaf_rn(__fmaf_rn(-q0, 255.0f, x), r, q0);
+}
 __device__ __forceinline__ float px_load(const float* p) { return __ldg(p); }
-__device__ __forceinline__ float px_load(const uint8_t* p) { return __fdiv_rn(static_cast<float>(__ldg(p)), 255.0f); }
+__device__ __forceinline__ float px_load(const uint8_t* p) { return u8_unit(__ldg(p)); }
 __device__ __forceinline__ void px_load2(const float* p, float& a, float& b) {  // 8-byte aligned
   const float2 f = __ldg(reinterpret_cast<const float2*>(p));
   a = f.x;
@@ -51,8 +61,8 @@ __device__ __forceinline__ void px_load2(const float* p, float& a, float& b) {  
 }
 __device__ __forceinline__ void px_load2(const uint8_t* p, float& a, float& b) {  // 2-byte aligned
   const uchar2 u = __ldg(reinterpret_cast<const uchar2*>(p));
-  a = __fdiv_rn(static_cast<float>(u.x), 255.0f);
-  b = __fdiv_rn(static_cast<float>(u.y), 255.0f);
+  a = u8_unit(u.x);
+  b = u8_unit(u.y);
 }
 __device__ __forceinline__ void px_load4(const float* p, float (&v)[4]) {  // 16-byte aligned
   const float4 f = __ldg(reinterpret_cast<const float4*>(p));
@@ -63,10 +73,10 @@ __device__ __forceinline__ void px_load4(const float* p, float (&v)[4]) {  // 16
 }
 __device__ __forceinline__ void px_load4(const uint8_t* p, float (&v)[4]) {  // 4-byte aligned
   const uchar4 u = __ldg(reinterpret_cast<const uchar4*>(p));
-  v[0] = __fdiv_rn(static_cast<float>(u.x), 255.0f);
-  v[1] = __fdiv_rn(static_cast<float>(u.y), 255.0f);
-  v[2] = __fdiv_rn(static_cast<float>(u.z), 255.0f);
-  v[3] = __fdiv_rn(static_cast<float>(u.w), 255.0f);
+  v[0] = u8_unit(u.x);
+  v[1] = u8_unit(u.y);
+  v[2] = u8_unit(u.z);
+  v[3] = u8_unit(u.w);
 }
 
 // ---------------------------------------------------------------------------------------------------
