@@ -42,10 +42,9 @@ __device__ __forceinline__ void block_accumulate(float v, double* dst, float* re
 // frame pixel loads: fp32 frames as they are, 8-bit frames as float(v) / 255 (the IEEE quotient), which is what
 // torchvision's ToTensor computes for the PNG frames of stem/evalSTEM.py:185 - bit-identical to uploading fp32
 // ---------------------------------------------------------------------------------------------------
-// float(v) / 255 for a byte v, correctly rounded, without the division subroutine (whose range checks and slow path
-// made the 8-bit frame kernels ALU-bound: col2im 246 -> 474 us): one Newton step on q0 = v * fp32(1 / 255) -
-// q = fma(fma(-q0, 255, v), r, q0) - equals the IEEE quotient for all 256 inputs (checked exhaustively, and by the
-// bit-identity tests against torch's division).
+// float(v) / 255 for a byte v, correctly rounded, without the division subroutine (range checks + slow path: ~7 % of
+// the 8-bit col2im kernel): one Newton step on q0 = v * fp32(1 / 255) - q = fma(fma(-q0, 255, v), r, q0) - equals the
+// IEEE quotient for all 256 inputs (checked exhaustively, and by the bit-identity tests against torch's division).
 __device__ __forceinline__ float u8_unit(uint32_t v) {
   const float x = static_cast<float>(v);
   const float r = 0.0039215688593685627f;  // fp32(1 / 255)
@@ -54,30 +53,44 @@ __device__ __forceinline__ float u8_unit(uint32_t v) {
 }
 __device__ __forceinline__ float px_load(const float* p) { return __ldg(p); }
 __device__ __forceinline__ float px_load(const uint8_t* p) { return u8_unit(__ldg(p)); }
-__device__ __forceinline__ void px_load2(const float* p, float& a, float& b) {  // 8-byte aligned
-  const float2 f = __ldg(reinterpret_cast<const float2*>(p));
-  a = f.x;
-  b = f.y;
+// Raw pixel pairs: fetched early (before a kernel waits on something else), converted where they are used - converting
+// at the load site makes the thread wait for the DRAM round trip right there, in front of the TMA wait instead of
+// behind it (col2im with 8-bit frames: 446 us that way, 226 us this way; 243 us with fp32 frames).
+struct RawPairF { float a, b; };
+struct RawPairU8 { uint32_t v; };  // byte 0 = first pixel, byte 1 = second
+__device__ __forceinline__ RawPairF px_raw2(const float* p, bool vec, bool ok0, bool ok1) {
+  RawPairF r{0.f, 0.f};
+  if (vec && ok0 && ok1) {
+    const float2 f = __ldg(reinterpret_cast<const float2*>(p));
+    r.a = f.x;
+    r.b = f.y;
+  } else {
+    if (ok0) r.a = __ldg(p);
+    if (ok1) r.b = __ldg(p + 1);
+  }
+  return r;
 }
-__device__ __forceinline__ void px_load2(const uint8_t* p, float& a, float& b) {  // 2-byte aligned
-  const uchar2 u = __ldg(reinterpret_cast<const uchar2*>(p));
-  a = u8_unit(u.x);
-  b = u8_unit(u.y);
+__device__ __forceinline__ RawPairU8 px_raw2(const uint8_t* p, bool vec, bool ok0, bool ok1) {
+  RawPairU8 r{0u};
+  if (vec && ok0 && ok1) {
+    r.v = __ldg(reinterpret_cast<const unsigned short*>(p));
+  } else {
+    if (ok0) r.v = __ldg(p);
+    if (ok1) r.v |= static_cast<uint32_t>(__ldg(p + 1)) << 8;
+  }
+  return r;
 }
-__device__ __forceinline__ void px_load4(const float* p, float (&v)[4]) {  // 16-byte aligned
-  const float4 f = __ldg(reinterpret_cast<const float4*>(p));
-  v[0] = f.x;
-  v[1] = f.y;
-  v[2] = f.z;
-  v[3] = f.w;
+__device__ __forceinline__ void px_unpack(const RawPairF& r, float& a, float& b) {
+  a = r.a;
+  b = r.b;
 }
-__device__ __forceinline__ void px_load4(const uint8_t* p, float (&v)[4]) {  // 4-byte aligned
-  const uchar4 u = __ldg(reinterpret_cast<const uchar4*>(p));
-  v[0] = u8_unit(u.x);
-  v[1] = u8_unit(u.y);
-  v[2] = u8_unit(u.z);
-  v[3] = u8_unit(u.w);
+__device__ __forceinline__ void px_unpack(const RawPairU8& r, float& a, float& b) {
+  a = u8_unit(r.v & 0xFFu);
+  b = u8_unit((r.v >> 8) & 0xFFu);
 }
+template <typename T> struct RawPairOf;
+template <> struct RawPairOf<float> { using type = RawPairF; };
+template <> struct RawPairOf<uint8_t> { using type = RawPairU8; };
 
 // ---------------------------------------------------------------------------------------------------
 // layout kernels (32x32 smem transposes)
@@ -745,11 +758,15 @@ synthesis_col2im_kernel(const __grid_constant__ CUtensorMap col_map, const float
     const int qi_g = ty * kC2iQH + qi, qj_g = tx * kC2iQW + qj;
     const bool valid = qi_g < h2 && qj_g < w2;
     const int oh = 2 * qi_g, ow = 2 * qj_g;
-    // reference pixels of this quad: fetched before the tile is awaited
-    float rv[3][2][2];
+    // reference pixels of this quad: fetched (raw) before the tile is awaited, converted where they are used
+    typename RawPairOf<TRef>::type rv[3][2];
     bool rok[2] = {false, false};
     const int xr = ow - pad_left;
     const bool cok0 = xr >= 0 && xr < w_ref, cok1 = xr + 1 >= 0 && xr + 1 < w_ref;
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+      for (int c = 0; c < 3; ++c) rv[c][a] = {};
     if (xref && valid) {
 #pragma unroll
       for (int a = 0; a < 2; ++a) {
@@ -757,15 +774,9 @@ synthesis_col2im_kernel(const __grid_constant__ CUtensorMap col_map, const float
         rok[a] = yr >= 0 && yr < h_ref;
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
-          rv[c][a][0] = rv[c][a][1] = 0.f;
           if (rok[a]) {
             const TRef* rr = xref + (static_cast<long long>(n) * 3 + c) * rp + static_cast<long long>(yr) * w_ref + xr;
-            if (ref_vec && cok0 && cok1) {
-              px_load2(rr, rv[c][a][0], rv[c][a][1]);
-            } else {
-              if (cok0) rv[c][a][0] = px_load(rr);
-              if (cok1) rv[c][a][1] = px_load(rr + 1);
-            }
+            rv[c][a] = px_raw2(rr, ref_vec != 0, cok0, cok1);
           }
         }
       }
@@ -810,7 +821,9 @@ synthesis_col2im_kernel(const __grid_constant__ CUtensorMap col_map, const float
           }
           *reinterpret_cast<float2*>(dst + c * plane + a * W) = make_float2(v0, v1);
           if (xref && rok[a]) {
-            const float d0 = rv[c][a][0] - v0, d1 = rv[c][a][1] - v1;
+            float r0, r1;
+            px_unpack(rv[c][a], r0, r1);
+            const float d0 = r0 - v0, d1 = r1 - v1;
             if (cok0) err += d0 * d0;
             if (cok1) err += d1 * d1;
           }
@@ -891,50 +904,83 @@ __device__ __forceinline__ uint4 pack_nhwc8(const float (&v)[8]) {
   return o;
 }
 
+// 4 consecutive pixels of one channel plane, as loaded (conversion happens after every load of the thread is in flight)
+struct RawQuadF { float4 v; };
+struct RawQuadU8 { uint32_t v; };
+__device__ __forceinline__ RawQuadF px_raw4(const float* p) { return {__ldg(reinterpret_cast<const float4*>(p))}; }
+__device__ __forceinline__ RawQuadU8 px_raw4(const uint8_t* p) { return {__ldg(reinterpret_cast<const uint32_t*>(p))}; }
+__device__ __forceinline__ void px_unpack4(const RawQuadF& r, float (&f)[4]) {
+  f[0] = r.v.x, f[1] = r.v.y, f[2] = r.v.z, f[3] = r.v.w;
+}
+__device__ __forceinline__ void px_unpack4(const RawQuadU8& r, float (&f)[4]) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) f[i] = u8_unit((r.v >> (8 * i)) & 0xFFu);
+}
+template <typename T> struct RawQuadOf;
+template <> struct RawQuadOf<float> { using type = RawQuadF; };
+template <> struct RawQuadOf<uint8_t> { using type = RawQuadU8; };
+
+constexpr int kCanvasRowsPerThread = 2;  // two canvas rows per thread: twice the loads in flight (the kernel is latency-bound)
+
 template <typename TIn>
 __global__ void __launch_bounds__(128)
 frame_to_nhwc8_kernel(const TIn* __restrict__ x, uint4* __restrict__ canvas, int c, int h, int w, int hc, int wc,
-                      int off_top, int off_left, int groups, int vec_ok) {
-  const int row = blockIdx.x;  // n * hc + canvas row
-  const int n = row / hc, chh = row - n * hc;
-  const int ih = chh - off_top;
+                      int off_top, int off_left, int groups, int vec_ok, int total_rows) {
   const int g = blockIdx.y * 128 + threadIdx.x;
   if (g >= groups) return;
   const int iw0 = 4 * g - ((off_left + 3) & ~3);  // multiple of 4 (may start left of the frame)
   const int cw0 = iw0 + off_left;
-  uint4* dst = canvas + static_cast<long long>(row) * wc;
-  float v[4][8];
+  const long long plane = static_cast<long long>(h) * w;
+  const bool vec = vec_ok && iw0 >= 0 && iw0 + 3 < w;
+  typename RawQuadOf<TIn>::type raw[kCanvasRowsPerThread][3];
+  const TIn* px[kCanvasRowsPerThread];
+  bool inside[kCanvasRowsPerThread];
 #pragma unroll
-  for (int p = 0; p < 4; ++p)
+  for (int r = 0; r < kCanvasRowsPerThread; ++r) {
+    const int row = blockIdx.x * kCanvasRowsPerThread + r;  // n * hc + canvas row
+    const int n = row / hc, ih = row - n * hc - off_top;
+    inside[r] = row < total_rows && ih >= 0 && ih < h;
+    px[r] = x + (static_cast<long long>(n) * c * h + (inside[r] ? ih : 0)) * w;
+    if (inside[r] && vec && c == 3) {
 #pragma unroll
-    for (int ch = 0; ch < 8; ++ch) v[p][ch] = 0.f;
-  if (ih >= 0 && ih < h) {
-    const TIn* px = x + (static_cast<long long>(n) * c * h + ih) * w;
-    const long long plane = static_cast<long long>(h) * w;
-    if (vec_ok && iw0 >= 0 && iw0 + 3 < w) {
+      for (int ch = 0; ch < 3; ++ch) raw[r][ch] = px_raw4(px[r] + ch * plane + iw0);
+    }
+  }
 #pragma unroll
-      for (int ch = 0; ch < 8; ++ch)
-        if (ch < c) {
+  for (int r = 0; r < kCanvasRowsPerThread; ++r) {
+    const int row = blockIdx.x * kCanvasRowsPerThread + r;
+    if (row >= total_rows) break;
+    float v[4][8];
+#pragma unroll
+    for (int p = 0; p < 4; ++p)
+#pragma unroll
+      for (int ch = 0; ch < 8; ++ch) v[p][ch] = 0.f;
+    if (inside[r]) {
+      if (vec && c == 3) {
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch) {
           float f[4];
-          px_load4(px + ch * plane + iw0, f);
+          px_unpack4(raw[r][ch], f);
           v[0][ch] = f[0];
           v[1][ch] = f[1];
           v[2][ch] = f[2];
           v[3][ch] = f[3];
         }
-    } else {
+      } else {
 #pragma unroll
-      for (int p = 0; p < 4; ++p)
-        if (iw0 + p >= 0 && iw0 + p < w) {
+        for (int p = 0; p < 4; ++p)
+          if (iw0 + p >= 0 && iw0 + p < w) {
 #pragma unroll
-          for (int ch = 0; ch < 8; ++ch)
-            if (ch < c) v[p][ch] = px_load(px + ch * plane + iw0 + p);
-        }
+            for (int ch = 0; ch < 8; ++ch)
+              if (ch < c) v[p][ch] = px_load(px[r] + ch * plane + iw0 + p);
+          }
+      }
     }
-  }
+    uint4* dst = canvas + static_cast<long long>(row) * wc;
 #pragma unroll
-  for (int p = 0; p < 4; ++p)
-    if (cw0 + p >= 0 && cw0 + p < wc) dst[cw0 + p] = pack_nhwc8(v[p]);
+    for (int p = 0; p < 4; ++p)
+      if (cw0 + p >= 0 && cw0 + p < wc) dst[cw0 + p] = pack_nhwc8(v[p]);
+  }
 }
 
 extern "C" int stemb200_synthesis_col_index(int32_t r, int32_t s, int32_t c) {
@@ -1004,9 +1050,10 @@ static int frame_to_nhwc8_impl(const TIn* x_nchw, void* canvas, int32_t n, int32
   // groups of 4 canvas pixels, the first one starting at canvas column off_left - roundup4(off_left) <= 0
   const int groups = (wc + ((off_left + 3) & ~3) - off_left + 3) / 4;
   const int vec_ok = (w % 4 == 0) && (reinterpret_cast<uintptr_t>(x_nchw) % (4 * sizeof(TIn)) == 0);
-  dim3 grid(n * hc, (groups + 127) / 128);
+  const int total_rows = n * hc;
+  dim3 grid((total_rows + kCanvasRowsPerThread - 1) / kCanvasRowsPerThread, (groups + 127) / 128);
   frame_to_nhwc8_kernel<TIn><<<grid, 128, 0, static_cast<cudaStream_t>(stream)>>>(
-      x_nchw, static_cast<uint4*>(canvas), c, h, w, hc, wc, off_top, off_left, groups, vec_ok);
+      x_nchw, static_cast<uint4*>(canvas), c, h, w, hc, wc, off_top, off_left, groups, vec_ok, total_rows);
   CHECK_LAUNCH("frame_to_nhwc8");
   return 0;
 }

@@ -101,26 +101,29 @@ def main():
                       f"{-10 * np.log10(mse):.2f} dB, floored y likelihoods {float((ly <= 1.0001e-9).float().mean()):.4f}, "
                       f"clamped x_hat pixels {float(((x_hat <= 0) | (x_hat >= 1)).float().mean()):.4f}")
 
-    # ---------------------------------------------------------------- stem_roi (a13)
+    # ---------------------------------------------------------------- stem_roi (a13), both calibrations
     from compressai.models.stem_roi import stem_roi as ref_stem_roi
     from spatiotemporalentropymodel_b200 import stem_roi as R
-    sd_r = R.make_synthetic_state_dict(seed=0)
-    roi = ref_stem_roi()
-    roi.load_state_dict(sd_r)
-    roi.update(force=True)
-    roi.eval()
-    frames = S.make_frames(2, 128, 128, seed=11)
-    rec = {}
-    with torch.no_grad():
-        for name, qmap in (("ramp", R.make_qmap(1, 128, 128, "ramp")), ("uniform", R.make_qmap(1, 128, 128, "uniform", 0.25))):
-            out = roi(frames[1:2], frames[0:1], qmap)
-            rec[f"{name}_x_hat"] = out["x_hat"].numpy()
-            rec[f"{name}_y_hat"] = out["y_hat"].numpy()
-            rec[f"{name}_lik_y"] = out["likelihoods"]["y"].numpy()
-            rec[f"{name}_lik_z"] = out["likelihoods"]["z"].numpy()
-            bits = float((-torch.log2(out["likelihoods"]["y"])).sum() + (-torch.log2(out["likelihoods"]["z"])).sum())
-            print(f"stem_roi[{name}]: bpp {bits / (128 * 128):.4f}")
-    np.savez_compressed(os.path.join(OUT, "stem_roi.npz"), **rec)
+    for calibration in ("default", "lowrate"):
+        sd_r = R.make_synthetic_state_dict(seed=0, calibration=calibration)
+        roi = ref_stem_roi()
+        roi.load_state_dict(sd_r)
+        roi.update(force=True)
+        roi.eval()
+        frames = S.make_frames(2, 128, 128, seed=11)
+        rec = {}
+        with torch.no_grad():
+            for name, qmap in (("ramp", R.make_qmap(1, 128, 128, "ramp")), ("uniform", R.make_qmap(1, 128, 128, "uniform", 0.25))):
+                out = roi(frames[1:2], frames[0:1], qmap)
+                rec[f"{name}_x_hat"] = out["x_hat"].numpy()
+                rec[f"{name}_y_hat"] = out["y_hat"].numpy()
+                rec[f"{name}_lik_y"] = out["likelihoods"]["y"].numpy()
+                rec[f"{name}_lik_z"] = out["likelihoods"]["z"].numpy()
+                ly = out["likelihoods"]["y"]
+                bits = float((-torch.log2(ly)).sum() + (-torch.log2(out["likelihoods"]["z"])).sum())
+                print(f"[{calibration}] stem_roi[{name}]: bpp {bits / (128 * 128):.4f}, floored y likelihoods "
+                      f"{float((ly <= 1.0001e-9).float().mean()):.4f}")
+        np.savez_compressed(os.path.join(OUT, "stem_roi.npz" if calibration == "default" else "stem_roi_lowrate.npz"), **rec)
 
     # ---------------------------------------------------------------- isolated GaussianConditional (a9)
     table = ref_stem.get_scale_table()

@@ -23,10 +23,14 @@ def _inputs():
                                       "uniform": R.make_qmap(1, 128, 128, "uniform", 0.25)}
 
 
-def test_oracle_matches_reference_golden(golden):
+CAL_FILE = {"default": "stem_roi.npz", "lowrate": "stem_roi_lowrate.npz"}
+
+
+@pytest.mark.parametrize("calibration", ["default", "lowrate"])
+def test_oracle_matches_reference_golden(golden, calibration):
     from spatiotemporalentropymodel_b200 import stem_roi as R
-    g = golden("stem_roi.npz")
-    sd = R.make_synthetic_state_dict(seed=0)
+    g = golden(CAL_FILE[calibration])
+    sd = R.make_synthetic_state_dict(seed=0, calibration=calibration)
     x_cur, x_cond, qmaps = _inputs()
     for name, qmap in qmaps.items():
         out = RO.stem_roi_forward(x_cur, x_cond, qmap, sd)
@@ -39,6 +43,8 @@ def test_oracle_matches_reference_golden(golden):
             bad = ((got - ref).abs() > 1e-4 * ref.abs() + 1e-9).float().mean()
             assert float(bad) < 1e-3, (key, float(bad))
             assert abs(bits(got) - bits(ref)) / bits(ref) < 1e-5
+        if calibration == "lowrate":   # the checkpoint whose bpp gate sees sigma / mu errors: < 1 % floored likelihoods
+            assert float((t(g[f"{name}_lik_y"]) <= 1.0001e-9).float().mean()) < 0.01
         assert torch.allclose(out["x_hat"], t(g[f"{name}_x_hat"]), rtol=1e-4, atol=1e-4)
 
 
@@ -58,13 +64,14 @@ def test_state_dict_contract_and_no_cpu_fallback():
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("calibration", ["default", "lowrate"])
 @pytest.mark.parametrize("name", ["ramp", "uniform"])
-def test_cuda_forward_vs_reference_golden(golden, name):
+def test_cuda_forward_vs_reference_golden(golden, name, calibration):
     from spatiotemporalentropymodel_b200 import stem_roi as R
     dev = torch.device("cuda:0")
-    g = golden("stem_roi.npz")
+    g = golden(CAL_FILE[calibration])
     model = R.stem_roi()
-    model.load_state_dict(R.make_synthetic_state_dict(seed=0))
+    model.load_state_dict(R.make_synthetic_state_dict(seed=0, calibration=calibration))
     model.update(force=True)
     model = model.to(dev).eval()
     x_cur, x_cond, qmaps = _inputs()
