@@ -293,7 +293,7 @@ class Ctx:
 
 
 def time_pframes(ctx, pipe, frames8_host, y_cond0, steps, warmup, graph=True, reduce_every_step=False,
-                 sample_clocks=False):
+                 sample_clocks=False, full_outputs=False):
     """Device-resident and end-to-end timing of one P-frame workload on this rank; times are max over ranks."""
     from spatiotemporalentropymodel_b200 import _lib
     from spatiotemporalentropymodel_b200.dist import reduce_stats
@@ -388,7 +388,37 @@ def time_pframes(ctx, pipe, frames8_host, y_cond0, steps, warmup, graph=True, re
     e1.record()
     torch.cuda.synchronize()
     e2e_ms = ctx.max_ms(max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3))
+
+    # the same call when EVERY output tensor of the forward API is wanted on the host (x_hat, y_hat, both likelihood
+    # tensors): D2H inside the timed region. PCIe-bound by construction (~410 MB per 11-frame 1080p GOP); reported
+    # next to the evaluation-loop figure above, whose result is the 3 x T statistics.
+    full = None
+    if full_outputs:
+        keys = ("x_hat_padded", "y_hat", "lik_y", "lik_z")
+        o = pipe.run_gop(frames_pin, y_cond0, want_outputs=True)
+        host = {k: torch.empty(o[k].shape, dtype=o[k].dtype).pin_memory() for k in keys}
+        n_full = max(3, min(steps, 10))
+
+        def full_loop(n):
+            for _ in range(n):
+                o = pipe.run_gop(frames_pin, y_cond0, want_outputs=True)
+                for k in keys:
+                    host[k].copy_(o[k], non_blocking=True)
+                host_stats.copy_(o["stats"], non_blocking=True)
+            torch.cuda.synchronize()
+
+        full_loop(2)
+        ctx.barrier()
+        t0 = time.perf_counter()
+        full_loop(n_full)
+        full_ms = ctx.max_ms((time.perf_counter() - t0) * 1e3) / n_full
+        d2h = sum(v.numel() * v.element_size() for v in host.values()) + host_stats.numel() * 8
+        full = {"value": world * T / (full_ms / 1e3), "unit": UNIT, "ms_per_step": full_ms,
+                "h2d_bytes_per_step": frames8_host.numel() * frames8_host.element_size(), "d2h_bytes_per_step": d2h,
+                "d2h_gb_per_s": d2h / full_ms / 1e6, "steps": n_full,
+                "note": "run_gop + every forward() output tensor copied to pinned host memory each step (PCIe-bound)"}
     return {"ms_per_step": ms_total / steps, "e2e_ms_per_step": e2e_ms / steps, "launches": launches, "clocks": clocks,
+            "e2e_full_outputs": full,
             "cuda_graph": g is not None, "h2d_bytes_per_step": frames8_host.numel() * frames8_host.element_size(),
             "d2h_bytes_per_step": host_stats.numel() * 8, "step_resident": step_resident, "last_out": out}
 
@@ -433,7 +463,7 @@ def run_pframe_workload(ctx, name, steps, warmup, args, full):
     net, stem, pipe, sd_i, sd_s = make_models(variant, "default", dev)
     frames8, y_cond0 = make_inputs(T, H, W, 1234 + rank, "default")
     tm = time_pframes(ctx, pipe, frames8, y_cond0, steps, warmup, graph=not args.no_graph,
-                      reduce_every_step=args.reduce_every_step, sample_clocks=full)
+                      reduce_every_step=args.reduce_every_step, sample_clocks=full, full_outputs=full)
     ms_step = tm["ms_per_step"]
     gflop_frame = algorithmic_gflop_per_frame(variant, H, W)
     peaks = load_peaks()
@@ -442,6 +472,7 @@ def run_pframe_workload(ctx, name, steps, warmup, args, full):
         "ms_per_step": ms_step, "frames_per_step": T, "steps": steps,
         "e2e": {"value": world * T / (tm["e2e_ms_per_step"] / 1e3), "unit": UNIT,
                 "h2d_bytes_per_step": tm["h2d_bytes_per_step"], "d2h_bytes_per_step": tm["d2h_bytes_per_step"]},
+        "e2e_full_outputs": tm["e2e_full_outputs"],
         "gpu_launches": tm["launches"], "cuda_graph": tm["cuda_graph"], "clocks": tm["clocks"],
         "whole_step_roofline": {"bound": "tensor", "achieved": gflop_frame * T / ms_step, "peak": peaks["tf_sustained"],
                                 "unit": "TFLOP/s", "frac": gflop_frame * T / ms_step / peaks["tf_sustained"],
@@ -779,7 +810,8 @@ def main():
                        "stats_reduction": "every step" if args.reduce_every_step else "once per run (inside the timed region)",
                        "l2": "per-step working set (several GB of activations) exceeds the 126 MB L2; no flush needed",
                        "checkpoint": "seeded synthetic (spatiotemporalentropymodel_b200.synthetic)"},
-            "clocks": res["clocks"], "e2e": res["e2e"], "gpu_launches": res["gpu_launches"],
+            "clocks": res["clocks"], "e2e": res["e2e"], "e2e_full_outputs": res.get("e2e_full_outputs"),
+            "gpu_launches": res["gpu_launches"],
             "roofline": res.get("roofline") or res.get("whole_step_roofline"),
             "whole_step_roofline": res["whole_step_roofline"],
             "cpu_baseline": res.get("cpu_baseline"), "parity": res.get("parity"),
