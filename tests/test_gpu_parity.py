@@ -432,6 +432,26 @@ def test_parity_at_benchmark_size_1080p(dev, variant, calibration, monkeypatch):
         assert rep["max_mu_err_over_sigma_rms"] < 0.2, rep
 
 
+def test_parity_4k_frame(dev):
+    """Largest frame of BASELINE.json (3840 x 2160, padded to 3840 x 2176: 32 640 latent pixels, 522 k first-layer
+    pixels per frame) through the full P-frame pipeline, 8-bit input, against the oracle: the same gates. Exercises
+    the tile / index arithmetic at four times the 1080p extents."""
+    from oracle import parity as P
+    variant, calibration = "SpatioTemporalPriorModel", "lowrate"
+    net, stem, pipe, sd_i, sd_s = _models(variant, calibration, dev)
+    H, W = 2160, 3840
+    frames, y_cond0 = _gop_inputs(1, H, W, 99, calibration, sd_i)
+    f8 = torch.round(frames * 255).to(torch.uint8)
+    out = pipe.forward_gop(f8.to(dev), y_cond0.to(dev))
+    torch.cuda.synchronize()
+    torch.set_num_threads(max(1, __import__("os").cpu_count() or 1))
+    with torch.no_grad():
+        ref = O.gop_forward(f8.float().div(255.0), y_cond0, sd_i, sd_s, variant)
+    rep = P.gop_parity(out, ref, H, W)
+    assert rep["ok"], rep
+    assert rep["max_y_hat_mismatch_frac"] < 0.02
+
+
 @pytest.mark.parametrize("variant", ["SpatioTemporalPriorModel", "SpatioTemporalPriorModelWithoutSPM"])
 def test_uint8_frames_bit_identical_to_totensor_frames(dev, variant):
     """8-bit frames (v / 255 on the device) against the fp32 frames torchvision's ToTensor makes of them
