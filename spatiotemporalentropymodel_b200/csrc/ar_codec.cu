@@ -578,72 +578,109 @@ __global__ void __launch_bounds__(kArThreads, 1) ar_codec_kernel(const ArParams 
           s_idx[ch] = ci < 0 ? 0 : (ci >= p.n_cdfs ? p.n_cdfs - 1 : ci);
         }
         __syncwarp();
-        // row data of the next symbol is fetched while the current one is resolved (it does not depend on the state)
+        // One symbol = one trip through a dependent chain, so the chain is what is optimised (it was ~640 cycles per
+        // symbol, 77 % of the decode time):
+        //   cum -> ballot over the 32 level-1 probes (registers) -> k -> one shared-memory round for the <= 32 entries
+        //   of chunk k -> ballot / popc -> start and next boundary by SHUFFLE from the values the lanes already hold
+        //   (the boundary after a full chunk is level-1 probe k + 1) -> 64-bit state update -> renormalisation with a
+        //   stream word that was shuffled out speculatively at the top of the iteration.
+        // Row data of the next symbol is fetched while the current one is resolved (it does not depend on the state).
         int ci = s_idx[0];
         int4 mt = s_meta[ci];
         uint32_t l1v = static_cast<uint32_t>(s_l1[ci][lane]);
+        int widx = static_cast<int>(rpos - wbase);  // position of the next stream word inside the 32-word window
         for (int ch = 0; ch < C; ++ch) {
           const int ci_n = s_idx[ch + 1 < C ? ch + 1 : ch];
           const int4 mt_n = s_meta[ci_n];
           const uint32_t l1_n = static_cast<uint32_t>(s_l1[ci_n][lane]);
-          int value = 0;
-          if (!rbad) {
-            const uint16_t* row = cdf16 + mt.x;
-            const int size = mt.y, n = size - 1, step = mt.w;  // candidates s in [0, n): row[s] <= cum < row[s+1]
-            const uint32_t cum = static_cast<uint32_t>(rx & 0xFFFFu);
-            const unsigned int m1 = __ballot_sync(0xffffffffu, l1v <= cum);
-            const int k = m1 ? 31 - __clz(m1) : 0;
-            int s_found = k;
-            if (step > 1) {
-              const int slo = k * step;
-              const int rem = (n - slo) < step ? (n - slo) : step;  // 1 <= rem <= 98
-              int cnt = 0;
-              for (int o0 = 0; o0 < rem; o0 += 32) {
-                const int o = o0 + lane;
-                cnt += __popc(__ballot_sync(0xffffffffu, o < rem && static_cast<uint32_t>(row[slo + o]) <= cum));
-              }
-              s_found = slo + (cnt > 0 ? cnt - 1 : 0);
-            }
-            uint32_t start = 0, nxt = 0;
-            if (n >= 1) {
-              start = row[s_found];
-              nxt = (s_found + 1 >= n) ? 65536u : static_cast<uint32_t>(row[s_found + 1]);
-            }
-            const uint32_t freq = nxt - start;
-            if (freq == 0 || freq > 65536u || cum < start || cum >= nxt) rbad = true;
-            rx = static_cast<uint64_t>(freq) * (rx >> 16) + cum - start;
-            if (rx < kRansL && rpos < rwords) rx = (rx << 32) | next_word();
-            value = s_found;
-            if (s_found == size - 2) {
-              // bypass: nibble count (unary in chunks of 15), then the nibbles, least significant first
-              auto get4 = [&]() -> int {
-                const int v4 = static_cast<int>(rx & 15u);
-                rx >>= 4;
-                if (rx < kRansL && rpos < rwords) rx = (rx << 32) | next_word();
-                return v4;
-              };
-              int v4 = get4();
-              int n_nib = v4;
-              while (v4 == 15 && n_nib < 64) {
-                v4 = get4();
-                n_nib += v4;
-              }
-              uint32_t raw = 0;
-              for (int k2 = 0; k2 < n_nib; ++k2) {
-                const uint32_t nib = static_cast<uint32_t>(get4());
-                if (k2 < 8) raw |= nib << (4 * k2);
-              }
-              value = static_cast<int>(raw >> 1);
-              if (raw & 1u) value = -value - 1;
-              else value += size - 2;
-            }
-            value += mt.z;
+          if (widx >= 32) {  // every 32 words: refill the window
+            wbase += 32;
+            widx -= 32;
+            wbuf = (wbase + lane) < rwords ? __ldg(rstream + wbase + lane) : 0u;
           }
+          const uint32_t w_spec = __shfl_sync(0xffffffffu, wbuf, widx & 31);  // used only if this symbol renormalises
+          const uint16_t* row = cdf16 + mt.x;
+          const int size = mt.y, n = size - 1, step = mt.w;  // candidates s in [0, n): row[s] <= cum < row[s+1]
+          const uint32_t cum = static_cast<uint32_t>(rx & 0xFFFFu);
+          const unsigned int m1 = __ballot_sync(0xffffffffu, l1v <= cum);
+          const int k = m1 ? 31 - __clz(m1) : 0;
+          int s_found;
+          uint32_t start, nxt;
+          if (step <= 1) {
+            // rows of <= 32 candidates: the probes are the row
+            s_found = k;
+            start = __shfl_sync(0xffffffffu, l1v, k);
+            nxt = __shfl_sync(0xffffffffu, l1v, (k + 1) & 31);
+            if (k + 1 >= n) nxt = 65536u;
+          } else if (step <= 32) {
+            const int slo = k * step;
+            const int rem = (n - slo) < step ? (n - slo) : step;  // 1 <= rem <= 32
+            const uint32_t v = lane < rem ? static_cast<uint32_t>(row[slo + lane]) : 0xFFFFFFFFu;
+            const int cnt = __popc(__ballot_sync(0xffffffffu, v <= cum));  // >= 1: row[slo] is probe k
+            const int c1 = cnt > 0 ? cnt - 1 : 0;
+            s_found = slo + c1;
+            start = __shfl_sync(0xffffffffu, v, c1);
+            const uint32_t in_chunk = __shfl_sync(0xffffffffu, v, (c1 + 1) & 31);
+            const uint32_t next_probe = __shfl_sync(0xffffffffu, l1v, (k + 1) & 31);
+            nxt = (c1 + 1 < rem) ? in_chunk : next_probe;
+            if (s_found + 1 >= n) nxt = 65536u;
+          } else {
+            // rows of more than 1024 candidates (sigma > ~84): several rounds per chunk
+            const int slo = k * step;
+            const int rem = (n - slo) < step ? (n - slo) : step;
+            int cnt = 0;
+            for (int o0 = 0; o0 < rem; o0 += 32) {
+              const int o = o0 + lane;
+              cnt += __popc(__ballot_sync(0xffffffffu, o < rem && static_cast<uint32_t>(row[slo + o]) <= cum));
+            }
+            s_found = slo + (cnt > 0 ? cnt - 1 : 0);
+            start = row[s_found];
+            nxt = (s_found + 1 >= n) ? 65536u : static_cast<uint32_t>(row[s_found + 1]);
+          }
+          if (n < 1) {  // an empty row cannot be decoded
+            start = 0u;
+            nxt = 0u;
+          }
+          const uint32_t freq = nxt - start;
+          rbad = rbad || freq == 0u || freq > 65536u || cum < start || cum >= nxt;
+          rx = static_cast<uint64_t>(freq) * (rx >> 16) + cum - start;
+          if (rx < kRansL && (wbase + widx) < rwords) {
+            rx = (rx << 32) | w_spec;
+            ++widx;
+          }
+          int value = s_found;
+          if (s_found == size - 2) {
+            // bypass (rare): nibble count (unary in chunks of 15), then the nibbles, least significant first
+            rpos = wbase + widx;
+            auto get4 = [&]() -> int {
+              const int v4 = static_cast<int>(rx & 15u);
+              rx >>= 4;
+              if (rx < kRansL && rpos < rwords) rx = (rx << 32) | next_word();
+              return v4;
+            };
+            int v4 = get4();
+            int n_nib = v4;
+            while (v4 == 15 && n_nib < 64) {
+              v4 = get4();
+              n_nib += v4;
+            }
+            uint32_t raw = 0;
+            for (int k2 = 0; k2 < n_nib; ++k2) {
+              const uint32_t nib = static_cast<uint32_t>(get4());
+              if (k2 < 8) raw |= nib << (4 * k2);
+            }
+            value = static_cast<int>(raw >> 1);
+            if (raw & 1u) value = -value - 1;
+            else value += size - 2;
+            widx = static_cast<int>(rpos - wbase);
+          }
+          value = rbad ? 0 : value + mt.z;
           if (lane == 0) s_sym[ch] = value;
           ci = ci_n;
           mt = mt_n;
           l1v = l1_n;
         }
+        rpos = wbase + widx;
         __syncwarp();
         for (int ch = lane; ch < C; ch += 32) {
           const int sv = s_sym[ch];
