@@ -5,13 +5,16 @@ streams and parameter storage only.  Nothing here falls back to torch ops for co
 missing library raises.
 
 Kernel chains (reference lines in parentheses):
-  analysis   g_a  (priors.py:421-429)      im2col -> [GEMM+GDN] -> [conv s2+GDN] x2 -> conv s2 (fp32 y)
-  STEM            (spatiotemporalpriors.py:561-585 and variants) HE -> EB -> HD, TPM, ctx, EPM -> GC
-  synthesis  g_s  (priors.py:431-439,397-402)  [deconv+IGDN] x3 -> merged-phase deconv -> tail (clamp, MSE)
+  analysis   g_a  (priors.py:421-429)      frame canvas -> [row-taps conv+GDN] -> [conv s2+GDN] x2 -> conv s2 (fp32 y)
+  STEM            (spatiotemporalpriors.py:561-585 and variants) {HE -> EB -> HD} || {TPM, ctx} -> EPM.0, EPM.2 ->
+                  [EPM.4 + GaussianConditional]
+  synthesis  g_s  (priors.py:431-439,397-402)  [deconv+IGDN] x2 -> [deconv+IGDN+last-layer GEMM] -> col2im (clamp, MSE),
+                  on a side stream next to the entropy model where y_hat does not depend on it
 """
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Dict, List, Optional, Sequence, Tuple
 
 import torch
@@ -45,7 +48,6 @@ def fuse_gc_enabled() -> bool:
     HBM; BASELINE north_star item 2). On by default: bit-identical to the two separate kernels, 155 us instead of
     65 + 119 us per 11 x 1080p latents and 226 MB less DRAM traffic (profiles/r02_ncu_fused_gc.txt). STEMB200_FUSE_GC=0
     selects the separate kernels (which also leave sigma | mu in the workspace buffer "gparams")."""
-    import os
     return os.environ.get("STEMB200_FUSE_GC", "1") != "0"
 
 
@@ -53,7 +55,6 @@ def overlap_level() -> int:
     """STEMB200_OVERLAP: 0 = one stream; 1 = the temporal-prior / context chain runs beside the hyper-prior chain;
     2 (default) = in addition the synthesis transform of a GOP runs beside its entropy model (SPM variants, where
     y_hat = round(y) is known before the entropy parameters are)."""
-    import os
     try:
         return int(os.environ.get("STEMB200_OVERLAP", "2"))
     except ValueError:
@@ -493,7 +494,6 @@ class TransformsEngine:
         # default path: the same layer as a per-pixel GEMM fused behind gs4's IGDN epilogue,
         # W6[col_index(r, s, c)][ci] = w[ci][c][r][s] (75 of 96 rows, quad-grouped order of the col2im kernel),
         # followed by that col2im kernel (STEMB200_FUSE_LAST=0 selects the stand-alone merged-phase conv above)
-        import os
         self.fuse_last = os.environ.get("STEMB200_FUSE_LAST", "1") != "0" and N == 192
         lib = _lib.load()
         w6 = torch.zeros((96, N), device=dev)
