@@ -432,6 +432,31 @@ def test_parity_at_benchmark_size_1080p(dev, variant, calibration, monkeypatch):
         assert rep["max_mu_err_over_sigma_rms"] < 0.2, rep
 
 
+@pytest.mark.parametrize("size", [(64, 64, 1), (119, 201, 2), (181, 333, 1)], ids=["one_tile", "odd", "odd2"])
+@pytest.mark.parametrize("u8", [False, True], ids=["f32", "u8"])
+def test_ragged_frame_sizes(dev, size, u8):
+    """Frame sizes that are not multiples of anything (evalSTEM.py:96-109 pads them to 64; odd widths switch the frame
+    kernels to their scalar loads, odd left / top offsets exercise the crop of the squared-error sum), a single-tile
+    frame, T = 1: the same gates against the oracle, 8-bit and fp32 input."""
+    from oracle import parity as P
+    variant, calibration = "SpatioTemporalPriorModel", "lowrate"
+    net, stem, pipe, sd_i, sd_s = _models(variant, calibration, dev)
+    H, W, T = size
+    frames, y_cond0 = _gop_inputs(T, H, W, 5, calibration, sd_i)
+    if u8:
+        f8 = torch.round(frames * 255).to(torch.uint8)
+        frames, inp = f8.float().div(255.0), f8
+    else:
+        inp = frames
+    out = pipe.forward_gop(inp.to(dev), y_cond0.to(dev))
+    with torch.no_grad():
+        ref = O.gop_forward(frames, y_cond0, sd_i, sd_s, variant)
+    rep = P.gop_parity(out, ref, H, W)
+    # a 64 x 64 frame has 16 latent pixels: one rounding flip is 0.03 % of its bits - the bpp gate still holds,
+    # the PSNR gate is the north-star one
+    assert rep["ok"], rep
+
+
 def test_parity_4k_frame(dev):
     """Largest frame of BASELINE.json (3840 x 2160, padded to 3840 x 2176: 32 640 latent pixels, 522 k first-layer
     pixels per frame) through the full P-frame pipeline, 8-bit input, against the oracle: the same gates. Exercises
