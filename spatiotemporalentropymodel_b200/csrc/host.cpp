@@ -39,7 +39,7 @@ int num_sms() {
 }
 }  // namespace stem
 
-extern "C" const char* stemb200_version(void) { return "stemb200 0.1.0 (sm_100a)"; }
+extern "C" const char* stemb200_version(void) { return "stemb200 0.2.0 (sm_100a)"; }
 extern "C" const char* stemb200_last_error(void) { return stem::g_err; }
 extern "C" uint64_t stemb200_launch_count(void) { return stem::g_launches.load(); }
 
