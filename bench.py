@@ -577,7 +577,6 @@ def run_pframe_workload(ctx, name, steps, warmup, args, full):
 def run_stem_roi(ctx, name, steps, warmup, args, full):
     """BASELINE.json configs[4]: stem_roi.forward (x_cur, x_conditioned, Qmap) on frames padded to a multiple of
     64, one model replica per GPU, frames sharded over ranks (weak scaling), fps = frames / max-over-ranks time."""
-    import torch.nn.functional as F
     from spatiotemporalentropymodel_b200 import _lib, stem_roi as R, synthetic as S
     from spatiotemporalentropymodel_b200.engine import ConvOp
     dev, rank, world = ctx.dev, ctx.rank, ctx.world
@@ -588,10 +587,11 @@ def run_stem_roi(ctx, name, steps, warmup, args, full):
     model.update(force=True)
     model = model.to(dev).eval()
     Hp, Wp = (H + 63) // 64 * 64, (W + 63) // 64 * 64
-    frames = S.make_frames(T + 1, H, W, seed=77 + rank)
-    pad = (0, Wp - W, 0, Hp - H)
-    x_cur = F.pad(frames[1:], pad).to(dev)
-    x_cond = F.pad(frames[:-1], pad).to(dev)
+    # 8-bit frames (v / 255 on the device), zero-padded to a multiple of 64 like the reference's scripts do
+    frames = torch.zeros((T + 1, 3, Hp, Wp), dtype=torch.uint8)
+    frames[:, :, :H, :W] = quantize_frames(S.make_frames(T + 1, H, W, seed=77 + rank))
+    x_cur = frames[1:].contiguous().to(dev)
+    x_cond = frames[:-1].contiguous().to(dev)
     qmap = R.make_qmap(T, Hp, Wp, "ramp").to(dev)
     step = lambda: model(x_cur, x_cond, qmap)  # noqa: E731
     for _ in range(max(warmup, 3)):
@@ -649,7 +649,8 @@ def run_stem_roi(ctx, name, steps, warmup, args, full):
         "value": world * T * steps / (ms_total / 1e3), "unit": UNIT, "ms_per_step": ms_step, "frames_per_step": T,
         "steps": steps, "cuda_graph": False, "clocks": clocks,
         "e2e": {"value": world * T * steps / (e2e_ms / 1e3), "unit": UNIT,
-                "h2d_bytes_per_step": (hx.numel() + hc.numel() + hq.numel()) * 4, "d2h_bytes_per_step": hbits.numel() * 8},
+                "h2d_bytes_per_step": hx.numel() * hx.element_size() + hc.numel() * hc.element_size() + hq.numel() * 4,
+                "d2h_bytes_per_step": hbits.numel() * 8},
         "gpu_launches": launches,
         "whole_step_roofline": {"bound": "tensor", "achieved": gflop_step / ms_step, "peak": peaks["tf_sustained"],
                                 "unit": "TFLOP/s", "frac": gflop_step / ms_step / peaks["tf_sustained"],
@@ -813,7 +814,7 @@ def main():
             "scaling": "weak", "vs_baseline": None, "dtype": DTYPE, "data": "synthetic",
             "config": {"workload": args.workload, "desc": desc, "variant": variant, "height": H, "width": W,
                        "frames_per_step": T, "per_gpu_frames_per_step": T, "cuda_graph": res["cuda_graph"],
-                       "frame_dtype": "uint8 (8-bit samples, v / 255 on the device)" if variant != "stem_roi" else "f32",
+                       "frame_dtype": "uint8 (8-bit samples, v / 255 on the device)",
                        "stats_reduction": "every step" if args.reduce_every_step else "once per run (inside the timed region)",
                        "l2": "per-step working set (several GB of activations) exceeds the 126 MB L2; no flush needed",
                        "checkpoint": "seeded synthetic (spatiotemporalentropymodel_b200.synthetic)"},

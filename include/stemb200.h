@@ -146,6 +146,9 @@ int stemb200_nhwc_f32_to_nchw_f32(const float* in, float* out, int32_t n, int32_
  * 64). The rows are the NHWC input (C = 80) of a 1x1 stemb200_conv2d_gdn_fwd whose weight is the [N][75] reshape. */
 int stemb200_im2col_k5s2_c3(const float* x_nchw, void* out_rows, int32_t n, int32_t h, int32_t w,
                             int32_t h_pad, int32_t w_pad, int32_t pad_top, int32_t pad_left, void* stream);
+/* Same from an 8-bit NCHW frame (pixel = float(v) / 255, see stemb200_synthesis_col2im_u8). */
+int stemb200_im2col_k5s2_c3_u8(const uint8_t* x_nchw, void* out_rows, int32_t n, int32_t h, int32_t w, int32_t h_pad,
+                               int32_t w_pad, int32_t pad_top, int32_t pad_left, void* stream);
 /* Operand canvas of the row_taps first layer (priors.py:422 on the evalSTEM.py:96-109 padded frame): NCHW fp32
  * (n, c <= 8, h, w) -> NHWC fp16 [n][h_pad + 2*border][w_pad + 2*border][8], the frame at (pad_top + border,
  * pad_left + border), zeros elsewhere (conv padding, frame padding and channels c..7). */
@@ -166,6 +169,8 @@ int stemb200_frame_u8_to_nhwc8(const uint8_t* x_nchw, void* canvas, int32_t n, i
  *   [n][h_out][w_out][8], channel 0 = block mean, channels 1..7 = 0 (so it can be a K segment of the next conv). */
 int stemb200_im2col_k3s1_c4(const float* x_nchw, const float* q_nchw, void* out_rows, int32_t n, int32_t h,
                             int32_t w, void* stream);
+int stemb200_im2col_k3s1_c4_u8(const uint8_t* x_nchw, const float* q_nchw, void* out_rows, int32_t n, int32_t h,
+                               int32_t w, void* stream); /* 8-bit frame, fp32 quality map */
 int stemb200_avgpool_nhwc_f16(const void* in, void* out, int32_t n, int32_t h_out, int32_t w_out, int32_t c,
                               int32_t factor, void* stream);
 /* fp16 -> fp32 element cast (numel % 8 == 0): latents produced by an fp16 epilogue that feed the entropy kernels */

@@ -66,6 +66,8 @@ SIGNATURES = {
     "stemb200_frame_to_nhwc8": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
     "stemb200_frame_u8_to_nhwc8": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
     "stemb200_im2col_k3s1_c4": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _vp]),
+    "stemb200_im2col_k3s1_c4_u8": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _vp]),
+    "stemb200_im2col_k5s2_c3_u8": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
     "stemb200_avgpool_nhwc_f16": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp]),
     "stemb200_qmap_pool": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _vp]),
     "stemb200_latent_stage": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, _vp]),

@@ -151,8 +151,9 @@ constexpr int kIm2colRow = 80;
 constexpr int kIm2colPix = 64;
 constexpr int kIm2colInW = 2 * kIm2colPix + 3;  // 131 input columns feed 64 stride-2 outputs of a 5-tap filter
 
+template <typename TIn>
 __global__ void __launch_bounds__(256)
-im2col_k5s2_c3_kernel(const float* __restrict__ x, __half* __restrict__ rows, int h, int w, int h_out, int w_out,
+im2col_k5s2_c3_kernel(const TIn* __restrict__ x, __half* __restrict__ rows, int h, int w, int h_out, int w_out,
                       int pad_top, int pad_left) {
   __shared__ float s_in[3][5][kIm2colInW + 1];
   __shared__ unsigned short s_off[kIm2colRow];  // k -> offset of (ch, r, s) inside s_in, 0xFFFF for the padding
@@ -166,13 +167,13 @@ im2col_k5s2_c3_kernel(const float* __restrict__ x, __half* __restrict__ rows, in
     }
     s_off[k] = off;
   }
-  const float* xi = x + static_cast<long long>(n) * 3 * h * w;
+  const TIn* xi = x + static_cast<long long>(n) * 3 * h * w;
   const int ih0 = 2 * oh - 2 - pad_top, iw0 = 2 * ow0 - 2 - pad_left;
   for (int i = threadIdx.x; i < 3 * 5 * kIm2colInW; i += blockDim.x) {
     const int col = i % kIm2colInW, rr = (i / kIm2colInW) % 5, ch = i / (5 * kIm2colInW);
     const int ih = ih0 + rr, iw = iw0 + col;
     float v = 0.f;
-    if (ih >= 0 && ih < h && iw >= 0 && iw < w) v = __ldg(xi + (static_cast<long long>(ch) * h + ih) * w + iw);
+    if (ih >= 0 && ih < h && iw >= 0 && iw < w) v = px_load(xi + (static_cast<long long>(ch) * h + ih) * w + iw);
     s_in[ch][rr][col] = v;
   }
   __syncthreads();
@@ -202,8 +203,9 @@ im2col_k5s2_c3_kernel(const float* __restrict__ x, __half* __restrict__ rows, in
 constexpr int kIm2col3Row = 40;
 constexpr int kIm2col3InW = kIm2colPix + 2;
 
+template <typename TIn>
 __global__ void __launch_bounds__(256)
-im2col_k3s1_c4_kernel(const float* __restrict__ x, const float* __restrict__ q, __half* __restrict__ rows, int h,
+im2col_k3s1_c4_kernel(const TIn* __restrict__ x, const float* __restrict__ q, __half* __restrict__ rows, int h,
                       int w) {
   __shared__ float s_in[4][3][kIm2col3InW + 2];
   const int n = blockIdx.z, oh = blockIdx.y, ow0 = blockIdx.x * kIm2colPix;
@@ -212,7 +214,7 @@ im2col_k3s1_c4_kernel(const float* __restrict__ x, const float* __restrict__ q, 
     const int ih = oh - 1 + rr, iw = ow0 - 1 + col;
     float v = 0.f;
     if (ih >= 0 && ih < h && iw >= 0 && iw < w)
-      v = ch < 3 ? __ldg(x + ((static_cast<long long>(n) * 3 + ch) * h + ih) * w + iw)
+      v = ch < 3 ? px_load(x + ((static_cast<long long>(n) * 3 + ch) * h + ih) * w + iw)
                  : __ldg(q + (static_cast<long long>(n) * h + ih) * w + iw);
     s_in[ch][rr][col] = v;
   }
@@ -876,18 +878,30 @@ extern "C" int stemb200_nhwc_f32_to_nchw_f32(const float* in, float* out, int32_
   return 0;
 }
 
-extern "C" int stemb200_im2col_k5s2_c3(const float* x_nchw, void* out_rows, int32_t n, int32_t h, int32_t w,
-                                       int32_t h_pad, int32_t w_pad, int32_t pad_top, int32_t pad_left,
-                                       void* stream) {
+template <typename TIn>
+static int im2col_k5s2_c3_impl(const TIn* x_nchw, void* out_rows, int32_t n, int32_t h, int32_t w, int32_t h_pad,
+                               int32_t w_pad, int32_t pad_top, int32_t pad_left, void* stream) {
   if (!x_nchw || !out_rows || n < 1 || h < 1 || w < 1 || h_pad < h || w_pad < w || pad_top < 0 || pad_left < 0)
     return set_error("im2col: bad argument");
   const int h_out = (h_pad - 1) / 2 + 1, w_out = (w_pad - 1) / 2 + 1;
   if (h_out > 65535 || n > 65535) return set_error("im2col: frame too large");
   dim3 grid((w_out + kIm2colPix - 1) / kIm2colPix, h_out, n);
-  im2col_k5s2_c3_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  im2col_k5s2_c3_kernel<TIn><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
       x_nchw, static_cast<__half*>(out_rows), h, w, h_out, w_out, pad_top, pad_left);
   CHECK_LAUNCH("im2col_k5s2_c3");
   return 0;
+}
+
+extern "C" int stemb200_im2col_k5s2_c3(const float* x_nchw, void* out_rows, int32_t n, int32_t h, int32_t w,
+                                       int32_t h_pad, int32_t w_pad, int32_t pad_top, int32_t pad_left,
+                                       void* stream) {
+  return im2col_k5s2_c3_impl<float>(x_nchw, out_rows, n, h, w, h_pad, w_pad, pad_top, pad_left, stream);
+}
+
+extern "C" int stemb200_im2col_k5s2_c3_u8(const uint8_t* x_nchw, void* out_rows, int32_t n, int32_t h, int32_t w,
+                                          int32_t h_pad, int32_t w_pad, int32_t pad_top, int32_t pad_left,
+                                          void* stream) {
+  return im2col_k5s2_c3_impl<uint8_t>(x_nchw, out_rows, n, h, w, h_pad, w_pad, pad_top, pad_left, stream);
 }
 
 // NCHW fp32 frame -> zero-bordered NHWC8 fp16 canvas (operand of the row_taps first layer). One block row = one canvas
@@ -1070,15 +1084,26 @@ extern "C" int stemb200_frame_u8_to_nhwc8(const uint8_t* x_nchw, void* canvas, i
   return frame_to_nhwc8_impl<uint8_t>(x_nchw, canvas, n, c, h, w, h_pad, w_pad, pad_top, pad_left, border, stream);
 }
 
-extern "C" int stemb200_im2col_k3s1_c4(const float* x_nchw, const float* q_nchw, void* out_rows, int32_t n,
-                                       int32_t h, int32_t w, void* stream) {
+template <typename TIn>
+static int im2col_k3s1_c4_impl(const TIn* x_nchw, const float* q_nchw, void* out_rows, int32_t n, int32_t h, int32_t w,
+                               void* stream) {
   if (!x_nchw || !q_nchw || !out_rows || n < 1 || h < 1 || w < 1 || h > 65535 || n > 65535)
     return set_error("im2col_k3s1_c4: bad argument");
   dim3 grid((w + kIm2colPix - 1) / kIm2colPix, h, n);
-  im2col_k3s1_c4_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(x_nchw, q_nchw,
-                                                                            static_cast<__half*>(out_rows), h, w);
+  im2col_k3s1_c4_kernel<TIn><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      x_nchw, q_nchw, static_cast<__half*>(out_rows), h, w);
   CHECK_LAUNCH("im2col_k3s1_c4");
   return 0;
+}
+
+extern "C" int stemb200_im2col_k3s1_c4(const float* x_nchw, const float* q_nchw, void* out_rows, int32_t n,
+                                       int32_t h, int32_t w, void* stream) {
+  return im2col_k3s1_c4_impl<float>(x_nchw, q_nchw, out_rows, n, h, w, stream);
+}
+
+extern "C" int stemb200_im2col_k3s1_c4_u8(const uint8_t* x_nchw, const float* q_nchw, void* out_rows, int32_t n,
+                                          int32_t h, int32_t w, void* stream) {
+  return im2col_k3s1_c4_impl<uint8_t>(x_nchw, q_nchw, out_rows, n, h, w, stream);
 }
 
 extern "C" int stemb200_avgpool_nhwc_f16(const void* in, void* out, int32_t n, int32_t h_out, int32_t w_out,

@@ -352,12 +352,13 @@ class RoiEngine:
         return self.ws.get(name, shape, dtype)
 
     def _analysis4(self, ops, tag, x: Tensor) -> Tuple[Tensor, int, int]:
-        """ConditionEncoder: four stride-2 layers on an image (B, 3, H, W) fp32 NCHW."""
+        """ConditionEncoder: four stride-2 layers on an image (B, 3, H, W) NCHW, fp32 or 8-bit."""
         B, _, H, W = x.shape
         lib = _lib.load()
         h, w = H // 2, W // 2
         rows = self._buf(f"{tag}_rows", (B, h, w, 80))
-        _lib.check(lib.stemb200_im2col_k5s2_c3(x.data_ptr(), rows.data_ptr(), B, H, W, H, W, 0, 0, _stream()), "im2col")
+        im2col = lib.stemb200_im2col_k5s2_c3_u8 if x.dtype == torch.uint8 else lib.stemb200_im2col_k5s2_c3
+        _lib.check(im2col(x.data_ptr(), rows.data_ptr(), B, H, W, H, W, 0, 0, _stream()), "im2col")
         cur = ops[0]([rows], B, h, w, self._buf(f"{tag}_0", (B, h, w, ops[0].c_out)))
         for i in (1, 2, 3):
             ho, wo = ops[i].out_hw(h, w)
@@ -369,7 +370,7 @@ class RoiEngine:
         """PEncoder, ConditionEncoder, HE (stem_roi.py:586-589) -> y_cur fp32 (what is quantised) and its fp16 copy
         (operand of the hyper-encoder), y_conditioned fp16, z fp32 (all NHWC)."""
         _require_cuda(x_cur, x_cond, qmap)
-        x_cur, x_cond, qmap = x_cur.contiguous().float(), x_cond.contiguous().float(), qmap.contiguous().float()
+        x_cur, x_cond, qmap = self._frame(x_cur), self._frame(x_cond), qmap.contiguous().float()
         B, _, H, W = x_cur.shape
         if H % 64 or W % 64:
             raise ValueError("stem_roi needs frame sizes that are multiples of 64 (the scripts pad to 64)")
@@ -378,14 +379,16 @@ class RoiEngine:
         bf = self._buf
         # ================= PEncoder =================
         rows_q = bf("q_rows", (B, H, W, 40))
-        _lib.check(lib.stemb200_im2col_k3s1_c4(x_cur.data_ptr(), qmap.data_ptr(), rows_q.data_ptr(), B, H, W, _stream()),
-                   "im2col_k3s1_c4")
+        u8 = x_cur.dtype == torch.uint8
+        im2col3 = lib.stemb200_im2col_k3s1_c4_u8 if u8 else lib.stemb200_im2col_k3s1_c4
+        _lib.check(im2col3(x_cur.data_ptr(), qmap.data_ptr(), rows_q.data_ptr(), B, H, W, _stream()), "im2col_k3s1_c4")
         q = self.qga1[0]([rows_q], B, H, W, bf("q1a", (B, H, W, 192)))
         q = self.qga1[1]([q], B, H, W, bf("q1b", (B, H, W, 160)))
         q = self.qga1[2]([q], B, H, W, bf("q1", (B, H, W, 128)))
         h, w = H // 2, W // 2
         rows = bf("ga_rows", (B, h, w, 80))
-        _lib.check(lib.stemb200_im2col_k5s2_c3(x_cur.data_ptr(), rows.data_ptr(), B, H, W, H, W, 0, 0, _stream()), "im2col")
+        im2col5 = lib.stemb200_im2col_k5s2_c3_u8 if u8 else lib.stemb200_im2col_k5s2_c3
+        _lib.check(im2col5(x_cur.data_ptr(), rows.data_ptr(), B, H, W, H, W, 0, 0, _stream()), "im2col")
         x = self.ga1([rows], B, h, w, bf("ga1", (B, h, w, 128)))
         qh, qw = H, W  # resolution of q
         for lvl in range(3):
@@ -429,7 +432,12 @@ class RoiEngine:
     def condition(self, x_cond: Tensor) -> Tensor:
         """ConditionEncoder (stem_roi.py:493-501) -> y_conditioned NHWC fp16."""
         _require_cuda(x_cond)
-        return self._analysis4(self.ce, "ce", x_cond.contiguous().float())[0]
+        return self._analysis4(self.ce, "ce", self._frame(x_cond))[0]
+
+    @staticmethod
+    def _frame(x: Tensor) -> Tensor:
+        """Frames are fp32 in [0, 1] or 8-bit samples (used as v / 255 on the device, like ToTensor would make them)."""
+        return x.contiguous() if x.dtype == torch.uint8 else x.contiguous().float()
 
     def gaussian_params(self, zhat16: Tensor, yc16: Tensor, B: int, h: int, w: int) -> Tensor:
         """HD(z_hat), TPM(y_conditioned), EPM (stem_roi.py:591-598) -> (scales | means) NHWC fp32."""

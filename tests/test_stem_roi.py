@@ -136,3 +136,24 @@ def test_cuda_compress_decompress_round_trip():
     real_bits = 8 * sum(len(s) for part in enc["strings"] for s in part)
     est_bits = bits(fwd["likelihoods"]["y"].cpu()) + bits(fwd["likelihoods"]["z"].cpu())
     assert 0.6 * est_bits < real_bits < 1.02 * est_bits, (real_bits, est_bits)
+
+
+@pytest.mark.gpu
+def test_cuda_forward_8bit_frames_bit_identical():
+    """8-bit frames (v / 255 on the device, as in the P-frame pipeline) against the fp32 frames ToTensor makes of them:
+    every output of stem_roi.forward bit for bit (both im2col staging kernels and the ConditionEncoder path)."""
+    from spatiotemporalentropymodel_b200 import stem_roi as R
+    dev = torch.device("cuda:0")
+    model = R.stem_roi()
+    model.load_state_dict(R.make_synthetic_state_dict(seed=0))
+    model = model.to(dev).eval()
+    f8 = torch.round(S.make_frames(3, 128, 192, seed=5) * 255).to(torch.uint8)
+    f32 = f8.float().div(255.0)
+    qmap = torch.cat([R.make_qmap(1, 128, 192, "ramp"), R.make_qmap(1, 128, 192, "uniform", 1.0)]).to(dev)
+    want = model(f32[1:3].to(dev), f32[0:2].to(dev), qmap)
+    want = {"x_hat": want["x_hat"].clone(), "y_hat": want["y_hat"].clone(), "ly": want["likelihoods"]["y"].clone(),
+            "lz": want["likelihoods"]["z"].clone(), "bits": want["bits"].clone()}
+    got = model(f8[1:3].to(dev), f8[0:2].to(dev), qmap)
+    assert torch.equal(got["x_hat"], want["x_hat"]) and torch.equal(got["y_hat"], want["y_hat"])
+    assert torch.equal(got["likelihoods"]["y"], want["ly"]) and torch.equal(got["likelihoods"]["z"], want["lz"])
+    assert torch.equal(got["bits"], want["bits"])
