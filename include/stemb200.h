@@ -160,6 +160,26 @@ int stemb200_frame_u8_to_nhwc8(const uint8_t* x_nchw, void* canvas, int32_t n, i
                                int32_t h_pad, int32_t w_pad, int32_t pad_top, int32_t pad_left, int32_t border,
                                void* stream);
 
+/* Canvas with 4 channels per pixel (R, G, B, 0): the operand of stemb200_conv_first_gdn_fwd. Same geometry as
+ * stemb200_frame_to_nhwc8 with 8 bytes per pixel; c <= 4. */
+int stemb200_frame_to_nhwc4(const float* x_nchw, void* canvas, int32_t n, int32_t c, int32_t h, int32_t w,
+                            int32_t h_pad, int32_t w_pad, int32_t pad_top, int32_t pad_left, int32_t border,
+                            void* stream);
+int stemb200_frame_u8_to_nhwc4(const uint8_t* x_nchw, void* canvas, int32_t n, int32_t c, int32_t h, int32_t w,
+                               int32_t h_pad, int32_t w_pad, int32_t pad_top, int32_t pad_left, int32_t border,
+                               void* stream);
+/* First analysis layer + GDN with resident weights (priors.py:422 conv(3, N) + :423 GDN(N); layers/gdn.py:52-67),
+ * N = 192: conv 3 -> 192, k5, s2, p2 on the NHWC4 canvas [n][h_in + 4][w_in + 4][4] fp16 (+ 64 elements of slack;
+ * h_in / w_in the even padded frame size, border = 2), then x * rsqrt(beta + gamma . x^2).
+ *   packed_w0   : [192][5 kernel rows][8 taps][4 channels] fp16 = w[o][ch][r][s] at k = r*32 + s*4 + ch (taps 5..7 and
+ *                 channel 3 zero): one kernel row of an output pixel is 32 contiguous fp16 of the canvas;
+ *   packed_gamma: [192][192] fp16, K-major, of the re-parametrised gamma (as for stemb200_conv2d_gdn_fwd); beta fp32;
+ *   sq_scale    : x is prescaled by it before squaring (power of two; fp16 range), out: NHWC fp16 [n][h_in/2][w_in/2][192].
+ * W0 and gamma stay in shared memory for the whole launch; the TMA ring carries only the 8 KB operand tiles. */
+int stemb200_conv_first_gdn_fwd(const void* canvas_nhwc4, int32_t n, int32_t h_in, int32_t w_in, int32_t border,
+                                const void* packed_w0, const float* bias, const void* packed_gamma, const float* beta,
+                                float sq_scale, void* out, void* stream);
+
 /* stem_roi (compressai/models/stem_roi.py) staging kernels.
  * im2col_k3s1_c4: operand rows of conv(4, 192, k3, s1) on cat[x (3 ch), Qmap (1 ch)] (:379, :586):
  *   [n*h*w][40] fp16, k = (r*3+s)*4 + ch for 36 entries, then 4 zeros.

@@ -65,6 +65,9 @@ SIGNATURES = {
     "stemb200_im2col_k5s2_c3": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
     "stemb200_frame_to_nhwc8": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
     "stemb200_frame_u8_to_nhwc8": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
+    "stemb200_frame_to_nhwc4": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
+    "stemb200_frame_u8_to_nhwc4": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
+    "stemb200_conv_first_gdn_fwd": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _f32, _vp, _vp]),
     "stemb200_im2col_k3s1_c4": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _vp]),
     "stemb200_im2col_k3s1_c4_u8": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _vp]),
     "stemb200_im2col_k5s2_c3_u8": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),

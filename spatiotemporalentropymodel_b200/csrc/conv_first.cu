@@ -1,0 +1,506 @@
+// First analysis layer of g_a fused with its GDN (sm_100a): compact operands, resident gamma, ping-pong epilogue.
+//
+//   x   = conv(frame, W0; 3 -> 192 channels, k5, s2, p2) + bias      priors.py:422 (conv(3, N)), models/utils.py:112-119
+//   out = x * rsqrt(beta + gamma . x^2)                              layers/gdn.py:52-67
+//
+// Why a kernel of its own: with 15 real input values per kernel row the layer is bound by shared-memory bandwidth and by
+// its epilogue chain, not by the tensor pipe.  conv_gdn_pp_kernel (conv_igemm.cu) moves ~690 KB per 128-pixel tile
+// through shared memory - 192 KB of it W0 and gamma re-streamed by TMA for every tile, 150 KB operand reads of a
+// K = 240 contraction for 75 real taps x channels - against 2 600 tensor cycles: 5 800 cycles per tile, 0.42 of the
+// sustained tensor peak (profiles/r02_ncu_full_conv_gdn.txt).  Here
+//   * the frame canvas has 4 channels per pixel (R, G, B, 0), so one kernel row of an output pixel is 5 taps x 4 = 20
+//     contiguous fp16 inside a 32-element (64-byte) TMA box: K = 5 x 32 = 160 issued (10 MMAs instead of 15), 64-byte
+//     swizzled operand tiles of 8 KB (A) and 12 KB (W0 row) instead of 16 and 24 KB;
+//   * gamma (3 x 24 KB, 128-byte swizzle) is loaded ONCE per CTA and stays in shared memory;
+//   * the 16 epilogue warps form two groups on alternating tiles, each with its own accumulator and (x s)^2 / staging
+//     buffer and x s kept in registers between its two phases (the ping-pong of conv_gdn_pp_kernel): a first version
+//     of this kernel with one group and everything resident was no longer shared-memory-bound (62 % of the pipe) but
+//     ran at the same 6 100 cycles per tile - the chain phase 1 -> gamma MMA -> phase 2 behind a 5-step main loop.
+// ~460 KB per tile.  Persistent, one CTA per SM, 640 threads: warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM
+// allocator, warps 4-19 = epilogue.
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+
+#include "../../include/stemb200.h"
+#include "internal.h"
+#include "ptx.cuh"
+
+namespace stem {
+namespace {
+
+constexpr int kN = 192;                        // output channels (mbt2018: N = 192)
+constexpr int kRows = 5;                       // kernel rows = k-steps per tile
+constexpr int kKRow = 32;                      // fp16 per kernel row in the operand (5 taps x 4 ch = 20 real)
+constexpr int kWRowBytes = kN * kKRow * 2;     // 12 KB: W0 slice of one kernel row (64-byte swizzle)
+constexpr int kGChunks = kN / 64;              // 3
+constexpr int kGChunkBytes = kN * 128;         // 24 KB: gamma chunk (128-byte swizzle)
+constexpr int kAStage = 128 * kKRow * 2;       // 8 KB: A tile of one kernel row
+constexpr int kStageBytes = kAStage + kWRowBytes;  // 20 KB: A tile + the W0 slice of that kernel row
+constexpr int kStages = 2;
+constexpr int kA2Chunk = 128 * 128;            // 16 KB: (x s)^2 chunk / output staging chunk
+constexpr int kA2Bytes = kGChunks * kA2Chunk;  // 48 KB per epilogue group
+constexpr int kEpiWarps = 16;
+constexpr int kEpiThreads = kEpiWarps * 32;
+constexpr int kGroupThreads = kEpiThreads / 2;
+constexpr int kThreads = 128 + kEpiThreads;
+constexpr int kSmem = 1024 + kGChunks * kGChunkBytes + kStages * kStageBytes + 2 * kA2Bytes + 256 + 2 * kN * 4;
+static_assert(kSmem <= 232448, "shared memory budget");
+
+struct FirstParams {
+  alignas(64) CUtensorMap a_map[2];  // canvas rows of parity 0 / 1
+  alignas(64) CUtensorMap w_map;
+  alignas(64) CUtensorMap g_map;
+  alignas(64) CUtensorMap out_map;
+  int batch, h_out, w_out, tile_h, tile_w, tiles_h, tiles_w, total_tiles;
+  float sq_scale;
+  const float* bias;
+  const float* beta;
+};
+
+// K-major, SWIZZLE_64B shared-memory matrix descriptor: rows of 64 B, 8-row swizzle atoms of 512 B
+__device__ __forceinline__ uint64_t umma_desc_sw64(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
+  d |= static_cast<uint64_t>(1) << 16;
+  d |= static_cast<uint64_t>(512 >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(4) << 61;
+  return d;
+}
+
+__device__ __forceinline__ float rsqrt_approx(float x) {
+  float y;
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+__device__ __forceinline__ uint32_t pack2(float a, float b) {
+  __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+__global__ void __launch_bounds__(kThreads, 1) conv_first_gdn_kernel(const __grid_constant__ FirstParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t g_base = smem_base;
+  const uint32_t stage_base = g_base + kGChunks * kGChunkBytes;
+  const uint32_t a2_base0 = stage_base + kStages * kStageBytes;
+  const uint32_t bar_base = a2_base0 + 2 * kA2Bytes;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (kStages + s); };
+  auto tfull_bar = [&](int g) { return bar_base + 8u * (2 * kStages + g); };
+  auto a2rdy_bar = [&](int g) { return bar_base + 8u * (2 * kStages + 2 + g); };
+  auto nfull_bar = [&](int g) { return bar_base + 8u * (2 * kStages + 4 + g); };
+  auto accfree_bar = [&](int g) { return bar_base + 8u * (2 * kStages + 6 + g); };
+  const uint32_t wfull_bar = bar_base + 8u * (2 * kStages + 8);
+  const uint32_t tmem_slot = bar_base + 8u * (2 * kStages + 9);
+  const uint32_t bias_smem = bar_base + 256u;
+  const uint32_t beta_smem = bias_smem + 4u * kN;
+
+  const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);
+  const int lane = threadIdx.x & 31;
+  const int first = static_cast<int>(blockIdx.x), stride = static_cast<int>(gridDim.x);
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.a_map[0]);
+    tma_prefetch_desc(&p.a_map[1]);
+    tma_prefetch_desc(&p.w_map);
+    tma_prefetch_desc(&p.g_map);
+    tma_prefetch_desc(&p.out_map);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int g = 0; g < 2; ++g) {
+      mbar_init(tfull_bar(g), 1);
+      mbar_init(a2rdy_bar(g), kEpiWarps / 2);
+      mbar_init(nfull_bar(g), 1);
+      mbar_init(accfree_bar(g), kEpiWarps / 2);
+    }
+    mbar_init(wfull_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  if (warp >= 4) {
+    // bias pre-scaled (x s = fma(acc, s, b s)) and the folded normaliser offset s^2 beta
+    for (int i = threadIdx.x - 128; i < kN; i += kEpiThreads) {
+      const float b = __ldg(p.bias + i) * p.sq_scale, g = __ldg(p.beta + i) * p.sq_scale * p.sq_scale;
+      asm volatile("st.shared.f32 [%0], %1;" ::"r"(bias_smem + 4u * i), "f"(b) : "memory");
+      asm volatile("st.shared.f32 [%0], %1;" ::"r"(beta_smem + 4u * i), "f"(g) : "memory");
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  tmem_base = __shfl_sync(0xffffffffu, tmem_base, 0);
+
+  const uint32_t a_tx_bytes = static_cast<uint32_t>(p.tile_h * p.tile_w) * (kKRow * 2);
+  auto decode = [&](int tile, int& n_img, int& h0, int& w0) {
+    int m = tile;
+    const int twi = m % p.tiles_w;
+    m /= p.tiles_w;
+    const int thi = m % p.tiles_h;
+    n_img = m / p.tiles_h;
+    h0 = thi * p.tile_h;
+    w0 = twi * p.tile_w;
+  };
+
+  if (warp == 0) {
+    // ============ TMA producer: gamma once, then per kernel row one A tile + the W0 slice of that row ============
+    const bool leader = elect_one();
+    if (leader) {
+      mbar_arrive_expect_tx(wfull_bar, kGChunks * kGChunkBytes);
+      for (int kc = 0; kc < kGChunks; ++kc) tma_load_2d(g_base + kc * kGChunkBytes, &p.g_map, wfull_bar, kc * 64, 0);
+    }
+    int s = 0;
+    uint32_t ph = 0;
+    for (int tile = first; tile < p.total_tiles; tile += stride) {
+      int n_img, h0, w0;
+      decode(tile, n_img, h0, w0);
+      for (int r = 0; r < kRows; ++r) {
+        mbar_wait(empty_bar(s), ph ^ 1u);
+        if (leader) {
+          const uint32_t dst = stage_base + s * kStageBytes;
+          mbar_arrive_expect_tx(full_bar(s), a_tx_bytes + kWRowBytes);
+          // canvas row 2 (h0 + i) + r has parity r & 1 and index h0 + i + (r >> 1) among the rows of that parity
+          tma_load_4d(dst, &p.a_map[r & 1], full_bar(s), 0, w0, h0 + (r >> 1), n_img);
+          tma_load_2d(dst + kAStage, &p.w_map, full_bar(s), r * kKRow, 0);
+        }
+        if (++s == kStages) {
+          s = 0;
+          ph ^= 1u;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    const bool leader = elect_one();
+    constexpr uint32_t idesc = umma_idesc(/*F16*/ 0u, 128u, kN);
+    mbar_wait(wfull_bar, 0);
+    tc_fence_after();
+    int s = 0;
+    uint32_t ph = 0;
+    auto mma_row = [&](uint32_t d_tmem, int r) {
+      mbar_wait(full_bar(s), ph);
+      tc_fence_after();
+      const uint32_t a_addr = stage_base + s * kStageBytes;
+      const uint64_t adesc = umma_desc_sw64(a_addr);
+      const uint64_t bdesc = umma_desc_sw64(a_addr + kAStage);
+      if (leader) {
+#pragma unroll
+        for (int kk = 0; kk < kKRow / 16; ++kk)
+          mma_f16_ss(d_tmem, adesc + 2u * kk, bdesc + 2u * kk, idesc, (r > 0 || kk > 0) ? 1u : 0u);
+        mma_commit(empty_bar(s));
+      }
+      if (++s == kStages) {
+        s = 0;
+        ph ^= 1u;
+      }
+    };
+    // norm(j) = gamma . (x s)^2 over the accumulator of tile j, operand in group (j & 1)'s buffer, gamma resident
+    auto mma_gamma = [&](int j) {
+      const int g = j & 1;
+      mbar_wait(a2rdy_bar(g), (j >> 1) & 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + g * kN;
+      const uint32_t a2 = a2_base0 + g * kA2Bytes;
+      if (leader) {
+#pragma unroll
+        for (int kc = 0; kc < kGChunks; ++kc) {
+          const uint64_t adesc = umma_desc_sw128(a2 + kc * kA2Chunk);
+          const uint64_t bdesc = umma_desc_sw128(g_base + kc * kGChunkBytes);
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk)
+            mma_f16_ss(d_tmem, adesc + 2u * kk, bdesc + 2u * kk, idesc, (kc > 0 || kk > 0) ? 1u : 0u);
+        }
+        mma_commit(nfull_bar(g));
+      }
+    };
+    int it = 0;
+    for (int tile = first; tile < p.total_tiles; tile += stride, ++it) {
+      const int g = it & 1;
+      const uint32_t d_tmem = tmem_base + g * kN;
+      if (it >= 2) {  // phase 2 of tile it-2 (same group) has finished reading this accumulator
+        mbar_wait(accfree_bar(g), ((it >> 1) - 1) & 1);
+        tc_fence_after();
+      }
+      mma_row(d_tmem, 0);
+      mma_row(d_tmem, 1);
+      if (it > 0) mma_gamma(it - 1);
+      mma_row(d_tmem, 2);
+      mma_row(d_tmem, 3);
+      mma_row(d_tmem, 4);
+      if (leader) mma_commit(tfull_bar(g));
+    }
+    if (it > 0) mma_gamma(it - 1);
+  } else if (warp >= 4) {
+    // ===================== epilogue: two groups of 8 warps on alternating tiles =====================
+    const int G = (warp - 4) >> 3;           // group = parity of the tiles it owns
+    const int wg = (warp - 4) & 7;           // warp inside the group
+    const int gtid = wg * 32 + lane;         // 0..255
+    const int row = (wg & 3) * 32 + lane;    // accumulator row == pixel of the patch (TMEM lane group = warp % 4)
+    const int half = wg >> 2;                // 32-column half of every 64-channel chunk
+    const uint32_t lane_off = static_cast<uint32_t>((wg & 3) * 32) << 16;
+    const uint32_t rsw = static_cast<uint32_t>(row & 7);
+    const uint32_t row_off = static_cast<uint32_t>(row) * 128u;
+    const uint32_t a2_base = a2_base0 + G * kA2Bytes;
+    const uint32_t acc_col = tmem_base + lane_off + G * kN + 32 * half;
+    const uint32_t bar_id = 1 + G;
+    const float sc = p.sq_scale;  // power of two: fma(acc, s, b s) rounds exactly like (acc + b) s
+    int n = 0;
+    for (int tile = first + G * stride; tile < p.total_tiles; tile += 2 * stride, ++n) {
+      int n_img, h0, w0;
+      decode(tile, n_img, h0, w0);
+      const uint32_t par = n & 1;
+      uint32_t hx[kGChunks * 16];  // x s of this thread's 32 columns per chunk, packed fp16
+      mbar_wait(tfull_bar(G), par);
+      tc_fence_after();
+      // ---- phase 1: x s -> registers, (x s)^2 -> this group's smem operand (its previous tile's stores must be out)
+#pragma unroll
+      for (int g = 0; g < kGChunks; ++g) {
+        if (gtid == 0) {
+          if (g == 0) tma_store_wait_read<kGChunks - 1>();
+          else if (g + 1 < kGChunks) tma_store_wait_read<1>();
+          else tma_store_wait_read<0>();
+        }
+        named_bar_sync(bar_id, kGroupThreads);
+#pragma unroll
+        for (int sub = 0; sub < 2; ++sub) {
+          const int c = 64 * g + 32 * half + 16 * sub;
+          uint32_t r[16];
+          tmem_ld_32x16(acc_col + 64 * g + 16 * sub, r);
+          tmem_ld_wait();
+          uint32_t hq[8];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            float b0, b1, b2, b3;
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                         : "=f"(b0), "=f"(b1), "=f"(b2), "=f"(b3)
+                         : "r"(bias_smem + 4u * (c + 4 * j)));
+            const __half2 h0v =
+                __floats2half2_rn(fmaf(__uint_as_float(r[4 * j]), sc, b0), fmaf(__uint_as_float(r[4 * j + 1]), sc, b1));
+            const __half2 h1v = __floats2half2_rn(fmaf(__uint_as_float(r[4 * j + 2]), sc, b2),
+                                                  fmaf(__uint_as_float(r[4 * j + 3]), sc, b3));
+            const __half2 q0 = __hmul2(h0v, h0v), q1 = __hmul2(h1v, h1v);
+            hx[g * 16 + sub * 8 + 2 * j] = *reinterpret_cast<const uint32_t*>(&h0v);
+            hx[g * 16 + sub * 8 + 2 * j + 1] = *reinterpret_cast<const uint32_t*>(&h1v);
+            hq[2 * j] = *reinterpret_cast<const uint32_t*>(&q0);
+            hq[2 * j + 1] = *reinterpret_cast<const uint32_t*>(&q1);
+          }
+          const uint32_t cbase = a2_base + static_cast<uint32_t>(g) * kA2Chunk + row_off;
+          const uint32_t pa = ((4u * half + 2u * sub) ^ rsw) << 4, pb = ((4u * half + 2u * sub + 1u) ^ rsw) << 4;
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(cbase + pa), "r"(hq[0]), "r"(hq[1]), "r"(hq[2]),
+                       "r"(hq[3])
+                       : "memory");
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(cbase + pb), "r"(hq[4]), "r"(hq[5]), "r"(hq[6]),
+                       "r"(hq[7])
+                       : "memory");
+        }
+      }
+      fence_proxy_async_smem();  // (x s)^2 is read by the tensor core through the async proxy
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(a2rdy_bar(G));
+
+      // ---- phase 2: out = (x s) * rsqrt(s^2 beta + acc) into the group's (now free) x^2 buffers, one TMA store per chunk
+      mbar_wait(nfull_bar(G), par);
+      tc_fence_after();
+#pragma unroll
+      for (int g = 0; g < kGChunks; ++g) {
+#pragma unroll
+        for (int sub = 0; sub < 2; ++sub) {
+          const int c = 64 * g + 32 * half + 16 * sub;
+          uint32_t r[16];
+          tmem_ld_32x16(acc_col + 64 * g + 16 * sub, r);
+          tmem_ld_wait();
+          if (g + 1 == kGChunks && sub == 1) {
+            // every TMEM read of this tile has completed: hand the accumulator back to the MMA warp
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(accfree_bar(G));
+          }
+          uint32_t ho[8];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            float b0, b1, b2, b3;
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                         : "=f"(b0), "=f"(b1), "=f"(b2), "=f"(b3)
+                         : "r"(beta_smem + 4u * (c + 4 * j)));
+            const float f0 = rsqrt_approx(__uint_as_float(r[4 * j]) + b0);
+            const float f1 = rsqrt_approx(__uint_as_float(r[4 * j + 1]) + b1);
+            const float f2 = rsqrt_approx(__uint_as_float(r[4 * j + 2]) + b2);
+            const float f3 = rsqrt_approx(__uint_as_float(r[4 * j + 3]) + b3);
+            const float2 x0 = __half22float2(*reinterpret_cast<const __half2*>(&hx[g * 16 + sub * 8 + 2 * j]));
+            const float2 x1 = __half22float2(*reinterpret_cast<const __half2*>(&hx[g * 16 + sub * 8 + 2 * j + 1]));
+            ho[2 * j] = pack2(x0.x * f0, x0.y * f1);
+            ho[2 * j + 1] = pack2(x1.x * f2, x1.y * f3);
+          }
+          const uint32_t cbase = a2_base + static_cast<uint32_t>(g) * kA2Chunk + row_off;
+          const uint32_t pa = ((4u * half + 2u * sub) ^ rsw) << 4, pb = ((4u * half + 2u * sub + 1u) ^ rsw) << 4;
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(cbase + pa), "r"(ho[0]), "r"(ho[1]), "r"(ho[2]),
+                       "r"(ho[3])
+                       : "memory");
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(cbase + pb), "r"(ho[4]), "r"(ho[5]), "r"(ho[6]),
+                       "r"(ho[7])
+                       : "memory");
+        }
+        fence_proxy_async_smem();
+        named_bar_sync(bar_id, kGroupThreads);
+        if (gtid == 0) {
+          tma_store_4d(&p.out_map, a2_base + static_cast<uint32_t>(g) * kA2Chunk, 64 * g, w0, h0, n_img);
+          tma_store_commit();
+        }
+      }
+    }
+    if (gtid == 0) tma_store_wait_all<0>();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, 512);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(f);
+  });
+  return fn;
+}
+
+int encode(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides,
+           const cuuint32_t* box, CUtensorMapSwizzle swz, const char* what) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return set_error("cuTensorMapEncodeTiled unavailable");
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, rank, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    char buf[160];
+    snprintf(buf, sizeof(buf), "cuTensorMapEncodeTiled(%s) failed: %d", what, static_cast<int>(r));
+    return set_error(buf);
+  }
+  return 0;
+}
+
+// output patch of <= 128 pixels that tiles (h, w) with the fewest tiles, ties towards square patches
+void pick_patch(int h, int w, int& th, int& tw) {
+  double best = -1.0;
+  th = 1;
+  tw = std::min(w, 128);
+  for (int a = 1; a <= 128; ++a)
+    for (int b = 1; b <= 128 / a; ++b) {
+      const long long tiles = static_cast<long long>((h + a - 1) / a) * ((w + b - 1) / b);
+      const double eff = static_cast<double>(h) * w / (static_cast<double>(tiles) * 128.0);
+      const double score = eff - 1e-4 * (static_cast<double>(a + b) / (a * b));
+      if (score > best) {
+        best = score;
+        th = a;
+        tw = b;
+      }
+    }
+}
+
+}  // namespace
+}  // namespace stem
+
+using namespace stem;
+
+extern "C" int stemb200_conv_first_gdn_fwd(const void* canvas_nhwc4, int32_t n, int32_t h_in, int32_t w_in,
+                                           int32_t border, const void* packed_w0, const float* bias,
+                                           const void* packed_gamma, const float* beta, float sq_scale, void* out,
+                                           void* stream) {
+  if (!canvas_nhwc4 || !packed_w0 || !bias || !packed_gamma || !beta || !out)
+    return set_error("conv_first_gdn_fwd: null argument");
+  if (n < 1 || h_in < 2 || w_in < 2 || (h_in & 1) || (w_in & 1) || border != 2 || sq_scale <= 0.f)
+    return set_error("conv_first_gdn_fwd: needs even h_in / w_in, border == 2 (k5 s2 p2), sq_scale > 0");
+  if ((reinterpret_cast<uintptr_t>(canvas_nhwc4) | reinterpret_cast<uintptr_t>(packed_w0) |
+       reinterpret_cast<uintptr_t>(packed_gamma) | reinterpret_cast<uintptr_t>(out)) & 15)
+    return set_error("conv_first_gdn_fwd: pointers must be 16-byte aligned");
+  FirstParams p;
+  memset(&p, 0, sizeof(p));
+  const int h_out = h_in / 2, w_out = w_in / 2;
+  const long long hc = h_in + 2 * border, wc = w_in + 2 * border;
+  int th, tw;
+  pick_patch(h_out, w_out, th, tw);
+  for (int par = 0; par < 2; ++par) {
+    // view {32 contiguous fp16 (8 pixels x 4 ch), w_out windows 2 pixels apart, canvas rows of one parity, n}
+    const cuuint64_t dims[4] = {static_cast<cuuint64_t>(kKRow), static_cast<cuuint64_t>(w_out),
+                                static_cast<cuuint64_t>((hc - par + 1) / 2), static_cast<cuuint64_t>(n)};
+    const cuuint64_t strides[3] = {16, static_cast<cuuint64_t>(wc) * 8 * 2, static_cast<cuuint64_t>(hc * wc) * 8};
+    const cuuint32_t box[4] = {static_cast<cuuint32_t>(kKRow), static_cast<cuuint32_t>(tw), static_cast<cuuint32_t>(th), 1u};
+    const char* origin = static_cast<const char*>(canvas_nhwc4) + static_cast<size_t>(par) * wc * 8;
+    if (int rc = encode(&p.a_map[par], origin, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_64B, "canvas")) return rc;
+  }
+  {
+    const cuuint64_t dims[2] = {static_cast<cuuint64_t>(kRows * kKRow), static_cast<cuuint64_t>(kN)};
+    const cuuint64_t strides[1] = {static_cast<cuuint64_t>(kRows * kKRow) * 2};
+    const cuuint32_t box[2] = {static_cast<cuuint32_t>(kKRow), static_cast<cuuint32_t>(kN)};
+    if (int rc = encode(&p.w_map, packed_w0, 2, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_64B, "W0")) return rc;
+  }
+  {
+    const cuuint64_t dims[2] = {static_cast<cuuint64_t>(kN), static_cast<cuuint64_t>(kN)};
+    const cuuint64_t strides[1] = {static_cast<cuuint64_t>(kN) * 2};
+    const cuuint32_t box[2] = {64u, static_cast<cuuint32_t>(kN)};
+    if (int rc = encode(&p.g_map, packed_gamma, 2, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B, "gamma")) return rc;
+  }
+  {
+    const cuuint64_t dims[4] = {static_cast<cuuint64_t>(kN), static_cast<cuuint64_t>(w_out),
+                                static_cast<cuuint64_t>(h_out), static_cast<cuuint64_t>(n)};
+    const cuuint64_t strides[3] = {static_cast<cuuint64_t>(kN) * 2, static_cast<cuuint64_t>(w_out) * kN * 2,
+                                   static_cast<cuuint64_t>(h_out) * w_out * kN * 2};
+    const cuuint32_t box[4] = {64u, static_cast<cuuint32_t>(tw), static_cast<cuuint32_t>(th), 1u};
+    if (int rc = encode(&p.out_map, out, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B, "out")) return rc;
+  }
+  p.batch = n;
+  p.h_out = h_out;
+  p.w_out = w_out;
+  p.tile_h = th;
+  p.tile_w = tw;
+  p.tiles_h = (h_out + th - 1) / th;
+  p.tiles_w = (w_out + tw - 1) / tw;
+  const long long total = static_cast<long long>(n) * p.tiles_h * p.tiles_w;
+  if (total > 0x7fffffffLL) return set_error("conv_first_gdn_fwd: too many tiles");
+  p.total_tiles = static_cast<int>(total);
+  p.sq_scale = sq_scale;
+  p.bias = bias;
+  p.beta = beta;
+  static bool configured = false;  // benign race: the attribute set is idempotent
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(conv_first_gdn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
+    if (e != cudaSuccess) return set_cuda_error("cudaFuncSetAttribute(conv_first_gdn)", e);
+    configured = true;
+  }
+  const int grid = static_cast<int>(std::min<long long>(total, num_sms()));
+  conv_first_gdn_kernel<<<grid, kThreads, kSmem, static_cast<cudaStream_t>(stream)>>>(p);
+  count_launch();
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_cuda_error("conv_first_gdn launch", e);
+  return 0;
+}

@@ -936,9 +936,10 @@ template <> struct RawQuadOf<uint8_t> { using type = RawQuadU8; };
 
 constexpr int kCanvasRowsPerThread = 2;  // two canvas rows per thread: twice the loads in flight (the kernel is latency-bound)
 
-template <typename TIn>
+// kCP = channels per canvas pixel: 8 (uint4 per pixel, row_taps conv kernel) or 4 (uint2 per pixel, conv_first.cu)
+template <typename TIn, int kCP>
 __global__ void __launch_bounds__(128)
-frame_to_nhwc8_kernel(const TIn* __restrict__ x, uint4* __restrict__ canvas, int c, int h, int w, int hc, int wc,
+frame_to_nhwc8_kernel(const TIn* __restrict__ x, void* __restrict__ canvas, int c, int h, int w, int hc, int wc,
                       int off_top, int off_left, int groups, int vec_ok, int total_rows) {
   const int g = blockIdx.y * 128 + threadIdx.x;
   if (g >= groups) return;
@@ -990,10 +991,20 @@ frame_to_nhwc8_kernel(const TIn* __restrict__ x, uint4* __restrict__ canvas, int
           }
       }
     }
-    uint4* dst = canvas + static_cast<long long>(row) * wc;
+    if constexpr (kCP == 8) {
+      uint4* dst = static_cast<uint4*>(canvas) + static_cast<long long>(row) * wc;
 #pragma unroll
-    for (int p = 0; p < 4; ++p)
-      if (cw0 + p >= 0 && cw0 + p < wc) dst[cw0 + p] = pack_nhwc8(v[p]);
+      for (int p = 0; p < 4; ++p)
+        if (cw0 + p >= 0 && cw0 + p < wc) dst[cw0 + p] = pack_nhwc8(v[p]);
+    } else {
+      uint2* dst = static_cast<uint2*>(canvas) + static_cast<long long>(row) * wc;
+#pragma unroll
+      for (int p = 0; p < 4; ++p)
+        if (cw0 + p >= 0 && cw0 + p < wc) {
+          const uint4 u = pack_nhwc8(v[p]);
+          dst[cw0 + p] = make_uint2(u.x, u.y);
+        }
+    }
   }
 }
 
@@ -1051,11 +1062,11 @@ extern "C" int stemb200_synthesis_col2im_u8(const void* col_f16, const float* bi
                                         pad_left, sq_err, clamp01, stream);
 }
 
-template <typename TIn>
+template <typename TIn, int kCP = 8>
 static int frame_to_nhwc8_impl(const TIn* x_nchw, void* canvas, int32_t n, int32_t c, int32_t h, int32_t w,
                                int32_t h_pad, int32_t w_pad, int32_t pad_top, int32_t pad_left, int32_t border,
                                void* stream) {
-  if (!x_nchw || !canvas || n < 1 || c < 1 || c > 8 || h < 1 || w < 1 || h_pad < h || w_pad < w || pad_top < 0 ||
+  if (!x_nchw || !canvas || n < 1 || c < 1 || c > kCP || h < 1 || w < 1 || h_pad < h || w_pad < w || pad_top < 0 ||
       pad_left < 0 || border < 0 || pad_top + h > h_pad || pad_left + w > w_pad)
     return set_error("frame_to_nhwc8: bad argument");
   const int hc = h_pad + 2 * border, wc = w_pad + 2 * border;
@@ -1066,8 +1077,8 @@ static int frame_to_nhwc8_impl(const TIn* x_nchw, void* canvas, int32_t n, int32
   const int vec_ok = (w % 4 == 0) && (reinterpret_cast<uintptr_t>(x_nchw) % (4 * sizeof(TIn)) == 0);
   const int total_rows = n * hc;
   dim3 grid((total_rows + kCanvasRowsPerThread - 1) / kCanvasRowsPerThread, (groups + 127) / 128);
-  frame_to_nhwc8_kernel<TIn><<<grid, 128, 0, static_cast<cudaStream_t>(stream)>>>(
-      x_nchw, static_cast<uint4*>(canvas), c, h, w, hc, wc, off_top, off_left, groups, vec_ok, total_rows);
+  frame_to_nhwc8_kernel<TIn, kCP><<<grid, 128, 0, static_cast<cudaStream_t>(stream)>>>(
+      x_nchw, canvas, c, h, w, hc, wc, off_top, off_left, groups, vec_ok, total_rows);
   CHECK_LAUNCH("frame_to_nhwc8");
   return 0;
 }
@@ -1082,6 +1093,18 @@ extern "C" int stemb200_frame_u8_to_nhwc8(const uint8_t* x_nchw, void* canvas, i
                                           int32_t w, int32_t h_pad, int32_t w_pad, int32_t pad_top, int32_t pad_left,
                                           int32_t border, void* stream) {
   return frame_to_nhwc8_impl<uint8_t>(x_nchw, canvas, n, c, h, w, h_pad, w_pad, pad_top, pad_left, border, stream);
+}
+
+extern "C" int stemb200_frame_to_nhwc4(const float* x_nchw, void* canvas, int32_t n, int32_t c, int32_t h, int32_t w,
+                                       int32_t h_pad, int32_t w_pad, int32_t pad_top, int32_t pad_left,
+                                       int32_t border, void* stream) {
+  return frame_to_nhwc8_impl<float, 4>(x_nchw, canvas, n, c, h, w, h_pad, w_pad, pad_top, pad_left, border, stream);
+}
+
+extern "C" int stemb200_frame_u8_to_nhwc4(const uint8_t* x_nchw, void* canvas, int32_t n, int32_t c, int32_t h,
+                                          int32_t w, int32_t h_pad, int32_t w_pad, int32_t pad_top, int32_t pad_left,
+                                          int32_t border, void* stream) {
+  return frame_to_nhwc8_impl<uint8_t, 4>(x_nchw, canvas, n, c, h, w, h_pad, w_pad, pad_top, pad_left, border, stream);
 }
 
 template <typename TIn>

@@ -217,6 +217,42 @@ class ConvOp:
         return out
 
 
+class FirstLayerOp:
+    """g_a.0 + GDN with resident weights (csrc/conv_first.cu, stemb200_conv_first_gdn_fwd): the frame is staged as an
+    NHWC4 canvas and W0 is packed as [192][5 rows][8 taps x 4 channels]."""
+
+    def __init__(self, weight: Tensor, bias: Tensor, beta: Tensor, gamma: Tensor):
+        _require_cuda(weight, bias)
+        N = weight.shape[0]
+        if tuple(weight.shape) != (192, 3, 5, 5):
+            raise ValueError("FirstLayerOp is built for conv(3, 192, k5, s2)")
+        dev = weight.device
+        self.lib = _lib.load()
+        w = torch.zeros((N, 5, 8, 4), dtype=torch.float32, device=dev)
+        w[:, :, :5, :3] = weight.detach().float().permute(0, 2, 3, 1)   # [o][r][s][ch]
+        self.packed = w.reshape(N, 160).to(torch.float16).contiguous()
+        self.bias = bias.detach().float().contiguous()
+        self.beta = beta.detach().to(dev, torch.float32).contiguous()
+        self.gamma_packed = gamma.detach().to(dev, torch.float32).to(torch.float16).contiguous()  # [c_out][c_in], K-major
+        self.c_out = N
+        self.alg_flops_per_out_pixel = 2.0 * 75 * N + 2.0 * N * N
+        self.gdn = False
+
+    def alg_flops(self, batch: int, h: int, w: int) -> float:
+        return self.alg_flops_per_out_pixel * batch * (h // 2) * (w // 2)
+
+    def out_hw(self, h: int, w: int) -> Tuple[int, int]:
+        return h // 2, w // 2
+
+    def __call__(self, inputs: Sequence[Tensor], batch: int, h: int, w: int, out: Tensor,
+                 aux: Optional[Tensor] = None) -> Tensor:
+        _lib.check(self.lib.stemb200_conv_first_gdn_fwd(
+            inputs[0].data_ptr(), batch, h, w, 2, self.packed.data_ptr(), self.bias.data_ptr(),
+            self.gamma_packed.data_ptr(), self.beta.data_ptr(), SQ_SCALE, out.data_ptr(), _stream()),
+            "conv_first_gdn_fwd")
+        return out
+
+
 def sft_op(w_gamma: Tensor, b_gamma: Tensor, w_beta: Tensor, b_beta: Tensor, c_in: int, slope: float = 1.0) -> ConvOp:
     """SFT.mlp_gamma / mlp_beta (stem_utils.py:33-34) as ONE conv whose epilogue applies x*(1+gamma)+beta
     (:41): output rows are interleaved per 64 channels as [gamma(64) | beta(64)], and the "+1" goes into the
@@ -452,9 +488,15 @@ class TransformsEngine:
             beta, gamma = _gdn_fold(g(f"{name}.beta"), g(f"{name}.gamma"))
             return (beta, gamma, inverse)
 
-        self.ga_conv = [ConvOp(w0, g("g_a.0.bias"), c_in=[8], c_out=N, k=5, stride=2, row_taps=True,
-                               gdn=gdn_of("g_a.1", False),
-                               alg_flops_per_out_pixel=2.0 * 75 * N + 2.0 * N * N)]
+        # STEMB200_FIRST=rowtaps selects the round-1 kernel (NHWC8 canvas, weights streamed per tile) for A/B
+        self.first_resident = os.environ.get("STEMB200_FIRST", "resident") != "rowtaps"
+        if self.first_resident:
+            beta0, gamma0, _ = gdn_of("g_a.1", False)
+            self.ga_conv = [FirstLayerOp(g("g_a.0.weight"), g("g_a.0.bias"), beta0, gamma0)]
+        else:
+            self.ga_conv = [ConvOp(w0, g("g_a.0.bias"), c_in=[8], c_out=N, k=5, stride=2, row_taps=True,
+                                   gdn=gdn_of("g_a.1", False),
+                                   alg_flops_per_out_pixel=2.0 * 75 * N + 2.0 * N * N)]
         for i in (2, 4):
             self.ga_conv.append(ConvOp(g(f"g_a.{i}.weight"), g(f"g_a.{i}.bias"), c_in=[N], c_out=N, k=5, stride=2,
                                        gdn=gdn_of(f"g_a.{i + 1}", False)))
@@ -525,8 +567,12 @@ class TransformsEngine:
         if Hp % 2 or Wp % 2:
             raise ValueError("analysis needs an even padded frame size")
         border = 2
-        canvas = ws.get("ga_canvas", (B * (Hp + 2 * border) * (Wp + 2 * border) * 8 + 64,), torch.float16)
-        stage = lib.stemb200_frame_u8_to_nhwc8 if x.dtype == torch.uint8 else lib.stemb200_frame_to_nhwc8
+        cp = 4 if self.first_resident else 8   # channels per canvas pixel
+        canvas = ws.get("ga_canvas", (B * (Hp + 2 * border) * (Wp + 2 * border) * cp + 64,), torch.float16)
+        if self.first_resident:
+            stage = lib.stemb200_frame_u8_to_nhwc4 if x.dtype == torch.uint8 else lib.stemb200_frame_to_nhwc4
+        else:
+            stage = lib.stemb200_frame_u8_to_nhwc8 if x.dtype == torch.uint8 else lib.stemb200_frame_to_nhwc8
         _lib.check(stage(x.data_ptr(), canvas.data_ptr(), B, 3, H, W, Hp, Wp, top, left, border, _stream()),
                    "frame_to_nhwc8")
         cur, h, w = canvas, Hp, Wp

@@ -277,6 +277,46 @@ def test_fused_conv_gdn_vs_oracle(dev, case):
     assert float((got - ref).abs().max()) < 6e-3 * max(1.0, float(ref.abs().max()))
 
 
+@pytest.mark.parametrize("geom", [(2, 40, 72), (1, 34, 60), (3, 272, 480), (1, 128, 130)],
+                         ids=["small", "ragged", "many_tiles", "odd_half"])
+def test_first_layer_resident_kernel_vs_oracle(dev, geom, monkeypatch):
+    """g_a.0 + GDN with resident weights (csrc/conv_first.cu: NHWC4 canvas, 64-byte-swizzled K = 160 operands, W0 and
+    gamma loaded once per CTA) against F.conv2d + the oracle's GDN (priors.py:422-423, gdn.py:52-67), and against the
+    row_taps kernel it replaces (same fp16 operands, another K order: equal to fp32 summation noise)."""
+    from spatiotemporalentropymodel_b200 import _lib
+    from spatiotemporalentropymodel_b200.engine import ConvOp, FirstLayerOp, _gdn_fold, SQ_SCALE, nhwc_f16_to_nchw
+    B, H, W = geom
+    g = torch.Generator().manual_seed(31)
+    x = torch.rand((B, 3, H, W), generator=g)
+    wt = 3.0 * (torch.rand((192, 3, 5, 5), generator=g) * 2 - 1) * math.sqrt(3.0 / 75)
+    bias = 0.1 * torch.randn(192, generator=g)
+    ped = torch.tensor([2.0 ** -36])
+    beta_p = torch.sqrt(torch.max(1.0 + 0.5 * torch.rand(192, generator=g) + ped, ped))
+    gamma_p = torch.sqrt(torch.max(0.1 * torch.eye(192) + 0.02 * torch.rand((192, 192), generator=g) + ped, ped))
+    ref = O.gdn(F.conv2d(x.half().float(), wt.half().float(), bias, stride=2, padding=2), beta_p, gamma_p, False)
+    beta, gamma = _gdn_fold(beta_p.to(dev), gamma_p.to(dev))
+    lib = _lib.load()
+    st = torch.cuda.current_stream().cuda_stream
+    ho, wo = H // 2, W // 2
+    outs = {}
+    for cp in (4, 8):
+        canvas = torch.full((B * (H + 4) * (W + 4) * cp + 64,), float("nan"), dtype=torch.float16, device=dev)
+        stage = lib.stemb200_frame_to_nhwc4 if cp == 4 else lib.stemb200_frame_to_nhwc8
+        _lib.check(stage(x.to(dev).data_ptr(), canvas.data_ptr(), B, 3, H, W, H, W, 0, 0, 2, st), "canvas")
+        canvas[-64:] = 0
+        if cp == 4:
+            op = FirstLayerOp(wt.to(dev), bias.to(dev), beta, gamma)
+        else:
+            w8 = F.pad(wt, (0, 0, 0, 0, 0, 5)).contiguous().to(dev)
+            op = ConvOp(w8, bias.to(dev), c_in=[8], c_out=192, k=5, stride=2, row_taps=True, gdn=(beta, gamma, False))
+        out = op([canvas], B, H, W, torch.full((B, ho, wo, 192), float("nan"), dtype=torch.float16, device=dev))
+        outs[cp] = nhwc_f16_to_nchw(out, torch.empty((B, 192, ho, wo), device=dev)).cpu()
+        assert torch.isfinite(outs[cp]).all(), cp
+    assert rel_rms(outs[4], ref) < 1.5e-3, rel_rms(outs[4], ref)
+    assert float((outs[4] - ref).abs().max()) < 6e-3 * max(1.0, float(ref.abs().max()))
+    assert rel_rms(outs[4], outs[8]) < 6e-4          # both round their result to fp16
+
+
 # ------------------------------------------------------------------------------------------- STEM forward
 CAL_TAG = {"default": "", "lowrate": "lowrate_"}
 
