@@ -42,14 +42,15 @@ constexpr int kGChunks = kN / 64;              // 3
 constexpr int kGChunkBytes = kN * 128;         // 24 KB: gamma chunk (128-byte swizzle)
 constexpr int kAStage = 128 * kKRow * 2;       // 8 KB: A tile of one kernel row
 constexpr int kStageBytes = kAStage + kWRowBytes;  // 20 KB: A tile + the W0 slice of that kernel row
-constexpr int kStages = 2;
-constexpr int kA2Chunk = 128 * 128;            // 16 KB: (x s)^2 chunk / output staging chunk
-constexpr int kA2Bytes = kGChunks * kA2Chunk;  // 48 KB per epilogue group
+constexpr int kStages = 4;
+constexpr int kOutChunk = 128 * 128;           // 16 KB: output staging of one 64-channel chunk
+constexpr int kOutBytes = 2 * kOutChunk;       // two staging chunks per epilogue group
+constexpr uint32_t kSqCol = 2 * kN;            // (x s)^2 operand: 96 packed columns after the two accumulators
 constexpr int kEpiWarps = 16;
 constexpr int kEpiThreads = kEpiWarps * 32;
 constexpr int kGroupThreads = kEpiThreads / 2;
 constexpr int kThreads = 128 + kEpiThreads;
-constexpr int kSmem = 1024 + kGChunks * kGChunkBytes + kStages * kStageBytes + 2 * kA2Bytes + 256 + 2 * kN * 4;
+constexpr int kSmem = 1024 + kGChunks * kGChunkBytes + kStages * kStageBytes + 2 * kOutBytes + 256 + 2 * kN * 4;
 static_assert(kSmem <= 232448, "shared memory budget");
 
 struct FirstParams {
@@ -90,8 +91,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_first_gdn_kernel(const __gri
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t g_base = smem_base;
   const uint32_t stage_base = g_base + kGChunks * kGChunkBytes;
-  const uint32_t a2_base0 = stage_base + kStages * kStageBytes;
-  const uint32_t bar_base = a2_base0 + 2 * kA2Bytes;
+  const uint32_t out_base0 = stage_base + kStages * kStageBytes;
+  const uint32_t bar_base = out_base0 + 2 * kOutBytes;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (kStages + s); };
   auto tfull_bar = [&](int g) { return bar_base + 8u * (2 * kStages + g); };
@@ -210,21 +211,20 @@ __global__ void __launch_bounds__(kThreads, 1) conv_first_gdn_kernel(const __gri
         ph ^= 1u;
       }
     };
-    // norm(j) = gamma . (x s)^2 over the accumulator of tile j, operand in group (j & 1)'s buffer, gamma resident
+    // norm(j) = gamma . (x s)^2 over the accumulator of tile j: A from tensor memory, gamma resident in shared memory
     auto mma_gamma = [&](int j) {
       const int g = j & 1;
       mbar_wait(a2rdy_bar(g), (j >> 1) & 1);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + g * kN;
-      const uint32_t a2 = a2_base0 + g * kA2Bytes;
       if (leader) {
 #pragma unroll
         for (int kc = 0; kc < kGChunks; ++kc) {
-          const uint64_t adesc = umma_desc_sw128(a2 + kc * kA2Chunk);
           const uint64_t bdesc = umma_desc_sw128(g_base + kc * kGChunkBytes);
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk)
-            mma_f16_ss(d_tmem, adesc + 2u * kk, bdesc + 2u * kk, idesc, (kc > 0 || kk > 0) ? 1u : 0u);
+            mma_f16_ts(d_tmem, tmem_base + kSqCol + 32u * kc + 8u * kk, bdesc + 2u * kk, idesc,
+                       (kc > 0 || kk > 0) ? 1u : 0u);
         }
         mma_commit(nfull_bar(g));
       }
@@ -256,27 +256,25 @@ __global__ void __launch_bounds__(kThreads, 1) conv_first_gdn_kernel(const __gri
     const uint32_t lane_off = static_cast<uint32_t>((wg & 3) * 32) << 16;
     const uint32_t rsw = static_cast<uint32_t>(row & 7);
     const uint32_t row_off = static_cast<uint32_t>(row) * 128u;
-    const uint32_t a2_base = a2_base0 + G * kA2Bytes;
+    const uint32_t out_base = out_base0 + G * kOutBytes;
     const uint32_t acc_col = tmem_base + lane_off + G * kN + 32 * half;
+    const uint32_t sq_col = tmem_base + lane_off + kSqCol + 16 * half;
     const uint32_t bar_id = 1 + G;
     const float sc = p.sq_scale;  // power of two: fma(acc, s, b s) rounds exactly like (acc + b) s
     int n = 0;
+    uint32_t buf = 0;  // staging chunk of the next store
     for (int tile = first + G * stride; tile < p.total_tiles; tile += 2 * stride, ++n) {
       int n_img, h0, w0;
       decode(tile, n_img, h0, w0);
       const uint32_t par = n & 1;
       uint32_t hx[kGChunks * 16];  // x s of this thread's 32 columns per chunk, packed fp16
+      // tfull of this tile is committed after the gamma MMAs of the previous tile (other group): the shared (x s)^2
+      // operand in tensor memory has been consumed when the wait returns
       mbar_wait(tfull_bar(G), par);
       tc_fence_after();
-      // ---- phase 1: x s -> registers, (x s)^2 -> this group's smem operand (its previous tile's stores must be out)
+      // ---- phase 1: x s -> registers, (x s)^2 -> tensor memory (A operand of the gamma MMAs)
 #pragma unroll
       for (int g = 0; g < kGChunks; ++g) {
-        if (gtid == 0) {
-          if (g == 0) tma_store_wait_read<kGChunks - 1>();
-          else if (g + 1 < kGChunks) tma_store_wait_read<1>();
-          else tma_store_wait_read<0>();
-        }
-        named_bar_sync(bar_id, kGroupThreads);
 #pragma unroll
         for (int sub = 0; sub < 2; ++sub) {
           const int c = 64 * g + 32 * half + 16 * sub;
@@ -300,26 +298,20 @@ __global__ void __launch_bounds__(kThreads, 1) conv_first_gdn_kernel(const __gri
             hq[2 * j] = *reinterpret_cast<const uint32_t*>(&q0);
             hq[2 * j + 1] = *reinterpret_cast<const uint32_t*>(&q1);
           }
-          const uint32_t cbase = a2_base + static_cast<uint32_t>(g) * kA2Chunk + row_off;
-          const uint32_t pa = ((4u * half + 2u * sub) ^ rsw) << 4, pb = ((4u * half + 2u * sub + 1u) ^ rsw) << 4;
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(cbase + pa), "r"(hq[0]), "r"(hq[1]), "r"(hq[2]),
-                       "r"(hq[3])
-                       : "memory");
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(cbase + pb), "r"(hq[4]), "r"(hq[5]), "r"(hq[6]),
-                       "r"(hq[7])
-                       : "memory");
+          tmem_st_32x8(sq_col + 32 * g + 8 * sub, hq);
         }
       }
-      fence_proxy_async_smem();  // (x s)^2 is read by the tensor core through the async proxy
+      tmem_st_wait();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(a2rdy_bar(G));
 
-      // ---- phase 2: out = (x s) * rsqrt(s^2 beta + acc) into the group's (now free) x^2 buffers, one TMA store per chunk
+      // ---- phase 2: out = (x s) * rsqrt(s^2 beta + acc) through two alternating staging chunks, one TMA store each
       mbar_wait(nfull_bar(G), par);
       tc_fence_after();
 #pragma unroll
       for (int g = 0; g < kGChunks; ++g) {
+        uint32_t ho[16];
 #pragma unroll
         for (int sub = 0; sub < 2; ++sub) {
           const int c = 64 * g + 32 * half + 16 * sub;
@@ -332,7 +324,6 @@ __global__ void __launch_bounds__(kThreads, 1) conv_first_gdn_kernel(const __gri
             __syncwarp();
             if (lane == 0) mbar_arrive(accfree_bar(G));
           }
-          uint32_t ho[8];
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             float b0, b1, b2, b3;
@@ -345,24 +336,31 @@ __global__ void __launch_bounds__(kThreads, 1) conv_first_gdn_kernel(const __gri
             const float f3 = rsqrt_approx(__uint_as_float(r[4 * j + 3]) + b3);
             const float2 x0 = __half22float2(*reinterpret_cast<const __half2*>(&hx[g * 16 + sub * 8 + 2 * j]));
             const float2 x1 = __half22float2(*reinterpret_cast<const __half2*>(&hx[g * 16 + sub * 8 + 2 * j + 1]));
-            ho[2 * j] = pack2(x0.x * f0, x0.y * f1);
-            ho[2 * j + 1] = pack2(x1.x * f2, x1.y * f3);
+            ho[sub * 8 + 2 * j] = pack2(x0.x * f0, x0.y * f1);
+            ho[sub * 8 + 2 * j + 1] = pack2(x1.x * f2, x1.y * f3);
           }
-          const uint32_t cbase = a2_base + static_cast<uint32_t>(g) * kA2Chunk + row_off;
+        }
+        // the store that last read this staging chunk (two stores ago) must have finished reading
+        if (gtid == 0) tma_store_wait_read<1>();
+        named_bar_sync(bar_id, kGroupThreads);
+        const uint32_t cbase = out_base + buf * kOutChunk + row_off;
+#pragma unroll
+        for (int sub = 0; sub < 2; ++sub) {
           const uint32_t pa = ((4u * half + 2u * sub) ^ rsw) << 4, pb = ((4u * half + 2u * sub + 1u) ^ rsw) << 4;
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(cbase + pa), "r"(ho[0]), "r"(ho[1]), "r"(ho[2]),
-                       "r"(ho[3])
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(cbase + pa), "r"(ho[sub * 8]),
+                       "r"(ho[sub * 8 + 1]), "r"(ho[sub * 8 + 2]), "r"(ho[sub * 8 + 3])
                        : "memory");
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(cbase + pb), "r"(ho[4]), "r"(ho[5]), "r"(ho[6]),
-                       "r"(ho[7])
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(cbase + pb), "r"(ho[sub * 8 + 4]),
+                       "r"(ho[sub * 8 + 5]), "r"(ho[sub * 8 + 6]), "r"(ho[sub * 8 + 7])
                        : "memory");
         }
         fence_proxy_async_smem();
         named_bar_sync(bar_id, kGroupThreads);
         if (gtid == 0) {
-          tma_store_4d(&p.out_map, a2_base + static_cast<uint32_t>(g) * kA2Chunk, 64 * g, w0, h0, n_img);
+          tma_store_4d(&p.out_map, out_base + buf * kOutChunk, 64 * g, w0, h0, n_img);
           tma_store_commit();
         }
+        buf ^= 1u;
       }
     }
     if (gtid == 0) tma_store_wait_all<0>();
