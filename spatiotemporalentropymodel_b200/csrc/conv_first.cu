@@ -1,23 +1,32 @@
-// First analysis layer of g_a fused with its GDN (sm_100a): compact operands, resident gamma, ping-pong epilogue.
+// First analysis layer of g_a fused with its GDN (sm_100a).
 //
 //   x   = conv(frame, W0; 3 -> 192 channels, k5, s2, p2) + bias      priors.py:422 (conv(3, N)), models/utils.py:112-119
 //   out = x * rsqrt(beta + gamma . x^2)                              layers/gdn.py:52-67
 //
-// Why a kernel of its own: with 15 real input values per kernel row the layer is bound by shared-memory bandwidth and by
-// its epilogue chain, not by the tensor pipe.  conv_gdn_pp_kernel (conv_igemm.cu) moves ~690 KB per 128-pixel tile
-// through shared memory - 192 KB of it W0 and gamma re-streamed by TMA for every tile, 150 KB operand reads of a
-// K = 240 contraction for 75 real taps x channels - against 2 600 tensor cycles: 5 800 cycles per tile, 0.42 of the
-// sustained tensor peak (profiles/r02_ncu_full_conv_gdn.txt).  Here
+// Why a kernel of its own: with 15 real input values per kernel row the layer is not bound by the tensor pipe
+// (2 100 cycles per 128-pixel tile) but by what surrounds it.  conv_gdn_pp_kernel (conv_igemm.cu) moves ~690 KB per
+// tile through shared memory - W0 and gamma re-streamed by TMA for every tile, a K = 240 contraction for 75 real
+// taps x channels, (x s)^2 written to and read back from shared memory - and runs at 5 800 cycles per tile
+// (profiles/r02_ncu_full_conv_gdn.txt).  Here
 //   * the frame canvas has 4 channels per pixel (R, G, B, 0), so one kernel row of an output pixel is 5 taps x 4 = 20
 //     contiguous fp16 inside a 32-element (64-byte) TMA box: K = 5 x 32 = 160 issued (10 MMAs instead of 15), 64-byte
 //     swizzled operand tiles of 8 KB (A) and 12 KB (W0 row) instead of 16 and 24 KB;
-//   * gamma (3 x 24 KB, 128-byte swizzle) is loaded ONCE per CTA and stays in shared memory;
-//   * the 16 epilogue warps form two groups on alternating tiles, each with its own accumulator and (x s)^2 / staging
-//     buffer and x s kept in registers between its two phases (the ping-pong of conv_gdn_pp_kernel): a first version
-//     of this kernel with one group and everything resident was no longer shared-memory-bound (62 % of the pipe) but
-//     ran at the same 6 100 cycles per tile - the chain phase 1 -> gamma MMA -> phase 2 behind a 5-step main loop.
-// ~460 KB per tile.  Persistent, one CTA per SM, 640 threads: warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM
-// allocator, warps 4-19 = epilogue.
+//   * W0 (5 x 12 KB) and gamma (3 x 24 KB, 128-byte swizzle) are loaded ONCE per CTA and stay in shared memory; only
+//     the 8 KB A tiles stream through a 5-stage TMA ring;
+//   * (x s)^2, the A operand of the gamma MMAs, is written to TENSOR memory (tcgen05.st) and read from there by
+//     tcgen05.mma [a_tmem]: no shared-memory round trip for it;
+//   * tensor memory holds one conv accumulator (192 columns), one norm accumulator (192) and the (x s)^2 operand (96
+//     packed columns).  The MMA warp issues conv(t+1), then gamma(t) as three 64-channel column chunks, each as soon
+//     as the epilogue has read that chunk of norm(t-1).  All 16 epilogue warps work on one tile per phase:
+//       1a  conv accumulator -> x s in registers                              -> accumulator free for conv(t+1)
+//       1b  (x s)^2 -> tensor memory, once gamma(t-1) has consumed the operand -> gamma(t) may issue
+//       2a  norm accumulator of tile t-1 -> out = x s * rsqrt(.) in place in registers, chunk by chunk
+//       2b  registers -> three 16 KB staging chunks; a dedicated warp issues the TMA stores and publishes when they
+//           have read the staging, so no epilogue warp ever waits for another one outside the mbarriers.
+// ~270 KB of shared-memory traffic per tile.  The floor of this layer is the HBM write of its output: 2.15 GB for 11
+// 1080p frames at the 3.9 TB/s a pure-write kernel reaches on this B200 = 0.55 ms.
+// Persistent, one CTA per SM, 640 threads: warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM allocator,
+// warp 3 = TMA store issuer, warps 4-19 = epilogue.
 #include <cuda.h>
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
@@ -41,16 +50,15 @@ constexpr int kWRowBytes = kN * kKRow * 2;     // 12 KB: W0 slice of one kernel 
 constexpr int kGChunks = kN / 64;              // 3
 constexpr int kGChunkBytes = kN * 128;         // 24 KB: gamma chunk (128-byte swizzle)
 constexpr int kAStage = 128 * kKRow * 2;       // 8 KB: A tile of one kernel row
-constexpr int kStageBytes = kAStage + kWRowBytes;  // 20 KB: A tile + the W0 slice of that kernel row
-constexpr int kStages = 4;
+constexpr int kStages = 5;                     // A ring
 constexpr int kOutChunk = 128 * 128;           // 16 KB: output staging of one 64-channel chunk
-constexpr int kOutBytes = 2 * kOutChunk;       // two staging chunks per epilogue group
+constexpr uint32_t kNormCol = kN;              // norm accumulator after the conv accumulator
 constexpr uint32_t kSqCol = 2 * kN;            // (x s)^2 operand: 96 packed columns after the two accumulators
 constexpr int kEpiWarps = 16;
 constexpr int kEpiThreads = kEpiWarps * 32;
-constexpr int kGroupThreads = kEpiThreads / 2;
 constexpr int kThreads = 128 + kEpiThreads;
-constexpr int kSmem = 1024 + kGChunks * kGChunkBytes + kStages * kStageBytes + 2 * kOutBytes + 256 + 2 * kN * 4;
+constexpr int kSmem = 1024 + kGChunks * kGChunkBytes + kRows * kWRowBytes + kStages * kAStage + kGChunks * kOutChunk +
+                      256 + 2 * kN * 4;
 static_assert(kSmem <= 232448, "shared memory budget");
 
 struct FirstParams {
@@ -90,17 +98,22 @@ __global__ void __launch_bounds__(kThreads, 1) conv_first_gdn_kernel(const __gri
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t g_base = smem_base;
-  const uint32_t stage_base = g_base + kGChunks * kGChunkBytes;
-  const uint32_t out_base0 = stage_base + kStages * kStageBytes;
-  const uint32_t bar_base = out_base0 + 2 * kOutBytes;
+  const uint32_t w_base = g_base + kGChunks * kGChunkBytes;
+  const uint32_t stage_base = w_base + kRows * kWRowBytes;
+  const uint32_t out_base = stage_base + kStages * kAStage;
+  const uint32_t bar_base = out_base + kGChunks * kOutChunk;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (kStages + s); };
-  auto tfull_bar = [&](int g) { return bar_base + 8u * (2 * kStages + g); };
-  auto a2rdy_bar = [&](int g) { return bar_base + 8u * (2 * kStages + 2 + g); };
-  auto nfull_bar = [&](int g) { return bar_base + 8u * (2 * kStages + 4 + g); };
-  auto accfree_bar = [&](int g) { return bar_base + 8u * (2 * kStages + 6 + g); };
-  const uint32_t wfull_bar = bar_base + 8u * (2 * kStages + 8);
-  const uint32_t tmem_slot = bar_base + 8u * (2 * kStages + 9);
+  const uint32_t tfull_bar = bar_base + 8u * (2 * kStages);         // conv accumulator complete
+  const uint32_t convfree_bar = bar_base + 8u * (2 * kStages + 1);  // phase 1a has read it
+  const uint32_t sqrdy_bar = bar_base + 8u * (2 * kStages + 2);     // (x s)^2 is in tensor memory
+  const uint32_t staged_bar = bar_base + 8u * (2 * kStages + 3);    // the output tile is in the staging chunks
+  const uint32_t stfree_bar = bar_base + 8u * (2 * kStages + 4);    // the TMA stores have read the staging chunks
+  const uint32_t wfull_bar = bar_base + 8u * (2 * kStages + 5);
+  const uint32_t tmem_slot = bar_base + 8u * (2 * kStages + 6);
+  // per 64-channel chunk of the norm accumulator: gamma MMAs complete / phase 2a has read it
+  auto nfull_bar = [&](int g) { return bar_base + 8u * (2 * kStages + 7 + g); };
+  auto normfree_bar = [&](int g) { return bar_base + 8u * (2 * kStages + 10 + g); };
   const uint32_t bias_smem = bar_base + 256u;
   const uint32_t beta_smem = bias_smem + 4u * kN;
 
@@ -120,13 +133,16 @@ __global__ void __launch_bounds__(kThreads, 1) conv_first_gdn_kernel(const __gri
       mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), 1);
     }
-    for (int g = 0; g < 2; ++g) {
-      mbar_init(tfull_bar(g), 1);
-      mbar_init(a2rdy_bar(g), kEpiWarps / 2);
-      mbar_init(nfull_bar(g), 1);
-      mbar_init(accfree_bar(g), kEpiWarps / 2);
-    }
+    mbar_init(tfull_bar, 1);
+    mbar_init(convfree_bar, kEpiWarps);
+    mbar_init(sqrdy_bar, kEpiWarps);
+    mbar_init(staged_bar, kEpiWarps);
+    mbar_init(stfree_bar, 1);
     mbar_init(wfull_bar, 1);
+    for (int g = 0; g < kGChunks; ++g) {
+      mbar_init(nfull_bar(g), 1);
+      mbar_init(normfree_bar(g), kEpiWarps);
+    }
     fence_barrier_init();
   }
   if (warp == 2) {
@@ -147,6 +163,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_first_gdn_kernel(const __gri
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
   tmem_base = __shfl_sync(0xffffffffu, tmem_base, 0);
+  // the four service warps hand registers to the sixteen epilogue warps (640 x 96 allocated: 128 x 40 + 512 x 104)
 
   const uint32_t a_tx_bytes = static_cast<uint32_t>(p.tile_h * p.tile_w) * (kKRow * 2);
   auto decode = [&](int tile, int& n_img, int& h0, int& w0) {
@@ -159,12 +176,15 @@ __global__ void __launch_bounds__(kThreads, 1) conv_first_gdn_kernel(const __gri
     w0 = twi * p.tile_w;
   };
 
+  if (warp < 4) {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
   if (warp == 0) {
-    // ============ TMA producer: gamma once, then per kernel row one A tile + the W0 slice of that row ============
+    // ============ TMA producer: gamma and W0 once, then one A tile per kernel row ============
     const bool leader = elect_one();
     if (leader) {
-      mbar_arrive_expect_tx(wfull_bar, kGChunks * kGChunkBytes);
+      mbar_arrive_expect_tx(wfull_bar, kGChunks * kGChunkBytes + kRows * kWRowBytes);
       for (int kc = 0; kc < kGChunks; ++kc) tma_load_2d(g_base + kc * kGChunkBytes, &p.g_map, wfull_bar, kc * 64, 0);
+      for (int r = 0; r < kRows; ++r) tma_load_2d(w_base + r * kWRowBytes, &p.w_map, wfull_bar, r * kKRow, 0);
     }
     int s = 0;
     uint32_t ph = 0;
@@ -174,11 +194,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_first_gdn_kernel(const __gri
       for (int r = 0; r < kRows; ++r) {
         mbar_wait(empty_bar(s), ph ^ 1u);
         if (leader) {
-          const uint32_t dst = stage_base + s * kStageBytes;
-          mbar_arrive_expect_tx(full_bar(s), a_tx_bytes + kWRowBytes);
+          mbar_arrive_expect_tx(full_bar(s), a_tx_bytes);
           // canvas row 2 (h0 + i) + r has parity r & 1 and index h0 + i + (r >> 1) among the rows of that parity
-          tma_load_4d(dst, &p.a_map[r & 1], full_bar(s), 0, w0, h0 + (r >> 1), n_img);
-          tma_load_2d(dst + kAStage, &p.w_map, full_bar(s), r * kKRow, 0);
+          tma_load_4d(stage_base + s * kAStage, &p.a_map[r & 1], full_bar(s), 0, w0, h0 + (r >> 1), n_img);
         }
         if (++s == kStages) {
           s = 0;
@@ -190,20 +208,20 @@ __global__ void __launch_bounds__(kThreads, 1) conv_first_gdn_kernel(const __gri
     // ===================== MMA issuer =====================
     const bool leader = elect_one();
     constexpr uint32_t idesc = umma_idesc(/*F16*/ 0u, 128u, kN);
+    constexpr uint32_t idesc64 = umma_idesc(/*F16*/ 0u, 128u, 64u);
     mbar_wait(wfull_bar, 0);
     tc_fence_after();
     int s = 0;
     uint32_t ph = 0;
-    auto mma_row = [&](uint32_t d_tmem, int r) {
+    auto mma_row = [&](int r) {
       mbar_wait(full_bar(s), ph);
       tc_fence_after();
-      const uint32_t a_addr = stage_base + s * kStageBytes;
-      const uint64_t adesc = umma_desc_sw64(a_addr);
-      const uint64_t bdesc = umma_desc_sw64(a_addr + kAStage);
+      const uint64_t adesc = umma_desc_sw64(stage_base + s * kAStage);
+      const uint64_t bdesc = umma_desc_sw64(w_base + r * kWRowBytes);
       if (leader) {
 #pragma unroll
         for (int kk = 0; kk < kKRow / 16; ++kk)
-          mma_f16_ss(d_tmem, adesc + 2u * kk, bdesc + 2u * kk, idesc, (r > 0 || kk > 0) ? 1u : 0u);
+          mma_f16_ss(tmem_base, adesc + 2u * kk, bdesc + 2u * kk, idesc, (r > 0 || kk > 0) ? 1u : 0u);
         mma_commit(empty_bar(s));
       }
       if (++s == kStages) {
@@ -211,159 +229,175 @@ __global__ void __launch_bounds__(kThreads, 1) conv_first_gdn_kernel(const __gri
         ph ^= 1u;
       }
     };
-    // norm(j) = gamma . (x s)^2 over the accumulator of tile j: A from tensor memory, gamma resident in shared memory
+    // norm(j) = gamma . (x s)^2 of tile j: A from tensor memory, gamma resident in shared memory.  One set of MMAs per
+    // 64-channel chunk of the norm accumulator, so a chunk is rewritten as soon as phase 2a of tile j-1 has read it.
     auto mma_gamma = [&](int j) {
-      const int g = j & 1;
-      mbar_wait(a2rdy_bar(g), (j >> 1) & 1);
-      tc_fence_after();
-      const uint32_t d_tmem = tmem_base + g * kN;
-      if (leader) {
+      mbar_wait(sqrdy_bar, j & 1);
 #pragma unroll
-        for (int kc = 0; kc < kGChunks; ++kc) {
-          const uint64_t bdesc = umma_desc_sw128(g_base + kc * kGChunkBytes);
+      for (int g = 0; g < kGChunks; ++g) {
+        if (j >= 1) mbar_wait(normfree_bar(g), (j - 1) & 1);
+        tc_fence_after();
+        if (leader) {
 #pragma unroll
-          for (int kk = 0; kk < 4; ++kk)
-            mma_f16_ts(d_tmem, tmem_base + kSqCol + 32u * kc + 8u * kk, bdesc + 2u * kk, idesc,
-                       (kc > 0 || kk > 0) ? 1u : 0u);
+          for (int kc = 0; kc < kGChunks; ++kc) {
+            const uint64_t bdesc = umma_desc_sw128(g_base + kc * kGChunkBytes + g * (64 * 128));
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk)
+              mma_f16_ts(tmem_base + kNormCol + 64u * g, tmem_base + kSqCol + 32u * kc + 8u * kk, bdesc + 2u * kk,
+                         idesc64, (kc > 0 || kk > 0) ? 1u : 0u);
+          }
+          mma_commit(nfull_bar(g));
         }
-        mma_commit(nfull_bar(g));
       }
     };
     int it = 0;
     for (int tile = first; tile < p.total_tiles; tile += stride, ++it) {
-      const int g = it & 1;
-      const uint32_t d_tmem = tmem_base + g * kN;
-      if (it >= 2) {  // phase 2 of tile it-2 (same group) has finished reading this accumulator
-        mbar_wait(accfree_bar(g), ((it >> 1) - 1) & 1);
+      if (it >= 1) {  // phase 1a of tile it-1 has moved the conv accumulator into registers
+        mbar_wait(convfree_bar, (it - 1) & 1);
         tc_fence_after();
       }
-      mma_row(d_tmem, 0);
-      mma_row(d_tmem, 1);
-      if (it > 0) mma_gamma(it - 1);
-      mma_row(d_tmem, 2);
-      mma_row(d_tmem, 3);
-      mma_row(d_tmem, 4);
-      if (leader) mma_commit(tfull_bar(g));
+      for (int r = 0; r < kRows; ++r) mma_row(r);
+      if (leader) mma_commit(tfull_bar);
+      if (it >= 1) mma_gamma(it - 1);
     }
     if (it > 0) mma_gamma(it - 1);
-  } else if (warp >= 4) {
-    // ===================== epilogue: two groups of 8 warps on alternating tiles =====================
-    const int G = (warp - 4) >> 3;           // group = parity of the tiles it owns
-    const int wg = (warp - 4) & 7;           // warp inside the group
-    const int gtid = wg * 32 + lane;         // 0..255
-    const int row = (wg & 3) * 32 + lane;    // accumulator row == pixel of the patch (TMEM lane group = warp % 4)
-    const int half = wg >> 2;                // 32-column half of every 64-channel chunk
-    const uint32_t lane_off = static_cast<uint32_t>((wg & 3) * 32) << 16;
+  } else if (warp == 3) {
+    // ===================== TMA store issuer =====================
+    if (lane == 0) {
+      int n = 0;
+      for (int tile = first; tile < p.total_tiles; tile += stride, ++n) {
+        int n_img, h0, w0;
+        decode(tile, n_img, h0, w0);
+        mbar_wait(staged_bar, n & 1);  // every epilogue warp has written and fenced its part of the tile
+#pragma unroll
+        for (int g = 0; g < kGChunks; ++g)
+          tma_store_4d(&p.out_map, out_base + static_cast<uint32_t>(g) * kOutChunk, 64 * g, w0, h0, n_img);
+        tma_store_commit();
+        tma_store_wait_read<0>();
+        mbar_arrive(stfree_bar);
+      }
+      tma_store_wait_all<0>();
+    }
+  }
+  } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
+    // ===================== epilogue: 16 warps, one tile per phase =====================
+    const int lq = (warp - 4) & 3;           // TMEM lane quarter of this warp (= warp % 4)
+    const int q = (warp - 4) >> 2;           // 16-column block of every 64-channel chunk
+    const int row = lq * 32 + lane;          // accumulator row == pixel of the patch
+    const uint32_t lane_off = static_cast<uint32_t>(lq * 32) << 16;
     const uint32_t rsw = static_cast<uint32_t>(row & 7);
-    const uint32_t row_off = static_cast<uint32_t>(row) * 128u;
-    const uint32_t out_base = out_base0 + G * kOutBytes;
-    const uint32_t acc_col = tmem_base + lane_off + G * kN + 32 * half;
-    const uint32_t sq_col = tmem_base + lane_off + kSqCol + 16 * half;
-    const uint32_t bar_id = 1 + G;
+    const uint32_t stage_row = out_base + static_cast<uint32_t>(row) * 128u;
+    const uint32_t pa = ((2u * q) ^ rsw) << 4, pb = ((2u * q + 1u) ^ rsw) << 4;
+    const uint32_t conv_col = tmem_base + lane_off + 16 * q;
+    const uint32_t norm_col = tmem_base + lane_off + kNormCol + 16 * q;
+    const uint32_t sq_col = tmem_base + lane_off + kSqCol + 8 * q;
     const float sc = p.sq_scale;  // power of two: fma(acc, s, b s) rounds exactly like (acc + b) s
+    uint32_t hx_prev[kGChunks * 8];  // x s of tile n-1 (then its output), 16 columns per chunk, packed fp16
     int n = 0;
-    uint32_t buf = 0;  // staging chunk of the next store
-    for (int tile = first + G * stride; tile < p.total_tiles; tile += 2 * stride, ++n) {
-      int n_img, h0, w0;
-      decode(tile, n_img, h0, w0);
-      const uint32_t par = n & 1;
-      uint32_t hx[kGChunks * 16];  // x s of this thread's 32 columns per chunk, packed fp16
-      // tfull of this tile is committed after the gamma MMAs of the previous tile (other group): the shared (x s)^2
-      // operand in tensor memory has been consumed when the wait returns
-      mbar_wait(tfull_bar(G), par);
-      tc_fence_after();
-      // ---- phase 1: x s -> registers, (x s)^2 -> tensor memory (A operand of the gamma MMAs)
+    for (int tile = first;; tile += stride, ++n) {
+      const bool have = tile < p.total_tiles;
+      if (!have && n == 0) break;
+      uint32_t hx[kGChunks * 8];
+      if (have) {
+        mbar_wait(tfull_bar, n & 1);
+        tc_fence_after();
+        // ---- phase 1a: x s -> registers (all three loads in flight before the first use)
+        uint32_t r[kGChunks][16];
 #pragma unroll
-      for (int g = 0; g < kGChunks; ++g) {
+        for (int g = 0; g < kGChunks; ++g) tmem_ld_32x16(conv_col + 64 * g, r[g]);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(convfree_bar);
 #pragma unroll
-        for (int sub = 0; sub < 2; ++sub) {
-          const int c = 64 * g + 32 * half + 16 * sub;
-          uint32_t r[16];
-          tmem_ld_32x16(acc_col + 64 * g + 16 * sub, r);
-          tmem_ld_wait();
-          uint32_t hq[8];
+        for (int g = 0; g < kGChunks; ++g) {
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             float b0, b1, b2, b3;
             asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
                          : "=f"(b0), "=f"(b1), "=f"(b2), "=f"(b3)
-                         : "r"(bias_smem + 4u * (c + 4 * j)));
-            const __half2 h0v =
-                __floats2half2_rn(fmaf(__uint_as_float(r[4 * j]), sc, b0), fmaf(__uint_as_float(r[4 * j + 1]), sc, b1));
-            const __half2 h1v = __floats2half2_rn(fmaf(__uint_as_float(r[4 * j + 2]), sc, b2),
-                                                  fmaf(__uint_as_float(r[4 * j + 3]), sc, b3));
-            const __half2 q0 = __hmul2(h0v, h0v), q1 = __hmul2(h1v, h1v);
-            hx[g * 16 + sub * 8 + 2 * j] = *reinterpret_cast<const uint32_t*>(&h0v);
-            hx[g * 16 + sub * 8 + 2 * j + 1] = *reinterpret_cast<const uint32_t*>(&h1v);
-            hq[2 * j] = *reinterpret_cast<const uint32_t*>(&q0);
-            hq[2 * j + 1] = *reinterpret_cast<const uint32_t*>(&q1);
+                         : "r"(bias_smem + 4u * (64 * g + 16 * q + 4 * j)));
+            hx[g * 8 + 2 * j] =
+                pack2(fmaf(__uint_as_float(r[g][4 * j]), sc, b0), fmaf(__uint_as_float(r[g][4 * j + 1]), sc, b1));
+            hx[g * 8 + 2 * j + 1] =
+                pack2(fmaf(__uint_as_float(r[g][4 * j + 2]), sc, b2), fmaf(__uint_as_float(r[g][4 * j + 3]), sc, b3));
           }
-          tmem_st_32x8(sq_col + 32 * g + 8 * sub, hq);
         }
       }
-      tmem_st_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(a2rdy_bar(G));
-
-      // ---- phase 2: out = (x s) * rsqrt(s^2 beta + acc) through two alternating staging chunks, one TMA store each
-      mbar_wait(nfull_bar(G), par);
-      tc_fence_after();
+      if (n >= 1) {
+        // the last gamma MMAs of tile n-1 are complete: they have consumed the (x s)^2 operand
+        mbar_wait(nfull_bar(kGChunks - 1), (n - 1) & 1);
+        tc_fence_after();
+      }
+      if (have) {
+        // ---- phase 1b: (x s)^2 -> tensor memory
 #pragma unroll
-      for (int g = 0; g < kGChunks; ++g) {
-        uint32_t ho[16];
+        for (int g = 0; g < kGChunks; ++g) {
+          uint32_t hq[8];
 #pragma unroll
-        for (int sub = 0; sub < 2; ++sub) {
-          const int c = 64 * g + 32 * half + 16 * sub;
-          uint32_t r[16];
-          tmem_ld_32x16(acc_col + 64 * g + 16 * sub, r);
-          tmem_ld_wait();
-          if (g + 1 == kGChunks && sub == 1) {
-            // every TMEM read of this tile has completed: hand the accumulator back to the MMA warp
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(accfree_bar(G));
+          for (int j = 0; j < 8; ++j) {
+            const __half2 v = *reinterpret_cast<const __half2*>(&hx[g * 8 + j]);
+            const __half2 sq = __hmul2(v, v);
+            hq[j] = *reinterpret_cast<const uint32_t*>(&sq);
           }
+          tmem_st_32x8(sq_col + 32 * g, hq);
+        }
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(sqrdy_bar);
+      }
+      if (n >= 1) {
+        // ---- phase 2a (tile n-1): out = (x s) * rsqrt(s^2 beta + norm), in place
+#pragma unroll
+        for (int g = 0; g < kGChunks; ++g) {
+          uint32_t r[16];
+          if (g + 1 < kGChunks) {  // (the last chunk was waited for before phase 1b)
+            mbar_wait(nfull_bar(g), (n - 1) & 1);
+            tc_fence_after();
+          }
+          tmem_ld_32x16(norm_col + 64 * g, r);
+          tmem_ld_wait();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(normfree_bar(g));
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             float b0, b1, b2, b3;
             asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
                          : "=f"(b0), "=f"(b1), "=f"(b2), "=f"(b3)
-                         : "r"(beta_smem + 4u * (c + 4 * j)));
+                         : "r"(beta_smem + 4u * (64 * g + 16 * q + 4 * j)));
             const float f0 = rsqrt_approx(__uint_as_float(r[4 * j]) + b0);
             const float f1 = rsqrt_approx(__uint_as_float(r[4 * j + 1]) + b1);
             const float f2 = rsqrt_approx(__uint_as_float(r[4 * j + 2]) + b2);
             const float f3 = rsqrt_approx(__uint_as_float(r[4 * j + 3]) + b3);
-            const float2 x0 = __half22float2(*reinterpret_cast<const __half2*>(&hx[g * 16 + sub * 8 + 2 * j]));
-            const float2 x1 = __half22float2(*reinterpret_cast<const __half2*>(&hx[g * 16 + sub * 8 + 2 * j + 1]));
-            ho[sub * 8 + 2 * j] = pack2(x0.x * f0, x0.y * f1);
-            ho[sub * 8 + 2 * j + 1] = pack2(x1.x * f2, x1.y * f3);
+            const float2 x0 = __half22float2(*reinterpret_cast<const __half2*>(&hx_prev[g * 8 + 2 * j]));
+            const float2 x1 = __half22float2(*reinterpret_cast<const __half2*>(&hx_prev[g * 8 + 2 * j + 1]));
+            hx_prev[g * 8 + 2 * j] = pack2(x0.x * f0, x0.y * f1);
+            hx_prev[g * 8 + 2 * j + 1] = pack2(x1.x * f2, x1.y * f3);
           }
         }
-        // the store that last read this staging chunk (two stores ago) must have finished reading
-        if (gtid == 0) tma_store_wait_read<1>();
-        named_bar_sync(bar_id, kGroupThreads);
-        const uint32_t cbase = out_base + buf * kOutChunk + row_off;
+        // ---- phase 2b: registers -> staging, once the stores of tile n-2 have read it; warp 3 issues the stores
+        if (n >= 2) mbar_wait(stfree_bar, n & 1);
 #pragma unroll
-        for (int sub = 0; sub < 2; ++sub) {
-          const uint32_t pa = ((4u * half + 2u * sub) ^ rsw) << 4, pb = ((4u * half + 2u * sub + 1u) ^ rsw) << 4;
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(cbase + pa), "r"(ho[sub * 8]),
-                       "r"(ho[sub * 8 + 1]), "r"(ho[sub * 8 + 2]), "r"(ho[sub * 8 + 3])
+        for (int g = 0; g < kGChunks; ++g) {
+          const uint32_t cbase = stage_row + static_cast<uint32_t>(g) * kOutChunk;
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(cbase + pa), "r"(hx_prev[g * 8]),
+                       "r"(hx_prev[g * 8 + 1]), "r"(hx_prev[g * 8 + 2]), "r"(hx_prev[g * 8 + 3])
                        : "memory");
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(cbase + pb), "r"(ho[sub * 8 + 4]),
-                       "r"(ho[sub * 8 + 5]), "r"(ho[sub * 8 + 6]), "r"(ho[sub * 8 + 7])
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(cbase + pb), "r"(hx_prev[g * 8 + 4]),
+                       "r"(hx_prev[g * 8 + 5]), "r"(hx_prev[g * 8 + 6]), "r"(hx_prev[g * 8 + 7])
                        : "memory");
         }
-        fence_proxy_async_smem();
-        named_bar_sync(bar_id, kGroupThreads);
-        if (gtid == 0) {
-          tma_store_4d(&p.out_map, out_base + buf * kOutChunk, 64 * g, w0, h0, n_img);
-          tma_store_commit();
-        }
-        buf ^= 1u;
+        fence_proxy_async_smem();  // generic-proxy writes -> visible to the TMA store warp 3 issues
+        __syncwarp();
+        if (lane == 0) mbar_arrive(staged_bar);
       }
+      if (!have) break;
+#pragma unroll
+      for (int i = 0; i < kGChunks * 8; ++i) hx_prev[i] = hx[i];
     }
-    if (gtid == 0) tma_store_wait_all<0>();
   }
 
   tc_fence_before();
