@@ -155,18 +155,25 @@ def load_peaks():
     return {"hbm_gbs": 6650.0, "tf_burst": 1590.0, "tf_sustained": 1400.0, "source": "B200_PROFILING.md fallback"}
 
 
+def kernel_source_sha():
+    """sha256 over the sources of the dominant kernels (csrc/conv_igemm.cu + csrc/conv_first.cu)."""
+    h = hashlib.sha256()
+    for name in ("conv_igemm.cu", "conv_first.cu"):
+        h.update(open(os.path.join(REPO, "spatiotemporalentropymodel_b200", "csrc", name), "rb").read())
+    return h.hexdigest()
+
+
 def measured_traffic():
-    """DRAM bytes per launch of the dominant kernel from the committed ncu capture, valid only for the kernel source it
-    was taken from (profiles/traffic.json is keyed on the sha256 of csrc/conv_igemm.cu); None when stale."""
+    """DRAM bytes per launch of the dominant kernels from the committed ncu capture, valid only for the kernel sources
+    it was taken from (profiles/traffic.json is keyed on kernel_source_sha()); None when stale."""
     p = os.path.join(REPO, "profiles", "traffic.json")
-    src = os.path.join(REPO, "spatiotemporalentropymodel_b200", "csrc", "conv_igemm.cu")
     try:
         rec = json.load(open(p))
-        sha = hashlib.sha256(open(src, "rb").read()).hexdigest()
+        sha = kernel_source_sha()
     except (OSError, ValueError):
         return None, "no committed ncu capture"
-    if rec.get("conv_igemm_cu_sha256") != sha:
-        return None, f"stale: {rec.get('source')} was captured on another build of conv_igemm.cu"
+    if rec.get("kernel_source_sha256") != sha:
+        return None, f"stale: {rec.get('source')} was captured on another build of the conv kernels"
     return rec.get("dram_bytes_per_launch"), rec.get("source")
 
 
