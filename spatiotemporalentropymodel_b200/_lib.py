@@ -10,7 +10,8 @@ import os
 from typing import Optional
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libstemb200.so")
+# STEMB200_LIB: another build of the same library (A/B measurements of kernel variants)
+LIB_PATH = os.environ.get("STEMB200_LIB") or os.path.join(_HERE, "libstemb200.so")
 
 DT_F16, DT_F32 = 0, 1
 EPI_LINEAR, EPI_SFT, EPI_ADD = 0, 1, 2

@@ -177,108 +177,109 @@ __global__ void __launch_bounds__(kThreads, 1) conv_first_gdn_kernel(const __gri
   };
 
   if (warp < 4) {
-  asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
-  if (warp == 0) {
-    // ============ TMA producer: gamma and W0 once, then one A tile per kernel row ============
-    const bool leader = elect_one();
-    if (leader) {
-      mbar_arrive_expect_tx(wfull_bar, kGChunks * kGChunkBytes + kRows * kWRowBytes);
-      for (int kc = 0; kc < kGChunks; ++kc) tma_load_2d(g_base + kc * kGChunkBytes, &p.g_map, wfull_bar, kc * 64, 0);
-      for (int r = 0; r < kRows; ++r) tma_load_2d(w_base + r * kWRowBytes, &p.w_map, wfull_bar, r * kKRow, 0);
-    }
-    int s = 0;
-    uint32_t ph = 0;
-    for (int tile = first; tile < p.total_tiles; tile += stride) {
-      int n_img, h0, w0;
-      decode(tile, n_img, h0, w0);
-      for (int r = 0; r < kRows; ++r) {
-        mbar_wait(empty_bar(s), ph ^ 1u);
+    // the four service warps hand registers to the sixteen epilogue warps (640 x 96 allocated: 128 x 40 + 512 x 104)
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+    if (warp == 0) {
+      // ============ TMA producer: gamma and W0 once, then one A tile per kernel row ============
+      const bool leader = elect_one();
+      if (leader) {
+        mbar_arrive_expect_tx(wfull_bar, kGChunks * kGChunkBytes + kRows * kWRowBytes);
+        for (int kc = 0; kc < kGChunks; ++kc) tma_load_2d(g_base + kc * kGChunkBytes, &p.g_map, wfull_bar, kc * 64, 0);
+        for (int r = 0; r < kRows; ++r) tma_load_2d(w_base + r * kWRowBytes, &p.w_map, wfull_bar, r * kKRow, 0);
+      }
+      int s = 0;
+      uint32_t ph = 0;
+      for (int tile = first; tile < p.total_tiles; tile += stride) {
+        int n_img, h0, w0;
+        decode(tile, n_img, h0, w0);
+        for (int r = 0; r < kRows; ++r) {
+          mbar_wait(empty_bar(s), ph ^ 1u);
+          if (leader) {
+            mbar_arrive_expect_tx(full_bar(s), a_tx_bytes);
+            // canvas row 2 (h0 + i) + r has parity r & 1 and index h0 + i + (r >> 1) among the rows of that parity
+            tma_load_4d(stage_base + s * kAStage, &p.a_map[r & 1], full_bar(s), 0, w0, h0 + (r >> 1), n_img);
+          }
+          if (++s == kStages) {
+            s = 0;
+            ph ^= 1u;
+          }
+        }
+      }
+    } else if (warp == 1) {
+      // ===================== MMA issuer =====================
+      const bool leader = elect_one();
+      constexpr uint32_t idesc = umma_idesc(/*F16*/ 0u, 128u, kN);
+      constexpr uint32_t idesc64 = umma_idesc(/*F16*/ 0u, 128u, 64u);
+      mbar_wait(wfull_bar, 0);
+      tc_fence_after();
+      int s = 0;
+      uint32_t ph = 0;
+      auto mma_row = [&](int r) {
+        mbar_wait(full_bar(s), ph);
+        tc_fence_after();
+        const uint64_t adesc = umma_desc_sw64(stage_base + s * kAStage);
+        const uint64_t bdesc = umma_desc_sw64(w_base + r * kWRowBytes);
         if (leader) {
-          mbar_arrive_expect_tx(full_bar(s), a_tx_bytes);
-          // canvas row 2 (h0 + i) + r has parity r & 1 and index h0 + i + (r >> 1) among the rows of that parity
-          tma_load_4d(stage_base + s * kAStage, &p.a_map[r & 1], full_bar(s), 0, w0, h0 + (r >> 1), n_img);
+  #pragma unroll
+          for (int kk = 0; kk < kKRow / 16; ++kk)
+            mma_f16_ss(tmem_base, adesc + 2u * kk, bdesc + 2u * kk, idesc, (r > 0 || kk > 0) ? 1u : 0u);
+          mma_commit(empty_bar(s));
         }
         if (++s == kStages) {
           s = 0;
           ph ^= 1u;
         }
-      }
-    }
-  } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    const bool leader = elect_one();
-    constexpr uint32_t idesc = umma_idesc(/*F16*/ 0u, 128u, kN);
-    constexpr uint32_t idesc64 = umma_idesc(/*F16*/ 0u, 128u, 64u);
-    mbar_wait(wfull_bar, 0);
-    tc_fence_after();
-    int s = 0;
-    uint32_t ph = 0;
-    auto mma_row = [&](int r) {
-      mbar_wait(full_bar(s), ph);
-      tc_fence_after();
-      const uint64_t adesc = umma_desc_sw64(stage_base + s * kAStage);
-      const uint64_t bdesc = umma_desc_sw64(w_base + r * kWRowBytes);
-      if (leader) {
-#pragma unroll
-        for (int kk = 0; kk < kKRow / 16; ++kk)
-          mma_f16_ss(tmem_base, adesc + 2u * kk, bdesc + 2u * kk, idesc, (r > 0 || kk > 0) ? 1u : 0u);
-        mma_commit(empty_bar(s));
-      }
-      if (++s == kStages) {
-        s = 0;
-        ph ^= 1u;
-      }
-    };
-    // norm(j) = gamma . (x s)^2 of tile j: A from tensor memory, gamma resident in shared memory.  One set of MMAs per
-    // 64-channel chunk of the norm accumulator, so a chunk is rewritten as soon as phase 2a of tile j-1 has read it.
-    auto mma_gamma = [&](int j) {
-      mbar_wait(sqrdy_bar, j & 1);
-#pragma unroll
-      for (int g = 0; g < kGChunks; ++g) {
-        if (j >= 1) mbar_wait(normfree_bar(g), (j - 1) & 1);
-        tc_fence_after();
-        if (leader) {
-#pragma unroll
-          for (int kc = 0; kc < kGChunks; ++kc) {
-            const uint64_t bdesc = umma_desc_sw128(g_base + kc * kGChunkBytes + g * (64 * 128));
-#pragma unroll
-            for (int kk = 0; kk < 4; ++kk)
-              mma_f16_ts(tmem_base + kNormCol + 64u * g, tmem_base + kSqCol + 32u * kc + 8u * kk, bdesc + 2u * kk,
-                         idesc64, (kc > 0 || kk > 0) ? 1u : 0u);
+      };
+      // norm(j) = gamma . (x s)^2 of tile j: A from tensor memory, gamma resident in shared memory.  One set of MMAs per
+      // 64-channel chunk of the norm accumulator, so a chunk is rewritten as soon as phase 2a of tile j-1 has read it.
+      auto mma_gamma = [&](int j) {
+        mbar_wait(sqrdy_bar, j & 1);
+  #pragma unroll
+        for (int g = 0; g < kGChunks; ++g) {
+          if (j >= 1) mbar_wait(normfree_bar(g), (j - 1) & 1);
+          tc_fence_after();
+          if (leader) {
+  #pragma unroll
+            for (int kc = 0; kc < kGChunks; ++kc) {
+              const uint64_t bdesc = umma_desc_sw128(g_base + kc * kGChunkBytes + g * (64 * 128));
+  #pragma unroll
+              for (int kk = 0; kk < 4; ++kk)
+                mma_f16_ts(tmem_base + kNormCol + 64u * g, tmem_base + kSqCol + 32u * kc + 8u * kk, bdesc + 2u * kk,
+                           idesc64, (kc > 0 || kk > 0) ? 1u : 0u);
+            }
+            mma_commit(nfull_bar(g));
           }
-          mma_commit(nfull_bar(g));
         }
+      };
+      int it = 0;
+      for (int tile = first; tile < p.total_tiles; tile += stride, ++it) {
+        if (it >= 1) {  // phase 1a of tile it-1 has moved the conv accumulator into registers
+          mbar_wait(convfree_bar, (it - 1) & 1);
+          tc_fence_after();
+        }
+        for (int r = 0; r < kRows; ++r) mma_row(r);
+        if (leader) mma_commit(tfull_bar);
+        if (it >= 1) mma_gamma(it - 1);
       }
-    };
-    int it = 0;
-    for (int tile = first; tile < p.total_tiles; tile += stride, ++it) {
-      if (it >= 1) {  // phase 1a of tile it-1 has moved the conv accumulator into registers
-        mbar_wait(convfree_bar, (it - 1) & 1);
-        tc_fence_after();
+      if (it > 0) mma_gamma(it - 1);
+    } else if (warp == 3) {
+      // ===================== TMA store issuer =====================
+      if (lane == 0) {
+        int n = 0;
+        for (int tile = first; tile < p.total_tiles; tile += stride, ++n) {
+          int n_img, h0, w0;
+          decode(tile, n_img, h0, w0);
+          mbar_wait(staged_bar, n & 1);  // every epilogue warp has written and fenced its part of the tile
+  #pragma unroll
+          for (int g = 0; g < kGChunks; ++g)
+            tma_store_4d(&p.out_map, out_base + static_cast<uint32_t>(g) * kOutChunk, 64 * g, w0, h0, n_img);
+          tma_store_commit();
+          tma_store_wait_read<0>();
+          mbar_arrive(stfree_bar);
+        }
+        tma_store_wait_all<0>();
       }
-      for (int r = 0; r < kRows; ++r) mma_row(r);
-      if (leader) mma_commit(tfull_bar);
-      if (it >= 1) mma_gamma(it - 1);
     }
-    if (it > 0) mma_gamma(it - 1);
-  } else if (warp == 3) {
-    // ===================== TMA store issuer =====================
-    if (lane == 0) {
-      int n = 0;
-      for (int tile = first; tile < p.total_tiles; tile += stride, ++n) {
-        int n_img, h0, w0;
-        decode(tile, n_img, h0, w0);
-        mbar_wait(staged_bar, n & 1);  // every epilogue warp has written and fenced its part of the tile
-#pragma unroll
-        for (int g = 0; g < kGChunks; ++g)
-          tma_store_4d(&p.out_map, out_base + static_cast<uint32_t>(g) * kOutChunk, 64 * g, w0, h0, n_img);
-        tma_store_commit();
-        tma_store_wait_read<0>();
-        mbar_arrive(stfree_bar);
-      }
-      tma_store_wait_all<0>();
-    }
-  }
   } else {
     asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
     // ===================== epilogue: 16 warps, one tile per phase =====================

@@ -82,10 +82,16 @@ struct ConvKernelParams {
   int igdn;
 };
 
-template <int BLOCK_N>
+template <int BLOCK_N, bool kDuo = false>
 struct ConvCfg {
-  static constexpr int kBStageBytes = BLOCK_N * 128;
-  static constexpr int kStageBytes = kAStageBytes + kBStageBytes;
+  static constexpr int kBStageBytes = BLOCK_N * 128;  // one K chunk of the weights (all BLOCK_N rows)
+  // duo mode: a CTA stages only its half of every B tile: smaller ring slots, more k-steps in flight (see GdnCfgT)
+#ifdef STEMB200_SHALLOW_DUO_RING
+  static constexpr int kBSlotBytes = kBStageBytes;
+#else
+  static constexpr int kBSlotBytes = kDuo ? kBStageBytes / 2 : kBStageBytes;
+#endif
+  static constexpr int kStageBytes = kAStageBytes + kBSlotBytes;
   static constexpr int kNumOutBufs = 2;
   static constexpr int kBarrierBytes = 256 + BLOCK_N * 4;  // mbarriers + TMEM slot, then the tile's bias slice
   static constexpr int kFree = kSmemLimit - 1024 - kNumOutBufs * kOutStageBytes - kBarrierBytes;
@@ -163,7 +169,7 @@ __device__ __forceinline__ uint32_t pack_half2(float a, float b) {
 template <int BLOCK_N, int EPI, bool kDuo = false>
 __global__ void __launch_bounds__(kNumThreads, 1)
 conv_igemm_kernel(const __grid_constant__ ConvKernelParams p) {
-  using Cfg = ConvCfg<BLOCK_N>;
+  using Cfg = ConvCfg<BLOCK_N, kDuo>;
   constexpr int kStages = Cfg::kStages;
 
   extern __shared__ uint8_t smem_raw[];
@@ -586,20 +592,33 @@ conv_igemm_kernel(const __grid_constant__ ConvKernelParams p) {
 // =====================================================================================================
 constexpr int kLastN = 96;  // columns of the fused last-layer GEMM (75 real)
 
-template <int kNT, bool kLast = false>
+template <int kNT, bool kLast = false, bool kDuo = false>
 struct GdnCfgT {
   static constexpr int kN = kNT;
-  static constexpr int kBStageBytes = kN * 128;
-  static constexpr int kStageBytes = kAStageBytes + kBStageBytes;
-  static constexpr int kStages = kLast ? 3 : 4;  // the resident W6 operand takes one stage's worth of shared memory
+  static constexpr int kBStageBytes = kN * 128;  // one K chunk of the weights (all kN rows)
+  // duo mode: a CTA stages only its half of every B tile, so a ring slot is 28 KB instead of 40 KB and the same shared
+  // memory holds more k-steps in flight.  The main loop is bound by bytes in flight / TMA latency (~1 250 cycles from
+  // L2 under the step's 14 TB/s of operand traffic): 3 x 40 KB -> one k-step per 610 cycles, 4 -> 460, 6 x 28 KB -> 384
+  // (the tensor pipe's own rate).
+#ifdef STEMB200_SHALLOW_DUO_RING  // A/B build: the round-1 ring (full-size slots, 4 / 3 stages) also in duo mode
+  static constexpr bool kSmallSlots = false;
+#else
+  static constexpr bool kSmallSlots = kDuo;
+#endif
+  static constexpr int kBSlotBytes = kSmallSlots ? kBStageBytes / 2 : kBStageBytes;
+  static constexpr int kStageBytes = kAStageBytes + kBSlotBytes;
+  // kLast: the resident W6 operand (all of it, or this CTA's half in duo mode) shares the budget
+  static constexpr int kStages = kSmallSlots ? (kLast ? 5 : 6) : (kLast ? 3 : 4);
   static constexpr int kA2Bytes = (kN / 64) * kAStageBytes;  // x^2 operand (64-channel chunks); reused as output staging
   static constexpr int kW6Bytes = kLast ? (kN / 64) * kLastN * 128 : 0;
+  static constexpr int kW6SlotBytes = kSmallSlots ? kW6Bytes / 2 : kW6Bytes;
   static constexpr int kBarrierBytes = 256 + 2 * kN * 4;
-  static constexpr int kSmemBytes = 1024 + kStages * kStageBytes + kA2Bytes + kW6Bytes + kBarrierBytes;
+  static constexpr int kSmemBytes = 1024 + kStages * kStageBytes + kA2Bytes + kW6SlotBytes + kBarrierBytes;
   static constexpr int kTmemCols = 512;
   static constexpr uint32_t kStashCol = 2 * kN;
   static_assert(kN % 64 == 0 && 2 * kN + kN / 2 <= 512, "TMEM budget");
   static_assert(!kLast || kN / 2 >= kLastN, "the last-layer accumulator reuses the stash columns");
+  static_assert(2 * kStages + 9 <= 32, "barrier slots");
   static_assert(kSmemBytes <= kSmemLimit, "smem overflow");
 };
 
@@ -610,7 +629,7 @@ constexpr int kGdnThreads = 128 + kGdnEpiThreads;       // 4 control warps + 16 
 template <int kNT, bool kInverse, bool kLast = false, bool kDuo = false>
 __global__ void __launch_bounds__(kGdnThreads, 1)
 conv_gdn_kernel(const __grid_constant__ ConvKernelParams p) {
-  using Cfg = GdnCfgT<kNT, kLast>;
+  using Cfg = GdnCfgT<kNT, kLast, kDuo>;
   constexpr int kStages = Cfg::kStages;
   constexpr int BLOCK_N = Cfg::kN;
   constexpr int kGChunks = BLOCK_N / kKChunk;
@@ -620,7 +639,8 @@ conv_gdn_kernel(const __grid_constant__ ConvKernelParams p) {
   const uint32_t stage_base = smem_base;
   const uint32_t a2_base = smem_base + kStages * Cfg::kStageBytes;
   const uint32_t w6_base = a2_base + Cfg::kA2Bytes;  // kLast: W6 as K-major chunks [kN/64][96 rows][128 B]
-  const uint32_t bar_base = w6_base + Cfg::kW6Bytes;
+  const uint32_t bar_base = w6_base + Cfg::kW6SlotBytes;
+  constexpr uint32_t kW6ChunkBytes = (Cfg::kSmallSlots ? kLastN / 2 : kLastN) * 128;  // duo: this CTA's 48 of the 96 rows
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (kStages + s); };
   const uint32_t tfull_bar = bar_base + 8u * (2 * kStages);
@@ -757,17 +777,17 @@ conv_gdn_kernel(const __grid_constant__ ConvKernelParams p) {
     };
     if constexpr (kLast) {
       if (leader && duo) {
-        // each CTA holds 48 of W6's 96 rows (the first 48 row slots of every K chunk)
+        // each CTA holds 48 of W6's 96 rows
         tma_prefetch_desc(&p.w6_half_map);
         const uint32_t lbar = mapa_shared(w6full_bar, 0);
         if (crank == 0) mbar_arrive_expect_tx(w6full_bar, Cfg::kW6Bytes);
         for (int kc = 0; kc < kGChunks; ++kc)
-          tma_load_2d_2sm(w6_base + kc * (kLastN * 128), &p.w6_half_map, lbar, kc * kKChunk, crank * (kLastN / 2));
+          tma_load_2d_2sm(w6_base + kc * kW6ChunkBytes, &p.w6_half_map, lbar, kc * kKChunk, crank * (kLastN / 2));
       } else if (leader) {
         tma_prefetch_desc(&p.w6_map);
         mbar_arrive_expect_tx(w6full_bar, Cfg::kW6Bytes);
         for (int kc = 0; kc < kGChunks; ++kc)
-          tma_load_2d(w6_base + kc * (kLastN * 128), &p.w6_map, w6full_bar, kc * kKChunk, 0);
+          tma_load_2d(w6_base + kc * kW6ChunkBytes, &p.w6_map, w6full_bar, kc * kKChunk, 0);
       }
     }
     int it = 0;
@@ -819,7 +839,7 @@ conv_gdn_kernel(const __grid_constant__ ConvKernelParams p) {
 #pragma unroll
           for (int kc = 0; kc < kGChunks; ++kc) {
             const uint64_t adesc = umma_desc_sw128(a2_base + kc * kAStageBytes);
-            const uint64_t bdesc = umma_desc_sw128(w6_base + kc * (kLastN * 128));
+            const uint64_t bdesc = umma_desc_sw128(w6_base + kc * kW6ChunkBytes);
 #pragma unroll
             for (int kk = 0; kk < 4; ++kk)
               mma(tmem_base + Cfg::kStashCol, adesc + 2u * kk, bdesc + 2u * kk, idesc3, (kc > 0 || kk > 0) ? 1u : 0u);
@@ -2055,7 +2075,7 @@ int launch_pairs(Kern kernel, const ConvKernelParams& kp, int threads, size_t sm
 
 template <int BLOCK_N, int EPI>
 int launch_conv_duo(const ConvKernelParams& kp, cudaStream_t stream) {
-  using Cfg = ConvCfg<BLOCK_N>;
+  using Cfg = ConvCfg<BLOCK_N, true>;
   static bool configured = false;  // benign race: attribute set is idempotent
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(conv_igemm_kernel<BLOCK_N, EPI, true>,
@@ -2296,7 +2316,7 @@ extern "C" int stemb200_conv2d_fwd(const stemb200_conv_desc* d, const void* cons
 namespace {
 template <int kNT, bool kInverse, bool kLast = false, bool kDuo = false>
 int launch_gdn(const ConvKernelParams& kp, int grid, cudaStream_t stream) {
-  using Cfg = GdnCfgT<kNT, kLast>;
+  using Cfg = GdnCfgT<kNT, kLast, kDuo>;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(conv_gdn_kernel<kNT, kInverse, kLast, kDuo>,
