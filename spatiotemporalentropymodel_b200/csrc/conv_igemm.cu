@@ -75,6 +75,7 @@ struct ConvKernelParams {
   int duo;  // conv_gdn_kernel, csize == 2: cta_group::2 MMAs (see ptx.cuh)
   __half* col_out;  // [batch][full_h][full_w][96] fp16
   int store_act;    // 0: the layer's own activation is not written at all
+  int gamma_pos;  // conv_gdn_kernel: the gamma MMAs of tile i-1 are issued after this many k-steps of tile i (at most half the loop)
   int kk_main;  // K = 16 slices issued per main-loop k-step (4; 3 in row_taps mode: 5 taps x 8 channels = 40 <= 48)
   // fused GDN / IGDN (conv_gdn_kernel only)
   alignas(64) CUtensorMap g_map;  // gamma [c_out][c_out] fp16, K-major
@@ -592,7 +593,7 @@ conv_igemm_kernel(const __grid_constant__ ConvKernelParams p) {
 // =====================================================================================================
 constexpr int kLastN = 96;  // columns of the fused last-layer GEMM (75 real)
 
-template <int kNT, bool kLast = false, bool kDuo = false>
+template <int kNT, bool kLast = false, bool kDuo = false, bool kTm = false>
 struct GdnCfgT {
   static constexpr int kN = kNT;
   static constexpr int kBStageBytes = kN * 128;  // one K chunk of the weights (all kN rows)
@@ -607,17 +608,19 @@ struct GdnCfgT {
 #endif
   static constexpr int kBSlotBytes = kSmallSlots ? kBStageBytes / 2 : kBStageBytes;
   static constexpr int kStageBytes = kAStageBytes + kBSlotBytes;
-  // kLast: the resident W6 operand (all of it, or this CTA's half in duo mode) shares the budget
-  static constexpr int kStages = kSmallSlots ? (kLast ? 5 : 6) : (kLast ? 3 : 4);
-  static constexpr int kA2Bytes = (kN / 64) * kAStageBytes;  // x^2 operand (64-channel chunks); reused as output staging
+  // kLast: the resident W6 operand (all of it, or this CTA's half in duo mode) shares the budget.
+  // kTm (operands in tensor memory): no x^2 / staging buffers in shared memory, their room goes to a fourth stage.
+  static constexpr int kStages = kSmallSlots ? (kLast ? 5 : 6) : ((kLast && !kTm) ? 3 : 4);
+  static constexpr int kA2Bytes = kTm ? 0 : (kN / 64) * kAStageBytes;  // x^2 operand (64-channel chunks) / staging
   static constexpr int kW6Bytes = kLast ? (kN / 64) * kLastN * 128 : 0;
   static constexpr int kW6SlotBytes = kSmallSlots ? kW6Bytes / 2 : kW6Bytes;
   static constexpr int kBarrierBytes = 256 + 2 * kN * 4;
   static constexpr int kSmemBytes = 1024 + kStages * kStageBytes + kA2Bytes + kW6SlotBytes + kBarrierBytes;
   static constexpr int kTmemCols = 512;
-  static constexpr uint32_t kStashCol = 2 * kN;
+  static constexpr uint32_t kStashCol = 2 * kN;  // x s stash; kTm: the packed fp16 operand ((x s)^2, then the output)
   static_assert(kN % 64 == 0 && 2 * kN + kN / 2 <= 512, "TMEM budget");
   static_assert(!kLast || kN / 2 >= kLastN, "the last-layer accumulator reuses the stash columns");
+  static_assert(!kTm || (kLast && !kDuo), "tensor-memory operands: fused last layer, one CTA per MMA");
   static_assert(2 * kStages + 9 <= 32, "barrier slots");
   static_assert(kSmemBytes <= kSmemLimit, "smem overflow");
 };
@@ -626,10 +629,10 @@ constexpr int kGdnEpiWarps = 16;                        // 4 per TMEM lane group
 constexpr int kGdnEpiThreads = kGdnEpiWarps * 32;       // 512
 constexpr int kGdnThreads = 128 + kGdnEpiThreads;       // 4 control warps + 16 epilogue warps
 
-template <int kNT, bool kInverse, bool kLast = false, bool kDuo = false>
+template <int kNT, bool kInverse, bool kLast = false, bool kDuo = false, bool kTm = false>
 __global__ void __launch_bounds__(kGdnThreads, 1)
 conv_gdn_kernel(const __grid_constant__ ConvKernelParams p) {
-  using Cfg = GdnCfgT<kNT, kLast, kDuo>;
+  using Cfg = GdnCfgT<kNT, kLast, kDuo, kTm>;
   constexpr int kStages = Cfg::kStages;
   constexpr int BLOCK_N = Cfg::kN;
   constexpr int kGChunks = BLOCK_N / kKChunk;
@@ -794,7 +797,7 @@ conv_gdn_kernel(const __grid_constant__ ConvKernelParams p) {
     for (int tile = q_first; tile < n_items; tile += q_stride, ++it) {
       const TileCoord t = decode_tile(p, tile, crank, BLOCK_N);
       const int kbeg = p.sub_kbeg[t.sub], kend = p.sub_kend[t.sub];
-      const int ksplit = kbeg + ((kend - kbeg) >> 1);
+      const int ksplit = kbeg + min((kend - kbeg) >> 1, p.gamma_pos);
       for (int k = kbeg; k < ksplit; ++k) load_main(t, k);
       if (it > 0) load_gamma();
       for (int k = ksplit; k < kend; ++k) load_main(t, k);
@@ -841,8 +844,13 @@ conv_gdn_kernel(const __grid_constant__ ConvKernelParams p) {
             const uint64_t adesc = umma_desc_sw128(a2_base + kc * kAStageBytes);
             const uint64_t bdesc = umma_desc_sw128(w6_base + kc * kW6ChunkBytes);
 #pragma unroll
-            for (int kk = 0; kk < 4; ++kk)
-              mma(tmem_base + Cfg::kStashCol, adesc + 2u * kk, bdesc + 2u * kk, idesc3, (kc > 0 || kk > 0) ? 1u : 0u);
+            for (int kk = 0; kk < 4; ++kk) {
+              if constexpr (kTm)  // A = the tile's output in tensor memory, D = the (dead) accumulator of that tile
+                mma_f16_ts(tmem_base + (n3_done & 1) * BLOCK_N, tmem_base + Cfg::kStashCol + 32u * kc + 8u * kk,
+                           bdesc + 2u * kk, idesc3, (kc > 0 || kk > 0) ? 1u : 0u);
+              else
+                mma(tmem_base + Cfg::kStashCol, adesc + 2u * kk, bdesc + 2u * kk, idesc3, (kc > 0 || kk > 0) ? 1u : 0u);
+            }
           }
           commit_local(d3full_bar);
         }
@@ -889,8 +897,13 @@ conv_gdn_kernel(const __grid_constant__ ConvKernelParams p) {
         const uint64_t bdesc = umma_desc_sw128(stage_base + s * Cfg::kStageBytes + kAStageBytes);
         if (leader) {
 #pragma unroll
-          for (int kk = 0; kk < 4; ++kk)
-            mma(d_tmem, adesc + 2u * kk, bdesc + 2u * kk, idesc, (kc > 0 || kk > 0) ? 1u : 0u);
+          for (int kk = 0; kk < 4; ++kk) {
+            if constexpr (kTm)  // A = (x s)^2 in tensor memory
+              mma_f16_ts(d_tmem, tmem_base + Cfg::kStashCol + 32u * kc + 8u * kk, bdesc + 2u * kk, idesc,
+                         (kc > 0 || kk > 0) ? 1u : 0u);
+            else
+              mma(d_tmem, adesc + 2u * kk, bdesc + 2u * kk, idesc, (kc > 0 || kk > 0) ? 1u : 0u);
+          }
           release_slot(empty_bar(s));
         }
         if (++s == kStages) {
@@ -904,7 +917,7 @@ conv_gdn_kernel(const __grid_constant__ ConvKernelParams p) {
     for (int tile = q_first; tile < n_items; tile += q_stride, ++it) {
       const int sub = tile_sub(p, tile);
       const int kbeg = p.sub_kbeg[sub], kend = p.sub_kend[sub];
-      const int ksplit = kbeg + ((kend - kbeg) >> 1);
+      const int ksplit = kbeg + min((kend - kbeg) >> 1, p.gamma_pos);
       const uint32_t d_tmem = tmem_base + (it & 1) * BLOCK_N;
       if (it >= 2) {  // phase 2 of tile it-2 has finished reading this accumulator
         wait_bar(accfree_bar(it & 1), ((it >> 1) - 1) & 1, true);
@@ -947,6 +960,116 @@ conv_gdn_kernel(const __grid_constant__ ConvKernelParams p) {
       const uint32_t stash_col = tmem_base + lane_off + Cfg::kStashCol + 8 * q;
       mbar_wait(tfull_bar, par);
       tc_fence_after();
+      if constexpr (kTm) {
+        // ===== operands in tensor memory (fused last layer, activation not stored): x s stays in registers, (x s)^2
+        // and then the layer's output are written as packed fp16 into the operand columns, from where the gamma and
+        // W6 MMAs read their A operand; no shared-memory buffer, no named barrier, no proxy fence
+        uint32_t hx[kGChunks * 8];
+        {  // ---- phase 1
+          uint32_t r[kGChunks][16];
+#pragma unroll
+          for (int g = 0; g < kGChunks; ++g) tmem_ld_32x16(acc_col + 64 * g, r[g]);
+          tmem_ld_wait();
+#pragma unroll
+          for (int g = 0; g < kGChunks; ++g) {
+            uint32_t hq[8];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              float b0, b1, b2, b3;
+              asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                           : "=f"(b0), "=f"(b1), "=f"(b2), "=f"(b3)
+                           : "r"(bias_smem + 4u * (64 * g + 16 * q + 4 * j)));
+              const __half2 h0 = __floats2half2_rn(fmaf(__uint_as_float(r[g][4 * j]), sc, b0),
+                                                   fmaf(__uint_as_float(r[g][4 * j + 1]), sc, b1));
+              const __half2 h1 = __floats2half2_rn(fmaf(__uint_as_float(r[g][4 * j + 2]), sc, b2),
+                                                   fmaf(__uint_as_float(r[g][4 * j + 3]), sc, b3));
+              const __half2 q0 = __hmul2(h0, h0), q1 = __hmul2(h1, h1);
+              hx[g * 8 + 2 * j] = *reinterpret_cast<const uint32_t*>(&h0);
+              hx[g * 8 + 2 * j + 1] = *reinterpret_cast<const uint32_t*>(&h1);
+              hq[2 * j] = *reinterpret_cast<const uint32_t*>(&q0);
+              hq[2 * j + 1] = *reinterpret_cast<const uint32_t*>(&q1);
+            }
+            tmem_st_32x8(stash_col + 32 * g, hq);
+          }
+          tmem_st_wait();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) arrive_mma(a2rdy_bar);
+        }
+        // ---- phase 2: out = (x s) * (r)sqrt(.) over the operand columns (the gamma MMAs have consumed (x s)^2)
+        mbar_wait(nfull_bar, par);
+        tc_fence_after();
+#pragma unroll
+        for (int g = 0; g < kGChunks; ++g) {
+          uint32_t r[16];
+          tmem_ld_32x16(acc_col + 64 * g, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            float b0, b1, b2, b3;
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                         : "=f"(b0), "=f"(b1), "=f"(b2), "=f"(b3)
+                         : "r"(beta_smem + 4u * (64 * g + 16 * q + 4 * j)));
+            const float n0 = fmaf(__uint_as_float(r[4 * j]), ka, b0);
+            const float n1 = fmaf(__uint_as_float(r[4 * j + 1]), ka, b1);
+            const float n2 = fmaf(__uint_as_float(r[4 * j + 2]), ka, b2);
+            const float n3 = fmaf(__uint_as_float(r[4 * j + 3]), ka, b3);
+            float f0, f1, f2, f3;
+            if constexpr (kInverse) {
+              f0 = approx_sqrt(n0), f1 = approx_sqrt(n1), f2 = approx_sqrt(n2), f3 = approx_sqrt(n3);
+            } else {
+              f0 = approx_rsqrt(n0), f1 = approx_rsqrt(n1), f2 = approx_rsqrt(n2), f3 = approx_rsqrt(n3);
+            }
+            const float2 x0 = __half22float2(*reinterpret_cast<const __half2*>(&hx[g * 8 + 2 * j]));
+            const float2 x1 = __half22float2(*reinterpret_cast<const __half2*>(&hx[g * 8 + 2 * j + 1]));
+            hx[g * 8 + 2 * j] = pack_half2(x0.x * f0, x0.y * f1);
+            hx[g * 8 + 2 * j + 1] = pack_half2(x1.x * f2, x1.y * f3);
+          }
+          uint32_t ho[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) ho[j] = hx[g * 8 + j];
+          tmem_st_32x8(stash_col + 32 * g, ho);
+        }
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) arrive_mma(a3rdy_bar);
+        // ---- phase 3: col = out . W6^T, accumulated by the MMA warp in the first 96 columns of this tile's (dead)
+        // accumulator; this thread's 24 of the 96 columns go to the col buffer as fp16
+        mbar_wait(d3full_bar, par);
+        tc_fence_after();
+        uint32_t d[24];
+        {
+          uint32_t d16[16], d8[8];
+          const uint32_t d3_col = tmem_base + lane_off + (it & 1) * BLOCK_N + 24 * q;
+          tmem_ld_32x16(d3_col, d16);
+          tmem_ld_32x8(d3_col + 16, d8);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 16; ++i) d[i] = d16[i];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) d[16 + i] = d8[i];
+        }
+        // every TMEM read of this tile has completed: hand the accumulator back to the MMA thread
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) arrive_mma(accfree_bar(it & 1));
+        const int th = row / p.tile_w, tw = row - th * p.tile_w;
+        const int oh = t.h0 + th, ow = t.w0 + tw;
+        if (row < p.tile_h * p.tile_w && oh < p.h_out && ow < p.w_out) {
+          const long long pix =
+              (static_cast<long long>(t.n_img) * p.full_h + (oh * p.os + p.sub_p[t.sub])) * p.full_w +
+              (ow * p.os + p.sub_q[t.sub]);
+          uint4* dst = reinterpret_cast<uint4*>(p.col_out + pix * kLastN + 24 * q);
+#pragma unroll
+          for (int i = 0; i < 3; ++i)
+            dst[i] = make_uint4(pack_half2(__uint_as_float(d[8 * i]), __uint_as_float(d[8 * i + 1])),
+                                pack_half2(__uint_as_float(d[8 * i + 2]), __uint_as_float(d[8 * i + 3])),
+                                pack_half2(__uint_as_float(d[8 * i + 4]), __uint_as_float(d[8 * i + 5])),
+                                pack_half2(__uint_as_float(d[8 * i + 6]), __uint_as_float(d[8 * i + 7])));
+        }
+        continue;
+      }
       // ---- phase 1: x = A + bias; x s -> stash (TMEM, packed fp16), (x s)^2 -> smem operand.
       // Buffer g was the staging of the previous tile's g-th output store (one bulk group each, oldest first).
       {
@@ -2228,6 +2351,7 @@ int setup_params(const stemb200_conv_desc* d, const Plan& pl, const void* const*
     if (int rc = encode_weight(&kp.b_half_map, packed_weight, K, d->c_out, pl.block_n / 2)) return rc;
   }
   kp.kk_main = (pl.row_taps && d->kw * 8 <= 48) ? 3 : 4;
+  kp.gamma_pos = getenv("STEMB200_GAMMA_POS") ? atoi(getenv("STEMB200_GAMMA_POS")) : 1 << 20;
   kp.c_out = d->c_out;
   kp.slope = d->lrelu_slope;
   kp.sq_scale = d->sq_scale;
@@ -2314,25 +2438,25 @@ extern "C" int stemb200_conv2d_fwd(const stemb200_conv_desc* d, const void* cons
 }
 
 namespace {
-template <int kNT, bool kInverse, bool kLast = false, bool kDuo = false>
+template <int kNT, bool kInverse, bool kLast = false, bool kDuo = false, bool kTm = false>
 int launch_gdn(const ConvKernelParams& kp, int grid, cudaStream_t stream) {
-  using Cfg = GdnCfgT<kNT, kLast, kDuo>;
+  using Cfg = GdnCfgT<kNT, kLast, kDuo, kTm>;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(conv_gdn_kernel<kNT, kInverse, kLast, kDuo>,
+    cudaError_t e = cudaFuncSetAttribute(conv_gdn_kernel<kNT, kInverse, kLast, kDuo, kTm>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
     if (e != cudaSuccess) return set_cuda_error("cudaFuncSetAttribute(conv_gdn)", e);
     configured = true;
   }
   if (kp.csize == 2) {
     static int clusters = 0;
-    return launch_pairs(conv_gdn_kernel<kNT, kInverse, kLast, kDuo>, kp, kGdnThreads, Cfg::kSmemBytes, stream,
+    return launch_pairs(conv_gdn_kernel<kNT, kInverse, kLast, kDuo, kTm>, kp, kGdnThreads, Cfg::kSmemBytes, stream,
                         clusters);
   }
   if constexpr (kDuo) {
     return set_error("conv_gdn: duo mode needs a cluster launch");
   } else {
-    conv_gdn_kernel<kNT, kInverse, kLast><<<grid, kGdnThreads, Cfg::kSmemBytes, stream>>>(kp);
+    conv_gdn_kernel<kNT, kInverse, kLast, false, kTm><<<grid, kGdnThreads, Cfg::kSmemBytes, stream>>>(kp);
     count_launch();
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return set_cuda_error("conv_gdn launch", e);
@@ -2404,10 +2528,10 @@ int gdn_forward(const stemb200_conv_desc* d, const void* const* in, const void* 
   int max_k = 0;
   for (int i = 0; i < pl.n_sub; ++i) max_k = std::max(max_k, pl.sub_kend[i] - pl.sub_kbeg[i]);
   const bool use_pp = !last && pp_mode_enabled() && !inverse && max_k <= 8;
-  // (the fused-last variant stays in pair mode: its epilogue chain has three hand-offs to the MMA warp per tile, and
-  // routing them through the leader CTA costs more than the halved B reads give back: measured 2.9 -> 3.3 ms;
-  // STEMB200_DUO_LAST=1 selects duo mode for it anyway, for A/B measurements)
-  static const bool duo_last = [] { const char* e = getenv("STEMB200_DUO_LAST"); return e && e[0] == '1'; }();
+  // (the fused-last variant: duo mode since round 2 - with cluster-scope release arrives its three epilogue -> MMA
+  // hand-offs per tile cost more than the halved B reads gave back (2.9 -> 3.3 ms); with CTA-scope arrives and five
+  // 28 KB ring slots it is the faster one (2.66 -> 2.44 ms, the step 9.55 -> 9.27 ms).  STEMB200_DUO_LAST=0: pair mode)
+  static const bool duo_last = [] { const char* e = getenv("STEMB200_DUO_LAST"); return !(e && e[0] == '0'); }();
   kp.duo = (kp.csize == 2 && !use_pp && (!last || duo_last) && duo_mode_enabled()) ? 1 : 0;
   if (last) {
     if (kp.duo)
@@ -2415,7 +2539,12 @@ int gdn_forward(const stemb200_conv_desc* d, const void* const* in, const void* 
     if (int rc = encode_weight(&kp.w6_map, packed_w6, d->c_out, kLastN, kLastN)) return rc;
     kp.col_out = static_cast<__half*>(col_out);
     kp.store_act = out ? 1 : 0;
-    return kp.duo ? launch_gdn<192, true, true, true>(kp, grid, st) : launch_gdn<192, true, true>(kp, grid, st);
+    if (kp.duo) return launch_gdn<192, true, true, true>(kp, grid, st);
+    // the layer's own activation is normally not stored: (x s)^2 and the output then live in tensor memory as MMA
+    // operands and the shared memory of their buffers is a fourth ring stage (STEMB200_LAST_TMEM=0: the round-1 kernel)
+    static const bool tm_off = [] { const char* e = getenv("STEMB200_LAST_TMEM"); return e && e[0] == '0'; }();
+    if (!out && !tm_off) return launch_gdn<192, true, true, false, true>(kp, grid, st);
+    return launch_gdn<192, true, true>(kp, grid, st);
   }
   if (use_pp)
     return d->c_out == 192 ? launch_gdn_pp<192, false>(kp, grid, st) : launch_gdn_pp<128, false>(kp, grid, st);

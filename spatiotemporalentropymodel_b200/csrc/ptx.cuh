@@ -299,9 +299,17 @@ __device__ __forceinline__ uint32_t mapa_shared(uint32_t addr, uint32_t rank) {
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
   return r;
 }
-// arrive on an mbarrier of any CTA of the cluster (address from mapa_shared); release at cluster scope
+// arrive on an mbarrier of any CTA of the cluster (address from mapa_shared).  Release at CTA scope (the default):
+// what the arriving epilogue threads produced - shared-memory operands behind fence.proxy.async, tensor-memory reads
+// and writes behind tcgen05.wait / tcgen05.fence - is consumed by the tensor core of their OWN SM; the leader CTA's
+// MMA thread only needs the signal.  (.release.cluster compiles to MEMBAR.ALL.GPU + ERRBAR in front of every arrive:
+// 25-30 % of the epilogue warps' time in the duo-mode kernels, profiles/r02_ncu_duo_arrive.txt.)
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+#ifdef STEMB200_CLUSTER_RELEASE_ARRIVE  // A/B build
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+#else
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+#endif
 }
 // wait with acquire at cluster scope (pairs with mbar_arrive_cluster from the peer CTA)
 __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
