@@ -75,7 +75,6 @@ struct ConvKernelParams {
   int duo;  // conv_gdn_kernel, csize == 2: cta_group::2 MMAs (see ptx.cuh)
   __half* col_out;  // [batch][full_h][full_w][96] fp16
   int store_act;    // 0: the layer's own activation is not written at all
-  int gamma_pos;  // conv_gdn_kernel: the gamma MMAs of tile i-1 are issued after this many k-steps of tile i (at most half the loop)
   int kk_main;  // K = 16 slices issued per main-loop k-step (4; 3 in row_taps mode: 5 taps x 8 channels = 40 <= 48)
   // fused GDN / IGDN (conv_gdn_kernel only)
   alignas(64) CUtensorMap g_map;  // gamma [c_out][c_out] fp16, K-major
@@ -797,7 +796,7 @@ conv_gdn_kernel(const __grid_constant__ ConvKernelParams p) {
     for (int tile = q_first; tile < n_items; tile += q_stride, ++it) {
       const TileCoord t = decode_tile(p, tile, crank, BLOCK_N);
       const int kbeg = p.sub_kbeg[t.sub], kend = p.sub_kend[t.sub];
-      const int ksplit = kbeg + min((kend - kbeg) >> 1, p.gamma_pos);
+      const int ksplit = kbeg + ((kend - kbeg) >> 1);
       for (int k = kbeg; k < ksplit; ++k) load_main(t, k);
       if (it > 0) load_gamma();
       for (int k = ksplit; k < kend; ++k) load_main(t, k);
@@ -917,7 +916,7 @@ conv_gdn_kernel(const __grid_constant__ ConvKernelParams p) {
     for (int tile = q_first; tile < n_items; tile += q_stride, ++it) {
       const int sub = tile_sub(p, tile);
       const int kbeg = p.sub_kbeg[sub], kend = p.sub_kend[sub];
-      const int ksplit = kbeg + min((kend - kbeg) >> 1, p.gamma_pos);
+      const int ksplit = kbeg + ((kend - kbeg) >> 1);
       const uint32_t d_tmem = tmem_base + (it & 1) * BLOCK_N;
       if (it >= 2) {  // phase 2 of tile it-2 has finished reading this accumulator
         wait_bar(accfree_bar(it & 1), ((it >> 1) - 1) & 1, true);
@@ -2351,7 +2350,6 @@ int setup_params(const stemb200_conv_desc* d, const Plan& pl, const void* const*
     if (int rc = encode_weight(&kp.b_half_map, packed_weight, K, d->c_out, pl.block_n / 2)) return rc;
   }
   kp.kk_main = (pl.row_taps && d->kw * 8 <= 48) ? 3 : 4;
-  kp.gamma_pos = getenv("STEMB200_GAMMA_POS") ? atoi(getenv("STEMB200_GAMMA_POS")) : 1 << 20;
   kp.c_out = d->c_out;
   kp.slope = d->lrelu_slope;
   kp.sq_scale = d->sq_scale;
