@@ -609,7 +609,7 @@ struct GdnCfgT {
   static constexpr int kStageBytes = kAStageBytes + kBSlotBytes;
   // kLast: the resident W6 operand (all of it, or this CTA's half in duo mode) shares the budget.
   // kTm (operands in tensor memory): no x^2 / staging buffers in shared memory, their room goes to a fourth stage.
-  static constexpr int kStages = kSmallSlots ? (kLast ? 5 : 6) : ((kLast && !kTm) ? 3 : 4);
+  static constexpr int kStages = kSmallSlots ? ((kLast && !kTm) ? 5 : 6) : ((kLast && !kTm) ? 3 : 4);
   static constexpr int kA2Bytes = kTm ? 0 : (kN / 64) * kAStageBytes;  // x^2 operand (64-channel chunks) / staging
   static constexpr int kW6Bytes = kLast ? (kN / 64) * kLastN * 128 : 0;
   static constexpr int kW6SlotBytes = kSmallSlots ? kW6Bytes / 2 : kW6Bytes;
@@ -619,7 +619,7 @@ struct GdnCfgT {
   static constexpr uint32_t kStashCol = 2 * kN;  // x s stash; kTm: the packed fp16 operand ((x s)^2, then the output)
   static_assert(kN % 64 == 0 && 2 * kN + kN / 2 <= 512, "TMEM budget");
   static_assert(!kLast || kN / 2 >= kLastN, "the last-layer accumulator reuses the stash columns");
-  static_assert(!kTm || (kLast && !kDuo), "tensor-memory operands: fused last layer, one CTA per MMA");
+  static_assert(!kTm || kLast, "tensor-memory operands: fused last layer");
   static_assert(2 * kStages + 9 <= 32, "barrier slots");
   static_assert(kSmemBytes <= kSmemLimit, "smem overflow");
 };
@@ -811,6 +811,10 @@ conv_gdn_kernel(const __grid_constant__ ConvKernelParams p) {
       if (duo) mma_f16_ss2(d, ad, bd, id, acc);
       else mma_f16_ss(d, ad, bd, id, acc);
     };
+    auto mma_ts = [&](uint32_t d, uint32_t a_tmem, uint64_t bd, uint32_t id, uint32_t acc) {  // A from tensor memory
+      if (duo) mma_f16_ts2(d, a_tmem, bd, id, acc);
+      else mma_f16_ts(d, a_tmem, bd, id, acc);
+    };
     auto release_slot = [&](uint32_t bar) {
       if (duo) mma_commit2_mc(bar, 3);
       else if (pair) mma_commit_mc(bar, 3);
@@ -845,8 +849,8 @@ conv_gdn_kernel(const __grid_constant__ ConvKernelParams p) {
 #pragma unroll
             for (int kk = 0; kk < 4; ++kk) {
               if constexpr (kTm)  // A = the tile's output in tensor memory, D = the (dead) accumulator of that tile
-                mma_f16_ts(tmem_base + (n3_done & 1) * BLOCK_N, tmem_base + Cfg::kStashCol + 32u * kc + 8u * kk,
-                           bdesc + 2u * kk, idesc3, (kc > 0 || kk > 0) ? 1u : 0u);
+                mma_ts(tmem_base + (n3_done & 1) * BLOCK_N, tmem_base + Cfg::kStashCol + 32u * kc + 8u * kk,
+                       bdesc + 2u * kk, idesc3, (kc > 0 || kk > 0) ? 1u : 0u);
               else
                 mma(tmem_base + Cfg::kStashCol, adesc + 2u * kk, bdesc + 2u * kk, idesc3, (kc > 0 || kk > 0) ? 1u : 0u);
             }
@@ -898,8 +902,8 @@ conv_gdn_kernel(const __grid_constant__ ConvKernelParams p) {
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk) {
             if constexpr (kTm)  // A = (x s)^2 in tensor memory
-              mma_f16_ts(d_tmem, tmem_base + Cfg::kStashCol + 32u * kc + 8u * kk, bdesc + 2u * kk, idesc,
-                         (kc > 0 || kk > 0) ? 1u : 0u);
+              mma_ts(d_tmem, tmem_base + Cfg::kStashCol + 32u * kc + 8u * kk, bdesc + 2u * kk, idesc,
+                     (kc > 0 || kk > 0) ? 1u : 0u);
             else
               mma(d_tmem, adesc + 2u * kk, bdesc + 2u * kk, idesc, (kc > 0 || kk > 0) ? 1u : 0u);
           }
@@ -2537,12 +2541,13 @@ int gdn_forward(const stemb200_conv_desc* d, const void* const* in, const void* 
     if (int rc = encode_weight(&kp.w6_map, packed_w6, d->c_out, kLastN, kLastN)) return rc;
     kp.col_out = static_cast<__half*>(col_out);
     kp.store_act = out ? 1 : 0;
-    if (kp.duo) return launch_gdn<192, true, true, true>(kp, grid, st);
     // the layer's own activation is normally not stored: (x s)^2 and the output then live in tensor memory as MMA
-    // operands and the shared memory of their buffers is a fourth ring stage (STEMB200_LAST_TMEM=0: the round-1 kernel)
+    // operands, the epilogue needs no shared-memory buffer / named barrier / proxy fence, and the room goes to the ring
+    // (STEMB200_LAST_TMEM=0: the kernel with shared-memory operands)
     static const bool tm_off = [] { const char* e = getenv("STEMB200_LAST_TMEM"); return e && e[0] == '0'; }();
-    if (!out && !tm_off) return launch_gdn<192, true, true, false, true>(kp, grid, st);
-    return launch_gdn<192, true, true>(kp, grid, st);
+    const bool tm = !out && !tm_off;
+    if (kp.duo) return tm ? launch_gdn<192, true, true, true, true>(kp, grid, st) : launch_gdn<192, true, true, true>(kp, grid, st);
+    return tm ? launch_gdn<192, true, true, false, true>(kp, grid, st) : launch_gdn<192, true, true>(kp, grid, st);
   }
   if (use_pp)
     return d->c_out == 192 ? launch_gdn_pp<192, false>(kp, grid, st) : launch_gdn_pp<128, false>(kp, grid, st);
