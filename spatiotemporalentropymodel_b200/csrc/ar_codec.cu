@@ -34,6 +34,7 @@ constexpr int kArWarps = kArThreads / 32;
 constexpr int kArTaps = 12;  // mask 'A' of a 5x5 kernel: rows 0-1 complete, row 2 columns 0-1 (layers.py:39-42)
 constexpr uint64_t kRansL = 1ull << 31;
 constexpr int kArMaxCdfs = 64;
+constexpr int kArLutN = 128;  // buckets of the decoder's symbol lookup (cum >> 9)
 constexpr int kArMaxScales = 256;
 
 struct ArParams {
@@ -202,6 +203,22 @@ __device__ __forceinline__ float cta_row(float (*lp)[kArWarps][32], int r, int l
   return lane_tree(b);
 }
 
+// shared-memory accesses on explicit 32-bit addresses (the decoder's symbol loop: no address arithmetic per access)
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ uint32_t lds_u16(uint32_t a) {
+  uint16_t v;
+  asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ int4 lds_v4(uint32_t a) {
+  int4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ void sts_b32(uint32_t a, int v) {
+  asm volatile("st.shared.b32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
+}
+
 struct Pix {
   int b, hh, ww;
   long long g;  // flat position index (b*h + hh)*w + ww
@@ -213,10 +230,10 @@ __global__ void __launch_bounds__(kArThreads, 1) ar_codec_kernel(const ArParams 
   __shared__ float s_lp[kArMaxRows][kArWarps][32];  // decode: per-lane segment sums of the rows of one position
   __shared__ float s_res[kArWarps][16];             // encode: row values of the warp's position
   __shared__ int s_sym[320];                 // decode: symbols of one position
-  __shared__ int s_idx[320];                 //         their CDF indexes
-  // decode: first level of the 32-ary CDF search for every table row (probe positions depend on the row only) and
-  // per-row {offset into the compact table, size, symbol offset, level-1 step}
-  __shared__ int s_l1[kArMaxCdfs][32];
+  __shared__ int4 s_desc[320];               //         per channel {row address, lookup address, n, symbol offset}
+  // decode: per table row a 128-bucket lookup (symbol that contains cum = b << 9; entry 128 = the last symbol) and
+  // {offset into the compact table, size, symbol offset, -}
+  __shared__ uint16_t s_lut[kArMaxCdfs][kArLutN + 2];
   __shared__ int4 s_meta[kArMaxCdfs];
   __shared__ float s_table[kArMaxScales];
 
@@ -259,24 +276,36 @@ __global__ void __launch_bounds__(kArThreads, 1) ar_codec_kernel(const ArParams 
       for (int i = tid; i < mt.y; i += kArThreads) cdf16[mt.x + i] = static_cast<uint16_t>(__ldg(row + i));
     }
     __syncthreads();
-    for (int i = tid; i < p.n_cdfs * 32; i += kArThreads) {
-      const int row = i >> 5, ln = i & 31;
+    for (int i = tid; i < p.n_cdfs * (kArLutN + 1); i += kArThreads) {
+      const int row = i / (kArLutN + 1), b = i - row * (kArLutN + 1);
       const int4 mt = s_meta[row];
-      const int n = mt.y - 1;
-      s_l1[row][ln] = (n >= 1 && ln * mt.w < n) ? static_cast<int>(cdf16[mt.x + ln * mt.w]) : 0x7fffffff;
+      const int n = mt.y - 1;  // symbols s in [0, n): row[s] <= cum < row[s + 1], row[n] = 65536 (stored as 0)
+      int lo = 0;
+      if (b == kArLutN) {
+        lo = n > 0 ? n - 1 : 0;
+      } else {
+        const uint32_t target = static_cast<uint32_t>(b) << 9;
+        int hi = n > 0 ? n - 1 : 0;  // largest s in [0, n) with row[s] <= target (row[0] = 0)
+        while (lo < hi) {
+          const int mid = (lo + hi + 1) >> 1;
+          if (static_cast<uint32_t>(cdf16[mt.x + mid]) <= target) lo = mid;
+          else hi = mid - 1;
+        }
+      }
+      s_lut[row][b] = static_cast<uint16_t>(lo);
     }
     __syncthreads();
   }
   // rANS decoder state of image j (warp 0 of CTA j < batch), identical in every lane; the stream is read 32 words at
   // a time (lane l holds word wbase + l)
   uint64_t rx = 0;
-  long long rpos = 0, rwords = 0, wbase = 0;
+  int rpos = 0, rwords = 0, wbase = 0;  // in 32-bit words (a stream is < 8 GiB)
   uint32_t wbuf = 0;
   const uint32_t* rstream = nullptr;
   bool rbad = false;
   if (p.mode == 1 && j < p.batch && warp == 0) {
     rstream = reinterpret_cast<const uint32_t*>(p.streams + p.stream_off[j]);
-    rwords = p.stream_len[j] / 4;
+    rwords = static_cast<int>(p.stream_len[j] / 4);
     wbuf = lane < rwords ? __ldg(rstream + lane) : 0u;
     if (rwords >= 2) {
       rx = static_cast<uint64_t>(__shfl_sync(0xffffffffu, wbuf, 0)) |
@@ -291,7 +320,7 @@ __global__ void __launch_bounds__(kArThreads, 1) ar_codec_kernel(const ArParams 
       wbase += 32;
       wbuf = (wbase + lane) < rwords ? __ldg(rstream + wbase + lane) : 0u;
     }
-    const uint32_t wv = __shfl_sync(0xffffffffu, wbuf, static_cast<int>(rpos - wbase));
+    const uint32_t wv = __shfl_sync(0xffffffffu, wbuf, rpos - wbase);
     ++rpos;
     return wv;
   };
@@ -573,83 +602,77 @@ __global__ void __launch_bounds__(kArThreads, 1) ar_codec_kernel(const ArParams 
       if (j < p.batch && warp == 0) {
         const Pix q = pix(j);
         const long long e0i = q.g * C;
+        // per channel (state-independent, so all lanes prepare it up front): shared-memory byte addresses of the CDF
+        // row and of its bucket lookup, the symbol count and the symbol offset
+        const uint32_t cdf_sa = smem_addr(cdf16), lut_sa = smem_addr(&s_lut[0][0]);
+        const uint32_t desc_sa = smem_addr(s_desc), sym_sa = smem_addr(s_sym);
         for (int ch = lane; ch < C; ch += 32) {
-          const int ci = __ldcg(p.idx + e0i + ch);
-          s_idx[ch] = ci < 0 ? 0 : (ci >= p.n_cdfs ? p.n_cdfs - 1 : ci);
+          int ci = __ldcg(p.idx + e0i + ch);
+          ci = ci < 0 ? 0 : (ci >= p.n_cdfs ? p.n_cdfs - 1 : ci);
+          const int4 mt = s_meta[ci];
+          s_desc[ch] = make_int4(static_cast<int>(cdf_sa + 2u * mt.x), static_cast<int>(lut_sa + 2u * (kArLutN + 2) * ci),
+                                 mt.y - 1, mt.z);
         }
         __syncwarp();
-        // One symbol = one trip through a dependent chain, so the chain is what is optimised (it was ~640 cycles per
-        // symbol, 77 % of the decode time):
-        //   cum -> ballot over the 32 level-1 probes (registers) -> k -> one shared-memory round for the <= 32 entries
-        //   of chunk k -> ballot / popc -> start and next boundary by SHUFFLE from the values the lanes already hold
-        //   (the boundary after a full chunk is level-1 probe k + 1) -> 64-bit state update -> renormalisation with a
-        //   stream word that was shuffled out speculatively at the top of the iteration.
-        // Row data of the next symbol is fetched while the current one is resolved (it does not depend on the state).
-        int ci = s_idx[0];
-        int4 mt = s_meta[ci];
-        uint32_t l1v = static_cast<uint32_t>(s_l1[ci][lane]);
-        int widx = static_cast<int>(rpos - wbase);  // position of the next stream word inside the 32-word window
+        // One symbol = one trip through a dependent chain of the rANS state, and ONE warp walks it, so both the length
+        // of the chain and the number of instructions around it count (a single warp issues a dependent instruction
+        // every ~5 cycles).  Every lane runs the same scalar sequence on explicit 32-bit shared addresses:
+        //   cum -> bucket cum >> 9 -> two lookup entries (first / last symbol that can contain cum) -> the two CDF
+        //   boundaries of the first candidate (almost always the symbol; a short scan or a bisection otherwise) ->
+        //   64-bit state update -> renormalisation with a stream word that was shuffled out speculatively at the top
+        //   of the iteration.  The descriptor of the next channel is fetched while the current one is resolved.
+        // History (1080p latent, decompress): warp-parallel 32-ary search with ballots / shuffles on the chain 0.66 ->
+        // 0.61 s; bucket lookup alone 0.62 s (the ~100 instructions around it, half of them address arithmetic, were the
+        // cost); with per-channel descriptors and explicit shared addresses 0.58 s (0.50 s at 4.8 bits per symbol).  ncu
+        // on the benchmark's synthetic latent: 42 % of the symbols need the scan behind the first candidate (128
+        // buckets are coarse for its sigma ~ 30 rows; there is no shared memory left for more) and 18 % take the
+        // bypass path, which a trained checkpoint uses for < 0.1 %.
+        int4 dc = lds_v4(desc_sa);
+        int widx = rpos - wbase;  // position of the next stream word inside the 32-word window
         for (int ch = 0; ch < C; ++ch) {
-          const int ci_n = s_idx[ch + 1 < C ? ch + 1 : ch];
-          const int4 mt_n = s_meta[ci_n];
-          const uint32_t l1_n = static_cast<uint32_t>(s_l1[ci_n][lane]);
+          const int4 dn = lds_v4(desc_sa + 16u * static_cast<uint32_t>(ch + 1 < C ? ch + 1 : ch));
           if (widx >= 32) {  // every 32 words: refill the window
             wbase += 32;
             widx -= 32;
             wbuf = (wbase + lane) < rwords ? __ldg(rstream + wbase + lane) : 0u;
           }
-          const uint32_t w_spec = __shfl_sync(0xffffffffu, wbuf, widx & 31);  // used only if this symbol renormalises
-          const uint16_t* row = cdf16 + mt.x;
-          const int size = mt.y, n = size - 1, step = mt.w;  // candidates s in [0, n): row[s] <= cum < row[s+1]
-          const uint32_t cum = static_cast<uint32_t>(rx & 0xFFFFu);
-          const unsigned int m1 = __ballot_sync(0xffffffffu, l1v <= cum);
-          const int k = m1 ? 31 - __clz(m1) : 0;
-          int s_found;
-          uint32_t start, nxt;
-          if (step <= 1) {
-            // rows of <= 32 candidates: the probes are the row
-            s_found = k;
-            start = __shfl_sync(0xffffffffu, l1v, k);
-            nxt = __shfl_sync(0xffffffffu, l1v, (k + 1) & 31);
-            if (k + 1 >= n) nxt = 65536u;
-          } else if (step <= 32) {
-            const int slo = k * step;
-            const int rem = (n - slo) < step ? (n - slo) : step;  // 1 <= rem <= 32
-            const uint32_t v = lane < rem ? static_cast<uint32_t>(row[slo + lane]) : 0xFFFFFFFFu;
-            const int cnt = __popc(__ballot_sync(0xffffffffu, v <= cum));  // >= 1: row[slo] is probe k
-            const int c1 = cnt > 0 ? cnt - 1 : 0;
-            s_found = slo + c1;
-            start = __shfl_sync(0xffffffffu, v, c1);
-            const uint32_t in_chunk = __shfl_sync(0xffffffffu, v, (c1 + 1) & 31);
-            const uint32_t next_probe = __shfl_sync(0xffffffffu, l1v, (k + 1) & 31);
-            nxt = (c1 + 1 < rem) ? in_chunk : next_probe;
-            if (s_found + 1 >= n) nxt = 65536u;
-          } else {
-            // rows of more than 1024 candidates (sigma > ~84): several rounds per chunk
-            const int slo = k * step;
-            const int rem = (n - slo) < step ? (n - slo) : step;
-            int cnt = 0;
-            for (int o0 = 0; o0 < rem; o0 += 32) {
-              const int o = o0 + lane;
-              cnt += __popc(__ballot_sync(0xffffffffu, o < rem && static_cast<uint32_t>(row[slo + o]) <= cum));
+          const uint32_t w_spec = __shfl_sync(0xffffffffu, wbuf, widx);  // used only if this symbol renormalises
+          const uint32_t row_sa = static_cast<uint32_t>(dc.x);
+          const int n = dc.z;  // candidates s in [0, n): row[s] <= cum < row[s+1], row[n] = 65536 stored as 0
+          const uint32_t cum = static_cast<uint32_t>(rx) & 0xFFFFu;
+          const uint32_t la = static_cast<uint32_t>(dc.y) + ((cum >> 9) << 1);
+          int s_found = static_cast<int>(lds_u16(la));
+          const int s_last = static_cast<int>(lds_u16(la + 2));
+          uint32_t start = lds_u16(row_sa + 2u * s_found);
+          uint32_t nxt = lds_u16(row_sa + 2u * s_found + 2u);
+          nxt = nxt ? nxt : 65536u;  // only row[n] wraps to 0 (row[0] = 0 is never a "next" boundary)
+          if (cum >= nxt) {
+            if (s_last - s_found > 6) {  // a tail bucket with many narrow symbols: bisection
+              int lo = s_found + 1, hi = s_last;
+              while (lo < hi) {
+                const int mid = (lo + hi + 1) >> 1;
+                if (lds_u16(row_sa + 2u * mid) <= cum) lo = mid;
+                else hi = mid - 1;
+              }
+              s_found = lo;
+            } else {
+              do {
+                ++s_found;
+              } while (s_found < s_last && lds_u16(row_sa + 2u * s_found + 2u) <= cum);
             }
-            s_found = slo + (cnt > 0 ? cnt - 1 : 0);
-            start = row[s_found];
-            nxt = (s_found + 1 >= n) ? 65536u : static_cast<uint32_t>(row[s_found + 1]);
+            start = lds_u16(row_sa + 2u * s_found);
+            nxt = lds_u16(row_sa + 2u * s_found + 2u);
+            nxt = (nxt && s_found + 1 < n) ? nxt : 65536u;
           }
-          if (n < 1) {  // an empty row cannot be decoded
-            start = 0u;
-            nxt = 0u;
-          }
-          const uint32_t freq = nxt - start;
-          rbad = rbad || freq == 0u || freq > 65536u || cum < start || cum >= nxt;
-          rx = static_cast<uint64_t>(freq) * (rx >> 16) + cum - start;
+          const uint32_t freq = nxt - start, off = cum - start;
+          rbad = rbad || n < 1 || off >= freq;  // (freq == 0 and cum outside [start, nxt) both show up as off >= freq)
+          rx = static_cast<uint64_t>(freq) * (rx >> 16) + off;
           if (rx < kRansL && (wbase + widx) < rwords) {
             rx = (rx << 32) | w_spec;
             ++widx;
           }
           int value = s_found;
-          if (s_found == size - 2) {
+          if (s_found == n - 1) {
             // bypass (rare): nibble count (unary in chunks of 15), then the nibbles, least significant first
             rpos = wbase + widx;
             auto get4 = [&]() -> int {
@@ -671,14 +694,12 @@ __global__ void __launch_bounds__(kArThreads, 1) ar_codec_kernel(const ArParams 
             }
             value = static_cast<int>(raw >> 1);
             if (raw & 1u) value = -value - 1;
-            else value += size - 2;
-            widx = static_cast<int>(rpos - wbase);
+            else value += n - 1;
+            widx = rpos - wbase;
           }
-          value = rbad ? 0 : value + mt.z;
-          if (lane == 0) s_sym[ch] = value;
-          ci = ci_n;
-          mt = mt_n;
-          l1v = l1_n;
+          value = rbad ? 0 : value + dc.w;
+          if (lane == 0) sts_b32(sym_sa + 4u * static_cast<uint32_t>(ch), value);
+          dc = dn;
         }
         rpos = wbase + widx;
         __syncwarp();
@@ -756,8 +777,16 @@ Scratch carve(const stemb200_ar_desc* d, void* ws) {
 int launch_ar(ArParams& p, cudaStream_t st) {
   const size_t smem = (static_cast<size_t>((p.block_floats + 3) & ~3) + static_cast<size_t>(p.nstage) * p.kmax) * 4 +
                       static_cast<size_t>(p.cdf16_entries + 8) * 2;
-  if (smem > 227 * 1024) return set_error("ar: weights + staging exceed shared memory");
-  if (smem > 215 * 1024) return set_error("ar: weights + staging + CDF table exceed shared memory");
+  static size_t static_smem = [] {
+    cudaFuncAttributes a;
+    return cudaFuncGetAttributes(&a, ar_codec_kernel) == cudaSuccess ? a.sharedSizeBytes : size_t(40 * 1024);
+  }();
+  if (smem + static_smem > 227 * 1024) {
+    char buf[160];
+    snprintf(buf, sizeof(buf), "ar: weights + staging + CDF table need %zu + %zu bytes of shared memory (limit 232448)",
+             smem, static_smem);
+    return set_error(buf);
+  }
   static size_t configured = 0;
   if (configured < smem) {
     cudaError_t e = cudaFuncSetAttribute(ar_codec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
